@@ -1,0 +1,529 @@
+"""CPU fp32 restatement of the DESTR transformer-half hot path  --  TEST INFRASTRUCTURE ONLY.
+
+This module is the *oracle*: an independent, plain-torch (CPU, fp32, autograd-capable)
+restatement of the reference algorithm for every row of SURVEY.md section 8(a).  It is NOT
+part of the product.  Only `tests/`, `__graft_entry__.smoke()` and the `cpu_baseline` /
+`--impl reference` legs of `bench.py` may import it; the product package
+`object_detection_destr_b200` never does and fails loudly if its CUDA library is missing.
+
+Parity status: the reference ships no tests/golden vectors for this path, so
+the oracle is pinned against OUTPUTS OF THE REFERENCE ITSELF, generated in the authoring
+container by `tests/golden/make_golden.py` (imports /root/reference) and committed under
+`tests/golden/*.pt`; plus the known-answer vectors extracted from the reference's `__main__`
+snippets.  `tests/test_oracle_golden.py` checks all of them.
+
+Every function cites the reference file:line it restates (paths relative to the reference
+root).  Dropout is the identity here (the reference's dropouts are neutralised when the golden
+vectors are generated: p=0 / eval), which is the deterministic semantics parity is defined on.
+
+Conventions: B batch, N = H*W encoder tokens, Q object queries, d = 256, h = 8 heads.
+Weights are passed as dicts keyed exactly like the reference modules' `state_dict()`.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+SD = Dict[str, Tensor]
+
+
+# --------------------------------------------------------------------------------------
+# small math: a11 / a12
+# --------------------------------------------------------------------------------------
+def inverse_sigmoid(x: Tensor, eps: float = 1e-6) -> Tensor:
+    """logit with a lower clip only (src/utils/misc.py:59-62): -log(1/max(x,eps) - 1)."""
+    return -torch.log(1.0 / x.clamp(min=eps) - 1.0)
+
+
+def _sine_table(d_half: int, device=None) -> Tensor:
+    # 10000 ** (2*floor(i/2)/d_half), i = 0..d_half-1  (positional_embedding.py:20-23,
+    # position_encoding_cdetr.py:51-52)
+    i = torch.arange(d_half, dtype=torch.float32, device=device)
+    return 10000.0 ** (2.0 * torch.div(i, 2, rounding_mode="floor") / d_half)
+
+
+def _sincos_interleave(angle: Tensor) -> Tensor:
+    # even channels -> sin, odd channels -> cos of the *same-index* angle
+    # (positional_embedding.py:31-36): stack(sin(a[0::2]), cos(a[1::2])).flatten == this select.
+    idx = torch.arange(angle.shape[-1], device=angle.device)
+    return torch.where(idx % 2 == 0, angle.sin(), angle.cos())
+
+
+def query_sine_embed(pos_xy: Tensor, d_model: int = 256) -> Tensor:
+    """gen_sineembed_for_position (src/utils/positional_embedding.py:6-39).
+
+    pos_xy (..., 2) = (x, y) in [0,1]  ->  (..., d_model); channels [0,d/2) encode y and
+    [d/2,d) encode x (the reference concatenates pos_y first, :37)."""
+    t = _sine_table(d_model // 2, pos_xy.device)
+    ax = (pos_xy[..., 0:1] * (2 * math.pi)) / t
+    ay = (pos_xy[..., 1:2] * (2 * math.pi)) / t
+    return torch.cat([_sincos_interleave(ay), _sincos_interleave(ax)], dim=-1)
+
+
+def sine_pos2d(mask: Tensor, num_pos_feats: int = 128) -> Tensor:
+    """PositionEmbeddingSine(normalize=True) (src/utils/position_encoding_cdetr.py:39-63,
+    built by build_position_encoding_fix :144-150).  mask (B,H,W) bool, True = padded.
+    Returns (B, 2*num_pos_feats, H, W) fp32: first half from the row (y) cumsum, second from x."""
+    valid = (~mask).to(torch.float32)
+    y = valid.cumsum(1)
+    x = valid.cumsum(2)
+    y = y / (y[:, -1:, :] + 1e-6) * (2 * math.pi)
+    x = x / (x[:, :, -1:] + 1e-6) * (2 * math.pi)
+    t = _sine_table(num_pos_feats, mask.device)
+    py = _sincos_interleave(y[..., None] / t)
+    px = _sincos_interleave(x[..., None] / t)
+    return torch.cat([py, px], dim=-1).permute(0, 3, 1, 2)
+
+
+def cxcyhw_to_xyxy(b: Tensor) -> Tensor:
+    """from_cxcyhw_to_xyxy (src/utils/bbox_utils.py:33-63).  NOTE the box order is
+    (cx, cy, h, w): x uses component 3 (w), y uses component 2 (h).  mins clipped >=0, maxs <=1."""
+    if b.shape[0] == 0:
+        return b
+    cx, cy, hh, ww = b.unbind(-1)
+    return torch.stack(
+        [(cx - ww / 2).clamp(min=0), (cy - hh / 2).clamp(min=0),
+         (cx + ww / 2).clamp(max=1), (cy + hh / 2).clamp(max=1)], dim=-1)
+
+
+def xyxy_to_cxcyhw(b: Tensor) -> Tensor:
+    """from_xyxy_to_cxcyhw (src/utils/bbox_utils.py:66-103): everything clipped to [0,1]."""
+    if b.shape[0] == 0:
+        return b
+    x0, y0, x1, y1 = b.unbind(-1)
+    return torch.stack(
+        [((x0 + x1) / 2).clamp(0, 1), ((y0 + y1) / 2).clamp(0, 1),
+         (y1 - y0).clamp(0, 1), (x1 - x0).clamp(0, 1)], dim=-1)
+
+
+def pairwise_iou(a: Tensor, b: Tensor, eps: float = 1e-6) -> Tensor:
+    """get_iou (src/utils/bbox_utils.py:201-216): (M,4),(T,4) xyxy -> (M,T)."""
+    lo = torch.maximum(a[:, None, :2], b[None, :, :2])
+    hi = torch.minimum(a[:, None, 2:], b[None, :, 2:])
+    wh = (hi - lo).clamp(min=0)
+    inter = wh[..., 0] * wh[..., 1]
+    area_a = (a[:, 2] - a[:, 0]) * (a[:, 3] - a[:, 1])
+    area_b = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+    union = area_a[:, None] + area_b[None, :] - inter
+    return inter / union.clamp(min=eps)
+
+
+def complete_iou_cost(pred_xyxy: Tensor, gt_xyxy: Tensor, eps: float = 1e-6) -> Tensor:
+    """complete_iou (src/utils/bbox_utils.py:160-198): returns 1 - clamp(CIoU,-1,1), (M,T).
+    This is Complete-IoU (centre-distance + aspect term), not Generalized IoU.  alpha carries
+    no gradient in the reference (:191-193)."""
+    p = xyxy_to_cxcyhw(pred_xyxy)
+    g = xyxy_to_cxcyhw(gt_xyxy)
+    iou = pairwise_iou(pred_xyxy, gt_xyxy)
+    hull = (torch.maximum(pred_xyxy[:, None, 2:], gt_xyxy[None, :, 2:])
+            - torch.minimum(pred_xyxy[:, None, :2], gt_xyxy[None, :, :2])).clamp(min=0)
+    c2 = (hull * hull).sum(-1)
+    dc = (p[:, None, :2] - g[None, :, :2]).abs()
+    rho2 = (dc * dc).sum(-1)
+    at_g = torch.atan(g[:, 3] / g[:, 2].clamp(min=eps))
+    at_p = torch.atan(p[:, 3] / p[:, 2].clamp(min=eps))
+    v = (4.0 / (math.pi ** 2)) * (at_g[None, :] - at_p[:, None]) ** 2
+    with torch.no_grad():
+        alpha = (iou > 0.5).to(iou.dtype) * (v / (1 - iou + v))
+    ciou = (iou - rho2 / c2.clamp(min=eps) - alpha * v).clamp(-1.0, 1.0)
+    return 1 - ciou
+
+
+# --------------------------------------------------------------------------------------
+# a10: pairing,  a7: scaled dot-product attention,  a9: pair self-attention
+# --------------------------------------------------------------------------------------
+def get_pairs(coords_cxcyhw: Tensor, eps: float = 1e-6) -> Tensor:
+    """_get_pairs (src/model/attention/pair_self_attention.py:110-171).
+
+    coords (B,Q,4) cxcyhw -> (B,Q,2) int64.  partner = first argmax over j of
+    inter(i,j)/(area_i+area_j-inter+eps) - [i==j] with an UNCLAMPED intersection (:124-126);
+    the pair is ordered so the box with the larger |x1-x0|+|y1-y0| comes first, ties keep
+    (i, partner) (:152-169)."""
+    B, Q, _ = coords_cxcyhw.shape
+    box = cxcyhw_to_xyxy(coords_cxcyhw)
+    lo = torch.maximum(box[:, :, None, :2], box[:, None, :, :2])
+    hi = torch.minimum(box[:, :, None, 2:], box[:, None, :, 2:])
+    wh = hi - lo
+    inter = wh[..., 0] * wh[..., 1]
+    area = (box[..., 2] - box[..., 0]) * (box[..., 3] - box[..., 1])
+    union = area[:, :, None] + area[:, None, :] - inter
+    score = inter / (union + eps) - torch.eye(Q, device=box.device)
+    partner = score.argmax(-1)
+    me = torch.arange(Q, device=box.device).expand(B, Q)
+    size = (box[..., 2] - box[..., 0]).abs() + (box[..., 3] - box[..., 1]).abs()
+    keep = size >= size.gather(1, partner)
+    first = torch.where(keep, me, partner)
+    second = torch.where(keep, partner, me)
+    return torch.stack([first, second], dim=-1)
+
+
+def sdp_attention(q: Tensor, k: Tensor, v: Tensor, attn_mask: Optional[Tensor] = None,
+                  key_padding_mask: Optional[Tensor] = None) -> Tensor:
+    """SelfAttention.forward (src/model/attention/self_attention.py:18-47), dropout = identity.
+
+    q (B,h,Sq,dq), k (B,h,Sk,dq), v (B,h,Sk,dv) -> (B,Sq,h*dv).  The scale is 1/sqrt of the
+    LAST DIM OF q AS PASSED (:26)."""
+    s = torch.einsum("bhqd,bhkd->bhqk", q, k) / math.sqrt(q.shape[-1])
+    if attn_mask is not None:
+        s = s.masked_fill(attn_mask, float("-inf")) if attn_mask.dtype == torch.bool else s + attn_mask
+    if key_padding_mask is not None:
+        s = s.masked_fill(key_padding_mask.bool()[:, None, None, :], float("-inf"))
+    p = s.softmax(-1)
+    o = torch.einsum("bhqk,bhkd->bqhd", p, v)
+    return o.reshape(o.shape[0], o.shape[1], -1)
+
+
+def pair_self_attention(q: Tensor, k: Tensor, v: Tensor, coords_cxcyhw: Tensor,
+                        pairs: Optional[Tensor] = None) -> Tensor:
+    """PairSelfAttention.forward (src/model/attention/pair_self_attention.py:19-107).
+
+    q,k,v (B,h,Q,dh) -> (B,Q,h*dh).  A2[i,j] = <q[L_i],k[L_j]> + <q[R_i],k[R_j]> with
+    (L_i,R_i)=pairs[i]; P = softmax(A2)/sqrt(2*dh) (softmax FIRST, then the division, :98);
+    O = P.[v[L]|v[R]] (B,h,Q,2dh) laid out head-major (B,Q,h*2dh) and then reshaped to
+    (B,Q,2,h*dh) (:101-105) -- which splits it into heads [0,h/2) vs heads [h/2,h), NOT into
+    left vs right.  Slot s is kept iff pairs[b,i,s]==i; kept slots are summed."""
+    B, H, Q, dh = q.shape
+    if pairs is None:
+        pairs = get_pairs(coords_cxcyhw)
+
+    def take(t: Tensor, col: int) -> Tensor:
+        idx = pairs[:, None, :, col, None].expand(B, H, Q, dh)
+        return t.gather(2, idx)
+
+    ql, qr, kl, kr, vl, vr = take(q, 0), take(q, 1), take(k, 0), take(k, 1), take(v, 0), take(v, 1)
+    a2 = torch.einsum("bhqd,bhkd->bhqk", ql, kl) + torch.einsum("bhqd,bhkd->bhqk", qr, kr)
+    p = a2.softmax(-1) / math.sqrt(2 * dh)
+    o = torch.einsum("bhqk,bhkd->bqhd", p, torch.cat([vl, vr], dim=-1))  # (B,Q,H,2dh)
+    o = o.reshape(B, Q, 2, H * dh)
+    me = torch.arange(Q, device=q.device)[None, :, None]
+    keep = (pairs == me).to(o.dtype)  # (B,Q,2)
+    return (o * keep[..., None]).sum(2)
+
+
+# --------------------------------------------------------------------------------------
+# a2-a4: encoder
+# --------------------------------------------------------------------------------------
+def _mlp2(x: Tensor, sd: SD, prefix: str) -> Tensor:
+    h = F.relu(F.linear(x, sd[prefix + "0.weight"], sd[prefix + "0.bias"]))
+    return F.linear(h, sd[prefix + "2.weight"], sd[prefix + "2.bias"])
+
+
+def _ln(x: Tensor, sd: SD, prefix: str) -> Tensor:
+    return F.layer_norm(x, (x.shape[-1],), sd[prefix + "weight"], sd[prefix + "bias"], 1e-5)
+
+
+def encoder_mha(x_qk: Tensor, x_v: Tensor, kpm: Optional[Tensor], sd: SD, prefix: str,
+                heads: int = 8) -> Tensor:
+    """nn.MultiheadAttention(256, 8) as called at src/model/blocks/encoder_block.py:97-103
+    (torch F.multi_head_attention_forward: packed in-proj, q scaled by 1/sqrt(d_head) before
+    QK^T, bool key-padding mask -> -inf, softmax, PV, out-proj).  Batch-first (B,N,d) here."""
+    W, bvec = sd[prefix + "in_proj_weight"], sd[prefix + "in_proj_bias"]
+    d = x_qk.shape[-1]
+    q = F.linear(x_qk, W[:d], bvec[:d])
+    k = F.linear(x_qk, W[d:2 * d], bvec[d:2 * d])
+    v = F.linear(x_v, W[2 * d:], bvec[2 * d:])
+    B, N, _ = q.shape
+    dh = d // heads
+    split = lambda t: t.reshape(B, N, heads, dh).transpose(1, 2)
+    o = sdp_attention(split(q), split(k), split(v), key_padding_mask=kpm)  # scale 1/sqrt(dh)
+    return F.linear(o, sd[prefix + "out_proj.weight"], sd[prefix + "out_proj.bias"])
+
+
+def encoder_block(x: Tensor, pos: Tensor, kpm: Optional[Tensor], sd: SD, prefix: str) -> Tensor:
+    """EncoderBlock.forward (src/model/blocks/encoder_block.py:88-112), batch-first."""
+    a = encoder_mha(x + pos, x, kpm, sd, prefix + "self_attn.")
+    x1 = _ln(x + a, sd, prefix + "norm1.")
+    f = F.linear(F.relu(F.linear(x1, sd[prefix + "fc1.weight"], sd[prefix + "fc1.bias"])),
+                 sd[prefix + "fc2.weight"], sd[prefix + "fc2.bias"])
+    return _ln(x1 + f, sd, prefix + "norm2.")
+
+
+def encoder_forward(x: Tensor, mask: Tensor, pos: Tensor, sd: SD, num_layers: int) -> Tensor:
+    """Encoder.forward (src/model/blocks/encoder_block.py:24-44).
+    x,pos (B,256,H,W), mask (B,H,W) bool -> (B,256,H,W).  `_pos_scale` and `norm` are shared
+    by all layers (:17-22)."""
+    B, C, H, W = x.shape
+    t = x.flatten(2).transpose(1, 2)
+    p = pos.flatten(2).transpose(1, 2)
+    kpm = mask.flatten(1)
+    for l in range(num_layers):
+        scale = _mlp2(t, sd, "_pos_scale.")
+        y = encoder_block(t, p * scale, kpm, sd, f"_encoder.{l}.")
+        t = _ln(t + y, sd, "norm.")
+    return t.transpose(1, 2).reshape(B, C, H, W)
+
+
+def fine_pos_tokens(enc_out: Tensor, pos: Tensor, enc_sd: SD) -> Tensor:
+    """fine_pos = pos * encoder._pos_scale(enc_out) (src/model/model.py:89-97), token-major
+    (B,N,256) as the decoder receives it (:114)."""
+    t = enc_out.flatten(2).transpose(1, 2)
+    return pos.flatten(2).transpose(1, 2) * _mlp2(t, enc_sd, "_pos_scale.")
+
+
+# --------------------------------------------------------------------------------------
+# a5, a6, a8: decoder
+# --------------------------------------------------------------------------------------
+def cls_reg_branch(inp: Tensor, q512: Tensor, k512: Tensor, v256: Tensor, kpm: Tensor,
+                   sd: SD, prefix: str) -> Tensor:
+    """ClsRegBranch.forward (src/model/blocks/decoder_block.py:238-260): single-head
+    cross-attention with scale 1/sqrt(512), post-LN residual, FFN 256->1024->256, post-LN."""
+    ca = sdp_attention(q512[:, None], k512[:, None], v256[:, None], key_padding_mask=kpm)
+    x = _ln(inp + ca, sd, prefix + "norm1.")
+    f = F.linear(F.relu(F.linear(x, sd[prefix + "fc1.weight"], sd[prefix + "fc1.bias"])),
+                 sd[prefix + "fc2.weight"], sd[prefix + "fc2.bias"])
+    return _ln(x + f, sd, prefix + "norm2.")
+
+
+def _interleave_heads(a: Tensor, b: Tensor, heads: int) -> Tensor:
+    # (.., 256),(.., 256) -> (.., 512) with per-head [a_h(32) | b_h(32)] blocks
+    # (decoder_block.py:195-210: split_heads -> concat last dim -> combine_heads)
+    sh = a.shape[:-1]
+    a = a.reshape(*sh, heads, -1)
+    b = b.reshape(*sh, heads, -1)
+    return torch.cat([a, b], dim=-1).reshape(*sh, -1)
+
+
+def decoder_block(x: Tensor, enc_out: Tensor, coords: Tensor, pos_embed: Tensor,
+                  sin_embed: Tensor, fine_pos: Tensor, kpm: Tensor, sd: SD, prefix: str,
+                  heads: int = 8, lam: float = 0.5, pairs: Optional[Tensor] = None) -> Tensor:
+    """DecoderBlock.forward (src/model/blocks/decoder_block.py:157-220).
+    x (B,Q,512), enc_out/fine_pos (B,N,256), coords (B,Q,4), pos_embed/sin_embed (B,Q,256)."""
+    B, Q, D = x.shape
+    w = lambda n: sd[prefix + n + ".weight"]
+    qp = F.linear(pos_embed, w("_sa_proj_to_q_pos"))
+    kp = F.linear(pos_embed, w("_sa_proj_to_k_pos"))
+    q = F.linear(x, w("_sa_proj_to_q_obj")) + torch.cat([qp, qp], -1)
+    k = F.linear(x, w("_sa_proj_to_k_obj")) + torch.cat([kp, kp], -1)
+    v = F.linear(x, w("_sa_proj_to_v_obj"))
+    split = lambda t: t.reshape(B, Q, heads, D // heads).transpose(1, 2)
+    q, k, v = split(q), split(k), split(v)
+    o1 = sdp_attention(q, k, v)
+    o2 = pair_self_attention(q, k, v, coords, pairs=pairs)
+    o = lam * _ln(x + o1, sd, prefix + "norm1.") + (1 - lam) * _ln(x + o2, sd, prefix + "norm2.")
+    o_cls, o_reg = o[..., :D // 2], o[..., D // 2:]
+
+    q_obj = F.linear(o, w("_ca_proj_to_q_obj"))
+    q_pos = F.linear(sin_embed, w("_ca_proj_to_q_pos"))
+    k_enc = F.linear(enc_out, w("_ca_proj_to_k_enc"))
+    k_pos = F.linear(fine_pos, w("_ca_proj_to_k_pos"))
+    v2 = F.linear(enc_out, w("_ca_proj_to_v_enc"))
+    q_cls = _interleave_heads(q_obj[..., :D // 2], q_pos, heads)
+    q_reg = _interleave_heads(q_obj[..., D // 2:], q_pos, heads)
+    kk = _interleave_heads(k_enc, k_pos, heads)
+    c = cls_reg_branch(o_cls, q_cls, kk, v2, kpm, sd, prefix + "_cls_branch.")
+    r = cls_reg_branch(o_reg, q_reg, kk, v2, kpm, sd, prefix + "_reg_branch.")
+    return torch.cat([c, r], dim=-1)
+
+
+def box_refine(x_reg: Tensor, centers_logit: Tensor, bbox_sd: SD, prefix: str = "") -> Tensor:
+    """sigmoid(bbox_embed(x_reg) + [logit(cx), logit(cy), 0, 0])
+    (decoder_block.py:51-54, model.py:127-129).  bbox_embed = Linear-ReLU-Linear(256->256->4)."""
+    t = _mlp2(x_reg, bbox_sd, prefix)
+    t = torch.cat([t[..., :2] + centers_logit, t[..., 2:]], dim=-1)
+    return t.sigmoid()
+
+
+def decoder_forward(x: Tensor, enc_out: Tensor, kpm: Tensor, fine_pos: Tensor,
+                    pos_embed: Tensor, centers: Tensor, dec_sd: SD, bbox_sd: SD,
+                    num_layers: int, pairs_per_layer: Optional[Sequence[Tensor]] = None,
+                    return_coords: bool = False):
+    """Decoder.forward (src/model/blocks/decoder_block.py:28-67).
+    x (B,Q,512); enc_out, fine_pos (B,N,256); kpm (B,N) bool; pos_embed (B,Q,256);
+    centers (B,Q,2) -> (B,Q,512).  `_pos_scale`, `norm` shared across layers (:21-26);
+    bbox_embed is the model head passed in (model.py:117)."""
+    half = x.shape[-1] // 2
+    c_logit = inverse_sigmoid(centers)
+    sine = query_sine_embed(centers, half)  # loop-invariant (:45-47)
+    coords_all = []
+    for l in range(num_layers):
+        x_reg = x[..., half:]
+        sin_embed = sine * _mlp2(x_reg, dec_sd, "_pos_scale.")
+        coords = box_refine(x_reg, c_logit, bbox_sd)
+        coords_all.append(coords)
+        pr = None if pairs_per_layer is None else pairs_per_layer[l]
+        y = decoder_block(x, enc_out, coords, pos_embed, sin_embed, fine_pos, kpm, dec_sd,
+                          f"_decoder.{l}.", pairs=pr)
+        x = _ln(x + y, dec_sd, "norm.")
+    return (x, coords_all) if return_coords else x
+
+
+def heads_forward(x: Tensor, centers: Tensor, cls_sd: SD, bbox_sd: SD) -> Dict[str, Tensor]:
+    """Output heads (src/model/model.py:120-131): pred_class = cls_embed(x[..., :256]),
+    pred_boxes = sigmoid(bbox_embed(x[..., 256:]) + [logit(centres), 0, 0])."""
+    half = x.shape[-1] // 2
+    return {
+        "pred_class": F.linear(x[..., :half], cls_sd["weight"], cls_sd["bias"]),
+        "pred_boxes": box_refine(x[..., half:], inverse_sigmoid(centers), bbox_sd),
+    }
+
+
+# --------------------------------------------------------------------------------------
+# a13: matcher,  a14: set criterion
+# --------------------------------------------------------------------------------------
+def match_cost_blocks(pred_class: Tensor, pred_boxes: Tensor, tgt_labels: List[Tensor],
+                      tgt_boxes: List[Tensor], w_class: float, w_bbox: float, w_ciou: float,
+                      with_l1: bool = True) -> List[Tensor]:
+    """Cost matrix of HungarianMatcher / HungarianMatcherWoL1 (src/utils/matcher.py:72-107,
+    158-184), restricted to the B diagonal blocks the assignment actually uses (:109-112).
+
+    pred_class (B,Q,C) logits, pred_boxes (B,Q,4) cxcyhw; tgt_labels[i] int64 (T_i,) class ids,
+    tgt_boxes[i] (T_i,4) xyxy.  Returns list of (Q,T_i) fp32.  The L1 term compares predicted
+    cxcyhw against target xyxy as-is (:96) -- reference behaviour, kept.  Evaluation order of
+    the weighted sum follows :102-106: (w_b*L1 + w_c*class) + w_i*ciou."""
+    out = []
+    for b in range(pred_class.shape[0]):
+        p = pred_class[b].sigmoid()
+        ids = tgt_labels[b]
+        neg = (1 - 0.25) * (p ** 2.0) * (-(1 - p + 1e-8).log())
+        pos = 0.25 * ((1 - p) ** 2.0) * (-(p + 1e-8).log())
+        c_cls = pos[:, ids] - neg[:, ids]
+        c_iou = complete_iou_cost(cxcyhw_to_xyxy(pred_boxes[b]), tgt_boxes[b])
+        if with_l1:
+            c_l1 = (pred_boxes[b][:, None, :] - tgt_boxes[b][None, :, :]).abs().sum(-1)
+            C = w_bbox * c_l1 + w_class * c_cls + w_ciou * c_iou
+        else:
+            C = w_class * c_cls + w_ciou * c_iou
+        out.append(C)
+    return out
+
+
+def hungarian_match(cost_blocks: List[Tensor]) -> List[Tuple[Tensor, Tensor]]:
+    """Per-image scipy linear_sum_assignment on the (Q,T_i) block (matcher.py:109-119)."""
+    from scipy.optimize import linear_sum_assignment
+    res = []
+    for c in cost_blocks:
+        i, j = linear_sum_assignment(c.detach().cpu().numpy())
+        res.append((torch.as_tensor(i, dtype=torch.int64), torch.as_tensor(j, dtype=torch.int64)))
+    return res
+
+
+def sigmoid_focal_loss(logits: Tensor, targets: Tensor, num_boxes: float, alpha: float = 0.25,
+                       gamma: float = 2.0) -> Tensor:
+    """sigmoid_focal_loss (src/utils/misc.py:99-128)."""
+    p = logits.sigmoid()
+    t = targets.to(logits.dtype)
+    ce = F.binary_cross_entropy_with_logits(logits, t, reduction="none")
+    pt = p * t + (1 - p) * (1 - t)
+    loss = (alpha * t + (1 - alpha) * (1 - t)) * ce * (1 - pt) ** gamma
+    return loss.mean(1).sum() / num_boxes
+
+
+def set_criterion(pred_class: Tensor, pred_boxes: Tensor, tgt_labels: List[Tensor],
+                  tgt_boxes: List[Tensor], indices: List[Tuple[Tensor, Tensor]],
+                  num_classes: int = 2) -> Dict[str, Tensor]:
+    """SetCriterion.forward after matching (src/utils/criterion.py:57-79) with
+    loss_fn = {class: sigmoid_focal_loss, bbox: L1Loss(mean), ciou: CompleteIOULoss}
+    (src/train/train.py:255-262).  `num_classes` is the one-hot width; the reference
+    hard-codes 2 (:45) -- passing the logits width is the 91-class harness shim of SURVEY 7.3-8.
+    Unmatched queries get class 1 (:41-44).  CompleteIOULoss is the mean of the full (n x n)
+    matrix (:87-89), reference behaviour."""
+    cls_l, box_l, iou_l = [], [], []
+    for b, (pi, ti) in enumerate(indices):
+        logits = pred_class[b]
+        Qn = logits.shape[0]
+        sel = torch.zeros(Qn, dtype=torch.bool)
+        sel[pi] = True
+        ordered = torch.cat([logits[pi], logits[~sel]], dim=0)
+        gt = torch.cat([tgt_labels[b][ti], torch.ones(Qn - pi.numel(), dtype=torch.int64)])
+        cls_l.append(sigmoid_focal_loss(ordered, F.one_hot(gt, num_classes), Qn))
+        if pi.numel() > 0:
+            pb = cxcyhw_to_xyxy(pred_boxes[b])[pi]
+            gb = tgt_boxes[b][ti]
+            box_l.append((pb - gb).abs().mean())
+            iou_l.append(complete_iou_cost(pb, gb).mean())
+    red = lambda v: torch.stack(v).mean() if v else torch.zeros(1)
+    return {"class": red(cls_l), "bbox": red(box_l), "ciou": red(iou_l)}
+
+
+# --------------------------------------------------------------------------------------
+# deterministic synthetic weights (shared by golden generation, tests, bench)
+# --------------------------------------------------------------------------------------
+def _lin(g: torch.Generator, out_f: int, in_f: int, bias: bool, sd: SD, name: str, gain: float = 1.0):
+    bound = gain / math.sqrt(in_f)
+    sd[name + ".weight"] = (torch.rand(out_f, in_f, generator=g) * 2 - 1) * bound
+    if bias:
+        sd[name + ".bias"] = (torch.rand(out_f, generator=g) * 2 - 1) * bound
+
+
+def _lnp(g: torch.Generator, d: int, sd: SD, name: str):
+    sd[name + ".weight"] = 1.0 + 0.1 * (torch.rand(d, generator=g) * 2 - 1)
+    sd[name + ".bias"] = 0.1 * (torch.rand(d, generator=g) * 2 - 1)
+
+
+def make_encoder_weights(num_layers: int, seed: int = 0, d: int = 256) -> SD:
+    """Random-init weights with the key names of reference `Encoder.state_dict()`
+    (encoder_block.py:8-22, 47-82), including the dead `_proj_to_q/k/v` parameters."""
+    g = torch.Generator().manual_seed(seed)
+    sd: SD = {}
+    for l in range(num_layers):
+        p = f"_encoder.{l}."
+        sd[p + "self_attn.in_proj_weight"] = (torch.rand(3 * d, d, generator=g) * 2 - 1) * math.sqrt(3.0 / d)
+        sd[p + "self_attn.in_proj_bias"] = (torch.rand(3 * d, generator=g) * 2 - 1) * 0.05
+        _lin(g, d, d, True, sd, p + "self_attn.out_proj")
+        _lin(g, 2048, d, True, sd, p + "fc1")
+        _lin(g, d, 2048, True, sd, p + "fc2")
+        _lnp(g, d, sd, p + "norm1")
+        _lnp(g, d, sd, p + "norm2")
+        _lin(g, d, d, False, sd, p + "_proj_to_q")
+        _lin(g, d, d, False, sd, p + "_proj_to_k")
+        _lin(g, d, d, False, sd, p + "_proj_to_v")
+    _lin(g, d, d, True, sd, "_pos_scale.0")
+    _lin(g, d, d, True, sd, "_pos_scale.2")
+    _lnp(g, d, sd, "norm")
+    return sd
+
+
+def make_decoder_weights(num_layers: int, seed: int = 1, d: int = 256) -> SD:
+    """Key names of reference `Decoder.state_dict()` (decoder_block.py:12-26, 70-131, 223-236)."""
+    g = torch.Generator().manual_seed(seed)
+    sd: SD = {}
+    for l in range(num_layers):
+        p = f"_decoder.{l}."
+        for br in ("_cls_branch", "_reg_branch"):
+            _lin(g, 4 * d, d, True, sd, p + br + ".fc1")
+            _lin(g, d, 4 * d, True, sd, p + br + ".fc2")
+            _lnp(g, d, sd, p + br + ".norm1")
+            _lnp(g, d, sd, p + br + ".norm2")
+        for n, (o, i) in {"_sa_proj_to_q_obj": (2 * d, 2 * d), "_sa_proj_to_q_pos": (d, d),
+                          "_sa_proj_to_k_obj": (2 * d, 2 * d), "_sa_proj_to_k_pos": (d, d),
+                          "_sa_proj_to_v_obj": (2 * d, 2 * d), "_ca_proj_to_q_obj": (2 * d, 2 * d),
+                          "_ca_proj_to_q_pos": (d, d), "_ca_proj_to_k_enc": (d, d),
+                          "_ca_proj_to_k_pos": (d, d), "_ca_proj_to_v_enc": (d, d)}.items():
+            _lin(g, o, i, False, sd, p + n, gain=1.7)
+        _lnp(g, 2 * d, sd, p + "norm1")
+        _lnp(g, 2 * d, sd, p + "norm2")
+    _lin(g, d, d, True, sd, "_pos_scale.0")
+    _lin(g, d, d, True, sd, "_pos_scale.2")
+    _lnp(g, 2 * d, sd, "norm")
+    return sd
+
+
+def make_head_weights(num_cls: int, seed: int = 2, d: int = 256) -> Tuple[SD, SD]:
+    """(`_cls_embed` Linear(256,num_cls), `_bbox_embed` Linear-ReLU-Linear(256,256,4))
+    (src/model/model.py:30-39)."""
+    g = torch.Generator().manual_seed(seed)
+    cls_sd: SD = {}
+    _lin(g, num_cls, d, True, cls_sd, "x")
+    cls_sd = {k[2:]: v for k, v in cls_sd.items()}
+    bbox_sd: SD = {}
+    _lin(g, d, d, True, bbox_sd, "0")
+    _lin(g, 4, d, True, bbox_sd, "2")
+    return cls_sd, bbox_sd
+
+
+def make_targets(batch: int, seed: int = 0, max_t: int = 40, num_cls: int = 91):
+    """Synthetic targets of SURVEY 8(d) config 2: T_i ~ U{1..max_t}, boxes xyxy with
+    xy ~ U(0,.6)^2, wh ~ U(.02,.37)^2, labels ~ U{0..num_cls-1}  (format: dataset.py:56-64)."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    labels, boxes = [], []
+    for _ in range(batch):
+        t = int(torch.randint(1, max_t + 1, (1,), generator=g))
+        xy = torch.rand(t, 2, generator=g) * 0.6
+        wh = 0.02 + torch.rand(t, 2, generator=g) * 0.35
+        boxes.append(torch.cat([xy, xy + wh], dim=-1))
+        labels.append(torch.randint(0, num_cls, (t,), generator=g))
+    return labels, boxes
