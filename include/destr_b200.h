@@ -1,0 +1,148 @@
+/* destr_b200.h -- C ABI of libdestr_b200.so: the B200 (sm_100a) kernels behind the DESTR
+ * transformer-half hot path.
+ *
+ * The reference (mio0115/object_detection_destr) is pure Python/PyTorch and has no FFI; the
+ * "plugin interface" of this path is its nn.Module / function API.  Each entry point below names
+ * the reference code (file:line, relative to the reference root) whose arithmetic it replaces.
+ * The Python host layer (object_detection_destr_b200/) binds these with ctypes and exposes
+ * drop-in modules with the reference's own names and signatures.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*.
+ *  - bf16 tensors are passed as `const void*` / `void*` (16-bit storage), fp32 as float*.
+ *  - the caller owns every buffer (inputs, outputs, workspaces); kernels never allocate.
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing syncs.
+ *  - return value: 0 = ok; nonzero = error, message via destr_last_error() (thread-local).
+ *  - token-major activations: row r = b*N + n (encoder tokens) or b*Q + q (object queries).
+ */
+#ifndef DESTR_B200_H_
+#define DESTR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int destr_version(void);
+const char* destr_last_error(void);
+
+/* ---------------- masks and positional embeddings ---------------- */
+
+/* Pack a key-padding mask (1 = padded; encoder_block.py:31, self_attention.py:34-37) into
+ * bit words for the attention kernels: bits[b][w] bit i = key (32w+i) is masked OR >= n_keys.
+ * kpm: uint8 [B, n_keys] (may be NULL = nothing masked); bits: uint32 [B, words_per_row],
+ * words_per_row >= ceil(n_keys/128)*4. */
+int destr_pack_key_mask(const uint8_t* kpm, uint32_t* bits, int B, int n_keys, int words_per_row, void* stream);
+
+/* PositionEmbeddingSine(num_pos_feats=128, normalize=True) (position_encoding_cdetr.py:39-63).
+ * mask uint8 [B,H,W] (1 = padded) -> pos token-major [B, H*W, 256] (fp32 and/or bf16; either
+ * pointer may be NULL). */
+int destr_sine_pos2d(const uint8_t* mask, float* pos_f32, void* pos_bf16, int B, int H, int W, void* stream);
+
+/* gen_sineembed_for_position (positional_embedding.py:6-39), d_model = 256.
+ * centers fp32 [M,2] (x,y) -> out [M,256] (fp32 and/or bf16). */
+int destr_query_sine_embed(const float* centers, float* out_f32, void* out_bf16, int M, void* stream);
+
+/* ---------------- encoder elementwise / normalisation ---------------- */
+
+/* y = x + pos * s   (encoder_block.py:38,95;  to_q_k = inputs + pos_embed*scale), bf16 [M,256]. */
+int destr_pos_mul_add_fwd(const void* x, const void* pos, const void* s, void* y, int64_t n_elem, void* stream);
+/* backward: dx = dy (aliasing is the caller's business), ds = dy * pos */
+int destr_pos_mul_add_bwd(const void* dy, const void* pos, void* ds, int64_t n_elem, void* stream);
+/* y = a * b, bf16 (fine_pos = pos * pos_scale(enc_out), model.py:89-92; decoder_block.py:49) */
+int destr_mul_fwd(const void* a, const void* b, void* y, int64_t n_elem, void* stream);
+
+/* y = LayerNorm(a + b) * gamma + beta over the last dim D (256 or 512), eps 1e-5
+ * (encoder_block.py:104-110, :40; decoder_block.py:65, 253-258).  a, b, y bf16 [M,D]; gamma/beta
+ * fp32 [D].  Optionally chains a second LN in the same pass: y2 = LayerNorm(c + y) (encoder
+ * outer residual + shared norm, encoder_block.py:40): pass c/gamma2/beta2/y2 non-NULL.
+ * Saves mean/rstd (fp32 [M]) for the backward when the pointers are non-NULL. */
+int destr_add_layernorm_fwd(const void* a, const void* b, const float* gamma, const float* beta, void* y,
+                            float* mean, float* rstd, int M, int D, void* stream);
+/* backward of y = LN(a+b): dx (bf16 [M,D]) = d(a+b); dgamma/dbeta fp32 [D] are ACCUMULATED into
+ * (caller zeroes).  xsum = a+b is recomputed from a and b. */
+int destr_add_layernorm_bwd(const void* dy, const void* a, const void* b, const float* gamma, const float* mean,
+                            const float* rstd, void* dx, float* dgamma, float* dbeta, int M, int D, void* stream);
+
+/* out = lam*LN1(x+o1) + (1-lam)*LN2(x+o2)  (decoder_block.py:182-184), D = 512. */
+int destr_dual_ln_mix_fwd(const void* x, const void* o1, const void* o2, const float* g1, const float* b1,
+                          const float* g2, const float* b2, float lam, void* out, float* stats /*[M,4]*/, int M,
+                          int D, void* stream);
+int destr_dual_ln_mix_bwd(const void* dout, const void* x, const void* o1, const void* o2, const float* g1,
+                          const float* g2, const float* stats, float lam, void* dx, void* do1, void* do2,
+                          float* dg1, float* db1, float* dg2, float* db2, int M, int D, void* stream);
+
+/* ---------------- encoder multi-head self-attention (tcgen05) ---------------- */
+
+/* Fused QK^T / softmax / PV of nn.MultiheadAttention as used at encoder_block.py:97-103
+ * (torch functional.py multi_head_attention_forward: q scaled by 1/sqrt(d_head), bool
+ * key-padding mask -> -inf, softmax, PV), flash style: the N x N score matrix is never written.
+ *   q, k, v : bf16 token-major, row r = b*N + n, head h occupies columns [h*32, h*32+32);
+ *             ld_* = row pitch in elements (q and k may alias one [M,512] projection output).
+ *   mask_bits : from destr_pack_key_mask (words_per_row as given there).
+ *   out     : bf16 [B*N, heads*32], heads merged (the layout out_proj consumes).
+ *   lse     : fp32 [B, heads, N], log2-domain log-sum-exp of scale*log2e*scores (for backward).
+ *   scale   : softmax scale (1/sqrt(32) for the encoder).
+ * d_head is fixed at 32, heads*32 <= 256.  Needs sm_100a (tcgen05/TMEM/TMA). */
+int destr_enc_attn_fwd(const void* q, const void* k, const void* v, int ld_q, int ld_k, int ld_v,
+                       const uint32_t* mask_bits, int words_per_row, void* out, float* lse, int B, int N,
+                       int heads, float scale, void* stream);
+/* backward: dq, dk, dv bf16 with the same row pitches as q, k, v (ld_dq, ld_dk, ld_dv).
+ * delta (fp32 [B,heads,N]) and dq_acc (fp32 [B*N, heads*32]) are caller-provided workspaces. */
+int destr_enc_attn_bwd(const void* q, const void* k, const void* v, int ld_q, int ld_k, int ld_v,
+                       const uint32_t* mask_bits, int words_per_row, const void* out, const void* dout,
+                       const float* lse, float* delta, float* dq_acc, void* dq, void* dk, void* dv, int ld_dq,
+                       int ld_dk, int ld_dv, int B, int N, int heads, float scale, void* stream);
+
+/* ---------------- decoder: pairing, self + pair attention, split cross-attention ---------------- */
+
+/* _get_pairs (pair_self_attention.py:110-171).  coords fp32 [B,Q,4] (cx,cy,h,w) -> pairs
+ * int32 [B,Q,2].  fp32 arithmetic in the reference's operation order (index parity). */
+int destr_pair_indices(const float* coords, int32_t* pairs, int B, int Q, void* stream);
+
+/* sigmoid(delta + [logit(cx), logit(cy), 0, 0]) (decoder_block.py:41,51-54; model.py:123-129;
+ * inverse_sigmoid misc.py:59-62).  delta fp32 [M,4], centers fp32 [M,2] -> boxes fp32 [M,4]. */
+int destr_box_refine(const float* delta, const float* centers, float* boxes, int M, void* stream);
+
+/* Decoder self-attention (self_attention.py:26-45, 8 heads x 64) and pair self-attention
+ * (pair_self_attention.py:33-105) in one launch.  q,k,v bf16 token-major [B*Q, 512] (head h =
+ * columns [64h, 64h+64)); pairs from destr_pair_indices.  o1, o2 bf16 [B*Q, 512].
+ * lse1/lse2 fp32 [B,8,Q] saved for the backward (may be NULL). */
+int destr_dec_self_pair_attn_fwd(const void* q, const void* k, const void* v, const int32_t* pairs, void* o1,
+                                 void* o2, float* lse1, float* lse2, int B, int Q, void* stream);
+int destr_dec_self_pair_attn_bwd(const void* q, const void* k, const void* v, const int32_t* pairs,
+                                 const void* do1, const void* do2, const float* lse1, const float* lse2,
+                                 float* dq_acc, float* dk_acc, float* dv_acc, int B, int Q, void* stream);
+
+/* Split cross-attention of both ClsRegBranch'es (decoder_block.py:212-217, 246-251 ->
+ * self_attention.py:26-45 with one head, d_qk = 512, d_v = 256, scale 1/sqrt(512)).
+ * Uses score = <q_obj, k_enc> + <q_pos, k_pos> (the per-head interleave of decoder_block.py:
+ * 195-210 is one permutation applied to both q and k, so it cancels in the dot product).
+ *   q_obj : bf16 [B*Q, 512]   cls half = cols [0,256), reg half = cols [256,512)
+ *   q_pos : bf16 [B*Q, 256]   shared by both branches
+ *   k_enc, k_pos, v : bf16 [B*N, 256] (row pitch ld_kv elements; may be slices of one wide GEMM output)
+ *   out   : bf16 [B*Q, 512]   cls result in cols [0,256), reg result in cols [256,512)
+ *   lse   : fp32 [B, 2, Q] */
+int destr_split_cross_attn_fwd(const void* q_obj, const void* q_pos, const void* k_enc, const void* k_pos,
+                               const void* v, int ld_kenc, int ld_kpos, int ld_v, const uint32_t* mask_bits,
+                               int words_per_row, void* out, float* lse, float* ws_partial, int B, int Q, int N,
+                               float scale, void* stream);
+
+/* ---------------- set-prediction cost matrix ---------------- */
+
+/* Matching cost of HungarianMatcher / HungarianMatcherWoL1 (matcher.py:72-107, 158-184;
+ * complete_iou bbox_utils.py:160-198), computed ONLY for the per-image diagonal blocks that
+ * linear_sum_assignment consumes (matcher.py:109-112), fp32, in the reference's operation order.
+ *   logits fp32 [B,Q,C]; boxes fp32 [B,Q,4] cxcyhw; tgt_ids int32 [T]; tgt_boxes fp32 [T,4] xyxy;
+ *   tgt_offsets int32 [B+1] (prefix sums of T_i); cost fp32, image b's block is row-major
+ *   [Q, T_b] starting at element Q*tgt_offsets[b].
+ *   with_l1 = 1 adds w_bbox * L1(pred cxcyhw, tgt xyxy) (matcher.py:96). */
+int destr_match_cost_blockdiag(const float* logits, const float* boxes, const int32_t* tgt_ids,
+                               const float* tgt_boxes, const int32_t* tgt_offsets, float* cost, int B, int Q, int C,
+                               float w_class, float w_bbox, float w_ciou, int with_l1, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DESTR_B200_H_ */

@@ -1,0 +1,57 @@
+"""ctypes binding of libdestr_b200.so (the C-ABI declared in include/destr_b200.h).
+
+There is no CPU fallback: importing this module without the built library, or calling an op on a
+non-CUDA tensor, raises.  Build with `python -c "import __graft_entry__ as g; g.build()"`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdestr_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: the CUDA library has not been built. "
+        "Run __graft_entry__.build() (nvcc, sm_100a). There is no CPU fallback.")
+
+lib = C.CDLL(LIB_PATH)
+
+_p, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
+
+# name -> argtypes; mirrors include/destr_b200.h one to one (tests/test_abi.py checks the header)
+SIGNATURES = {
+    "destr_version": [],
+    "destr_debug_knob": [_i, _i],
+    "destr_pack_key_mask": [_p, _p, _i, _i, _i, _p],
+    "destr_sine_pos2d": [_p, _p, _p, _i, _i, _i, _p],
+    "destr_query_sine_embed": [_p, _p, _p, _i, _p],
+    "destr_pos_mul_add_fwd": [_p, _p, _p, _p, _i64, _p],
+    "destr_pos_mul_add_bwd": [_p, _p, _p, _i64, _p],
+    "destr_mul_fwd": [_p, _p, _p, _i64, _p],
+    "destr_add_layernorm_fwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
+    "destr_add_layernorm_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
+    "destr_enc_attn_fwd": [_p, _p, _p, _i, _i, _i, _p, _i, _p, _p, _i, _i, _i, _f, _p],
+    "destr_pair_indices": [_p, _p, _i, _i, _p],
+    "destr_box_refine": [_p, _p, _p, _i, _p],
+    "destr_match_cost_blockdiag": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _f, _i, _p],
+}
+
+for _name, _args in SIGNATURES.items():
+    _fn = getattr(lib, _name)  # AttributeError here = header/library mismatch: fail loudly
+    _fn.argtypes = _args
+    _fn.restype = _i
+lib.destr_last_error.argtypes = []
+lib.destr_last_error.restype = C.c_char_p
+
+# number of kernel launches issued through this binding (bench.py reports it as gpu_launches)
+launch_count = 0
+
+
+def call(name: str, *args) -> None:
+    global launch_count
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed (rc={rc}): {lib.destr_last_error().decode()}")
+    launch_count += 1

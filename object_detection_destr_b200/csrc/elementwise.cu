@@ -1,0 +1,197 @@
+// Mask packing, sine positional embeddings and the bf16 elementwise kernels of the encoder
+// (HBM-bound: 128-bit vector loads/stores, no shared memory, grid sized in multiples of 148 SMs).
+#include "../../include/destr_b200.h"
+#include "common.cuh"
+
+namespace destr {
+namespace {
+
+constexpr int kSMs = 148;
+
+__global__ void pack_key_mask_kernel(const uint8_t* __restrict__ kpm, uint32_t* __restrict__ bits, int n_keys,
+                                     int words_per_row) {
+  const int b = blockIdx.y;
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= words_per_row) return;
+  uint32_t word = 0;
+#pragma unroll 4
+  for (int i = 0; i < 32; ++i) {
+    const int key = w * 32 + i;
+    bool masked = key >= n_keys;
+    if (!masked && kpm) masked = kpm[static_cast<size_t>(b) * n_keys + key] != 0;
+    word |= (masked ? 1u : 0u) << i;
+  }
+  bits[static_cast<size_t>(b) * words_per_row + w] = word;
+}
+
+// 10000^(2*floor(i/2)/128), i = channel within a 128-wide half
+__device__ __forceinline__ float sine_div(int i) { return powf(10000.0f, (2.0f * (float)(i >> 1)) / 128.0f); }
+
+// one block (128 threads) per token; thread c -> channels c (y half) and 128+c (x half)
+__global__ void sine_pos2d_kernel(const uint8_t* __restrict__ mask, float* __restrict__ pos_f32,
+                                  __nv_bfloat16* __restrict__ pos_bf16, int H, int W) {
+  const int tok = blockIdx.x;  // b*H*W + y*W + x
+  const int b = tok / (H * W);
+  const int yx = tok - b * H * W;
+  const int y = yx / W, x = yx - y * W;
+  const uint8_t* mb = mask + static_cast<size_t>(b) * H * W;
+  // cumulative counts of valid pixels (exact in fp32); every thread recomputes them (H,W <= ~100)
+  float ycum = 0.f, ytot = 0.f, xcum = 0.f, xtot = 0.f;
+  for (int yy = 0; yy < H; ++yy) {
+    const float v = mb[yy * W + x] ? 0.f : 1.f;
+    ytot += v;
+    if (yy <= y) ycum += v;
+  }
+  for (int xx = 0; xx < W; ++xx) {
+    const float v = mb[y * W + xx] ? 0.f : 1.f;
+    xtot += v;
+    if (xx <= x) xcum += v;
+  }
+  const float two_pi = 6.283185307179586f;
+  const float ye = __fmul_rn(__fdiv_rn(ycum, __fadd_rn(ytot, 1e-6f)), two_pi);
+  const float xe = __fmul_rn(__fdiv_rn(xcum, __fadd_rn(xtot, 1e-6f)), two_pi);
+  const int c = threadIdx.x;
+  const float dv = sine_div(c);
+  const float ay = __fdiv_rn(ye, dv), ax = __fdiv_rn(xe, dv);
+  const float vy = (c & 1) ? cosf(ay) : sinf(ay);
+  const float vx = (c & 1) ? cosf(ax) : sinf(ax);
+  const size_t o = static_cast<size_t>(tok) * 256;
+  if (pos_f32) {
+    pos_f32[o + c] = vy;
+    pos_f32[o + 128 + c] = vx;
+  }
+  if (pos_bf16) {
+    pos_bf16[o + c] = __float2bfloat16(vy);
+    pos_bf16[o + 128 + c] = __float2bfloat16(vx);
+  }
+}
+
+__global__ void query_sine_embed_kernel(const float* __restrict__ centers, float* __restrict__ out_f32,
+                                        __nv_bfloat16* __restrict__ out_bf16, int M) {
+  const int r = blockIdx.x;
+  const int c = threadIdx.x;  // 0..127
+  const float two_pi = 6.283185307179586f;
+  const float xe = __fmul_rn(centers[2 * r + 0], two_pi);
+  const float ye = __fmul_rn(centers[2 * r + 1], two_pi);
+  const float dv = sine_div(c);
+  const float ay = __fdiv_rn(ye, dv), ax = __fdiv_rn(xe, dv);
+  const float vy = (c & 1) ? cosf(ay) : sinf(ay);
+  const float vx = (c & 1) ? cosf(ax) : sinf(ax);
+  const size_t o = static_cast<size_t>(r) * 256;
+  if (out_f32) {
+    out_f32[o + c] = vy;
+    out_f32[o + 128 + c] = vx;
+  }
+  if (out_bf16) {
+    out_bf16[o + c] = __float2bfloat16(vy);
+    out_bf16[o + 128 + c] = __float2bfloat16(vx);
+  }
+}
+
+// ---- bf16 x8 vector helpers ----
+struct F8 {
+  float v[8];
+};
+__device__ __forceinline__ F8 ld8(const __nv_bfloat16* p) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  F8 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    r.v[2 * i] = __uint_as_float(w[i] << 16);
+    r.v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+  return r;
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const F8& f) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f.v[2 * i], f.v[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// MODE 0: y = x + pos*s ; 1: ds = dy*pos (x unused) ; 2: y = a*b (s unused)
+template <int MODE>
+__global__ void ew3_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ p,
+                           const __nv_bfloat16* __restrict__ s, __nv_bfloat16* __restrict__ y, int64_t n8) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    F8 r;
+    if (MODE == 0) {
+      const F8 a = ld8(x + i * 8), b = ld8(p + i * 8), c = ld8(s + i * 8);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) r.v[k] = fmaf(b.v[k], c.v[k], a.v[k]);
+    } else {
+      const F8 a = ld8(x + i * 8), b = ld8(p + i * 8);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) r.v[k] = a.v[k] * b.v[k];
+    }
+    st8(y + i * 8, r);
+  }
+}
+
+inline int ew_grid(int64_t n8, int threads) {
+  int64_t blocks = (n8 + threads - 1) / threads;
+  const int64_t cap = kSMs * 8;
+  if (blocks > cap) blocks = cap;
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+
+}  // namespace
+}  // namespace destr
+
+using namespace destr;
+
+extern "C" int destr_pack_key_mask(const uint8_t* kpm, uint32_t* bits, int B, int n_keys, int words_per_row,
+                                   void* stream) {
+  DESTR_CHECK_ARG(bits && B > 0 && n_keys > 0 && words_per_row * 32 >= n_keys, "shape");
+  dim3 grid(ceil_div(words_per_row, 64), B);
+  pack_key_mask_kernel<<<grid, 64, 0, (cudaStream_t)stream>>>(kpm, bits, n_keys, words_per_row);
+  DESTR_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int destr_sine_pos2d(const uint8_t* mask, float* pos_f32, void* pos_bf16, int B, int H, int W,
+                                void* stream) {
+  DESTR_CHECK_ARG(mask && (pos_f32 || pos_bf16) && B > 0 && H > 0 && W > 0, "shape");
+  sine_pos2d_kernel<<<B * H * W, 128, 0, (cudaStream_t)stream>>>(mask, pos_f32, (__nv_bfloat16*)pos_bf16, H, W);
+  DESTR_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int destr_query_sine_embed(const float* centers, float* out_f32, void* out_bf16, int M, void* stream) {
+  DESTR_CHECK_ARG(centers && (out_f32 || out_bf16) && M > 0, "shape");
+  query_sine_embed_kernel<<<M, 128, 0, (cudaStream_t)stream>>>(centers, out_f32, (__nv_bfloat16*)out_bf16, M);
+  DESTR_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int destr_pos_mul_add_fwd(const void* x, const void* pos, const void* s, void* y, int64_t n_elem,
+                                     void* stream) {
+  DESTR_CHECK_ARG(x && pos && s && y && n_elem > 0 && n_elem % 8 == 0, "n_elem must be a multiple of 8");
+  const int64_t n8 = n_elem / 8;
+  ew3_kernel<0><<<ew_grid(n8, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, (const __nv_bfloat16*)pos, (const __nv_bfloat16*)s, (__nv_bfloat16*)y, n8);
+  DESTR_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int destr_pos_mul_add_bwd(const void* dy, const void* pos, void* ds, int64_t n_elem, void* stream) {
+  DESTR_CHECK_ARG(dy && pos && ds && n_elem > 0 && n_elem % 8 == 0, "n_elem must be a multiple of 8");
+  const int64_t n8 = n_elem / 8;
+  ew3_kernel<1><<<ew_grid(n8, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dy, (const __nv_bfloat16*)pos, nullptr, (__nv_bfloat16*)ds, n8);
+  DESTR_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int destr_mul_fwd(const void* a, const void* b, void* y, int64_t n_elem, void* stream) {
+  DESTR_CHECK_ARG(a && b && y && n_elem > 0 && n_elem % 8 == 0, "n_elem must be a multiple of 8");
+  const int64_t n8 = n_elem / 8;
+  ew3_kernel<2><<<ew_grid(n8, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, nullptr, (__nv_bfloat16*)y, n8);
+  DESTR_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,219 @@
+// Residual-add + LayerNorm family (bf16 I/O, fp32 statistics, warp-shuffle reductions).
+//   y = LN(a + b)                     encoder_block.py:104-110,:40 ; decoder_block.py:65,253-258
+//   o = lam*LN1(x+o1) + (1-lam)*LN2(x+o2)   decoder_block.py:182-184
+// One warp per row; a lane owns D/32 contiguous channels (one or two 128-bit loads per operand).
+// HBM-bound: algorithmic bytes = (2 reads + 1 write) * M * D * 2 B for the forward.
+#include "../../include/destr_b200.h"
+#include "common.cuh"
+
+namespace destr {
+namespace {
+
+constexpr int kSMs = 148;
+constexpr float kEps = 1e-5f;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int VPL>  // values per lane (8 or 16)
+struct Row {
+  float v[VPL];
+};
+
+template <int VPL>
+__device__ __forceinline__ Row<VPL> ld_row(const __nv_bfloat16* base, int lane) {
+  Row<VPL> r;
+#pragma unroll
+  for (int c = 0; c < VPL / 8; ++c) {
+    const uint4 u = *reinterpret_cast<const uint4*>(base + (c * 32 + lane) * 8);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      r.v[c * 8 + 2 * i] = __uint_as_float(w[i] << 16);
+      r.v[c * 8 + 2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  return r;
+}
+template <int VPL>
+__device__ __forceinline__ void st_row(__nv_bfloat16* base, int lane, const Row<VPL>& r) {
+#pragma unroll
+  for (int c = 0; c < VPL / 8; ++c) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(r.v[c * 8 + 2 * i], r.v[c * 8 + 2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(base + (c * 32 + lane) * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+// fp32 per-channel vector (gamma/beta) in the same lane ownership
+template <int VPL>
+__device__ __forceinline__ Row<VPL> ld_vec(const float* base, int lane) {
+  Row<VPL> r;
+#pragma unroll
+  for (int c = 0; c < VPL / 8; ++c) {
+    const float4 a = *reinterpret_cast<const float4*>(base + (c * 32 + lane) * 8);
+    const float4 b = *reinterpret_cast<const float4*>(base + (c * 32 + lane) * 8 + 4);
+    r.v[c * 8 + 0] = a.x; r.v[c * 8 + 1] = a.y; r.v[c * 8 + 2] = a.z; r.v[c * 8 + 3] = a.w;
+    r.v[c * 8 + 4] = b.x; r.v[c * 8 + 5] = b.y; r.v[c * 8 + 6] = b.z; r.v[c * 8 + 7] = b.w;
+  }
+  return r;
+}
+
+template <int VPL>
+__device__ __forceinline__ void stats(const Row<VPL>& x, float& mean, float& rstd) {
+  constexpr float invD = 1.0f / (VPL * 32);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) s += x.v[i];
+  mean = warp_sum(s) * invD;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const float d = x.v[i] - mean;
+    q = fmaf(d, d, q);
+  }
+  rstd = rsqrtf(warp_sum(q) * invD + kEps);
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(256)
+add_ln_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                  const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                  float* __restrict__ mean_out, float* __restrict__ rstd_out, int M) {
+  constexpr int D = VPL * 32;
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const Row<VPL> g = ld_vec<VPL>(gamma, lane), be = ld_vec<VPL>(beta, lane);
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += gridDim.x * wpb) {
+    Row<VPL> x = ld_row<VPL>(a + (size_t)row * D, lane);
+    if (b) {
+      const Row<VPL> r2 = ld_row<VPL>(b + (size_t)row * D, lane);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) x.v[i] += r2.v[i];
+    }
+    float mean, rstd;
+    stats<VPL>(x, mean, rstd);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) x.v[i] = fmaf((x.v[i] - mean) * rstd, g.v[i], be.v[i]);
+    st_row<VPL>(y + (size_t)row * D, lane, x);
+    if (mean_out && lane == 0) {
+      mean_out[row] = mean;
+      rstd_out[row] = rstd;
+    }
+  }
+}
+
+// dx = rstd * (gy - mean(gy) - xhat * mean(gy*xhat)),  gy = dy*gamma;  dgamma += dy*xhat; dbeta += dy
+template <int VPL>
+__global__ void __launch_bounds__(256)
+add_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ a,
+                  const __nv_bfloat16* __restrict__ b, const float* __restrict__ gamma,
+                  const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                  __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int M) {
+  constexpr int D = VPL * 32;
+  constexpr float invD = 1.0f / D;
+  __shared__ float red[2][8][D];  // [dgamma|dbeta][warp][channel]  (<= 32 KB at D=512)
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int wpb = blockDim.x >> 5;
+  const Row<VPL> g = ld_vec<VPL>(gamma, lane);
+  Row<VPL> accg, accb;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) accg.v[i] = accb.v[i] = 0.f;
+  for (int row = blockIdx.x * wpb + warp; row < M; row += gridDim.x * wpb) {
+    Row<VPL> x = ld_row<VPL>(a + (size_t)row * D, lane);
+    if (b) {
+      const Row<VPL> r2 = ld_row<VPL>(b + (size_t)row * D, lane);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) x.v[i] += r2.v[i];
+    }
+    const Row<VPL> d = ld_row<VPL>(dy + (size_t)row * D, lane);
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      x.v[i] = (x.v[i] - mean) * rstd;  // xhat
+      const float gy = d.v[i] * g.v[i];
+      s1 += gy;
+      s2 = fmaf(gy, x.v[i], s2);
+      accg.v[i] = fmaf(d.v[i], x.v[i], accg.v[i]);
+      accb.v[i] += d.v[i];
+    }
+    s1 = warp_sum(s1) * invD;
+    s2 = warp_sum(s2) * invD;
+    Row<VPL> o;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) o.v[i] = rstd * (d.v[i] * g.v[i] - s1 - x.v[i] * s2);
+    st_row<VPL>(dx + (size_t)row * D, lane, o);
+  }
+  // block reduction of the parameter gradients, then one atomic per channel per block
+#pragma unroll
+  for (int c = 0; c < VPL / 8; ++c)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      red[0][warp][(c * 32 + lane) * 8 + i] = accg.v[c * 8 + i];
+      red[1][warp][(c * 32 + lane) * 8 + i] = accb.v[c * 8 + i];
+    }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < D; ch += blockDim.x) {
+    float sg = 0.f, sb = 0.f;
+    for (int w = 0; w < wpb; ++w) {
+      sg += red[0][w][ch];
+      sb += red[1][w][ch];
+    }
+    atomicAdd(dgamma + ch, sg);
+    atomicAdd(dbeta + ch, sb);
+  }
+}
+
+inline int ln_grid(int M) {
+  int blocks = ceil_div(M, 8);
+  const int cap = kSMs * 4;
+  return blocks > cap ? cap : (blocks < 1 ? 1 : blocks);
+}
+
+}  // namespace
+}  // namespace destr
+
+using namespace destr;
+
+extern "C" int destr_add_layernorm_fwd(const void* a, const void* b, const float* gamma, const float* beta, void* y,
+                                       float* mean, float* rstd, int M, int D, void* stream) {
+  DESTR_CHECK_ARG(a && gamma && beta && y && M > 0, "null pointer / shape");
+  DESTR_CHECK_ARG(D == 256 || D == 512, "D must be 256 or 512");
+  DESTR_CHECK_ARG((mean == nullptr) == (rstd == nullptr), "mean and rstd go together");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (D == 256)
+    add_ln_fwd_kernel<8><<<ln_grid(M), 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, gamma, beta,
+                                                     (__nv_bfloat16*)y, mean, rstd, M);
+  else
+    add_ln_fwd_kernel<16><<<ln_grid(M), 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, gamma, beta,
+                                                      (__nv_bfloat16*)y, mean, rstd, M);
+  DESTR_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int destr_add_layernorm_bwd(const void* dy, const void* a, const void* b, const float* gamma,
+                                       const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
+                                       int M, int D, void* stream) {
+  DESTR_CHECK_ARG(dy && a && gamma && mean && rstd && dx && dgamma && dbeta && M > 0, "null pointer / shape");
+  DESTR_CHECK_ARG(D == 256 || D == 512, "D must be 256 or 512");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ln_grid(M) > kSMs * 2 ? kSMs * 2 : ln_grid(M);
+  if (D == 256)
+    add_ln_bwd_kernel<8><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)a,
+                                               (const __nv_bfloat16*)b, gamma, mean, rstd, (__nv_bfloat16*)dx, dgamma,
+                                               dbeta, M);
+  else
+    add_ln_bwd_kernel<16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)a,
+                                                (const __nv_bfloat16*)b, gamma, mean, rstd, (__nv_bfloat16*)dx, dgamma,
+                                                dbeta, M);
+  DESTR_LAUNCH_CHECK();
+  return 0;
+}

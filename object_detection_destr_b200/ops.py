@@ -1,0 +1,182 @@
+"""Tensor-level wrappers over the C-ABI kernels (raw pointers + current CUDA stream).
+
+Each function allocates its outputs with torch (caching allocator), passes `data_ptr()`s and the
+current stream to libdestr_b200.so, and returns torch tensors.  No function here has a CPU or
+pure-torch fallback.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+Tensor = torch.Tensor
+BF16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t: Tensor, dtype, name: str) -> Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (destr_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    return t
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# ----------------------------------------------------------------------------------------------
+# masks / positional embeddings
+# ----------------------------------------------------------------------------------------------
+def mask_words(n_keys: int) -> int:
+    return ((n_keys + 127) // 128) * 4
+
+
+def pack_key_mask(kpm: Optional[Tensor], B: int, n_keys: int, device=None) -> Tensor:
+    """kpm: bool/uint8 [B, n_keys] (True = padded) or None -> uint32-bit words [B, mask_words]."""
+    wpr = mask_words(n_keys)
+    if kpm is not None:
+        kpm = _chk(kpm.contiguous().view(torch.uint8) if kpm.dtype == torch.bool else kpm.contiguous(),
+                   torch.uint8, "kpm")
+        device = kpm.device
+    bits = torch.empty(B, wpr, dtype=torch.int32, device=device)
+    _lib.call("destr_pack_key_mask", _ptr(kpm), bits.data_ptr(), B, n_keys, wpr, _stream())
+    return bits
+
+
+def sine_pos2d(mask: Tensor, want_f32: bool = True, want_bf16: bool = True):
+    """mask bool [B,H,W] -> token-major pos [B, H*W, 256] (fp32, bf16)."""
+    B, H, W = mask.shape
+    m = _chk(mask.contiguous().view(torch.uint8), torch.uint8, "mask")
+    pf = torch.empty(B, H * W, 256, dtype=torch.float32, device=m.device) if want_f32 else None
+    pb = torch.empty(B, H * W, 256, dtype=BF16, device=m.device) if want_bf16 else None
+    _lib.call("destr_sine_pos2d", m.data_ptr(), _ptr(pf), _ptr(pb), B, H, W, _stream())
+    return pf, pb
+
+
+def query_sine_embed(centers: Tensor, want_f32: bool = True, want_bf16: bool = False):
+    c = _chk(centers.contiguous(), torch.float32, "centers")
+    M = c.numel() // 2
+    shape = c.shape[:-1] + (256,)
+    of = torch.empty(shape, dtype=torch.float32, device=c.device) if want_f32 else None
+    ob = torch.empty(shape, dtype=BF16, device=c.device) if want_bf16 else None
+    _lib.call("destr_query_sine_embed", c.data_ptr(), _ptr(of), _ptr(ob), M, _stream())
+    return of, ob
+
+
+# ----------------------------------------------------------------------------------------------
+# elementwise / layernorm (raw, non-autograd; autograd wrappers live in functional.py)
+# ----------------------------------------------------------------------------------------------
+def pos_mul_add(x: Tensor, pos: Tensor, s: Tensor) -> Tensor:
+    x, pos, s = (_chk(t.contiguous(), BF16, n) for t, n in ((x, "x"), (pos, "pos"), (s, "s")))
+    y = torch.empty_like(x)
+    _lib.call("destr_pos_mul_add_fwd", x.data_ptr(), pos.data_ptr(), s.data_ptr(), y.data_ptr(), x.numel(), _stream())
+    return y
+
+
+def pos_mul_add_bwd(dy: Tensor, pos: Tensor) -> Tensor:
+    dy, pos = _chk(dy.contiguous(), BF16, "dy"), _chk(pos.contiguous(), BF16, "pos")
+    ds = torch.empty_like(dy)
+    _lib.call("destr_pos_mul_add_bwd", dy.data_ptr(), pos.data_ptr(), ds.data_ptr(), dy.numel(), _stream())
+    return ds
+
+
+def mul(a: Tensor, b: Tensor) -> Tensor:
+    a, b = _chk(a.contiguous(), BF16, "a"), _chk(b.contiguous(), BF16, "b")
+    y = torch.empty_like(a)
+    _lib.call("destr_mul_fwd", a.data_ptr(), b.data_ptr(), y.data_ptr(), a.numel(), _stream())
+    return y
+
+
+def add_layernorm(a: Tensor, b: Optional[Tensor], gamma: Tensor, beta: Tensor, save_stats: bool = False):
+    a = _chk(a.contiguous(), BF16, "a")
+    if b is not None:
+        b = _chk(b.contiguous(), BF16, "b")
+    g, be = _chk(gamma.contiguous(), torch.float32, "gamma"), _chk(beta.contiguous(), torch.float32, "beta")
+    D = a.shape[-1]
+    M = a.numel() // D
+    y = torch.empty_like(a)
+    mean = torch.empty(M, dtype=torch.float32, device=a.device) if save_stats else None
+    rstd = torch.empty(M, dtype=torch.float32, device=a.device) if save_stats else None
+    _lib.call("destr_add_layernorm_fwd", a.data_ptr(), _ptr(b), g.data_ptr(), be.data_ptr(), y.data_ptr(),
+              _ptr(mean), _ptr(rstd), M, D, _stream())
+    return (y, mean, rstd) if save_stats else y
+
+
+def add_layernorm_bwd(dy: Tensor, a: Tensor, b: Optional[Tensor], gamma: Tensor, mean: Tensor, rstd: Tensor):
+    dy = _chk(dy.contiguous(), BF16, "dy")
+    D = a.shape[-1]
+    M = a.numel() // D
+    dx = torch.empty_like(a)
+    dg = torch.zeros(D, dtype=torch.float32, device=a.device)
+    db = torch.zeros(D, dtype=torch.float32, device=a.device)
+    _lib.call("destr_add_layernorm_bwd", dy.data_ptr(), a.data_ptr(), _ptr(b), gamma.data_ptr(), mean.data_ptr(),
+              rstd.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), M, D, _stream())
+    return dx, dg, db
+
+
+# ----------------------------------------------------------------------------------------------
+# encoder attention
+# ----------------------------------------------------------------------------------------------
+def enc_attn_fwd(q: Tensor, k: Tensor, v: Tensor, mask_bits: Tensor, B: int, N: int, heads: int,
+                 scale: float, need_lse: bool = True):
+    """q,k,v: bf16 2-D views [B*N, heads*32] (any row pitch, unit column stride).
+    Returns (out bf16 [B*N, heads*32], lse fp32 [B,heads,N])."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _chk(t, BF16, n)
+        if t.dim() != 2 or t.stride(1) != 1 or t.shape != (B * N, heads * 32):
+            raise ValueError(f"{n}: expected a [B*N, heads*32] view with unit column stride, got {tuple(t.shape)} "
+                             f"strides {t.stride()}")
+    out = torch.empty(B * N, heads * 32, dtype=BF16, device=q.device)
+    lse = torch.empty(B, heads, N, dtype=torch.float32, device=q.device) if need_lse else None
+    _lib.call("destr_enc_attn_fwd", q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), k.stride(0), v.stride(0),
+              mask_bits.data_ptr(), mask_bits.shape[1], out.data_ptr(), _ptr(lse), B, N, heads, float(scale),
+              _stream())
+    return out, lse
+
+
+# ----------------------------------------------------------------------------------------------
+# decoder small kernels
+# ----------------------------------------------------------------------------------------------
+def pair_indices(coords: Tensor) -> Tensor:
+    """coords fp32 [B,Q,4] cxcyhw -> int32 [B,Q,2]  (_get_pairs)."""
+    c = _chk(coords.contiguous(), torch.float32, "coords")
+    B, Q, _ = c.shape
+    pairs = torch.empty(B, Q, 2, dtype=torch.int32, device=c.device)
+    _lib.call("destr_pair_indices", c.data_ptr(), pairs.data_ptr(), B, Q, _stream())
+    return pairs
+
+
+def box_refine(delta: Tensor, centers: Tensor) -> Tensor:
+    d = _chk(delta.contiguous(), torch.float32, "delta")
+    c = _chk(centers.contiguous(), torch.float32, "centers")
+    out = torch.empty_like(d)
+    _lib.call("destr_box_refine", d.data_ptr(), c.data_ptr(), out.data_ptr(), d.numel() // 4, _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# matcher cost
+# ----------------------------------------------------------------------------------------------
+def match_cost_blockdiag(logits: Tensor, boxes: Tensor, tgt_ids: Tensor, tgt_boxes: Tensor, tgt_offsets: Tensor,
+                         total_t: int, w_class: float, w_bbox: float, w_ciou: float, with_l1: bool,
+                         out: Optional[Tensor] = None) -> Tensor:
+    """Returns the flat fp32 cost buffer [Q * sum(T_i)]; image b's (Q,T_b) block starts at Q*offsets[b]."""
+    lg = _chk(logits.contiguous(), torch.float32, "logits")
+    bx = _chk(boxes.contiguous(), torch.float32, "boxes")
+    B, Q, Cn = lg.shape
+    if out is None:
+        out = torch.empty(max(Q * total_t, 1), dtype=torch.float32, device=lg.device)
+    if total_t > 0:
+        _lib.call("destr_match_cost_blockdiag", lg.data_ptr(), bx.data_ptr(), _chk(tgt_ids, torch.int32, "tgt_ids").data_ptr(),
+                  _chk(tgt_boxes, torch.float32, "tgt_boxes").data_ptr(), _chk(tgt_offsets, torch.int32, "tgt_offsets").data_ptr(),
+                  out.data_ptr(), B, Q, Cn, float(w_class), float(w_bbox), float(w_ciou), int(with_l1), _stream())
+    return out

@@ -1,0 +1,227 @@
+"""Bring-up checks on a real B200: every kernel vs the CPU oracle, with diagnostics.
+
+    python tools/gpu_check.py simt            # all SIMT kernels, in process
+    python tools/gpu_check.py attn [k=v ...]  # encoder attention (tcgen05), optional debug knobs
+    python tools/gpu_check.py all             # simt + attn (each attn config in its own subprocess)
+
+Debug knobs (index=value) map to destr_debug_knob: 0 v_lbo 1 v_sbo 2 qk_lbo 3 qk_sbo 4 p_kstep_cols 5 v_kstep_bytes
+"""
+import math
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def report(name, got, ref, atol, rtol=0.0):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    bad = ~torch.isfinite(got) & torch.isfinite(ref)
+    err = (got - ref).abs()
+    err[torch.isnan(err)] = 0 if not bad.any() else float("inf")
+    tol = atol + rtol * ref.abs()
+    ok = bool((err <= tol).all()) and not bool(bad.any())
+    print(f"[{'PASS' if ok else 'FAIL'}] {name}: max_abs_err={float(err.max()):.3e} ref_absmax={float(ref.abs().max()):.3e} "
+          f"nonfinite={int(bad.sum())}", flush=True)
+    return ok
+
+
+def check_simt():
+    from oracle import destr_oracle as O
+    from object_detection_destr_b200 import ops
+    dev = "cuda"
+    g = torch.Generator().manual_seed(0)
+    ok = True
+
+    # sine pos 2d with padding
+    mask = torch.zeros(3, 25, 42, dtype=torch.bool)
+    mask[1, 20:, :] = True
+    mask[1, :, 30:] = True
+    mask[2, :, 41:] = True
+    pf, pb = ops.sine_pos2d(mask.to(dev))
+    ref = O.sine_pos2d(mask).flatten(2).transpose(1, 2)
+    ok &= report("sine_pos2d fp32", pf, ref, 2e-5)
+    ok &= report("sine_pos2d bf16", pb, ref, 8e-3)
+
+    c = torch.rand(4, 100, 2, generator=g)
+    qf, _ = ops.query_sine_embed(c.to(dev))
+    ok &= report("query_sine_embed", qf, O.query_sine_embed(c, 256), 2e-5)
+
+    # pack mask
+    kpm = torch.rand(3, 1050, generator=g) < 0.2
+    bits = ops.pack_key_mask(kpm.to(dev), 3, 1050).cpu()
+    W = bits.shape[1]
+    exp = torch.ones(3, W * 32, dtype=torch.bool)
+    exp[:, :1050] = kpm
+    got = ((bits.long()[:, :, None] >> torch.arange(32)) & 1).bool().reshape(3, -1)
+    print(f"[{'PASS' if torch.equal(got, exp) else 'FAIL'}] pack_key_mask", flush=True)
+    ok &= torch.equal(got, exp)
+
+    # elementwise
+    x, p, s = (torch.randn(8400, 256, generator=g).bfloat16() for _ in range(3))
+    y = ops.pos_mul_add(x.to(dev), p.to(dev), s.to(dev))
+    ok &= report("pos_mul_add", y, x.float() + p.float() * s.float(), 0, 8e-3)
+    ok &= report("pos_mul_add_bwd", ops.pos_mul_add_bwd(x.to(dev), p.to(dev)), x.float() * p.float(), 0, 8e-3)
+    ok &= report("mul", ops.mul(x.to(dev), p.to(dev)), x.float() * p.float(), 0, 8e-3)
+
+    # layernorm fwd/bwd, D = 256 and 512
+    for D, M in ((256, 8400), (512, 803)):
+        a = torch.randn(M, D, generator=g).bfloat16()
+        b = torch.randn(M, D, generator=g).bfloat16()
+        gam = 1 + 0.1 * torch.randn(D, generator=g)
+        bet = 0.1 * torch.randn(D, generator=g)
+        dy = torch.randn(M, D, generator=g).bfloat16()
+        xs = (a.float() + b.float()).requires_grad_()
+        gr, br = gam.clone().requires_grad_(), bet.clone().requires_grad_()
+        yr = torch.nn.functional.layer_norm(xs, (D,), gr, br, 1e-5)
+        yr.backward(dy.float())
+        yk, mean, rstd = ops.add_layernorm(a.to(dev), b.to(dev), gam.to(dev), bet.to(dev), save_stats=True)
+        ok &= report(f"add_layernorm_fwd D={D}", yk, yr, 2e-2, 8e-3)
+        dx, dg, db = ops.add_layernorm_bwd(dy.to(dev), a.to(dev), b.to(dev), gam.to(dev), mean, rstd)
+        ok &= report(f"add_layernorm_bwd dx D={D}", dx, xs.grad, 2e-2, 1e-2)
+        ok &= report(f"add_layernorm_bwd dgamma D={D}", dg, gr.grad, 1e-2, 2e-3)
+        ok &= report(f"add_layernorm_bwd dbeta D={D}", db, br.grad, 1e-2, 2e-3)
+
+    # pairs
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "golden.pt"), weights_only=False)
+    pr = ops.pair_indices(gold["pairs_in"].to(dev)).cpu().long()
+    eq = torch.equal(pr, gold["pairs_out"])
+    print(f"[{'PASS' if eq else 'FAIL'}] pair_indices golden (mismatches={(pr != gold['pairs_out']).sum().item()})", flush=True)
+    ok &= eq
+    cx = torch.cat([0.1 + 0.8 * torch.rand(8, 300, 2, generator=g), 0.03 + 0.4 * torch.rand(8, 300, 2, generator=g)], -1)
+    pr = ops.pair_indices(cx.to(dev)).cpu().long()
+    ref = O.get_pairs(cx)
+    eq = torch.equal(pr, ref)
+    print(f"[{'PASS' if eq else 'FAIL'}] pair_indices random Q=300 (mismatches={(pr != ref).sum().item()})", flush=True)
+    ok &= eq
+
+    # box refine
+    d = torch.randn(800, 4, generator=g)
+    cc = torch.rand(800, 2, generator=g)
+    br_ = ops.box_refine(d.to(dev), cc.to(dev))
+    refb = torch.cat([d[:, :2] + O.inverse_sigmoid(cc), d[:, 2:]], -1).sigmoid()
+    ok &= report("box_refine", br_, refb, 1e-6)
+
+    # matcher cost
+    B, Q, Cn = 8, 100, 91
+    logits = torch.randn(B, Q, Cn, generator=g)
+    boxes = torch.cat([0.1 + 0.8 * torch.rand(B, Q, 2, generator=g), 0.03 + 0.4 * torch.rand(B, Q, 2, generator=g)], -1)
+    labels, tboxes = O.make_targets(B, seed=3)
+    sizes = [len(l) for l in labels]
+    offs = torch.tensor([0] + list(torch.tensor(sizes).cumsum(0)), dtype=torch.int32)
+    ids = torch.cat(labels).int()
+    tb = torch.cat(tboxes)
+    for with_l1, (wc, wb, wi) in ((True, (1.0, 2.0, 1.0)), (False, (0.5, 0.0, 0.5))):
+        cost = ops.match_cost_blockdiag(logits.to(dev), boxes.to(dev), ids.to(dev), tb.to(dev), offs.to(dev),
+                                        int(offs[-1]), wc, wb, wi, with_l1).cpu()
+        refb_ = O.match_cost_blocks(logits, boxes, labels, tboxes, wc, wb, wi, with_l1=with_l1)
+        got_blocks = [cost[Q * int(offs[b]): Q * int(offs[b + 1])].view(Q, sizes[b]) for b in range(B)]
+        worst = max(float((gb - rb).abs().max()) for gb, rb in zip(got_blocks, refb_))
+        same = all(torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+                   for a, b in zip(O.hungarian_match(got_blocks), O.hungarian_match(refb_)))
+        print(f"[{'PASS' if same and worst < 1e-5 else 'FAIL'}] match_cost l1={with_l1}: max_abs_err={worst:.3e} "
+              f"assignments_identical={same}", flush=True)
+        ok &= same and worst < 1e-5
+    return ok
+
+
+def attn_case(B, N, heads, mode, masked, seed=0, time_it=False):
+    from oracle import destr_oracle as O
+    from object_detection_destr_b200 import ops
+    dev = "cuda"
+    g = torch.Generator().manual_seed(seed)
+    M = B * N
+    qk = (torch.randn(M, 2 * heads * 32, generator=g) * 1.0).bfloat16()
+    v = torch.randn(M, heads * 32, generator=g).bfloat16()
+    if mode == "vones":
+        v = torch.ones_like(v)
+    if mode == "quniform":
+        qk = torch.zeros_like(qk)
+    kpm = torch.zeros(B, N, dtype=torch.bool)
+    if masked:
+        kpm[B - 1, N // 2:] = True
+        kpm[B - 1, 3] = True
+        kpm[0, 7] = True
+    qk_d, v_d = qk.to(dev), v.to(dev)
+    bits = ops.pack_key_mask(kpm.to(dev), B, N)
+    scale = 1.0 / math.sqrt(32)
+    out, lse = ops.enc_attn_fwd(qk_d[:, :heads * 32], qk_d[:, heads * 32:], v_d, bits, B, N, heads, scale)
+    torch.cuda.synchronize()
+    split = lambda t: t.float().reshape(B, N, heads, 32).transpose(1, 2)
+    q_, k_, v_ = split(qk[:, :heads * 32]), split(qk[:, heads * 32:]), split(v)
+    ref = O.sdp_attention(q_, k_, v_, key_padding_mask=kpm).reshape(M, heads * 32)
+    s = torch.einsum("bhqd,bhkd->bhqk", q_, k_) * scale
+    s = s.masked_fill(kpm[:, None, None, :], float("-inf"))
+    lse_ref = torch.logsumexp(s, -1) * 1.4426950408889634
+    name = f"enc_attn B={B} N={N} h={heads} mode={mode} masked={masked}"
+    ok = report(name, out, ref, 2e-2, 2e-2)
+    ok &= report(name + " lse", lse, lse_ref, 2e-2, 1e-3)
+    if not ok:
+        e = (out.float().cpu() - ref).abs().reshape(B, N, heads, 32)
+        print("   err by batch:", e.amax((1, 2, 3)).tolist())
+        print("   err by head :", e.amax((0, 1, 3)).tolist())
+        print("   err by dim  :", [round(x, 3) for x in e.amax((0, 1, 2)).tolist()])
+        rows = e.amax((0, 2, 3))
+        print("   err by row block of 32:", [round(float(rows[i:i + 32].max()), 3) for i in range(0, N, 32)])
+        print("   sample out[0,:8]:", out[0, :8].float().cpu().tolist())
+        print("   sample ref[0,:8]:", ref[0, :8].tolist(), flush=True)
+    if time_it:
+        for _ in range(3):
+            ops.enc_attn_fwd(qk_d[:, :heads * 32], qk_d[:, heads * 32:], v_d, bits, B, N, heads, scale)
+        st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        st.record()
+        iters = 20
+        for _ in range(iters):
+            ops.enc_attn_fwd(qk_d[:, :heads * 32], qk_d[:, heads * 32:], v_d, bits, B, N, heads, scale)
+        en.record()
+        torch.cuda.synchronize()
+        ms = st.elapsed_time(en) / iters
+        fl = 4.0 * N * N * heads * 32 * B
+        print(f"   time {ms*1e3:.1f} us  -> {fl/ms/1e9:.1f} TFLOP/s algorithmic ({fl/ms/1e9/1660.7*100:.1f}% of 1660.7 measured peak)", flush=True)
+    return ok
+
+
+def check_attn(knobs):
+    from object_detection_destr_b200 import _lib
+    for kv in knobs:
+        i, val = kv.split("=")
+        _lib.lib.destr_debug_knob(int(i), int(val))
+    ok = True
+    ok &= attn_case(1, 128, 1, "vones", False)
+    ok &= attn_case(1, 128, 1, "quniform", False)
+    ok &= attn_case(1, 128, 1, "random", False)
+    ok &= attn_case(1, 256, 2, "random", False)
+    ok &= attn_case(2, 300, 8, "random", True)
+    if ok:
+        ok &= attn_case(8, 1050, 8, "random", True, time_it=True)
+        ok &= attn_case(16, 4200, 8, "random", False, time_it=True) if os.environ.get("DESTR_BIG") else True
+    return ok
+
+
+def main():
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what == "simt":
+        sys.exit(0 if check_simt() else 1)
+    if what == "attn":
+        sys.exit(0 if check_attn(sys.argv[2:]) else 1)
+    rc = subprocess.call([sys.executable, __file__, "simt"], timeout=600)
+    print(f"== simt rc={rc}", flush=True)
+    configs = [[], ["2=0"], ["0=64", "1=512"], ["0=512", "1=64"], ["4=4"], ["4=16"], ["2=512"]]
+    for cfg in configs:
+        print(f"== attn knobs={cfg}", flush=True)
+        try:
+            rc2 = subprocess.call([sys.executable, __file__, "attn"] + cfg, timeout=300)
+        except subprocess.TimeoutExpired:
+            rc2 = -9
+        print(f"== attn knobs={cfg} rc={rc2}", flush=True)
+        if rc2 == 0:
+            break
+    sys.exit(0)
+
+
+if __name__ == "__main__":
+    main()
