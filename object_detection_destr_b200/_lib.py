@@ -33,6 +33,8 @@ SIGNATURES = {
     "destr_add_layernorm_fwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
     "destr_add_layernorm_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
     "destr_enc_attn_fwd": [_p, _p, _p, _i, _i, _i, _p, _i, _p, _p, _i, _i, _i, _f, _p],
+    "destr_enc_attn_bwd": [_p, _p, _p, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i,
+                           _f, _p],
     "destr_pair_indices": [_p, _p, _i, _i, _p],
     "destr_box_refine": [_p, _p, _p, _i, _p],
     "destr_match_cost_blockdiag": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _f, _i, _p],

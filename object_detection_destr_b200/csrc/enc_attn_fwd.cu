@@ -24,7 +24,7 @@
 
 namespace destr {
 
-int g_knobs[16] = {512, 512, 16, 512, 8, 1024, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+int g_knobs[16] = {512, 512, 16, 512, 8, 1024, 16384, 1024, 2048, 0, 0, 0, 0, 0, 0, 0};
 
 namespace {
 

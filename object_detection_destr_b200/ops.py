@@ -143,6 +143,23 @@ def enc_attn_fwd(q: Tensor, k: Tensor, v: Tensor, mask_bits: Tensor, B: int, N: 
     return out, lse
 
 
+def enc_attn_bwd(q: Tensor, k: Tensor, v: Tensor, mask_bits: Tensor, out: Tensor, dout: Tensor, lse: Tensor,
+                 B: int, N: int, heads: int, scale: float):
+    """Returns (dqk bf16 [B*N, 2*heads*32] = [dq | dk], dv bf16 [B*N, heads*32])."""
+    C = heads * 32
+    dout = _chk(dout.contiguous(), BF16, "dout")
+    dqk = torch.empty(B * N, 2 * C, dtype=BF16, device=q.device)
+    dv = torch.empty(B * N, C, dtype=BF16, device=q.device)
+    delta = torch.empty(B, heads, N, dtype=torch.float32, device=q.device)
+    dq_acc = torch.empty(B * N, C, dtype=torch.float32, device=q.device)
+    dq, dk = dqk[:, :C], dqk[:, C:]
+    _lib.call("destr_enc_attn_bwd", q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), k.stride(0), v.stride(0),
+              mask_bits.data_ptr(), mask_bits.shape[1], out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
+              delta.data_ptr(), dq_acc.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), 2 * C, 2 * C, C,
+              B, N, heads, float(scale), _stream())
+    return dqk, dv
+
+
 # ----------------------------------------------------------------------------------------------
 # decoder small kernels
 # ----------------------------------------------------------------------------------------------

@@ -185,6 +185,66 @@ def attn_case(B, N, heads, mode, masked, seed=0, time_it=False):
     return ok
 
 
+def attn_bwd_case(B, N, heads, masked, seed=0, time_it=False):
+    from oracle import destr_oracle as O
+    from object_detection_destr_b200 import ops
+    dev = "cuda"
+    g = torch.Generator().manual_seed(seed)
+    M, C = B * N, heads * 32
+    qk = torch.randn(M, 2 * C, generator=g).bfloat16()
+    v = torch.randn(M, C, generator=g).bfloat16()
+    dout = torch.randn(M, C, generator=g).bfloat16()
+    kpm = torch.zeros(B, N, dtype=torch.bool)
+    if masked:
+        kpm[B - 1, N // 2:] = True
+        kpm[B - 1, 3] = True
+        kpm[0, 7] = True
+    qk_d, v_d, do_d = qk.to(dev), v.to(dev), dout.to(dev)
+    bits = ops.pack_key_mask(kpm.to(dev), B, N)
+    scale = 1.0 / math.sqrt(32)
+    out, lse = ops.enc_attn_fwd(qk_d[:, :C], qk_d[:, C:], v_d, bits, B, N, heads, scale)
+    dqk, dv = ops.enc_attn_bwd(qk_d[:, :C], qk_d[:, C:], v_d, bits, out, do_d, lse, B, N, heads, scale)
+    torch.cuda.synchronize()
+    qf = qk[:, :C].float().requires_grad_()
+    kf = qk[:, C:].float().requires_grad_()
+    vf = v.float().requires_grad_()
+    split = lambda t: t.reshape(B, N, heads, 32).transpose(1, 2)
+    ref = O.sdp_attention(split(qf), split(kf), split(vf), key_padding_mask=kpm).reshape(M, C)
+    ref.backward(dout.float())
+    name = f"enc_attn_bwd B={B} N={N} h={heads} masked={masked}"
+    sc = float(qf.grad.abs().max())
+    ok = report(name + " dV", dv, vf.grad, 2e-2 * float(vf.grad.abs().max()), 2e-2)
+    ok &= report(name + " dK", dqk[:, C:], kf.grad, 2e-2 * float(kf.grad.abs().max()), 2e-2)
+    ok &= report(name + " dQ", dqk[:, :C], qf.grad, 2e-2 * sc, 2e-2)
+    if time_it:
+        for _ in range(3):
+            ops.enc_attn_bwd(qk_d[:, :C], qk_d[:, C:], v_d, bits, out, do_d, lse, B, N, heads, scale)
+        st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        st.record()
+        iters = 20
+        for _ in range(iters):
+            ops.enc_attn_bwd(qk_d[:, :C], qk_d[:, C:], v_d, bits, out, do_d, lse, B, N, heads, scale)
+        en.record()
+        torch.cuda.synchronize()
+        ms = st.elapsed_time(en) / iters
+        fl = 8.0 * N * N * C * B
+        print(f"   bwd time {ms*1e3:.1f} us  -> {fl/ms/1e9:.1f} TFLOP/s algorithmic (2x fwd flops)", flush=True)
+    return ok
+
+
+def check_attn_bwd(knobs):
+    from object_detection_destr_b200 import _lib
+    for kv in knobs:
+        i, val = kv.split("=")
+        _lib.lib.destr_debug_knob(int(i), int(val))
+    ok = attn_bwd_case(1, 128, 1, False)
+    ok &= attn_bwd_case(1, 256, 2, False)
+    ok &= attn_bwd_case(2, 300, 8, True)
+    if ok:
+        ok &= attn_bwd_case(8, 1050, 8, True, time_it=True)
+    return ok
+
+
 def check_attn(knobs):
     from object_detection_destr_b200 import _lib
     for kv in knobs:
@@ -208,6 +268,19 @@ def main():
         sys.exit(0 if check_simt() else 1)
     if what == "attn":
         sys.exit(0 if check_attn(sys.argv[2:]) else 1)
+    if what == "attnbwd":
+        sys.exit(0 if check_attn_bwd(sys.argv[2:]) else 1)
+    if what == "bwdsweep":
+        for cfg in [[], ["6=1024", "7=16384"], ["8=1024"], ["6=16384", "7=2048"], ["6=128", "7=1024"]]:
+            print(f"== attnbwd knobs={cfg}", flush=True)
+            try:
+                rc2 = subprocess.call([sys.executable, __file__, "attnbwd"] + cfg, timeout=300)
+            except subprocess.TimeoutExpired:
+                rc2 = -9
+            print(f"== attnbwd knobs={cfg} rc={rc2}", flush=True)
+            if rc2 == 0:
+                break
+        sys.exit(0)
     rc = subprocess.call([sys.executable, __file__, "simt"], timeout=600)
     print(f"== simt rc={rc}", flush=True)
     configs = [[], ["2=0"], ["0=64", "1=512"], ["0=512", "1=64"], ["4=4"], ["4=16"], ["2=512"]]
