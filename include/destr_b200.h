@@ -26,6 +26,8 @@ extern "C" {
 
 int destr_version(void);
 const char* destr_last_error(void);
+/* bring-up only: overrides UMMA descriptor fields (tools/gpu_check.py); not part of the product API */
+int destr_debug_knob(int idx, int value);
 
 /* ---------------- masks and positional embeddings ---------------- */
 
@@ -65,13 +67,18 @@ int destr_add_layernorm_fwd(const void* a, const void* b, const float* gamma, co
 int destr_add_layernorm_bwd(const void* dy, const void* a, const void* b, const float* gamma, const float* mean,
                             const float* rstd, void* dx, float* dgamma, float* dbeta, int M, int D, void* stream);
 
-/* out = lam*LN1(x+o1) + (1-lam)*LN2(x+o2)  (decoder_block.py:182-184), D = 512. */
-int destr_dual_ln_mix_fwd(const void* x, const void* o1, const void* o2, const float* g1, const float* b1,
-                          const float* g2, const float* b2, float lam, void* out, float* stats /*[M,4]*/, int M,
-                          int D, void* stream);
-int destr_dual_ln_mix_bwd(const void* dout, const void* x, const void* o1, const void* o2, const float* g1,
-                          const float* g2, const float* stats, float lam, void* dx, void* do1, void* do2,
-                          float* dg1, float* db1, float* dg2, float* db2, int M, int D, void* stream);
+/* out = lam*LN1(x+o1) + (1-lam)*LN2(x+o2eff)  (decoder_block.py:182-184), D = 512, fused with the
+ * head-group slot masking of PairSelfAttention (pair_self_attention.py:101-105):
+ *   o2eff[c] = [pairs[row,0]==i]*o2[row,c] + [pairs[row,1]==i]*o2[row,512+c],  i = row % Q.
+ * x, o1, out bf16 [M,512]; o2 bf16 [M,1024] (head-major pair-attention output); pairs int32 [M,2];
+ * stats fp32 [M,4] = mean1,rstd1,mean2,rstd2 (saved for the backward, may be NULL). */
+int destr_dual_ln_mix_fwd(const void* x, const void* o1, const void* o2, const int32_t* pairs, const float* g1,
+                          const float* b1, const float* g2, const float* b2, float lam, void* out, float* stats,
+                          int M, int Q, void* stream);
+/* backward: dx, do1 bf16 [M,512]; do2 bf16 [M,1024]; dg1,db1,dg2,db2 fp32 [512] ACCUMULATED into. */
+int destr_dual_ln_mix_bwd(const void* dout, const void* x, const void* o1, const void* o2, const int32_t* pairs,
+                          const float* g1, const float* g2, const float* stats, float lam, void* dx, void* do1,
+                          void* do2, float* dg1, float* db1, float* dg2, float* db2, int M, int Q, void* stream);
 
 /* ---------------- encoder multi-head self-attention (tcgen05) ---------------- */
 
@@ -105,15 +112,22 @@ int destr_pair_indices(const float* coords, int32_t* pairs, int B, int Q, void* 
  * inverse_sigmoid misc.py:59-62).  delta fp32 [M,4], centers fp32 [M,2] -> boxes fp32 [M,4]. */
 int destr_box_refine(const float* delta, const float* centers, float* boxes, int M, void* stream);
 
-/* Decoder self-attention (self_attention.py:26-45, 8 heads x 64) and pair self-attention
- * (pair_self_attention.py:33-105) in one launch.  q,k,v bf16 token-major [B*Q, 512] (head h =
- * columns [64h, 64h+64)); pairs from destr_pair_indices.  o1, o2 bf16 [B*Q, 512].
- * lse1/lse2 fp32 [B,8,Q] saved for the backward (may be NULL). */
-int destr_dec_self_pair_attn_fwd(const void* q, const void* k, const void* v, const int32_t* pairs, void* o1,
-                                 void* o2, float* lse1, float* lse2, int B, int Q, void* stream);
-int destr_dec_self_pair_attn_bwd(const void* q, const void* k, const void* v, const int32_t* pairs,
-                                 const void* do1, const void* do2, const float* lse1, const float* lse2,
-                                 float* dq_acc, float* dk_acc, float* dv_acc, int B, int Q, void* stream);
+/* SA operand preparation (decoder_block.py:167-177) + the left/right gathers of pair attention
+ * (pair_self_attention.py:47-89) in one pass.
+ *   qkv_obj bf16 [B*Q,1536] = [W_q x | W_k x | W_v x];  qk_pos bf16 [B*Q,512] = [W_qp p | W_kp p]
+ *   -> qkv bf16 [B*Q,1536] = [q_obj+[qp|qp] | k_obj+[kp|kp] | v]
+ *   -> cat bf16 [3][B*Q,1024]: cat[w][i, 128h .. 128h+64) = x_w[L_i, 64h..], [128h+64 .. 128h+128) = x_w[R_i, 64h..]
+ *      with (L_i, R_i) = pairs[i] (indices within the image) and x_0,x_1,x_2 = q,k,v. */
+int destr_dec_qkv_prep(const void* qkv_obj, const void* qk_pos, const int32_t* pairs, void* qkv, void* cat, int B,
+                       int Q, void* stream);
+
+/* Decoder self-attention (self_attention.py:26-45, 8 heads x 64, scale 1/8) and pair self-attention
+ * (pair_self_attention.py:91-99: softmax(Ql.Kl^T + Qr.Kr^T)/sqrt(128) . [Vl|Vr]) in ONE launch on
+ * tcgen05.  qkv / cat as written by destr_dec_qkv_prep.  o1 bf16 [B*Q,512]; o2 bf16 [B*Q,1024]
+ * (head-major, before the slot masking that destr_dual_ln_mix_fwd applies).  lse1/lse2 fp32 [B,8,Q]
+ * (log2 domain, for the backward; may be NULL).  Q <= 384. */
+int destr_dec_self_pair_attn_fwd(const void* qkv, const void* cat, void* o1, void* o2, float* lse1, float* lse2,
+                                 int B, int Q, void* stream);
 
 /* Split cross-attention of both ClsRegBranch'es (decoder_block.py:212-217, 246-251 ->
  * self_attention.py:26-45 with one head, d_qk = 512, d_v = 256, scale 1/sqrt(512)).
@@ -123,7 +137,9 @@ int destr_dec_self_pair_attn_bwd(const void* q, const void* k, const void* v, co
  *   q_pos : bf16 [B*Q, 256]   shared by both branches
  *   k_enc, k_pos, v : bf16 [B*N, 256] (row pitch ld_kv elements; may be slices of one wide GEMM output)
  *   out   : bf16 [B*Q, 512]   cls result in cols [0,256), reg result in cols [256,512)
- *   lse   : fp32 [B, 2, Q] */
+ *   lse   : fp32 [B, 2, Q] (log2 domain)
+ *   ws_partial : fp32 workspace of destr_split_cross_attn_ws_floats(B,Q,N) floats (split-KV partials) */
+int64_t destr_split_cross_attn_ws_floats(int B, int Q, int N);
 int destr_split_cross_attn_fwd(const void* q_obj, const void* q_pos, const void* k_enc, const void* k_pos,
                                const void* v, int ld_kenc, int ld_kpos, int ld_v, const uint32_t* mask_bits,
                                int words_per_row, void* out, float* lse, float* ws_partial, int B, int Q, int N,

@@ -35,6 +35,11 @@ SIGNATURES = {
     "destr_enc_attn_fwd": [_p, _p, _p, _i, _i, _i, _p, _i, _p, _p, _i, _i, _i, _f, _p],
     "destr_enc_attn_bwd": [_p, _p, _p, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i,
                            _f, _p],
+    "destr_dual_ln_mix_fwd": [_p, _p, _p, _p, _p, _p, _p, _p, _f, _p, _p, _i, _i, _p],
+    "destr_dual_ln_mix_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
+    "destr_dec_qkv_prep": [_p, _p, _p, _p, _p, _i, _i, _p],
+    "destr_dec_self_pair_attn_fwd": [_p, _p, _p, _p, _p, _p, _i, _i, _p],
+    "destr_split_cross_attn_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _p, _i, _p, _p, _p, _i, _i, _i, _f, _p],
     "destr_pair_indices": [_p, _p, _i, _i, _p],
     "destr_box_refine": [_p, _p, _p, _i, _p],
     "destr_match_cost_blockdiag": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _f, _i, _p],
@@ -44,6 +49,8 @@ for _name, _args in SIGNATURES.items():
     _fn = getattr(lib, _name)  # AttributeError here = header/library mismatch: fail loudly
     _fn.argtypes = _args
     _fn.restype = _i
+lib.destr_split_cross_attn_ws_floats.argtypes = [_i, _i, _i]
+lib.destr_split_cross_attn_ws_floats.restype = _i64
 lib.destr_last_error.argtypes = []
 lib.destr_last_error.restype = C.c_char_p
 

@@ -66,7 +66,7 @@ __device__ __forceinline__ Row<VPL> ld_vec(const float* base, int lane) {
 }
 
 template <int VPL>
-__device__ __forceinline__ void stats(const Row<VPL>& x, float& mean, float& rstd) {
+__device__ __forceinline__ void row_stats(const Row<VPL>& x, float& mean, float& rstd) {
   constexpr float invD = 1.0f / (VPL * 32);
   float s = 0.f;
 #pragma unroll
@@ -98,7 +98,7 @@ add_ln_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __re
       for (int i = 0; i < VPL; ++i) x.v[i] += r2.v[i];
     }
     float mean, rstd;
-    stats<VPL>(x, mean, rstd);
+    row_stats<VPL>(x, mean, rstd);
 #pragma unroll
     for (int i = 0; i < VPL; ++i) x.v[i] = fmaf((x.v[i] - mean) * rstd, g.v[i], be.v[i]);
     st_row<VPL>(y + (size_t)row * D, lane, x);
@@ -172,6 +172,128 @@ add_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __r
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// out = lam*LN1(x+o1) + (1-lam)*LN2(x+o2eff), D = 512  (decoder_block.py:182-184), where o2eff folds
+// the head-group slot masking of PairSelfAttention (pair_self_attention.py:101-105):
+//   o2eff[c] = [pairs[row,0]==i]*o2[c] + [pairs[row,1]==i]*o2[512+c],  i = row % Q,  o2 is [M,1024].
+// stats[row] = {mean1, rstd1, mean2, rstd2}.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dual_ln_mix_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ o1,
+                       const __nv_bfloat16* __restrict__ o2, const int32_t* __restrict__ pairs,
+                       const float* __restrict__ g1, const float* __restrict__ b1, const float* __restrict__ g2,
+                       const float* __restrict__ b2, float lam, __nv_bfloat16* __restrict__ out,
+                       float* __restrict__ stats, int M, int Q) {
+  constexpr int VPL = 16, D = 512;
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const Row<VPL> G1 = ld_vec<VPL>(g1, lane), B1 = ld_vec<VPL>(b1, lane);
+  const Row<VPL> G2 = ld_vec<VPL>(g2, lane), B2 = ld_vec<VPL>(b2, lane);
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += gridDim.x * wpb) {
+    const int i = row % Q;
+    const float k0 = pairs[2 * row] == i ? 1.f : 0.f, k1 = pairs[2 * row + 1] == i ? 1.f : 0.f;
+    const Row<VPL> xr = ld_row<VPL>(x + (size_t)row * D, lane);
+    Row<VPL> u = ld_row<VPL>(o1 + (size_t)row * D, lane);
+    const Row<VPL> a = ld_row<VPL>(o2 + (size_t)row * 2 * D, lane);
+    const Row<VPL> c = ld_row<VPL>(o2 + (size_t)row * 2 * D + D, lane);
+    Row<VPL> w;
+#pragma unroll
+    for (int e = 0; e < VPL; ++e) {
+      u.v[e] += xr.v[e];
+      w.v[e] = xr.v[e] + (k0 * a.v[e] + k1 * c.v[e]);
+    }
+    float m1, r1, m2, r2;
+    row_stats<VPL>(u, m1, r1);
+    row_stats<VPL>(w, m2, r2);
+    Row<VPL> o;
+#pragma unroll
+    for (int e = 0; e < VPL; ++e) {
+      const float y1 = fmaf((u.v[e] - m1) * r1, G1.v[e], B1.v[e]);
+      const float y2 = fmaf((w.v[e] - m2) * r2, G2.v[e], B2.v[e]);
+      o.v[e] = lam * y1 + (1.f - lam) * y2;
+    }
+    st_row<VPL>(out + (size_t)row * D, lane, o);
+    if (stats && lane == 0) reinterpret_cast<float4*>(stats)[row] = make_float4(m1, r1, m2, r2);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+dual_ln_mix_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ x,
+                       const __nv_bfloat16* __restrict__ o1, const __nv_bfloat16* __restrict__ o2,
+                       const int32_t* __restrict__ pairs, const float* __restrict__ g1,
+                       const float* __restrict__ g2, const float* __restrict__ stats, float lam,
+                       __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ do1,
+                       __nv_bfloat16* __restrict__ do2, float* __restrict__ dg1, float* __restrict__ db1,
+                       float* __restrict__ dg2, float* __restrict__ db2, int M, int Q) {
+  constexpr int VPL = 16, D = 512;
+  constexpr float invD = 1.0f / D;
+  extern __shared__ float red[];  // [4][warps][D]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wpb = blockDim.x >> 5;
+  const Row<VPL> G1 = ld_vec<VPL>(g1, lane), G2 = ld_vec<VPL>(g2, lane);
+  Row<VPL> ag1, ab1, ag2, ab2;
+#pragma unroll
+  for (int e = 0; e < VPL; ++e) ag1.v[e] = ab1.v[e] = ag2.v[e] = ab2.v[e] = 0.f;
+  for (int row = blockIdx.x * wpb + warp; row < M; row += gridDim.x * wpb) {
+    const int i = row % Q;
+    const float k0 = pairs[2 * row] == i ? 1.f : 0.f, k1 = pairs[2 * row + 1] == i ? 1.f : 0.f;
+    const Row<VPL> xr = ld_row<VPL>(x + (size_t)row * D, lane);
+    Row<VPL> u = ld_row<VPL>(o1 + (size_t)row * D, lane);
+    const Row<VPL> a = ld_row<VPL>(o2 + (size_t)row * 2 * D, lane);
+    const Row<VPL> c = ld_row<VPL>(o2 + (size_t)row * 2 * D + D, lane);
+    const Row<VPL> d = ld_row<VPL>(dout + (size_t)row * D, lane);
+    const float4 st = reinterpret_cast<const float4*>(stats)[row];
+    Row<VPL> w;
+    float s11 = 0.f, s12 = 0.f, s21 = 0.f, s22 = 0.f;
+#pragma unroll
+    for (int e = 0; e < VPL; ++e) {
+      u.v[e] = (u.v[e] + xr.v[e] - st.x) * st.y;                                   // xhat1
+      w.v[e] = (xr.v[e] + (k0 * a.v[e] + k1 * c.v[e]) - st.z) * st.w;              // xhat2
+      const float d1 = lam * d.v[e], d2 = (1.f - lam) * d.v[e];
+      const float gy1 = d1 * G1.v[e], gy2 = d2 * G2.v[e];
+      s11 += gy1; s12 = fmaf(gy1, u.v[e], s12);
+      s21 += gy2; s22 = fmaf(gy2, w.v[e], s22);
+      ag1.v[e] = fmaf(d1, u.v[e], ag1.v[e]); ab1.v[e] += d1;
+      ag2.v[e] = fmaf(d2, w.v[e], ag2.v[e]); ab2.v[e] += d2;
+    }
+    s11 = warp_sum(s11) * invD; s12 = warp_sum(s12) * invD;
+    s21 = warp_sum(s21) * invD; s22 = warp_sum(s22) * invD;
+    Row<VPL> r1, r2, rx, ra, rc;
+#pragma unroll
+    for (int e = 0; e < VPL; ++e) {
+      r1.v[e] = st.y * (lam * d.v[e] * G1.v[e] - s11 - u.v[e] * s12);
+      r2.v[e] = st.w * ((1.f - lam) * d.v[e] * G2.v[e] - s21 - w.v[e] * s22);
+      rx.v[e] = r1.v[e] + r2.v[e];
+      ra.v[e] = k0 * r2.v[e];
+      rc.v[e] = k1 * r2.v[e];
+    }
+    st_row<VPL>(dx + (size_t)row * D, lane, rx);
+    st_row<VPL>(do1 + (size_t)row * D, lane, r1);
+    st_row<VPL>(do2 + (size_t)row * 2 * D, lane, ra);
+    st_row<VPL>(do2 + (size_t)row * 2 * D + D, lane, rc);
+  }
+  float* R[4] = {red, red + wpb * D, red + 2 * wpb * D, red + 3 * wpb * D};
+#pragma unroll
+  for (int c = 0; c < VPL / 8; ++c)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int ch = (c * 32 + lane) * 8 + e;
+      R[0][warp * D + ch] = ag1.v[c * 8 + e];
+      R[1][warp * D + ch] = ab1.v[c * 8 + e];
+      R[2][warp * D + ch] = ag2.v[c * 8 + e];
+      R[3][warp * D + ch] = ab2.v[c * 8 + e];
+    }
+  __syncthreads();
+  float* outp[4] = {dg1, db1, dg2, db2};
+  for (int idx = threadIdx.x; idx < 4 * D; idx += blockDim.x) {
+    const int which = idx / D, ch = idx - which * D;
+    float s = 0.f;
+    for (int w2 = 0; w2 < wpb; ++w2) s += R[which][w2 * D + ch];
+    atomicAdd(outp[which] + ch, s);
+  }
+}
+
 inline int ln_grid(int M) {
   int blocks = ceil_div(M, 8);
   const int cap = kSMs * 4;
@@ -214,6 +336,33 @@ extern "C" int destr_add_layernorm_bwd(const void* dy, const void* a, const void
     add_ln_bwd_kernel<16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)a,
                                                 (const __nv_bfloat16*)b, gamma, mean, rstd, (__nv_bfloat16*)dx, dgamma,
                                                 dbeta, M);
+  DESTR_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int destr_dual_ln_mix_fwd(const void* x, const void* o1, const void* o2, const int32_t* pairs,
+                                     const float* g1, const float* b1, const float* g2, const float* b2, float lam,
+                                     void* out, float* stats, int M, int Q, void* stream) {
+  DESTR_CHECK_ARG(x && o1 && o2 && pairs && g1 && b1 && g2 && b2 && out && M > 0 && Q > 0, "null pointer / shape");
+  dual_ln_mix_fwd_kernel<<<ln_grid(M), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, (const __nv_bfloat16*)o1, (const __nv_bfloat16*)o2, pairs, g1, b1, g2, b2, lam,
+      (__nv_bfloat16*)out, stats, M, Q);
+  DESTR_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int destr_dual_ln_mix_bwd(const void* dout, const void* x, const void* o1, const void* o2,
+                                     const int32_t* pairs, const float* g1, const float* g2, const float* stats,
+                                     float lam, void* dx, void* do1, void* do2, float* dg1, float* db1, float* dg2,
+                                     float* db2, int M, int Q, void* stream) {
+  DESTR_CHECK_ARG(dout && x && o1 && o2 && pairs && g1 && g2 && stats && dx && do1 && do2 && dg1 && db1 && dg2 && db2,
+                  "null pointer");
+  const int threads = 128;  // 4 warps -> 4*4*512*4 B = 32 KB of reduction scratch
+  int grid = ceil_div(M, 4);
+  if (grid > kSMs * 2) grid = kSMs * 2;
+  dual_ln_mix_bwd_kernel<<<grid, threads, 4 * 4 * 512 * sizeof(float), (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dout, (const __nv_bfloat16*)x, (const __nv_bfloat16*)o1, (const __nv_bfloat16*)o2, pairs,
+      g1, g2, stats, lam, (__nv_bfloat16*)dx, (__nv_bfloat16*)do1, (__nv_bfloat16*)do2, dg1, db1, dg2, db2, M, Q);
   DESTR_LAUNCH_CHECK();
   return 0;
 }

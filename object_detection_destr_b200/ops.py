@@ -180,6 +180,68 @@ def box_refine(delta: Tensor, centers: Tensor) -> Tensor:
     return out
 
 
+def dec_qkv_prep(qkv_obj: Tensor, qk_pos: Tensor, pairs: Tensor, B: int, Q: int):
+    """-> (qkv bf16 [B*Q,1536], cat bf16 [3, B*Q, 1024])."""
+    qkv_obj, qk_pos = _chk(qkv_obj.contiguous(), BF16, "qkv_obj"), _chk(qk_pos.contiguous(), BF16, "qk_pos")
+    pairs = _chk(pairs.contiguous(), torch.int32, "pairs")
+    qkv = torch.empty(B * Q, 1536, dtype=BF16, device=qkv_obj.device)
+    cat = torch.empty(3, B * Q, 1024, dtype=BF16, device=qkv_obj.device)
+    _lib.call("destr_dec_qkv_prep", qkv_obj.data_ptr(), qk_pos.data_ptr(), pairs.data_ptr(), qkv.data_ptr(),
+              cat.data_ptr(), B, Q, _stream())
+    return qkv, cat
+
+
+def dec_self_pair_attn_fwd(qkv: Tensor, cat: Tensor, B: int, Q: int, need_lse: bool = True):
+    """-> (o1 bf16 [B*Q,512], o2 bf16 [B*Q,1024], lse1, lse2 fp32 [B,8,Q])."""
+    o1 = torch.empty(B * Q, 512, dtype=BF16, device=qkv.device)
+    o2 = torch.empty(B * Q, 1024, dtype=BF16, device=qkv.device)
+    lse1 = torch.empty(B, 8, Q, dtype=torch.float32, device=qkv.device) if need_lse else None
+    lse2 = torch.empty(B, 8, Q, dtype=torch.float32, device=qkv.device) if need_lse else None
+    _lib.call("destr_dec_self_pair_attn_fwd", _chk(qkv, BF16, "qkv").data_ptr(), _chk(cat, BF16, "cat").data_ptr(),
+              o1.data_ptr(), o2.data_ptr(), _ptr(lse1), _ptr(lse2), B, Q, _stream())
+    return o1, o2, lse1, lse2
+
+
+def dual_ln_mix(x: Tensor, o1: Tensor, o2: Tensor, pairs: Tensor, g1, b1, g2, b2, lam: float, Q: int,
+                save_stats: bool = True):
+    x, o1, o2 = (_chk(t.contiguous(), BF16, n) for t, n in ((x, "x"), (o1, "o1"), (o2, "o2")))
+    M = x.shape[0]
+    out = torch.empty_like(x)
+    stats = torch.empty(M, 4, dtype=torch.float32, device=x.device) if save_stats else None
+    _lib.call("destr_dual_ln_mix_fwd", x.data_ptr(), o1.data_ptr(), o2.data_ptr(), pairs.data_ptr(), g1.data_ptr(),
+              b1.data_ptr(), g2.data_ptr(), b2.data_ptr(), float(lam), out.data_ptr(), _ptr(stats), M, Q, _stream())
+    return out, stats
+
+
+def dual_ln_mix_bwd(dout: Tensor, x: Tensor, o1: Tensor, o2: Tensor, pairs: Tensor, g1, g2, stats, lam: float, Q: int):
+    dout = _chk(dout.contiguous(), BF16, "dout")
+    M = x.shape[0]
+    dx, do1, do2 = torch.empty_like(x), torch.empty_like(o1), torch.empty_like(o2)
+    pg = torch.zeros(4, 512, dtype=torch.float32, device=x.device)
+    _lib.call("destr_dual_ln_mix_bwd", dout.data_ptr(), x.data_ptr(), o1.data_ptr(), o2.data_ptr(), pairs.data_ptr(),
+              g1.data_ptr(), g2.data_ptr(), stats.data_ptr(), float(lam), dx.data_ptr(), do1.data_ptr(),
+              do2.data_ptr(), pg[0].data_ptr(), pg[1].data_ptr(), pg[2].data_ptr(), pg[3].data_ptr(), M, Q, _stream())
+    return dx, do1, do2, pg[0], pg[1], pg[2], pg[3]
+
+
+def split_cross_attn_fwd(q_obj: Tensor, q_pos: Tensor, k_enc: Tensor, k_pos: Tensor, v: Tensor, mask_bits: Tensor,
+                         B: int, Q: int, N: int, need_lse: bool = True):
+    """q_obj bf16 [B*Q,512], q_pos bf16 [B*Q,256], k_enc/k_pos/v bf16 [B*N,256] views (unit column stride).
+    -> (out bf16 [B*Q,512] = [cls|reg], lse fp32 [B,2,Q])."""
+    q_obj, q_pos = _chk(q_obj.contiguous(), BF16, "q_obj"), _chk(q_pos.contiguous(), BF16, "q_pos")
+    for t, n in ((k_enc, "k_enc"), (k_pos, "k_pos"), (v, "v")):
+        _chk(t, BF16, n)
+        if t.dim() != 2 or t.stride(1) != 1 or t.shape != (B * N, 256):
+            raise ValueError(f"{n}: expected a [B*N,256] view with unit column stride")
+    out = torch.empty(B * Q, 512, dtype=BF16, device=q_obj.device)
+    lse = torch.empty(B, 2, Q, dtype=torch.float32, device=q_obj.device) if need_lse else None
+    ws = torch.empty(_lib.lib.destr_split_cross_attn_ws_floats(B, Q, N), dtype=torch.float32, device=q_obj.device)
+    _lib.call("destr_split_cross_attn_fwd", q_obj.data_ptr(), q_pos.data_ptr(), k_enc.data_ptr(), k_pos.data_ptr(),
+              v.data_ptr(), k_enc.stride(0), k_pos.stride(0), v.stride(0), mask_bits.data_ptr(), mask_bits.shape[1],
+              out.data_ptr(), _ptr(lse), ws.data_ptr(), B, Q, N, 1.0 / math.sqrt(512.0), _stream())
+    return out, lse
+
+
 # ----------------------------------------------------------------------------------------------
 # matcher cost
 # ----------------------------------------------------------------------------------------------

@@ -129,6 +129,101 @@ def check_simt():
     return ok
 
 
+def check_decoder_kernels(B=2, Q=100, N=300):
+    """dec_qkv_prep + dec_self_pair_attn_fwd + dual_ln_mix fwd/bwd + split_cross_attn_fwd vs the oracle."""
+    from oracle import destr_oracle as O
+    from object_detection_destr_b200 import ops
+    dev = "cuda"
+    g = torch.Generator().manual_seed(7)
+    ok = True
+    M = B * Q
+    qkv_obj = (torch.randn(M, 1536, generator=g) * 0.7).bfloat16()
+    qk_pos = (torch.randn(M, 512, generator=g) * 0.7).bfloat16()
+    coords = torch.cat([0.1 + 0.8 * torch.rand(B, Q, 2, generator=g), 0.03 + 0.4 * torch.rand(B, Q, 2, generator=g)], -1)
+    coords[0, :, 2:] *= 0.1  # tiny boxes -> self pairs
+    pairs = O.get_pairs(coords)
+    pairs_d = ops.pair_indices(coords.to(dev))
+    assert torch.equal(pairs_d.cpu().long(), pairs)
+    qkv, cat = ops.dec_qkv_prep(qkv_obj.to(dev), qk_pos.to(dev), pairs_d, B, Q)
+    # reference of the prep
+    qf = qkv_obj[:, :512].float() + torch.cat([qk_pos[:, :256], qk_pos[:, :256]], -1).float()
+    kf = qkv_obj[:, 512:1024].float() + torch.cat([qk_pos[:, 256:], qk_pos[:, 256:]], -1).float()
+    vf = qkv_obj[:, 1024:].float()
+    ok &= report("dec_qkv_prep q", qkv[:, :512], qf, 0, 8e-3)
+    ok &= report("dec_qkv_prep k", qkv[:, 512:1024], kf, 0, 8e-3)
+    ok &= report("dec_qkv_prep v", qkv[:, 1024:], vf, 0, 0)
+    qb, kb, vb = (t.float().cpu() for t in (qkv[:, :512], qkv[:, 512:1024], qkv[:, 1024:]))  # bf16-rounded
+    heads = lambda t: t.reshape(B, Q, 8, 64).transpose(1, 2)
+    q4, k4, v4 = heads(qb), heads(kb), heads(vb)
+    gidx = lambda col: (pairs[..., col] + torch.arange(B)[:, None] * Q).reshape(-1)
+    for w, t in enumerate((qb, kb, vb)):
+        ref_cat = torch.cat([t[gidx(0)].reshape(M, 8, 64), t[gidx(1)].reshape(M, 8, 64)], -1).reshape(M, 1024)
+        ok &= report(f"dec_qkv_prep cat[{w}]", cat[w], ref_cat, 0, 0)
+    o1, o2, lse1, lse2 = ops.dec_self_pair_attn_fwd(qkv, cat, B, Q)
+    torch.cuda.synchronize()
+    ref1 = O.sdp_attention(q4, k4, v4).reshape(M, 512)
+    ok &= report(f"dec self-attn o1 Q={Q}", o1, ref1, 1e-2, 2e-2)
+    # full (unmasked) pair attention output, head-major [M, 8*128]
+    take = lambda t, col: t.gather(2, pairs[:, None, :, col, None].expand(B, 8, Q, 64))
+    a2 = torch.einsum("bhqd,bhkd->bhqk", take(q4, 0), take(k4, 0)) + torch.einsum("bhqd,bhkd->bhqk", take(q4, 1), take(k4, 1))
+    p2 = a2.softmax(-1) / math.sqrt(128)
+    ref2 = torch.einsum("bhqk,bhkd->bqhd", p2, torch.cat([take(v4, 0), take(v4, 1)], -1)).reshape(M, 1024)
+    ok &= report(f"dec pair-attn o2 Q={Q}", o2, ref2, 2e-3, 2e-2)
+    ok &= report("dec lse1", lse1, torch.logsumexp(torch.einsum("bhqd,bhkd->bhqk", q4, k4) / 8, -1) * 1.4426950408889634, 2e-2, 1e-3)
+    ok &= report("dec lse2", lse2, torch.logsumexp(a2, -1) * 1.4426950408889634, 2e-2, 1e-3)
+
+    # dual_ln_mix fwd/bwd (with slot masking) vs autograd
+    x = torch.randn(M, 512, generator=g).bfloat16()
+    g1, b1, g2, b2 = (1 + 0.1 * torch.randn(512, generator=g), 0.1 * torch.randn(512, generator=g),
+                      1 + 0.1 * torch.randn(512, generator=g), 0.1 * torch.randn(512, generator=g))
+    o1c, o2c = o1.float().cpu(), (o2.float().cpu() * 8)  # bf16-exact inputs; o2 scaled up to be LN-relevant
+    o2s = o2c.bfloat16()
+    dout = torch.randn(M, 512, generator=g).bfloat16()
+    xr, o1r, o2r = x.float().requires_grad_(), o1c.clone().requires_grad_(), o2s.float().requires_grad_()
+    pr = [t.clone().requires_grad_() for t in (g1, b1, g2, b2)]
+    me = torch.arange(Q).repeat(B)
+    keep = (pairs.reshape(M, 2) == me[:, None]).float()
+    o2eff = o2r[:, :512] * keep[:, :1] + o2r[:, 512:] * keep[:, 1:]
+    LN = torch.nn.functional.layer_norm
+    ref = 0.5 * LN(xr + o1r, (512,), pr[0], pr[1], 1e-5) + 0.5 * LN(xr + o2eff, (512,), pr[2], pr[3], 1e-5)
+    ref.backward(dout.float())
+    dev_p = [t.to(dev) for t in (g1, b1, g2, b2)]
+    out, stats = ops.dual_ln_mix(x.to(dev), o1, o2s.to(dev), pairs_d, *dev_p, 0.5, Q)
+    ok &= report("dual_ln_mix fwd", out, ref, 2e-2, 8e-3)
+    dx, do1, do2, dg1, db1, dg2, db2 = ops.dual_ln_mix_bwd(dout.to(dev), x.to(dev), o1, o2s.to(dev), pairs_d,
+                                                           dev_p[0], dev_p[2], stats, 0.5, Q)
+    ok &= report("dual_ln_mix bwd dx", dx, xr.grad, 2e-2, 1e-2)
+    ok &= report("dual_ln_mix bwd do1", do1, o1r.grad, 2e-2, 1e-2)
+    ok &= report("dual_ln_mix bwd do2", do2, o2r.grad, 2e-2, 1e-2)
+    for nm, got, rf in (("dg1", dg1, pr[0].grad), ("db1", db1, pr[1].grad), ("dg2", dg2, pr[2].grad), ("db2", db2, pr[3].grad)):
+        ok &= report("dual_ln_mix bwd " + nm, got, rf, 1e-2, 3e-3)
+
+    # split cross attention
+    q_obj = (torch.randn(M, 512, generator=g) * 0.8).bfloat16()
+    q_pos = (torch.randn(M, 256, generator=g) * 0.8).bfloat16()
+    kv = (torch.randn(B * N, 768, generator=g) * 0.8).bfloat16()  # k_enc | v | k_pos packed: strided views
+    kpm = torch.zeros(B, N, dtype=torch.bool)
+    kpm[B - 1, N - 70:] = True
+    kpm[0, 5] = True
+    bits = ops.pack_key_mask(kpm.to(dev), B, N)
+    kv_d = kv.to(dev)
+    out, lse = ops.split_cross_attn_fwd(q_obj.to(dev), q_pos.to(dev), kv_d[:, :256], kv_d[:, 512:], kv_d[:, 256:512],
+                                        bits, B, Q, N)
+    torch.cuda.synchronize()
+    kenc, vv, kpos = (kv[:, :256].float().reshape(B, N, 256), kv[:, 256:512].float().reshape(B, N, 256),
+                      kv[:, 512:].float().reshape(B, N, 256))
+    qo, qp = q_obj.float().reshape(B, Q, 512), q_pos.float().reshape(B, Q, 256)
+    refs = []
+    for br in range(2):
+        # through the oracle's own interleaved formulation (validates the no-shuffle identity too)
+        qq = O._interleave_heads(qo[..., br * 256:(br + 1) * 256], qp, 8)
+        kk = O._interleave_heads(kenc, kpos, 8)
+        refs.append(O.sdp_attention(qq[:, None], kk[:, None], vv[:, None], key_padding_mask=kpm))
+    refc = torch.cat(refs, -1).reshape(M, 512)
+    ok &= report(f"split_cross_attn fwd Q={Q} N={N}", out, refc, 1e-2, 2e-2)
+    return ok
+
+
 def attn_case(B, N, heads, mode, masked, seed=0, time_it=False):
     from oracle import destr_oracle as O
     from object_detection_destr_b200 import ops
@@ -268,6 +363,11 @@ def main():
         sys.exit(0 if check_simt() else 1)
     if what == "attn":
         sys.exit(0 if check_attn(sys.argv[2:]) else 1)
+    if what == "dec":
+        ok = check_decoder_kernels(2, 100, 300)
+        ok &= check_decoder_kernels(1, 300, 1050)
+        ok &= check_decoder_kernels(3, 40, 54)
+        sys.exit(0 if ok else 1)
     if what == "attnbwd":
         sys.exit(0 if check_attn_bwd(sys.argv[2:]) else 1)
     if what == "bwdsweep":
