@@ -56,16 +56,17 @@ int destr_pos_mul_add_bwd(const void* dy, const void* pos, void* ds, int64_t n_e
 int destr_mul_fwd(const void* a, const void* b, void* y, int64_t n_elem, void* stream);
 
 /* y = LayerNorm(a + b) * gamma + beta over the last dim D (256 or 512), eps 1e-5
- * (encoder_block.py:104-110, :40; decoder_block.py:65, 253-258).  a, b, y bf16 [M,D]; gamma/beta
- * fp32 [D].  Optionally chains a second LN in the same pass: y2 = LayerNorm(c + y) (encoder
- * outer residual + shared norm, encoder_block.py:40): pass c/gamma2/beta2/y2 non-NULL.
+ * (encoder_block.py:104-110, :40; decoder_block.py:65, 253-258).  a, b, y bf16 rows of D channels
+ * with row pitches lda/ldb/ldy elements (so the 256-wide cls/reg halves of a [M,512] tensor can be
+ * normalised in place, decoder_block.py:185-187,218); b may be NULL; gamma/beta fp32 [D].
  * Saves mean/rstd (fp32 [M]) for the backward when the pointers are non-NULL. */
-int destr_add_layernorm_fwd(const void* a, const void* b, const float* gamma, const float* beta, void* y,
-                            float* mean, float* rstd, int M, int D, void* stream);
-/* backward of y = LN(a+b): dx (bf16 [M,D]) = d(a+b); dgamma/dbeta fp32 [D] are ACCUMULATED into
- * (caller zeroes).  xsum = a+b is recomputed from a and b. */
-int destr_add_layernorm_bwd(const void* dy, const void* a, const void* b, const float* gamma, const float* mean,
-                            const float* rstd, void* dx, float* dgamma, float* dbeta, int M, int D, void* stream);
+int destr_add_layernorm_fwd(const void* a, int lda, const void* b, int ldb, const float* gamma, const float* beta,
+                            void* y, int ldy, float* mean, float* rstd, int M, int D, void* stream);
+/* backward of y = LN(a+b): dx (bf16, pitch lddx) = d(a+b); dgamma/dbeta fp32 [D] are ACCUMULATED into
+ * (caller zeroes).  a+b is recomputed from a and b. */
+int destr_add_layernorm_bwd(const void* dy, int lddy, const void* a, int lda, const void* b, int ldb,
+                            const float* gamma, const float* mean, const float* rstd, void* dx, int lddx,
+                            float* dgamma, float* dbeta, int M, int D, void* stream);
 
 /* out = lam*LN1(x+o1) + (1-lam)*LN2(x+o2eff)  (decoder_block.py:182-184), D = 512, fused with the
  * head-group slot masking of PairSelfAttention (pair_self_attention.py:101-105):

@@ -30,8 +30,8 @@ SIGNATURES = {
     "destr_pos_mul_add_fwd": [_p, _p, _p, _p, _i64, _p],
     "destr_pos_mul_add_bwd": [_p, _p, _p, _i64, _p],
     "destr_mul_fwd": [_p, _p, _p, _i64, _p],
-    "destr_add_layernorm_fwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
-    "destr_add_layernorm_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
+    "destr_add_layernorm_fwd": [_p, _i, _p, _i, _p, _p, _p, _i, _p, _p, _i, _i, _p],
+    "destr_add_layernorm_bwd": [_p, _i, _p, _i, _p, _i, _p, _p, _p, _p, _i, _p, _p, _i, _i, _p],
     "destr_enc_attn_fwd": [_p, _p, _p, _i, _i, _i, _p, _i, _p, _p, _i, _i, _i, _f, _p],
     "destr_enc_attn_bwd": [_p, _p, _p, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i,
                            _f, _p],

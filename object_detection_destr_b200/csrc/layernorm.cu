@@ -85,15 +85,14 @@ template <int VPL>
 __global__ void __launch_bounds__(256)
 add_ln_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
                   const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
-                  float* __restrict__ mean_out, float* __restrict__ rstd_out, int M) {
-  constexpr int D = VPL * 32;
+                  float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int lda, int ldb, int ldy) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const Row<VPL> g = ld_vec<VPL>(gamma, lane), be = ld_vec<VPL>(beta, lane);
   for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += gridDim.x * wpb) {
-    Row<VPL> x = ld_row<VPL>(a + (size_t)row * D, lane);
+    Row<VPL> x = ld_row<VPL>(a + (size_t)row * lda, lane);
     if (b) {
-      const Row<VPL> r2 = ld_row<VPL>(b + (size_t)row * D, lane);
+      const Row<VPL> r2 = ld_row<VPL>(b + (size_t)row * ldb, lane);
 #pragma unroll
       for (int i = 0; i < VPL; ++i) x.v[i] += r2.v[i];
     }
@@ -101,7 +100,7 @@ add_ln_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __re
     row_stats<VPL>(x, mean, rstd);
 #pragma unroll
     for (int i = 0; i < VPL; ++i) x.v[i] = fmaf((x.v[i] - mean) * rstd, g.v[i], be.v[i]);
-    st_row<VPL>(y + (size_t)row * D, lane, x);
+    st_row<VPL>(y + (size_t)row * ldy, lane, x);
     if (mean_out && lane == 0) {
       mean_out[row] = mean;
       rstd_out[row] = rstd;
@@ -115,7 +114,8 @@ __global__ void __launch_bounds__(256)
 add_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ a,
                   const __nv_bfloat16* __restrict__ b, const float* __restrict__ gamma,
                   const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
-                  __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int M) {
+                  __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int M,
+                  int lddy, int lda, int ldb, int lddx) {
   constexpr int D = VPL * 32;
   constexpr float invD = 1.0f / D;
   __shared__ float red[2][8][D];  // [dgamma|dbeta][warp][channel]  (<= 32 KB at D=512)
@@ -127,13 +127,13 @@ add_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __r
 #pragma unroll
   for (int i = 0; i < VPL; ++i) accg.v[i] = accb.v[i] = 0.f;
   for (int row = blockIdx.x * wpb + warp; row < M; row += gridDim.x * wpb) {
-    Row<VPL> x = ld_row<VPL>(a + (size_t)row * D, lane);
+    Row<VPL> x = ld_row<VPL>(a + (size_t)row * lda, lane);
     if (b) {
-      const Row<VPL> r2 = ld_row<VPL>(b + (size_t)row * D, lane);
+      const Row<VPL> r2 = ld_row<VPL>(b + (size_t)row * ldb, lane);
 #pragma unroll
       for (int i = 0; i < VPL; ++i) x.v[i] += r2.v[i];
     }
-    const Row<VPL> d = ld_row<VPL>(dy + (size_t)row * D, lane);
+    const Row<VPL> d = ld_row<VPL>(dy + (size_t)row * lddy, lane);
     const float mean = mean_in[row], rstd = rstd_in[row];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -150,7 +150,7 @@ add_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __r
     Row<VPL> o;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) o.v[i] = rstd * (d.v[i] * g.v[i] - s1 - x.v[i] * s2);
-    st_row<VPL>(dx + (size_t)row * D, lane, o);
+    st_row<VPL>(dx + (size_t)row * lddx, lane, o);
   }
   // block reduction of the parameter gradients, then one atomic per channel per block
 #pragma unroll
@@ -305,25 +305,28 @@ inline int ln_grid(int M) {
 
 using namespace destr;
 
-extern "C" int destr_add_layernorm_fwd(const void* a, const void* b, const float* gamma, const float* beta, void* y,
-                                       float* mean, float* rstd, int M, int D, void* stream) {
+extern "C" int destr_add_layernorm_fwd(const void* a, int lda, const void* b, int ldb, const float* gamma,
+                                       const float* beta, void* y, int ldy, float* mean, float* rstd, int M, int D,
+                                       void* stream) {
+  DESTR_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && ldy % 8 == 0 && lda >= D && ldy >= D, "row pitch");
   DESTR_CHECK_ARG(a && gamma && beta && y && M > 0, "null pointer / shape");
   DESTR_CHECK_ARG(D == 256 || D == 512, "D must be 256 or 512");
   DESTR_CHECK_ARG((mean == nullptr) == (rstd == nullptr), "mean and rstd go together");
   cudaStream_t st = (cudaStream_t)stream;
   if (D == 256)
     add_ln_fwd_kernel<8><<<ln_grid(M), 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, gamma, beta,
-                                                     (__nv_bfloat16*)y, mean, rstd, M);
+                                                     (__nv_bfloat16*)y, mean, rstd, M, lda, ldb, ldy);
   else
     add_ln_fwd_kernel<16><<<ln_grid(M), 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, gamma, beta,
-                                                      (__nv_bfloat16*)y, mean, rstd, M);
+                                                      (__nv_bfloat16*)y, mean, rstd, M, lda, ldb, ldy);
   DESTR_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int destr_add_layernorm_bwd(const void* dy, const void* a, const void* b, const float* gamma,
-                                       const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
-                                       int M, int D, void* stream) {
+extern "C" int destr_add_layernorm_bwd(const void* dy, int lddy, const void* a, int lda, const void* b, int ldb,
+                                       const float* gamma, const float* mean, const float* rstd, void* dx, int lddx,
+                                       float* dgamma, float* dbeta, int M, int D, void* stream) {
+  DESTR_CHECK_ARG(lddy % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && lddx % 8 == 0, "row pitch");
   DESTR_CHECK_ARG(dy && a && gamma && mean && rstd && dx && dgamma && dbeta && M > 0, "null pointer / shape");
   DESTR_CHECK_ARG(D == 256 || D == 512, "D must be 256 or 512");
   cudaStream_t st = (cudaStream_t)stream;
@@ -331,11 +334,11 @@ extern "C" int destr_add_layernorm_bwd(const void* dy, const void* a, const void
   if (D == 256)
     add_ln_bwd_kernel<8><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)a,
                                                (const __nv_bfloat16*)b, gamma, mean, rstd, (__nv_bfloat16*)dx, dgamma,
-                                               dbeta, M);
+                                               dbeta, M, lddy, lda, ldb, lddx);
   else
     add_ln_bwd_kernel<16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)a,
                                                 (const __nv_bfloat16*)b, gamma, mean, rstd, (__nv_bfloat16*)dx, dgamma,
-                                                dbeta, M);
+                                                dbeta, M, lddy, lda, ldb, lddx);
   DESTR_LAUNCH_CHECK();
   return 0;
 }

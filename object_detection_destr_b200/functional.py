@@ -118,3 +118,164 @@ def encoder_tokens(x: Tensor, pos: Tensor, bits: Tensor, p: Dict[str, Tensor], n
     for l in range(num_layers):
         x = encoder_layer(x, pos, bits, p, f"_encoder.{l}.", B, N)
     return x
+
+
+# ----------------------------------------------------------------------------------------------
+# decoder  (reference: src/model/blocks/decoder_block.py)
+# ----------------------------------------------------------------------------------------------
+class _MulConst(torch.autograd.Function):
+    """y = a * c with c constant (sin_embed = sine * pos_scale(x_reg), decoder_block.py:49)."""
+
+    @staticmethod
+    def forward(ctx, a, c):
+        ctx.save_for_backward(c)
+        return ops.mul(a, c)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (c,) = ctx.saved_tensors
+        return ops.mul(dy.contiguous(), c), None
+
+
+class _DualLnMix(torch.autograd.Function):
+    """lam*LN1(x+o1) + (1-lam)*LN2(x+o2eff) with the pair-attention slot masking fused."""
+
+    @staticmethod
+    def forward(ctx, x, o1, o2, pairs, g1, b1, g2, b2, lam, Q):
+        out, stats = ops.dual_ln_mix(x, o1, o2, pairs, g1, b1, g2, b2, lam, Q)
+        ctx.save_for_backward(x, o1, o2, pairs, g1, g2, stats)
+        ctx.lam, ctx.Q = lam, Q
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, o1, o2, pairs, g1, g2, stats = ctx.saved_tensors
+        dx, do1, do2, dg1, db1, dg2, db2 = ops.dual_ln_mix_bwd(dout, x, o1, o2, pairs, g1, g2, stats, ctx.lam, ctx.Q)
+        return dx, do1, do2, None, dg1, db1, dg2, db2, None, None
+
+
+class _DecQkvPrep(torch.autograd.Function):
+    """q/k position add + left/right pair gathers (decoder_block.py:167-177, pair_self_attention.py:47-89)."""
+
+    @staticmethod
+    def forward(ctx, qkv_obj, qk_pos, pairs, B, Q):
+        qkv, cat = ops.dec_qkv_prep(qkv_obj, qk_pos, pairs, B, Q)
+        ctx.save_for_backward(pairs)
+        ctx.dims = (B, Q)
+        return qkv, cat
+
+    @staticmethod
+    def backward(ctx, d_qkv, d_cat):
+        (pairs,) = ctx.saved_tensors
+        B, Q = ctx.dims
+        return ops.dec_qkv_prep_bwd(d_qkv.contiguous(), d_cat.contiguous(), pairs, B, Q) + (None, None, None)
+
+
+class _DecSelfPairAttn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, cat, B, Q):
+        o1, o2, lse1, lse2 = ops.dec_self_pair_attn_fwd(qkv, cat, B, Q)
+        ctx.save_for_backward(qkv, cat, o1, o2, lse1, lse2)
+        ctx.dims = (B, Q)
+        return o1, o2
+
+    @staticmethod
+    def backward(ctx, do1, do2):
+        qkv, cat, o1, o2, lse1, lse2 = ctx.saved_tensors
+        B, Q = ctx.dims
+        d_qkv, d_cat = ops.dec_self_pair_attn_bwd(qkv, cat, o1, o2, do1.contiguous(), do2.contiguous(), lse1, lse2,
+                                                  B, Q)
+        return d_qkv, d_cat, None, None
+
+
+class _SplitCrossAttn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q_obj, q_pos, k_enc, k_pos, v, bits, kpm, B, Q, N):
+        out, lse = ops.split_cross_attn_fwd(q_obj, q_pos, k_enc, k_pos, v, bits, B, Q, N)
+        ctx.save_for_backward(q_obj, q_pos, k_enc, k_pos, v, kpm, out, lse)
+        ctx.dims = (B, Q, N)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q_obj, q_pos, k_enc, k_pos, v, kpm, out, lse = ctx.saved_tensors
+        B, Q, N = ctx.dims
+        g = ops.split_cross_attn_bwd(q_obj, q_pos, k_enc, k_pos, v, kpm, out, dout.contiguous(), lse, B, Q, N)
+        return g + (None, None, None, None, None)
+
+
+def decoder_hoisted_projections(enc_out: Tensor, fine_pos: Tensor, pos_embed: Tensor, p: Dict[str, Tensor],
+                                num_layers: int):
+    """The projections of decoder_block.py:167-177,189-193 that depend only on layer weights and
+    layer-invariant inputs, for ALL layers as three packed GEMMs:
+      kv_all   [B*N, L*512]: per layer [W_k_enc enc | W_v_enc enc]
+      kpos_all [B*N, L*256]: per layer  W_k_pos fine_pos
+      qkpos_all[B*Q, L*512]: per layer [W_sa_q_pos pos | W_sa_k_pos pos]"""
+    wkv = torch.cat([torch.cat([p[f"_decoder.{l}._ca_proj_to_k_enc.weight"], p[f"_decoder.{l}._ca_proj_to_v_enc.weight"]])
+                     for l in range(num_layers)])
+    wkp = torch.cat([p[f"_decoder.{l}._ca_proj_to_k_pos.weight"] for l in range(num_layers)])
+    wqk = torch.cat([torch.cat([p[f"_decoder.{l}._sa_proj_to_q_pos.weight"], p[f"_decoder.{l}._sa_proj_to_k_pos.weight"]])
+                     for l in range(num_layers)])
+    return linear(enc_out, wkv), linear(fine_pos, wkp), linear(pos_embed, wqk)
+
+
+def decoder_block_core(x: Tensor, sin_embed: Tensor, pairs: Tensor, qk_pos: Tensor, k_enc: Tensor, k_pos: Tensor,
+                       v: Tensor, bits: Tensor, kpm: Optional[Tensor], p: Dict[str, Tensor], lp: str, B: int, Q: int,
+                       N: int, lam: float = 0.5) -> Tensor:
+    """DecoderBlock.forward (decoder_block.py:157-220) given the projected keys/values.
+    x bf16 [B*Q,512]; sin_embed bf16 [B*Q,256]; pairs int32 [B,Q,2]; qk_pos bf16 [B*Q,512] = [W_q_pos p | W_k_pos p];
+    k_enc, k_pos, v bf16 [B*N,256] views.  Returns cat(cls, reg) bf16 [B*Q,512]."""
+    wqkv = torch.cat([p[lp + "_sa_proj_to_q_obj.weight"], p[lp + "_sa_proj_to_k_obj.weight"],
+                      p[lp + "_sa_proj_to_v_obj.weight"]])
+    qkv_obj = linear(x, wqkv)
+    qkv, cat = _DecQkvPrep.apply(qkv_obj, qk_pos, pairs, B, Q)
+    o1, o2 = _DecSelfPairAttn.apply(qkv, cat, B, Q)
+    o = _DualLnMix.apply(x, o1, o2, pairs, p[lp + "norm1.weight"], p[lp + "norm1.bias"], p[lp + "norm2.weight"],
+                         p[lp + "norm2.bias"], lam, Q)
+    q_obj = linear(o, p[lp + "_ca_proj_to_q_obj.weight"])
+    q_pos = linear(sin_embed, p[lp + "_ca_proj_to_q_pos.weight"])
+    ca = _SplitCrossAttn.apply(q_obj, q_pos, k_enc, k_pos, v, bits, kpm, B, Q, N)
+    outs = []
+    for i, br in enumerate(("_cls_branch.", "_reg_branch.")):
+        bp = lp + br
+        xb = add_layernorm(o[:, i * 256:(i + 1) * 256], ca[:, i * 256:(i + 1) * 256], p[bp + "norm1.weight"],
+                           p[bp + "norm1.bias"])
+        f = linear(torch.relu(linear(xb, p[bp + "fc1.weight"], p[bp + "fc1.bias"])), p[bp + "fc2.weight"],
+                   p[bp + "fc2.bias"])
+        outs.append(add_layernorm(xb, f, p[bp + "norm2.weight"], p[bp + "norm2.bias"]))
+    return torch.cat(outs, dim=-1)
+
+
+def decoder_layer(x: Tensor, l: int, kv_all: Tensor, kpos_all: Tensor, qkpos_all: Tensor, sine: Tensor,
+                  centers: Tensor, bits: Tensor, kpm: Optional[Tensor], p: Dict[str, Tensor],
+                  bbox_p: Dict[str, Tensor], B: int, Q: int, N: int, lam: float = 0.5,
+                  pairs_override: Optional[Tensor] = None):
+    """x = norm(x + DecoderBlock(x, ...)) (decoder_block.py:43-65).  x bf16 [B*Q, 512].
+    `pairs_override` (int32 [B,Q,2]) injects the discrete pairing (parity tests)."""
+    x_reg = x[:, 256:]
+    sin_embed = _MulConst.apply(mlp2(x_reg, p, "_pos_scale."), sine)
+    with torch.no_grad():  # coords only select the pairing (an argmax): fp32, no gradient
+        xr32 = x_reg.float()
+        delta = F.linear(torch.relu(F.linear(xr32, bbox_p["0.weight"], bbox_p["0.bias"])), bbox_p["2.weight"],
+                         bbox_p["2.bias"])
+        coords = ops.box_refine(delta, centers)
+        pairs = ops.pair_indices(coords.view(B, Q, 4)) if pairs_override is None else pairs_override
+    y = decoder_block_core(x, sin_embed, pairs, qkpos_all[:, l * 512:(l + 1) * 512],
+                           kv_all[:, l * 512:l * 512 + 256], kpos_all[:, l * 256:(l + 1) * 256],
+                           kv_all[:, l * 512 + 256:(l + 1) * 512], bits, kpm, p, f"_decoder.{l}.", B, Q, N, lam)
+    return add_layernorm(x, y, p["norm.weight"], p["norm.bias"]), (coords, pairs)
+
+
+def decoder_tokens(x: Tensor, enc_out: Tensor, bits: Tensor, kpm: Tensor, fine_pos: Tensor, pos_embed: Tensor,
+                   centers: Tensor, p: Dict[str, Tensor], bbox_p: Dict[str, Tensor], num_layers: int, B: int, Q: int,
+                   N: int, pairs_override=None, aux: Optional[list] = None):
+    """Decoder.forward (decoder_block.py:28-67) on token-major bf16 activations.
+    x [B*Q,512], enc_out/fine_pos [B*N,256], pos_embed [B*Q,256] bf16; centers fp32 [B*Q,2]."""
+    kv_all, kpos_all, qkpos_all = decoder_hoisted_projections(enc_out, fine_pos, pos_embed, p, num_layers)
+    _, sine = ops.query_sine_embed(centers, want_f32=False, want_bf16=True)  # loop-invariant (decoder_block.py:45-47)
+    for l in range(num_layers):
+        x, a = decoder_layer(x, l, kv_all, kpos_all, qkpos_all, sine, centers, bits, kpm, p, bbox_p, B, Q, N,
+                             pairs_override=None if pairs_override is None else pairs_override[l])
+        if aux is not None:
+            aux.append(a)
+    return x

@@ -1,0 +1,63 @@
+"""The DESTR transformer half as one module: everything between the backbone's 1x1 `reduce_dim`
+conv and the loss (src/model/model.py:84-131 minus the mini-detector), on the B200 kernels.
+
+Parameter names follow the reference `ObjDetSplitTransformer` (`_encoder.*`, `_decoder.*`,
+`_cls_embed.*`, `_bbox_embed.*`) so a reference checkpoint's matching entries load directly.
+The mini-detector (query selection, out of scope) is replaced by explicit `selected_objects` /
+`selected_centers` inputs, which is exactly what it hands to the decoder (model.py:100-118).
+"""
+from __future__ import annotations
+
+from argparse import Namespace
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import functional as Fn
+from . import ops
+from .decoder import build_decoder
+from .encoder import _params, build_encoder
+
+BF16 = torch.bfloat16
+
+
+def inverse_sigmoid(x: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    """reference: misc.py:59-62."""
+    return -torch.log(1.0 / x.clamp(min=eps) - 1.0)
+
+
+class TransformerHalf(nn.Module):
+    def __init__(self, args: Namespace):
+        super().__init__()
+        self._encoder = build_encoder(args)
+        self._decoder = build_decoder(args)
+        d = args.hidden_dim
+        self._hidden_dim = d
+        self._cls_embed = nn.Linear(d, args.num_cls)
+        self._bbox_embed = nn.Sequential(nn.Linear(d, d), nn.ReLU(), nn.Linear(d, 4))
+
+    def forward(self, features: torch.Tensor, mask: torch.Tensor, selected_objects: torch.Tensor,
+                selected_centers: torch.Tensor):
+        """features (B,256,H,W) fp32 = reduce_dim(backbone) output; mask (B,H,W) bool;
+        selected_objects (B,Q,512); selected_centers (B,Q,2) in (0,1).
+        Returns {"pred_class": (B,Q,C) fp32, "pred_boxes": (B,Q,4) fp32} (model.py:120-131)."""
+        B, C, H, W = features.shape
+        N = H * W
+        Q = selected_objects.shape[1]
+        x = features.flatten(2).transpose(1, 2).reshape(B * N, C).to(BF16)
+        _, pos = ops.sine_pos2d(mask, want_f32=False, want_bf16=True)  # K1 (position_encoding_cdetr.py:39-63)
+        pos = pos.view(B * N, C)
+        kpm = mask.flatten(1).contiguous()
+        bits = ops.pack_key_mask(kpm, B, N, device=features.device)
+        enc = self._encoder.forward_tokens(x, pos, bits, B, N)
+        # fine_pos = pos * encoder._pos_scale(enc_out)  (model.py:89-92)
+        fine_pos = Fn._MulConst.apply(Fn.mlp2(enc, _params(self._encoder), "_pos_scale."), pos)
+        centers = selected_centers.reshape(B * Q, 2).float().contiguous()
+        _, pos_embed = ops.query_sine_embed(centers, want_f32=False, want_bf16=True)  # model.py:104-106
+        dec = self._decoder.forward_tokens(selected_objects.reshape(B * Q, 512).to(BF16), enc, bits, kpm, fine_pos,
+                                           pos_embed, centers, self._bbox_embed, B, Q, N)
+        cls = Fn.linear(dec[:, :256], self._cls_embed.weight, self._cls_embed.bias).float()
+        delta = self._bbox_embed(dec[:, 256:].float())  # fp32 box head (box coords need 1e-3 abs)
+        boxes = torch.cat([delta[:, :2] + inverse_sigmoid(centers), delta[:, 2:]], dim=-1).sigmoid()
+        return {"pred_class": cls.view(B, Q, -1), "pred_boxes": boxes.view(B, Q, 4)}, enc.view(B, N, C)

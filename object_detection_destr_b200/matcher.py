@@ -1,0 +1,219 @@
+"""Drop-in replacements for the reference matchers and loss entry point
+(src/utils/matcher.py:30-196, 286-287; src/utils/criterion.py:15-89).
+
+The cost matrix is one fp32 CUDA kernel that computes ONLY the per-image diagonal blocks the
+assignment consumes (the reference builds the full cross-batch (B*Q) x sum(T) matrix and throws all
+off-diagonal blocks away, matcher.py:102-112).  The assignment itself stays scipy's
+linear_sum_assignment on the host, exactly as in the reference (bit-exact indices are required);
+only the block-diagonal costs cross PCIe, through a pinned buffer.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from scipy.optimize import linear_sum_assignment
+from torch import nn
+
+from . import ops
+
+
+class _MatcherBase(nn.Module):
+    with_l1 = True
+
+    def __init__(self):
+        super().__init__()
+        self._pinned: Optional[torch.Tensor] = None
+
+    def _weights(self) -> Tuple[float, float, float]:
+        raise NotImplementedError
+
+    def _labels(self, tgt) -> torch.Tensor:
+        raise NotImplementedError
+
+    @torch.no_grad()
+    def cost_blocks(self, outputs, targets):
+        """Launch the cost kernel; returns (flat device cost buffer, sizes, Q)."""
+        logits = outputs["pred_class"].detach().float()
+        boxes = outputs["pred_boxes"].detach().float()
+        B, Q, _ = logits.shape
+        sizes = [int(t["boxes"].shape[0]) for t in targets]
+        total = sum(sizes)
+        dev = logits.device
+        if total > 0:
+            ids = torch.cat([self._labels(t) for t in targets]).to(device=dev, dtype=torch.int32)
+            tb = torch.cat([t["boxes"] for t in targets]).to(device=dev, dtype=torch.float32).contiguous()
+        else:
+            ids = torch.zeros(1, dtype=torch.int32, device=dev)
+            tb = torch.zeros(1, 4, dtype=torch.float32, device=dev)
+        offs = torch.tensor(np.concatenate([[0], np.cumsum(sizes)]), dtype=torch.int32).to(dev, non_blocking=True)
+        wc, wb, wi = self._weights()
+        cost = ops.match_cost_blockdiag(logits, boxes, ids, tb, offs, total, wc, wb, wi, self.with_l1)
+        return cost, sizes, Q
+
+    @torch.no_grad()
+    def forward(self, outputs, targets):
+        """Same contract as the reference (matcher.py:54-119): list over the batch of
+        (index_i, index_j) CPU int64 tensors, len = min(Q, T_b), rows ascending."""
+        cost, sizes, Q = self.cost_blocks(outputs, targets)
+        n = Q * sum(sizes)
+        if self._pinned is None or self._pinned.numel() < max(n, 1):
+            self._pinned = torch.empty(max(n, 1), dtype=torch.float32, pin_memory=True)
+        host = self._pinned[:max(n, 1)]
+        host.copy_(cost[:max(n, 1)], non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the one D2H sync of the matcher (matcher.py:107)
+        c = host.numpy()
+        out, off = [], 0
+        for t in sizes:
+            blk = c[off:off + Q * t].reshape(Q, t)
+            off += Q * t
+            i, j = linear_sum_assignment(blk)
+            out.append((torch.as_tensor(i, dtype=torch.int64), torch.as_tensor(j, dtype=torch.int64)))
+        return out
+
+
+class HungarianMatcher(_MatcherBase):
+    """reference: matcher.py:30-119 (class + L1 + CIoU; expects ONE-HOT labels, :83)."""
+    with_l1 = True
+
+    def __init__(self, cost_class: float = 1, cost_bbox: float = 1, cost_ciou: float = 1):
+        super().__init__()
+        self.cost_class, self.cost_bbox, self.cost_ciou = cost_class, cost_bbox, cost_ciou
+        assert cost_class != 0 or cost_bbox != 0 or cost_ciou != 0, "all costs cant be 0"
+
+    def _weights(self):
+        return self.cost_class, self.cost_bbox, self.cost_ciou
+
+    def _labels(self, tgt):
+        return tgt["labels"].argmax(-1)
+
+
+class HungarianMatcherWoL1(_MatcherBase):
+    """reference: matcher.py:122-196 (class + CIoU; expects INTEGER labels, :167)."""
+    with_l1 = False
+
+    def __init__(self, cost_class: float = 1, cost_ciou: float = 1):
+        super().__init__()
+        self.cost_class, self.cost_ciou = cost_class, cost_ciou
+        assert cost_class != 0 or cost_ciou != 0, "all costs cant be 0"
+
+    def _weights(self):
+        return self.cost_class, 0.0, self.cost_ciou
+
+    def _labels(self, tgt):
+        return tgt["labels"]
+
+
+def build_matcher(cls, args):
+    """reference: matcher.py:286-287."""
+    return cls(args)
+
+
+# --------------------------------------------------------------------------------------------------
+# loss entry point (host PyTorch, as in the reference; batched instead of a per-image Python loop)
+# --------------------------------------------------------------------------------------------------
+def _cxcyhw_to_xyxy(b):
+    cx, cy, hh, ww = b.unbind(-1)
+    return torch.stack([(cx - ww / 2).clamp(min=0), (cy - hh / 2).clamp(min=0), (cx + ww / 2).clamp(max=1),
+                        (cy + hh / 2).clamp(max=1)], dim=-1)
+
+
+def _xyxy_to_cxcyhw(b):
+    x0, y0, x1, y1 = b.unbind(-1)
+    return torch.stack([((x0 + x1) / 2).clamp(0, 1), ((y0 + y1) / 2).clamp(0, 1), (y1 - y0).clamp(0, 1),
+                        (x1 - x0).clamp(0, 1)], dim=-1)
+
+
+def _ciou_cost_batched(p, g, eps: float = 1e-6):
+    """complete_iou (bbox_utils.py:160-198) on padded batches: p, g (B,n,4) xyxy -> (B,n,n)."""
+    pc, gc = _xyxy_to_cxcyhw(p), _xyxy_to_cxcyhw(g)
+    lo = torch.maximum(p[:, :, None, :2], g[:, None, :, :2])
+    hi = torch.minimum(p[:, :, None, 2:], g[:, None, :, 2:])
+    wh = (hi - lo).clamp(min=0)
+    inter = wh[..., 0] * wh[..., 1]
+    ap = (p[..., 2] - p[..., 0]) * (p[..., 3] - p[..., 1])
+    ag = (g[..., 2] - g[..., 0]) * (g[..., 3] - g[..., 1])
+    iou = inter / (ap[:, :, None] + ag[:, None, :] - inter).clamp(min=eps)
+    hull = (torch.maximum(p[:, :, None, 2:], g[:, None, :, 2:]) - torch.minimum(p[:, :, None, :2], g[:, None, :, :2])).clamp(min=0)
+    c2 = (hull * hull).sum(-1)
+    dc = (pc[:, :, None, :2] - gc[:, None, :, :2]).abs()
+    rho2 = (dc * dc).sum(-1)
+    v = (4.0 / (torch.pi ** 2)) * (torch.atan(gc[..., 3] / gc[..., 2].clamp(min=eps))[:, None, :]
+                                   - torch.atan(pc[..., 3] / pc[..., 2].clamp(min=eps))[:, :, None]) ** 2
+    with torch.no_grad():
+        alpha = (iou > 0.5).to(iou.dtype) * (v / (1 - iou + v))
+    return 1 - (iou - rho2 / c2.clamp(min=eps) - alpha * v).clamp(-1.0, 1.0)
+
+
+class SetCriterion(nn.Module):
+    """reference: criterion.py:15-79 with loss_fn = {class: sigmoid_focal_loss, bbox: L1Loss,
+    ciou: CompleteIOULoss} (train.py:255-262).  Same constructor and forward contract; the three
+    losses are computed for the whole batch at once.  `num_classes` is the one-hot width of the
+    class loss: the reference hard-codes 2 (criterion.py:45); pass the logits width for the
+    91-class harness shim of SURVEY 7.3-8.  `loss_fn` is accepted for signature parity."""
+
+    def __init__(self, num_classes, matcher, loss_fn=None):
+        super().__init__()
+        self._num_cls = num_classes
+        self._matcher = matcher
+        self._loss_fns = loss_fn
+
+    def forward(self, outputs, targets, indices=None):
+        logits, boxes = outputs["pred_class"].float(), outputs["pred_boxes"].float()
+        B, Q, C = logits.shape
+        dev = logits.device
+        if indices is None:
+            indices = self._matcher(outputs, targets)
+        n = [int(i.numel()) for i, _ in indices]
+        nmax = max(max(n), 1)
+        # padded index tensors, one H2D copy
+        pi = torch.full((B, nmax), Q, dtype=torch.int64)  # padded slots point at a dummy query column Q
+        ti = torch.zeros(B, nmax, dtype=torch.int64)
+        valid = torch.zeros(B, nmax, dtype=torch.bool)
+        for b, (i, j) in enumerate(indices):
+            pi[b, :n[b]], ti[b, :n[b]], valid[b, :n[b]] = i, j, True
+        tmax = max(max(int(t["boxes"].shape[0]) for t in targets), 1)
+        tl = torch.ones(B, tmax, dtype=torch.int64, device=dev)
+        tb = torch.zeros(B, tmax, 4, dtype=torch.float32, device=dev)
+        for b, t in enumerate(targets):
+            k = int(t["boxes"].shape[0])
+            if k:
+                tl[b, :k], tb[b, :k] = t["labels"].to(dev), t["boxes"].to(dev)
+        pi, ti, valid = pi.to(dev), ti.to(dev), valid.to(dev)
+        # class loss (criterion.py:29-49): matched queries get their target class, the rest class 1
+        tcls = torch.ones(B, Q + 1, dtype=torch.int64, device=dev)
+        tcls.scatter_(1, pi, tl.gather(1, ti))
+        tcls = tcls[:, :Q]
+        pi = pi.clamp(max=Q - 1)  # padded slots are masked by `valid` below
+        onehot = F.one_hot(tcls, self._num_cls).to(logits.dtype)
+        prob = logits.sigmoid()
+        ce = F.binary_cross_entropy_with_logits(logits, onehot, reduction="none")
+        pt = prob * onehot + (1 - prob) * (1 - onehot)
+        focal = (0.25 * onehot + 0.75 * (1 - onehot)) * ce * (1 - pt) ** 2
+        loss_cls = (focal.mean(2).sum(1) / Q).mean()
+        # box losses on matched pairs (criterion.py:60-71); images without matches are skipped
+        pb = _cxcyhw_to_xyxy(boxes).gather(1, pi[..., None].expand(B, nmax, 4))
+        gb = tb.gather(1, ti[..., None].expand(B, nmax, 4))
+        has = valid.any(1)
+        cnt = valid.sum(1).clamp(min=1).to(logits.dtype)
+        if bool(has.any()):
+            l1 = ((pb - gb).abs().sum(-1) * valid).sum(1) / (4 * cnt)
+            pair_ok = (valid[:, :, None] & valid[:, None, :]).to(logits.dtype)
+            # neutral boxes in the padded slots keep the (discarded) entries finite
+            neutral = torch.tensor([0.25, 0.25, 0.5, 0.5], device=dev)
+            ci = _ciou_cost_batched(torch.where(valid[..., None], pb, neutral), torch.where(valid[..., None], gb, neutral + 0.1))
+            ciou = (ci * pair_ok).sum((1, 2)) / (cnt * cnt)
+            w = has.to(logits.dtype)
+            loss_box, loss_ciou = (l1 * w).sum() / w.sum(), (ciou * w).sum() / w.sum()
+        else:
+            loss_box, loss_ciou = torch.zeros(1, device=dev), torch.zeros(1, device=dev)
+        return {"class": loss_cls, "bbox": loss_box, "ciou": loss_ciou}
+
+
+class CompleteIOULoss(nn.Module):
+    """reference: criterion.py:82-89 (mean of the full n x n CIoU cost matrix)."""
+
+    def forward(self, outputs, gt):
+        return _ciou_cost_batched(outputs[None], gt[None]).mean()

@@ -96,30 +96,46 @@ def mul(a: Tensor, b: Tensor) -> Tensor:
     return y
 
 
-def add_layernorm(a: Tensor, b: Optional[Tensor], gamma: Tensor, beta: Tensor, save_stats: bool = False):
-    a = _chk(a.contiguous(), BF16, "a")
-    if b is not None:
-        b = _chk(b.contiguous(), BF16, "b")
-    g, be = _chk(gamma.contiguous(), torch.float32, "gamma"), _chk(beta.contiguous(), torch.float32, "beta")
+def _rows(t: Tensor, dtype, name: str, D: int) -> Tensor:
+    """2-D [M, D] view with unit column stride (row pitch free)."""
+    _chk(t, dtype, name)
+    if t.dim() != 2:
+        t = t.reshape(-1, t.shape[-1])
+    if t.stride(1) != 1 or t.shape[1] != D or t.stride(0) % 8 != 0:
+        t = t.contiguous()
+    return t
+
+
+def add_layernorm(a: Tensor, b: Optional[Tensor], gamma: Tensor, beta: Tensor, save_stats: bool = False,
+                  out: Optional[Tensor] = None):
+    """y = LN(a + b).  a, b (and `out`, if given) may be strided [M, D] views."""
     D = a.shape[-1]
-    M = a.numel() // D
-    y = torch.empty_like(a)
+    a = _rows(a, BF16, "a", D)
+    M = a.shape[0]
+    if b is not None:
+        b = _rows(b, BF16, "b", D)
+    g, be = _chk(gamma.contiguous(), torch.float32, "gamma"), _chk(beta.contiguous(), torch.float32, "beta")
+    y = torch.empty(M, D, dtype=BF16, device=a.device) if out is None else out
     mean = torch.empty(M, dtype=torch.float32, device=a.device) if save_stats else None
     rstd = torch.empty(M, dtype=torch.float32, device=a.device) if save_stats else None
-    _lib.call("destr_add_layernorm_fwd", a.data_ptr(), _ptr(b), g.data_ptr(), be.data_ptr(), y.data_ptr(),
-              _ptr(mean), _ptr(rstd), M, D, _stream())
+    _lib.call("destr_add_layernorm_fwd", a.data_ptr(), a.stride(0), _ptr(b), 0 if b is None else b.stride(0),
+              g.data_ptr(), be.data_ptr(), y.data_ptr(), y.stride(0), _ptr(mean), _ptr(rstd), M, D, _stream())
     return (y, mean, rstd) if save_stats else y
 
 
 def add_layernorm_bwd(dy: Tensor, a: Tensor, b: Optional[Tensor], gamma: Tensor, mean: Tensor, rstd: Tensor):
-    dy = _chk(dy.contiguous(), BF16, "dy")
     D = a.shape[-1]
-    M = a.numel() // D
-    dx = torch.empty_like(a)
+    dy = _rows(dy, BF16, "dy", D)
+    a = _rows(a, BF16, "a", D)
+    if b is not None:
+        b = _rows(b, BF16, "b", D)
+    M = a.shape[0]
+    dx = torch.empty(M, D, dtype=BF16, device=a.device)
     dg = torch.zeros(D, dtype=torch.float32, device=a.device)
     db = torch.zeros(D, dtype=torch.float32, device=a.device)
-    _lib.call("destr_add_layernorm_bwd", dy.data_ptr(), a.data_ptr(), _ptr(b), gamma.data_ptr(), mean.data_ptr(),
-              rstd.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), M, D, _stream())
+    _lib.call("destr_add_layernorm_bwd", dy.data_ptr(), dy.stride(0), a.data_ptr(), a.stride(0), _ptr(b),
+              0 if b is None else b.stride(0), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(),
+              dx.stride(0), dg.data_ptr(), db.data_ptr(), M, D, _stream())
     return dx, dg, db
 
 
@@ -240,6 +256,11 @@ def split_cross_attn_fwd(q_obj: Tensor, q_pos: Tensor, k_enc: Tensor, k_pos: Ten
               v.data_ptr(), k_enc.stride(0), k_pos.stride(0), v.stride(0), mask_bits.data_ptr(), mask_bits.shape[1],
               out.data_ptr(), _ptr(lse), ws.data_ptr(), B, Q, N, 1.0 / math.sqrt(512.0), _stream())
     return out, lse
+
+
+# Backward of the decoder attention ops: cuBLAS batched GEMMs + elementwise torch on the GPU
+# (see _composed_bwd.py for status; the fused tcgen05 backward exists for the encoder only so far).
+from ._composed_bwd import dec_qkv_prep_bwd, dec_self_pair_attn_bwd, split_cross_attn_bwd  # noqa: E402,F401
 
 
 # ----------------------------------------------------------------------------------------------
