@@ -54,13 +54,25 @@ lib.destr_split_cross_attn_ws_floats.restype = _i64
 lib.destr_last_error.argtypes = []
 lib.destr_last_error.restype = C.c_char_p
 
-# number of kernel launches issued through this binding (bench.py reports it as gpu_launches)
+# kernels launched per C-ABI call (bench.py reports the sum over a step as gpu_launches)
+KERNELS_PER_CALL = {"destr_enc_attn_bwd": 3, "destr_split_cross_attn_fwd": 2}
 launch_count = 0
+# bench.py: {name: []} -> (start, end) CUDA-event pairs are appended around every call of `name`
+KERNEL_TIMERS = None
 
 
 def call(name: str, *args) -> None:
     global launch_count
-    rc = getattr(lib, name)(*args)
+    timers = KERNEL_TIMERS
+    if timers is not None and name in timers:
+        import torch
+        st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        st.record()
+        rc = getattr(lib, name)(*args)
+        en.record()
+        timers[name].append((st, en))
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed (rc={rc}): {lib.destr_last_error().decode()}")
-    launch_count += 1
+    launch_count += KERNELS_PER_CALL.get(name, 1)
