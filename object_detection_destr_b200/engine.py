@@ -1,0 +1,203 @@
+"""CUDA-graph training / inference steps for the hot path.
+
+The eager step issues ~2000 small launches and is CPU-bound; the engine captures it into two CUDA
+graphs around the one unavoidable host round trip (the reference's `C.cpu()` + scipy
+linear_sum_assignment, matcher.py:107-112):
+
+    graph A : forward (encoder, decoder, heads) -> block-diagonal cost kernel -> D2H into pinned memory
+    host    : stream sync, linear_sum_assignment per image, indices -> pinned -> H2D
+    graph B : set loss -> backward -> [NCCL gradient all-reduce] -> fused AdamW
+
+All shapes are static: targets are padded to `t_max` per image (the cost kernel and the loss read the
+true counts from device tensors), so one capture serves every batch.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from scipy.optimize import linear_sum_assignment
+
+from . import ops
+from .matcher import _ciou_cost_batched, _cxcyhw_to_xyxy
+
+
+def set_loss_static(logits, boxes, tl, tb, pi, ti, valid, num_classes: int):
+    """SetCriterion.forward (criterion.py:29-79) on static, padded shapes (no host branches).
+    logits (B,Q,C), boxes (B,Q,4) cxcyhw; tl (B,Tm) int64, tb (B,Tm,4) padded targets;
+    pi (B,n) matched query index (Q in padded slots), ti (B,n) matched target index, valid (B,n) bool."""
+    B, Q, _ = logits.shape
+    n = pi.shape[1]
+    logits, boxes = logits.float(), boxes.float()
+    tcls = torch.ones(B, Q + 1, dtype=torch.int64, device=logits.device)
+    tcls.scatter_(1, pi, tl.gather(1, ti))
+    onehot = F.one_hot(tcls[:, :Q], num_classes).to(logits.dtype)
+    prob = logits.sigmoid()
+    ce = F.binary_cross_entropy_with_logits(logits, onehot, reduction="none")
+    pt = prob * onehot + (1 - prob) * (1 - onehot)
+    focal = (0.25 * onehot + 0.75 * (1 - onehot)) * ce * (1 - pt) ** 2
+    loss_cls = (focal.mean(2).sum(1) / Q).mean()
+    pic = pi.clamp(max=Q - 1)
+    pb = _cxcyhw_to_xyxy(boxes).gather(1, pic[..., None].expand(B, n, 4))
+    gb = tb.gather(1, ti[..., None].expand(B, n, 4))
+    vf = valid.to(logits.dtype)
+    cnt = vf.sum(1).clamp(min=1)
+    has = (vf.sum(1) > 0).to(logits.dtype)
+    l1 = ((pb - gb).abs().sum(-1) * vf).sum(1) / (4 * cnt)
+    neutral = 0.25 + 0.25 * (torch.arange(4, device=logits.device) >= 2).to(logits.dtype)  # no H2D (graph capture)
+    ci = _ciou_cost_batched(torch.where(valid[..., None], pb, neutral), torch.where(valid[..., None], gb, neutral + 0.1))
+    ciou = (ci * (vf[:, :, None] * vf[:, None, :])).sum((1, 2)) / (cnt * cnt)
+    denom = has.sum().clamp(min=1)
+    return {"class": loss_cls, "bbox": (l1 * has).sum() / denom, "ciou": (ciou * has).sum() / denom}
+
+
+class GraphedTrainStep:
+    """One training step of the hot path as two CUDA graphs (see module docstring)."""
+
+    def __init__(self, model, optimizer, *, B: int, H: int, W: int, Q: int, num_classes: int, t_max: int = 40,
+                 cost_class: float = 0.5, cost_ciou: float = 0.5, loss_weights: Optional[Dict[str, float]] = None,
+                 world: int = 1, device=None):
+        self.model, self.opt = model, optimizer
+        self.B, self.Q, self.C, self.t_max, self.world = B, Q, num_classes, t_max, world
+        self.wc, self.wi = cost_class, cost_ciou
+        self.lw = loss_weights or {"class": 0.5, "bbox": 0.0, "ciou": 0.5}
+        dev = device or torch.device("cuda", torch.cuda.current_device())
+        self.dev = dev
+        n = min(Q, t_max)
+        self.n = n
+        z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)
+        self.s_feats, self.s_mask = z(B, 256, H, W), z(B, H, W, dt=torch.bool)
+        self.s_sel, self.s_centers = z(B, Q, 512), z(B, Q, 2) + 0.5
+        self.s_ids, self.s_tboxes = z(B * t_max, dt=torch.int32), z(B * t_max, 4)
+        self.s_offs = z(B + 1, dt=torch.int32)
+        self.s_cost = z(Q * B * t_max)
+        self.h_cost = torch.empty(Q * B * t_max, dtype=torch.float32, pin_memory=True)
+        # loss-side statics: padded per-image targets and the matching
+        self.s_tl, self.s_tb = z(B, t_max, dt=torch.int64) + 1, z(B, t_max, 4)
+        self.s_pi, self.s_ti, self.s_valid = z(B, n, dt=torch.int64) + Q, z(B, n, dt=torch.int64), z(B, n, dt=torch.bool)
+        self.h_idx = torch.empty(3, B, n, dtype=torch.int64, pin_memory=True)
+        self.h_tgt_i = torch.empty(B * t_max + B + 1, dtype=torch.int32, pin_memory=True)
+        self.h_tgt_f = torch.empty(B * t_max * 4, dtype=torch.float32, pin_memory=True)
+        self.h_tl = torch.empty(B, t_max, dtype=torch.int64, pin_memory=True)
+        self.h_tb = torch.empty(B, t_max, 4, dtype=torch.float32, pin_memory=True)
+        self.params = [p for p in model.parameters()]
+        self.gA: Optional[torch.cuda.CUDAGraph] = None
+        self.gB: Optional[torch.cuda.CUDAGraph] = None
+        self.loss = None
+        self.out = None
+        self.sizes: List[int] = []
+        self.launches_per_step = 0
+
+    # ---- pieces (also run eagerly during warm-up) ----
+    def _forward(self):
+        out, _ = self.model(self.s_feats, self.s_mask, self.s_sel, self.s_centers)
+        with torch.no_grad():
+            ops.match_cost_blockdiag(out["pred_class"].detach(), out["pred_boxes"].detach(), self.s_ids, self.s_tboxes,
+                                     self.s_offs, self.B * self.t_max, self.wc, 0.0, self.wi, False, out=self.s_cost)
+            self.h_cost.copy_(self.s_cost, non_blocking=True)
+        return out
+
+    def _backward(self, out):
+        losses = set_loss_static(out["pred_class"], out["pred_boxes"], self.s_tl, self.s_tb, self.s_pi, self.s_ti,
+                                 self.s_valid, self.C)
+        loss = sum(self.lw[k] * losses[k] for k in self.lw)
+        loss.backward()
+        if self.world > 1:
+            import torch.distributed as dist
+            grads = [p.grad for p in self.params if p.grad is not None]
+            flat = torch._utils._flatten_dense_tensors(grads)
+            dist.all_reduce(flat)
+            flat.div_(self.world)
+            torch._foreach_copy_(grads, list(torch._utils._unflatten_dense_tensors(flat, grads)))
+        self.opt.step()
+        return loss
+
+    def _assign(self):
+        """host: block-diagonal costs -> scipy LSA -> padded index tensors (pinned) -> device."""
+        c = self.h_cost.numpy()
+        idx = self.h_idx.numpy()
+        idx[0].fill(self.Q)
+        idx[1].fill(0)
+        idx[2].fill(0)
+        off = 0
+        for b, t in enumerate(self.sizes):
+            if t:
+                i, j = linear_sum_assignment(c[off:off + self.Q * t].reshape(self.Q, t))
+                k = len(i)
+                idx[0, b, :k], idx[1, b, :k], idx[2, b, :k] = i, j, 1
+            off += self.Q * t
+        self.s_pi.copy_(self.h_idx[0], non_blocking=True)
+        self.s_ti.copy_(self.h_idx[1], non_blocking=True)
+        self.s_valid.copy_(self.h_idx[2], non_blocking=True)
+
+    def load_batch(self, feats, mask, sel, centers, labels: Sequence[torch.Tensor], boxes: Sequence[torch.Tensor]):
+        """Copy one batch into the static buffers.  feats/mask/sel/centers may be host (pinned) or device
+        tensors; labels/boxes are per-image HOST tensors (int64 [T_i], fp32 [T_i,4] xyxy), T_i <= t_max."""
+        nb = True
+        self.s_feats.copy_(feats, non_blocking=nb)
+        self.s_mask.copy_(mask, non_blocking=nb)
+        self.s_sel.copy_(sel, non_blocking=nb)
+        self.s_centers.copy_(centers, non_blocking=nb)
+        B, tm = self.B, self.t_max
+        self.sizes = [int(l.numel()) for l in labels]
+        assert max(self.sizes) <= tm, "raise t_max"
+        hi, hf = self.h_tgt_i.numpy(), self.h_tgt_f.numpy().reshape(-1, 4)
+        tl, tb = self.h_tl.numpy(), self.h_tb.numpy()
+        tl.fill(1)
+        tb.fill(0)
+        off = 0
+        for b, (l, bx) in enumerate(zip(labels, boxes)):
+            t = self.sizes[b]
+            hi[B * tm + b] = off
+            if t:
+                hi[off:off + t] = l.numpy()
+                hf[off:off + t] = bx.numpy()
+                tl[b, :t] = l.numpy()
+                tb[b, :t] = bx.numpy()
+            off += t
+        hi[B * tm + B] = off
+        self.s_ids.copy_(self.h_tgt_i[:B * tm], non_blocking=nb)
+        self.s_offs.copy_(self.h_tgt_i[B * tm:], non_blocking=nb)
+        self.s_tboxes.copy_(self.h_tgt_f.view(-1, 4), non_blocking=nb)
+        self.s_tl.copy_(self.h_tl, non_blocking=nb)
+        self.s_tb.copy_(self.h_tb, non_blocking=nb)
+
+    def eager_step(self):
+        out = self._forward()
+        torch.cuda.current_stream().synchronize()
+        self._assign()
+        self.opt.zero_grad(set_to_none=False)  # keep the (possibly graph-static) .grad tensors in place
+        return self._backward(out)
+
+    def capture(self, warmup: int = 3):
+        """Warm up eagerly on a side stream (PyTorch's capture protocol), then capture graphs A and B."""
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self.eager_step()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.opt.zero_grad(set_to_none=True)  # backward inside the capture allocates .grad from the graph pool
+        from . import _lib
+        n0 = _lib.launch_count
+        self.gA = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.gA):
+            self.out = self._forward()
+        torch.cuda.synchronize()
+        self._assign()
+        self.gB = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.gB, pool=self.gA.pool()):
+            self.loss = self._backward(self.out)
+        torch.cuda.synchronize()
+        self.launches_per_step = _lib.launch_count - n0  # our kernels captured in graphs A + B
+
+    def step(self):
+        """Replay: graph A, host assignment, graph B.  Returns the (device) loss tensor."""
+        self.gA.replay()
+        torch.cuda.current_stream().synchronize()
+        self._assign()
+        self.gB.replay()
+        return self.loss

@@ -202,7 +202,7 @@ class SetCriterion(nn.Module):
             l1 = ((pb - gb).abs().sum(-1) * valid).sum(1) / (4 * cnt)
             pair_ok = (valid[:, :, None] & valid[:, None, :]).to(logits.dtype)
             # neutral boxes in the padded slots keep the (discarded) entries finite
-            neutral = torch.tensor([0.25, 0.25, 0.5, 0.5], device=dev)
+            neutral = 0.25 + 0.25 * (torch.arange(4, device=dev) >= 2).to(logits.dtype)
             ci = _ciou_cost_batched(torch.where(valid[..., None], pb, neutral), torch.where(valid[..., None], gb, neutral + 0.1))
             ciou = (ci * pair_ok).sum((1, 2)) / (cnt * cnt)
             w = has.to(logits.dtype)

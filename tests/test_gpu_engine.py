@@ -1,0 +1,33 @@
+"""-m gpu: the CUDA-graph training step replays exactly what the eager step computes."""
+from argparse import Namespace
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_graphed_step_matches_eager():
+    import bench
+    from object_detection_destr_b200.encoder import disable_dropout
+    from object_detection_destr_b200.engine import GraphedTrainStep
+    from object_detection_destr_b200.hotpath import TransformerHalf
+    cfg = dict(bench.CFG, B=2, L=2, H=10, W=14, Q=60)
+    torch.manual_seed(0)
+    model = TransformerHalf(Namespace(hidden_dim=256, num_encoder_blocks=2, num_decoder_blocks=2, num_cls=cfg["C"]))
+    disable_dropout(model).cuda().train()
+    opt = torch.optim.AdamW(model.parameters(), lr=0.0, fused=True, capturable=True)
+    eng = GraphedTrainStep(model, opt, B=2, H=10, W=14, Q=60, num_classes=cfg["C"], t_max=40)
+    batches = [bench.make_batch(0, s, 2, cfg, padded=True) for s in range(3)]
+    eng.load_batch(*batches[0])
+    eng.capture(warmup=2)
+    assert eng.launches_per_step > 50
+    for bt in batches:
+        eng.load_batch(*bt)
+        l_graph = float(eng.step())
+        g_graph = model._encoder._encoder[0].fc1.weight.grad.clone()
+        l_eager = float(eng.eager_step())
+        g_eager = model._encoder._encoder[0].fc1.weight.grad
+        assert abs(l_graph - l_eager) <= 1e-5 * max(1.0, abs(l_eager)), (l_graph, l_eager)
+        assert torch.allclose(g_graph, g_eager, rtol=1e-3, atol=1e-6)
+        assert l_graph == l_graph and l_graph > 0
