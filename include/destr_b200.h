@@ -52,6 +52,15 @@ int destr_query_sine_embed(const float* centers, float* out_f32, void* out_bf16,
 int destr_pos_mul_add_fwd(const void* x, const void* pos, const void* s, void* y, int64_t n_elem, void* stream);
 /* backward: dx = dy (aliasing is the caller's business), ds = dy * pos */
 int destr_pos_mul_add_bwd(const void* dy, const void* pos, void* ds, int64_t n_elem, void* stream);
+/* dx_out = dx_in + dy ; ds = dy*pos  (pos_mul_add backward with the residual gradient folded in) */
+int destr_pos_mul_add_bwd_acc(const void* dy, const void* pos, const void* dx_in, void* ds, void* dx_out,
+                              int64_t n_elem, void* stream);
+/* ReLU backward fused with the bias gradient of the Linear in front of it (encoder_block.py:107,
+ * decoder_block.py:255): dpre = dy * (h > 0), dbias[c] += sum_rows dpre[:,c] (fp32, accumulated).
+ * With h = dpre = NULL it is a plain column sum of dy (bias gradient of a Linear without activation).
+ * bf16 [M,C] operands with row pitches lddy/ldh/ldo. */
+int destr_relu_bwd_colsum(const void* dy, int lddy, const void* h, int ldh, void* dpre, int ldo, float* dbias, int M,
+                          int C, void* stream);
 /* y = a * b, bf16 (fine_pos = pos * pos_scale(enc_out), model.py:89-92; decoder_block.py:49) */
 int destr_mul_fwd(const void* a, const void* b, void* y, int64_t n_elem, void* stream);
 
@@ -66,7 +75,10 @@ int destr_add_layernorm_fwd(const void* a, int lda, const void* b, int ldb, cons
  * (caller zeroes).  a+b is recomputed from a and b. */
 int destr_add_layernorm_bwd(const void* dy, int lddy, const void* a, int lda, const void* b, int ldb,
                             const float* gamma, const float* mean, const float* rstd, void* dx, int lddx,
-                            float* dgamma, float* dbeta, int M, int D, void* stream);
+                            float* dgamma, float* dbeta, float* dbias, const void* res_in, int ldri, void* res_out,
+                            int ldro, int M, int D, void* stream);
+/*   optional fusions: dbias (fp32 [D], accumulated) = column sum of dx = gradient of the bias of the Linear
+ *   that produced b;  res_out = res_in + dx = gradient flowing on into the residual stream. */
 
 /* out = lam*LN1(x+o1) + (1-lam)*LN2(x+o2eff)  (decoder_block.py:182-184), D = 512, fused with the
  * head-group slot masking of PairSelfAttention (pair_self_attention.py:101-105):
@@ -115,12 +127,12 @@ int destr_box_refine(const float* delta, const float* centers, float* boxes, int
 
 /* SA operand preparation (decoder_block.py:167-177) + the left/right gathers of pair attention
  * (pair_self_attention.py:47-89) in one pass.
- *   qkv_obj bf16 [B*Q,1536] = [W_q x | W_k x | W_v x];  qk_pos bf16 [B*Q,512] = [W_qp p | W_kp p]
+ *   qkv_obj bf16 [B*Q,1536] = [W_q x | W_k x | W_v x];  qk_pos bf16 [B*Q,512] (row pitch ld_pos) = [W_qp p | W_kp p]
  *   -> qkv bf16 [B*Q,1536] = [q_obj+[qp|qp] | k_obj+[kp|kp] | v]
  *   -> cat bf16 [3][B*Q,1024]: cat[w][i, 128h .. 128h+64) = x_w[L_i, 64h..], [128h+64 .. 128h+128) = x_w[R_i, 64h..]
  *      with (L_i, R_i) = pairs[i] (indices within the image) and x_0,x_1,x_2 = q,k,v. */
-int destr_dec_qkv_prep(const void* qkv_obj, const void* qk_pos, const int32_t* pairs, void* qkv, void* cat, int B,
-                       int Q, void* stream);
+int destr_dec_qkv_prep(const void* qkv_obj, const void* qk_pos, int ld_pos, const int32_t* pairs, void* qkv,
+                       void* cat, int B, int Q, void* stream);
 
 /* Decoder self-attention (self_attention.py:26-45, 8 heads x 64, scale 1/8) and pair self-attention
  * (pair_self_attention.py:91-99: softmax(Ql.Kl^T + Qr.Kr^T)/sqrt(128) . [Vl|Vr]) in ONE launch on

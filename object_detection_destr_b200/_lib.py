@@ -31,13 +31,15 @@ SIGNATURES = {
     "destr_pos_mul_add_bwd": [_p, _p, _p, _i64, _p],
     "destr_mul_fwd": [_p, _p, _p, _i64, _p],
     "destr_add_layernorm_fwd": [_p, _i, _p, _i, _p, _p, _p, _i, _p, _p, _i, _i, _p],
-    "destr_add_layernorm_bwd": [_p, _i, _p, _i, _p, _i, _p, _p, _p, _p, _i, _p, _p, _i, _i, _p],
+    "destr_add_layernorm_bwd": [_p, _i, _p, _i, _p, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _p, _i, _i, _i, _p],
+    "destr_pos_mul_add_bwd_acc": [_p, _p, _p, _p, _p, _i64, _p],
+    "destr_relu_bwd_colsum": [_p, _i, _p, _i, _p, _i, _p, _i, _i, _p],
     "destr_enc_attn_fwd": [_p, _p, _p, _i, _i, _i, _p, _i, _p, _p, _i, _i, _i, _f, _p],
     "destr_enc_attn_bwd": [_p, _p, _p, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i,
                            _f, _p],
     "destr_dual_ln_mix_fwd": [_p, _p, _p, _p, _p, _p, _p, _p, _f, _p, _p, _i, _i, _p],
     "destr_dual_ln_mix_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
-    "destr_dec_qkv_prep": [_p, _p, _p, _p, _p, _i, _i, _p],
+    "destr_dec_qkv_prep": [_p, _p, _i, _p, _p, _p, _i, _i, _p],
     "destr_dec_self_pair_attn_fwd": [_p, _p, _p, _p, _p, _p, _i, _i, _p],
     "destr_split_cross_attn_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _p, _i, _p, _p, _p, _i, _i, _i, _f, _p],
     "destr_pair_indices": [_p, _p, _i, _i, _p],

@@ -233,14 +233,14 @@ __global__ void dec_qkv_prep_kernel(const __nv_bfloat16* __restrict__ qkv_obj,  
                                     const __nv_bfloat16* __restrict__ qk_pos,   // [B*Q, 512] = qp|kp
                                     const int32_t* __restrict__ pairs, __nv_bfloat16* __restrict__ qkv,  // [B*Q,1536]
                                     __nv_bfloat16* __restrict__ cat,  // [3][B*Q, 1024]
-                                    int Q, int rows) {
+                                    int Q, int rows, int ld_pos) {
   const int row = blockIdx.x;
   const int b = row / Q;
   const int t = threadIdx.x;  // 0..63 -> channel t*8 of 512
   const int L = b * Q + pairs[2 * row], R = b * Q + pairs[2 * row + 1];
   auto qk_at = [&](int r, int which) {  // which: 0 q, 1 k
     const uint4 o = *reinterpret_cast<const uint4*>(qkv_obj + static_cast<size_t>(r) * 1536 + which * 512 + t * 8);
-    const uint4 p = *reinterpret_cast<const uint4*>(qk_pos + static_cast<size_t>(r) * 512 + which * 256 + (t & 31) * 8);
+    const uint4 p = *reinterpret_cast<const uint4*>(qk_pos + static_cast<size_t>(r) * ld_pos + which * 256 + (t & 31) * 8);
     return add_bf16x8(o, p);
   };
   auto v_at = [&](int r) {
@@ -263,13 +263,14 @@ __global__ void dec_qkv_prep_kernel(const __nv_bfloat16* __restrict__ qkv_obj,  
 }  // namespace
 }  // namespace destr
 
-extern "C" int destr_dec_qkv_prep(const void* qkv_obj, const void* qk_pos, const int32_t* pairs, void* qkv,
-                                  void* cat, int B, int Q, void* stream) {
+extern "C" int destr_dec_qkv_prep(const void* qkv_obj, const void* qk_pos, int ld_pos, const int32_t* pairs,
+                                  void* qkv, void* cat, int B, int Q, void* stream) {
   using namespace destr;
   DESTR_CHECK_ARG(qkv_obj && qk_pos && pairs && qkv && cat && B > 0 && Q > 0, "null pointer / shape");
+  DESTR_CHECK_ARG(ld_pos >= 512 && ld_pos % 8 == 0, "ld_pos");
   dec_qkv_prep_kernel<<<B * Q, 64, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(qkv_obj), static_cast<const __nv_bfloat16*>(qk_pos), pairs,
-      static_cast<__nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(cat), Q, B * Q);
+      static_cast<__nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(cat), Q, B * Q, ld_pos);
   DESTR_LAUNCH_CHECK();
   return 0;
 }

@@ -132,6 +132,60 @@ __global__ void ew3_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloa
   }
 }
 
+// MODE 3: dx_out = dx_in + dy ; ds = dy*pos   (backward of y = x + pos*s with the residual gradient folded in)
+__global__ void pos_mul_add_bwd_acc_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ pos,
+                                           const __nv_bfloat16* __restrict__ dx_in, __nv_bfloat16* __restrict__ ds,
+                                           __nv_bfloat16* __restrict__ dx_out, int64_t n8) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const F8 g = ld8(dy + i * 8), p = ld8(pos + i * 8), r = ld8(dx_in + i * 8);
+    F8 a, b;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      a.v[k] = g.v[k] * p.v[k];
+      b.v[k] = g.v[k] + r.v[k];
+    }
+    st8(ds + i * 8, a);
+    st8(dx_out + i * 8, b);
+  }
+}
+
+// dpre = dy * (h > 0); dbias[c] += sum_rows dpre[:, c].  Block = 32 x 8 threads: 32 column groups of 8 channels
+// x 8 row lanes; grid.x tiles the columns (256 per block), grid.y strides the rows.
+__global__ void __launch_bounds__(256)
+relu_bwd_colsum_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ h,
+                       __nv_bfloat16* __restrict__ dpre, float* __restrict__ dbias, int M, int C, int lddy, int ldh,
+                       int ldo) {
+  __shared__ float red[8][256];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + cg * 8;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  if (col < C) {
+    for (int row = blockIdx.y * 8 + rl; row < M; row += gridDim.y * 8) {
+      F8 g = ld8(dy + (size_t)row * lddy + col);
+      if (h) {
+        const F8 a = ld8(h + (size_t)row * ldh + col);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g.v[k] = a.v[k] > 0.f ? g.v[k] : 0.f;
+        st8(dpre + (size_t)row * ldo + col, g);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += g.v[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[rl][cg * 8 + k] = acc[k];
+  __syncthreads();
+  const int c = threadIdx.x;
+  if (blockIdx.x * 256 + c < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) s += red[r][c];
+    atomicAdd(dbias + blockIdx.x * 256 + c, s);
+  }
+}
+
 inline int ew_grid(int64_t n8, int threads) {
   int64_t blocks = (n8 + threads - 1) / threads;
   const int64_t cap = kSMs * 8;
@@ -192,6 +246,31 @@ extern "C" int destr_mul_fwd(const void* a, const void* b, void* y, int64_t n_el
   const int64_t n8 = n_elem / 8;
   ew3_kernel<2><<<ew_grid(n8, 256), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, nullptr, (__nv_bfloat16*)y, n8);
+  DESTR_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int destr_pos_mul_add_bwd_acc(const void* dy, const void* pos, const void* dx_in, void* ds, void* dx_out,
+                                         int64_t n_elem, void* stream) {
+  DESTR_CHECK_ARG(dy && pos && dx_in && ds && dx_out && n_elem > 0 && n_elem % 8 == 0, "n_elem must be a multiple of 8");
+  const int64_t n8 = n_elem / 8;
+  pos_mul_add_bwd_acc_kernel<<<ew_grid(n8, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dy, (const __nv_bfloat16*)pos, (const __nv_bfloat16*)dx_in, (__nv_bfloat16*)ds,
+      (__nv_bfloat16*)dx_out, n8);
+  DESTR_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int destr_relu_bwd_colsum(const void* dy, int lddy, const void* h, int ldh, void* dpre, int ldo,
+                                     float* dbias, int M, int C, void* stream) {
+  DESTR_CHECK_ARG(dy && dbias && M > 0 && C > 0 && C % 8 == 0 && lddy % 8 == 0, "shape");
+  DESTR_CHECK_ARG((h == nullptr) == (dpre == nullptr), "h and dpre go together (both NULL = plain column sum)");
+  dim3 grid(ceil_div(C, 256), 1);
+  int rows_blocks = ceil_div(M, 8 * 16);
+  const int cap = (kSMs * 4) / (int)grid.x;
+  grid.y = rows_blocks > cap ? cap : (rows_blocks < 1 ? 1 : rows_blocks);
+  relu_bwd_colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)h,
+                                                                 (__nv_bfloat16*)dpre, dbias, M, C, lddy, ldh, ldo);
   DESTR_LAUNCH_CHECK();
   return 0;
 }

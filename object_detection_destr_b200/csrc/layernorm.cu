@@ -115,17 +115,18 @@ add_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __r
                   const __nv_bfloat16* __restrict__ b, const float* __restrict__ gamma,
                   const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                   __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int M,
-                  int lddy, int lda, int ldb, int lddx) {
+                  int lddy, int lda, int ldb, int lddx, float* __restrict__ dbias,
+                  const __nv_bfloat16* __restrict__ res_in, __nv_bfloat16* __restrict__ res_out, int ldri, int ldro) {
   constexpr int D = VPL * 32;
   constexpr float invD = 1.0f / D;
-  __shared__ float red[2][8][D];  // [dgamma|dbeta][warp][channel]  (<= 32 KB at D=512)
+  __shared__ float red[3][8][D];  // [dgamma|dbeta|dbias][warp][channel]  (<= 48 KB at D=512)
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
   const Row<VPL> g = ld_vec<VPL>(gamma, lane);
-  Row<VPL> accg, accb;
+  Row<VPL> accg, accb, accx;
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) accg.v[i] = accb.v[i] = 0.f;
+  for (int i = 0; i < VPL; ++i) accg.v[i] = accb.v[i] = accx.v[i] = 0.f;
   for (int row = blockIdx.x * wpb + warp; row < M; row += gridDim.x * wpb) {
     Row<VPL> x = ld_row<VPL>(a + (size_t)row * lda, lane);
     if (b) {
@@ -149,8 +150,17 @@ add_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __r
     s2 = warp_sum(s2) * invD;
     Row<VPL> o;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) o.v[i] = rstd * (d.v[i] * g.v[i] - s1 - x.v[i] * s2);
+    for (int i = 0; i < VPL; ++i) {
+      o.v[i] = rstd * (d.v[i] * g.v[i] - s1 - x.v[i] * s2);
+      accx.v[i] += o.v[i];
+    }
     st_row<VPL>(dx + (size_t)row * lddx, lane, o);
+    if (res_out) {  // res_out = res_in + dx  (gradient of the residual stream)
+      const Row<VPL> r = ld_row<VPL>(res_in + (size_t)row * ldri, lane);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) o.v[i] += r.v[i];
+      st_row<VPL>(res_out + (size_t)row * ldro, lane, o);
+    }
   }
   // block reduction of the parameter gradients, then one atomic per channel per block
 #pragma unroll
@@ -159,16 +169,19 @@ add_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __r
     for (int i = 0; i < 8; ++i) {
       red[0][warp][(c * 32 + lane) * 8 + i] = accg.v[c * 8 + i];
       red[1][warp][(c * 32 + lane) * 8 + i] = accb.v[c * 8 + i];
+      red[2][warp][(c * 32 + lane) * 8 + i] = accx.v[c * 8 + i];
     }
   __syncthreads();
   for (int ch = threadIdx.x; ch < D; ch += blockDim.x) {
-    float sg = 0.f, sb = 0.f;
+    float sg = 0.f, sb = 0.f, sx = 0.f;
     for (int w = 0; w < wpb; ++w) {
       sg += red[0][w][ch];
       sb += red[1][w][ch];
+      sx += red[2][w][ch];
     }
     atomicAdd(dgamma + ch, sg);
     atomicAdd(dbeta + ch, sb);
+    if (dbias) atomicAdd(dbias + ch, sx);
   }
 }
 
@@ -325,20 +338,25 @@ extern "C" int destr_add_layernorm_fwd(const void* a, int lda, const void* b, in
 
 extern "C" int destr_add_layernorm_bwd(const void* dy, int lddy, const void* a, int lda, const void* b, int ldb,
                                        const float* gamma, const float* mean, const float* rstd, void* dx, int lddx,
-                                       float* dgamma, float* dbeta, int M, int D, void* stream) {
-  DESTR_CHECK_ARG(lddy % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && lddx % 8 == 0, "row pitch");
+                                       float* dgamma, float* dbeta, float* dbias, const void* res_in, int ldri,
+                                       void* res_out, int ldro, int M, int D, void* stream) {
+  DESTR_CHECK_ARG(lddy % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && lddx % 8 == 0 && ldri % 8 == 0 && ldro % 8 == 0,
+                  "row pitch");
+  DESTR_CHECK_ARG((res_in == nullptr) == (res_out == nullptr), "res_in and res_out go together");
   DESTR_CHECK_ARG(dy && a && gamma && mean && rstd && dx && dgamma && dbeta && M > 0, "null pointer / shape");
   DESTR_CHECK_ARG(D == 256 || D == 512, "D must be 256 or 512");
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = ln_grid(M) > kSMs * 2 ? kSMs * 2 : ln_grid(M);
+  const __nv_bfloat16* ri = (const __nv_bfloat16*)res_in;
+  __nv_bfloat16* ro = (__nv_bfloat16*)res_out;
   if (D == 256)
     add_ln_bwd_kernel<8><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)a,
                                                (const __nv_bfloat16*)b, gamma, mean, rstd, (__nv_bfloat16*)dx, dgamma,
-                                               dbeta, M, lddy, lda, ldb, lddx);
+                                               dbeta, M, lddy, lda, ldb, lddx, dbias, ri, ro, ldri, ldro);
   else
     add_ln_bwd_kernel<16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)a,
                                                 (const __nv_bfloat16*)b, gamma, mean, rstd, (__nv_bfloat16*)dx, dgamma,
-                                                dbeta, M, lddy, lda, ldb, lddx);
+                                                dbeta, M, lddy, lda, ldb, lddx, dbias, ri, ro, ldri, ldro);
   DESTR_LAUNCH_CHECK();
   return 0;
 }

@@ -112,6 +112,8 @@ class GraphedTrainStep:
             flat.div_(self.world)
             torch._foreach_copy_(grads, list(torch._utils._unflatten_dense_tensors(flat, grads)))
         self.opt.step()
+        if hasattr(self.model, "after_optimizer_step"):
+            self.model.after_optimizer_step()
         return loss
 
     def _assign(self):

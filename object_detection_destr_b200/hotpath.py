@@ -17,7 +17,7 @@ from torch import nn
 from . import functional as Fn
 from . import ops
 from .decoder import build_decoder
-from .encoder import _params, build_encoder
+from .encoder import _check_dropout, _params, build_encoder
 
 BF16 = torch.bfloat16
 
@@ -28,8 +28,14 @@ def inverse_sigmoid(x: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
 
 
 class TransformerHalf(nn.Module):
-    def __init__(self, args: Namespace):
+    """`runtime=True` (default) executes encoder+decoder through the hand-scheduled HotPathRuntime
+    (flat parameter buffers, explicit backward); `runtime=False` goes through the module-level autograd
+    path of functional.py.  Both compute the same function (tests/test_gpu_decoder.py)."""
+
+    def __init__(self, args: Namespace, runtime: bool = True):
         super().__init__()
+        self.use_runtime = runtime
+        self._rt = None
         self._encoder = build_encoder(args)
         self._decoder = build_decoder(args)
         d = args.hidden_dim
@@ -37,8 +43,21 @@ class TransformerHalf(nn.Module):
         self._cls_embed = nn.Linear(d, args.num_cls)
         self._bbox_embed = nn.Sequential(nn.Linear(d, d), nn.ReLU(), nn.Linear(d, 4))
 
+    def runtime(self):
+        """The hand-scheduled executor (created on first use, after the module sits on its device; it
+        re-points the encoder/decoder parameters at views of its flat master buffer)."""
+        if self._rt is None:
+            from .runtime import HotPathRuntime
+            self._rt = HotPathRuntime(self._encoder, self._decoder, self._bbox_embed, self._cls_embed.weight.device)
+        return self._rt
+
+    def after_optimizer_step(self):
+        """Refresh the bf16 weight shadows (call after every optimizer step when runtime=True)."""
+        if self._rt is not None:
+            self._rt.P.refresh()
+
     def forward(self, features: torch.Tensor, mask: torch.Tensor, selected_objects: torch.Tensor,
-                selected_centers: torch.Tensor):
+                selected_centers: torch.Tensor, pairs_override=None, aux=None):
         """features (B,256,H,W) fp32 = reduce_dim(backbone) output; mask (B,H,W) bool;
         selected_objects (B,Q,512); selected_centers (B,Q,2) in (0,1).
         Returns {"pred_class": (B,Q,C) fp32, "pred_boxes": (B,Q,4) fp32} (model.py:120-131)."""
@@ -50,13 +69,22 @@ class TransformerHalf(nn.Module):
         pos = pos.view(B * N, C)
         kpm = mask.flatten(1).contiguous()
         bits = ops.pack_key_mask(kpm, B, N, device=features.device)
-        enc = self._encoder.forward_tokens(x, pos, bits, B, N)
-        # fine_pos = pos * encoder._pos_scale(enc_out)  (model.py:89-92)
-        fine_pos = Fn._MulConst.apply(Fn.mlp2(enc, _params(self._encoder), "_pos_scale."), pos)
         centers = selected_centers.reshape(B * Q, 2).float().contiguous()
         _, pos_embed = ops.query_sine_embed(centers, want_f32=False, want_bf16=True)  # model.py:104-106
-        dec = self._decoder.forward_tokens(selected_objects.reshape(B * Q, 512).to(BF16), enc, bits, kpm, fine_pos,
-                                           pos_embed, centers, self._bbox_embed, B, Q, N)
+        sel = selected_objects.reshape(B * Q, 512).to(BF16)
+        if self.use_runtime:
+            from .runtime import _RuntimeFn
+            _check_dropout(self)
+            rt = self.runtime()
+            dec, enc = _RuntimeFn.apply(rt, rt.anchor, x, pos, bits, kpm, sel, pos_embed, pos_embed, centers, B, N, Q,
+                                        pairs_override, aux)
+        else:
+            enc = self._encoder.forward_tokens(x, pos, bits, B, N)
+            # fine_pos = pos * encoder._pos_scale(enc_out)  (model.py:89-92)
+            fine_pos = Fn._MulConst.apply(Fn.mlp2(enc, _params(self._encoder), "_pos_scale."), pos)
+            dec = Fn.decoder_tokens(sel, enc, bits, kpm, fine_pos, pos_embed, centers, _params(self._decoder),
+                                    _params(self._bbox_embed), len(self._decoder._decoder), B, Q, N,
+                                    pairs_override=pairs_override, aux=aux)
         cls = Fn.linear(dec[:, :256], self._cls_embed.weight, self._cls_embed.bias).float()
         delta = self._bbox_embed(dec[:, 256:].float())  # fp32 box head (box coords need 1e-3 abs)
         boxes = torch.cat([delta[:, :2] + inverse_sigmoid(centers), delta[:, 2:]], dim=-1).sigmoid()

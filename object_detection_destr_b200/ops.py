@@ -123,20 +123,50 @@ def add_layernorm(a: Tensor, b: Optional[Tensor], gamma: Tensor, beta: Tensor, s
     return (y, mean, rstd) if save_stats else y
 
 
-def add_layernorm_bwd(dy: Tensor, a: Tensor, b: Optional[Tensor], gamma: Tensor, mean: Tensor, rstd: Tensor):
+def add_layernorm_bwd(dy: Tensor, a: Tensor, b: Optional[Tensor], gamma: Tensor, mean: Tensor, rstd: Tensor,
+                      dgamma: Optional[Tensor] = None, dbeta: Optional[Tensor] = None, dbias: Optional[Tensor] = None,
+                      res_in: Optional[Tensor] = None, dx_out: Optional[Tensor] = None,
+                      res_out: Optional[Tensor] = None):
+    """dx = d(a+b).  dgamma/dbeta/dbias (fp32 [D]) are accumulated into when given (else fresh zeros for
+    dgamma/dbeta).  res_in: returns additionally res_out = res_in + dx."""
     D = a.shape[-1]
     dy = _rows(dy, BF16, "dy", D)
     a = _rows(a, BF16, "a", D)
     if b is not None:
         b = _rows(b, BF16, "b", D)
     M = a.shape[0]
-    dx = torch.empty(M, D, dtype=BF16, device=a.device)
-    dg = torch.zeros(D, dtype=torch.float32, device=a.device)
-    db = torch.zeros(D, dtype=torch.float32, device=a.device)
+    dx = torch.empty(M, D, dtype=BF16, device=a.device) if dx_out is None else dx_out
+    dg = torch.zeros(D, dtype=torch.float32, device=a.device) if dgamma is None else dgamma
+    db = torch.zeros(D, dtype=torch.float32, device=a.device) if dbeta is None else dbeta
+    ro = None
+    if res_in is not None:
+        res_in = _rows(res_in, BF16, "res_in", D)
+        ro = torch.empty(M, D, dtype=BF16, device=a.device) if res_out is None else res_out
     _lib.call("destr_add_layernorm_bwd", dy.data_ptr(), dy.stride(0), a.data_ptr(), a.stride(0), _ptr(b),
               0 if b is None else b.stride(0), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(),
-              dx.stride(0), dg.data_ptr(), db.data_ptr(), M, D, _stream())
+              dx.stride(0), dg.data_ptr(), db.data_ptr(), _ptr(dbias), _ptr(res_in),
+              0 if res_in is None else res_in.stride(0), _ptr(ro), 0 if ro is None else ro.stride(0), M, D, _stream())
+    if res_in is not None:
+        return dx, dg, db, ro
     return dx, dg, db
+
+
+def pos_mul_add_bwd_acc(dy: Tensor, pos: Tensor, dx_in: Tensor):
+    """-> (ds = dy*pos, dx_out = dx_in + dy)."""
+    ds, dx_out = torch.empty_like(dy), torch.empty_like(dy)
+    _lib.call("destr_pos_mul_add_bwd_acc", dy.data_ptr(), pos.data_ptr(), dx_in.data_ptr(), ds.data_ptr(),
+              dx_out.data_ptr(), dy.numel(), _stream())
+    return ds, dx_out
+
+
+def relu_bwd_colsum(dy: Tensor, h: Optional[Tensor], dbias: Tensor) -> Optional[Tensor]:
+    """dpre = dy*(h>0) (returned), dbias += colsum(dpre).  h=None: dbias += colsum(dy), returns None.
+    dy, h: bf16 [M,C] views with unit column stride."""
+    M, C = dy.shape
+    dpre = torch.empty(M, C, dtype=BF16, device=dy.device) if h is not None else None
+    _lib.call("destr_relu_bwd_colsum", dy.data_ptr(), dy.stride(0), _ptr(h), 0 if h is None else h.stride(0),
+              _ptr(dpre), C, dbias.data_ptr(), M, C, _stream())
+    return dpre
 
 
 # ----------------------------------------------------------------------------------------------
@@ -198,11 +228,12 @@ def box_refine(delta: Tensor, centers: Tensor) -> Tensor:
 
 def dec_qkv_prep(qkv_obj: Tensor, qk_pos: Tensor, pairs: Tensor, B: int, Q: int):
     """-> (qkv bf16 [B*Q,1536], cat bf16 [3, B*Q, 1024])."""
-    qkv_obj, qk_pos = _chk(qkv_obj.contiguous(), BF16, "qkv_obj"), _chk(qk_pos.contiguous(), BF16, "qk_pos")
+    qkv_obj = _chk(qkv_obj.contiguous(), BF16, "qkv_obj")
+    qk_pos = _rows(qk_pos, BF16, "qk_pos", 512)
     pairs = _chk(pairs.contiguous(), torch.int32, "pairs")
     qkv = torch.empty(B * Q, 1536, dtype=BF16, device=qkv_obj.device)
     cat = torch.empty(3, B * Q, 1024, dtype=BF16, device=qkv_obj.device)
-    _lib.call("destr_dec_qkv_prep", qkv_obj.data_ptr(), qk_pos.data_ptr(), pairs.data_ptr(), qkv.data_ptr(),
+    _lib.call("destr_dec_qkv_prep", qkv_obj.data_ptr(), qk_pos.data_ptr(), qk_pos.stride(0), pairs.data_ptr(), qkv.data_ptr(),
               cat.data_ptr(), B, Q, _stream())
     return qkv, cat
 
@@ -229,11 +260,14 @@ def dual_ln_mix(x: Tensor, o1: Tensor, o2: Tensor, pairs: Tensor, g1, b1, g2, b2
     return out, stats
 
 
-def dual_ln_mix_bwd(dout: Tensor, x: Tensor, o1: Tensor, o2: Tensor, pairs: Tensor, g1, g2, stats, lam: float, Q: int):
+def dual_ln_mix_bwd(dout: Tensor, x: Tensor, o1: Tensor, o2: Tensor, pairs: Tensor, g1, g2, stats, lam: float, Q: int,
+                    pg: Optional[Sequence[Tensor]] = None):
+    """pg: optional (dg1, db1, dg2, db2) fp32 [512] buffers to ACCUMULATE the parameter gradients into."""
     dout = _chk(dout.contiguous(), BF16, "dout")
     M = x.shape[0]
     dx, do1, do2 = torch.empty_like(x), torch.empty_like(o1), torch.empty_like(o2)
-    pg = torch.zeros(4, 512, dtype=torch.float32, device=x.device)
+    if pg is None:
+        pg = torch.zeros(4, 512, dtype=torch.float32, device=x.device)
     _lib.call("destr_dual_ln_mix_bwd", dout.data_ptr(), x.data_ptr(), o1.data_ptr(), o2.data_ptr(), pairs.data_ptr(),
               g1.data_ptr(), g2.data_ptr(), stats.data_ptr(), float(lam), dx.data_ptr(), do1.data_ptr(),
               do2.data_ptr(), pg[0].data_ptr(), pg[1].data_ptr(), pg[2].data_ptr(), pg[3].data_ptr(), M, Q, _stream())

@@ -1,0 +1,397 @@
+"""Hand-scheduled executor of the DESTR transformer half: explicit forward AND backward over the
+C-ABI kernels and cuBLAS GEMMs, with flat parameter / gradient buffers.
+
+Why: run through torch autograd op by op, a training step is ~2700 launches of which our kernels are
+12 % of the GPU time -- the rest is glue (per-parameter bf16 casts, slice/cat copies, zero fills,
+bias-gradient reductions, gradient accumulation adds; see profiles/r01_launches_graph_autograd.txt).
+Here the schedule is written out by hand instead:
+  * fp32 master parameters, their bf16 shadows and their gradients live in three flat buffers with one
+    layout in which every fused GEMM weight (in_proj, decoder q|k|v, the per-layer key/value/position
+    projections hoisted over all layers) is one contiguous block -> no cat, no cast, no slice kernels;
+    one kernel refreshes the shadows after the optimizer step, one converts the bf16 weight gradients.
+  * bias gradients come out of our LayerNorm-backward / ReLU-backward kernels as fused column sums;
+    residual-gradient adds are folded into kernel epilogues or GEMM accumulations (addmm, beta = 1).
+  * plain GEMMs are cuBLAS (torch.mm/addmm on bf16, fp32 accumulate); everything else is a destr_* kernel.
+The module-level autograd path (functional.py) computes the same thing and stays as the cross-check.
+
+Reference semantics: src/model/blocks/encoder_block.py:24-44,88-112; src/model/model.py:89-92;
+src/model/blocks/decoder_block.py:28-67,157-220,238-260.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import ops
+
+Tensor = torch.Tensor
+BF16 = torch.bfloat16
+_ALIGN = 64
+
+
+def _mm_bias(x: Tensor, w: Tensor, b: Tensor) -> Tensor:
+    return torch.addmm(b, x, w.t())
+
+
+def _mm_bias_relu(x: Tensor, w: Tensor, b: Tensor) -> Tensor:
+    # cuBLASLt GEMM with the bias + ReLU epilogue fused
+    return torch._addmm_activation(b, x, w.t(), use_gelu=False)
+
+
+class FlatParams:
+    """Flat fp32 master / bf16 shadow / gradient storage for the encoder + decoder parameters.
+
+    Region W (GEMM weights, fused groups contiguous) comes first, region S (biases, LayerNorm affine)
+    after it.  `module.parameters()` are re-pointed at views of the master buffer, so state_dict, the
+    reference parameter names and any optimizer keep working; the dead `_proj_to_q/k/v` parameters of
+    the reference encoder block are left alone (they never receive gradients)."""
+
+    def __init__(self, encoder: nn.Module, decoder: nn.Module, device):
+        e, d = dict(encoder.named_parameters()), dict(decoder.named_parameters())
+        Le, Ld = len(encoder._encoder), len(decoder._decoder)
+        self.Le, self.Ld = Le, Ld
+        W: List[Tuple[str, Tensor]] = []
+        S: List[Tuple[str, Tensor]] = []
+        for l in range(Le):
+            p = f"_encoder.{l}."
+            W += [(f"e{l}.in_w", e[p + "self_attn.in_proj_weight"]), (f"e{l}.out_w", e[p + "self_attn.out_proj.weight"]),
+                  (f"e{l}.fc1_w", e[p + "fc1.weight"]), (f"e{l}.fc2_w", e[p + "fc2.weight"])]
+            S += [(f"e{l}.in_b", e[p + "self_attn.in_proj_bias"]), (f"e{l}.out_b", e[p + "self_attn.out_proj.bias"]),
+                  (f"e{l}.fc1_b", e[p + "fc1.bias"]), (f"e{l}.fc2_b", e[p + "fc2.bias"]),
+                  (f"e{l}.n1_w", e[p + "norm1.weight"]), (f"e{l}.n1_b", e[p + "norm1.bias"]),
+                  (f"e{l}.n2_w", e[p + "norm2.weight"]), (f"e{l}.n2_b", e[p + "norm2.bias"])]
+        W += [("e.ps0_w", e["_pos_scale.0.weight"]), ("e.ps2_w", e["_pos_scale.2.weight"])]
+        S += [("e.ps0_b", e["_pos_scale.0.bias"]), ("e.ps2_b", e["_pos_scale.2.bias"]),
+              ("e.n_w", e["norm.weight"]), ("e.n_b", e["norm.bias"])]
+        for l in range(Ld):
+            p = f"_decoder.{l}."
+            W += [(f"d{l}.q_w", d[p + "_sa_proj_to_q_obj.weight"]), (f"d{l}.k_w", d[p + "_sa_proj_to_k_obj.weight"]),
+                  (f"d{l}.v_w", d[p + "_sa_proj_to_v_obj.weight"]), (f"d{l}.cq_w", d[p + "_ca_proj_to_q_obj.weight"]),
+                  (f"d{l}.cqp_w", d[p + "_ca_proj_to_q_pos.weight"])]
+            S += [(f"d{l}.n1_w", d[p + "norm1.weight"]), (f"d{l}.n1_b", d[p + "norm1.bias"]),
+                  (f"d{l}.n2_w", d[p + "norm2.weight"]), (f"d{l}.n2_b", d[p + "norm2.bias"])]
+            for i, br in enumerate(("_cls_branch.", "_reg_branch.")):
+                W += [(f"d{l}.b{i}.fc1_w", d[p + br + "fc1.weight"]), (f"d{l}.b{i}.fc2_w", d[p + br + "fc2.weight"])]
+                S += [(f"d{l}.b{i}.fc1_b", d[p + br + "fc1.bias"]), (f"d{l}.b{i}.fc2_b", d[p + br + "fc2.bias"]),
+                      (f"d{l}.b{i}.n1_w", d[p + br + "norm1.weight"]), (f"d{l}.b{i}.n1_b", d[p + br + "norm1.bias"]),
+                      (f"d{l}.b{i}.n2_w", d[p + br + "norm2.weight"]), (f"d{l}.b{i}.n2_b", d[p + br + "norm2.bias"])]
+        for l in range(Ld):  # hoisted groups: contiguous over layers
+            p = f"_decoder.{l}."
+            W += [(f"d{l}.ke_w", d[p + "_ca_proj_to_k_enc.weight"]), (f"d{l}.ve_w", d[p + "_ca_proj_to_v_enc.weight"])]
+        for l in range(Ld):
+            W += [(f"d{l}.kp_w", d[f"_decoder.{l}._ca_proj_to_k_pos.weight"])]
+        for l in range(Ld):
+            p = f"_decoder.{l}."
+            W += [(f"d{l}.sqp_w", d[p + "_sa_proj_to_q_pos.weight"]), (f"d{l}.skp_w", d[p + "_sa_proj_to_k_pos.weight"])]
+        W += [("d.ps0_w", d["_pos_scale.0.weight"]), ("d.ps2_w", d["_pos_scale.2.weight"])]
+        S += [("d.ps0_b", d["_pos_scale.0.bias"]), ("d.ps2_b", d["_pos_scale.2.bias"]),
+              ("d.n_w", d["norm.weight"]), ("d.n_b", d["norm.bias"])]
+
+        # fused groups must be adjacent and unpadded: weights are multiples of 64 elements already
+        self.off: Dict[str, Tuple[int, torch.Size]] = {}
+        o = 0
+        for name, t in W:
+            assert t.numel() % _ALIGN == 0
+            self.off[name] = (o, t.shape)
+            o += t.numel()
+        self.nW = o
+        for name, t in S:
+            self.off[name] = (o, t.shape)
+            o += (t.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.n = o
+        self.m32 = torch.zeros(o, dtype=torch.float32, device=device)
+        self.s16 = torch.zeros(o, dtype=BF16, device=device)
+        self.g32 = torch.zeros(o, dtype=torch.float32, device=device)
+        self.g16 = torch.zeros(self.nW, dtype=BF16, device=device)
+        self.params: List[nn.Parameter] = []
+        self._gviews: List[Tensor] = []
+        with torch.no_grad():
+            for name, t in W + S:
+                off, shape = self.off[name]
+                view = self.m32[off:off + t.numel()].view(shape)
+                view.copy_(t.detach().to(device))
+                t.data = view
+                t.grad = self.g32[off:off + t.numel()].view(shape)
+                self.params.append(t)
+                self._gviews.append(t.grad)
+        self.refresh()
+        self._written = set()
+
+    def _v(self, buf: Tensor, name: str, rows: Optional[int] = None) -> Tensor:
+        off, shape = self.off[name]
+        if rows is None:
+            return buf[off:off + shape.numel()].view(shape)
+        return buf[off:off + rows * shape[1]].view(rows, shape[1])  # fused group starting at `name`
+
+    def w(self, name, rows=None):      # bf16 shadow (weights and biases)
+        return self._v(self.s16, name, rows)
+
+    def f(self, name):                 # fp32 master (LayerNorm affine)
+        return self._v(self.m32, name)
+
+    def g(self, name):                 # fp32 gradient (region S: accumulated into by our kernels)
+        return self._v(self.g32, name)
+
+    def gw(self, name, rows=None):     # bf16 weight gradient (region W)
+        return self._v(self.g16, name, rows)
+
+    def refresh(self):
+        """bf16 shadows <- fp32 masters (one kernel; call after every optimizer step)."""
+        self.s16.copy_(self.m32)
+
+    def begin_backward(self):
+        self.g32[self.nW:].zero_()
+        self._written.clear()
+
+    def end_backward(self):
+        self.g32[:self.nW].copy_(self.g16)
+        for t, gv in zip(self.params, self._gviews):  # zero_grad(set_to_none=True) may have detached them
+            if t.grad is not gv:
+                t.grad = gv
+
+    def acc_gw(self, name: str, dy: Tensor, x: Tensor, rows: Optional[int] = None, sl: Optional[slice] = None):
+        """weight gradient dW (+)= dy^T x into the bf16 gradient buffer (first write overwrites)."""
+        gv = self.gw(name, rows)
+        key = name
+        if sl is not None:
+            gv = gv[sl]
+            key = (name, sl.start)
+        if key in self._written:
+            gv.addmm_(dy.t(), x)
+        else:
+            torch.mm(dy.t(), x, out=gv)
+            self._written.add(key)
+
+
+class HotPathRuntime:
+    """forward()/backward() of encoder -> fine_pos -> decoder on token-major bf16 activations."""
+
+    def __init__(self, encoder: nn.Module, decoder: nn.Module, bbox_embed: nn.Module, device):
+        self.P = FlatParams(encoder, decoder, device)
+        self.bbox = bbox_embed
+        self.Le, self.Ld = self.P.Le, self.P.Ld
+        self.saved = None
+        self.anchor = torch.zeros(1, device=device, requires_grad=True)
+
+    # ------------------------------------------------------------------ encoder
+    def _enc_fwd(self, l: int, x: Tensor, pos: Tensor, bits: Tensor, B: int, N: int):
+        P = self.P
+        h1 = _mm_bias_relu(x, P.w("e.ps0_w"), P.w("e.ps0_b"))
+        s = _mm_bias(h1, P.w("e.ps2_w"), P.w("e.ps2_b"))
+        xq = ops.pos_mul_add(x, pos, s)
+        Win, b_in = P.w(f"e{l}.in_w"), P.w(f"e{l}.in_b")
+        qk = _mm_bias(xq, Win[:512], b_in[:512])
+        v = _mm_bias(x, Win[512:], b_in[512:])
+        a, lse = ops.enc_attn_fwd(qk[:, :256], qk[:, 256:], v, bits, B, N, 8, 1.0 / math.sqrt(32))
+        o = _mm_bias(a, P.w(f"e{l}.out_w"), P.w(f"e{l}.out_b"))
+        x1, m1, r1 = ops.add_layernorm(x, o, P.f(f"e{l}.n1_w"), P.f(f"e{l}.n1_b"), save_stats=True)
+        f1 = _mm_bias_relu(x1, P.w(f"e{l}.fc1_w"), P.w(f"e{l}.fc1_b"))
+        g = _mm_bias(f1, P.w(f"e{l}.fc2_w"), P.w(f"e{l}.fc2_b"))
+        x2, m2, r2 = ops.add_layernorm(x1, g, P.f(f"e{l}.n2_w"), P.f(f"e{l}.n2_b"), save_stats=True)
+        xo, m3, r3 = ops.add_layernorm(x, x2, P.f("e.n_w"), P.f("e.n_b"), save_stats=True)
+        return xo, (x, h1, xq, qk, v, a, lse, o, x1, m1, r1, f1, g, x2, m2, r2, m3, r3)
+
+    def _enc_bwd(self, l: int, dxo: Tensor, sv, pos: Tensor, bits: Tensor, B: int, N: int) -> Tensor:
+        P = self.P
+        x, h1, xq, qk, v, a, lse, o, x1, m1, r1, f1, g, x2, m2, r2, m3, r3 = sv
+        # xo = LN(x + x2)
+        d3, _, _ = ops.add_layernorm_bwd(dxo, x, x2, P.f("e.n_w"), m3, r3, dgamma=P.g("e.n_w"), dbeta=P.g("e.n_b"))
+        # x2 = LN(x1 + fc2(relu(fc1 x1)))
+        d2, _, _ = ops.add_layernorm_bwd(d3, x1, g, P.f(f"e{l}.n2_w"), m2, r2, dgamma=P.g(f"e{l}.n2_w"),
+                                         dbeta=P.g(f"e{l}.n2_b"), dbias=P.g(f"e{l}.fc2_b"))
+        P.acc_gw(f"e{l}.fc2_w", d2, f1)
+        df1 = torch.mm(d2, P.w(f"e{l}.fc2_w"))
+        dpre = ops.relu_bwd_colsum(df1, f1, P.g(f"e{l}.fc1_b"))
+        P.acc_gw(f"e{l}.fc1_w", dpre, x1)
+        dx1 = torch.addmm(d2, dpre, P.w(f"e{l}.fc1_w"))
+        # x1 = LN(x + out_proj(attn));  dx = d3 + d1
+        d1, _, _, dx = ops.add_layernorm_bwd(dx1, x, o, P.f(f"e{l}.n1_w"), m1, r1, dgamma=P.g(f"e{l}.n1_w"),
+                                             dbeta=P.g(f"e{l}.n1_b"), dbias=P.g(f"e{l}.out_b"), res_in=d3)
+        P.acc_gw(f"e{l}.out_w", d1, a)
+        da = torch.mm(d1, P.w(f"e{l}.out_w"))
+        dqk, dv = ops.enc_attn_bwd(qk[:, :256], qk[:, 256:], v, bits, a, da, lse, B, N, 8, 1.0 / math.sqrt(32))
+        gb = P.g(f"e{l}.in_b")
+        ops.relu_bwd_colsum(dqk, None, gb[:512])
+        ops.relu_bwd_colsum(dv, None, gb[512:])
+        Win = P.w(f"e{l}.in_w")
+        P.acc_gw(f"e{l}.in_w", dqk, xq, sl=slice(0, 512))
+        P.acc_gw(f"e{l}.in_w", dv, x, sl=slice(512, 768))
+        dxq = torch.mm(dqk, Win[:512])
+        dx.addmm_(dv, Win[512:])
+        ds, dx = ops.pos_mul_add_bwd_acc(dxq, pos, dx)
+        return self._pos_scale_bwd("e", ds, h1, x, dx)
+
+    def _pos_scale_bwd(self, pfx: str, ds: Tensor, h1: Tensor, xin: Tensor, dx_acc: Tensor) -> Tensor:
+        """backward of s = W2 relu(W0 xin + b0) + b2 (shared MLP): accumulates weight grads, dx_acc += ..."""
+        P = self.P
+        ops.relu_bwd_colsum(ds, None, P.g(pfx + ".ps2_b"))
+        P.acc_gw(pfx + ".ps2_w", ds, h1)
+        dh = torch.mm(ds, P.w(pfx + ".ps2_w"))
+        dpre = ops.relu_bwd_colsum(dh, h1, P.g(pfx + ".ps0_b"))
+        P.acc_gw(pfx + ".ps0_w", dpre, xin)
+        dx_acc.addmm_(dpre, P.w(pfx + ".ps0_w"))
+        return dx_acc
+
+    # ------------------------------------------------------------------ decoder
+    def _dec_fwd(self, l: int, x: Tensor, kv_all, kpos_all, qkpos_all, sine, centers, bits, B, Q, N, lam, pairs_ov):
+        P = self.P
+        xr = x[:, 256:]
+        t1 = _mm_bias_relu(xr, P.w("d.ps0_w"), P.w("d.ps0_b"))
+        t2 = _mm_bias(t1, P.w("d.ps2_w"), P.w("d.ps2_b"))
+        sin = ops.mul(t2, sine)
+        bp = self.bbox
+        delta = F.linear(torch.relu(F.linear(xr.float(), bp[0].weight, bp[0].bias)), bp[2].weight, bp[2].bias)
+        coords = ops.box_refine(delta, centers)
+        pairs = ops.pair_indices(coords.view(B, Q, 4)) if pairs_ov is None else pairs_ov
+        qkv_obj = torch.mm(x, P.w(f"d{l}.q_w", rows=1536).t())
+        qkv, cat = ops.dec_qkv_prep(qkv_obj, qkpos_all[:, l * 512:(l + 1) * 512], pairs, B, Q)
+        o1, o2, lse1, lse2 = ops.dec_self_pair_attn_fwd(qkv, cat, B, Q)
+        o, st = ops.dual_ln_mix(x, o1, o2, pairs, P.f(f"d{l}.n1_w"), P.f(f"d{l}.n1_b"), P.f(f"d{l}.n2_w"),
+                                P.f(f"d{l}.n2_b"), lam, Q)
+        qo = torch.mm(o, P.w(f"d{l}.cq_w").t())
+        qp = torch.mm(sin, P.w(f"d{l}.cqp_w").t())
+        ke, vv = kv_all[:, l * 512:l * 512 + 256], kv_all[:, l * 512 + 256:(l + 1) * 512]
+        kp = kpos_all[:, l * 256:(l + 1) * 256]
+        ca, lse_c = ops.split_cross_attn_fwd(qo, qp, ke, kp, vv, bits, B, Q, N)
+        y = torch.empty_like(x)
+        br_saved = []
+        for i in range(2):
+            sl = slice(i * 256, (i + 1) * 256)
+            xb, mb1, rb1 = ops.add_layernorm(o[:, sl], ca[:, sl], P.f(f"d{l}.b{i}.n1_w"), P.f(f"d{l}.b{i}.n1_b"),
+                                             save_stats=True)
+            f = _mm_bias_relu(xb, P.w(f"d{l}.b{i}.fc1_w"), P.w(f"d{l}.b{i}.fc1_b"))
+            g = _mm_bias(f, P.w(f"d{l}.b{i}.fc2_w"), P.w(f"d{l}.b{i}.fc2_b"))
+            _, mb2, rb2 = ops.add_layernorm(xb, g, P.f(f"d{l}.b{i}.n2_w"), P.f(f"d{l}.b{i}.n2_b"), save_stats=True,
+                                            out=y[:, sl])
+            br_saved.append((xb, mb1, rb1, f, g, mb2, rb2))
+        xo, mn, rn = ops.add_layernorm(x, y, P.f("d.n_w"), P.f("d.n_b"), save_stats=True)
+        return xo, (x, t1, sin, pairs, qkv, cat, o1, o2, lse1, lse2, o, st, qo, qp, ca, lse_c, y, br_saved, mn, rn), \
+            (coords, pairs)
+
+    def _dec_bwd(self, l: int, dxo: Tensor, sv, ctx, d_kv_all, d_kpos_all, d_qkpos_all) -> Tensor:
+        P = self.P
+        kv_all, kpos_all, sine, bits, kpm, B, Q, N, lam = ctx
+        x, t1, sin, pairs, qkv, cat, o1, o2, lse1, lse2, o, st, qo, qp, ca, lse_c, y, br_saved, mn, rn = sv
+        d, _, _ = ops.add_layernorm_bwd(dxo, x, y, P.f("d.n_w"), mn, rn, dgamma=P.g("d.n_w"), dbeta=P.g("d.n_b"))
+        dca = torch.empty_like(x)
+        for i in range(2):
+            sl = slice(i * 256, (i + 1) * 256)
+            xb, mb1, rb1, f, g, mb2, rb2 = br_saved[i]
+            pf = f"d{l}.b{i}."
+            d2, _, _ = ops.add_layernorm_bwd(d[:, sl], xb, g, P.f(pf + "n2_w"), mb2, rb2, dgamma=P.g(pf + "n2_w"),
+                                             dbeta=P.g(pf + "n2_b"), dbias=P.g(pf + "fc2_b"))
+            P.acc_gw(pf + "fc2_w", d2, f)
+            df = torch.mm(d2, P.w(pf + "fc2_w"))
+            dpre = ops.relu_bwd_colsum(df, f, P.g(pf + "fc1_b"))
+            P.acc_gw(pf + "fc1_w", dpre, xb)
+            dxb = torch.addmm(d2, dpre, P.w(pf + "fc1_w"))
+            ops.add_layernorm_bwd(dxb, o[:, sl], ca[:, sl], P.f(pf + "n1_w"), mb1, rb1, dgamma=P.g(pf + "n1_w"),
+                                  dbeta=P.g(pf + "n1_b"), dx_out=dca[:, sl])
+        ke, vv = kv_all[:, l * 512:l * 512 + 256], kv_all[:, l * 512 + 256:(l + 1) * 512]
+        kp = kpos_all[:, l * 256:(l + 1) * 256]
+        dqo, dqp, dke, dkp, dvv = ops.split_cross_attn_bwd(qo, qp, ke, kp, vv, kpm, ca, dca, lse_c, B, Q, N)
+        d_kv_all[:, l * 512:l * 512 + 256].copy_(dke)
+        d_kv_all[:, l * 512 + 256:(l + 1) * 512].copy_(dvv)
+        d_kpos_all[:, l * 256:(l + 1) * 256].copy_(dkp)
+        P.acc_gw(f"d{l}.cq_w", dqo, o)
+        do = torch.addmm(dca, dqo, P.w(f"d{l}.cq_w"))   # d(o) = d(o_cls|o_reg residual) + dq_obj W
+        P.acc_gw(f"d{l}.cqp_w", dqp, sin)
+        dsin = torch.mm(dqp, P.w(f"d{l}.cqp_w"))
+        dx2, do1, do2, *_ = ops.dual_ln_mix_bwd(do, x, o1, o2, pairs, P.f(f"d{l}.n1_w"), P.f(f"d{l}.n2_w"), st, lam, Q,
+                                                pg=(P.g(f"d{l}.n1_w"), P.g(f"d{l}.n1_b"), P.g(f"d{l}.n2_w"),
+                                                    P.g(f"d{l}.n2_b")))
+        dx = d + dx2
+        d_qkv, d_cat = ops.dec_self_pair_attn_bwd(qkv, cat, o1, o2, do1, do2, lse1, lse2, B, Q)
+        d_qkv_obj, d_qkpos = ops.dec_qkv_prep_bwd(d_qkv, d_cat, pairs, B, Q)
+        d_qkpos_all[:, l * 512:(l + 1) * 512].copy_(d_qkpos)
+        P.acc_gw(f"d{l}.q_w", d_qkv_obj, x, rows=1536)
+        dx.addmm_(d_qkv_obj, P.w(f"d{l}.q_w", rows=1536))
+        # sin = sine * pos_scale(x_reg)
+        dt2 = ops.mul(dsin, sine)
+        xr = x[:, 256:]
+        dxr = torch.zeros(x.shape[0], 256, dtype=BF16, device=x.device)
+        self._pos_scale_bwd("d", dt2, t1, xr, dxr)
+        dx[:, 256:] += dxr
+        return dx
+
+    # ------------------------------------------------------------------ whole path
+    def forward(self, x: Tensor, pos: Tensor, bits: Tensor, kpm: Tensor, sel: Tensor, pos_embed: Tensor, sine: Tensor,
+                centers: Tensor, B: int, N: int, Q: int, lam: float = 0.5, pairs_override=None, aux=None):
+        """x, pos bf16 [B*N,256]; sel bf16 [B*Q,512]; pos_embed, sine bf16 [B*Q,256]; centers fp32 [B*Q,2].
+        Returns (dec_out bf16 [B*Q,512], enc_out bf16 [B*N,256])."""
+        P, Ld = self.P, self.Ld
+        enc_saved = []
+        for l in range(self.Le):
+            x, sv = self._enc_fwd(l, x, pos, bits, B, N)
+            enc_saved.append(sv)
+        enc = x
+        # fine_pos = pos * encoder._pos_scale(enc_out)   (model.py:89-92)
+        hfp = _mm_bias_relu(enc, P.w("e.ps0_w"), P.w("e.ps0_b"))
+        fine = ops.mul(_mm_bias(hfp, P.w("e.ps2_w"), P.w("e.ps2_b")), pos)
+        # projections of layer-invariant inputs for ALL decoder layers: three packed GEMMs
+        kv_all = torch.mm(enc, P.w("d0.ke_w", rows=Ld * 512).t())
+        kpos_all = torch.mm(fine, P.w("d0.kp_w", rows=Ld * 256).t())
+        qkpos_all = torch.mm(pos_embed, P.w("d0.sqp_w", rows=Ld * 512).t())
+        dec_saved = []
+        y = sel
+        for l in range(Ld):
+            y, sv, a = self._dec_fwd(l, y, kv_all, kpos_all, qkpos_all, sine, centers, bits, B, Q, N, lam,
+                                     None if pairs_override is None else pairs_override[l])
+            dec_saved.append(sv)
+            if aux is not None:
+                aux.append(a)
+        self.saved = (enc_saved, dec_saved, enc, hfp, fine, pos, bits, kpm, kv_all, kpos_all, pos_embed, sine,
+                      B, N, Q, lam)
+        return y, enc
+
+    def backward(self, d_dec: Tensor, d_enc_ext: Optional[Tensor] = None) -> Tensor:
+        """Overwrites the .grad of every encoder/decoder parameter (= zero_grad + backward) and returns
+        the gradient w.r.t. the encoder input tokens (bf16 [B*N,256])."""
+        P, Ld = self.P, self.Ld
+        enc_saved, dec_saved, enc, hfp, fine, pos, bits, kpm, kv_all, kpos_all, pos_embed, sine, B, N, Q, lam = self.saved
+        P.begin_backward()
+        d_kv_all = torch.empty_like(kv_all)
+        d_kpos_all = torch.empty_like(kpos_all)
+        d_qkpos_all = torch.empty(B * Q, Ld * 512, dtype=BF16, device=enc.device)
+        ctx = (kv_all, kpos_all, sine, bits, kpm, B, Q, N, lam)
+        dy = d_dec.contiguous()
+        for l in reversed(range(Ld)):
+            dy = self._dec_bwd(l, dy, dec_saved[l], ctx, d_kv_all, d_kpos_all, d_qkpos_all)
+        P.acc_gw("d0.ke_w", d_kv_all, enc, rows=Ld * 512)
+        d_enc = torch.mm(d_kv_all, P.w("d0.ke_w", rows=Ld * 512))
+        P.acc_gw("d0.kp_w", d_kpos_all, fine, rows=Ld * 256)
+        d_fine = torch.mm(d_kpos_all, P.w("d0.kp_w", rows=Ld * 256))
+        P.acc_gw("d0.sqp_w", d_qkpos_all, pos_embed, rows=Ld * 512)
+        du = ops.mul(d_fine, pos)
+        if d_enc_ext is not None:
+            d_enc += d_enc_ext
+        dx = self._pos_scale_bwd("e", du, hfp, enc, d_enc)
+        for l in reversed(range(self.Le)):
+            dx = self._enc_bwd(l, dx, enc_saved[l], pos, bits, B, N)
+        P.end_backward()
+        self.saved = None
+        return dx
+
+
+class _RuntimeFn(torch.autograd.Function):
+    """Splices the hand-written forward/backward into torch autograd (heads + loss stay in autograd)."""
+
+    @staticmethod
+    def forward(ctx, rt: HotPathRuntime, anchor, x, pos, bits, kpm, sel, pos_embed, sine, centers, B, N, Q,
+                pairs_override, aux):
+        # `anchor` is a dummy leaf with requires_grad=True: the parameters are not autograd inputs here, so
+        # without it the outputs would not require grad and backward() would never be called.
+        ctx.rt = rt
+        ctx.set_materialize_grads(False)
+        dec, enc = rt.forward(x, pos, bits, kpm, sel, pos_embed, sine, centers, B, N, Q, pairs_override=pairs_override,
+                              aux=aux)
+        return dec, enc
+
+    @staticmethod
+    def backward(ctx, d_dec, d_enc):
+        dx = ctx.rt.backward(d_dec, d_enc)
+        return (None, None, dx) + (None,) * 12

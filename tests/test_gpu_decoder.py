@@ -88,7 +88,8 @@ def test_matcher_c5_shape_bit_exact():
     assert all(torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) for a, b in zip(got, ref))
 
 
-def test_transformer_half_fwd_bwd():
+@pytest.mark.parametrize("runtime", [False, True])
+def test_transformer_half_fwd_bwd(runtime):
     """Whole hot path (2+2 layers, N=1050 padded, Q=100): forward vs oracle with the oracle's pairing injected
     (SURVEY 7.3-3), gradients vs stock-torch bf16 autocast yardstick."""
     from object_detection_destr_b200.encoder import disable_dropout
@@ -121,31 +122,22 @@ def test_transformer_half_fwd_bwd():
     gbox = torch.randn(B, Q, 4, generator=g)
     (ref["pred_class"] * gcls).sum().add((ref["pred_boxes"] * gbox).sum()).backward()
 
-    model = TransformerHalf(Namespace(hidden_dim=256, num_encoder_blocks=L, num_decoder_blocks=L, num_cls=C))
+    model = TransformerHalf(Namespace(hidden_dim=256, num_encoder_blocks=L, num_decoder_blocks=L, num_cls=C),
+                            runtime=runtime)
     model._encoder.load_state_dict(enc_sd)
     model._decoder.load_state_dict(dec_sd)
     model._cls_embed.load_state_dict(cls_sd)
     model._bbox_embed.load_state_dict(bbox_sd)
     disable_dropout(model).cuda()
     # inject the oracle's pairing so the comparison is not dominated by argmax flips under bf16
-    orig = Fn.decoder_tokens
-    aux = []
-    Fn.decoder_tokens = lambda *a, **k: orig(*a, pairs_override=ref_pairs, aux=aux, **k)
-    try:
-        out, _ = model(feats.cuda(), mask.cuda(), sel.cuda(), centers.cuda())
-    finally:
-        Fn.decoder_tokens = orig
+    out, _ = model(feats.cuda(), mask.cuda(), sel.cuda(), centers.cuda(), pairs_override=ref_pairs)
     (out["pred_class"] * gcls.cuda()).sum().add((out["pred_boxes"] * gbox.cuda()).sum()).backward()
     _cmp(out["pred_class"], ref["pred_class"].detach(), 1.5e-1, 1.5e-2, "pred_class (logits)")
     _cmp(out["pred_boxes"], ref["pred_boxes"].detach(), 2e-2, 2e-3, "pred_boxes")
     # own pairing (no injection) must agree with the oracle's on (almost) every query
     with torch.no_grad():
         aux2 = []
-        Fn.decoder_tokens = lambda *a, **k: orig(*a, aux=aux2, **k)
-        try:
-            model(feats.cuda(), mask.cuda(), sel.cuda(), centers.cuda())
-        finally:
-            Fn.decoder_tokens = orig
+        model(feats.cuda(), mask.cuda(), sel.cuda(), centers.cuda(), aux=aux2)
     for l, (coords, pairs) in enumerate(aux2):
         agree = (pairs.cpu() == ref_pairs[l].cpu()).all(-1).float().mean()
         cerr = (coords.view(B, Q, 4).cpu() - ref_coords[l].detach()).abs().max()
@@ -162,23 +154,20 @@ def test_transformer_half_fwd_bwd():
         return float((a.float().cpu() - b).norm() / b.norm())
 
     named = dict(model.named_parameters())
-    checks = [("_encoder._encoder.0.fc1.weight", r_e["_encoder.0.fc1.weight"], y_e["_encoder.0.fc1.weight"]),
-              ("_encoder._encoder.1.self_attn.in_proj_weight", r_e["_encoder.1.self_attn.in_proj_weight"], y_e["_encoder.1.self_attn.in_proj_weight"]),
-              ("_encoder._pos_scale.2.weight", r_e["_pos_scale.2.weight"], y_e["_pos_scale.2.weight"]),
-              ("_decoder._decoder.0._sa_proj_to_q_obj.weight", r_d["_decoder.0._sa_proj_to_q_obj.weight"], y_d["_decoder.0._sa_proj_to_q_obj.weight"]),
-              ("_decoder._decoder.0._sa_proj_to_k_pos.weight", r_d["_decoder.0._sa_proj_to_k_pos.weight"], y_d["_decoder.0._sa_proj_to_k_pos.weight"]),
-              ("_decoder._decoder.1._sa_proj_to_v_obj.weight", r_d["_decoder.1._sa_proj_to_v_obj.weight"], y_d["_decoder.1._sa_proj_to_v_obj.weight"]),
-              ("_decoder._decoder.0._ca_proj_to_k_enc.weight", r_d["_decoder.0._ca_proj_to_k_enc.weight"], y_d["_decoder.0._ca_proj_to_k_enc.weight"]),
-              ("_decoder._decoder.1._ca_proj_to_k_pos.weight", r_d["_decoder.1._ca_proj_to_k_pos.weight"], y_d["_decoder.1._ca_proj_to_k_pos.weight"]),
-              ("_decoder._decoder.1._ca_proj_to_v_enc.weight", r_d["_decoder.1._ca_proj_to_v_enc.weight"], y_d["_decoder.1._ca_proj_to_v_enc.weight"]),
-              ("_decoder._decoder.0._ca_proj_to_q_pos.weight", r_d["_decoder.0._ca_proj_to_q_pos.weight"], y_d["_decoder.0._ca_proj_to_q_pos.weight"]),
-              ("_decoder._decoder.1._cls_branch.fc1.weight", r_d["_decoder.1._cls_branch.fc1.weight"], y_d["_decoder.1._cls_branch.fc1.weight"]),
-              ("_decoder._decoder.0.norm2.weight", r_d["_decoder.0.norm2.weight"], y_d["_decoder.0.norm2.weight"]),
-              ("_decoder._pos_scale.0.weight", r_d["_pos_scale.0.weight"], y_d["_pos_scale.0.weight"]),
-              ("_decoder.norm.weight", r_d["norm.weight"], y_d["norm.weight"]),
-              ("_cls_embed.weight", r_c["weight"], y_c["weight"]),
-              ("_bbox_embed.2.weight", r_b["2.weight"], y_b["2.weight"])]
+    # EVERY parameter of the hot path (weights, biases, LayerNorm affine, shared and hoisted groups)
+    checks = []
+    for prefix, r_sd, y_sd in (("_encoder.", r_e, y_e), ("_decoder.", r_d, y_d), ("_cls_embed.", r_c, y_c),
+                               ("_bbox_embed.", r_b, y_b)):
+        for k in r_sd:
+            if "_proj_to_q." in k or "_proj_to_k." in k or "_proj_to_v." in k:
+                if prefix == "_encoder.":
+                    assert named[prefix + k].grad is None  # dead parameters
+                    continue
+            checks.append((prefix + k, r_sd[k], y_sd[k]))
+    assert len(checks) > 100
     for name, r, y in checks:
         ours, yd = rel(named[name].grad, r.grad), rel(y.grad, r.grad)
-        print(f"grad {name}: rel-fro ours {ours:.3e}  torch-autocast {yd:.3e}")
+        if ours > max(1.5 * yd, 2e-2):
+            print(f"grad {name}: rel-fro ours {ours:.3e}  torch-autocast {yd:.3e}")
         assert ours <= max(2.5 * yd, 4e-2), name
+    print(f"checked {len(checks)} parameter gradients")
