@@ -158,6 +158,19 @@ int destr_split_cross_attn_fwd(const void* q_obj, const void* q_pos, const void*
                                int words_per_row, void* out, float* lse, float* ws_partial, int B, int Q, int N,
                                float scale, void* stream);
 
+/* Backward of destr_split_cross_attn_fwd, stage 1: recomputes S and dP = dO.V^T on tcgen05 and applies
+ * the softmax backward.  Rows are ordered (2q + br):
+ *   P_all, dS_all : bf16 [B, 2Q, Np]   (Np = ceil(N/128)*128; padded / masked keys are written as 0)
+ *   dS_sum        : bf16 [B,  Q, Np]   = dS_cls + dS_reg
+ *   delta         : fp32 [B, 2, Q] workspace (rowsum(dO o O), computed here)
+ * The caller finishes with five batched GEMMs on plain views (see ops.split_cross_attn_bwd):
+ *   dV = P^T dO, dK_enc = dS^T q_obj, dK_pos = dSsum^T q_pos, dq_obj = dS k_enc, dq_pos = dSsum k_pos. */
+int destr_split_cross_attn_bwd_ds(const void* q_obj, const void* q_pos, const void* k_enc, const void* k_pos,
+                                  const void* v, int ld_kenc, int ld_kpos, int ld_v, const uint32_t* mask_bits,
+                                  int words_per_row, const void* out, const void* dout, const float* lse,
+                                  float* delta, void* P_all, void* dS_all, void* dS_sum, int B, int Q, int N,
+                                  float scale, void* stream);
+
 /* ---------------- set-prediction cost matrix ---------------- */
 
 /* Matching cost of HungarianMatcher / HungarianMatcherWoL1 (matcher.py:72-107, 158-184;

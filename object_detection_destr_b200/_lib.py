@@ -42,6 +42,8 @@ SIGNATURES = {
     "destr_dec_qkv_prep": [_p, _p, _i, _p, _p, _p, _i, _i, _p],
     "destr_dec_self_pair_attn_fwd": [_p, _p, _p, _p, _p, _p, _i, _i, _p],
     "destr_split_cross_attn_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _p, _i, _p, _p, _p, _i, _i, _i, _f, _p],
+    "destr_split_cross_attn_bwd_ds": [_p, _p, _p, _p, _p, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i,
+                                      _f, _p],
     "destr_pair_indices": [_p, _p, _i, _i, _p],
     "destr_box_refine": [_p, _p, _p, _i, _p],
     "destr_match_cost_blockdiag": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _f, _i, _p],
@@ -57,7 +59,7 @@ lib.destr_last_error.argtypes = []
 lib.destr_last_error.restype = C.c_char_p
 
 # kernels launched per C-ABI call (bench.py reports the sum over a step as gpu_launches)
-KERNELS_PER_CALL = {"destr_enc_attn_bwd": 3, "destr_split_cross_attn_fwd": 2}
+KERNELS_PER_CALL = {"destr_enc_attn_bwd": 3, "destr_split_cross_attn_fwd": 2, "destr_split_cross_attn_bwd_ds": 2}
 launch_count = 0
 # bench.py: {name: []} -> (start, end) CUDA-event pairs are appended around every call of `name`
 KERNEL_TIMERS = None

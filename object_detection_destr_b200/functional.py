@@ -192,15 +192,15 @@ class _SplitCrossAttn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q_obj, q_pos, k_enc, k_pos, v, bits, kpm, B, Q, N):
         out, lse = ops.split_cross_attn_fwd(q_obj, q_pos, k_enc, k_pos, v, bits, B, Q, N)
-        ctx.save_for_backward(q_obj, q_pos, k_enc, k_pos, v, kpm, out, lse)
+        ctx.save_for_backward(q_obj, q_pos, k_enc, k_pos, v, bits, out, lse)
         ctx.dims = (B, Q, N)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        q_obj, q_pos, k_enc, k_pos, v, kpm, out, lse = ctx.saved_tensors
+        q_obj, q_pos, k_enc, k_pos, v, bits, out, lse = ctx.saved_tensors
         B, Q, N = ctx.dims
-        g = ops.split_cross_attn_bwd(q_obj, q_pos, k_enc, k_pos, v, kpm, out, dout.contiguous(), lse, B, Q, N)
+        g = ops.split_cross_attn_bwd(q_obj, q_pos, k_enc, k_pos, v, bits, out, dout.contiguous(), lse, B, Q, N)
         return g + (None, None, None, None, None)
 
 

@@ -294,7 +294,35 @@ def split_cross_attn_fwd(q_obj: Tensor, q_pos: Tensor, k_enc: Tensor, k_pos: Ten
 
 # Backward of the decoder attention ops: cuBLAS batched GEMMs + elementwise torch on the GPU
 # (see _composed_bwd.py for status; the fused tcgen05 backward exists for the encoder only so far).
-from ._composed_bwd import dec_qkv_prep_bwd, dec_self_pair_attn_bwd, split_cross_attn_bwd  # noqa: E402,F401
+from ._composed_bwd import dec_qkv_prep_bwd, dec_self_pair_attn_bwd  # noqa: E402,F401
+from ._composed_bwd import _bmm_f32  # noqa: E402
+
+
+def split_cross_attn_bwd(q_obj: Tensor, q_pos: Tensor, k_enc: Tensor, k_pos: Tensor, v: Tensor, mask_bits: Tensor,
+                         out: Tensor, dout: Tensor, lse: Tensor, B: int, Q: int, N: int):
+    """Backward of split_cross_attn_fwd: the tcgen05 kernel recomputes S, dP and does the softmax backward
+    (P, dS, dS_cls+dS_reg in bf16); five cuBLAS batched GEMMs on plain views finish the contractions.
+    -> (dq_obj [B*Q,512], dq_pos [B*Q,256], dk_enc, dk_pos, dv [B*N,256]) bf16."""
+    Np = ((N + 127) // 128) * 128
+    dev = q_obj.device
+    dout = _chk(dout.contiguous(), BF16, "dout")
+    P_all = torch.empty(B, 2 * Q, Np, dtype=BF16, device=dev)
+    dS_all = torch.empty(B, 2 * Q, Np, dtype=BF16, device=dev)
+    dS_sum = torch.empty(B, Q, Np, dtype=BF16, device=dev)
+    delta = torch.empty(B, 2, Q, dtype=torch.float32, device=dev)
+    _lib.call("destr_split_cross_attn_bwd_ds", q_obj.data_ptr(), q_pos.data_ptr(), k_enc.data_ptr(), k_pos.data_ptr(),
+              v.data_ptr(), k_enc.stride(0), k_pos.stride(0), v.stride(0), mask_bits.data_ptr(), mask_bits.shape[1],
+              out.data_ptr(), dout.data_ptr(), lse.data_ptr(), delta.data_ptr(), P_all.data_ptr(), dS_all.data_ptr(),
+              dS_sum.data_ptr(), B, Q, N, 1.0 / math.sqrt(512.0), _stream())
+    Pv, dSv, dSs = P_all[:, :, :N], dS_all[:, :, :N], dS_sum[:, :, :N]
+    v3 = lambda t: t.as_strided((B, N, 256), (N * t.stride(0), t.stride(0), 1))  # [B*N,256] view -> [B,N,256]
+    do_v, qo_v, qp_v = dout.view(B, 2 * Q, 256), q_obj.view(B, 2 * Q, 256), q_pos.view(B, Q, 256)
+    dv = torch.bmm(Pv.transpose(1, 2), do_v).view(B * N, 256)
+    dke = torch.bmm(dSv.transpose(1, 2), qo_v).view(B * N, 256)
+    dkp = torch.bmm(dSs.transpose(1, 2), qp_v).view(B * N, 256)
+    dqo = torch.bmm(dSv, v3(k_enc)).view(B * Q, 512)
+    dqp = torch.bmm(dSs, v3(k_pos)).view(B * Q, 256)
+    return dqo, dqp, dke, dkp, dv
 
 
 # ----------------------------------------------------------------------------------------------

@@ -293,7 +293,7 @@ class HotPathRuntime:
                                   dbeta=P.g(pf + "n1_b"), dx_out=dca[:, sl])
         ke, vv = kv_all[:, l * 512:l * 512 + 256], kv_all[:, l * 512 + 256:(l + 1) * 512]
         kp = kpos_all[:, l * 256:(l + 1) * 256]
-        dqo, dqp, dke, dkp, dvv = ops.split_cross_attn_bwd(qo, qp, ke, kp, vv, kpm, ca, dca, lse_c, B, Q, N)
+        dqo, dqp, dke, dkp, dvv = ops.split_cross_attn_bwd(qo, qp, ke, kp, vv, bits, ca, dca, lse_c, B, Q, N)
         d_kv_all[:, l * 512:l * 512 + 256].copy_(dke)
         d_kv_all[:, l * 512 + 256:(l + 1) * 512].copy_(dvv)
         d_kpos_all[:, l * 256:(l + 1) * 256].copy_(dkp)

@@ -221,6 +221,21 @@ def check_decoder_kernels(B=2, Q=100, N=300):
         refs.append(O.sdp_attention(qq[:, None], kk[:, None], vv[:, None], key_padding_mask=kpm))
     refc = torch.cat(refs, -1).reshape(M, 512)
     ok &= report(f"split_cross_attn fwd Q={Q} N={N}", out, refc, 1e-2, 2e-2)
+    # backward vs oracle autograd (same bf16-rounded inputs)
+    dout = (torch.randn(M, 512, generator=g) * 0.5).bfloat16()
+    leaves = [t.float().requires_grad_() for t in (q_obj, q_pos, kv[:, :256], kv[:, 512:], kv[:, 256:512])]
+    qo_r, qp_r = leaves[0].reshape(B, Q, 512), leaves[1].reshape(B, Q, 256)
+    ke_r, kp_r, v_r = (t.reshape(B, N, 256) for t in leaves[2:])
+    outs = []
+    for br in range(2):
+        qq = torch.cat([qo_r[..., br * 256:(br + 1) * 256], qp_r], -1)
+        kk = torch.cat([ke_r, kp_r], -1)
+        outs.append(O.sdp_attention(qq[:, None], kk[:, None], v_r[:, None], key_padding_mask=kpm))
+    torch.cat(outs, -1).reshape(M, 512).backward(dout.float())
+    got = ops.split_cross_attn_bwd(q_obj.to(dev), q_pos.to(dev), kv_d[:, :256], kv_d[:, 512:], kv_d[:, 256:512], bits,
+                                   out, dout.to(dev), lse, B, Q, N)
+    for nm, gt, lf in zip(("dq_obj", "dq_pos", "dk_enc", "dk_pos", "dv"), got, leaves):
+        ok &= report(f"split_cross_attn bwd {nm}", gt, lf.grad, 2e-2 * float(lf.grad.abs().max()), 2e-2)
     return ok
 
 
