@@ -128,15 +128,15 @@ int destr_box_refine(const float* delta, const float* centers, float* boxes, int
 /* SA operand preparation (decoder_block.py:167-177) + the left/right gathers of pair attention
  * (pair_self_attention.py:47-89) in one pass.
  *   qkv_obj bf16 [B*Q,1536] = [W_q x | W_k x | W_v x];  qk_pos bf16 [B*Q,512] (row pitch ld_pos) = [W_qp p | W_kp p]
- *   -> qkv bf16 [B*Q,1536] = [q_obj+[qp|qp] | k_obj+[kp|kp] | v]
- *   -> cat bf16 [3][B*Q,1024]: cat[w][i, 128h .. 128h+64) = x_w[L_i, 64h..], [128h+64 .. 128h+128) = x_w[R_i, 64h..]
- *      with (L_i, R_i) = pairs[i] (indices within the image) and x_0,x_1,x_2 = q,k,v. */
+ *   -> qkv bf16 [3][B,8,Q,64]  head-major: x_0 = q_obj+[qp|qp], x_1 = k_obj+[kp|kp], x_2 = v
+ *   -> cat bf16 [3][B,8,Q,128] head-major: cat[w][b,h,i, 0..64) = x_w[b,h,L_i], [64..128) = x_w[b,h,R_i]
+ *      with (L_i, R_i) = pairs[b,i] (indices within the image). */
 int destr_dec_qkv_prep(const void* qkv_obj, const void* qk_pos, int ld_pos, const int32_t* pairs, void* qkv,
                        void* cat, int B, int Q, void* stream);
 
 /* Decoder self-attention (self_attention.py:26-45, 8 heads x 64, scale 1/8) and pair self-attention
  * (pair_self_attention.py:91-99: softmax(Ql.Kl^T + Qr.Kr^T)/sqrt(128) . [Vl|Vr]) in ONE launch on
- * tcgen05.  qkv / cat as written by destr_dec_qkv_prep.  o1 bf16 [B*Q,512]; o2 bf16 [B*Q,1024]
+ * tcgen05.  qkv / cat head-major as written by destr_dec_qkv_prep.  o1 bf16 [B*Q,512]; o2 bf16 [B*Q,1024]
  * (head-major, before the slot masking that destr_dual_ln_mix_fwd applies).  lse1/lse2 fp32 [B,8,Q]
  * (log2 domain, for the backward; may be NULL).  Q <= 384. */
 int destr_dec_self_pair_attn_fwd(const void* qkv, const void* cat, void* o1, void* o2, float* lse1, float* lse2,

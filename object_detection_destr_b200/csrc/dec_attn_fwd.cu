@@ -53,21 +53,22 @@ __device__ __forceinline__ void body(Smem& sm, const CUtensorMap* tm_q, const CU
   constexpr int NCH = D / 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkv = (Q + BT - 1) / BT;
-  const int row_base = b * Q;
+  const int row_base = b * Q;            // token-major output rows
+  const int hrow = (b * 8 + h) * Q;      // head-major operand rows: [B, 8, Q, D]
   constexpr uint32_t C_O = 384;
 
   if (warp == 4) {
     if (elect_one()) {
       mbar_arrive_expect_tx(&sm.q_full, NCH * CHUNK_BYTES);
-      for (int c = 0; c < NCH; ++c) tma_load_2d(sm.q[c], tm_q, &sm.q_full, h * D + c * 64, row_base + mt * BT);
+      for (int c = 0; c < NCH; ++c) tma_load_2d(sm.q[c], tm_q, &sm.q_full, c * 64, hrow + mt * BT);
       for (int j = 0; j < nkv; ++j) {
         mbar_arrive_expect_tx(&sm.k_full[j], NCH * CHUNK_BYTES);
-        for (int c = 0; c < NCH; ++c) tma_load_2d(sm.kv[j][c], tm_k, &sm.k_full[j], h * D + c * 64, row_base + j * BT);
+        for (int c = 0; c < NCH; ++c) tma_load_2d(sm.kv[j][c], tm_k, &sm.k_full[j], c * 64, hrow + j * BT);
       }
       for (int j = 0; j < nkv; ++j) {
         mbar_wait(&sm.k_free[j], 0, 21);
         mbar_arrive_expect_tx(&sm.v_full[j], NCH * CHUNK_BYTES);
-        for (int c = 0; c < NCH; ++c) tma_load_2d(sm.kv[j][c], tm_v, &sm.v_full[j], h * D + c * 64, row_base + j * BT);
+        for (int c = 0; c < NCH; ++c) tma_load_2d(sm.kv[j][c], tm_v, &sm.v_full[j], c * 64, hrow + j * BT);
       }
     }
     __syncwarp();
@@ -230,12 +231,13 @@ __device__ __forceinline__ uint4 add_bf16x8(uint4 a, uint4 b) {
 }
 
 __global__ void dec_qkv_prep_kernel(const __nv_bfloat16* __restrict__ qkv_obj,  // [B*Q, 1536] = q|k|v
-                                    const __nv_bfloat16* __restrict__ qk_pos,   // [B*Q, 512] = qp|kp
-                                    const int32_t* __restrict__ pairs, __nv_bfloat16* __restrict__ qkv,  // [B*Q,1536]
-                                    __nv_bfloat16* __restrict__ cat,  // [3][B*Q, 1024]
+                                    const __nv_bfloat16* __restrict__ qk_pos,   // [B*Q, 512] = qp|kp (pitch ld_pos)
+                                    const int32_t* __restrict__ pairs,
+                                    __nv_bfloat16* __restrict__ qkv,  // [3][B, 8, Q, 64]   head-major
+                                    __nv_bfloat16* __restrict__ cat,  // [3][B, 8, Q, 128]  head-major [left|right]
                                     int Q, int rows, int ld_pos) {
   const int row = blockIdx.x;
-  const int b = row / Q;
+  const int b = row / Q, i = row - b * Q;
   const int t = threadIdx.x;  // 0..63 -> channel t*8 of 512
   const int L = b * Q + pairs[2 * row], R = b * Q + pairs[2 * row + 1];
   auto qk_at = [&](int r, int which) {  // which: 0 q, 1 k
@@ -247,14 +249,15 @@ __global__ void dec_qkv_prep_kernel(const __nv_bfloat16* __restrict__ qkv_obj,  
     return *reinterpret_cast<const uint4*>(qkv_obj + static_cast<size_t>(r) * 1536 + 1024 + t * 8);
   };
   const int hh = t >> 3, within = (t & 7) * 8;  // head, channel within head
-  const size_t cat_stride = static_cast<size_t>(rows) * 1024;
+  const size_t hm_row = static_cast<size_t>(b * 8 + hh) * Q + i;
+  const size_t self_stride = static_cast<size_t>(rows) * 512, cat_stride = static_cast<size_t>(rows) * 1024;
 #pragma unroll
   for (int which = 0; which < 3; ++which) {
     const uint4 self = which < 2 ? qk_at(row, which) : v_at(row);
-    *reinterpret_cast<uint4*>(qkv + static_cast<size_t>(row) * 1536 + which * 512 + t * 8) = self;
+    *reinterpret_cast<uint4*>(qkv + which * self_stride + hm_row * 64 + within) = self;
     const uint4 left = which < 2 ? qk_at(L, which) : v_at(L);
     const uint4 right = which < 2 ? qk_at(R, which) : v_at(R);
-    __nv_bfloat16* dst = cat + which * cat_stride + static_cast<size_t>(row) * 1024 + hh * 128 + within;
+    __nv_bfloat16* dst = cat + which * cat_stride + hm_row * 128 + within;
     *reinterpret_cast<uint4*>(dst) = left;
     *reinterpret_cast<uint4*>(dst + 64) = right;
   }
@@ -285,9 +288,10 @@ extern "C" int destr_dec_self_pair_attn_fwd(const void* qkv, const void* cat, vo
   const __nv_bfloat16* c = static_cast<const __nv_bfloat16*>(cat);
   CUtensorMap t[6];
   int rc;
-  for (int w = 0; w < 3; ++w) {
-    if ((rc = make_tmap_bf16_2d(&t[w], x + w * 512, rows, 512, 1536, BT, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-    if ((rc = make_tmap_bf16_2d(&t[3 + w], c + w * rows * 1024, rows, 1024, 1024, BT, 64,
+  for (int w = 0; w < 3; ++w) {  // head-major operands: 2-D [B*8*Q, D]
+    if ((rc = make_tmap_bf16_2d(&t[w], x + w * rows * 512, rows * 8, 64, 64, BT, 64, CU_TENSOR_MAP_SWIZZLE_128B)))
+      return rc;
+    if ((rc = make_tmap_bf16_2d(&t[3 + w], c + w * rows * 1024, rows * 8, 128, 128, BT, 64,
                                 CU_TENSOR_MAP_SWIZZLE_128B)))
       return rc;
   }

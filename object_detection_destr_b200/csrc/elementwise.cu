@@ -149,8 +149,10 @@ __global__ void pos_mul_add_bwd_acc_kernel(const __nv_bfloat16* __restrict__ dy,
   }
 }
 
-// dpre = dy * (h > 0); dbias[c] += sum_rows dpre[:, c].  Block = 32 x 8 threads: 32 column groups of 8 channels
-// x 8 row lanes; grid.x tiles the columns (256 per block), grid.y strides the rows.
+// dpre = dy * (h > 0); dbias[c] += sum_rows dpre[:, c].  Block = 32 column groups (8 channels each) x 8 row
+// lanes; a block owns ROWS_PER_BLOCK rows of a 256-column stripe and every thread issues its 4 row loads up
+// front (latency-bound otherwise).  grid = (ceil(C/256), ceil(M/ROWS_PER_BLOCK)).
+constexpr int kRowsPerBlock = 32;
 __global__ void __launch_bounds__(256)
 relu_bwd_colsum_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ h,
                        __nv_bfloat16* __restrict__ dpre, float* __restrict__ dbias, int M, int C, int lddy, int ldh,
@@ -158,20 +160,32 @@ relu_bwd_colsum_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16
   __shared__ float red[8][256];
   const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + cg * 8;
+  const int row0 = blockIdx.y * kRowsPerBlock + rl;
   float acc[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
   if (col < C) {
-    for (int row = blockIdx.y * 8 + rl; row < M; row += gridDim.y * 8) {
-      F8 g = ld8(dy + (size_t)row * lddy + col);
-      if (h) {
-        const F8 a = ld8(h + (size_t)row * ldh + col);
+    F8 g[kRowsPerBlock / 8], a[kRowsPerBlock / 8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) g.v[k] = a.v[k] > 0.f ? g.v[k] : 0.f;
-        st8(dpre + (size_t)row * ldo + col, g);
+    for (int u = 0; u < kRowsPerBlock / 8; ++u) {
+      const int row = row0 + u * 8;
+      if (row < M) {
+        g[u] = ld8(dy + (size_t)row * lddy + col);
+        if (h) a[u] = ld8(h + (size_t)row * ldh + col);
       }
+    }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] += g.v[k];
+    for (int u = 0; u < kRowsPerBlock / 8; ++u) {
+      const int row = row0 + u * 8;
+      if (row < M) {
+        if (h) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) g[u].v[k] = a[u].v[k] > 0.f ? g[u].v[k] : 0.f;
+          st8(dpre + (size_t)row * ldo + col, g[u]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += g[u].v[k];
+      }
     }
   }
 #pragma unroll
@@ -265,10 +279,7 @@ extern "C" int destr_relu_bwd_colsum(const void* dy, int lddy, const void* h, in
                                      float* dbias, int M, int C, void* stream) {
   DESTR_CHECK_ARG(dy && dbias && M > 0 && C > 0 && C % 8 == 0 && lddy % 8 == 0, "shape");
   DESTR_CHECK_ARG((h == nullptr) == (dpre == nullptr), "h and dpre go together (both NULL = plain column sum)");
-  dim3 grid(ceil_div(C, 256), 1);
-  int rows_blocks = ceil_div(M, 8 * 16);
-  const int cap = (kSMs * 4) / (int)grid.x;
-  grid.y = rows_blocks > cap ? cap : (rows_blocks < 1 ? 1 : rows_blocks);
+  dim3 grid(ceil_div(C, 256), ceil_div(M, kRowsPerBlock));
   relu_bwd_colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)h,
                                                                  (__nv_bfloat16*)dpre, dbias, M, C, lddy, ldh, ldo);
   DESTR_LAUNCH_CHECK();

@@ -227,12 +227,12 @@ def box_refine(delta: Tensor, centers: Tensor) -> Tensor:
 
 
 def dec_qkv_prep(qkv_obj: Tensor, qk_pos: Tensor, pairs: Tensor, B: int, Q: int):
-    """-> (qkv bf16 [B*Q,1536], cat bf16 [3, B*Q, 1024])."""
+    """-> head-major (qkv bf16 [3, B, 8, Q, 64], cat bf16 [3, B, 8, Q, 128])."""
     qkv_obj = _chk(qkv_obj.contiguous(), BF16, "qkv_obj")
     qk_pos = _rows(qk_pos, BF16, "qk_pos", 512)
     pairs = _chk(pairs.contiguous(), torch.int32, "pairs")
-    qkv = torch.empty(B * Q, 1536, dtype=BF16, device=qkv_obj.device)
-    cat = torch.empty(3, B * Q, 1024, dtype=BF16, device=qkv_obj.device)
+    qkv = torch.empty(3, B, 8, Q, 64, dtype=BF16, device=qkv_obj.device)
+    cat = torch.empty(3, B, 8, Q, 128, dtype=BF16, device=qkv_obj.device)
     _lib.call("destr_dec_qkv_prep", qkv_obj.data_ptr(), qk_pos.data_ptr(), qk_pos.stride(0), pairs.data_ptr(), qkv.data_ptr(),
               cat.data_ptr(), B, Q, _stream())
     return qkv, cat

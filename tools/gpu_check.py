@@ -149,16 +149,17 @@ def check_decoder_kernels(B=2, Q=100, N=300):
     qf = qkv_obj[:, :512].float() + torch.cat([qk_pos[:, :256], qk_pos[:, :256]], -1).float()
     kf = qkv_obj[:, 512:1024].float() + torch.cat([qk_pos[:, 256:], qk_pos[:, 256:]], -1).float()
     vf = qkv_obj[:, 1024:].float()
-    ok &= report("dec_qkv_prep q", qkv[:, :512], qf, 0, 8e-3)
-    ok &= report("dec_qkv_prep k", qkv[:, 512:1024], kf, 0, 8e-3)
-    ok &= report("dec_qkv_prep v", qkv[:, 1024:], vf, 0, 0)
-    qb, kb, vb = (t.float().cpu() for t in (qkv[:, :512], qkv[:, 512:1024], qkv[:, 1024:]))  # bf16-rounded
+    tokm = lambda t: t.transpose(1, 2).reshape(M, -1)  # head-major [B,8,Q,d] -> token-major [B*Q, 8d]
+    ok &= report("dec_qkv_prep q", tokm(qkv[0]), qf, 0, 8e-3)
+    ok &= report("dec_qkv_prep k", tokm(qkv[1]), kf, 0, 8e-3)
+    ok &= report("dec_qkv_prep v", tokm(qkv[2]), vf, 0, 0)
+    qb, kb, vb = (tokm(qkv[w]).float().cpu() for w in range(3))  # bf16-rounded
     heads = lambda t: t.reshape(B, Q, 8, 64).transpose(1, 2)
     q4, k4, v4 = heads(qb), heads(kb), heads(vb)
     gidx = lambda col: (pairs[..., col] + torch.arange(B)[:, None] * Q).reshape(-1)
     for w, t in enumerate((qb, kb, vb)):
         ref_cat = torch.cat([t[gidx(0)].reshape(M, 8, 64), t[gidx(1)].reshape(M, 8, 64)], -1).reshape(M, 1024)
-        ok &= report(f"dec_qkv_prep cat[{w}]", cat[w], ref_cat, 0, 0)
+        ok &= report(f"dec_qkv_prep cat[{w}]", tokm(cat[w]), ref_cat, 0, 0)
     o1, o2, lse1, lse2 = ops.dec_self_pair_attn_fwd(qkv, cat, B, Q)
     torch.cuda.synchronize()
     ref1 = O.sdp_attention(q4, k4, v4).reshape(M, 512)
