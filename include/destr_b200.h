@@ -88,10 +88,14 @@ int destr_add_layernorm_bwd(const void* dy, int lddy, const void* a, int lda, co
 int destr_dual_ln_mix_fwd(const void* x, const void* o1, const void* o2, const int32_t* pairs, const float* g1,
                           const float* b1, const float* g2, const float* b2, float lam, void* out, float* stats,
                           int M, int Q, void* stream);
-/* backward: dx, do1 bf16 [M,512]; do2 bf16 [M,1024]; dg1,db1,dg2,db2 fp32 [512] ACCUMULATED into. */
+/* backward: dx bf16 [M,512]; do1 bf16 [M,512] and do2 bf16 [M,1024] token-major, or (head_major = 1)
+ * do1 [B,8,Q,64] and do2 [B,8,Q,128] as the attention backward wants them; dg1,db1,dg2,db2 fp32 [512] are
+ * ACCUMULATED into.  With head_major, delta1/delta2 (fp32 [B,8,Q], may be NULL) receive rowsum(dO o O) per
+ * head for the self / pair attention backward. */
 int destr_dual_ln_mix_bwd(const void* dout, const void* x, const void* o1, const void* o2, const int32_t* pairs,
                           const float* g1, const float* g2, const float* stats, float lam, void* dx, void* do1,
-                          void* do2, float* dg1, float* db1, float* dg2, float* db2, int M, int Q, void* stream);
+                          void* do2, float* dg1, float* db1, float* dg2, float* db2, int M, int Q, int head_major,
+                          float* delta1, float* delta2, void* stream);
 
 /* ---------------- encoder multi-head self-attention (tcgen05) ---------------- */
 
@@ -141,6 +145,19 @@ int destr_dec_qkv_prep(const void* qkv_obj, const void* qk_pos, int ld_pos, cons
  * (log2 domain, for the backward; may be NULL).  Q <= 384. */
 int destr_dec_self_pair_attn_fwd(const void* qkv, const void* cat, void* o1, void* o2, float* lse1, float* lse2,
                                  int B, int Q, void* stream);
+
+/* Backward of destr_dec_self_pair_attn_fwd, stage 1 (one launch, tcgen05): recomputes S and dP = dO.v^T and
+ * applies the softmax backward.  qkv / cat / do1 [B,8,Q,64] / do2 [B,8,Q,128] head-major; lse*, delta*
+ * fp32 [B,8,Q] (delta = rowsum(dO o O), from destr_dual_ln_mix_bwd).  Outputs bf16 [B,8,Q,Qp],
+ * Qp = ceil(Q/128)*128 (keys >= Q written as 0): P1,dS1 (self) and P2,dS2 (pair).  The caller finishes with
+ * batched GEMMs: dV = P^T dO, dQ = dS K, dK = dS^T Q (see ops.dec_self_pair_attn_bwd). */
+int destr_dec_self_pair_attn_bwd_ds(const void* qkv, const void* cat, const void* do1, const void* do2,
+                                    const float* lse1, const float* lse2, const float* delta1, const float* delta2,
+                                    void* P1, void* dS1, void* P2, void* dS2, int B, int Q, void* stream);
+/* Backward of destr_dec_qkv_prep (gather formulation of the scatter-add, deterministic): head-major
+ * d_qkv [3][B,8,Q,64], d_cat [3][B,8,Q,128] -> d_qkv_obj bf16 [B*Q,1536], d_qk_pos bf16 [B*Q,512] (pitch ld_pos). */
+int destr_dec_qkv_prep_bwd(const void* d_qkv, const void* d_cat, const int32_t* pairs, void* d_qkv_obj,
+                           void* d_qk_pos, int ld_pos, int B, int Q, void* stream);
 
 /* Split cross-attention of both ClsRegBranch'es (decoder_block.py:212-217, 246-251 ->
  * self_attention.py:26-45 with one head, d_qk = 512, d_v = 256, scale 1/sqrt(512)).

@@ -1,0 +1,305 @@
+// Decoder self-attention + pair self-attention backward, stage 1 (tcgen05 / TMEM / TMA), one launch:
+// recompute S = q.k^T and dP = dO.v^T on the tensor cores, apply the softmax backward and emit P and dS
+// (bf16, head-major [B,8,Q,Qp]).  The contractions dV = P^T dO, dQ = dS K, dK = dS^T Q are then plain
+// batched GEMMs over contiguous head-major operands; the scatter back through the pair gathers is
+// destr_dec_qkv_prep_bwd.  (Reference forward: self_attention.py:26-45, pair_self_attention.py:91-99.)
+//
+//   self (D = 64) :  P = 2^(c*S - lse),  c = log2e/8        dS = P (dP - delta) / 8
+//   pair (D = 128):  A = 2^(c*S - lse),  c = log2e,  P = A r,   dS = A (r dP - delta),  r = 1/sqrt(128)
+// with delta = rowsum(dO o O) (from destr_dual_ln_mix_bwd).  grid = (ceil(Q/128), 16, B) as in the forward.
+// Per CTA: S for all key tiles in TMEM [0,384); dP_j in one 128-column buffer [384,512) that the math warps
+// hand back to the MMA warp per key tile; dO reuses Q's smem slot, V_j reuses K_j's.
+#include "../../include/destr_b200.h"
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace destr {
+namespace {
+
+constexpr int BT = 128;
+constexpr int MAX_TILES = 3;
+constexpr int NTHREADS = 192;
+constexpr uint32_t CHUNK_BYTES = BT * 128;
+
+struct __align__(1024) Smem {
+  uint8_t q[2][CHUNK_BYTES];              // Q tile, then dO tile
+  uint8_t kv[MAX_TILES][2][CHUNK_BYTES];  // K_j, then V_j
+  uint64_t q_full, s_full, do_full;
+  uint64_t k_full[MAX_TILES], k_free[MAX_TILES], v_full[MAX_TILES], dp_full[MAX_TILES], dp_free[MAX_TILES];
+  uint32_t tmem_base;
+};
+
+struct Params {
+  const float* lse1; const float* lse2; const float* delta1; const float* delta2;
+  __nv_bfloat16* P1; __nv_bfloat16* dS1; __nv_bfloat16* P2; __nv_bfloat16* dS2;
+  int Q, Qp;
+};
+
+template <int D>
+__device__ __forceinline__ void body(Smem& sm, const CUtensorMap* tm_q, const CUtensorMap* tm_k,
+                                     const CUtensorMap* tm_v, const CUtensorMap* tm_do, const float* __restrict__ lse,
+                                     const float* __restrict__ delta, __nv_bfloat16* __restrict__ P_out,
+                                     __nv_bfloat16* __restrict__ dS_out, int Q, int Qp, int h, int b, int mt,
+                                     float scale_log2, float p_scale, float dp_scale, float ds_scale, uint32_t tmem) {
+  constexpr int NCH = D / 64;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkv = (Q + BT - 1) / BT;
+  const int hrow = (b * 8 + h) * Q;
+  constexpr uint32_t C_DP = 384;
+
+  if (warp == 4) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&sm.q_full, NCH * CHUNK_BYTES);
+      for (int c = 0; c < NCH; ++c) tma_load_2d(sm.q[c], tm_q, &sm.q_full, c * 64, hrow + mt * BT);
+      for (int j = 0; j < nkv; ++j) {
+        mbar_arrive_expect_tx(&sm.k_full[j], NCH * CHUNK_BYTES);
+        for (int c = 0; c < NCH; ++c) tma_load_2d(sm.kv[j][c], tm_k, &sm.k_full[j], c * 64, hrow + j * BT);
+      }
+      mbar_wait(&sm.s_full, 0, 51);  // every Q.K^T has retired: Q's slot is free for dO
+      mbar_arrive_expect_tx(&sm.do_full, NCH * CHUNK_BYTES);
+      for (int c = 0; c < NCH; ++c) tma_load_2d(sm.q[c], tm_do, &sm.do_full, c * 64, hrow + mt * BT);
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(&sm.k_free[j], 0, 52);
+        mbar_arrive_expect_tx(&sm.v_full[j], NCH * CHUNK_BYTES);
+        for (int c = 0; c < NCH; ++c) tma_load_2d(sm.kv[j][c], tm_v, &sm.v_full[j], c * 64, hrow + j * BT);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BT, BT, false, false);
+      mbar_wait(&sm.q_full, 0, 53);
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(&sm.k_full[j], 0, 54);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < D / 16; ++ks) {
+          umma_ss(tmem + j * BT, umma_smem_desc(smem_u32(sm.q[ks >> 2]) + (ks & 3) * 32, 16, 1024, SWZ_128B),
+                  umma_smem_desc(smem_u32(sm.kv[j][ks >> 2]) + (ks & 3) * 32, 16, 1024, SWZ_128B), idesc, ks > 0);
+        }
+        tc_commit(&sm.k_free[j]);
+      }
+      tc_commit(&sm.s_full);
+      mbar_wait(&sm.do_full, 0, 55);
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(&sm.v_full[j], 0, 56);
+        if (j > 0) mbar_wait(&sm.dp_free[j - 1], 0, 57);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < D / 16; ++ks) {  // dP_j = dO . V_j^T  (both K-major, contraction over D)
+          umma_ss(tmem + C_DP, umma_smem_desc(smem_u32(sm.q[ks >> 2]) + (ks & 3) * 32, 16, 1024, SWZ_128B),
+                  umma_smem_desc(smem_u32(sm.kv[j][ks >> 2]) + (ks & 3) * 32, 16, 1024, SWZ_128B), idesc, ks > 0);
+        }
+        tc_commit(&sm.dp_full[j]);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int wq = warp;
+    const uint32_t lane_addr = static_cast<uint32_t>(wq * 32) << 16;
+    const int qrow = mt * BT + wq * 32 + lane;
+    const bool valid = qrow < Q;
+    const float l2 = valid ? lse[static_cast<size_t>(hrow) + qrow] : INFINITY;
+    const float dl = valid ? delta[static_cast<size_t>(hrow) + qrow] : 0.f;
+    __nv_bfloat16* prow = P_out + (static_cast<size_t>(hrow) + (valid ? qrow : 0)) * Qp;
+    __nv_bfloat16* drow = dS_out + (static_cast<size_t>(hrow) + (valid ? qrow : 0)) * Qp;
+    mbar_wait(&sm.s_full, 0, 58);
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(&sm.dp_full[j], 0, 59);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t s[32], d[32];
+        tmem_ld_x32(tmem + lane_addr + j * BT + c * 32, s);
+        tmem_ld_x32(tmem + lane_addr + C_DP + c * 32, d);
+        tc_wait_ld();
+        const int key0 = j * BT + c * 32;
+        uint32_t pp[16], dd[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float pv[2], dv[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int k = 2 * i + e;
+            float p = ex2_approx(fmaf(__uint_as_float(s[k]), scale_log2, -l2));
+            p = (key0 + k < Q) ? p : 0.f;
+            pv[e] = p * p_scale;
+            dv[e] = p * (__uint_as_float(d[k]) * dp_scale - dl) * ds_scale;
+          }
+          pp[i] = pack_bf16x2(pv[0], pv[1]);
+          dd[i] = pack_bf16x2(dv[0], dv[1]);
+        }
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            reinterpret_cast<uint4*>(prow + key0)[i] = make_uint4(pp[4 * i], pp[4 * i + 1], pp[4 * i + 2], pp[4 * i + 3]);
+            reinterpret_cast<uint4*>(drow + key0)[i] = make_uint4(dd[4 * i], dd[4 * i + 1], dd[4 * i + 2], dd[4 * i + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&sm.dp_free[j]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+dec_attn_bwd_ds_kernel(const __grid_constant__ CUtensorMap tq1, const __grid_constant__ CUtensorMap tk1,
+                       const __grid_constant__ CUtensorMap tv1, const __grid_constant__ CUtensorMap td1,
+                       const __grid_constant__ CUtensorMap tq2, const __grid_constant__ CUtensorMap tk2,
+                       const __grid_constant__ CUtensorMap tv2, const __grid_constant__ CUtensorMap td2, Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 4 && lane == 0) {
+    mbar_init(&sm.q_full, 1);
+    mbar_init(&sm.s_full, 1);
+    mbar_init(&sm.do_full, 1);
+    for (int j = 0; j < MAX_TILES; ++j) {
+      mbar_init(&sm.k_full[j], 1);
+      mbar_init(&sm.k_free[j], 1);
+      mbar_init(&sm.v_full[j], 1);
+      mbar_init(&sm.dp_full[j], 1);
+      mbar_init(&sm.dp_free[j], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 5) tmem_alloc<512>(&sm.tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+  const int mt = blockIdx.x, hy = blockIdx.y, b = blockIdx.z;
+  const float log2e = 1.4426950408889634f, r = 0.08838834764831845f;
+  if (hy < 8)
+    body<64>(sm, &tq1, &tk1, &tv1, &td1, p.lse1, p.delta1, p.P1, p.dS1, p.Q, p.Qp, hy, b, mt, log2e * 0.125f, 1.f, 1.f,
+             0.125f, tmem);
+  else
+    body<128>(sm, &tq2, &tk2, &tv2, &td2, p.lse2, p.delta2, p.P2, p.dS2, p.Q, p.Qp, hy - 8, b, mt, log2e, r, r, 1.f,
+              tmem);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<512>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward of dec_qkv_prep: gather formulation of the scatter-add (no atomics, deterministic).
+//   d_x_w[b,i] = d_self_w[b,i] + sum_{i': L_i' = i} d_cat_w[b,i'][left] + sum_{i': R_i' = i} d_cat_w[b,i'][right]
+//   d_qkv_obj = [d_q | d_k | d_v] token-major;  d_qk_pos = [d_q lo+hi halves | d_k lo+hi halves]
+// One block per (b, i), 64 threads x 8 channels; the image's pairs sit in shared memory.
+// ------------------------------------------------------------------------------------------------
+__global__ void dec_qkv_prep_bwd_kernel(const __nv_bfloat16* __restrict__ d_qkv,  // [3][B,8,Q,64]
+                                        const __nv_bfloat16* __restrict__ d_cat,  // [3][B,8,Q,128]
+                                        const int32_t* __restrict__ pairs, __nv_bfloat16* __restrict__ d_obj,
+                                        __nv_bfloat16* __restrict__ d_pos, int ld_pos, int Q, int rows) {
+  extern __shared__ int32_t sp[];  // [Q][2]
+  __shared__ float fold[2][512];
+  const int row = blockIdx.x;
+  const int b = row / Q, i = row - b * Q;
+  const int t = threadIdx.x;
+  for (int k = t; k < 2 * Q; k += blockDim.x) sp[k] = pairs[static_cast<size_t>(b) * Q * 2 + k];
+  __syncthreads();
+  const int hh = t >> 3, within = (t & 7) * 8;
+  const size_t hm_base = static_cast<size_t>(b * 8 + hh) * Q;
+  const size_t self_stride = static_cast<size_t>(rows) * 512, cat_stride = static_cast<size_t>(rows) * 1024;
+  float acc[3][8];
+#pragma unroll
+  for (int w = 0; w < 3; ++w) {
+    const uint4 u = *reinterpret_cast<const uint4*>(d_qkv + w * self_stride + (hm_base + i) * 64 + within);
+    const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      acc[w][2 * e] = __uint_as_float(uw[e] << 16);
+      acc[w][2 * e + 1] = __uint_as_float(uw[e] & 0xffff0000u);
+    }
+  }
+  for (int ip = 0; ip < Q; ++ip) {
+    const int L = sp[2 * ip], R = sp[2 * ip + 1];
+    if (L != i && R != i) continue;
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      if ((side == 0 ? L : R) != i) continue;
+#pragma unroll
+      for (int w = 0; w < 3; ++w) {
+        const uint4 u =
+            *reinterpret_cast<const uint4*>(d_cat + w * cat_stride + (hm_base + ip) * 128 + side * 64 + within);
+        const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc[w][2 * e] += __uint_as_float(uw[e] << 16);
+          acc[w][2 * e + 1] += __uint_as_float(uw[e] & 0xffff0000u);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int w = 0; w < 3; ++w) {
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[e] = pack_bf16x2(acc[w][2 * e], acc[w][2 * e + 1]);
+    *reinterpret_cast<uint4*>(d_obj + static_cast<size_t>(row) * 1536 + w * 512 + t * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    if (w < 2) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) fold[w][t * 8 + e] = acc[w][e];
+    }
+  }
+  __syncthreads();
+  // q_pos / k_pos were added to BOTH 256-wide halves (decoder_block.py:169,173): fold the halves
+  for (int k = t; k < 512; k += blockDim.x) {
+    const int w = k >> 8, c = k & 255;
+    d_pos[static_cast<size_t>(row) * ld_pos + w * 256 + c] = __float2bfloat16(fold[w][c] + fold[w][256 + c]);
+  }
+}
+
+}  // namespace
+}  // namespace destr
+
+extern "C" int destr_dec_qkv_prep_bwd(const void* d_qkv, const void* d_cat, const int32_t* pairs, void* d_qkv_obj,
+                                      void* d_qk_pos, int ld_pos, int B, int Q, void* stream) {
+  using namespace destr;
+  DESTR_CHECK_ARG(d_qkv && d_cat && pairs && d_qkv_obj && d_qk_pos && B > 0 && Q > 0, "null pointer / shape");
+  DESTR_CHECK_ARG(ld_pos >= 512, "ld_pos");
+  dec_qkv_prep_bwd_kernel<<<B * Q, 64, 2 * Q * sizeof(int32_t), static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(d_qkv), static_cast<const __nv_bfloat16*>(d_cat), pairs,
+      static_cast<__nv_bfloat16*>(d_qkv_obj), static_cast<__nv_bfloat16*>(d_qk_pos), ld_pos, Q, B * Q);
+  DESTR_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int destr_dec_self_pair_attn_bwd_ds(const void* qkv, const void* cat, const void* do1, const void* do2,
+                                               const float* lse1, const float* lse2, const float* delta1,
+                                               const float* delta2, void* P1, void* dS1, void* P2, void* dS2, int B,
+                                               int Q, void* stream) {
+  using namespace destr;
+  DESTR_CHECK_ARG(qkv && cat && do1 && do2 && lse1 && lse2 && delta1 && delta2 && P1 && dS1 && P2 && dS2,
+                  "null pointer");
+  DESTR_CHECK_ARG(B > 0 && Q > 0 && Q <= BT * MAX_TILES, "Q must be <= 384");
+  const uint64_t rows = static_cast<uint64_t>(B) * Q;
+  const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(qkv);
+  const __nv_bfloat16* c = static_cast<const __nv_bfloat16*>(cat);
+  CUtensorMap t[8];
+  int rc;
+  for (int w = 0; w < 3; ++w) {
+    if ((rc = make_tmap_bf16_2d(&t[w], x + w * rows * 512, rows * 8, 64, 64, BT, 64, CU_TENSOR_MAP_SWIZZLE_128B)))
+      return rc;
+    if ((rc = make_tmap_bf16_2d(&t[4 + w], c + w * rows * 1024, rows * 8, 128, 128, BT, 64,
+                                CU_TENSOR_MAP_SWIZZLE_128B)))
+      return rc;
+  }
+  if ((rc = make_tmap_bf16_2d(&t[3], do1, rows * 8, 64, 64, BT, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_tmap_bf16_2d(&t[7], do2, rows * 8, 128, 128, BT, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  const size_t smem = sizeof(Smem) + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DESTR_CUDA(cudaFuncSetAttribute(dec_attn_bwd_ds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  const int Qp = ceil_div(Q, BT) * BT;
+  Params p{lse1, lse2, delta1, delta2, static_cast<__nv_bfloat16*>(P1), static_cast<__nv_bfloat16*>(dS1),
+           static_cast<__nv_bfloat16*>(P2), static_cast<__nv_bfloat16*>(dS2), Q, Qp};
+  dim3 grid(ceil_div(Q, BT), 16, B);
+  dec_attn_bwd_ds_kernel<<<grid, NTHREADS, smem, static_cast<cudaStream_t>(stream)>>>(t[0], t[1], t[2], t[3], t[4],
+                                                                                      t[5], t[6], t[7], p);
+  DESTR_LAUNCH_CHECK();
+  return 0;
+}

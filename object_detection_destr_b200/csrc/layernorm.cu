@@ -238,7 +238,8 @@ dual_ln_mix_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat
                        const float* __restrict__ g2, const float* __restrict__ stats, float lam,
                        __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ do1,
                        __nv_bfloat16* __restrict__ do2, float* __restrict__ dg1, float* __restrict__ db1,
-                       float* __restrict__ dg2, float* __restrict__ db2, int M, int Q) {
+                       float* __restrict__ dg2, float* __restrict__ db2, int M, int Q, int head_major,
+                       float* __restrict__ delta1, float* __restrict__ delta2) {
   constexpr int VPL = 16, D = 512;
   constexpr float invD = 1.0f / D;
   extern __shared__ float red[];  // [4][warps][D]
@@ -253,6 +254,7 @@ dual_ln_mix_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat
     const float k0 = pairs[2 * row] == i ? 1.f : 0.f, k1 = pairs[2 * row + 1] == i ? 1.f : 0.f;
     const Row<VPL> xr = ld_row<VPL>(x + (size_t)row * D, lane);
     Row<VPL> u = ld_row<VPL>(o1 + (size_t)row * D, lane);
+    const Row<VPL> o1v = u;
     const Row<VPL> a = ld_row<VPL>(o2 + (size_t)row * 2 * D, lane);
     const Row<VPL> c = ld_row<VPL>(o2 + (size_t)row * 2 * D + D, lane);
     const Row<VPL> d = ld_row<VPL>(dout + (size_t)row * D, lane);
@@ -282,9 +284,52 @@ dual_ln_mix_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat
       rc.v[e] = k1 * r2.v[e];
     }
     st_row<VPL>(dx + (size_t)row * D, lane, rx);
-    st_row<VPL>(do1 + (size_t)row * D, lane, r1);
-    st_row<VPL>(do2 + (size_t)row * 2 * D, lane, ra);
-    st_row<VPL>(do2 + (size_t)row * 2 * D + D, lane, rc);
+    if (!head_major) {
+      st_row<VPL>(do1 + (size_t)row * D, lane, r1);
+      st_row<VPL>(do2 + (size_t)row * 2 * D, lane, ra);
+      st_row<VPL>(do2 + (size_t)row * 2 * D + D, lane, rc);
+    } else {
+      // head-major gradients for the attention backward: do1 [B,8,Q,64], do2 [B,8,Q,128]
+      const int b = row / Q;
+      auto st8v = [](__nv_bfloat16* p, const float* v) {
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+          w[e] = *reinterpret_cast<uint32_t*>(&hh);
+        }
+        *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+      };
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {  // lane owns channels (g*32 + lane)*8 .. +8
+        const int h1 = g * 4 + (lane >> 3), h2 = g * 2 + (lane >> 4);
+        st8v(do1 + ((size_t)(b * 8 + h1) * Q + i) * 64 + (lane & 7) * 8, &r1.v[g * 8]);
+        st8v(do2 + ((size_t)(b * 8 + h2) * Q + i) * 128 + (lane & 15) * 8, &ra.v[g * 8]);
+        st8v(do2 + ((size_t)(b * 8 + 4 + h2) * Q + i) * 128 + (lane & 15) * 8, &rc.v[g * 8]);
+        if (delta1) {  // delta = rowsum(dO o O) per head, for the attention backward
+          float p1 = 0.f, pa = 0.f, pc = 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            p1 = fmaf(r1.v[g * 8 + e], o1v.v[g * 8 + e], p1);
+            pa = fmaf(ra.v[g * 8 + e], a.v[g * 8 + e], pa);
+            pc = fmaf(rc.v[g * 8 + e], c.v[g * 8 + e], pc);
+          }
+#pragma unroll
+          for (int off = 1; off < 8; off <<= 1) {
+            p1 += __shfl_xor_sync(0xffffffffu, p1, off);
+            pa += __shfl_xor_sync(0xffffffffu, pa, off);
+            pc += __shfl_xor_sync(0xffffffffu, pc, off);
+          }
+          pa += __shfl_xor_sync(0xffffffffu, pa, 8);
+          pc += __shfl_xor_sync(0xffffffffu, pc, 8);
+          if ((lane & 7) == 0) delta1[(size_t)(b * 8 + h1) * Q + i] = p1;
+          if ((lane & 15) == 0) {
+            delta2[(size_t)(b * 8 + h2) * Q + i] = pa;
+            delta2[(size_t)(b * 8 + 4 + h2) * Q + i] = pc;
+          }
+        }
+      }
+    }
   }
   float* R[4] = {red, red + wpb * D, red + 2 * wpb * D, red + 3 * wpb * D};
 #pragma unroll
@@ -375,15 +420,18 @@ extern "C" int destr_dual_ln_mix_fwd(const void* x, const void* o1, const void* 
 extern "C" int destr_dual_ln_mix_bwd(const void* dout, const void* x, const void* o1, const void* o2,
                                      const int32_t* pairs, const float* g1, const float* g2, const float* stats,
                                      float lam, void* dx, void* do1, void* do2, float* dg1, float* db1, float* dg2,
-                                     float* db2, int M, int Q, void* stream) {
+                                     float* db2, int M, int Q, int head_major, float* delta1, float* delta2,
+                                     void* stream) {
   DESTR_CHECK_ARG(dout && x && o1 && o2 && pairs && g1 && g2 && stats && dx && do1 && do2 && dg1 && db1 && dg2 && db2,
                   "null pointer");
+  DESTR_CHECK_ARG((delta1 == nullptr) == (delta2 == nullptr) && (!delta1 || head_major), "delta needs head_major");
   const int threads = 128;  // 4 warps -> 4*4*512*4 B = 32 KB of reduction scratch
   int grid = ceil_div(M, 4);
   if (grid > kSMs * 2) grid = kSMs * 2;
   dual_ln_mix_bwd_kernel<<<grid, threads, 4 * 4 * 512 * sizeof(float), (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)dout, (const __nv_bfloat16*)x, (const __nv_bfloat16*)o1, (const __nv_bfloat16*)o2, pairs,
-      g1, g2, stats, lam, (__nv_bfloat16*)dx, (__nv_bfloat16*)do1, (__nv_bfloat16*)do2, dg1, db1, dg2, db2, M, Q);
+      g1, g2, stats, lam, (__nv_bfloat16*)dx, (__nv_bfloat16*)do1, (__nv_bfloat16*)do2, dg1, db1, dg2, db2, M, Q,
+      head_major, delta1, delta2);
   DESTR_LAUNCH_CHECK();
   return 0;
 }

@@ -183,8 +183,11 @@ class _DecSelfPairAttn(torch.autograd.Function):
     def backward(ctx, do1, do2):
         qkv, cat, o1, o2, lse1, lse2 = ctx.saved_tensors
         B, Q = ctx.dims
-        d_qkv, d_cat = ops.dec_self_pair_attn_bwd(qkv, cat, o1, o2, do1.contiguous(), do2.contiguous(), lse1, lse2,
-                                                  B, Q)
+        hm = lambda t, d: t.reshape(B, Q, 8, d).transpose(1, 2).contiguous()  # token-major -> head-major
+        d1, d2 = hm(do1, 64), hm(do2, 128)
+        delta1 = (d1.float() * hm(o1, 64).float()).sum(-1)
+        delta2 = (d2.float() * hm(o2, 128).float()).sum(-1)
+        d_qkv, d_cat = ops.dec_self_pair_attn_bwd(qkv, cat, d1, d2, lse1, lse2, delta1, delta2, B, Q)
         return d_qkv, d_cat, None, None
 
 

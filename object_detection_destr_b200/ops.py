@@ -261,16 +261,28 @@ def dual_ln_mix(x: Tensor, o1: Tensor, o2: Tensor, pairs: Tensor, g1, b1, g2, b2
 
 
 def dual_ln_mix_bwd(dout: Tensor, x: Tensor, o1: Tensor, o2: Tensor, pairs: Tensor, g1, g2, stats, lam: float, Q: int,
-                    pg: Optional[Sequence[Tensor]] = None):
-    """pg: optional (dg1, db1, dg2, db2) fp32 [512] buffers to ACCUMULATE the parameter gradients into."""
+                    pg: Optional[Sequence[Tensor]] = None, head_major: bool = False):
+    """pg: optional (dg1, db1, dg2, db2) fp32 [512] buffers to ACCUMULATE the parameter gradients into.
+    head_major: do1 -> [B,8,Q,64], do2 -> [B,8,Q,128] and additionally returns (delta1, delta2) fp32 [B,8,Q]."""
     dout = _chk(dout.contiguous(), BF16, "dout")
     M = x.shape[0]
-    dx, do1, do2 = torch.empty_like(x), torch.empty_like(o1), torch.empty_like(o2)
+    B = M // Q
+    dx = torch.empty_like(x)
+    if head_major:
+        do1 = torch.empty(B, 8, Q, 64, dtype=BF16, device=x.device)
+        do2 = torch.empty(B, 8, Q, 128, dtype=BF16, device=x.device)
+        delta = torch.empty(2, B, 8, Q, dtype=torch.float32, device=x.device)
+    else:
+        do1, do2, delta = torch.empty_like(o1), torch.empty_like(o2), None
     if pg is None:
         pg = torch.zeros(4, 512, dtype=torch.float32, device=x.device)
     _lib.call("destr_dual_ln_mix_bwd", dout.data_ptr(), x.data_ptr(), o1.data_ptr(), o2.data_ptr(), pairs.data_ptr(),
               g1.data_ptr(), g2.data_ptr(), stats.data_ptr(), float(lam), dx.data_ptr(), do1.data_ptr(),
-              do2.data_ptr(), pg[0].data_ptr(), pg[1].data_ptr(), pg[2].data_ptr(), pg[3].data_ptr(), M, Q, _stream())
+              do2.data_ptr(), pg[0].data_ptr(), pg[1].data_ptr(), pg[2].data_ptr(), pg[3].data_ptr(), M, Q,
+              int(head_major), None if delta is None else delta[0].data_ptr(),
+              None if delta is None else delta[1].data_ptr(), _stream())
+    if head_major:
+        return dx, do1, do2, delta[0], delta[1]
     return dx, do1, do2, pg[0], pg[1], pg[2], pg[3]
 
 
@@ -294,8 +306,35 @@ def split_cross_attn_fwd(q_obj: Tensor, q_pos: Tensor, k_enc: Tensor, k_pos: Ten
 
 # Backward of the decoder attention ops: cuBLAS batched GEMMs + elementwise torch on the GPU
 # (see _composed_bwd.py for status; the fused tcgen05 backward exists for the encoder only so far).
-from ._composed_bwd import dec_qkv_prep_bwd, dec_self_pair_attn_bwd  # noqa: E402,F401
-from ._composed_bwd import _bmm_f32  # noqa: E402
+def dec_self_pair_attn_bwd(qkv: Tensor, cat: Tensor, do1: Tensor, do2: Tensor, lse1: Tensor, lse2: Tensor,
+                           delta1: Tensor, delta2: Tensor, B: int, Q: int):
+    """Backward of dec_self_pair_attn_fwd.  All operands head-major: qkv [3,B,8,Q,64], cat [3,B,8,Q,128],
+    do1 [B,8,Q,64], do2 [B,8,Q,128]; lse/delta fp32 [B,8,Q].  The tcgen05 kernel recomputes S, dP and does the
+    softmax backward; six cuBLAS batched GEMMs finish.  -> head-major (d_qkv [3,B,8,Q,64], d_cat [3,B,8,Q,128])."""
+    dev = qkv.device
+    Qp = ((Q + 127) // 128) * 128
+    BH = B * 8
+    PD = torch.empty(4, BH, Q, Qp, dtype=BF16, device=dev)  # P1, dS1, P2, dS2
+    _lib.call("destr_dec_self_pair_attn_bwd_ds", qkv.data_ptr(), cat.data_ptr(), do1.data_ptr(), do2.data_ptr(),
+              lse1.data_ptr(), lse2.data_ptr(), delta1.data_ptr(), delta2.data_ptr(), PD[0].data_ptr(),
+              PD[1].data_ptr(), PD[2].data_ptr(), PD[3].data_ptr(), B, Q, _stream())
+    d_qkv = torch.empty(3, BH, Q, 64, dtype=BF16, device=dev)
+    d_cat = torch.empty(3, BH, Q, 128, dtype=BF16, device=dev)
+    for x, dx, P, dS, dO in ((qkv.view(3, BH, Q, 64), d_qkv, PD[0][:, :, :Q], PD[1][:, :, :Q], do1.view(BH, Q, 64)),
+                             (cat.view(3, BH, Q, 128), d_cat, PD[2][:, :, :Q], PD[3][:, :, :Q], do2.view(BH, Q, 128))):
+        torch.bmm(dS, x[1], out=dx[0])                   # dQ = dS K
+        torch.bmm(dS.transpose(1, 2), x[0], out=dx[1])   # dK = dS^T Q
+        torch.bmm(P.transpose(1, 2), dO, out=dx[2])      # dV = P^T dO
+    return d_qkv.view(3, B, 8, Q, 64), d_cat.view(3, B, 8, Q, 128)
+
+
+def dec_qkv_prep_bwd(d_qkv: Tensor, d_cat: Tensor, pairs: Tensor, B: int, Q: int, d_pos_out: Optional[Tensor] = None):
+    """-> (d_qkv_obj bf16 [B*Q,1536], d_qk_pos bf16 [B*Q,512] (written into `d_pos_out` if given, any row pitch))."""
+    d_obj = torch.empty(B * Q, 1536, dtype=BF16, device=d_qkv.device)
+    d_pos = torch.empty(B * Q, 512, dtype=BF16, device=d_qkv.device) if d_pos_out is None else d_pos_out
+    _lib.call("destr_dec_qkv_prep_bwd", d_qkv.data_ptr(), d_cat.data_ptr(), pairs.data_ptr(), d_obj.data_ptr(),
+              d_pos.data_ptr(), d_pos.stride(0), B, Q, _stream())
+    return d_obj, d_pos
 
 
 def split_cross_attn_bwd(q_obj: Tensor, q_pos: Tensor, k_enc: Tensor, k_pos: Tensor, v: Tensor, mask_bits: Tensor,

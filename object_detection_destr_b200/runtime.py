@@ -301,13 +301,13 @@ class HotPathRuntime:
         do = torch.addmm(dca, dqo, P.w(f"d{l}.cq_w"))   # d(o) = d(o_cls|o_reg residual) + dq_obj W
         P.acc_gw(f"d{l}.cqp_w", dqp, sin)
         dsin = torch.mm(dqp, P.w(f"d{l}.cqp_w"))
-        dx2, do1, do2, *_ = ops.dual_ln_mix_bwd(do, x, o1, o2, pairs, P.f(f"d{l}.n1_w"), P.f(f"d{l}.n2_w"), st, lam, Q,
-                                                pg=(P.g(f"d{l}.n1_w"), P.g(f"d{l}.n1_b"), P.g(f"d{l}.n2_w"),
-                                                    P.g(f"d{l}.n2_b")))
+        dx2, do1, do2, delta1, delta2 = ops.dual_ln_mix_bwd(
+            do, x, o1, o2, pairs, P.f(f"d{l}.n1_w"), P.f(f"d{l}.n2_w"), st, lam, Q,
+            pg=(P.g(f"d{l}.n1_w"), P.g(f"d{l}.n1_b"), P.g(f"d{l}.n2_w"), P.g(f"d{l}.n2_b")), head_major=True)
         dx = d + dx2
-        d_qkv, d_cat = ops.dec_self_pair_attn_bwd(qkv, cat, o1, o2, do1, do2, lse1, lse2, B, Q)
-        d_qkv_obj, d_qkpos = ops.dec_qkv_prep_bwd(d_qkv, d_cat, pairs, B, Q)
-        d_qkpos_all[:, l * 512:(l + 1) * 512].copy_(d_qkpos)
+        d_qkv, d_cat = ops.dec_self_pair_attn_bwd(qkv, cat, do1, do2, lse1, lse2, delta1, delta2, B, Q)
+        d_qkv_obj, _ = ops.dec_qkv_prep_bwd(d_qkv, d_cat, pairs, B, Q,
+                                            d_pos_out=d_qkpos_all[:, l * 512:(l + 1) * 512])
         P.acc_gw(f"d{l}.q_w", d_qkv_obj, x, rows=1536)
         dx.addmm_(d_qkv_obj, P.w(f"d{l}.q_w", rows=1536))
         # sin = sine * pos_scale(x_reg)

@@ -173,6 +173,27 @@ def check_decoder_kernels(B=2, Q=100, N=300):
     ok &= report("dec lse1", lse1, torch.logsumexp(torch.einsum("bhqd,bhkd->bhqk", q4, k4) / 8, -1) * 1.4426950408889634, 2e-2, 1e-3)
     ok &= report("dec lse2", lse2, torch.logsumexp(a2, -1) * 1.4426950408889634, 2e-2, 1e-3)
 
+    # decoder attention backward (tcgen05 ds kernel + bmm) and prep backward (gather kernel) vs oracle autograd
+    do1 = (torch.randn(M, 512, generator=g) * 0.5).bfloat16()
+    do2 = (torch.randn(M, 1024, generator=g) * 0.5).bfloat16()
+    qo_l = qkv_obj.float().requires_grad_()
+    qp_l = qk_pos.float().requires_grad_()
+    q_r = qo_l[:, :512] + torch.cat([qp_l[:, :256], qp_l[:, :256]], -1)
+    k_r = qo_l[:, 512:1024] + torch.cat([qp_l[:, 256:], qp_l[:, 256:]], -1)
+    q4r, k4r, v4r = heads(q_r), heads(k_r), heads(qo_l[:, 1024:])
+    r1 = O.sdp_attention(q4r, k4r, v4r).reshape(M, 512)
+    a2r = torch.einsum("bhqd,bhkd->bhqk", take(q4r, 0), take(k4r, 0)) + torch.einsum("bhqd,bhkd->bhqk", take(q4r, 1), take(k4r, 1))
+    r2 = torch.einsum("bhqk,bhkd->bqhd", a2r.softmax(-1) / math.sqrt(128), torch.cat([take(v4r, 0), take(v4r, 1)], -1)).reshape(M, 1024)
+    ((r1 * do1.float()).sum() + (r2 * do2.float()).sum()).backward()
+    hm = lambda t, d: t.to(dev).reshape(B, Q, 8, d).transpose(1, 2).contiguous()
+    d1h, d2h = hm(do1, 64), hm(do2, 128)
+    dl1 = (d1h.float() * hm(o1, 64).float()).sum(-1)
+    dl2 = (d2h.float() * hm(o2, 128).float()).sum(-1)
+    d_qkv, d_cat = ops.dec_self_pair_attn_bwd(qkv, cat, d1h, d2h, lse1, lse2, dl1, dl2, B, Q)
+    d_obj, d_pos = ops.dec_qkv_prep_bwd(d_qkv, d_cat, pairs_d, B, Q)
+    ok &= report(f"dec attn bwd -> d_qkv_obj Q={Q}", d_obj, qo_l.grad, 3e-2 * float(qo_l.grad.abs().max()), 3e-2)
+    ok &= report(f"dec attn bwd -> d_qk_pos Q={Q}", d_pos, qp_l.grad, 3e-2 * float(qp_l.grad.abs().max()), 3e-2)
+
     # dual_ln_mix fwd/bwd (with slot masking) vs autograd
     x = torch.randn(M, 512, generator=g).bfloat16()
     g1, b1, g2, b2 = (1 + 0.1 * torch.randn(512, generator=g), 0.1 * torch.randn(512, generator=g),
@@ -198,6 +219,14 @@ def check_decoder_kernels(B=2, Q=100, N=300):
     ok &= report("dual_ln_mix bwd do2", do2, o2r.grad, 2e-2, 1e-2)
     for nm, got, rf in (("dg1", dg1, pr[0].grad), ("db1", db1, pr[1].grad), ("dg2", dg2, pr[2].grad), ("db2", db2, pr[3].grad)):
         ok &= report("dual_ln_mix bwd " + nm, got, rf, 1e-2, 3e-3)
+    # head-major variant with fused delta
+    dxh, do1h, do2h, dlt1, dlt2 = ops.dual_ln_mix_bwd(dout.to(dev), x.to(dev), o1, o2s.to(dev), pairs_d, dev_p[0],
+                                                      dev_p[2], stats, 0.5, Q, head_major=True)
+    tokm2 = lambda t: t.transpose(1, 2).reshape(M, -1)
+    ok &= report("dual_ln_mix bwd head-major do1", tokm2(do1h), do1, 0, 0)
+    ok &= report("dual_ln_mix bwd head-major do2", tokm2(do2h), do2, 0, 0)
+    ok &= report("dual_ln_mix bwd delta1", dlt1, (hm(do1, 64).float() * hm(o1, 64).float()).sum(-1), 2e-2, 1e-2)
+    ok &= report("dual_ln_mix bwd delta2", dlt2, (hm(do2, 128).float() * hm(o2s, 128).float()).sum(-1), 2e-2, 1e-2)
 
     # split cross attention
     q_obj = (torch.randn(M, 512, generator=g) * 0.8).bfloat16()
