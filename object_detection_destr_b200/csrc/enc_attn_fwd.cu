@@ -4,48 +4,64 @@
 // the reference at src/model/blocks/encoder_block.py:97-103 (need_weights=True math path: q*scale,
 // QK^T, key-padding mask -> -inf, softmax, PV) without ever materialising the N x N scores.
 //
-// One CTA = 128 query rows of one (batch, head); 192 threads:
-//   warps 0-3  softmax   (thread t <-> query row t <-> TMEM lane t; no cross-thread reductions)
-//   warp  4    TMA producer  (Q once; K_j / V_j tiles through a KSTAGES ring)
-//   warp  5    tcgen05.mma issuer + TMEM allocator
-// Head split is done by TMA: Q/K/V tiles are 128 x 32 boxes of the token-major projection output
+// At d_head = 32 the exp (MUFU) pipe and the issue slots of the softmax warps bound this kernel, not
+// the tensor pipe (a 128x96 score tile = 12 k exps = 768 MUFU cycles/SM against 192 tensor cycles), so
+// everything is arranged to keep four softmax warps per SM sub-partition busy:
+//   * persistent CTAs, 2 per SM, 320 threads: work item = 128 query rows of one (batch, head); the TMA
+//     and MMA warps run ahead across item boundaries, so an item's prologue hides under the previous
+//     item's softmax.
+//   * warps 0-7 softmax: thread <-> query row (TMEM lane 32*(warp%4)+lane); warps 0-3 own keys [0,48) of
+//     every 96-key tile, warps 4-7 keys [48,96).  Each half keeps its own running max / sum and its own
+//     O accumulator (split-K); the halves merge once per item through shared memory.
+//   * O stays in TMEM: P.V accumulates in place over the key tiles and is rescaled only when a row's
+//     running max grows by more than 2^8 (lazy rescale) -- no per-tile O read-back, no accumulator
+//     registers, which is what lets 640 threads/SM fit the register file.
+//   * S is double buffered (Q.K_{j+1}^T runs under softmax(S_j)); packed fp32x2 FMA/ADD, 3-input max;
+//     a knob moves a fraction of the exps from MUFU to an FMA-pipe polynomial (ex2_poly_f32x2).
+//   warp 8 TMA producer (Q double buffered; K_j / V_j through a KSTAGES ring), warp 9 tcgen05.mma issuer.
+// TMEM (256 columns per CTA): S0 [0,96) S1 [96,192) O_a [192,224) O_b [224,256).  P (bf16) overwrites
+// the first 24 columns of each half's own S region and is the A operand of P.V straight from TMEM.
+// Head split is done by TMA: Q/K/V tiles are rows x 32 boxes of the token-major projection output
 // (row pitch ld_*), 64-byte rows, SWIZZLE_64B.  Q,K are K-major UMMA operands; V is the MN-major B
-// operand of P.V.  S_j = Q.K_j^T lands in one of TWO 128-column TMEM buffers, so Q.K_{j+1}^T is issued
-// (and runs) while the softmax warps are still busy with S_j -- the exp (MUFU) pipe, not the tensor
-// pipe, bounds this kernel at d_head = 32 (16 k exps vs 2 x 1 MFLOP per tile).  Softmax threads read S
-// with tcgen05.ld, write P (bf16) back over the same columns with tcgen05.st, and the P.V MMA takes
-// A = P straight from TMEM.  O_j = P_j.V_j lands in a double-buffered 32-column TMEM slot and is folded
-// into a per-thread fp32 register accumulator with the online-softmax rescale.
-//
-// TMEM map (512 columns allocated): S0 [0,128) S1 [128,256) O0 [256,288) O1 [288,320).
-// P_b aliases the first 64 columns of S_b.
+// operand of P.V.
 #include "../../include/destr_b200.h"
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
 namespace destr {
 
+// debug / tuning knobs (destr_debug_knob): 0 v_lbo 1 v_sbo 2 qk_lbo 3 qk_sbo 4 p_kstep_cols 5 v_kstep_bytes
+// 6-8 enc_attn_bwd descriptors, 9 enc fwd polynomial-exp quarter count (0..3), 10 enc bwd ditto
 int g_knobs[16] = {512, 512, 16, 512, 8, 1024, 16384, 1024, 2048, 0, 0, 0, 0, 0, 0, 0};
 
 namespace {
 
 constexpr int DH = 32;
 constexpr int BM = 128;
-constexpr int BN = 128;
+constexpr int BN = 96;
+constexpr int HN = BN / 2;  // keys per softmax half
 constexpr int KSTAGES = 4;
-constexpr int NTHREADS = 192;
-constexpr uint32_t TILE_BYTES = BM * DH * 2;  // 8192
+constexpr int NTHREADS = 320;
+constexpr uint32_t Q_BYTES = BM * DH * 2;   // 8192
+constexpr uint32_t KV_BYTES = BN * DH * 2;  // 6144
+constexpr uint32_t C_S = 0, C_O = 2 * BN;   // TMEM columns
+constexpr float kLazyTau = 8.f;             // rescale O only when the row max grows by > 2^8
+constexpr int XCH = 20;                     // floats per row of the half-merge exchange (m, l, 16 x O, pad)
 
 struct __align__(1024) Smem {
-  uint8_t q[TILE_BYTES];
-  uint8_t k[KSTAGES][TILE_BYTES];
-  uint8_t v[KSTAGES][TILE_BYTES];
-  uint64_t q_full;
+  uint8_t q[2][Q_BYTES];
+  uint8_t k[KSTAGES][KV_BYTES];
+  uint8_t v[KSTAGES][KV_BYTES];
+  float xch[2][BM][XCH];
+  uint64_t q_full[2];
+  uint64_t q_empty[2];
   uint64_t kv_full[KSTAGES];
   uint64_t kv_empty[KSTAGES];
-  uint64_t s_full[2];  // indexed by tile parity j & 1
-  uint64_t p_full[2];
-  uint64_t o_full[2];
+  uint64_t s_full[2];     // indexed by flat tile parity f & 1
+  uint64_t p_full[2][2];  // [half][f & 1]
+  uint64_t o_full[2];     // [half]: one phase per tile
+  uint64_t o_free[2];     // [half]: one phase per item (epilogue has read O)
+  uint64_t o_done[2];     // [half]: one phase per item (last P.V of the item has landed)
   uint32_t tmem_base;
 };
 
@@ -53,192 +69,269 @@ struct Knobs {
   uint32_t v_lbo, v_sbo, qk_lbo, qk_sbo, p_kstep_cols, v_kstep_bytes;
 };
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+// POLYQ of every 4 key pairs take the FMA-pipe polynomial exp instead of MUFU.EX2
+template <int POLYQ>
+__global__ void __launch_bounds__(NTHREADS, 2)
 enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const uint32_t* __restrict__ mask_bits,
                     int words_per_row, __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int N, int heads,
-                    float scale_log2, Knobs kn) {
+                    int n_items, float scale_log2, float lazy_tau, Knobs kn) {
   extern __shared__ uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int q0 = qt * BM;
   const int nkv = (N + BN - 1) / BN;
-  const int row_base = b * N;  // first token row of this image
+  const int nqt = (N + BM - 1) / BM;
+  // items of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...;  item -> ((b*heads + h)*nqt + qt)
+  const int my_items = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int T = my_items * nkv;  // flat tile count
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
-    mbar_init(&sm.q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&sm.q_full[s], 1);
+      mbar_init(&sm.q_empty[s], 1);
+      mbar_init(&sm.s_full[s], 1);
+      mbar_init(&sm.p_full[0][s], BM);
+      mbar_init(&sm.p_full[1][s], BM);
+      mbar_init(&sm.o_full[s], 1);
+      mbar_init(&sm.o_free[s], BM);
+      mbar_init(&sm.o_done[s], 1);
+    }
     for (int s = 0; s < KSTAGES; ++s) {
       mbar_init(&sm.kv_full[s], 1);
       mbar_init(&sm.kv_empty[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&sm.s_full[s], 1);
-      mbar_init(&sm.p_full[s], BM);
-      mbar_init(&sm.o_full[s], 1);
-    }
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc<512>(&sm.tmem_base);
+  if (warp == 9) tmem_alloc<256>(&sm.tmem_base);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ------------------------------ TMA producer ------------------------------
     if (elect_one()) {
-      mbar_arrive_expect_tx(&sm.q_full, TILE_BYTES);
-      tma_load_2d(sm.q, &tm_q, &sm.q_full, h * DH, row_base + q0);
-      for (int j = 0; j < nkv; ++j) {
-        const int s = j % KSTAGES;
-        const uint32_t ph = (j / KSTAGES) & 1;
-        mbar_wait(&sm.kv_empty[s], ph ^ 1, 1);
-        mbar_arrive_expect_tx(&sm.kv_full[s], 2 * TILE_BYTES);
-        tma_load_2d(sm.k[s], &tm_k, &sm.kv_full[s], h * DH, row_base + j * BN);
-        tma_load_2d(sm.v[s], &tm_v, &sm.kv_full[s], h * DH, row_base + j * BN);
+      int f = 0;
+      for (int it = 0; it < my_items; ++it) {
+        const int w = blockIdx.x + it * gridDim.x;
+        const int qt = w % nqt, bh = w / nqt;
+        const int h = bh % heads, b = bh / heads;
+        const int row_base = b * N;
+        const int qb = it & 1;
+        mbar_wait_backoff(&sm.q_empty[qb], ((it >> 1) & 1) ^ 1, 1);
+        mbar_arrive_expect_tx(&sm.q_full[qb], Q_BYTES);
+        tma_load_2d(sm.q[qb], &tm_q, &sm.q_full[qb], h * DH, row_base + qt * BM);
+        for (int j = 0; j < nkv; ++j, ++f) {
+          const int s = f % KSTAGES;
+          mbar_wait_backoff(&sm.kv_empty[s], ((f / KSTAGES) & 1) ^ 1, 2);
+          mbar_arrive_expect_tx(&sm.kv_full[s], 2 * KV_BYTES);
+          tma_load_2d(sm.k[s], &tm_k, &sm.kv_full[s], h * DH, row_base + j * BN);
+          tma_load_2d(sm.v[s], &tm_v, &sm.kv_full[s], h * DH, row_base + j * BN);
+        }
       }
     }
     __syncwarp();
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ------------------------------ MMA issuer ------------------------------
     if (elect_one()) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(BM, BN, false, false);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(BM, DH, false, true);
-      auto issue_qk = [&](int j) {  // S_{j&1} = Q . K_j^T
-        const int stage = j % KSTAGES;
-        mbar_wait(&sm.kv_full[stage], (j / KSTAGES) & 1, 3);
+      auto issue_qk = [&](int f) {  // S_{f&1} = Q_item . K_j^T
+        const int it = f / nkv, j = f - it * nkv;
+        const int stage = f % KSTAGES, qb = it & 1;
+        if (j == 0) mbar_wait_backoff(&sm.q_full[qb], (it >> 1) & 1, 3);
+        mbar_wait_backoff(&sm.kv_full[stage], (f / KSTAGES) & 1, 4);
         tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < DH / 16; ++ks) {
-          const uint64_t a = umma_smem_desc(smem_u32(sm.q) + ks * 32, kn.qk_lbo, kn.qk_sbo, SWZ_64B);
+          const uint64_t a = umma_smem_desc(smem_u32(sm.q[qb]) + ks * 32, kn.qk_lbo, kn.qk_sbo, SWZ_64B);
           const uint64_t bd = umma_smem_desc(smem_u32(sm.k[stage]) + ks * 32, kn.qk_lbo, kn.qk_sbo, SWZ_64B);
-          umma_ss(tmem + (j & 1) * 128, a, bd, idesc_qk, ks > 0);
+          umma_ss(tmem + C_S + (f & 1) * BN, a, bd, idesc_qk, ks > 0);
         }
-        tc_commit(&sm.s_full[j & 1]);
+        tc_commit(&sm.s_full[f & 1]);
+        if (j == nkv - 1) tc_commit(&sm.q_empty[qb]);  // every Q.K^T of the item has been issued
       };
-      mbar_wait(&sm.q_full, 0, 2);
-      issue_qk(0);
-      if (nkv > 1) issue_qk(1);
-      for (int j = 0; j < nkv; ++j) {
-        const int stage = j % KSTAGES;
-        mbar_wait(&sm.p_full[j & 1], (j >> 1) & 1, 4);
-        tc_fence_after();
+      if (T > 0) issue_qk(0);
+      if (T > 1) issue_qk(1);
+      int it = 0, j = 0;
+      for (int f = 0; f < T; ++f) {
+        const int stage = f % KSTAGES;
 #pragma unroll
-        for (int ks = 0; ks < BN / 16; ++ks) {  // O_{j&1} = P_j . V_j
-          const uint64_t bd =
-              umma_smem_desc(smem_u32(sm.v[stage]) + ks * kn.v_kstep_bytes, kn.v_lbo, kn.v_sbo, SWZ_64B);
-          umma_ts(tmem + 256 + (j & 1) * 32, tmem + (j & 1) * 128 + ks * kn.p_kstep_cols, bd, idesc_pv, ks > 0);
+        for (int hf = 0; hf < 2; ++hf) {  // O_hf (+)= P_hf . V[keys of the half]
+          mbar_wait(&sm.p_full[hf][f & 1], (f >> 1) & 1, 5);
+          if (j == 0 && it > 0) mbar_wait_backoff(&sm.o_free[hf], (it - 1) & 1, 6);  // epilogue has read O
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < HN / 16; ++ks) {
+            const uint64_t bd = umma_smem_desc(smem_u32(sm.v[stage]) + (hf * (HN / 16) + ks) * kn.v_kstep_bytes,
+                                               kn.v_lbo, kn.v_sbo, SWZ_64B);
+            umma_ts(tmem + C_O + hf * DH, tmem + C_S + (f & 1) * BN + hf * HN + ks * kn.p_kstep_cols, bd, idesc_pv,
+                    (j > 0 || ks > 0) ? 1u : 0u);
+          }
+          tc_commit(&sm.o_full[hf]);
+          if (j == nkv - 1) tc_commit(&sm.o_done[hf]);
         }
-        tc_commit(&sm.o_full[j & 1]);
         tc_commit(&sm.kv_empty[stage]);
-        if (j + 2 < nkv) issue_qk(j + 2);  // reuses S_{j&1}: ordered behind P_j.V_j in the tensor pipe
+        if (f + 2 < T) issue_qk(f + 2);  // reuses S_{f&1}: ordered behind P.V(f) in the tensor pipe
+        if (++j == nkv) { j = 0; ++it; }
       }
     }
     __syncwarp();
   } else {
     // ------------------------------ softmax warps ------------------------------
-    const int wq = warp;
+    const int wq = warp & 3, hf = warp >> 2;
+    const int row = wq * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(wq * 32) << 16;
-    const uint32_t* mrow = mask_bits + static_cast<size_t>(b) * words_per_row;
+    const uint64_t sc2 = pack_f32x2(scale_log2, scale_log2);
+    int f = 0;
+    for (int it = 0; it < my_items; ++it) {
+      const int w = blockIdx.x + it * gridDim.x;
+      const int qt = w % nqt, bh = w / nqt;
+      const int h = bh % heads, b = bh / heads;
+      const uint32_t* mrow = mask_bits + static_cast<size_t>(b) * words_per_row;
+      float m_ref = -INFINITY, l = 0.f;
+      // mask bits of this half's 48 keys of tile j (bit i <-> key 96 j + 48 hf + i) live in two words; the raw
+      // words are prefetched one tile ahead and only combined when consumed (no stall on the load)
+      const uint32_t* mw = mrow + hf;
+      uint32_t mw0 = mw[0], mw1 = mw[1];
 
-    float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
-    float acc[DH];
+      for (int j = 0; j < nkv; ++j, ++f) {
+        const uint32_t s_addr = tmem + lane_addr + C_S + (f & 1) * BN + hf * HN;
+        const uint32_t c0 = mw0, c1 = mw1;
+        if (j + 1 < nkv) {
+          mw0 = mw[3 * (j + 1)];
+          mw1 = mw[3 * (j + 1) + 1];
+        }
+        mbar_wait(&sm.s_full[f & 1], (f >> 1) & 1, 7);
+        tc_fence_after();
+        uint32_t sr[HN];
+        {
+          uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sr[0]);
+          uint32_t(&hi)[16] = *reinterpret_cast<uint32_t(*)[16]>(&sr[32]);
+          tmem_ld_x32(s_addr, lo);
+          tmem_ld_x16(s_addr + 32, hi);
+        }
+        tc_wait_ld();
+        // hf 0: keys [0,48) = word0 | low half of word1;  hf 1: keys [48,96) = high half of word1 | word2
+        const uint64_t mb = hf == 0 ? (static_cast<uint64_t>(c0) | (static_cast<uint64_t>(c1 & 0xffffu) << 32))
+                                    : (static_cast<uint64_t>(c0 >> 16) | (static_cast<uint64_t>(c1) << 16));
+        if (mb != 0ull) {
 #pragma unroll
-    for (int i = 0; i < DH; ++i) acc[i] = 0.f;
-
-    for (int j = 0; j < nkv; ++j) {
-      const uint32_t s_addr = tmem + lane_addr + (j & 1) * 128;
-      mbar_wait(&sm.s_full[j & 1], (j >> 1) & 1, 6);
-      tc_fence_after();
-      uint32_t sr[4][32];
+          for (int i = 0; i < HN; ++i)
+            if ((mb >> i) & 1ull) sr[i] = 0xff800000u;  // -inf
+        }
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four independent FMNMX3 chains
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_x32(s_addr + c * 32, sr[c]);
-      tc_wait_ld();
-
-      const uint4 mw = *reinterpret_cast<const uint4*>(mrow + j * 4);
-      const uint32_t mwa[4] = {mw.x, mw.y, mw.z, mw.w};
-      if ((mw.x | mw.y | mw.z | mw.w) != 0u) {
+        for (int i = 0; i < HN; i += 8)
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+          for (int u = 0; u < 4; ++u)
+            mx4[u] = max3(mx4[u], __uint_as_float(sr[i + 2 * u]), __uint_as_float(sr[i + 2 * u + 1]));
+        const float m_new = fmaxf(m_ref, fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * scale_log2);
+        // lazy rescale: O and l stay relative to m_ref unless the max grew by more than 2^tau
+        const bool grow = m_new > m_ref + lazy_tau;  // also true for the first finite tile (m_ref = -inf)
+        const bool need = grow && (m_ref != -INFINITY);
+        if (__any_sync(0xffffffffu, need)) {
+          const float alpha = need ? ex2_approx(m_ref - m_new) : 1.f;
+          mbar_wait(&sm.o_full[hf], (f - 1) & 1, 8);  // P.V of the previous tile has landed
+          tc_fence_after();
+          uint32_t orr[32];
+          tmem_ld_x32(tmem + lane_addr + C_O + hf * DH, orr);
+          tc_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if ((mwa[c] >> i) & 1u) sr[c][i] = 0xff800000u;  // -inf
-      }
-      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four independent chains (ILP)
+          for (int i = 0; i < DH; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * alpha);
+          tmem_st_x32(tmem + lane_addr + C_O + hf * DH, orr);
+          l *= alpha;
+        }
+        if (grow) m_ref = m_new;
+        const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
+        const uint64_t nm2 = pack_f32x2(-m_use, -m_use);
+        uint64_t rs2[2] = {0ull, 0ull};
+        uint32_t pk[HN / 2];
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int i = 0; i < 32; ++i) mx4[c] = fmaxf(mx4[c], __uint_as_float(sr[c][i]));
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-      const float m_new = fmaxf(m, mx * scale_log2);
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = ex2_approx(m - m_use);
-      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t pk[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          // P columns [32c, 32c+32) hold keys [64c, 64c+64) packed two per column
-          const int e = 2 * i;
-          const float p0 = ex2_approx(fmaf(__uint_as_float(sr[2 * c + (e >> 5)][e & 31]), scale_log2, -m_use));
-          const float p1 =
-              ex2_approx(fmaf(__uint_as_float(sr[2 * c + ((e + 1) >> 5)][(e + 1) & 31]), scale_log2, -m_use));
-          rs4[i & 3] += p0 + p1;
+        for (int i = 0; i < HN / 2; ++i) {  // P column i holds keys 2i, 2i+1 of the half
+          const uint64_t x2 =
+              fma_f32x2(pack_f32x2(__uint_as_float(sr[2 * i]), __uint_as_float(sr[2 * i + 1])), sc2, nm2);
+          float x0, x1, p0, p1;
+          unpack_f32x2(x2, x0, x1);
+          if ((i & 3) < POLYQ) {
+            ex2_poly_f32x2(x0, x1, p0, p1);
+          } else {
+            p0 = ex2_approx(x0);
+            p1 = ex2_approx(x1);
+          }
+          rs2[i & 1] = add_f32x2(rs2[i & 1], pack_f32x2(p0, p1));
           pk[i] = pack_bf16x2(p0, p1);
         }
-        tmem_st_x32(s_addr + c * 32, pk);
+        {
+          uint32_t(&lo)[16] = *reinterpret_cast<uint32_t(*)[16]>(&pk[0]);
+          uint32_t(&hi)[8] = *reinterpret_cast<uint32_t(*)[8]>(&pk[16]);
+          tmem_st_x16(s_addr, lo);
+          tmem_st_x8(s_addr + 16, hi);
+        }
+        float r0, r1, r2, r3;
+        unpack_f32x2(rs2[0], r0, r1);
+        unpack_f32x2(rs2[1], r2, r3);
+        l += (r0 + r1) + (r2 + r3);
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(&sm.p_full[hf][f & 1]);
       }
-      l = l * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
-      tc_wait_st();
-      tc_fence_before();
-      mbar_arrive(&sm.p_full[j & 1]);
 
-      if (j > 0) {
-        const int jb = (j - 1) & 1;
-        mbar_wait(&sm.o_full[jb], ((j - 1) >> 1) & 1, 7);
-        tc_fence_after();
-        uint32_t orr[32];
-        tmem_ld_x32(tmem + lane_addr + 256 + jb * 32, orr);
-        tc_wait_ld();
-#pragma unroll
-        for (int i = 0; i < DH; ++i) acc[i] = fmaf(acc[i], alpha_prev, __uint_as_float(orr[i]));
-      }
-      alpha_prev = alpha;
-      m = m_new;
-    }
-    {
-      const int jl = nkv - 1;
-      mbar_wait(&sm.o_full[jl & 1], (jl >> 1) & 1, 8);
+      // ---- item epilogue: read O, free it for the next item, merge the two key halves ----
+      // (o_full advances one phase per tile and is only waited on by the lazy rescale, where it is provably at
+      // most one phase behind; the epilogue gets its own once-per-item barrier so parities cannot alias)
+      mbar_wait(&sm.o_done[hf], it & 1, 9);
       tc_fence_after();
       uint32_t orr[32];
-      tmem_ld_x32(tmem + lane_addr + 256 + (jl & 1) * 32, orr);
+      tmem_ld_x32(tmem + lane_addr + C_O + hf * DH, orr);
       tc_wait_ld();
+      tc_fence_before();
+      mbar_arrive(&sm.o_free[hf]);
+      float* xw = sm.xch[hf][row];
+      xw[0] = m_ref;
+      xw[1] = l;
 #pragma unroll
-      for (int i = 0; i < DH; ++i) acc[i] = fmaf(acc[i], alpha_prev, __uint_as_float(orr[i]));
-    }
-    const int qrow = q0 + wq * 32 + lane;
-    if (qrow < N) {
-      const float inv = 1.f / l;
-      uint32_t ob[DH / 2];
+      for (int i = 0; i < 16; i += 4)  // the 16 dims the other half finalises
+        *reinterpret_cast<float4*>(xw + 4 + i) =
+            make_float4(__uint_as_float(orr[(1 - hf) * 16 + i]), __uint_as_float(orr[(1 - hf) * 16 + i + 1]),
+                        __uint_as_float(orr[(1 - hf) * 16 + i + 2]), __uint_as_float(orr[(1 - hf) * 16 + i + 3]));
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float* xr = sm.xch[1 - hf][row];
+      const float m_o = xr[0], l_o = xr[1];
+      const float m_all = fmaxf(m_ref, m_o);
+      const float m_fin = (m_all == -INFINITY) ? 0.f : m_all;
+      const float a_s = ex2_approx(m_ref - m_fin), a_o = ex2_approx(m_o - m_fin);
+      const float l_all = l * a_s + l_o * a_o;
+      const float inv = 1.f / l_all;
+      const float cs = a_s * inv, co = a_o * inv;
+      const int qrow = qt * BM + row;
+      uint32_t ob[8];
 #pragma unroll
-      for (int i = 0; i < DH / 2; ++i) ob[i] = pack_bf16x2(acc[2 * i] * inv, acc[2 * i + 1] * inv);
-      uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(row_base + qrow) * heads + h) * DH);
-#pragma unroll
-      for (int i = 0; i < DH / 8; ++i) dst[i] = make_uint4(ob[4 * i], ob[4 * i + 1], ob[4 * i + 2], ob[4 * i + 3]);
-      if (lse) lse[(static_cast<size_t>(b) * heads + h) * N + qrow] = m + lg2_approx(l);
+      for (int i = 0; i < 16; i += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(xr + 4 + i);
+        ob[i / 2] = pack_bf16x2(__uint_as_float(orr[hf * 16 + i]) * cs + t.x * co,
+                                __uint_as_float(orr[hf * 16 + i + 1]) * cs + t.y * co);
+        ob[i / 2 + 1] = pack_bf16x2(__uint_as_float(orr[hf * 16 + i + 2]) * cs + t.z * co,
+                                    __uint_as_float(orr[hf * 16 + i + 3]) * cs + t.w * co);
+      }
+      if (qrow < N) {
+        uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(b * N + qrow) * heads + h) * DH + hf * 16);
+        dst[0] = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+        dst[1] = make_uint4(ob[4], ob[5], ob[6], ob[7]);
+        if (lse && hf == 0) lse[(static_cast<size_t>(b) * heads + h) * N + qrow] = m_all + lg2_approx(l_all);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // exchange buffer is reused by the next item
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc<512>(tmem);
+  if (warp == 9) tmem_dealloc<256>(tmem);
 }
 
 }  // namespace
@@ -256,7 +349,7 @@ extern "C" int destr_enc_attn_fwd(const void* q, const void* k, const void* v, i
   using namespace destr;
   DESTR_CHECK_ARG(q && k && v && mask_bits && out, "null pointer");
   DESTR_CHECK_ARG(B > 0 && N > 0 && heads > 0 && heads * DH <= 256, "shape");
-  DESTR_CHECK_ARG(words_per_row >= ceil_div(N, BN) * 4 && (words_per_row % 4) == 0, "words_per_row");
+  DESTR_CHECK_ARG(words_per_row >= ceil_div(N, BN) * 3, "words_per_row (need >= 3 words per 96-key tile)");
   const uint64_t rows = static_cast<uint64_t>(B) * N;
   CUtensorMap tq, tk, tv;
   int rc;
@@ -264,17 +357,24 @@ extern "C" int destr_enc_attn_fwd(const void* q, const void* k, const void* v, i
   if ((rc = make_tmap_bf16_2d(&tk, k, rows, heads * DH, ld_k, BN, DH, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   if ((rc = make_tmap_bf16_2d(&tv, v, rows, heads * DH, ld_v, BN, DH, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   const size_t smem = sizeof(Smem) + 1024;
+  using KernelT = decltype(&enc_attn_fwd_kernel<0>);
+  static const KernelT kernels[4] = {enc_attn_fwd_kernel<0>, enc_attn_fwd_kernel<1>, enc_attn_fwd_kernel<2>,
+                                     enc_attn_fwd_kernel<3>};
   static bool attr_done = false;
   if (!attr_done) {
-    DESTR_CUDA(cudaFuncSetAttribute(enc_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int i = 0; i < 4; ++i)
+      DESTR_CUDA(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
+  const KernelT kernel = kernels[g_knobs[9] & 3];
+  const int n_items = B * heads * ceil_div(N, BM);
+  int grid = n_items < 2 * 148 ? n_items : 2 * 148;  // persistent: 2 CTAs per SM
+  if (g_knobs[12] > 0 && g_knobs[12] < grid) grid = g_knobs[12];
   Knobs kn{(uint32_t)g_knobs[0], (uint32_t)g_knobs[1], (uint32_t)g_knobs[2],
            (uint32_t)g_knobs[3], (uint32_t)g_knobs[4], (uint32_t)g_knobs[5]};
-  dim3 grid(ceil_div(N, BM), heads, B);
-  enc_attn_fwd_kernel<<<grid, NTHREADS, smem, static_cast<cudaStream_t>(stream)>>>(
-      tq, tk, tv, mask_bits, words_per_row, static_cast<__nv_bfloat16*>(out), lse, N, heads,
-      scale * 1.4426950408889634f, kn);
+  kernel<<<grid, NTHREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+      tq, tk, tv, mask_bits, words_per_row, static_cast<__nv_bfloat16*>(out), lse, N, heads, n_items,
+      scale * 1.4426950408889634f, g_knobs[11] ? (float)(g_knobs[11] - 1) : kLazyTau, kn);
   DESTR_LAUNCH_CHECK();
   return 0;
 }

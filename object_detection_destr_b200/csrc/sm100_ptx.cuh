@@ -45,6 +45,70 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Blackwell packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2) and 3-input max (FMNMX3): halve the
+// issue slots of the softmax inner loops, which are bound by the exp (MUFU) pipe and issue rate.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t sub_f32x2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t add_rm_f32x2(uint64_t a, uint64_t b) {  // round toward -inf
+  uint64_t r;
+  asm("add.rm.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+// 2^x for a pair of x <= 0 on the FMA pipe (no MUFU): Cody-Waite split x = n + f, n = floor(x),
+// cubic minimax polynomial for 2^f on [0,1) (max rel err 7.5e-5 -- below bf16 rounding of P), then the
+// exponent is added with integer arithmetic.  x is clamped to >= -126 (results flush toward 2^-126).
+__device__ __forceinline__ void ex2_poly_f32x2(float x0, float x1, float& p0, float& p1) {
+  const float kMagic = 12582912.f;  // 1.5 * 2^23
+  x0 = fmaxf(x0, -126.f);
+  x1 = fmaxf(x1, -126.f);
+  const uint64_t x = pack_f32x2(x0, x1);
+  const uint64_t mg = pack_f32x2(kMagic, kMagic);
+  const uint64_t r = add_rm_f32x2(x, mg);        // low mantissa bits = floor(x)
+  const uint64_t n = sub_f32x2(r, mg);           // floor(x) as float
+  const uint64_t f = sub_f32x2(x, n);            // [0,1)
+  uint64_t p = fma_f32x2(f, pack_f32x2(0.0780245215f, 0.0780245215f), pack_f32x2(0.2260671556f, 0.2260671556f));
+  p = fma_f32x2(p, f, pack_f32x2(0.6958335638f, 0.6958335638f));
+  p = fma_f32x2(p, f, pack_f32x2(0.9999251962f, 0.9999251962f));
+  float q0, q1, r0, r1;
+  unpack_f32x2(p, q0, q1);
+  unpack_f32x2(r, r0, r1);
+  p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(r0) << 23));
+  p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(r1) << 23));
+}
+
+// ------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -83,6 +147,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
   const uint64_t t0 = globaltimer_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (((++spins) & 0x3ff) == 0 && globaltimer_ns() - t0 > DESTR_WAIT_TIMEOUT_NS) {
+      printf("destr_b200: mbarrier wait timeout tag=%d block=(%d,%d,%d) thread=%d parity=%u\n", tag,
+             blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+
+// Same, for the single-thread producer / MMA-issuer roles: sleeps between polls so the spin loop does not
+// take issue slots from the compute warps sharing the SM sub-partition.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, int tag = 0) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = globaltimer_ns();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(32);
     if (((++spins) & 0x3ff) == 0 && globaltimer_ns() - t0 > DESTR_WAIT_TIMEOUT_NS) {
       printf("destr_b200: mbarrier wait timeout tag=%d block=(%d,%d,%d) thread=%d parity=%u\n", tag,
              blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, parity);
@@ -211,6 +291,11 @@ __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t (&r)[
       "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
       "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
+}
+__device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
 }
 __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(

@@ -37,7 +37,8 @@ def _ptr(t: Optional[Tensor]) -> Optional[int]:
 # masks / positional embeddings
 # ----------------------------------------------------------------------------------------------
 def mask_words(n_keys: int) -> int:
-    return ((n_keys + 127) // 128) * 4
+    # >= 4 words per 128-key tile (decoder / backward kernels) and >= 3 words per 96-key tile (encoder forward)
+    return (max(((n_keys + 127) // 128) * 4, ((n_keys + 95) // 96) * 3) + 3) // 4 * 4
 
 
 def pack_key_mask(kpm: Optional[Tensor], B: int, n_keys: int, device=None) -> Tensor:

@@ -415,6 +415,18 @@ def main():
         sys.exit(0 if ok else 1)
     if what == "attnbwd":
         sys.exit(0 if check_attn_bwd(sys.argv[2:]) else 1)
+    if what == "polysweep":  # exp-offload knob sweep (9 = fwd, 10 = bwd): accuracy + time at config 2 / config 4
+        from object_detection_destr_b200 import _lib
+        ok = True
+        for pq in range(4):
+            _lib.lib.destr_debug_knob(9, pq)
+            _lib.lib.destr_debug_knob(10, pq)
+            print(f"== poly quarter count {pq}", flush=True)
+            ok &= attn_case(8, 1050, 8, "random", True, time_it=True)
+            ok &= attn_bwd_case(8, 1050, 8, True, time_it=True)
+            if os.environ.get("DESTR_BIG"):
+                ok &= attn_case(16, 4200, 8, "random", False, time_it=True)
+        sys.exit(0 if ok else 1)
     if what == "bwdsweep":
         for cfg in [[], ["6=1024", "7=16384"], ["8=1024"], ["6=16384", "7=2048"], ["6=128", "7=1024"]]:
             print(f"== attnbwd knobs={cfg}", flush=True)
