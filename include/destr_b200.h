@@ -113,10 +113,12 @@ int destr_enc_attn_fwd(const void* q, const void* k, const void* v, int ld_q, in
                        const uint32_t* mask_bits, int words_per_row, void* out, float* lse, int B, int N,
                        int heads, float scale, void* stream);
 /* backward: dq, dk, dv bf16 with the same row pitches as q, k, v (ld_dq, ld_dk, ld_dv).
- * delta (fp32 [B,heads,N]) and dq_acc (fp32 [B*N, heads*32]) are caller-provided workspaces. */
+ * Caller-provided workspaces: stats (fp32, destr_enc_attn_bwd_stats_floats(B,N,heads) elements: -lse and
+ * -delta = -rowsum(dO o O), padded to 128-query tiles) and dq_acc (fp32 [B*N, heads*32]). */
+int destr_enc_attn_bwd_stats_floats(int B, int N, int heads);
 int destr_enc_attn_bwd(const void* q, const void* k, const void* v, int ld_q, int ld_k, int ld_v,
                        const uint32_t* mask_bits, int words_per_row, const void* out, const void* dout,
-                       const float* lse, float* delta, float* dq_acc, void* dq, void* dk, void* dv, int ld_dq,
+                       const float* lse, float* stats, float* dq_acc, void* dq, void* dk, void* dv, int ld_dq,
                        int ld_dk, int ld_dv, int B, int N, int heads, float scale, void* stream);
 
 /* ---------------- decoder: pairing, self + pair attention, split cross-attention ---------------- */

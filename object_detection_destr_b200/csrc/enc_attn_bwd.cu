@@ -4,18 +4,27 @@
 // F.multi_head_attention_forward as called at src/model/blocks/encoder_block.py:97-103).
 // Scores are recomputed from Q,K and the saved log-sum-exp; nothing N x N is ever stored.
 //
-// One CTA = one 128-key tile j of one (batch, head); it loops over all 128-query tiles i.  Everything
-// is computed TRANSPOSED (rows = keys) so that thread t <-> key row t <-> TMEM lane t:
-//   S^T  = K_j . Q_i^T            (SS MMA, K-major x K-major)       -> TMEM ST   [0,128)
-//   dP^T = V_j . dO_i^T           (SS MMA)                           -> TMEM DPT  [128,256)
-//   P^T  = exp2(c*S^T - lse_q)    dS^T = P^T o (dP^T - delta_q)      (8 compute warps)
-//   dV_j += P^T . dO_i            (TS MMA, A = P^T bf16 in TMEM [256,320), B = dO_i MN-major)
-//   dK_j += dS^T . Q_i            (SS MMA, A = dS^T in smem K-major SW128, B = Q_i MN-major)
-//   dQ_i  = dS . K_j              (SS MMA, A = the same smem dS^T read MN-major, B = K_j MN-major)
-// dV_j / dK_j accumulate in TMEM ([320,352) / [352,384)) across the whole loop; dQ_i tiles
-// (double buffered at [384,416) / [416,448)) are drained with red.global.add.v4.f32 into an fp32
-// accumulator that a small kernel converts to bf16 afterwards.
-// Warps: 0-7 compute (warp w: TMEM lanes 32*(w%4).., query columns 64*(w/4)..), 8 TMA, 9 MMA.
+// Work item = one 128-key tile j of one (batch, head); a persistent CTA (one per SM, 576 threads) walks
+// its items and, inside an item, the queries in 64-row sub-tiles u.  Everything is computed TRANSPOSED
+// (rows = keys) so that thread <-> key row <-> TMEM lane:
+//   S^T_u  = K_j . Q_u^T            (SS MMA, N = 64)      -> TMEM ST[g]
+//   dP^T_u = V_j . dO_u^T           (SS MMA, N = 64)      -> TMEM DPT[g]
+//   P^T = exp2(c*S^T - lse_q),  dS^T = P^T o (dP^T - delta_q)          (compute group g = u & 1)
+//   dV_j += P^T_u . dO_u            (TS MMA, A = P^T bf16 in TMEM PT[g], B = dO_u MN-major)
+//   dK_j += dS^T_u . Q_u            (SS MMA, A = dS^T in smem K-major SW128, B = Q_u MN-major)
+//   dQ_p  = dS_p . K_j              once per PAIR p of sub-tiles (M = 128 queries): A = the two dS^T blocks
+//                                   of the pair read MN-major, B = K_j MN-major
+// Two compute groups of 8 warps ping-pong on the sub-tiles (group g owns ST[g]/DPT[g]/PT[g]), so the
+// tensor pipe works on sub-tile u+1 while the exp/FMA pipes work on u -- at d_head = 32 both are busy
+// (16 k exps = 1024 MUFU cycles against ~800 tensor cycles per 128x128 tile).  Warp w of a group:
+// TMEM lanes 32*(w%4).., query columns 32*((w/4)%2).. of the sub-tile.
+// Nothing in the loop waits for a drain: dQ_p is pulled out of TMEM one pair later (group p&1,
+// red.global.add.v4.f32 into an fp32 accumulator that a small kernel converts to bf16), dV_j / dK_j are
+// double buffered in TMEM by item parity and stored while the next item is already running, and the
+// TMA / MMA warps run ahead across item boundaries.
+//
+// TMEM (512 columns): ST0 [0,64) DPT0 [64,128) ST1 [128,192) DPT1 [192,256) DV0/DK0 [256,320)
+//                     DV1/DK1 [320,384) DQ0 [384,416) DQ1 [416,448) PT0 [448,480) PT1 [480,512)
 #include "../../include/destr_b200.h"
 #include "common.cuh"
 #include "sm100_ptx.cuh"
@@ -25,27 +34,28 @@ extern int g_knobs[16];
 namespace {
 
 constexpr int DH = 32;
-constexpr int BT = 128;  // tile edge (keys and queries)
-constexpr int QSTAGES = 2;
-constexpr int NTHREADS = 320;
-constexpr uint32_t TILE_BYTES = BT * DH * 2;  // 8192
-constexpr uint32_t DS_BLOCK_BYTES = BT * 128;  // 16384: [128 key rows][64 queries] bf16, SW128
+constexpr int BT = 128;  // keys per item, queries per pair
+constexpr int BQ = 64;   // queries per sub-tile
+constexpr int QSTAGES = 4;
+constexpr int NTHREADS = 576;  // 16 compute warps + TMA warp + MMA warp
+constexpr uint32_t KV_BYTES = BT * DH * 2;       // 8192
+constexpr uint32_t Q_BYTES = BQ * DH * 2;        // 4096
+constexpr uint32_t STAT_BYTES = 2 * BQ * 4;      // 512: -lse[64] | -delta[64]
+constexpr uint32_t DS_BLOCK_BYTES = BT * 128;    // 16384: [128 key rows][64 queries] bf16, SW128
+constexpr uint32_t C_ST = 0, C_DPT = 64, C_SBUF = 128, C_DV = 256, C_DK = 288, C_ACC = 64, C_DQ = 384, C_PT = 448;
 
 struct __align__(1024) Smem {
-  uint8_t k[TILE_BYTES];
-  uint8_t v[TILE_BYTES];
-  uint8_t q[QSTAGES][TILE_BYTES];
-  uint8_t d_o[QSTAGES][TILE_BYTES];
-  uint8_t ds[2][DS_BLOCK_BYTES];
-  float lse_s[2][BT];
-  float delta_s[2][BT];
-  uint64_t kv_full;
-  uint64_t q_full[QSTAGES];
-  uint64_t q_empty[QSTAGES];
-  uint64_t sdp_full;
-  uint64_t pds_full;
-  uint64_t dq_full[2];
-  uint64_t dkv_full;
+  uint8_t k[2][KV_BYTES];
+  uint8_t v[2][KV_BYTES];
+  uint8_t q[QSTAGES][Q_BYTES];
+  uint8_t d_o[QSTAGES][Q_BYTES];
+  uint8_t ds[2][2][DS_BLOCK_BYTES];  // [pair parity][sub-tile within the pair]
+  float stat[QSTAGES][2 * BQ];
+  uint64_t kv_full[2], kv_free[2];
+  uint64_t q_full[QSTAGES], q_empty[QSTAGES];
+  uint64_t sdp_full[2], pds_full[2];
+  uint64_t dq_done[2], dq_free[2];
+  uint64_t dkv_full[2], dkv_free[2];
   uint32_t tmem_base;
 };
 
@@ -58,243 +68,319 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                : "memory");
 }
 
+struct Item {
+  int b, h, j;
+};
+__device__ __forceinline__ Item decode_item(int w, int nkt, int heads) {
+  Item it;
+  it.j = w % nkt;
+  const int bh = w / nkt;
+  it.h = bh % heads;
+  it.b = bh / heads;
+  return it;
+}
+
+template <int POLYQ>
 __global__ void __launch_bounds__(NTHREADS, 1)
 enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
-                    const uint32_t* __restrict__ mask_bits, int words_per_row, const float* __restrict__ lse,
-                    const float* __restrict__ delta, float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dk,
-                    __nv_bfloat16* __restrict__ dv, int ld_dk, int ld_dv, int N, int heads, float scale,
-                    float scale_log2, Knobs kn) {
+                    const uint32_t* __restrict__ mask_bits, int words_per_row, const float* __restrict__ stats,
+                    float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv,
+                    int ld_dk, int ld_dv, int N, int heads, int n_items, float scale, float scale_log2, Knobs kn) {
   extern __shared__ uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int j = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int nq = (N + BT - 1) / BT;
-  const int row_base = b * N;
+  const int nkt = (N + BT - 1) / BT;  // key tiles per (b,h) == query pairs per item
+  const int npairs = nkt;
+  const int my_items = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int Ptot = my_items * npairs;  // flat pair count; flat sub-tile U = 2*Pf + g
 
-  if (warp == 8 && lane == 0) {
+  if (warp == 16 && lane == 0) {
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
     tma_prefetch_desc(&tm_do);
-    mbar_init(&sm.kv_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&sm.kv_full[s], 1);
+      mbar_init(&sm.kv_free[s], 1);
+      mbar_init(&sm.sdp_full[s], 1);
+      mbar_init(&sm.pds_full[s], 256);
+      mbar_init(&sm.dq_done[s], 1);
+      mbar_init(&sm.dq_free[s], 256);
+      mbar_init(&sm.dkv_full[s], 1);
+      mbar_init(&sm.dkv_free[s], 512);
+    }
     for (int s = 0; s < QSTAGES; ++s) {
       mbar_init(&sm.q_full[s], 1);
       mbar_init(&sm.q_empty[s], 1);
     }
-    mbar_init(&sm.sdp_full, 1);
-    mbar_init(&sm.pds_full, 256);
-    mbar_init(&sm.dq_full[0], 1);
-    mbar_init(&sm.dq_full[1], 1);
-    mbar_init(&sm.dkv_full, 1);
     fence_mbar_init();
   }
-  if (warp == 9) tmem_alloc<512>(&sm.tmem_base);
+  if (warp == 17) tmem_alloc<512>(&sm.tmem_base);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
-  constexpr uint32_t C_ST = 0, C_DPT = 128, C_PT = 256, C_DV = 320, C_DK = 352, C_DQ = 384;
 
-  if (warp == 8) {
+  if (warp == 16) {
+    // ------------------------------ TMA producer ------------------------------
     if (elect_one()) {
-      mbar_arrive_expect_tx(&sm.kv_full, 2 * TILE_BYTES);
-      tma_load_2d(sm.k, &tm_k, &sm.kv_full, h * DH, row_base + j * BT);
-      tma_load_2d(sm.v, &tm_v, &sm.kv_full, h * DH, row_base + j * BT);
-      for (int i = 0; i < nq; ++i) {
-        const int s = i % QSTAGES;
-        mbar_wait(&sm.q_empty[s], ((i / QSTAGES) & 1) ^ 1, 11);
-        mbar_arrive_expect_tx(&sm.q_full[s], 2 * TILE_BYTES);
-        tma_load_2d(sm.q[s], &tm_q, &sm.q_full[s], h * DH, row_base + i * BT);
-        tma_load_2d(sm.d_o[s], &tm_do, &sm.q_full[s], h * DH, row_base + i * BT);
+      int U = 0;
+      for (int it = 0; it < my_items; ++it) {
+        const Item im = decode_item(blockIdx.x + it * gridDim.x, nkt, heads);
+        const int row_base = im.b * N;
+        const int kb = it & 1;
+        mbar_wait_backoff(&sm.kv_free[kb], ((it >> 1) & 1) ^ 1, 1);
+        mbar_arrive_expect_tx(&sm.kv_full[kb], 2 * KV_BYTES);
+        tma_load_2d(sm.k[kb], &tm_k, &sm.kv_full[kb], im.h * DH, row_base + im.j * BT);
+        tma_load_2d(sm.v[kb], &tm_v, &sm.kv_full[kb], im.h * DH, row_base + im.j * BT);
+        const float* st_bh = stats + (static_cast<size_t>(im.b) * heads + im.h) * (2 * npairs) * (2 * BQ);
+        for (int u = 0; u < 2 * npairs; ++u, ++U) {
+          const int s = U % QSTAGES;
+          mbar_wait_backoff(&sm.q_empty[s], ((U / QSTAGES) & 1) ^ 1, 2);
+          mbar_arrive_expect_tx(&sm.q_full[s], 2 * Q_BYTES + STAT_BYTES);
+          tma_load_2d(sm.q[s], &tm_q, &sm.q_full[s], im.h * DH, row_base + u * BQ);
+          tma_load_2d(sm.d_o[s], &tm_do, &sm.q_full[s], im.h * DH, row_base + u * BQ);
+          bulk_load(sm.stat[s], st_bh + static_cast<size_t>(u) * (2 * BQ), STAT_BYTES, &sm.q_full[s]);
+        }
       }
     }
     __syncwarp();
-  } else if (warp == 9) {
+  } else if (warp == 17) {
+    // ------------------------------ MMA issuer ------------------------------
     if (elect_one()) {
-      constexpr uint32_t id_sT = umma_idesc_bf16(BT, BT, false, false);   // K-major x K-major, N=128
+      constexpr uint32_t id_sT = umma_idesc_bf16(BT, BQ, false, false);   // K-major x K-major, N = 64
       constexpr uint32_t id_kn = umma_idesc_bf16(BT, DH, false, true);    // A K-major (TMEM/smem), B MN-major
       constexpr uint32_t id_nn = umma_idesc_bf16(BT, DH, true, true);     // A MN-major, B MN-major
-      mbar_wait(&sm.kv_full, 0, 12);
-      for (int i = 0; i < nq; ++i) {
-        const int s = i % QSTAGES;
-        mbar_wait(&sm.q_full[s], (i / QSTAGES) & 1, 13);
+      const int Utot = 2 * Ptot;
+      auto issue_sdp = [&](int U) {
+        const int Pf = U >> 1, g = U & 1, s = U % QSTAGES;
+        const int it = Pf / npairs, kb = it & 1;
+        if (U == 2 * it * npairs) mbar_wait_backoff(&sm.kv_full[kb], (it >> 1) & 1, 3);  // first sub-tile of the item
+        mbar_wait_backoff(&sm.q_full[s], (U / QSTAGES) & 1, 4);
         tc_fence_after();
 #pragma unroll
-        for (int ks = 0; ks < DH / 16; ++ks) {
-          umma_ss(tmem + C_ST, umma_smem_desc(smem_u32(sm.k) + ks * 32, kn.kmaj_lbo, 512, SWZ_64B),
+        for (int ks = 0; ks < DH / 16; ++ks)
+          umma_ss(tmem + g * C_SBUF + C_ST, umma_smem_desc(smem_u32(sm.k[kb]) + ks * 32, kn.kmaj_lbo, 512, SWZ_64B),
                   umma_smem_desc(smem_u32(sm.q[s]) + ks * 32, kn.kmaj_lbo, 512, SWZ_64B), id_sT, ks > 0);
-        }
 #pragma unroll
-        for (int ks = 0; ks < DH / 16; ++ks) {
-          umma_ss(tmem + C_DPT, umma_smem_desc(smem_u32(sm.v) + ks * 32, kn.kmaj_lbo, 512, SWZ_64B),
+        for (int ks = 0; ks < DH / 16; ++ks)
+          umma_ss(tmem + g * C_SBUF + C_DPT, umma_smem_desc(smem_u32(sm.v[kb]) + ks * 32, kn.kmaj_lbo, 512, SWZ_64B),
                   umma_smem_desc(smem_u32(sm.d_o[s]) + ks * 32, kn.kmaj_lbo, 512, SWZ_64B), id_sT, ks > 0);
-        }
-        tc_commit(&sm.sdp_full);
-        mbar_wait(&sm.pds_full, i & 1, 14);
+        tc_commit(&sm.sdp_full[g]);
+      };
+      if (Utot > 0) issue_sdp(0);
+      if (Utot > 1) issue_sdp(1);
+      int it = 0, p = 0;  // item / pair within the item of sub-tile U
+      for (int U = 0; U < Utot; ++U) {
+        const int Pf = U >> 1, g = U & 1, s = U % QSTAGES, kb = it & 1, pb = Pf & 1;
+        mbar_wait(&sm.pds_full[g], Pf & 1, 5);
+        // group g has consumed ST[g]/DPT[g]: its next sub-tile goes to the tensor pipe FIRST (it is what the
+        // group waits for); dV/dK/dQ of this sub-tile are off the critical path and queue up behind it
+        if (U + 2 < Utot) issue_sdp(U + 2);
+        if (p == 0 && g == 0) mbar_wait_backoff(&sm.dkv_free[kb], ((it >> 1) & 1) ^ 1, 6);  // accumulators drained
         tc_fence_after();
-        // dV += P^T . dO_i
+        const uint32_t first = (p == 0 && g == 0) ? 0u : 1u;
+        // dV += P^T_u . dO_u
 #pragma unroll
-        for (int ks = 0; ks < BT / 16; ++ks) {
-          umma_ts(tmem + C_DV, tmem + C_PT + ks * 8,
+        for (int ks = 0; ks < BQ / 16; ++ks)
+          umma_ts(tmem + C_DV + kb * C_ACC, tmem + C_PT + g * 32 + ks * 8,
                   umma_smem_desc(smem_u32(sm.d_o[s]) + ks * 1024, kn.mn64_lbo, kn.mn64_sbo, SWZ_64B), id_kn,
-                  (i > 0 || ks > 0) ? 1u : 0u);
-        }
-        // dK += dS^T . Q_i
+                  (ks > 0) ? 1u : first);
+        // dK += dS^T_u . Q_u
 #pragma unroll
-        for (int ks = 0; ks < BT / 16; ++ks) {
-          umma_ss(tmem + C_DK,
-                  umma_smem_desc(smem_u32(sm.ds[ks >> 2]) + (ks & 3) * 32, kn.kmaj_lbo, 1024, SWZ_128B),
+        for (int ks = 0; ks < BQ / 16; ++ks)
+          umma_ss(tmem + C_DK + kb * C_ACC,
+                  umma_smem_desc(smem_u32(sm.ds[pb][g]) + ks * 32, kn.kmaj_lbo, 1024, SWZ_128B),
                   umma_smem_desc(smem_u32(sm.q[s]) + ks * 1024, kn.mn64_lbo, kn.mn64_sbo, SWZ_64B), id_kn,
-                  (i > 0 || ks > 0) ? 1u : 0u);
-        }
-        // dQ_i = dS . K_j
-#pragma unroll
-        for (int ks = 0; ks < BT / 16; ++ks) {
-          umma_ss(tmem + C_DQ + (i & 1) * 32,
-                  umma_smem_desc(smem_u32(sm.ds[0]) + ks * kn.a_mn_kstep, kn.a_mn_lbo, kn.a_mn_sbo, SWZ_128B),
-                  umma_smem_desc(smem_u32(sm.k) + ks * 1024, kn.mn64_lbo, kn.mn64_sbo, SWZ_64B), id_nn, ks > 0);
-        }
-        tc_commit(&sm.dq_full[i & 1]);
+                  (ks > 0) ? 1u : first);
         tc_commit(&sm.q_empty[s]);
+        if (g == 1) {
+          // dQ_pair = dS_pair . K_j   (M = 128 queries spanning the pair's two dS^T blocks)
+          mbar_wait_backoff(&sm.dq_free[pb], ((Pf >> 1) & 1) ^ 1, 7);
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < BT / 16; ++ks)
+            umma_ss(tmem + C_DQ + pb * 32,
+                    umma_smem_desc(smem_u32(sm.ds[pb][0]) + ks * kn.a_mn_kstep, kn.a_mn_lbo, kn.a_mn_sbo, SWZ_128B),
+                    umma_smem_desc(smem_u32(sm.k[kb]) + ks * 1024, kn.mn64_lbo, kn.mn64_sbo, SWZ_64B), id_nn, ks > 0);
+          tc_commit(&sm.dq_done[pb]);
+          if (p == npairs - 1) {
+            tc_commit(&sm.dkv_full[kb]);
+            tc_commit(&sm.kv_free[kb]);
+          }
+          if (++p == npairs) { p = 0; ++it; }
+        }
       }
-      tc_commit(&sm.dkv_full);
     }
     __syncwarp();
   } else {
     // ------------------------------ compute warps ------------------------------
-    const int wq = warp & 3, half = warp >> 2;
-    const int tid = threadIdx.x;  // 0..255
-    const int krow = wq * 32 + lane;
-    const int key = j * BT + krow;
+    const int g = warp >> 3;              // compute group: sub-tile parity
+    const int wq = warp & 3, cg = (warp >> 2) & 1;
+    const int krow = wq * 32 + lane;      // TMEM lane: key row (S^T, dV, dK) / query row (dQ)
     const uint32_t lane_addr = static_cast<uint32_t>(wq * 32) << 16;
-    const bool key_masked =
-        (mask_bits[static_cast<size_t>(b) * words_per_row + (key >> 5)] >> (key & 31)) & 1u;
-    const float* lse_bh = lse + (static_cast<size_t>(b) * heads + h) * N;
-    const float* delta_bh = delta + (static_cast<size_t>(b) * heads + h) * N;
+    const uint64_t sc2 = pack_f32x2(scale_log2, scale_log2);
 
-    auto drain_dq = [&](int i) {
-      mbar_wait(&sm.dq_full[i & 1], (i >> 1) & 1, 16);
+    auto drain_dq = [&](int Df, const Item& im, int pair) {  // flat pair Df (= pair `pair` of item im) -> dq_acc
+      const int pb = Df & 1;
+      mbar_wait(&sm.dq_done[pb], (Df >> 1) & 1, 8);
       tc_fence_after();
       uint32_t r[16];
-      tmem_ld_x16(tmem + lane_addr + C_DQ + (i & 1) * 32 + half * 16, r);
+      tmem_ld_x16(tmem + lane_addr + C_DQ + pb * 32 + cg * 16, r);
       tc_wait_ld();
-      const int qrow = i * BT + krow;  // dQ tile rows are queries
+      tc_fence_before();
+      mbar_arrive(&sm.dq_free[pb]);
+      const int qrow = pair * BT + krow;
       if (qrow < N) {
-        float* dst = dq_acc + (static_cast<size_t>(row_base + qrow) * heads + h) * DH + half * 16;
+        float* dst = dq_acc + (static_cast<size_t>(im.b * N + qrow) * heads + im.h) * DH + cg * 16;
 #pragma unroll
         for (int c = 0; c < 4; ++c)
           red_add_v4(dst + 4 * c, __uint_as_float(r[4 * c]) * scale, __uint_as_float(r[4 * c + 1]) * scale,
                      __uint_as_float(r[4 * c + 2]) * scale, __uint_as_float(r[4 * c + 3]) * scale);
       }
     };
-
-    for (int i = 0; i < nq; ++i) {
-      {
-        const int qq = i * BT + (tid & 127);
-        if (tid < 128)
-          sm.lse_s[i & 1][tid] = (qq < N) ? lse_bh[qq] : INFINITY;
-        else
-          sm.delta_s[i & 1][tid - 128] = (qq < N) ? delta_bh[qq] : 0.f;
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      mbar_wait(&sm.sdp_full, i & 1, 15);
+    auto drain_dkv = [&](int it, const Item& im) {  // group 0 stores dV_j, group 1 stores dK_j
+      const int kb = it & 1;
+      mbar_wait(&sm.dkv_full[kb], (it >> 1) & 1, 9);
       tc_fence_after();
-      uint32_t st[2][32], dp[2][32];
-      tmem_ld_x32(tmem + lane_addr + C_ST + half * 64, st[0]);
-      tmem_ld_x32(tmem + lane_addr + C_ST + half * 64 + 32, st[1]);
-      tmem_ld_x32(tmem + lane_addr + C_DPT + half * 64, dp[0]);
-      tmem_ld_x32(tmem + lane_addr + C_DPT + half * 64 + 32, dp[1]);
+      uint32_t r[16];
+      tmem_ld_x16(tmem + lane_addr + (g == 0 ? C_DV : C_DK) + kb * C_ACC + cg * 16, r);
       tc_wait_ld();
-      const float4* lse4 = reinterpret_cast<const float4*>(&sm.lse_s[i & 1][half * 64]);
-      const float4* del4 = reinterpret_cast<const float4*>(&sm.delta_s[i & 1][half * 64]);
-      uint32_t pk[32];
-      uint8_t* ds_row = sm.ds[half] + krow * 128;
-#pragma unroll
-      for (int c8 = 0; c8 < 8; ++c8) {  // 8 queries per 16-byte chunk
-        float pv[8], dsv[8];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const float4 l4 = lse4[c8 * 2 + u];
-          const float4 d4 = del4[c8 * 2 + u];
-          const float la[4] = {l4.x, l4.y, l4.z, l4.w};
-          const float da[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int c = c8 * 8 + u * 4 + e;
-            float p = ex2_approx(fmaf(__uint_as_float(st[c >> 5][c & 31]), scale_log2, -la[e]));
-            p = key_masked ? 0.f : p;
-            pv[u * 4 + e] = p;
-            dsv[u * 4 + e] = p * (__uint_as_float(dp[c >> 5][c & 31]) - da[e]);
-          }
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) pk[c8 * 4 + e] = pack_bf16x2(pv[2 * e], pv[2 * e + 1]);
-        const uint4 dsq = make_uint4(pack_bf16x2(dsv[0], dsv[1]), pack_bf16x2(dsv[2], dsv[3]),
-                                     pack_bf16x2(dsv[4], dsv[5]), pack_bf16x2(dsv[6], dsv[7]));
-        *reinterpret_cast<uint4*>(ds_row + ((c8 ^ (krow & 7)) << 4)) = dsq;
-      }
-      tmem_st_x32(tmem + lane_addr + C_PT + half * 32, pk);
-      tc_wait_st();
-      fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(&sm.pds_full);
-      if (i > 0) drain_dq(i - 1);
-    }
-    drain_dq(nq - 1);
-    mbar_wait(&sm.dkv_full, 0, 17);
-    tc_fence_after();
-    uint32_t rv[16], rk[16];
-    tmem_ld_x16(tmem + lane_addr + C_DV + half * 16, rv);
-    tmem_ld_x16(tmem + lane_addr + C_DK + half * 16, rk);
-    tc_wait_ld();
-    if (key < N) {
-      uint32_t ov[8], ok[8];
+      mbar_arrive(&sm.dkv_free[kb]);
+      const int key = im.j * BT + krow;
+      if (key < N) {
+        const float f = (g == 0) ? 1.f : scale;
+        uint32_t o[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        ov[c] = pack_bf16x2(__uint_as_float(rv[2 * c]), __uint_as_float(rv[2 * c + 1]));
-        ok[c] = pack_bf16x2(__uint_as_float(rk[2 * c]) * scale, __uint_as_float(rk[2 * c + 1]) * scale);
+        for (int c = 0; c < 8; ++c) o[c] = pack_bf16x2(__uint_as_float(r[2 * c]) * f, __uint_as_float(r[2 * c + 1]) * f);
+        __nv_bfloat16* base = (g == 0) ? dv + static_cast<size_t>(im.b * N + key) * ld_dv
+                                       : dk + static_cast<size_t>(im.b * N + key) * ld_dk;
+        uint4* dst = reinterpret_cast<uint4*>(base + im.h * DH + cg * 16);
+        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
       }
-      uint4* pv_ = reinterpret_cast<uint4*>(dv + static_cast<size_t>(row_base + key) * ld_dv + h * DH + half * 16);
-      uint4* pk_ = reinterpret_cast<uint4*>(dk + static_cast<size_t>(row_base + key) * ld_dk + h * DH + half * 16);
-      pv_[0] = make_uint4(ov[0], ov[1], ov[2], ov[3]);
-      pv_[1] = make_uint4(ov[4], ov[5], ov[6], ov[7]);
-      pk_[0] = make_uint4(ok[0], ok[1], ok[2], ok[3]);
-      pk_[1] = make_uint4(ok[4], ok[5], ok[6], ok[7]);
+    };
+
+    Item prev{0, 0, 0};
+    int Pf = 0;
+    for (int it = 0; it < my_items; ++it) {
+      const Item im = decode_item(blockIdx.x + it * gridDim.x, nkt, heads);
+      const int key = im.j * BT + krow;
+      const bool key_masked = (mask_bits[static_cast<size_t>(im.b) * words_per_row + (key >> 5)] >> (key & 31)) & 1u;
+      for (int p = 0; p < npairs; ++p, ++Pf) {
+        const int U = 2 * Pf + g, s = U % QSTAGES, pb = Pf & 1;
+        mbar_wait(&sm.sdp_full[g], Pf & 1, 10);
+        mbar_wait(&sm.q_full[s], (U / QSTAGES) & 1, 11);  // long complete: makes the TMA-written stats visible
+        tc_fence_after();
+        const float4* nl4 = reinterpret_cast<const float4*>(&sm.stat[s][cg * 32]);        // -lse
+        const float4* nd4 = reinterpret_cast<const float4*>(&sm.stat[s][BQ + cg * 32]);   // -delta
+        uint8_t* ds_row = sm.ds[pb][g] + krow * 128;
+#pragma unroll
+        for (int hc = 0; hc < 2; ++hc) {  // two chunks of 16 query columns (keeps the live set small)
+          uint32_t st[16], dp[16];
+          tmem_ld_x16(tmem + lane_addr + g * C_SBUF + C_ST + cg * 32 + hc * 16, st);
+          tmem_ld_x16(tmem + lane_addr + g * C_SBUF + C_DPT + cg * 32 + hc * 16, dp);
+          tc_wait_ld();
+          if (hc == 0) mbar_wait(&sm.dq_done[pb], ((Pf >> 1) & 1) ^ 1, 12);  // dS^T block free: dQ(Pf-2) has read it
+          uint32_t pk[8], dsk[8];
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const float4 a = nl4[hc * 4 + c4], d = nd4[hc * 4 + c4];
+            const float nl[4] = {a.x, a.y, a.z, a.w}, nd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int e = 0; e < 4; e += 2) {
+              const int c = c4 * 4 + e;
+              const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(st[c]), __uint_as_float(st[c + 1])), sc2,
+                                            pack_f32x2(nl[e], nl[e + 1]));
+              float x0, x1, p0, p1;
+              unpack_f32x2(x2, x0, x1);
+              if (((c >> 1) & 3) < POLYQ) {
+                ex2_poly_f32x2(x0, x1, p0, p1);
+              } else {
+                p0 = ex2_approx(x0);
+                p1 = ex2_approx(x1);
+              }
+              const uint64_t dd = add_f32x2(pack_f32x2(__uint_as_float(dp[c]), __uint_as_float(dp[c + 1])),
+                                            pack_f32x2(nd[e], nd[e + 1]));
+              const uint64_t ds2 = mul_f32x2(pack_f32x2(p0, p1), dd);
+              float d0, d1;
+              unpack_f32x2(ds2, d0, d1);
+              pk[c >> 1] = pack_bf16x2(p0, p1);
+              dsk[c >> 1] = pack_bf16x2(d0, d1);
+            }
+          }
+          if (key_masked) {  // a padded key contributes nothing: P^T row = dS^T row = 0
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pk[i] = dsk[i] = 0u;
+          }
+          tmem_st_x8(tmem + lane_addr + C_PT + g * 32 + cg * 16 + hc * 8, pk);
+#pragma unroll
+          for (int c = 0; c < 2; ++c)  // 8 queries per 16-byte chunk; chunk index = 4*cg + 2*hc + c
+            *reinterpret_cast<uint4*>(ds_row + (((4 * cg + 2 * hc + c) ^ (krow & 7)) << 4)) =
+                make_uint4(dsk[4 * c], dsk[4 * c + 1], dsk[4 * c + 2], dsk[4 * c + 3]);
+        }
+        tc_wait_st();
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(&sm.pds_full[g]);
+
+        // ---- deferred drains (their MMAs were issued one pair / one item ago) ----
+        if (Pf > 0 && ((Pf - 1) & 1) == g) {
+          if (p > 0) drain_dq(Pf - 1, im, p - 1);
+          else drain_dq(Pf - 1, prev, npairs - 1);
+        }
+        if (p == 0 && it > 0) drain_dkv(it - 1, prev);
+      }
+      prev = im;
+    }
+    if (Ptot > 0) {
+      if (((Ptot - 1) & 1) == g) drain_dq(Ptot - 1, prev, npairs - 1);
+      drain_dkv(my_items - 1, prev);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc<512>(tmem);
+  if (warp == 17) tmem_dealloc<512>(tmem);
 }
 
-// delta[b,h,n] = sum_d dO[n,h,d] * O[n,h,d]   (one warp per token row; 4 lanes per head)
-__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
-                                  float* __restrict__ delta, int B, int N, int heads) {
+// Pre-pass, one warp per (padded) token row q of an image, Np = 128*ceil(N/128) rows per image:
+//   delta[b,h,q] = sum_d dO[q,h,d] * O[q,h,d];  stats[b,h][q/64][0][q%64] = -lse, [1][q%64] = -delta
+//   (padding rows: -lse = -inf -> P = 0, -delta = 0);  dq_acc row q <- 0.
+__global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
+                                     const float* __restrict__ lse, float* __restrict__ stats,
+                                     float* __restrict__ dq_acc, int B, int N, int Np, int heads) {
   const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= B * N) return;
+  const int prow = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (prow >= B * Np) return;
+  const int b = prow / Np, q = prow - b * Np;
   const int cols = heads * DH;
+  const int hh = lane >> 2;
   float s = 0.f;
-  if (lane * 8 < cols) {
-    const uint4 a = *reinterpret_cast<const uint4*>(o + static_cast<size_t>(row) * cols + lane * 8);
-    const uint4 g = *reinterpret_cast<const uint4*>(d_o + static_cast<size_t>(row) * cols + lane * 8);
+  if (q < N && lane * 8 < cols) {
+    const size_t row = static_cast<size_t>(b) * N + q;
+    const uint4 a = *reinterpret_cast<const uint4*>(o + row * cols + lane * 8);
+    const uint4 g = *reinterpret_cast<const uint4*>(d_o + row * cols + lane * 8);
     const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       s = fmaf(__uint_as_float(aw[i] << 16), __uint_as_float(gw[i] << 16), s);
       s = fmaf(__uint_as_float(aw[i] & 0xffff0000u), __uint_as_float(gw[i] & 0xffff0000u), s);
     }
+    float4* z = reinterpret_cast<float4*>(dq_acc + row * cols + lane * 8);
+    z[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    z[1] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   s += __shfl_xor_sync(0xffffffffu, s, 1);
   s += __shfl_xor_sync(0xffffffffu, s, 2);
-  const int hh = lane >> 2;
   if ((lane & 3) == 0 && hh < heads) {
-    const int bb = row / N, n = row - bb * N;
-    delta[(static_cast<size_t>(bb) * heads + hh) * N + n] = s;
+    float* dst = stats + ((static_cast<size_t>(b) * heads + hh) * (Np / BQ) + q / BQ) * (2 * BQ) + (q % BQ);
+    dst[0] = (q < N) ? -lse[(static_cast<size_t>(b) * heads + hh) * N + q] : -INFINITY;
+    dst[BQ] = (q < N) ? -s : 0.f;
   }
 }
 
@@ -314,42 +400,53 @@ __global__ void cvt_f32_bf16_rows_kernel(const float* __restrict__ src, __nv_bfl
 }  // namespace
 }  // namespace destr
 
+extern "C" int destr_enc_attn_bwd_stats_floats(int B, int N, int heads) {
+  return B * heads * ((N + 127) / 128) * 128 * 2;
+}
+
 extern "C" int destr_enc_attn_bwd(const void* q, const void* k, const void* v, int ld_q, int ld_k, int ld_v,
                                   const uint32_t* mask_bits, int words_per_row, const void* out, const void* dout,
-                                  const float* lse, float* delta, float* dq_acc, void* dq, void* dk, void* dv,
+                                  const float* lse, float* stats, float* dq_acc, void* dq, void* dk, void* dv,
                                   int ld_dq, int ld_dk, int ld_dv, int B, int N, int heads, float scale,
                                   void* stream) {
   using namespace destr;
-  DESTR_CHECK_ARG(q && k && v && mask_bits && out && dout && lse && delta && dq_acc && dq && dk && dv, "null pointer");
+  DESTR_CHECK_ARG(q && k && v && mask_bits && out && dout && lse && stats && dq_acc && dq && dk && dv, "null pointer");
   DESTR_CHECK_ARG(B > 0 && N > 0 && heads > 0 && heads * DH <= 256, "shape");
   DESTR_CHECK_ARG(words_per_row >= ceil_div(N, BT) * 4, "words_per_row");
   DESTR_CHECK_ARG(ld_dq % 8 == 0 && ld_dk % 8 == 0 && ld_dv % 8 == 0, "gradient row pitch must be a multiple of 8");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const uint64_t rows = static_cast<uint64_t>(B) * N;
   const int cols = heads * DH;
+  const int Np = ceil_div(N, BT) * BT;
   CUtensorMap tq, tk, tv, tdo;
   int rc;
-  if ((rc = make_tmap_bf16_2d(&tq, q, rows, cols, ld_q, BT, DH, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tq, q, rows, cols, ld_q, BQ, DH, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   if ((rc = make_tmap_bf16_2d(&tk, k, rows, cols, ld_k, BT, DH, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   if ((rc = make_tmap_bf16_2d(&tv, v, rows, cols, ld_v, BT, DH, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tdo, dout, rows, cols, cols, BT, DH, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tdo, dout, rows, cols, cols, BQ, DH, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   const size_t smem = sizeof(Smem) + 1024;
+  using KernelT = decltype(&enc_attn_bwd_kernel<0>);
+  static const KernelT kernels[4] = {enc_attn_bwd_kernel<0>, enc_attn_bwd_kernel<1>, enc_attn_bwd_kernel<2>,
+                                     enc_attn_bwd_kernel<3>};
   static bool attr_done = false;
   if (!attr_done) {
-    DESTR_CUDA(cudaFuncSetAttribute(enc_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int i = 0; i < 4; ++i)
+      DESTR_CUDA(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  attn_delta_kernel<<<ceil_div((int)rows, 8), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(out),
-                                                            static_cast<const __nv_bfloat16*>(dout), delta, B, N,
-                                                            heads);
+  attn_bwd_prep_kernel<<<ceil_div(B * Np, 8), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(out),
+                                                            static_cast<const __nv_bfloat16*>(dout), lse, stats,
+                                                            dq_acc, B, N, Np, heads);
   DESTR_LAUNCH_CHECK();
-  DESTR_CUDA(cudaMemsetAsync(dq_acc, 0, rows * cols * sizeof(float), st));
   Knobs kn{(uint32_t)g_knobs[0], (uint32_t)g_knobs[1], (uint32_t)g_knobs[2],
            (uint32_t)g_knobs[6], (uint32_t)g_knobs[7], (uint32_t)g_knobs[8]};
-  dim3 grid(ceil_div(N, BT), heads, B);
-  enc_attn_bwd_kernel<<<grid, NTHREADS, smem, st>>>(tq, tk, tv, tdo, mask_bits, words_per_row, lse, delta, dq_acc,
-                                                    static_cast<__nv_bfloat16*>(dk), static_cast<__nv_bfloat16*>(dv),
-                                                    ld_dk, ld_dv, N, heads, scale, scale * 1.4426950408889634f, kn);
+  const int n_items = B * heads * ceil_div(N, BT);
+  int grid = n_items < 148 ? n_items : 148;  // persistent: one CTA per SM
+  if (g_knobs[13] > 0 && g_knobs[13] < grid) grid = g_knobs[13];
+  kernels[g_knobs[10] & 3]<<<grid, NTHREADS, smem, st>>>(tq, tk, tv, tdo, mask_bits, words_per_row, stats, dq_acc,
+                                                         static_cast<__nv_bfloat16*>(dk),
+                                                         static_cast<__nv_bfloat16*>(dv), ld_dk, ld_dv, N, heads,
+                                                         n_items, scale, scale * 1.4426950408889634f, kn);
   DESTR_LAUNCH_CHECK();
   const int64_t n4 = static_cast<int64_t>(rows) * cols / 4;
   int blocks = (int)((n4 + 255) / 256);

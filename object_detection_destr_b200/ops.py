@@ -197,7 +197,7 @@ def enc_attn_bwd(q: Tensor, k: Tensor, v: Tensor, mask_bits: Tensor, out: Tensor
     dout = _chk(dout.contiguous(), BF16, "dout")
     dqk = torch.empty(B * N, 2 * C, dtype=BF16, device=q.device)
     dv = torch.empty(B * N, C, dtype=BF16, device=q.device)
-    delta = torch.empty(B, heads, N, dtype=torch.float32, device=q.device)
+    delta = torch.empty(B * heads * ((N + 127) // 128) * 256, dtype=torch.float32, device=q.device)  # stats workspace
     dq_acc = torch.empty(B * N, C, dtype=torch.float32, device=q.device)
     dq, dk = dqk[:, :C], dqk[:, C:]
     _lib.call("destr_enc_attn_bwd", q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), k.stride(0), v.stride(0),
