@@ -150,62 +150,77 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     __syncwarp();
   } else if (warp == 17) {
     // ------------------------------ MMA issuer ------------------------------
+    // One thread issues every MMA, so its instruction stream is the critical path between "group g has
+    // consumed S/dP" and "group g's next S/dP is ready": descriptors are compile-time constants plus a
+    // shifted address, and everything the next S/dP needs is prepared BEFORE waiting for the group.
     if (elect_one()) {
       constexpr uint32_t id_sT = umma_idesc_bf16(BT, BQ, false, false);   // K-major x K-major, N = 64
       constexpr uint32_t id_kn = umma_idesc_bf16(BT, DH, false, true);    // A K-major (TMEM/smem), B MN-major
       constexpr uint32_t id_nn = umma_idesc_bf16(BT, DH, true, true);     // A MN-major, B MN-major
+      constexpr uint64_t D_KMAJ64 = umma_desc_const(16, 512, SWZ_64B);      // K-major, 64-byte rows
+      constexpr uint64_t D_MN64 = umma_desc_const(512, 512, SWZ_64B);       // MN-major, 64-byte rows (k-step 1024 B)
+      constexpr uint64_t D_KMAJ128 = umma_desc_const(16, 1024, SWZ_128B);   // dS^T as K-major A (k-step 32 B)
+      constexpr uint64_t D_AMN128 = umma_desc_const(16384, 1024, SWZ_128B); // dS^T pair as MN-major A (k-step 2048 B)
+      const uint32_t a_k = smem_u32(sm.k[0]) >> 4, a_v = smem_u32(sm.v[0]) >> 4, a_q = smem_u32(sm.q[0]) >> 4,
+                     a_do = smem_u32(sm.d_o[0]) >> 4, a_ds = smem_u32(sm.ds[0][0]) >> 4;
       const int Utot = 2 * Ptot;
-      auto issue_sdp = [&](int U) {
-        const int Pf = U >> 1, g = U & 1, s = U % QSTAGES;
-        const int it = Pf / npairs, kb = it & 1;
-        if (U == 2 * it * npairs) mbar_wait_backoff(&sm.kv_full[kb], (it >> 1) & 1, 3);  // first sub-tile of the item
-        mbar_wait_backoff(&sm.q_full[s], (U / QSTAGES) & 1, 4);
-        tc_fence_after();
-#pragma unroll
-        for (int ks = 0; ks < DH / 16; ++ks)
-          umma_ss(tmem + g * C_SBUF + C_ST, umma_smem_desc(smem_u32(sm.k[kb]) + ks * 32, kn.kmaj_lbo, 512, SWZ_64B),
-                  umma_smem_desc(smem_u32(sm.q[s]) + ks * 32, kn.kmaj_lbo, 512, SWZ_64B), id_sT, ks > 0);
-#pragma unroll
-        for (int ks = 0; ks < DH / 16; ++ks)
-          umma_ss(tmem + g * C_SBUF + C_DPT, umma_smem_desc(smem_u32(sm.v[kb]) + ks * 32, kn.kmaj_lbo, 512, SWZ_64B),
-                  umma_smem_desc(smem_u32(sm.d_o[s]) + ks * 32, kn.kmaj_lbo, 512, SWZ_64B), id_sT, ks > 0);
+      // S^T / dP^T of flat sub-tile U (item parity kb) into the buffers of group U & 1
+      auto issue_sdp = [&](int U, int kb) {
+        const uint32_t g = U & 1, s = U % QSTAGES;
+        const uint64_t dk_ = D_KMAJ64 + (a_k + kb * (KV_BYTES >> 4)), dv_ = D_KMAJ64 + (a_v + kb * (KV_BYTES >> 4));
+        const uint64_t dq_ = D_KMAJ64 + (a_q + s * (Q_BYTES >> 4)), ddo_ = D_KMAJ64 + (a_do + s * (Q_BYTES >> 4));
+        umma_ss(tmem + g * C_SBUF + C_ST, dk_, dq_, id_sT, 0u);
+        umma_ss(tmem + g * C_SBUF + C_ST, dk_ + 2, dq_ + 2, id_sT, 1u);
+        umma_ss(tmem + g * C_SBUF + C_DPT, dv_, ddo_, id_sT, 0u);
+        umma_ss(tmem + g * C_SBUF + C_DPT, dv_ + 2, ddo_ + 2, id_sT, 1u);
         tc_commit(&sm.sdp_full[g]);
       };
-      if (Utot > 0) issue_sdp(0);
-      if (Utot > 1) issue_sdp(1);
+      if (Utot > 0) {
+        mbar_wait_backoff(&sm.kv_full[0], 0, 3);
+        for (int U = 0; U < 2 && U < Utot; ++U) {
+          mbar_wait_backoff(&sm.q_full[U], 0, 4);
+          tc_fence_after();
+          issue_sdp(U, 0);
+        }
+      }
       int it = 0, p = 0;  // item / pair within the item of sub-tile U
       for (int U = 0; U < Utot; ++U) {
         const int Pf = U >> 1, g = U & 1, s = U % QSTAGES, kb = it & 1, pb = Pf & 1;
+        // ---- stage the group's NEXT sub-tile (U+2 = pair Pf+1): operands landed? ----
+        const bool has_next = U + 2 < Utot;
+        const int it_n = (p + 1 == npairs) ? it + 1 : it;
+        if (has_next) {
+          if (g == 0 && p + 1 == npairs) mbar_wait_backoff(&sm.kv_full[it_n & 1], (it_n >> 1) & 1, 3);
+          mbar_wait_backoff(&sm.q_full[(U + 2) % QSTAGES], ((U + 2) / QSTAGES) & 1, 4);
+        }
         mbar_wait(&sm.pds_full[g], Pf & 1, 5);
-        // group g has consumed ST[g]/DPT[g]: its next sub-tile goes to the tensor pipe FIRST (it is what the
-        // group waits for); dV/dK/dQ of this sub-tile are off the critical path and queue up behind it
-        if (U + 2 < Utot) issue_sdp(U + 2);
-        if (p == 0 && g == 0) mbar_wait_backoff(&sm.dkv_free[kb], ((it >> 1) & 1) ^ 1, 6);  // accumulators drained
         tc_fence_after();
+        if (has_next) issue_sdp(U + 2, it_n & 1);  // the group waits for this: first into the tensor pipe
+        // ---- gradients of sub-tile U: off the critical path, queue up behind ----
+        if (p == 0 && g == 0) {
+          mbar_wait_backoff(&sm.dkv_free[kb], ((it >> 1) & 1) ^ 1, 6);  // accumulators of item it-2 drained
+          tc_fence_after();
+        }
         const uint32_t first = (p == 0 && g == 0) ? 0u : 1u;
-        // dV += P^T_u . dO_u
+        const uint64_t ddo_mn = D_MN64 + (a_do + s * (Q_BYTES >> 4)), dq_mn = D_MN64 + (a_q + s * (Q_BYTES >> 4));
+        const uint64_t dds_k = D_KMAJ128 + (a_ds + (pb * 2 + g) * (DS_BLOCK_BYTES >> 4));
 #pragma unroll
-        for (int ks = 0; ks < BQ / 16; ++ks)
-          umma_ts(tmem + C_DV + kb * C_ACC, tmem + C_PT + g * 32 + ks * 8,
-                  umma_smem_desc(smem_u32(sm.d_o[s]) + ks * 1024, kn.mn64_lbo, kn.mn64_sbo, SWZ_64B), id_kn,
+        for (int ks = 0; ks < BQ / 16; ++ks)  // dV += P^T_u . dO_u
+          umma_ts(tmem + C_DV + kb * C_ACC, tmem + C_PT + g * 32 + ks * 8, ddo_mn + ks * 64, id_kn,
                   (ks > 0) ? 1u : first);
-        // dK += dS^T_u . Q_u
 #pragma unroll
-        for (int ks = 0; ks < BQ / 16; ++ks)
-          umma_ss(tmem + C_DK + kb * C_ACC,
-                  umma_smem_desc(smem_u32(sm.ds[pb][g]) + ks * 32, kn.kmaj_lbo, 1024, SWZ_128B),
-                  umma_smem_desc(smem_u32(sm.q[s]) + ks * 1024, kn.mn64_lbo, kn.mn64_sbo, SWZ_64B), id_kn,
-                  (ks > 0) ? 1u : first);
+        for (int ks = 0; ks < BQ / 16; ++ks)  // dK += dS^T_u . Q_u
+          umma_ss(tmem + C_DK + kb * C_ACC, dds_k + ks * 2, dq_mn + ks * 64, id_kn, (ks > 0) ? 1u : first);
         tc_commit(&sm.q_empty[s]);
         if (g == 1) {
           // dQ_pair = dS_pair . K_j   (M = 128 queries spanning the pair's two dS^T blocks)
           mbar_wait_backoff(&sm.dq_free[pb], ((Pf >> 1) & 1) ^ 1, 7);
           tc_fence_after();
+          const uint64_t dds_mn = D_AMN128 + (a_ds + pb * 2 * (DS_BLOCK_BYTES >> 4));
+          const uint64_t dk_mn = D_MN64 + (a_k + kb * (KV_BYTES >> 4));
 #pragma unroll
           for (int ks = 0; ks < BT / 16; ++ks)
-            umma_ss(tmem + C_DQ + pb * 32,
-                    umma_smem_desc(smem_u32(sm.ds[pb][0]) + ks * kn.a_mn_kstep, kn.a_mn_lbo, kn.a_mn_sbo, SWZ_128B),
-                    umma_smem_desc(smem_u32(sm.k[kb]) + ks * 1024, kn.mn64_lbo, kn.mn64_sbo, SWZ_64B), id_nn, ks > 0);
+            umma_ss(tmem + C_DQ + pb * 32, dds_mn + ks * 128, dk_mn + ks * 64, id_nn, ks > 0);
           tc_commit(&sm.dq_done[pb]);
           if (p == npairs - 1) {
             tc_commit(&sm.dkv_full[kb]);
@@ -265,31 +280,39 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       }
     };
 
+    const uint32_t sb = smem_u32(&sm);
+    const uint32_t b_sdp = sb + offsetof(Smem, sdp_full) + g * 8, b_pds = sb + offsetof(Smem, pds_full) + g * 8;
+    const uint32_t b_qfull = sb + offsetof(Smem, q_full), b_dqdone = sb + offsetof(Smem, dq_done);
+    const uint32_t a_stat = sb + offsetof(Smem, stat) + cg * 128;                 // -lse of my 32 queries (+256: -delta)
+    const uint32_t a_ds = sb + offsetof(Smem, ds) + g * DS_BLOCK_BYTES + krow * 128;  // my dS^T row (pair parity 0)
+    const uint32_t t_st = tmem + lane_addr + g * C_SBUF + C_ST + cg * 32;
+    const uint32_t t_pt = tmem + lane_addr + C_PT + g * 32 + cg * 16;
+    const uint32_t swz = krow & 7;
+
     Item prev{0, 0, 0};
-    int Pf = 0;
+    uint32_t Pf = 0;
     for (int it = 0; it < my_items; ++it) {
       const Item im = decode_item(blockIdx.x + it * gridDim.x, nkt, heads);
       const int key = im.j * BT + krow;
       const bool key_masked = (mask_bits[static_cast<size_t>(im.b) * words_per_row + (key >> 5)] >> (key & 31)) & 1u;
       for (int p = 0; p < npairs; ++p, ++Pf) {
-        const int U = 2 * Pf + g, s = U % QSTAGES, pb = Pf & 1;
-        mbar_wait(&sm.sdp_full[g], Pf & 1, 10);
-        mbar_wait(&sm.q_full[s], (U / QSTAGES) & 1, 11);  // long complete: makes the TMA-written stats visible
+        const uint32_t U = 2 * Pf + g, s = U % QSTAGES, pb = Pf & 1;
+        mbar_wait_a(b_sdp, Pf & 1, 10);
+        mbar_wait_a(b_qfull + s * 8, (U / QSTAGES) & 1, 11);  // long complete: makes the TMA-written stats visible
         tc_fence_after();
-        const float4* nl4 = reinterpret_cast<const float4*>(&sm.stat[s][cg * 32]);        // -lse
-        const float4* nd4 = reinterpret_cast<const float4*>(&sm.stat[s][BQ + cg * 32]);   // -delta
-        uint8_t* ds_row = sm.ds[pb][g] + krow * 128;
+        const uint32_t stat_s = a_stat + s * STAT_BYTES;
+        const uint32_t ds_row = a_ds + pb * (2 * DS_BLOCK_BYTES);
 #pragma unroll
         for (int hc = 0; hc < 2; ++hc) {  // two chunks of 16 query columns (keeps the live set small)
           uint32_t st[16], dp[16];
-          tmem_ld_x16(tmem + lane_addr + g * C_SBUF + C_ST + cg * 32 + hc * 16, st);
-          tmem_ld_x16(tmem + lane_addr + g * C_SBUF + C_DPT + cg * 32 + hc * 16, dp);
+          tmem_ld_x16(t_st + hc * 16, st);
+          tmem_ld_x16(t_st + (C_DPT - C_ST) + hc * 16, dp);
           tc_wait_ld();
-          if (hc == 0) mbar_wait(&sm.dq_done[pb], ((Pf >> 1) & 1) ^ 1, 12);  // dS^T block free: dQ(Pf-2) has read it
+          if (hc == 0) mbar_wait_a(b_dqdone + pb * 8, ((Pf >> 1) & 1) ^ 1, 12);  // dS^T block free: dQ(Pf-2) has read it
           uint32_t pk[8], dsk[8];
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4) {
-            const float4 a = nl4[hc * 4 + c4], d = nd4[hc * 4 + c4];
+            const float4 a = lds_f4(stat_s + (hc * 4 + c4) * 16), d = lds_f4(stat_s + BQ * 4 + (hc * 4 + c4) * 16);
             const float nl[4] = {a.x, a.y, a.z, a.w}, nd[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
             for (int e = 0; e < 4; e += 2) {
@@ -317,19 +340,19 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 #pragma unroll
             for (int i = 0; i < 8; ++i) pk[i] = dsk[i] = 0u;
           }
-          tmem_st_x8(tmem + lane_addr + C_PT + g * 32 + cg * 16 + hc * 8, pk);
+          tmem_st_x8(t_pt + hc * 8, pk);
 #pragma unroll
           for (int c = 0; c < 2; ++c)  // 8 queries per 16-byte chunk; chunk index = 4*cg + 2*hc + c
-            *reinterpret_cast<uint4*>(ds_row + (((4 * cg + 2 * hc + c) ^ (krow & 7)) << 4)) =
-                make_uint4(dsk[4 * c], dsk[4 * c + 1], dsk[4 * c + 2], dsk[4 * c + 3]);
+            sts_u4(ds_row + (((4 * cg + 2 * hc + c) ^ swz) << 4), dsk[4 * c], dsk[4 * c + 1], dsk[4 * c + 2],
+                   dsk[4 * c + 3]);
         }
         tc_wait_st();
         fence_proxy_async_smem();
         tc_fence_before();
-        mbar_arrive(&sm.pds_full[g]);
+        mbar_arrive_a(b_pds);
 
         // ---- deferred drains (their MMAs were issued one pair / one item ago) ----
-        if (Pf > 0 && ((Pf - 1) & 1) == g) {
+        if (Pf > 0 && ((Pf - 1) & 1) == static_cast<uint32_t>(g)) {
           if (p > 0) drain_dq(Pf - 1, im, p - 1);
           else drain_dq(Pf - 1, prev, npairs - 1);
         }

@@ -32,7 +32,7 @@ namespace destr {
 
 // debug / tuning knobs (destr_debug_knob): 0 v_lbo 1 v_sbo 2 qk_lbo 3 qk_sbo 4 p_kstep_cols 5 v_kstep_bytes
 // 6-8 enc_attn_bwd descriptors, 9 enc fwd polynomial-exp quarter count (0..3), 10 enc bwd ditto
-int g_knobs[16] = {512, 512, 16, 512, 8, 1024, 16384, 1024, 2048, 1, 1, 0, 0, 0, 0, 0};
+int g_knobs[16] = {512, 512, 16, 512, 8, 1024, 16384, 1024, 2048, 1, 0, 0, 0, 0, 0, 0};
 
 namespace {
 

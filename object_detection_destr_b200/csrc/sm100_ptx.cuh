@@ -138,6 +138,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// shared-space accessors on 32-bit shared::cta addresses (a generic pointer into dynamic shared memory makes the
+// compiler emit generic LD/ST, which take the long-latency L1 path instead of LDS/STS)
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
 // Bounded wait: a broken pipeline traps (with a message) after ~4 s instead of hanging the GPU.
 #ifndef DESTR_WAIT_TIMEOUT_NS
 #define DESTR_WAIT_TIMEOUT_NS 4000000000ull
@@ -153,6 +178,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
       __trap();
     }
   }
+}
+
+static __device__ __noinline__ void mbar_wait_slow_a(uint32_t bar, uint32_t parity, int tag) {
+  const uint64_t t0 = globaltimer_ns();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_a(bar, parity)) {
+    if (((++spins) & 0x3ff) == 0 && globaltimer_ns() - t0 > DESTR_WAIT_TIMEOUT_NS) {
+      printf("destr_b200: mbarrier wait timeout tag=%d block=(%d,%d,%d) thread=%d parity=%u\n", tag,
+             blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+// wait on a 32-bit shared address; the (rare) spin path is an out-of-line call so hot loops stay compact
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity, int tag = 0) {
+  if (!mbar_try_wait_a(bar, parity)) mbar_wait_slow_a(bar, parity, tag);
 }
 
 // Same, for the single-thread producer / MMA-issuer roles: sleeps between polls so the spin loop does not
@@ -232,6 +273,13 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t 
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(swizzle & 7) << 61;
   return d;
+}
+
+// Address-independent part of a shared-memory matrix descriptor: desc = umma_desc_const(...) + (addr >> 4)
+// (valid while addr < 256 KiB, i.e. always for shared::cta addresses)
+__host__ __device__ constexpr uint64_t umma_desc_const(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t swizzle) {
+  return (static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16) | (static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32) |
+         (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(swizzle & 7) << 61);
 }
 
 // Instruction descriptor for kind::f16, BF16 x BF16 -> FP32.
