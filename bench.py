@@ -316,7 +316,14 @@ def run_ours(args):
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # NCCL kernels are captured inside the CUDA graphs: release the graphs first, and leave without the
+        # NCCL communicator teardown (destroy_process_group can block forever behind captured collectives).
+        eng.gA = eng.gB = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -104,13 +104,10 @@ class GraphedTrainStep:
                                  self.s_valid, self.C)
         loss = sum(self.lw[k] * losses[k] for k in self.lw)
         loss.backward()
-        if self.world > 1:
-            import torch.distributed as dist
-            grads = [p.grad for p in self.params if p.grad is not None]
-            flat = torch._utils._flatten_dense_tensors(grads)
-            dist.all_reduce(flat)
-            flat.div_(self.world)
-            torch._foreach_copy_(grads, list(torch._utils._unflatten_dense_tensors(flat, grads)))
+        if self.world > 1:  # the one exchange of the step: mean all-reduce of the gradients (NCCL over NVLink)
+            from .dataparallel import allreduce_mean_, grads_of
+            flat, loose = grads_of(self.model)
+            allreduce_mean_(flat, loose, world=self.world)
         self.opt.step()
         if hasattr(self.model, "after_optimizer_step"):
             self.model.after_optimizer_step()
