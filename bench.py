@@ -291,8 +291,13 @@ def run_ours(args):
         t_f, t_b = kernel_ms["destr_enc_attn_fwd"], kernel_ms["destr_enc_attn_bwd"]
         dom = "destr_enc_attn_bwd" if t_b >= t_f else "destr_enc_attn_fwd"
         ach = (bwd_flops / t_b if dom.endswith("bwd") else fwd_flops / t_f) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get(dom)
         roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": pk["tf_burst"], "unit": "TFLOP/s",
-                "frac": ach / pk["tf_burst"], "traffic": None,
+                "frac": ach / pk["tf_burst"], "traffic": traffic,
                 "peak_source": pk["src"] + " (burst bf16 GEMM; kernel timed alone with CUDA events, L2 flushed between launches)",
                 "launch_ms": t_b if dom.endswith("bwd") else t_f,
                 "also": {"destr_enc_attn_fwd": {"launch_ms": t_f, "achieved": fwd_flops / t_f / 1e9,
