@@ -203,6 +203,22 @@ int destr_match_cost_blockdiag(const float* logits, const float* boxes, const in
                                const float* tgt_boxes, const int32_t* tgt_offsets, float* cost, int B, int Q, int C,
                                float w_class, float w_bbox, float w_ciou, int with_l1, void* stream);
 
+/* ---------------- set-prediction loss (after matching) ---------------- */
+
+/* SetCriterion.forward after the matcher (criterion.py:29-79; sigmoid_focal_loss misc.py:99-128, L1Loss,
+ * CompleteIOULoss criterion.py:82-89 = mean of the FULL n x n complete_iou matrix), forward and backward fused:
+ *   logits fp32 [B,Q,C]; boxes fp32 [B,Q,4] cxcyhw; tgt_labels int64 [B,t_max] and tgt_boxes fp32 [B,t_max,4]
+ *   xyxy (per-image targets, padded); pred_idx / tgt_idx int64 [B,n] and valid uint8 [B,n]: the matching
+ *   (linear_sum_assignment rows / columns, padded slots have valid = 0).
+ *   losses fp32 [4] = {class, bbox, ciou, w_class*class + w_bbox*bbox + w_ciou*ciou};
+ *   dlogits fp32 [B,Q,C], dboxes fp32 [B,Q,4] = gradient of losses[3] (torch autograd conventions).
+ *   workspace: 3*B + 1 floats, zero-initialised ONCE by the caller (the kernel leaves it reusable). */
+int destr_set_loss_fwd_bwd(const float* logits, const float* boxes, const int64_t* tgt_labels,
+                           const float* tgt_boxes, const int64_t* pred_idx, const int64_t* tgt_idx,
+                           const uint8_t* valid, int B, int Q, int C, int t_max, int n, float w_class,
+                           float w_bbox, float w_ciou, float* losses, float* dlogits, float* dboxes,
+                           float* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

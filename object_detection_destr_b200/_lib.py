@@ -49,6 +49,7 @@ SIGNATURES = {
     "destr_pair_indices": [_p, _p, _i, _i, _p],
     "destr_box_refine": [_p, _p, _p, _i, _p],
     "destr_match_cost_blockdiag": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _f, _i, _p],
+    "destr_set_loss_fwd_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _f, _p, _p, _p, _p, _p],
 }
 
 for _name, _args in SIGNATURES.items():
@@ -57,6 +58,8 @@ for _name, _args in SIGNATURES.items():
     _fn.restype = _i
 lib.destr_split_cross_attn_ws_floats.argtypes = [_i, _i, _i]
 lib.destr_split_cross_attn_ws_floats.restype = _i64
+lib.destr_enc_attn_bwd_stats_floats.argtypes = [_i, _i, _i]
+lib.destr_enc_attn_bwd_stats_floats.restype = _i
 lib.destr_last_error.argtypes = []
 lib.destr_last_error.restype = C.c_char_p
 

@@ -58,7 +58,7 @@ class GraphedTrainStep:
 
     def __init__(self, model, optimizer, *, B: int, H: int, W: int, Q: int, num_classes: int, t_max: int = 40,
                  cost_class: float = 0.5, cost_ciou: float = 0.5, loss_weights: Optional[Dict[str, float]] = None,
-                 world: int = 1, device=None):
+                 world: int = 1, device=None, fused_loss: bool = True):
         self.model, self.opt = model, optimizer
         self.B, self.Q, self.C, self.t_max, self.world = B, Q, num_classes, t_max, world
         self.wc, self.wi = cost_class, cost_ciou
@@ -83,6 +83,9 @@ class GraphedTrainStep:
         self.h_tl = torch.empty(B, t_max, dtype=torch.int64, pin_memory=True)
         self.h_tb = torch.empty(B, t_max, 4, dtype=torch.float32, pin_memory=True)
         self.params = [p for p in model.parameters()]
+        self.fused_loss = fused_loss
+        self.loss_ws = ops.set_loss_workspace(B, dev)
+        self.losses = None
         self.gA: Optional[torch.cuda.CUDAGraph] = None
         self.gB: Optional[torch.cuda.CUDAGraph] = None
         self.loss = None
@@ -100,9 +103,14 @@ class GraphedTrainStep:
         return out
 
     def _backward(self, out):
-        losses = set_loss_static(out["pred_class"], out["pred_boxes"], self.s_tl, self.s_tb, self.s_pi, self.s_ti,
-                                 self.s_valid, self.C)
-        loss = sum(self.lw[k] * losses[k] for k in self.lw)
+        if self.fused_loss:  # one kernel: the three losses, their weighted total and its gradients
+            loss, self.losses = ops.set_loss(out["pred_class"], out["pred_boxes"], self.s_tl, self.s_tb, self.s_pi,
+                                             self.s_ti, self.s_valid, (self.lw["class"], self.lw["bbox"], self.lw["ciou"]),
+                                             self.loss_ws)
+        else:  # batched torch restatement (autograd): the cross-check of the fused kernel
+            losses = set_loss_static(out["pred_class"], out["pred_boxes"], self.s_tl, self.s_tb, self.s_pi, self.s_ti,
+                                     self.s_valid, self.C)
+            loss = sum(self.lw[k] * losses[k] for k in self.lw)
         loss.backward()
         if self.world > 1:  # the one exchange of the step: mean all-reduce of the gradients (NCCL over NVLink)
             from .dataparallel import allreduce_mean_, grads_of

@@ -197,7 +197,7 @@ def enc_attn_bwd(q: Tensor, k: Tensor, v: Tensor, mask_bits: Tensor, out: Tensor
     dout = _chk(dout.contiguous(), BF16, "dout")
     dqk = torch.empty(B * N, 2 * C, dtype=BF16, device=q.device)
     dv = torch.empty(B * N, C, dtype=BF16, device=q.device)
-    delta = torch.empty(B * heads * ((N + 127) // 128) * 256, dtype=torch.float32, device=q.device)  # stats workspace
+    delta = torch.empty(_lib.lib.destr_enc_attn_bwd_stats_floats(B, N, heads), dtype=torch.float32, device=q.device)  # stats workspace
     dq_acc = torch.empty(B * N, C, dtype=torch.float32, device=q.device)
     dq, dk = dqk[:, :C], dqk[:, C:]
     _lib.call("destr_enc_attn_bwd", q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), k.stride(0), v.stride(0),
@@ -382,3 +382,47 @@ def match_cost_blockdiag(logits: Tensor, boxes: Tensor, tgt_ids: Tensor, tgt_box
                   _chk(tgt_boxes, torch.float32, "tgt_boxes").data_ptr(), _chk(tgt_offsets, torch.int32, "tgt_offsets").data_ptr(),
                   out.data_ptr(), B, Q, Cn, float(w_class), float(w_bbox), float(w_ciou), int(with_l1), _stream())
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# fused set-prediction loss (forward + backward in one launch)
+# ----------------------------------------------------------------------------------------------
+class _SetLossFn(torch.autograd.Function):
+    """total = w_class*class + w_bbox*bbox + w_ciou*ciou with hand-written gradients (csrc/set_loss.cu)."""
+
+    @staticmethod
+    def forward(ctx, logits, boxes, tl, tb, pi, ti, valid, weights, ws):
+        B, Q, C = logits.shape
+        lg = _chk(logits.contiguous(), torch.float32, "logits")
+        bx = _chk(boxes.contiguous(), torch.float32, "boxes")
+        losses = torch.empty(4, dtype=torch.float32, device=lg.device)
+        dlg, dbx = torch.empty_like(lg), torch.empty_like(bx)
+        v8 = valid.contiguous().view(torch.uint8) if valid.dtype == torch.bool else valid.contiguous()
+        _lib.call("destr_set_loss_fwd_bwd", lg.data_ptr(), bx.data_ptr(), tl.data_ptr(), tb.data_ptr(), pi.data_ptr(),
+                  ti.data_ptr(), v8.data_ptr(), B, Q, C, tl.shape[1], pi.shape[1], float(weights[0]), float(weights[1]),
+                  float(weights[2]), losses.data_ptr(), dlg.data_ptr(), dbx.data_ptr(), ws.data_ptr(), _stream())
+        ctx.save_for_backward(dlg, dbx)
+        ctx.mark_non_differentiable(losses)
+        return losses[3].clone(), losses
+
+    @staticmethod
+    def backward(ctx, g_total, _g_losses):
+        dlg, dbx = ctx.saved_tensors
+        return dlg * g_total, dbx * g_total, None, None, None, None, None, None, None
+
+
+def set_loss_workspace(B: int, device) -> Tensor:
+    """Zero-initialised scratch of destr_set_loss_fwd_bwd (allocate once, reuse every step)."""
+    return torch.zeros(3 * B + 1, dtype=torch.float32, device=device)
+
+
+def set_loss(logits: Tensor, boxes: Tensor, tl: Tensor, tb: Tensor, pi: Tensor, ti: Tensor, valid: Tensor,
+             weights=(1.0, 1.0, 1.0), workspace: Optional[Tensor] = None):
+    """logits (B,Q,C) fp32, boxes (B,Q,4) cxcyhw fp32; tl (B,Tm) int64 / tb (B,Tm,4) padded targets (xyxy);
+    pi, ti (B,n) int64 matched query / target index, valid (B,n) bool.
+    Returns (total, losses[4] = class, bbox, ciou, total); `total` is differentiable w.r.t. logits and boxes."""
+    for t, n_ in ((tl, "tl"), (pi, "pi"), (ti, "ti")):
+        _chk(t, torch.int64, n_)
+    tb = _chk(tb.contiguous(), torch.float32, "tb")
+    ws = workspace if workspace is not None else set_loss_workspace(logits.shape[0], logits.device)
+    return _SetLossFn.apply(logits, boxes, tl.contiguous(), tb, pi.contiguous(), ti.contiguous(), valid, weights, ws)

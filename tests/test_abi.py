@@ -38,7 +38,8 @@ def test_ctypes_table_matches_header_arity():
     for name, argtypes in _lib.SIGNATURES.items():
         assert name in funcs, f"{name} bound in _lib.py but not declared in destr_b200.h"
         assert len(argtypes) == len(funcs[name]), f"{name}: {len(argtypes)} ctypes args vs {len(funcs[name])} in header"
-    bound = set(_lib.SIGNATURES) | {"destr_last_error", "destr_split_cross_attn_ws_floats"}
+    bound = set(_lib.SIGNATURES) | {"destr_last_error", "destr_split_cross_attn_ws_floats",
+                                       "destr_enc_attn_bwd_stats_floats"}
     assert set(funcs) <= bound, f"declared but not bound: {set(funcs) - bound}"
 
 
