@@ -216,8 +216,7 @@ def run_ours(args):
     model = TransformerHalf(Namespace(hidden_dim=256, num_encoder_blocks=cfg["L"], num_decoder_blocks=cfg["L"],
                                       num_cls=cfg["C"]))
     disable_dropout(model).to(dev).train()
-    params = [p for p in model.parameters()]
-    opt = torch.optim.AdamW(params, lr=1e-5, fused=True, capturable=not args.eager)
+    opt = model.make_optimizer(lr=1e-5)  # AdamW: flat kernel over the runtime's parameter buffer + heads
     weights = {"class": 0.5, "bbox": 0.0, "ciou": 0.5}  # arg_parser.py:41-61 defaults
 
     n_batches = 4

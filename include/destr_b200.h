@@ -219,6 +219,15 @@ int destr_set_loss_fwd_bwd(const float* logits, const float* boxes, const int64_
                            float w_bbox, float w_ciou, float* losses, float* dlogits, float* dboxes,
                            float* workspace, void* stream);
 
+/* ---------------- optimizer step on the flat parameter buffer ---------------- */
+
+/* torch.optim.AdamW arithmetic (decoupled weight decay, bias correction; amsgrad off) on flat fp32 buffers of
+ * n elements (n % 4 == 0, 16-byte aligned), plus the refresh of the bf16 weight shadow the GEMMs read.
+ * `step` points to a device float holding the 1-based step count of THIS update. */
+int destr_flat_adamw(float* master, const float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16,
+                     int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, const float* step,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -158,7 +158,7 @@ __device__ float block_sum(float v, float* red) {  // blockDim.x <= 1024, result
 
 constexpr int kMaxQ = 1024;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 set_loss_kernel(const float* __restrict__ logits, const float* __restrict__ boxes, const int64_t* __restrict__ tl,
                 const float* __restrict__ tb, const int64_t* __restrict__ pi, const int64_t* __restrict__ ti,
                 const uint8_t* __restrict__ valid, int B, int Q, int C, int Tm, int n, float w_class, float w_bbox,
@@ -217,30 +217,40 @@ set_loss_kernel(const float* __restrict__ logits, const float* __restrict__ boxe
   if (cnt > 0) {
     const float denom = static_cast<float>(s_images_with_targets);
     const float g_l1 = w_bbox / (4.f * cnt * denom), g_ci = w_ciou / (static_cast<float>(cnt) * cnt * denom);
-    for (int k = tid; k < n; k += blockDim.x) {
-      if (!valid[b * n + k]) continue;
+    // one warp per matched prediction i, lanes over its targets j (long dependent dual-number chains: spreading
+    // the cnt x cnt pairs over the block is what makes this kernel short); fixed-order shuffle reductions
+    const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    for (int k = warp; k < n; k += nwarps) {
+      if (!valid[b * n + k]) continue;  // warp-uniform
       const int q = static_cast<int>(pi[b * n + k]);
       const float* pb = boxes + (static_cast<size_t>(b) * Q + q) * 4;
       const PredBox p = make_pred(pb);
       float grad[4] = {0.f, 0.f, 0.f, 0.f};
-      {  // L1 against its own target
+      float ci = 0.f;
+      for (int j = lane; j < n; j += 32) {  // CIoU against EVERY matched target of the image (criterion.py:87-89)
+        if (!valid[b * n + j]) continue;
+        const Dual c = ciou_cost(p, tb + (static_cast<size_t>(b) * Tm + ti[b * n + j]) * 4);
+        ci += c.v;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) grad[i] += g_ci * c.d[i];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ci += __shfl_xor_sync(0xffffffffu, ci, o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) grad[i] += __shfl_xor_sync(0xffffffffu, grad[i], o);
+      }
+      if (lane == 0) {
+        acc_ci += ci;
+        // L1 against its own target
         const float* g = tb + (static_cast<size_t>(b) * Tm + ti[b * n + k]) * 4;
         const Dual e = dabs(p.x0 - dconst(g[0])) + dabs(p.y0 - dconst(g[1])) + dabs(p.x1 - dconst(g[2])) +
                        dabs(p.y1 - dconst(g[3]));
         acc_l1 += e.v;
+        float* db = dboxes + (static_cast<size_t>(b) * Q + q) * 4;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) grad[i] += g_l1 * e.d[i];
+        for (int i = 0; i < 4; ++i) db[i] = grad[i] + g_l1 * e.d[i];
       }
-      for (int j = 0; j < n; ++j) {  // CIoU against EVERY matched target of the image (criterion.py:87-89)
-        if (!valid[b * n + j]) continue;
-        const Dual c = ciou_cost(p, tb + (static_cast<size_t>(b) * Tm + ti[b * n + j]) * 4);
-        acc_ci += c.v;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) grad[i] += g_ci * c.d[i];
-      }
-      float* db = dboxes + (static_cast<size_t>(b) * Q + q) * 4;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) db[i] = grad[i];
     }
   }
   const float l1_img = block_sum(acc_l1, red), ci_img = block_sum(acc_ci, red);
@@ -283,7 +293,7 @@ extern "C" int destr_set_loss_fwd_bwd(const float* logits, const float* boxes, c
   DESTR_CHECK_ARG(B > 0 && Q > 0 && Q <= kMaxQ && C > 0 && t_max > 0 && n > 0, "shape (Q <= 1024)");
   float* partial = workspace;
   unsigned int* counter = reinterpret_cast<unsigned int*>(workspace + 3 * B);
-  set_loss_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, boxes, tgt_labels, tgt_boxes, pred_idx,
+  set_loss_kernel<<<B, 512, 0, static_cast<cudaStream_t>(stream)>>>(logits, boxes, tgt_labels, tgt_boxes, pred_idx,
                                                                     tgt_idx, valid, B, Q, C, t_max, n, w_class,
                                                                     w_bbox, w_ciou, losses, dlogits, dboxes, partial,
                                                                     counter);

@@ -117,7 +117,7 @@ class GraphedTrainStep:
             flat, loose = grads_of(self.model)
             allreduce_mean_(flat, loose, world=self.world)
         self.opt.step()
-        if hasattr(self.model, "after_optimizer_step"):
+        if hasattr(self.model, "after_optimizer_step") and not getattr(self.opt, "refreshes_shadows", False):
             self.model.after_optimizer_step()
         return loss
 

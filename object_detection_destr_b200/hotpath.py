@@ -51,6 +51,19 @@ class TransformerHalf(nn.Module):
             self._rt = HotPathRuntime(self._encoder, self._decoder, self._bbox_embed, self._cls_embed.weight.device)
         return self._rt
 
+    def make_optimizer(self, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2):
+        """AdamW for this module (call after .to(device)).  With the hand-scheduled runtime: one flat kernel for
+        every encoder/decoder parameter (+ bf16 shadow refresh) and a fused torch AdamW for the heads; otherwise a
+        plain fused torch.optim.AdamW.  Same arithmetic either way (tests/test_gpu_engine.py)."""
+        if not self.use_runtime:
+            return torch.optim.AdamW(self.parameters(), lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
+                                     fused=True, capturable=True)
+        from .runtime import FlatAdamW
+        P = self.runtime().P
+        lo, hi = P.m32.data_ptr(), P.m32.data_ptr() + P.m32.numel() * 4
+        extra = [p for p in self.parameters() if not (lo <= p.data_ptr() < hi)]
+        return FlatAdamW(P, extra, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+
     def after_optimizer_step(self):
         """Refresh the bf16 weight shadows (call after every optimizer step when runtime=True)."""
         if self._rt is not None:

@@ -339,7 +339,9 @@ def dec_qkv_prep_bwd(d_qkv: Tensor, d_cat: Tensor, pairs: Tensor, B: int, Q: int
 
 
 def split_cross_attn_bwd(q_obj: Tensor, q_pos: Tensor, k_enc: Tensor, k_pos: Tensor, v: Tensor, mask_bits: Tensor,
-                         out: Tensor, dout: Tensor, lse: Tensor, B: int, Q: int, N: int):
+                         out: Tensor, dout: Tensor, lse: Tensor, B: int, Q: int, N: int,
+                         dke_out: Optional[Tensor] = None, dkp_out: Optional[Tensor] = None,
+                         dv_out: Optional[Tensor] = None):
     """Backward of split_cross_attn_fwd: the tcgen05 kernel recomputes S, dP and does the softmax backward
     (P, dS, dS_cls+dS_reg in bf16); five cuBLAS batched GEMMs on plain views finish the contractions.
     -> (dq_obj [B*Q,512], dq_pos [B*Q,256], dk_enc, dk_pos, dv [B*N,256]) bf16."""
@@ -357,9 +359,16 @@ def split_cross_attn_bwd(q_obj: Tensor, q_pos: Tensor, k_enc: Tensor, k_pos: Ten
     Pv, dSv, dSs = P_all[:, :, :N], dS_all[:, :, :N], dS_sum[:, :, :N]
     v3 = lambda t: t.as_strided((B, N, 256), (N * t.stride(0), t.stride(0), 1))  # [B*N,256] view -> [B,N,256]
     do_v, qo_v, qp_v = dout.view(B, 2 * Q, 256), q_obj.view(B, 2 * Q, 256), q_pos.view(B, Q, 256)
-    dv = torch.bmm(Pv.transpose(1, 2), do_v).view(B * N, 256)
-    dke = torch.bmm(dSv.transpose(1, 2), qo_v).view(B * N, 256)
-    dkp = torch.bmm(dSs.transpose(1, 2), qp_v).view(B * N, 256)
+    # the key-side gradients may land directly in column slices of a wider buffer ([B*N,256] views with any row
+    # pitch): cuBLAS writes them with ldc = pitch, no copy
+    def _into(a, b, dst):
+        if dst is None:
+            return torch.bmm(a, b).view(B * N, 256)
+        torch.bmm(a, b, out=v3(dst))
+        return dst
+    dv = _into(Pv.transpose(1, 2), do_v, dv_out)
+    dke = _into(dSv.transpose(1, 2), qo_v, dke_out)
+    dkp = _into(dSs.transpose(1, 2), qp_v, dkp_out)
     dqo = torch.bmm(dSv, v3(k_enc)).view(B * Q, 512)
     dqp = torch.bmm(dSs, v3(k_pos)).view(B * Q, 256)
     return dqo, dqp, dke, dkp, dv

@@ -167,6 +167,40 @@ class FlatParams:
             self._written.add(key)
 
 
+class FlatAdamW:
+    """torch.optim.AdamW semantics on the runtime's flat parameter buffer: one kernel per step updates every
+    encoder/decoder parameter and refreshes the bf16 shadows (csrc/optim.cu).  `extra` parameters (the class /
+    box heads, which live outside the flat buffer) go through a regular fused torch AdamW with the same
+    hyper-parameters.  CUDA-graph capturable (the step count lives on the device)."""
+
+    refreshes_shadows = True  # engine: no separate master -> bf16 shadow cast after step()
+
+    def __init__(self, P: "FlatParams", extra=(), lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 1e-2):
+        self.P, self.lr, self.betas, self.eps, self.wd = P, lr, betas, eps, weight_decay
+        self.exp_avg = torch.zeros_like(P.m32)
+        self.exp_avg_sq = torch.zeros_like(P.m32)
+        self.t = torch.zeros(1, dtype=torch.float32, device=P.m32.device)
+        extra = [p for p in extra if p.requires_grad]
+        self.extra = torch.optim.AdamW(extra, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, fused=True,
+                                       capturable=True) if extra else None
+
+    def zero_grad(self, set_to_none: bool = False):
+        if self.extra is not None:
+            self.extra.zero_grad(set_to_none=set_to_none)
+
+    def step(self):
+        P = self.P
+        self.t.add_(1.0)
+        n = (P.n + 3) // 4 * 4
+        from . import _lib
+        _lib.call("destr_flat_adamw", P.m32.data_ptr(), P.g32.data_ptr(), self.exp_avg.data_ptr(),
+                  self.exp_avg_sq.data_ptr(), P.s16.data_ptr(), n, float(self.lr), float(self.betas[0]),
+                  float(self.betas[1]), float(self.eps), float(self.wd), self.t.data_ptr(), ops._stream())
+        if self.extra is not None:
+            self.extra.step()
+
+
 class HotPathRuntime:
     """forward()/backward() of encoder -> fine_pos -> decoder on token-major bf16 activations."""
 
@@ -293,10 +327,9 @@ class HotPathRuntime:
                                   dbeta=P.g(pf + "n1_b"), dx_out=dca[:, sl])
         ke, vv = kv_all[:, l * 512:l * 512 + 256], kv_all[:, l * 512 + 256:(l + 1) * 512]
         kp = kpos_all[:, l * 256:(l + 1) * 256]
-        dqo, dqp, dke, dkp, dvv = ops.split_cross_attn_bwd(qo, qp, ke, kp, vv, bits, ca, dca, lse_c, B, Q, N)
-        d_kv_all[:, l * 512:l * 512 + 256].copy_(dke)
-        d_kv_all[:, l * 512 + 256:(l + 1) * 512].copy_(dvv)
-        d_kpos_all[:, l * 256:(l + 1) * 256].copy_(dkp)
+        dqo, dqp, _, _, _ = ops.split_cross_attn_bwd(
+            qo, qp, ke, kp, vv, bits, ca, dca, lse_c, B, Q, N, dke_out=d_kv_all[:, l * 512:l * 512 + 256],
+            dkp_out=d_kpos_all[:, l * 256:(l + 1) * 256], dv_out=d_kv_all[:, l * 512 + 256:(l + 1) * 512])
         P.acc_gw(f"d{l}.cq_w", dqo, o)
         do = torch.addmm(dca, dqo, P.w(f"d{l}.cq_w"))   # d(o) = d(o_cls|o_reg residual) + dq_obj W
         P.acc_gw(f"d{l}.cqp_w", dqp, sin)
