@@ -203,6 +203,15 @@ int destr_match_cost_blockdiag(const float* logits, const float* boxes, const in
                                const float* tgt_boxes, const int32_t* tgt_offsets, float* cost, int B, int Q, int C,
                                float w_class, float w_bbox, float w_ciou, int with_l1, void* stream);
 
+/* Per-image linear sum assignment on the block-diagonal cost buffer of destr_match_cost_blockdiag, bit-identical
+ * to scipy.optimize.linear_sum_assignment (matcher.py:109-112, 186-189), one warp per image.
+ *   cost / tgt_offsets: as above; max_targets >= max_b T_b.
+ *   pred_idx, tgt_idx int64 [B, n_slots], valid uint8 [B, n_slots], n_slots >= min(Q, max_targets): image b's
+ *   min(Q,T_b) pairs in ascending query order (scipy's row order), padded slots = (Q, 0, 0).
+ *   status int32 [B]: 0 ok, 1 = NaN/-inf in the block (scipy raises ValueError), 2 = infeasible. */
+int destr_lsap_blockdiag(const float* cost, const int32_t* tgt_offsets, int B, int Q, int max_targets, int n_slots,
+                         int64_t* pred_idx, int64_t* tgt_idx, uint8_t* valid, int32_t* status, void* stream);
+
 /* ---------------- set-prediction loss (after matching) ---------------- */
 
 /* SetCriterion.forward after the matcher (criterion.py:29-79; sigmoid_focal_loss misc.py:99-128, L1Loss,

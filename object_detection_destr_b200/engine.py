@@ -1,15 +1,18 @@
-"""CUDA-graph training / inference steps for the hot path.
+"""CUDA-graph training step for the hot path.
 
-The eager step issues ~2000 small launches and is CPU-bound; the engine captures it into two CUDA
-graphs around the one unavoidable host round trip (the reference's `C.cpu()` + scipy
-linear_sum_assignment, matcher.py:107-112):
+The eager step issues ~1000 small launches and is CPU-bound; the engine captures the WHOLE step into one CUDA
+graph:
 
-    graph A : forward (encoder, decoder, heads) -> block-diagonal cost kernel -> D2H into pinned memory
-    host    : stream sync, linear_sum_assignment per image, indices -> pinned -> H2D
-    graph B : set loss -> backward -> [NCCL gradient all-reduce] -> fused AdamW
+    forward (encoder, decoder, heads) -> block-diagonal cost kernel -> per-image assignment ON THE DEVICE
+    (ops.lsap_blockdiag, bit-identical to scipy) -> fused set loss (+ its gradients) -> backward ->
+    [NCCL gradient all-reduce] -> flat AdamW
 
-All shapes are static: targets are padded to `t_max` per image (the cost kernel and the loss read the
-true counts from device tensors), so one capture serves every batch.
+so a step is one graph replay with no host round trip.  `gpu_lsa=False` keeps the reference's own arrangement
+(`C.cpu()` + scipy linear_sum_assignment, matcher.py:107-112) as two graphs around a host assignment; the two
+modes are compared in tests/test_gpu_engine.py.
+
+All shapes are static: targets are padded to `t_max` per image (the cost kernel, the assignment and the loss
+read the true counts from device tensors), so one capture serves every batch.
 """
 from __future__ import annotations
 
@@ -58,7 +61,7 @@ class GraphedTrainStep:
 
     def __init__(self, model, optimizer, *, B: int, H: int, W: int, Q: int, num_classes: int, t_max: int = 40,
                  cost_class: float = 0.5, cost_ciou: float = 0.5, loss_weights: Optional[Dict[str, float]] = None,
-                 world: int = 1, device=None, fused_loss: bool = True):
+                 world: int = 1, device=None, fused_loss: bool = True, gpu_lsa: bool = True):
         self.model, self.opt = model, optimizer
         self.B, self.Q, self.C, self.t_max, self.world = B, Q, num_classes, t_max, world
         self.wc, self.wi = cost_class, cost_ciou
@@ -84,6 +87,8 @@ class GraphedTrainStep:
         self.h_tb = torch.empty(B, t_max, 4, dtype=torch.float32, pin_memory=True)
         self.params = [p for p in model.parameters()]
         self.fused_loss = fused_loss
+        self.gpu_lsa = gpu_lsa
+        self.s_status = z(B, dt=torch.int32)
         self.loss_ws = ops.set_loss_workspace(B, dev)
         self.losses = None
         self.gA: Optional[torch.cuda.CUDAGraph] = None
@@ -99,7 +104,11 @@ class GraphedTrainStep:
         with torch.no_grad():
             ops.match_cost_blockdiag(out["pred_class"].detach(), out["pred_boxes"].detach(), self.s_ids, self.s_tboxes,
                                      self.s_offs, self.B * self.t_max, self.wc, 0.0, self.wi, False, out=self.s_cost)
-            self.h_cost.copy_(self.s_cost, non_blocking=True)
+            if self.gpu_lsa:
+                ops.lsap_blockdiag(self.s_cost, self.s_offs, self.B, self.Q, self.t_max, self.n,
+                                   out=(self.s_pi, self.s_ti, self.s_valid, self.s_status))
+            else:
+                self.h_cost.copy_(self.s_cost, non_blocking=True)
         return out
 
     def _backward(self, out):
@@ -173,13 +182,14 @@ class GraphedTrainStep:
 
     def eager_step(self):
         out = self._forward()
-        torch.cuda.current_stream().synchronize()
-        self._assign()
+        if not self.gpu_lsa:
+            torch.cuda.current_stream().synchronize()
+            self._assign()
         self.opt.zero_grad(set_to_none=False)  # keep the (possibly graph-static) .grad tensors in place
         return self._backward(out)
 
     def capture(self, warmup: int = 3):
-        """Warm up eagerly on a side stream (PyTorch's capture protocol), then capture graphs A and B."""
+        """Warm up eagerly on a side stream (PyTorch's capture protocol), then capture the step."""
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -191,20 +201,33 @@ class GraphedTrainStep:
         from . import _lib
         n0 = _lib.launch_count
         self.gA = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.gA):
-            self.out = self._forward()
+        if self.gpu_lsa:  # one graph: forward, cost, assignment, loss, backward, optimizer
+            with torch.cuda.graph(self.gA):
+                self.out = self._forward()
+                self.loss = self._backward(self.out)
+            self.gB = None
+        else:
+            with torch.cuda.graph(self.gA):
+                self.out = self._forward()
+            torch.cuda.synchronize()
+            self._assign()
+            self.gB = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.gB, pool=self.gA.pool()):
+                self.loss = self._backward(self.out)
         torch.cuda.synchronize()
-        self._assign()
-        self.gB = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.gB, pool=self.gA.pool()):
-            self.loss = self._backward(self.out)
-        torch.cuda.synchronize()
-        self.launches_per_step = _lib.launch_count - n0  # our kernels captured in graphs A + B
+        self.launches_per_step = _lib.launch_count - n0  # our kernels captured in the graph(s)
 
     def step(self):
-        """Replay: graph A, host assignment, graph B.  Returns the (device) loss tensor."""
+        """Replay one training step.  Returns the (device) loss tensor."""
         self.gA.replay()
-        torch.cuda.current_stream().synchronize()
-        self._assign()
-        self.gB.replay()
+        if self.gB is not None:
+            torch.cuda.current_stream().synchronize()
+            self._assign()
+            self.gB.replay()
         return self.loss
+
+    def raise_if_invalid(self):
+        """scipy raises on NaN / -inf costs (identical boxes make the CIoU cost NaN); the device
+        assignment records it per image instead.  Synchronises."""
+        if self.gpu_lsa and int(self.s_status.max()) != 0:
+            raise ValueError("matrix contains invalid numeric entries")

@@ -3,9 +3,10 @@
 
 The cost matrix is one fp32 CUDA kernel that computes ONLY the per-image diagonal blocks the
 assignment consumes (the reference builds the full cross-batch (B*Q) x sum(T) matrix and throws all
-off-diagonal blocks away, matcher.py:102-112).  The assignment itself stays scipy's
-linear_sum_assignment on the host, exactly as in the reference (bit-exact indices are required);
-only the block-diagonal costs cross PCIe, through a pinned buffer.
+off-diagonal blocks away, matcher.py:102-112).  The assignment runs on the device too
+(`ops.lsap_blockdiag`: scipy's shortest-augmenting-path algorithm, one warp per image, bit-identical
+assignments -- tests/test_gpu_lsap.py); only the few hundred resulting indices cross PCIe, because the
+reference contract returns CPU tensors.  `assign_on_host=True` keeps scipy on the host as the cross-check.
 """
 from __future__ import annotations
 
@@ -22,6 +23,7 @@ from . import ops
 
 class _MatcherBase(nn.Module):
     with_l1 = True
+    assign_on_host = False  # True: scipy.optimize.linear_sum_assignment on the host (the reference's own path)
 
     def __init__(self):
         super().__init__()
@@ -58,12 +60,23 @@ class _MatcherBase(nn.Module):
         """Same contract as the reference (matcher.py:54-119): list over the batch of
         (index_i, index_j) CPU int64 tensors, len = min(Q, T_b), rows ascending."""
         cost, sizes, Q = self.cost_blocks(outputs, targets)
+        if not self.assign_on_host:
+            B = len(sizes)
+            if sum(sizes) == 0:
+                e = torch.zeros(0, dtype=torch.int64)
+                return [(e, e.clone()) for _ in sizes]
+            offs = torch.tensor(np.concatenate([[0], np.cumsum(sizes)]), dtype=torch.int32).to(cost.device)
+            pi, ti, valid, status = ops.lsap_blockdiag(cost, offs, B, Q, max(sizes))
+            pi, ti, status = pi.cpu(), ti.cpu(), status.cpu()  # the one D2H sync of the matcher (matcher.py:107)
+            if int(status.max()) != 0:  # scipy raises on NaN / -inf costs (identical boxes, SURVEY 8a12)
+                raise ValueError("matrix contains invalid numeric entries")
+            return [(pi[b, :min(Q, t)].clone(), ti[b, :min(Q, t)].clone()) for b, t in enumerate(sizes)]
         n = Q * sum(sizes)
         if self._pinned is None or self._pinned.numel() < max(n, 1):
             self._pinned = torch.empty(max(n, 1), dtype=torch.float32, pin_memory=True)
         host = self._pinned[:max(n, 1)]
         host.copy_(cost[:max(n, 1)], non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the one D2H sync of the matcher (matcher.py:107)
+        torch.cuda.current_stream().synchronize()
         c = host.numpy()
         out, off = [], 0
         for t in sizes:

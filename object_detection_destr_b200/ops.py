@@ -393,6 +393,24 @@ def match_cost_blockdiag(logits: Tensor, boxes: Tensor, tgt_ids: Tensor, tgt_box
     return out
 
 
+def lsap_blockdiag(cost: Tensor, tgt_offsets: Tensor, B: int, Q: int, max_targets: int, n_slots: Optional[int] = None,
+                   out=None):
+    """Hungarian matching of every image on the device (bit-identical to scipy.optimize.linear_sum_assignment).
+    cost: flat fp32 buffer of match_cost_blockdiag; tgt_offsets int32 [B+1].
+    Returns (pred_idx int64 [B,n], tgt_idx int64 [B,n], valid bool [B,n], status int32 [B]); padded slots are
+    (Q, 0, False); status != 0 marks an image whose block holds NaN/-inf (scipy would raise)."""
+    n = n_slots if n_slots is not None else min(Q, max_targets)
+    dev = cost.device
+    if out is None:
+        out = (torch.empty(B, n, dtype=torch.int64, device=dev), torch.empty(B, n, dtype=torch.int64, device=dev),
+               torch.empty(B, n, dtype=torch.bool, device=dev), torch.empty(B, dtype=torch.int32, device=dev))
+    pi, ti, valid, status = out
+    _lib.call("destr_lsap_blockdiag", _chk(cost, torch.float32, "cost").data_ptr(),
+              _chk(tgt_offsets, torch.int32, "tgt_offsets").data_ptr(), B, Q, max_targets, n, pi.data_ptr(), ti.data_ptr(),
+              valid.data_ptr(), status.data_ptr(), _stream())
+    return pi, ti, valid, status
+
+
 # ----------------------------------------------------------------------------------------------
 # fused set-prediction loss (forward + backward in one launch)
 # ----------------------------------------------------------------------------------------------

@@ -7,7 +7,8 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def test_graphed_step_matches_eager():
+@pytest.mark.parametrize("gpu_lsa", [True, False])
+def test_graphed_step_matches_eager(gpu_lsa):
     import bench
     from object_detection_destr_b200.encoder import disable_dropout
     from object_detection_destr_b200.engine import GraphedTrainStep
@@ -17,7 +18,7 @@ def test_graphed_step_matches_eager():
     model = TransformerHalf(Namespace(hidden_dim=256, num_encoder_blocks=2, num_decoder_blocks=2, num_cls=cfg["C"]))
     disable_dropout(model).cuda().train()
     opt = torch.optim.AdamW(model.parameters(), lr=0.0, fused=True, capturable=True)
-    eng = GraphedTrainStep(model, opt, B=2, H=10, W=14, Q=60, num_classes=cfg["C"], t_max=40)
+    eng = GraphedTrainStep(model, opt, B=2, H=10, W=14, Q=60, num_classes=cfg["C"], t_max=40, gpu_lsa=gpu_lsa)
     batches = [bench.make_batch(0, s, 2, cfg, padded=True) for s in range(3)]
     eng.load_batch(*batches[0])
     eng.capture(warmup=2)
@@ -54,3 +55,28 @@ def test_flat_adamw_matches_torch_adamw():
         assert torch.allclose(p, rp, rtol=2e-6, atol=2e-7), float((p - rp).abs().max())
     for name in ("e0.fc1_w", "d0.q_w"):  # bf16 shadows follow the masters
         assert torch.equal(P.w(name), P.f(name).to(torch.bfloat16))
+
+
+def test_device_assignment_step_equals_host_assignment_step():
+    """Same weights, same batch: the single-graph step (device LSAP + fused loss) and the reference arrangement
+    (host scipy + autograd loss) produce the same loss and gradients."""
+    import bench
+    from object_detection_destr_b200.encoder import disable_dropout
+    from object_detection_destr_b200.engine import GraphedTrainStep
+    from object_detection_destr_b200.hotpath import TransformerHalf
+    cfg = dict(bench.CFG, B=3, L=1, H=10, W=14, Q=60)
+    res = []
+    for gpu_lsa, fused in ((True, True), (False, False)):
+        torch.manual_seed(0)
+        model = TransformerHalf(Namespace(hidden_dim=256, num_encoder_blocks=1, num_decoder_blocks=1, num_cls=cfg["C"]))
+        disable_dropout(model).cuda().train()
+        opt = torch.optim.AdamW(model.parameters(), lr=0.0, fused=True, capturable=True)
+        eng = GraphedTrainStep(model, opt, B=3, H=10, W=14, Q=60, num_classes=cfg["C"], t_max=40, gpu_lsa=gpu_lsa,
+                               fused_loss=fused)
+        eng.load_batch(*bench.make_batch(0, 5, 3, cfg, padded=True))
+        loss = float(eng.eager_step())
+        eng.raise_if_invalid()
+        res.append((loss, model._decoder._decoder[0]._sa_proj_to_q_obj.weight.grad.clone(), eng.s_pi.clone(), eng.s_ti.clone()))
+    assert torch.equal(res[0][2], res[1][2]) and torch.equal(res[0][3], res[1][3])  # identical assignments
+    assert abs(res[0][0] - res[1][0]) <= 2e-5 * max(1.0, abs(res[1][0]))
+    assert torch.allclose(res[0][1], res[1][1], rtol=2e-2, atol=1e-6)
