@@ -19,6 +19,7 @@ src/model/blocks/decoder_block.py:28-67,157-220,238-260.
 """
 from __future__ import annotations
 
+import contextlib
 import math
 from typing import Dict, List, Optional, Tuple
 
@@ -120,6 +121,12 @@ class FlatParams:
                 self._gviews.append(t.grad)
         self.refresh()
         self._written = set()
+        # weight-gradient GEMMs are off the critical path of backward (nothing downstream reads them before the
+        # optimizer): they go to a side stream and overlap the dX chain; inside a CUDA-graph capture this becomes a
+        # parallel branch of the graph.  Their operands are kept alive until the streams join (end_backward).
+        self.side = torch.cuda.Stream(device=device) if torch.device(device).type == "cuda" else None
+        self.side2 = torch.cuda.Stream(device=device) if self.side is not None else None  # parallel decoder branches
+        self._keep: List[Tensor] = []
 
     def _v(self, buf: Tensor, name: str, rows: Optional[int] = None) -> Tensor:
         off, shape = self.off[name]
@@ -148,10 +155,37 @@ class FlatParams:
         self._written.clear()
 
     def end_backward(self):
+        if self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
+            self._keep.clear()
         self.g32[:self.nW].copy_(self.g16)
         for t, gv in zip(self.params, self._gviews):  # zero_grad(set_to_none=True) may have detached them
             if t.grad is not gv:
                 t.grad = gv
+
+    @contextlib.contextmanager
+    def fork(self, enable: bool = True):
+        """`with P.fork():` runs the body on the second side stream, concurrently with what the caller enqueues next
+        on its own stream; the caller joins with P.join().  (Graph capture turns this into a parallel branch.)"""
+        if self.side2 is None or not enable:
+            yield
+            return
+        self.side2.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.side2):
+            yield
+
+    def join(self):
+        if self.side2 is not None:
+            torch.cuda.current_stream().wait_stream(self.side2)
+
+    def off_path(self, fn, *operands: Tensor):
+        """Run `fn()` (work nothing downstream waits for, e.g. a bias-gradient column sum) on the side stream."""
+        if self.side is None:
+            return fn()
+        self.side.wait_stream(torch.cuda.current_stream())
+        self._keep += list(operands)
+        with torch.cuda.stream(self.side):
+            return fn()
 
     def acc_gw(self, name: str, dy: Tensor, x: Tensor, rows: Optional[int] = None, sl: Optional[slice] = None):
         """weight gradient dW (+)= dy^T x into the bf16 gradient buffer (first write overwrites)."""
@@ -160,11 +194,18 @@ class FlatParams:
         if sl is not None:
             gv = gv[sl]
             key = (name, sl.start)
-        if key in self._written:
-            gv.addmm_(dy.t(), x)
+        if self.side is not None:
+            self.side.wait_stream(torch.cuda.current_stream())
+            self._keep += [dy, x]
+            ctx = torch.cuda.stream(self.side)
         else:
-            torch.mm(dy.t(), x, out=gv)
-            self._written.add(key)
+            ctx = contextlib.nullcontext()
+        with ctx:
+            if key in self._written:
+                gv.addmm_(dy.t(), x)
+            else:
+                torch.mm(dy.t(), x, out=gv)
+                self._written.add(key)
 
 
 class FlatAdamW:
@@ -249,8 +290,7 @@ class HotPathRuntime:
         da = torch.mm(d1, P.w(f"e{l}.out_w"))
         dqk, dv = ops.enc_attn_bwd(qk[:, :256], qk[:, 256:], v, bits, a, da, lse, B, N, 8, 1.0 / math.sqrt(32))
         gb = P.g(f"e{l}.in_b")
-        ops.relu_bwd_colsum(dqk, None, gb[:512])
-        ops.relu_bwd_colsum(dv, None, gb[512:])
+        P.off_path(lambda: (ops.relu_bwd_colsum(dqk, None, gb[:512]), ops.relu_bwd_colsum(dv, None, gb[512:])), dqk, dv)
         Win = P.w(f"e{l}.in_w")
         P.acc_gw(f"e{l}.in_w", dqk, xq, sl=slice(0, 512))
         P.acc_gw(f"e{l}.in_w", dv, x, sl=slice(512, 768))
@@ -262,7 +302,7 @@ class HotPathRuntime:
     def _pos_scale_bwd(self, pfx: str, ds: Tensor, h1: Tensor, xin: Tensor, dx_acc: Tensor) -> Tensor:
         """backward of s = W2 relu(W0 xin + b0) + b2 (shared MLP): accumulates weight grads, dx_acc += ..."""
         P = self.P
-        ops.relu_bwd_colsum(ds, None, P.g(pfx + ".ps2_b"))
+        P.off_path(lambda: ops.relu_bwd_colsum(ds, None, P.g(pfx + ".ps2_b")), ds)
         P.acc_gw(pfx + ".ps2_w", ds, h1)
         dh = torch.mm(ds, P.w(pfx + ".ps2_w"))
         dpre = ops.relu_bwd_colsum(dh, h1, P.g(pfx + ".ps0_b"))
@@ -293,15 +333,18 @@ class HotPathRuntime:
         ca, lse_c = ops.split_cross_attn_fwd(qo, qp, ke, kp, vv, bits, B, Q, N)
         y = torch.empty_like(x)
         br_saved = []
-        for i in range(2):
+        for i in (1, 0):  # the class / box branches are independent: branch 1 is forked to the second stream
             sl = slice(i * 256, (i + 1) * 256)
-            xb, mb1, rb1 = ops.add_layernorm(o[:, sl], ca[:, sl], P.f(f"d{l}.b{i}.n1_w"), P.f(f"d{l}.b{i}.n1_b"),
-                                             save_stats=True)
-            f = _mm_bias_relu(xb, P.w(f"d{l}.b{i}.fc1_w"), P.w(f"d{l}.b{i}.fc1_b"))
-            g = _mm_bias(f, P.w(f"d{l}.b{i}.fc2_w"), P.w(f"d{l}.b{i}.fc2_b"))
-            _, mb2, rb2 = ops.add_layernorm(xb, g, P.f(f"d{l}.b{i}.n2_w"), P.f(f"d{l}.b{i}.n2_b"), save_stats=True,
-                                            out=y[:, sl])
+            with P.fork(i == 1):
+                xb, mb1, rb1 = ops.add_layernorm(o[:, sl], ca[:, sl], P.f(f"d{l}.b{i}.n1_w"), P.f(f"d{l}.b{i}.n1_b"),
+                                                 save_stats=True)
+                f = _mm_bias_relu(xb, P.w(f"d{l}.b{i}.fc1_w"), P.w(f"d{l}.b{i}.fc1_b"))
+                g = _mm_bias(f, P.w(f"d{l}.b{i}.fc2_w"), P.w(f"d{l}.b{i}.fc2_b"))
+                _, mb2, rb2 = ops.add_layernorm(xb, g, P.f(f"d{l}.b{i}.n2_w"), P.f(f"d{l}.b{i}.n2_b"), save_stats=True,
+                                                out=y[:, sl])
             br_saved.append((xb, mb1, rb1, f, g, mb2, rb2))
+        br_saved.reverse()
+        P.join()
         xo, mn, rn = ops.add_layernorm(x, y, P.f("d.n_w"), P.f("d.n_b"), save_stats=True)
         return xo, (x, t1, sin, pairs, qkv, cat, o1, o2, lse1, lse2, o, st, qo, qp, ca, lse_c, y, br_saved, mn, rn), \
             (coords, pairs)
@@ -312,19 +355,22 @@ class HotPathRuntime:
         x, t1, sin, pairs, qkv, cat, o1, o2, lse1, lse2, o, st, qo, qp, ca, lse_c, y, br_saved, mn, rn = sv
         d, _, _ = ops.add_layernorm_bwd(dxo, x, y, P.f("d.n_w"), mn, rn, dgamma=P.g("d.n_w"), dbeta=P.g("d.n_b"))
         dca = torch.empty_like(x)
-        for i in range(2):
+        for i in (1, 0):  # independent branches: branch 1 on the second stream
             sl = slice(i * 256, (i + 1) * 256)
             xb, mb1, rb1, f, g, mb2, rb2 = br_saved[i]
             pf = f"d{l}.b{i}."
-            d2, _, _ = ops.add_layernorm_bwd(d[:, sl], xb, g, P.f(pf + "n2_w"), mb2, rb2, dgamma=P.g(pf + "n2_w"),
-                                             dbeta=P.g(pf + "n2_b"), dbias=P.g(pf + "fc2_b"))
-            P.acc_gw(pf + "fc2_w", d2, f)
-            df = torch.mm(d2, P.w(pf + "fc2_w"))
-            dpre = ops.relu_bwd_colsum(df, f, P.g(pf + "fc1_b"))
-            P.acc_gw(pf + "fc1_w", dpre, xb)
-            dxb = torch.addmm(d2, dpre, P.w(pf + "fc1_w"))
-            ops.add_layernorm_bwd(dxb, o[:, sl], ca[:, sl], P.f(pf + "n1_w"), mb1, rb1, dgamma=P.g(pf + "n1_w"),
-                                  dbeta=P.g(pf + "n1_b"), dx_out=dca[:, sl])
+            with P.fork(i == 1):
+                d2, _, _ = ops.add_layernorm_bwd(d[:, sl], xb, g, P.f(pf + "n2_w"), mb2, rb2, dgamma=P.g(pf + "n2_w"),
+                                                 dbeta=P.g(pf + "n2_b"), dbias=P.g(pf + "fc2_b"))
+                P.acc_gw(pf + "fc2_w", d2, f)
+                df = torch.mm(d2, P.w(pf + "fc2_w"))
+                dpre = ops.relu_bwd_colsum(df, f, P.g(pf + "fc1_b"))
+                P.acc_gw(pf + "fc1_w", dpre, xb)
+                dxb = torch.addmm(d2, dpre, P.w(pf + "fc1_w"))
+                ops.add_layernorm_bwd(dxb, o[:, sl], ca[:, sl], P.f(pf + "n1_w"), mb1, rb1, dgamma=P.g(pf + "n1_w"),
+                                      dbeta=P.g(pf + "n1_b"), dx_out=dca[:, sl])
+                P._keep += [d2, df, dpre, dxb]
+        P.join()
         ke, vv = kv_all[:, l * 512:l * 512 + 256], kv_all[:, l * 512 + 256:(l + 1) * 512]
         kp = kpos_all[:, l * 256:(l + 1) * 256]
         dqo, dqp, _, _, _ = ops.split_cross_attn_bwd(
