@@ -32,6 +32,8 @@ from . import ops
 Tensor = torch.Tensor
 BF16 = torch.bfloat16
 _ALIGN = 64
+import os as _os
+_FORK = {k: _os.environ.get("DESTR_FORK_" + k, d) == "1" for k, d in (("ENC_V", "0"), ("DEC_HEAD", "1"), ("DSIN", "1"))}
 
 
 def _mm_bias(x: Tensor, w: Tensor, b: Tensor) -> Tensor:
@@ -125,8 +127,9 @@ class FlatParams:
         # optimizer): they go to a side stream and overlap the dX chain; inside a CUDA-graph capture this becomes a
         # parallel branch of the graph.  Their operands are kept alive until the streams join (end_backward).
         self.side = torch.cuda.Stream(device=device) if torch.device(device).type == "cuda" else None
-        self.side2 = torch.cuda.Stream(device=device) if self.side is not None else None  # parallel decoder branches
+        self.forks = [torch.cuda.Stream(device=device) for _ in range(2)] if self.side is not None else []  # parallel chains
         self._keep: List[Tensor] = []
+        self._forked = set()
 
     def _v(self, buf: Tensor, name: str, rows: Optional[int] = None) -> Tensor:
         off, shape = self.off[name]
@@ -164,19 +167,21 @@ class FlatParams:
                 t.grad = gv
 
     @contextlib.contextmanager
-    def fork(self, enable: bool = True):
-        """`with P.fork():` runs the body on the second side stream, concurrently with what the caller enqueues next
-        on its own stream; the caller joins with P.join().  (Graph capture turns this into a parallel branch.)"""
-        if self.side2 is None or not enable:
+    def fork(self, enable: bool = True, k: int = 0):
+        """`with P.fork():` runs the body on side stream k, concurrently with what the caller enqueues next on its
+        own stream; the caller joins with P.join(k).  (Graph capture turns this into a parallel branch.)"""
+        if not self.forks or not enable:
             yield
             return
-        self.side2.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(self.side2):
+        self.forks[k].wait_stream(torch.cuda.current_stream())
+        self._forked.add(k)
+        with torch.cuda.stream(self.forks[k]):
             yield
 
-    def join(self):
-        if self.side2 is not None:
-            torch.cuda.current_stream().wait_stream(self.side2)
+    def join(self, k: int = 0):
+        if k in self._forked:  # (joining a stream that never forked would pull un-captured work into a capture)
+            self._forked.discard(k)
+            torch.cuda.current_stream().wait_stream(self.forks[k])
 
     def off_path(self, fn, *operands: Tensor):
         """Run `fn()` (work nothing downstream waits for, e.g. a bias-gradient column sum) on the side stream."""
@@ -255,12 +260,14 @@ class HotPathRuntime:
     # ------------------------------------------------------------------ encoder
     def _enc_fwd(self, l: int, x: Tensor, pos: Tensor, bits: Tensor, B: int, N: int):
         P = self.P
+        Win, b_in = P.w(f"e{l}.in_w"), P.w(f"e{l}.in_b")
+        with P.fork(_FORK["ENC_V"], k=0):  # the value projection does not depend on the position-scale chain
+            v = _mm_bias(x, Win[512:], b_in[512:])
         h1 = _mm_bias_relu(x, P.w("e.ps0_w"), P.w("e.ps0_b"))
         s = _mm_bias(h1, P.w("e.ps2_w"), P.w("e.ps2_b"))
         xq = ops.pos_mul_add(x, pos, s)
-        Win, b_in = P.w(f"e{l}.in_w"), P.w(f"e{l}.in_b")
         qk = _mm_bias(xq, Win[:512], b_in[:512])
-        v = _mm_bias(x, Win[512:], b_in[512:])
+        P.join(0)
         a, lse = ops.enc_attn_fwd(qk[:, :256], qk[:, 256:], v, bits, B, N, 8, 1.0 / math.sqrt(32))
         o = _mm_bias(a, P.w(f"e{l}.out_w"), P.w(f"e{l}.out_b"))
         x1, m1, r1 = ops.add_layernorm(x, o, P.f(f"e{l}.n1_w"), P.f(f"e{l}.n1_b"), save_stats=True)
@@ -314,20 +321,25 @@ class HotPathRuntime:
     def _dec_fwd(self, l: int, x: Tensor, kv_all, kpos_all, qkpos_all, sine, centers, bits, B, Q, N, lam, pairs_ov):
         P = self.P
         xr = x[:, 256:]
-        t1 = _mm_bias_relu(xr, P.w("d.ps0_w"), P.w("d.ps0_b"))
-        t2 = _mm_bias(t1, P.w("d.ps2_w"), P.w("d.ps2_b"))
-        sin = ops.mul(t2, sine)
+        # three independent chains start from the layer input; only the box -> pairing chain is on the critical path
+        with P.fork(_FORK["DEC_HEAD"], k=0):  # query-position chain: pos_scale MLP -> sin -> its cross-attention projection
+            t1 = _mm_bias_relu(xr, P.w("d.ps0_w"), P.w("d.ps0_b"))
+            t2 = _mm_bias(t1, P.w("d.ps2_w"), P.w("d.ps2_b"))
+            sin = ops.mul(t2, sine)
+            qp = torch.mm(sin, P.w(f"d{l}.cqp_w").t())
+        with P.fork(_FORK["DEC_HEAD"], k=1):  # packed q|k|v object projection
+            qkv_obj = torch.mm(x, P.w(f"d{l}.q_w", rows=1536).t())
         bp = self.bbox
         delta = F.linear(torch.relu(F.linear(xr.float(), bp[0].weight, bp[0].bias)), bp[2].weight, bp[2].bias)
         coords = ops.box_refine(delta, centers)
         pairs = ops.pair_indices(coords.view(B, Q, 4)) if pairs_ov is None else pairs_ov
-        qkv_obj = torch.mm(x, P.w(f"d{l}.q_w", rows=1536).t())
+        P.join(1)
         qkv, cat = ops.dec_qkv_prep(qkv_obj, qkpos_all[:, l * 512:(l + 1) * 512], pairs, B, Q)
         o1, o2, lse1, lse2 = ops.dec_self_pair_attn_fwd(qkv, cat, B, Q)
         o, st = ops.dual_ln_mix(x, o1, o2, pairs, P.f(f"d{l}.n1_w"), P.f(f"d{l}.n1_b"), P.f(f"d{l}.n2_w"),
                                 P.f(f"d{l}.n2_b"), lam, Q)
         qo = torch.mm(o, P.w(f"d{l}.cq_w").t())
-        qp = torch.mm(sin, P.w(f"d{l}.cqp_w").t())
+        P.join(0)
         ke, vv = kv_all[:, l * 512:l * 512 + 256], kv_all[:, l * 512 + 256:(l + 1) * 512]
         kp = kpos_all[:, l * 256:(l + 1) * 256]
         ca, lse_c = ops.split_cross_attn_fwd(qo, qp, ke, kp, vv, bits, B, Q, N)
@@ -379,7 +391,12 @@ class HotPathRuntime:
         P.acc_gw(f"d{l}.cq_w", dqo, o)
         do = torch.addmm(dca, dqo, P.w(f"d{l}.cq_w"))   # d(o) = d(o_cls|o_reg residual) + dq_obj W
         P.acc_gw(f"d{l}.cqp_w", dqp, sin)
-        dsin = torch.mm(dqp, P.w(f"d{l}.cqp_w"))
+        with P.fork(_FORK["DSIN"], k=0):  # sin = sine * pos_scale(x_reg): independent of the self/pair-attention chain below
+            dsin = torch.mm(dqp, P.w(f"d{l}.cqp_w"))
+            dt2 = ops.mul(dsin, sine)
+            xr = x[:, 256:]
+            dxr = torch.zeros(x.shape[0], 256, dtype=BF16, device=x.device)
+            self._pos_scale_bwd("d", dt2, t1, xr, dxr)
         dx2, do1, do2, delta1, delta2 = ops.dual_ln_mix_bwd(
             do, x, o1, o2, pairs, P.f(f"d{l}.n1_w"), P.f(f"d{l}.n2_w"), st, lam, Q,
             pg=(P.g(f"d{l}.n1_w"), P.g(f"d{l}.n1_b"), P.g(f"d{l}.n2_w"), P.g(f"d{l}.n2_b")), head_major=True)
@@ -389,12 +406,9 @@ class HotPathRuntime:
                                             d_pos_out=d_qkpos_all[:, l * 512:(l + 1) * 512])
         P.acc_gw(f"d{l}.q_w", d_qkv_obj, x, rows=1536)
         dx.addmm_(d_qkv_obj, P.w(f"d{l}.q_w", rows=1536))
-        # sin = sine * pos_scale(x_reg)
-        dt2 = ops.mul(dsin, sine)
-        xr = x[:, 256:]
-        dxr = torch.zeros(x.shape[0], 256, dtype=BF16, device=x.device)
-        self._pos_scale_bwd("d", dt2, t1, xr, dxr)
+        P.join(0)
         dx[:, 256:] += dxr
+        P._keep += [dsin, dt2, dxr]
         return dx
 
     # ------------------------------------------------------------------ whole path
