@@ -23,14 +23,16 @@ __device__ __forceinline__ XYXY to_xyxy(float cx, float cy, float hh, float ww) 
 __device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.f), 1.f); }
 
 // ---------------------------------------------------------------------------------------------
-// _get_pairs (pair_self_attention.py:110-171): one CTA per image, thread i scans all j.
+// _get_pairs (pair_self_attention.py:110-171): one WARP per box i, lanes over the candidates j, then a warp
+// arg-max with torch.argmax's rule (first maximal element; NaN counts as maximal).  grid = (ceil(Q/8), B).
 // ---------------------------------------------------------------------------------------------
-__global__ void pair_indices_kernel(const float* __restrict__ coords, int32_t* __restrict__ pairs, int Q) {
+__global__ void __launch_bounds__(256)
+pair_indices_kernel(const float* __restrict__ coords, int32_t* __restrict__ pairs, int Q) {
   extern __shared__ float sh[];  // [Q][4] xyxy, [Q] area, [Q] l1
   float* bx = sh;
   float* area = sh + 4 * Q;
   float* l1 = area + Q;
-  const int b = blockIdx.x;
+  const int b = blockIdx.y;
   for (int i = threadIdx.x; i < Q; i += blockDim.x) {
     const float4 c = reinterpret_cast<const float4*>(coords)[(size_t)b * Q + i];
     const XYXY r = to_xyxy(c.x, c.y, c.z, c.w);
@@ -40,22 +42,38 @@ __global__ void pair_indices_kernel(const float* __restrict__ coords, int32_t* _
     l1[i] = __fadd_rn(fabsf(w), fabsf(h));
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < Q; i += blockDim.x) {
-    const float x0 = bx[4 * i], y0 = bx[4 * i + 1], x1 = bx[4 * i + 2], y1 = bx[4 * i + 3], ai = area[i];
-    float best = 0.f;
-    int bj = -1;
-    for (int j = 0; j < Q; ++j) {
-      // unclamped intersection (pair_self_attention.py:122-126)
-      const float iw = __fsub_rn(fminf(x1, bx[4 * j + 2]), fmaxf(x0, bx[4 * j + 0]));
-      const float ih = __fsub_rn(fminf(y1, bx[4 * j + 3]), fmaxf(y0, bx[4 * j + 1]));
-      const float inter = __fmul_rn(iw, ih);
-      const float uni = __fsub_rn(__fadd_rn(ai, area[j]), inter);
-      float v = __fdiv_rn(inter, __fadd_rn(uni, 1e-6f));
-      v = __fsub_rn(v, (i == j) ? 1.f : 0.f);
-      // torch.argmax: first maximal element, NaN counts as maximal
-      const bool better = (bj < 0) || (v > best) || (isnan(v) && !isnan(best));
-      if (better) { best = v; bj = j; }
-    }
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= Q) return;  // warp-uniform
+  const float x0 = bx[4 * i], y0 = bx[4 * i + 1], x1 = bx[4 * i + 2], y1 = bx[4 * i + 3], ai = area[i];
+  // better(a, b): a precedes b in torch.argmax's order (NaN first, then larger value, then smaller index)
+  auto better = [](float va, int ja, float vb, int jb) {
+    if (jb < 0) return ja >= 0;
+    if (ja < 0) return false;
+    const bool na = isnan(va), nb = isnan(vb);
+    if (na != nb) return na;
+    if (!na && va != vb) return va > vb;
+    return ja < jb;
+  };
+  float best = 0.f;
+  int bj = -1;
+  for (int j = lane; j < Q; j += 32) {
+    // unclamped intersection (pair_self_attention.py:122-126)
+    const float iw = __fsub_rn(fminf(x1, bx[4 * j + 2]), fmaxf(x0, bx[4 * j + 0]));
+    const float ih = __fsub_rn(fminf(y1, bx[4 * j + 3]), fmaxf(y0, bx[4 * j + 1]));
+    const float inter = __fmul_rn(iw, ih);
+    const float uni = __fsub_rn(__fadd_rn(ai, area[j]), inter);
+    float v = __fdiv_rn(inter, __fadd_rn(uni, 1e-6f));
+    v = __fsub_rn(v, (i == j) ? 1.f : 0.f);
+    if (better(v, j, best, bj)) { best = v; bj = j; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+    if (better(ov, oj, best, bj)) { best = ov; bj = oj; }
+  }
+  if (lane == 0) {
     const bool keep = l1[i] >= l1[bj];
     pairs[((size_t)b * Q + i) * 2 + 0] = keep ? i : bj;
     pairs[((size_t)b * Q + i) * 2 + 1] = keep ? bj : i;
@@ -159,8 +177,8 @@ using namespace destr;
 
 extern "C" int destr_pair_indices(const float* coords, int32_t* pairs, int B, int Q, void* stream) {
   DESTR_CHECK_ARG(coords && pairs && B > 0 && Q > 0 && Q <= 4096, "shape");
-  const int threads = Q >= 256 ? 256 : ((Q + 31) / 32) * 32;
-  pair_indices_kernel<<<B, threads, (size_t)Q * 6 * sizeof(float), (cudaStream_t)stream>>>(coords, pairs, Q);
+  dim3 grid(ceil_div(Q, 8), B);
+  pair_indices_kernel<<<grid, 256, (size_t)Q * 6 * sizeof(float), (cudaStream_t)stream>>>(coords, pairs, Q);
   DESTR_LAUNCH_CHECK();
   return 0;
 }

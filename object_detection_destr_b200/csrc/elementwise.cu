@@ -27,42 +27,48 @@ __global__ void pack_key_mask_kernel(const uint8_t* __restrict__ kpm, uint32_t* 
 // 10000^(2*floor(i/2)/128), i = channel within a 128-wide half
 __device__ __forceinline__ float sine_div(int i) { return powf(10000.0f, (2.0f * (float)(i >> 1)) / 128.0f); }
 
-// one block (128 threads) per token; thread c -> channels c (y half) and 128+c (x half)
-__global__ void sine_pos2d_kernel(const uint8_t* __restrict__ mask, float* __restrict__ pos_f32,
-                                  __nv_bfloat16* __restrict__ pos_bf16, int H, int W) {
-  const int tok = blockIdx.x;  // b*H*W + y*W + x
-  const int b = tok / (H * W);
-  const int yx = tok - b * H * W;
-  const int y = yx / W, x = yx - y * W;
+// one block (128 threads) per image ROW (b, y): the cumulative valid-pixel counts of the row and of every column
+// up to it are computed once into shared memory (exact in fp32), then thread c writes channels c (y half) and
+// 128+c (x half) of the row's W tokens.
+constexpr int kMaxW = 512;
+__global__ void __launch_bounds__(128)
+sine_pos2d_kernel(const uint8_t* __restrict__ mask, float* __restrict__ pos_f32, __nv_bfloat16* __restrict__ pos_bf16,
+                  int H, int W) {
+  __shared__ float s_ye[kMaxW], s_xe[kMaxW];
+  const int b = blockIdx.x / H, y = blockIdx.x - b * H;
   const uint8_t* mb = mask + static_cast<size_t>(b) * H * W;
-  // cumulative counts of valid pixels (exact in fp32); every thread recomputes them (H,W <= ~100)
-  float ycum = 0.f, ytot = 0.f, xcum = 0.f, xtot = 0.f;
-  for (int yy = 0; yy < H; ++yy) {
-    const float v = mb[yy * W + x] ? 0.f : 1.f;
-    ytot += v;
-    if (yy <= y) ycum += v;
-  }
-  for (int xx = 0; xx < W; ++xx) {
-    const float v = mb[y * W + xx] ? 0.f : 1.f;
-    xtot += v;
-    if (xx <= x) xcum += v;
-  }
   const float two_pi = 6.283185307179586f;
-  const float ye = __fmul_rn(__fdiv_rn(ycum, __fadd_rn(ytot, 1e-6f)), two_pi);
-  const float xe = __fmul_rn(__fdiv_rn(xcum, __fadd_rn(xtot, 1e-6f)), two_pi);
+  for (int x = threadIdx.x; x < W; x += blockDim.x) {
+    float ycum = 0.f, ytot = 0.f, xcum = 0.f, xtot = 0.f;
+    for (int yy = 0; yy < H; ++yy) {
+      const float v = mb[yy * W + x] ? 0.f : 1.f;
+      ytot += v;
+      if (yy <= y) ycum += v;
+    }
+    for (int xx = 0; xx < W; ++xx) {
+      const float v = mb[y * W + xx] ? 0.f : 1.f;
+      xtot += v;
+      if (xx <= x) xcum += v;
+    }
+    s_ye[x] = __fmul_rn(__fdiv_rn(ycum, __fadd_rn(ytot, 1e-6f)), two_pi);
+    s_xe[x] = __fmul_rn(__fdiv_rn(xcum, __fadd_rn(xtot, 1e-6f)), two_pi);
+  }
+  __syncthreads();
   const int c = threadIdx.x;
   const float dv = sine_div(c);
-  const float ay = __fdiv_rn(ye, dv), ax = __fdiv_rn(xe, dv);
-  const float vy = (c & 1) ? cosf(ay) : sinf(ay);
-  const float vx = (c & 1) ? cosf(ax) : sinf(ax);
-  const size_t o = static_cast<size_t>(tok) * 256;
-  if (pos_f32) {
-    pos_f32[o + c] = vy;
-    pos_f32[o + 128 + c] = vx;
-  }
-  if (pos_bf16) {
-    pos_bf16[o + c] = __float2bfloat16(vy);
-    pos_bf16[o + 128 + c] = __float2bfloat16(vx);
+  for (int x = 0; x < W; ++x) {
+    const float ay = __fdiv_rn(s_ye[x], dv), ax = __fdiv_rn(s_xe[x], dv);
+    const float vy = (c & 1) ? cosf(ay) : sinf(ay);
+    const float vx = (c & 1) ? cosf(ax) : sinf(ax);
+    const size_t o = (static_cast<size_t>(blockIdx.x) * W + x) * 256;
+    if (pos_f32) {
+      pos_f32[o + c] = vy;
+      pos_f32[o + 128 + c] = vx;
+    }
+    if (pos_bf16) {
+      pos_bf16[o + c] = __float2bfloat16(vy);
+      pos_bf16[o + 128 + c] = __float2bfloat16(vx);
+    }
   }
 }
 
@@ -150,9 +156,12 @@ __global__ void pos_mul_add_bwd_acc_kernel(const __nv_bfloat16* __restrict__ dy,
 }
 
 // dpre = dy * (h > 0); dbias[c] += sum_rows dpre[:, c].  Block = 32 column groups (8 channels each) x 8 row
-// lanes; a block owns ROWS_PER_BLOCK rows of a 256-column stripe and every thread issues its 4 row loads up
-// front (latency-bound otherwise).  grid = (ceil(C/256), ceil(M/ROWS_PER_BLOCK)).
-constexpr int kRowsPerBlock = 32;
+// lanes; a block owns 32*CHUNKS rows of a 256-column stripe, walks them in chunks of 32 rows and issues the 4 row
+// loads of a chunk up front (latency-bound otherwise); ONE atomicAdd per column per block at the end, so large
+// matrices use CHUNKS = 4 (4x fewer same-address atomics, which bounded the FFN-sized launches).
+// grid = (ceil(C/256), ceil(M/(32*CHUNKS))).
+constexpr int kRowsPerChunk = 32;
+template <int CHUNKS>
 __global__ void __launch_bounds__(256)
 relu_bwd_colsum_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ h,
                        __nv_bfloat16* __restrict__ dpre, float* __restrict__ dbias, int M, int C, int lddy, int ldh,
@@ -160,31 +169,34 @@ relu_bwd_colsum_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16
   __shared__ float red[8][256];
   const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + cg * 8;
-  const int row0 = blockIdx.y * kRowsPerBlock + rl;
   float acc[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
   if (col < C) {
-    F8 g[kRowsPerBlock / 8], a[kRowsPerBlock / 8];
+#pragma unroll 1
+    for (int ch = 0; ch < CHUNKS; ++ch) {
+      const int row0 = (blockIdx.y * CHUNKS + ch) * kRowsPerChunk + rl;
+      F8 g[kRowsPerChunk / 8], a[kRowsPerChunk / 8];
 #pragma unroll
-    for (int u = 0; u < kRowsPerBlock / 8; ++u) {
-      const int row = row0 + u * 8;
-      if (row < M) {
-        g[u] = ld8(dy + (size_t)row * lddy + col);
-        if (h) a[u] = ld8(h + (size_t)row * ldh + col);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < kRowsPerBlock / 8; ++u) {
-      const int row = row0 + u * 8;
-      if (row < M) {
-        if (h) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) g[u].v[k] = a[u].v[k] > 0.f ? g[u].v[k] : 0.f;
-          st8(dpre + (size_t)row * ldo + col, g[u]);
+      for (int u = 0; u < kRowsPerChunk / 8; ++u) {
+        const int row = row0 + u * 8;
+        if (row < M) {
+          g[u] = ld8(dy + (size_t)row * lddy + col);
+          if (h) a[u] = ld8(h + (size_t)row * ldh + col);
         }
+      }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] += g[u].v[k];
+      for (int u = 0; u < kRowsPerChunk / 8; ++u) {
+        const int row = row0 + u * 8;
+        if (row < M) {
+          if (h) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) g[u].v[k] = a[u].v[k] > 0.f ? g[u].v[k] : 0.f;
+            st8(dpre + (size_t)row * ldo + col, g[u]);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] += g[u].v[k];
+        }
       }
     }
   }
@@ -223,8 +235,8 @@ extern "C" int destr_pack_key_mask(const uint8_t* kpm, uint32_t* bits, int B, in
 
 extern "C" int destr_sine_pos2d(const uint8_t* mask, float* pos_f32, void* pos_bf16, int B, int H, int W,
                                 void* stream) {
-  DESTR_CHECK_ARG(mask && (pos_f32 || pos_bf16) && B > 0 && H > 0 && W > 0, "shape");
-  sine_pos2d_kernel<<<B * H * W, 128, 0, (cudaStream_t)stream>>>(mask, pos_f32, (__nv_bfloat16*)pos_bf16, H, W);
+  DESTR_CHECK_ARG(mask && (pos_f32 || pos_bf16) && B > 0 && H > 0 && W > 0 && W <= kMaxW, "shape (W <= 512)");
+  sine_pos2d_kernel<<<B * H, 128, 0, (cudaStream_t)stream>>>(mask, pos_f32, (__nv_bfloat16*)pos_bf16, H, W);
   DESTR_LAUNCH_CHECK();
   return 0;
 }
@@ -279,9 +291,15 @@ extern "C" int destr_relu_bwd_colsum(const void* dy, int lddy, const void* h, in
                                      float* dbias, int M, int C, void* stream) {
   DESTR_CHECK_ARG(dy && dbias && M > 0 && C > 0 && C % 8 == 0 && lddy % 8 == 0, "shape");
   DESTR_CHECK_ARG((h == nullptr) == (dpre == nullptr), "h and dpre go together (both NULL = plain column sum)");
-  dim3 grid(ceil_div(C, 256), ceil_div(M, kRowsPerBlock));
-  relu_bwd_colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)h,
-                                                                 (__nv_bfloat16*)dpre, dbias, M, C, lddy, ldh, ldo);
+  if (static_cast<int64_t>(M) * C >= (1 << 22)) {  // FFN-sized: fewer, longer blocks (atomics on dbias bound the short ones)
+    dim3 grid(ceil_div(C, 256), ceil_div(M, kRowsPerChunk * 4));
+    relu_bwd_colsum_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)dy, (const __nv_bfloat16*)h, (__nv_bfloat16*)dpre, dbias, M, C, lddy, ldh, ldo);
+  } else {
+    dim3 grid(ceil_div(C, 256), ceil_div(M, kRowsPerChunk));
+    relu_bwd_colsum_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)dy, (const __nv_bfloat16*)h, (__nv_bfloat16*)dpre, dbias, M, C, lddy, ldh, ldo);
+  }
   DESTR_LAUNCH_CHECK();
   return 0;
 }
