@@ -391,7 +391,7 @@ extern "C" int destr_add_layernorm_bwd(const void* dy, int lddy, const void* a, 
   DESTR_CHECK_ARG(dy && a && gamma && mean && rstd && dx && dgamma && dbeta && M > 0, "null pointer / shape");
   DESTR_CHECK_ARG(D == 256 || D == 512, "D must be 256 or 512");
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = ln_grid(M) > kSMs * 4 ? kSMs * 4 : ln_grid(M);  // 4 CTAs/SM: rows in flight hide the load latency
+  const int grid = ln_grid(M) > kSMs * 2 ? kSMs * 2 : ln_grid(M);
   const __nv_bfloat16* ri = (const __nv_bfloat16*)res_in;
   __nv_bfloat16* ro = (__nv_bfloat16*)res_out;
   if (D == 256)

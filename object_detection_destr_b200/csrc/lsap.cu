@@ -40,7 +40,7 @@ __device__ __forceinline__ Best warp_best(Best v) {
 
 // one warp per image; dynamic shared memory: 3 double[M] + 4 int[M] + 2 uint8[M], M = max(Q, max targets)
 __global__ void __launch_bounds__(32)
-lsap_kernel(const float* __restrict__ cost, const int32_t* __restrict__ offs, int Q, int n_slots, int M,
+lsap_kernel(const float* __restrict__ cost, const int32_t* __restrict__ offs, int Q, int n_slots, int M, int cost_in_smem,
             int64_t* __restrict__ pred_idx, int64_t* __restrict__ tgt_idx, uint8_t* __restrict__ valid,
             int32_t* __restrict__ status) {
   extern __shared__ double smem_d[];
@@ -81,7 +81,18 @@ lsap_kernel(const float* __restrict__ cost, const int32_t* __restrict__ offs, in
 
   const bool transpose = T < Q;  // tall matrix: rows = targets, columns = queries
   const int nr = transpose ? T : Q, nc = transpose ? Q : T;
+  // the scans re-read one row of the (possibly transposed) cost block per iteration: stage the block in shared
+  // memory, row-major in the orientation of the solve (coalesced scans, no L2 latency on the serial path)
+  float* Cs = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(SC + M) + 15) & ~uintptr_t(15));
+  const bool staged = cost_in_smem != 0;
+  if (staged) {
+    for (int e = lane; e < Q * T; e += 32) {
+      const int q = e / T, t = e - q * T;
+      Cs[transpose ? t * Q + q : e] = C[e];
+    }
+  }
   auto cst = [&](int r, int c) -> double {
+    if (staged) return static_cast<double>(Cs[r * nc + c]);
     return static_cast<double>(transpose ? C[static_cast<size_t>(c) * T + r] : C[static_cast<size_t>(r) * T + c]);
   };
   for (int k = lane; k < nr; k += 32) {
@@ -195,15 +206,18 @@ extern "C" int destr_lsap_blockdiag(const float* cost, const int32_t* tgt_offset
   DESTR_CHECK_ARG(B > 0 && Q > 0 && max_targets > 0, "shape");
   DESTR_CHECK_ARG(n_slots >= (Q < max_targets ? Q : max_targets), "n_slots must be >= min(Q, max_targets)");
   const int M = Q > max_targets ? Q : max_targets;
-  const size_t smem = static_cast<size_t>(M) * (3 * sizeof(double) + 4 * sizeof(int) + 2) + 64;
+  size_t smem = (static_cast<size_t>(M) * (3 * sizeof(double) + 4 * sizeof(int) + 2) + 15) / 16 * 16;
   DESTR_CHECK_ARG(smem <= 200 * 1024, "problem too large for one warp's shared memory");
+  const size_t block = static_cast<size_t>(Q) * max_targets * sizeof(float);
+  const int cost_in_smem = smem + block <= 200 * 1024 ? 1 : 0;
+  if (cost_in_smem) smem += block;
   static size_t attr = 0;
   if (smem > 48 * 1024 && smem > attr) {
     DESTR_CUDA(cudaFuncSetAttribute(lsap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  lsap_kernel<<<B, 32, smem, static_cast<cudaStream_t>(stream)>>>(cost, tgt_offsets, Q, n_slots, M, pred_idx, tgt_idx,
-                                                                  valid, status);
+  lsap_kernel<<<B, 32, smem, static_cast<cudaStream_t>(stream)>>>(cost, tgt_offsets, Q, n_slots, M, cost_in_smem, pred_idx,
+                                                                  tgt_idx, valid, status);
   DESTR_LAUNCH_CHECK();
   return 0;
 }

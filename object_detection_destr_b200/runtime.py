@@ -330,7 +330,14 @@ class HotPathRuntime:
         with P.fork(_FORK["DEC_HEAD"], k=1):  # packed q|k|v object projection
             qkv_obj = torch.mm(x, P.w(f"d{l}.q_w", rows=1536).t())
         bp = self.bbox
-        delta = F.linear(torch.relu(F.linear(xr.float(), bp[0].weight, bp[0].bias)), bp[2].weight, bp[2].bias)
+        # box refinement of the layer's queries: feeds ONLY the pairing (arg-max indices), its input is already bf16
+        # -> TF32 tensor-core GEMMs (10-bit mantissa, finer than the input rounding) instead of fp32 SIMT ones
+        tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            delta = F.linear(torch.relu(F.linear(xr.float(), bp[0].weight, bp[0].bias)), bp[2].weight, bp[2].bias)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = tf32
         coords = ops.box_refine(delta, centers)
         pairs = ops.pair_indices(coords.view(B, Q, 4)) if pairs_ov is None else pairs_ov
         P.join(1)
