@@ -52,4 +52,6 @@ def grads_of(model: torch.nn.Module):
     flat = rt.P.g32
     lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * flat.element_size()
     loose = [p.grad for p in model.parameters() if p.grad is not None and not (lo <= p.grad.data_ptr() < hi)]
+    if getattr(rt.P, "world", 1) > 1:  # the runtime already exchanged its flat buffer inside backward()
+        return [], loose
     return [flat], loose

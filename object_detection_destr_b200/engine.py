@@ -86,6 +86,8 @@ class GraphedTrainStep:
         self.h_tl = torch.empty(B, t_max, dtype=torch.int64, pin_memory=True)
         self.h_tb = torch.empty(B, t_max, 4, dtype=torch.float32, pin_memory=True)
         self.params = [p for p in model.parameters()]
+        if world > 1 and getattr(model, "use_runtime", False):
+            model.runtime().P.enable_data_parallel(world)  # gradient exchange overlapped with the encoder backward
         self.fused_loss = fused_loss
         self.gpu_lsa = gpu_lsa
         self.s_status = z(B, dt=torch.int32)

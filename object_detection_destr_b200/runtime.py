@@ -157,11 +157,41 @@ class FlatParams:
         self.g32[self.nW:].zero_()
         self._written.clear()
 
+    # ---- data parallel: the one exchange of a training step, overlapped with backward ----
+    def enable_data_parallel(self, world: int, group=None):
+        """Mean all-reduce of the gradients over `world` ranks inside backward(): the weight gradients travel as
+        bf16 (they are produced in bf16; half the NVLink bytes), in two pieces -- the decoder's as soon as the
+        decoder backward is done (it overlaps the encoder backward on a communication stream), the encoder's and
+        the fp32 bias / LayerNorm gradients at the end."""
+        self.world, self.group = world, group
+        self.comm = torch.cuda.Stream(device=self.g32.device) if world > 1 else None
+        self.dec_off = self.off["d0.q_w"][0]
+
+    def reduce_decoder_grads(self):
+        if getattr(self, "world", 1) <= 1:
+            return
+        import torch.distributed as dist
+        self.comm.wait_stream(self.side)                      # the decoder's weight-gradient GEMMs
+        self.comm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.comm):
+            dist.all_reduce(self.g16[self.dec_off:], group=self.group)
+
     def end_backward(self):
         if self.side is not None:
             torch.cuda.current_stream().wait_stream(self.side)
             self._keep.clear()
-        self.g32[:self.nW].copy_(self.g16)
+        if getattr(self, "world", 1) > 1:
+            import torch.distributed as dist
+            self.comm.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm):
+                dist.all_reduce(self.g16[:self.dec_off], group=self.group)
+                dist.all_reduce(self.g32[self.nW:], group=self.group)
+            torch.cuda.current_stream().wait_stream(self.comm)
+            inv = 1.0 / self.world
+            torch.mul(self.g16, inv, out=self.g32[:self.nW])   # bf16 -> fp32 with the 1/world of the mean
+            self.g32[self.nW:].mul_(inv)
+        else:
+            self.g32[:self.nW].copy_(self.g16)
         for t, gv in zip(self.params, self._gviews):  # zero_grad(set_to_none=True) may have detached them
             if t.grad is not gv:
                 t.grad = gv
@@ -466,6 +496,7 @@ class HotPathRuntime:
         P.acc_gw("d0.kp_w", d_kpos_all, fine, rows=Ld * 256)
         d_fine = torch.mm(d_kpos_all, P.w("d0.kp_w", rows=Ld * 256))
         P.acc_gw("d0.sqp_w", d_qkpos_all, pos_embed, rows=Ld * 512)
+        P.reduce_decoder_grads()  # data parallel: the decoder's gradients are final -> exchange them under the encoder backward
         du = ops.mul(d_fine, pos)
         if d_enc_ext is not None:
             d_enc += d_enc_ext
