@@ -99,6 +99,7 @@ class GraphedTrainStep:
         self.out = None
         self.sizes: List[int] = []
         self.launches_per_step = 0
+        self._slots = None
 
     # ---- pieces (also run eagerly during warm-up) ----
     def _forward(self):
@@ -150,24 +151,19 @@ class GraphedTrainStep:
         self.s_ti.copy_(self.h_idx[1], non_blocking=True)
         self.s_valid.copy_(self.h_idx[2], non_blocking=True)
 
-    def load_batch(self, feats, mask, sel, centers, labels: Sequence[torch.Tensor], boxes: Sequence[torch.Tensor]):
-        """Copy one batch into the static buffers.  feats/mask/sel/centers may be host (pinned) or device
-        tensors; labels/boxes are per-image HOST tensors (int64 [T_i], fp32 [T_i,4] xyxy), T_i <= t_max."""
-        nb = True
-        self.s_feats.copy_(feats, non_blocking=nb)
-        self.s_mask.copy_(mask, non_blocking=nb)
-        self.s_sel.copy_(sel, non_blocking=nb)
-        self.s_centers.copy_(centers, non_blocking=nb)
+    def _pack_targets(self, labels, boxes, h_tgt_i, h_tgt_f, h_tl, h_tb):
+        """Per-image host targets -> the pinned, padded arrays the kernels read (concatenated ids/boxes + offsets for
+        the cost kernel and the assignment; [B, t_max] padded labels/boxes for the loss)."""
         B, tm = self.B, self.t_max
-        self.sizes = [int(l.numel()) for l in labels]
-        assert max(self.sizes) <= tm, "raise t_max"
-        hi, hf = self.h_tgt_i.numpy(), self.h_tgt_f.numpy().reshape(-1, 4)
-        tl, tb = self.h_tl.numpy(), self.h_tb.numpy()
+        sizes = [int(l.numel()) for l in labels]
+        assert max(sizes) <= tm, "raise t_max"
+        hi, hf = h_tgt_i.numpy(), h_tgt_f.numpy().reshape(-1, 4)
+        tl, tb = h_tl.numpy(), h_tb.numpy()
         tl.fill(1)
         tb.fill(0)
         off = 0
         for b, (l, bx) in enumerate(zip(labels, boxes)):
-            t = self.sizes[b]
+            t = sizes[b]
             hi[B * tm + b] = off
             if t:
                 hi[off:off + t] = l.numpy()
@@ -176,11 +172,60 @@ class GraphedTrainStep:
                 tb[b, :t] = bx.numpy()
             off += t
         hi[B * tm + B] = off
-        self.s_ids.copy_(self.h_tgt_i[:B * tm], non_blocking=nb)
-        self.s_offs.copy_(self.h_tgt_i[B * tm:], non_blocking=nb)
-        self.s_tboxes.copy_(self.h_tgt_f.view(-1, 4), non_blocking=nb)
-        self.s_tl.copy_(self.h_tl, non_blocking=nb)
-        self.s_tb.copy_(self.h_tb, non_blocking=nb)
+        return sizes
+
+    def _statics(self):
+        return [self.s_feats, self.s_mask, self.s_sel, self.s_centers, self.s_ids, self.s_offs, self.s_tboxes, self.s_tl,
+                self.s_tb]
+
+    def load_batch(self, feats, mask, sel, centers, labels: Sequence[torch.Tensor], boxes: Sequence[torch.Tensor]):
+        """Copy one batch into the static buffers.  feats/mask/sel/centers may be host (pinned) or device
+        tensors; labels/boxes are per-image HOST tensors (int64 [T_i], fp32 [T_i,4] xyxy), T_i <= t_max."""
+        B, tm = self.B, self.t_max
+        self.sizes = self._pack_targets(labels, boxes, self.h_tgt_i, self.h_tgt_f, self.h_tl, self.h_tb)
+        srcs = [feats, mask, sel, centers, self.h_tgt_i[:B * tm], self.h_tgt_i[B * tm:], self.h_tgt_f.view(-1, 4),
+                self.h_tl, self.h_tb]
+        for dst, src in zip(self._statics(), srcs):
+            dst.copy_(src, non_blocking=True)
+
+    # ---- input pipelining: stage batch s+1 (host packing + H2D on a copy stream) while step s runs ----
+    def prefetch(self, feats, mask, sel, centers, labels: Sequence[torch.Tensor], boxes: Sequence[torch.Tensor]):
+        """Stage the NEXT batch: pack its targets into this slot's pinned arrays and enqueue all H2D copies into
+        device staging buffers on a copy stream.  Returns immediately; `step_prefetched()` consumes it."""
+        if self._slots is None:
+            B, tm = self.B, self.t_max
+            pin = lambda *s, dt: torch.empty(*s, dtype=dt, pin_memory=True)
+            self._copy_stream = torch.cuda.Stream(device=self.dev)
+            self._slots = [dict(dev=[torch.empty_like(t) for t in self._statics()],
+                                h_i=pin(B * tm + B + 1, dt=torch.int32), h_f=pin(B * tm * 4, dt=torch.float32),
+                                h_tl=pin(B, tm, dt=torch.int64), h_tb=pin(B, tm, 4, dt=torch.float32),
+                                ready=torch.cuda.Event(), consumed=torch.cuda.Event()) for _ in range(2)]
+            self._slot = 0
+        self._slot ^= 1
+        st = self._slots[self._slot]
+        st["ready"].synchronize()  # this slot's previous H2D copies are done: its pinned arrays may be rewritten
+        B, tm = self.B, self.t_max
+        st["sizes"] = self._pack_targets(labels, boxes, st["h_i"], st["h_f"], st["h_tl"], st["h_tb"])
+        srcs = [feats, mask, sel, centers, st["h_i"][:B * tm], st["h_i"][B * tm:], st["h_f"].view(-1, 4), st["h_tl"],
+                st["h_tb"]]
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(st["consumed"])  # the step that used this slot has copied it out
+            for dst, src in zip(st["dev"], srcs):
+                dst.copy_(src, non_blocking=True)
+            st["ready"].record(self._copy_stream)
+        self._pending = self._slot
+
+    def step_prefetched(self):
+        """One training step on the batch staged by the last prefetch(): device-to-device hand-over into the graph's
+        static inputs, then the graph replay.  Returns the (device) loss tensor without synchronising."""
+        st = self._slots[self._pending]
+        main = torch.cuda.current_stream()
+        main.wait_event(st["ready"])
+        for dst, src in zip(self._statics(), st["dev"]):
+            dst.copy_(src, non_blocking=True)
+        st["consumed"].record(main)
+        self.sizes = st["sizes"]
+        return self.step()
 
     def eager_step(self):
         out = self._forward()

@@ -80,3 +80,32 @@ def test_device_assignment_step_equals_host_assignment_step():
     assert torch.equal(res[0][2], res[1][2]) and torch.equal(res[0][3], res[1][3])  # identical assignments
     assert abs(res[0][0] - res[1][0]) <= 2e-5 * max(1.0, abs(res[1][0]))
     assert torch.allclose(res[0][1], res[1][1], rtol=2e-2, atol=1e-6)
+
+
+def test_prefetched_steps_equal_plain_steps():
+    """Input pipelining (prefetch on a copy stream + device hand-over) feeds the graph the same batches."""
+    import bench
+    from object_detection_destr_b200.encoder import disable_dropout
+    from object_detection_destr_b200.engine import GraphedTrainStep
+    from object_detection_destr_b200.hotpath import TransformerHalf
+    cfg = dict(bench.CFG, B=2, L=1, H=10, W=14, Q=60)
+    torch.manual_seed(0)
+    model = TransformerHalf(Namespace(hidden_dim=256, num_encoder_blocks=1, num_decoder_blocks=1, num_cls=cfg["C"]))
+    disable_dropout(model).cuda().train()
+    opt = model.make_optimizer(lr=0.0)
+    eng = GraphedTrainStep(model, opt, B=2, H=10, W=14, Q=60, num_classes=cfg["C"], t_max=40)
+    batches = [bench.make_batch(0, s, 2, cfg, padded=True) for s in range(4)]
+    pinned = [tuple(t.pin_memory() for t in bt[:4]) + (bt[4], bt[5]) for bt in batches]
+    eng.load_batch(*batches[0])
+    eng.capture(warmup=2)
+    plain = []
+    for bt in batches:
+        eng.load_batch(*bt)
+        plain.append(float(eng.step()))
+    eng.prefetch(*pinned[0])
+    piped = []
+    for s in range(4):
+        loss_t = eng.step_prefetched()
+        eng.prefetch(*pinned[(s + 1) % 4])
+        piped.append(float(loss_t))
+    assert piped == plain, (piped, plain)
