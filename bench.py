@@ -178,8 +178,12 @@ def time_dominant_kernels(cfg, B, dev, iters: int = 20):
     scale = 1.0 / math.sqrt(32)
     out, lse = ops.enc_attn_fwd(qk[:, :256], qk[:, 256:], v, bits, B, N, 8, scale)
     res = {}
+    bwd = lambda: ops.enc_attn_bwd(qk[:, :256], qk[:, 256:], v, bits, out, do, lse, B, N, 8, scale)
+    from object_detection_destr_b200 import _lib
     for name, fn in (("destr_enc_attn_fwd", lambda: ops.enc_attn_fwd(qk[:, :256], qk[:, 256:], v, bits, B, N, 8, scale)),
-                     ("destr_enc_attn_bwd", lambda: ops.enc_attn_bwd(qk[:, :256], qk[:, 256:], v, bits, out, do, lse, B, N, 8, scale))):
+                     ("destr_enc_attn_bwd_op", bwd),     # all three launches of the op: prep + tcgen05 kernel + dQ convert
+                     ("destr_enc_attn_bwd", bwd)):       # the tcgen05 kernel alone (debug knob 14 skips the two helpers)
+        _lib.lib.destr_debug_knob(14, 1 if name == "destr_enc_attn_bwd" else 0)
         for _ in range(3):
             fn()
         tot = 0.0
@@ -192,6 +196,7 @@ def time_dominant_kernels(cfg, B, dev, iters: int = 20):
             en.synchronize()
             tot += st.elapsed_time(en)
         res[name] = tot / iters
+    _lib.lib.destr_debug_knob(14, 0)
     return res
 
 
@@ -314,7 +319,8 @@ def run_ours(args):
                 "also": {"destr_enc_attn_fwd": {"launch_ms": t_f, "achieved": fwd_flops / t_f / 1e9,
                                                 "frac": fwd_flops / t_f / 1e9 / pk["tf_burst"]},
                          "destr_enc_attn_bwd": {"launch_ms": t_b, "achieved": bwd_flops / t_b / 1e9,
-                                                "frac": bwd_flops / t_b / 1e9 / pk["tf_burst"]}}}
+                                                "frac": bwd_flops / t_b / 1e9 / pk["tf_burst"],
+                                                "op_ms_with_prep_and_convert_launches": kernel_ms["destr_enc_attn_bwd_op"]}}}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             ips, spstep, cores = time_cpu_reference(1, 2, 1)

@@ -31,7 +31,8 @@
 namespace destr {
 
 // debug / tuning knobs (destr_debug_knob): 0 v_lbo 1 v_sbo 2 qk_lbo 3 qk_sbo 4 p_kstep_cols 5 v_kstep_bytes
-// 6-8 enc_attn_bwd descriptors, 9 enc fwd polynomial-exp quarter count (0..3), 10 enc bwd ditto
+// 6-8 enc_attn_bwd descriptors, 9 enc fwd polynomial-exp quarter count (0..3), 10 enc bwd ditto,
+// 11 lazy-rescale tau+1, 12/13 grid overrides, 14 enc bwd: launch the main kernel only (bench timing)
 int g_knobs[16] = {512, 512, 16, 512, 8, 1024, 16384, 1024, 2048, 1, 0, 0, 0, 0, 0, 0};
 
 namespace {
