@@ -139,46 +139,51 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     __syncwarp();
   } else if (warp == 9) {
     // ------------------------------ MMA issuer ------------------------------
+    // One thread issues every MMA and shares its scheduler with four softmax warps, so its instruction stream is
+    // kept minimal: descriptors are compile-time constants plus a shifted address, item/tile counters are
+    // incremental, and the operands of the look-ahead Q.K^T are awaited before the wait on P.
     if (elect_one()) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(BM, BN, false, false);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(BM, DH, false, true);
-      auto issue_qk = [&](int f) {  // S_{f&1} = Q_item . K_j^T
-        const int it = f / nkv, j = f - it * nkv;
-        const int stage = f % KSTAGES, qb = it & 1;
-        if (j == 0) mbar_wait_backoff(&sm.q_full[qb], (it >> 1) & 1, 3);
-        mbar_wait_backoff(&sm.kv_full[stage], (f / KSTAGES) & 1, 4);
+      constexpr uint64_t D_KMAJ = umma_desc_const(16, 512, SWZ_64B);   // Q, K: K-major, 64-byte rows (k-step 32 B)
+      constexpr uint64_t D_VMN = umma_desc_const(512, 512, SWZ_64B);   // V: MN-major B operand (k-step 16 keys = 1024 B)
+      const uint32_t a_q = smem_u32(sm.q[0]) >> 4, a_k = smem_u32(sm.k[0]) >> 4, a_v = smem_u32(sm.v[0]) >> 4;
+      // look-ahead cursor (item / tile of flat tile fq = the next Q.K^T to issue)
+      int fq = 0, itq = 0, jq = 0;
+      auto issue_qk = [&]() {  // S_{fq&1} = Q_item . K_j^T
+        const uint32_t stage = fq % KSTAGES, qb = itq & 1;
+        if (jq == 0) mbar_wait_backoff(&sm.q_full[qb], (itq >> 1) & 1, 3);
+        mbar_wait_backoff(&sm.kv_full[stage], (fq / KSTAGES) & 1, 4);
         tc_fence_after();
-#pragma unroll
-        for (int ks = 0; ks < DH / 16; ++ks) {
-          const uint64_t a = umma_smem_desc(smem_u32(sm.q[qb]) + ks * 32, kn.qk_lbo, kn.qk_sbo, SWZ_64B);
-          const uint64_t bd = umma_smem_desc(smem_u32(sm.k[stage]) + ks * 32, kn.qk_lbo, kn.qk_sbo, SWZ_64B);
-          umma_ss(tmem + C_S + (f & 1) * BN, a, bd, idesc_qk, ks > 0);
-        }
-        tc_commit(&sm.s_full[f & 1]);
-        if (j == nkv - 1) tc_commit(&sm.q_empty[qb]);  // every Q.K^T of the item has been issued
+        const uint64_t a = D_KMAJ + (a_q + qb * (Q_BYTES >> 4)), bd = D_KMAJ + (a_k + stage * (KV_BYTES >> 4));
+        umma_ss(tmem + C_S + (fq & 1) * BN, a, bd, idesc_qk, 0u);
+        umma_ss(tmem + C_S + (fq & 1) * BN, a + 2, bd + 2, idesc_qk, 1u);
+        tc_commit(&sm.s_full[fq & 1]);
+        if (jq == nkv - 1) tc_commit(&sm.q_empty[qb]);  // every Q.K^T of the item has been issued
+        ++fq;
+        if (++jq == nkv) { jq = 0; ++itq; }
       };
-      if (T > 0) issue_qk(0);
-      if (T > 1) issue_qk(1);
+      if (T > 0) issue_qk();
+      if (T > 1) issue_qk();
       int it = 0, j = 0;
       for (int f = 0; f < T; ++f) {
-        const int stage = f % KSTAGES;
+        const uint32_t stage = f % KSTAGES;
+        const uint64_t dv = D_VMN + (a_v + stage * (KV_BYTES >> 4));
+        const uint32_t t_p = tmem + C_S + (f & 1) * BN;
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {  // O_hf (+)= P_hf . V[keys of the half]
           mbar_wait(&sm.p_full[hf][f & 1], (f >> 1) & 1, 5);
           if (j == 0 && it > 0) mbar_wait_backoff(&sm.o_free[hf], (it - 1) & 1, 6);  // epilogue has read O
           tc_fence_after();
 #pragma unroll
-          for (int ks = 0; ks < HN / 16; ++ks) {
-            const uint64_t bd = umma_smem_desc(smem_u32(sm.v[stage]) + (hf * (HN / 16) + ks) * kn.v_kstep_bytes,
-                                               kn.v_lbo, kn.v_sbo, SWZ_64B);
-            umma_ts(tmem + C_O + hf * DH, tmem + C_S + (f & 1) * BN + hf * HN + ks * kn.p_kstep_cols, bd, idesc_pv,
+          for (int ks = 0; ks < HN / 16; ++ks)
+            umma_ts(tmem + C_O + hf * DH, t_p + hf * HN + ks * 8, dv + (hf * (HN / 16) + ks) * 64, idesc_pv,
                     (j > 0 || ks > 0) ? 1u : 0u);
-          }
           tc_commit(&sm.o_full[hf]);
           if (j == nkv - 1) tc_commit(&sm.o_done[hf]);
         }
         tc_commit(&sm.kv_empty[stage]);
-        if (f + 2 < T) issue_qk(f + 2);  // reuses S_{f&1}: ordered behind P.V(f) in the tensor pipe
+        if (fq < T) issue_qk();  // reuses S_{f&1}: ordered behind P.V(f) in the tensor pipe
         if (++j == nkv) { j = 0; ++it; }
       }
     }
