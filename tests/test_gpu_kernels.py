@@ -18,14 +18,43 @@ def test_simt_kernels_vs_oracle():
 @pytest.mark.parametrize("B,N,heads,mode,masked", [
     (1, 128, 1, "vones", False), (1, 128, 1, "quniform", False), (1, 128, 1, "random", False),
     (1, 256, 2, "random", False), (2, 300, 8, "random", True), (1, 40, 8, "random", True),
-    (8, 1050, 8, "random", True)])
+    (8, 1050, 8, "random", True), (5, 2100, 8, "random", True)])  # last two: several items per persistent CTA
 def test_enc_attn_fwd(B, N, heads, mode, masked):
     from tools import gpu_check
     assert gpu_check.attn_case(B, N, heads, mode, masked)
 
 
 @pytest.mark.parametrize("B,N,heads,masked", [(1, 128, 1, False), (1, 256, 2, False), (2, 300, 8, True),
-                                              (3, 54, 8, True), (8, 1050, 8, True)])
+                                              (3, 54, 8, True), (8, 1050, 8, True), (5, 2100, 8, True)])
 def test_enc_attn_bwd(B, N, heads, masked):
     from tools import gpu_check
     assert gpu_check.attn_bwd_case(B, N, heads, masked)
+
+
+@pytest.mark.parametrize("M,C,with_relu", [(800, 1024, True), (8400, 2048, True), (8400, 512, False), (37, 256, True)])
+def test_relu_bwd_colsum(M, C, with_relu):
+    """dpre = dy * (h > 0), dbias += colsum(dpre); both block shapes (short / FFN-sized) and the plain column sum."""
+    from object_detection_destr_b200 import ops
+    g = torch.Generator().manual_seed(M + C)
+    dy = torch.randn(M, C, generator=g).bfloat16()
+    h = torch.randn(M, C, generator=g).bfloat16().clamp(min=0) if with_relu else None
+    dbias = torch.full((C,), 0.5, dtype=torch.float32, device="cuda")
+    dpre = ops.relu_bwd_colsum(dy.cuda(), None if h is None else h.cuda(), dbias)
+    ref = dy.float() * (h.float() > 0) if with_relu else dy.float()
+    if with_relu:
+        assert torch.equal(dpre.cpu().float(), ref)
+    else:
+        assert dpre is None
+    exp = 0.5 + ref.sum(0)
+    assert torch.allclose(dbias.cpu(), exp, rtol=1e-4, atol=1e-2 * float(ref.abs().sum(0).max()) / M ** 0.5 + 1e-3)
+
+
+def test_sine_pos2d_wide_and_padded():
+    from oracle import destr_oracle as O
+    from object_detection_destr_b200 import ops
+    mask = torch.zeros(2, 50, 84, dtype=torch.bool)
+    mask[1, 40:, :] = True
+    mask[1, :, 70:] = True
+    pf, _ = ops.sine_pos2d(mask.cuda(), want_f32=True, want_bf16=False)
+    ref = O.sine_pos2d(mask).flatten(2).transpose(1, 2)
+    assert float((pf.cpu() - ref).abs().max()) < 2e-5
