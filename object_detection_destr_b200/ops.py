@@ -338,6 +338,18 @@ def dec_qkv_prep_bwd(d_qkv: Tensor, d_cat: Tensor, pairs: Tensor, B: int, Q: int
     return d_obj, d_pos
 
 
+def _bmm_aligned_k(a: Tensor, b: Tensor) -> Tensor:
+    """bmm(a [B,M,K], b [B,K,N]) whose contraction length K (= the token count, e.g. 1050) is not a multiple of 8:
+    cuBLAS would fall back to its slow 4-byte-aligned kernels for the whole product, so the bulk goes through the
+    16-byte-aligned kernels and the last K % 8 keys are a rank-(K % 8) update."""
+    K = a.shape[2]
+    r = K % 8
+    if r == 0 or K < 64:
+        return torch.bmm(a, b)
+    out = torch.bmm(a[:, :, :K - r], b[:, :K - r])
+    return out.baddbmm_(a[:, :, K - r:], b[:, K - r:])
+
+
 def split_cross_attn_bwd(q_obj: Tensor, q_pos: Tensor, k_enc: Tensor, k_pos: Tensor, v: Tensor, mask_bits: Tensor,
                          out: Tensor, dout: Tensor, lse: Tensor, B: int, Q: int, N: int,
                          dke_out: Optional[Tensor] = None, dkp_out: Optional[Tensor] = None,
@@ -369,8 +381,8 @@ def split_cross_attn_bwd(q_obj: Tensor, q_pos: Tensor, k_enc: Tensor, k_pos: Ten
     dv = _into(Pv.transpose(1, 2), do_v, dv_out)
     dke = _into(dSv.transpose(1, 2), qo_v, dke_out)
     dkp = _into(dSs.transpose(1, 2), qp_v, dkp_out)
-    dqo = torch.bmm(dSv, v3(k_enc)).view(B * Q, 512)
-    dqp = torch.bmm(dSs, v3(k_pos)).view(B * Q, 256)
+    dqo = _bmm_aligned_k(dSv, v3(k_enc)).view(B * Q, 512)
+    dqp = _bmm_aligned_k(dSs, v3(k_pos)).view(B * Q, 256)
     return dqo, dqp, dke, dkp, dv
 
 

@@ -285,7 +285,14 @@ class HotPathRuntime:
         self.bbox = bbox_embed
         self.Le, self.Ld = self.P.Le, self.P.Ld
         self.saved = None
+        self._bbox_cache = None
         self.anchor = torch.zeros(1, device=device, requires_grad=True)
+
+    def _bbox_bf16(self):
+        """bf16 copy of the box head's first layer, refreshed once per forward()."""
+        if self._bbox_cache is None:
+            self._bbox_cache = (self.bbox[0].weight.detach().to(BF16), self.bbox[0].bias.detach().to(BF16))
+        return self._bbox_cache
 
     # ------------------------------------------------------------------ encoder
     def _enc_fwd(self, l: int, x: Tensor, pos: Tensor, bits: Tensor, B: int, N: int):
@@ -360,14 +367,12 @@ class HotPathRuntime:
         with P.fork(_FORK["DEC_HEAD"], k=1):  # packed q|k|v object projection
             qkv_obj = torch.mm(x, P.w(f"d{l}.q_w", rows=1536).t())
         bp = self.bbox
-        # box refinement of the layer's queries: feeds ONLY the pairing (arg-max indices), its input is already bf16
-        # -> TF32 tensor-core GEMMs (10-bit mantissa, finer than the input rounding) instead of fp32 SIMT ones
-        tf32 = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = True
-        try:
-            delta = F.linear(torch.relu(F.linear(xr.float(), bp[0].weight, bp[0].bias)), bp[2].weight, bp[2].bias)
-        finally:
-            torch.backends.cuda.matmul.allow_tf32 = tf32
+        # box refinement of the layer's queries: feeds ONLY the pairing (arg-max indices) and its input is already bf16,
+        # so the 256x256 layer runs as a bf16 tensor-core GEMM (bias + ReLU fused) instead of an fp32 SIMT one; the
+        # 256 -> 4 output layer stays fp32
+        w0, b0 = self._bbox_bf16()
+        hbox = _mm_bias_relu(xr, w0, b0)
+        delta = F.linear(hbox.float(), bp[2].weight, bp[2].bias)
         coords = ops.box_refine(delta, centers)
         pairs = ops.pair_indices(coords.view(B, Q, 4)) if pairs_ov is None else pairs_ov
         P.join(1)
@@ -454,6 +459,7 @@ class HotPathRuntime:
         """x, pos bf16 [B*N,256]; sel bf16 [B*Q,512]; pos_embed, sine bf16 [B*Q,256]; centers fp32 [B*Q,2].
         Returns (dec_out bf16 [B*Q,512], enc_out bf16 [B*N,256])."""
         P, Ld = self.P, self.Ld
+        self._bbox_cache = None  # the box head is trained: re-cast it every step
         enc_saved = []
         for l in range(self.Le):
             x, sv = self._enc_fwd(l, x, pos, bits, B, N)

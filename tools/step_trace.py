@@ -1,0 +1,59 @@
+"""Kernel timeline of one graph-replayed training step (torch.profiler / CUPTI): per-kernel start, duration, stream.
+Prints the busy time per stream, the wall time of the step, and the largest gaps on the main stream."""
+import os, sys, json
+from argparse import Namespace
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import bench
+from torch.profiler import profile, ProfilerActivity
+from object_detection_destr_b200.encoder import disable_dropout
+from object_detection_destr_b200.engine import GraphedTrainStep
+from object_detection_destr_b200.hotpath import TransformerHalf
+
+cfg, B = bench.CFG, bench.CFG["B"]
+torch.manual_seed(0)
+model = TransformerHalf(Namespace(hidden_dim=256, num_encoder_blocks=cfg["L"], num_decoder_blocks=cfg["L"], num_cls=cfg["C"]))
+disable_dropout(model).cuda().train()
+opt = model.make_optimizer(lr=1e-5)
+eng = GraphedTrainStep(model, opt, B=B, H=cfg["H"], W=cfg["W"], Q=cfg["Q"], num_classes=cfg["C"], t_max=40)
+bt = bench.make_batch(0, 0, B)
+res = tuple(t.cuda() for t in bt[:4]) + (bt[4], bt[5])
+eng.load_batch(*res)
+eng.capture(warmup=3)
+for _ in range(5):
+    eng.step()
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    eng.step()
+    torch.cuda.synchronize()
+ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range is not None]
+ks = sorted(((e.time_range.start, e.time_range.end, e.name, getattr(e, "device_index", 0)) for e in ev), key=lambda t: t[0])
+ks = [k for k in ks if "Memcpy" not in k[2] and "Memset" not in k[2]] or ks
+t0, t1 = ks[0][0], max(k[1] for k in ks)
+print(f"kernels {len(ks)}  wall {(t1 - t0):.1f} us  sum {sum(k[1] - k[0] for k in ks):.1f} us")
+# coverage: time when at least one kernel runs / idle
+events = sorted([(k[0], 1) for k in ks] + [(k[1], -1) for k in ks])
+busy, depth, last = 0.0, 0, t0
+conc = {}
+for t, d in events:
+    if depth > 0:
+        busy += t - last
+    conc[depth] = conc.get(depth, 0.0) + (t - last)
+    depth += d
+    last = t
+print(f"busy (>=1 kernel) {busy:.1f} us, idle {(t1 - t0) - busy:.1f} us; time at concurrency: " +
+      ", ".join(f"{k}:{v:.0f}" for k, v in sorted(conc.items())))
+# per-name totals of time when the kernel was the ONLY one running (critical-path proxy)
+import collections
+solo = collections.defaultdict(float)
+cnt = collections.defaultdict(int)
+for i, k in enumerate(ks):
+    others = [o for o in ks if o is not k and o[0] < k[1] and o[1] > k[0]]
+    if not others:
+        n = k[2][:60]
+        solo[n] += k[1] - k[0]
+        cnt[n] += 1
+print("time running alone, by kernel:")
+for n, v in sorted(solo.items(), key=lambda kv: -kv[1])[:25]:
+    print(f"  {v:8.1f} us x{cnt[n]:3d}  {n}")
