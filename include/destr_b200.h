@@ -60,7 +60,13 @@ int destr_pos_mul_add_bwd_acc(const void* dy, const void* pos, const void* dx_in
  * With h = dpre = NULL it is a plain column sum of dy (bias gradient of a Linear without activation).
  * bf16 [M,C] operands with row pitches lddy/ldh/ldo. */
 int destr_relu_bwd_colsum(const void* dy, int lddy, const void* h, int ldh, void* dpre, int ldo, float* dbias, int M,
-                          int C, void* stream);
+                          int C, float scale, void* stream);
+/*   scale multiplies dpre: 1/(1-p) when a dropout followed the ReLU (h is then the DROPPED activation, whose zeros
+ *   already mask the dropped elements), else 1. */
+/* x <- dropout(x) in place, bf16 [M,C] with row pitch ld: the dropout that follows a fused GEMM+ReLU
+ * (encoder_block.py:108 dropout2; decoder_block.py:255). */
+int destr_dropout_inplace(void* x, int ld, int M, int C, const uint32_t* drop_seed, uint32_t drop_thr16,
+                          uint32_t drop_site, void* stream);
 /* y = a * b, bf16 (fine_pos = pos * pos_scale(enc_out), model.py:89-92; decoder_block.py:49) */
 int destr_mul_fwd(const void* a, const void* b, void* y, int64_t n_elem, void* stream);
 
@@ -70,15 +76,24 @@ int destr_mul_fwd(const void* a, const void* b, void* y, int64_t n_elem, void* s
  * normalised in place, decoder_block.py:185-187,218); b may be NULL; gamma/beta fp32 [D].
  * Saves mean/rstd (fp32 [M]) for the backward when the pointers are non-NULL. */
 int destr_add_layernorm_fwd(const void* a, int lda, const void* b, int ldb, const float* gamma, const float* beta,
-                            void* y, int ldy, float* mean, float* rstd, int M, int D, void* stream);
+                            void* y, int ldy, float* mean, float* rstd, int M, int D, const uint32_t* drop_seed,
+                            uint32_t drop_thr16, uint32_t drop_site, void* stream);
+/* DROPOUT ARGUMENTS (every entry point that has them): the reference's dropout sites (encoder_block.py:67-69,
+ * 104-109; decoder_block.py:132,182-184,234,253-256; self_attention.py:40) are applied INSIDE the kernels from a
+ * counter-based mask keep(seed, site, row, col): drop_seed = DEVICE pointer to a 32-bit seed (may change between
+ * CUDA-graph replays), drop_thr16 = round(p * 65536) (0 = no dropout), drop_site = id of the dropout call (the
+ * forward and the backward of one site must pass the same).  Kept values are scaled by 65536 / (65536 - thr16).
+ * Here: y = LN(a + dropout(b)). */
 /* backward of y = LN(a+b): dx (bf16, pitch lddx) = d(a+b); dgamma/dbeta fp32 [D] are ACCUMULATED into
  * (caller zeroes).  a+b is recomputed from a and b. */
 int destr_add_layernorm_bwd(const void* dy, int lddy, const void* a, int lda, const void* b, int ldb,
                             const float* gamma, const float* mean, const float* rstd, void* dx, int lddx,
                             float* dgamma, float* dbeta, float* dbias, const void* res_in, int ldri, void* res_out,
-                            int ldro, int M, int D, void* stream);
-/*   optional fusions: dbias (fp32 [D], accumulated) = column sum of dx = gradient of the bias of the Linear
- *   that produced b;  res_out = res_in + dx = gradient flowing on into the residual stream. */
+                            int ldro, int M, int D, const uint32_t* drop_seed, uint32_t drop_thr16,
+                            uint32_t drop_site, void* stream);
+/*   dx = gradient w.r.t. b (through b's dropout mask when one is active).  Optional fusions: dbias (fp32 [D],
+ *   accumulated) = column sum of dx = gradient of the bias of the Linear that produced b;  res_out = [res_in +]
+ *   d(a+b) = gradient flowing on into the residual stream (NOT masked; res_in may be NULL). */
 
 /* out = lam*LN1(x+o1) + (1-lam)*LN2(x+o2eff)  (decoder_block.py:182-184), D = 512, fused with the
  * head-group slot masking of PairSelfAttention (pair_self_attention.py:101-105):
@@ -87,7 +102,9 @@ int destr_add_layernorm_bwd(const void* dy, int lddy, const void* a, int lda, co
  * stats fp32 [M,4] = mean1,rstd1,mean2,rstd2 (saved for the backward, may be NULL). */
 int destr_dual_ln_mix_fwd(const void* x, const void* o1, const void* o2, const int32_t* pairs, const float* g1,
                           const float* b1, const float* g2, const float* b2, float lam, void* out, float* stats,
-                          int M, int Q, void* stream);
+                          int M, int Q, const uint32_t* drop_seed, uint32_t drop_thr16, uint32_t drop_site1,
+                          uint32_t drop_site2, void* stream);
+/*   dropout1(o1) uses drop_site1, dropout1(o2eff) drop_site2 (two independent masks, decoder_block.py:182-184) */
 /* backward: dx bf16 [M,512]; do1 bf16 [M,512] and do2 bf16 [M,1024] token-major, or (head_major = 1)
  * do1 [B,8,Q,64] and do2 [B,8,Q,128] as the attention backward wants them; dg1,db1,dg2,db2 fp32 [512] are
  * ACCUMULATED into.  With head_major, delta1/delta2 (fp32 [B,8,Q], may be NULL) receive rowsum(dO o O) per
@@ -95,7 +112,8 @@ int destr_dual_ln_mix_fwd(const void* x, const void* o1, const void* o2, const i
 int destr_dual_ln_mix_bwd(const void* dout, const void* x, const void* o1, const void* o2, const int32_t* pairs,
                           const float* g1, const float* g2, const float* stats, float lam, void* dx, void* do1,
                           void* do2, float* dg1, float* db1, float* dg2, float* db2, int M, int Q, int head_major,
-                          float* delta1, float* delta2, void* stream);
+                          float* delta1, float* delta2, const uint32_t* drop_seed, uint32_t drop_thr16,
+                          uint32_t drop_site1, uint32_t drop_site2, void* stream);
 
 /* ---------------- encoder multi-head self-attention (tcgen05) ---------------- */
 

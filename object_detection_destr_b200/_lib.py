@@ -18,7 +18,7 @@ if not os.path.exists(LIB_PATH):
 
 lib = C.CDLL(LIB_PATH)
 
-_p, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
+_p, _i, _f, _i64, _u = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_uint32
 
 # name -> argtypes; mirrors include/destr_b200.h one to one (tests/test_abi.py checks the header)
 SIGNATURES = {
@@ -30,15 +30,18 @@ SIGNATURES = {
     "destr_pos_mul_add_fwd": [_p, _p, _p, _p, _i64, _p],
     "destr_pos_mul_add_bwd": [_p, _p, _p, _i64, _p],
     "destr_mul_fwd": [_p, _p, _p, _i64, _p],
-    "destr_add_layernorm_fwd": [_p, _i, _p, _i, _p, _p, _p, _i, _p, _p, _i, _i, _p],
-    "destr_add_layernorm_bwd": [_p, _i, _p, _i, _p, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _p, _i, _i, _i, _p],
+    "destr_add_layernorm_fwd": [_p, _i, _p, _i, _p, _p, _p, _i, _p, _p, _i, _i, _p, _u, _u, _p],
+    "destr_add_layernorm_bwd": [_p, _i, _p, _i, _p, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _p, _i, _i, _i, _p, _u, _u,
+                                _p],
+    "destr_dropout_inplace": [_p, _i, _i, _i, _p, _u, _u, _p],
     "destr_pos_mul_add_bwd_acc": [_p, _p, _p, _p, _p, _i64, _p],
-    "destr_relu_bwd_colsum": [_p, _i, _p, _i, _p, _i, _p, _i, _i, _p],
+    "destr_relu_bwd_colsum": [_p, _i, _p, _i, _p, _i, _p, _i, _i, _f, _p],
     "destr_enc_attn_fwd": [_p, _p, _p, _i, _i, _i, _p, _i, _p, _p, _i, _i, _i, _f, _p],
     "destr_enc_attn_bwd": [_p, _p, _p, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i,
                            _f, _p],
-    "destr_dual_ln_mix_fwd": [_p, _p, _p, _p, _p, _p, _p, _p, _f, _p, _p, _i, _i, _p],
-    "destr_dual_ln_mix_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p],
+    "destr_dual_ln_mix_fwd": [_p, _p, _p, _p, _p, _p, _p, _p, _f, _p, _p, _i, _i, _p, _u, _u, _u, _p],
+    "destr_dual_ln_mix_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _u, _u,
+                              _u, _p],
     "destr_dec_qkv_prep": [_p, _p, _i, _p, _p, _p, _i, _i, _p],
     "destr_dec_self_pair_attn_fwd": [_p, _p, _p, _p, _p, _p, _i, _i, _p],
     "destr_split_cross_attn_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _p, _i, _p, _p, _p, _i, _i, _i, _f, _p],

@@ -39,3 +39,38 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace destr
+
+// ------------------------------------------------------------------------------------------------------
+// Dropout masks: counter-based, no state.  keep(seed, site, row, col) comes from one 32-bit mix hash per PAIR of
+// adjacent columns (even col -> low 16 bits, odd col -> high 16 bits); an element is KEPT when its 16 bits are
+// >= thr16 = round(p * 65536), and kept values are scaled by 65536 / (65536 - thr16).  `site` identifies the
+// dropout call (layer, position in the layer), `row`/`col` the element; forward and backward kernels recompute the
+// same mask from the same (seed, site), whatever their tiling.  oracle/dropout_mask.py is the numpy twin.
+// ------------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+namespace destr {
+__device__ __forceinline__ uint32_t drop_bits(uint32_t seed, uint32_t site, uint32_t row, uint32_t col_pair) {
+  uint32_t h = seed ^ (site * 0x9E3779B1u);
+  h ^= row * 0x85EBCA77u;
+  h ^= col_pair * 0xC2B2AE3Du;
+  h ^= h >> 16;
+  h *= 0x7FEB352Du;
+  h ^= h >> 15;
+  h *= 0x846CA68Bu;
+  h ^= h >> 16;
+  return h;
+}
+// keep flag of element (row, col)
+__device__ __forceinline__ bool drop_keep(uint32_t seed, uint32_t site, uint32_t row, uint32_t col, uint32_t thr16) {
+  const uint32_t b = drop_bits(seed, site, row, col >> 1);
+  return ((col & 1u) ? (b >> 16) : (b & 0xFFFFu)) >= thr16;
+}
+__host__ __device__ __forceinline__ float drop_scale(uint32_t thr16) { return 65536.f / (65536.f - (float)thr16); }
+// every dropout-capable entry point takes (const uint32_t* seed, uint32_t thr16, uint32_t site): `seed` is a DEVICE
+// pointer (so a CUDA graph replays with a fresh seed each step), thr16 = 0 disables dropout
+struct Drop {
+  const uint32_t* seed;
+  uint32_t thr16, site;
+};
+}  // namespace destr
+#endif

@@ -165,7 +165,7 @@ template <int CHUNKS>
 __global__ void __launch_bounds__(256)
 relu_bwd_colsum_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ h,
                        __nv_bfloat16* __restrict__ dpre, float* __restrict__ dbias, int M, int C, int lddy, int ldh,
-                       int ldo) {
+                       int ldo, float scale) {
   __shared__ float red[8][256];
   const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + cg * 8;
@@ -191,7 +191,7 @@ relu_bwd_colsum_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16
         if (row < M) {
           if (h) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) g[u].v[k] = a[u].v[k] > 0.f ? g[u].v[k] : 0.f;
+            for (int k = 0; k < 8; ++k) g[u].v[k] = a[u].v[k] > 0.f ? g[u].v[k] * scale : 0.f;
             st8(dpre + (size_t)row * ldo + col, g[u]);
           }
 #pragma unroll
@@ -209,6 +209,28 @@ relu_bwd_colsum_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16
 #pragma unroll
     for (int r = 0; r < 8; ++r) s += red[r][c];
     atomicAdd(dbias + blockIdx.x * 256 + c, s);
+  }
+}
+
+// x <- dropout(x) in place (the dropout after a fused GEMM+ReLU: encoder_block.py:108 dropout2, decoder_block.py:255):
+// thread = 8 consecutive channels of one row, one hash per channel pair
+__global__ void __launch_bounds__(256)
+dropout_inplace_kernel(__nv_bfloat16* __restrict__ x, int M, int C, int ld, Drop dp) {
+  const uint32_t seed = dp.seed ? *dp.seed : 0u;
+  const float s = drop_scale(dp.thr16);
+  const int c8 = C / 8;
+  const int64_t n = static_cast<int64_t>(M) * c8;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int row = static_cast<int>(i / c8), col = static_cast<int>(i - static_cast<int64_t>(row) * c8) * 8;
+    F8 v = ld8(x + static_cast<size_t>(row) * ld + col);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t bits = drop_bits(seed, dp.site, row, (col >> 1) + k);
+      v.v[2 * k] = ((bits & 0xFFFFu) >= dp.thr16) ? v.v[2 * k] * s : 0.f;
+      v.v[2 * k + 1] = ((bits >> 16) >= dp.thr16) ? v.v[2 * k + 1] * s : 0.f;
+    }
+    st8(x + static_cast<size_t>(row) * ld + col, v);
   }
 }
 
@@ -288,18 +310,29 @@ extern "C" int destr_pos_mul_add_bwd_acc(const void* dy, const void* pos, const 
 }
 
 extern "C" int destr_relu_bwd_colsum(const void* dy, int lddy, const void* h, int ldh, void* dpre, int ldo,
-                                     float* dbias, int M, int C, void* stream) {
+                                     float* dbias, int M, int C, float scale, void* stream) {
   DESTR_CHECK_ARG(dy && dbias && M > 0 && C > 0 && C % 8 == 0 && lddy % 8 == 0, "shape");
   DESTR_CHECK_ARG((h == nullptr) == (dpre == nullptr), "h and dpre go together (both NULL = plain column sum)");
   if (static_cast<int64_t>(M) * C >= (1 << 22)) {  // FFN-sized: fewer, longer blocks (atomics on dbias bound the short ones)
     dim3 grid(ceil_div(C, 256), ceil_div(M, kRowsPerChunk * 4));
     relu_bwd_colsum_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)dy, (const __nv_bfloat16*)h, (__nv_bfloat16*)dpre, dbias, M, C, lddy, ldh, ldo);
+        (const __nv_bfloat16*)dy, (const __nv_bfloat16*)h, (__nv_bfloat16*)dpre, dbias, M, C, lddy, ldh, ldo, scale);
   } else {
     dim3 grid(ceil_div(C, 256), ceil_div(M, kRowsPerChunk));
     relu_bwd_colsum_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)dy, (const __nv_bfloat16*)h, (__nv_bfloat16*)dpre, dbias, M, C, lddy, ldh, ldo);
+        (const __nv_bfloat16*)dy, (const __nv_bfloat16*)h, (__nv_bfloat16*)dpre, dbias, M, C, lddy, ldh, ldo, scale);
   }
+  DESTR_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int destr_dropout_inplace(void* x, int ld, int M, int C, const uint32_t* drop_seed, uint32_t drop_thr16,
+                                     uint32_t drop_site, void* stream) {
+  DESTR_CHECK_ARG(x && M > 0 && C > 0 && C % 8 == 0 && ld % 8 == 0 && ld >= C, "shape");
+  if (drop_thr16 == 0) return 0;
+  const int64_t n = static_cast<int64_t>(M) * (C / 8);
+  dropout_inplace_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      (__nv_bfloat16*)x, M, C, ld, destr::Drop{drop_seed, drop_thr16, drop_site});
   DESTR_LAUNCH_CHECK();
   return 0;
 }

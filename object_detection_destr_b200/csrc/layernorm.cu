@@ -65,6 +65,21 @@ __device__ __forceinline__ Row<VPL> ld_vec(const float* base, int lane) {
   return r;
 }
 
+// dropout on a row in the lane ownership above: value c*8+i <-> column (c*32+lane)*8+i; one hash per column pair
+template <int VPL>
+__device__ __forceinline__ void drop_row(Row<VPL>& r, uint32_t seed, uint32_t site, uint32_t row, int lane,
+                                         uint32_t thr16, float s) {
+#pragma unroll
+  for (int c = 0; c < VPL / 8; ++c)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t col = (c * 32 + lane) * 8 + 2 * i;
+      const uint32_t bits = drop_bits(seed, site, row, col >> 1);
+      r.v[c * 8 + 2 * i] = ((bits & 0xFFFFu) >= thr16) ? r.v[c * 8 + 2 * i] * s : 0.f;
+      r.v[c * 8 + 2 * i + 1] = ((bits >> 16) >= thr16) ? r.v[c * 8 + 2 * i + 1] * s : 0.f;
+    }
+}
+
 template <int VPL>
 __device__ __forceinline__ void row_stats(const Row<VPL>& x, float& mean, float& rstd) {
   constexpr float invD = 1.0f / (VPL * 32);
@@ -85,14 +100,18 @@ template <int VPL>
 __global__ void __launch_bounds__(256)
 add_ln_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
                   const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
-                  float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int lda, int ldb, int ldy) {
+                  float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int lda, int ldb, int ldy,
+                  Drop dp) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const Row<VPL> g = ld_vec<VPL>(gamma, lane), be = ld_vec<VPL>(beta, lane);
+  const uint32_t seed = (dp.thr16 && dp.seed) ? *dp.seed : 0u;
+  const float ds = drop_scale(dp.thr16);
   for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += gridDim.x * wpb) {
     Row<VPL> x = ld_row<VPL>(a + (size_t)row * lda, lane);
     if (b) {
-      const Row<VPL> r2 = ld_row<VPL>(b + (size_t)row * ldb, lane);
+      Row<VPL> r2 = ld_row<VPL>(b + (size_t)row * ldb, lane);
+      if (dp.thr16) drop_row<VPL>(r2, seed, dp.site, row, lane, dp.thr16, ds);  // y = LN(a + dropout(b))
 #pragma unroll
       for (int i = 0; i < VPL; ++i) x.v[i] += r2.v[i];
     }
@@ -116,7 +135,8 @@ add_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __r
                   const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                   __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int M,
                   int lddy, int lda, int ldb, int lddx, float* __restrict__ dbias,
-                  const __nv_bfloat16* __restrict__ res_in, __nv_bfloat16* __restrict__ res_out, int ldri, int ldro) {
+                  const __nv_bfloat16* __restrict__ res_in, __nv_bfloat16* __restrict__ res_out, int ldri, int ldro,
+                  Drop dp) {
   constexpr int D = VPL * 32;
   constexpr float invD = 1.0f / D;
   __shared__ float red[3][8][D];  // [dgamma|dbeta|dbias][warp][channel]  (<= 48 KB at D=512)
@@ -124,13 +144,16 @@ add_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __r
   const int warp = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
   const Row<VPL> g = ld_vec<VPL>(gamma, lane);
+  const uint32_t seed = (dp.thr16 && dp.seed) ? *dp.seed : 0u;
+  const float ds = drop_scale(dp.thr16);
   Row<VPL> accg, accb, accx;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) accg.v[i] = accb.v[i] = accx.v[i] = 0.f;
   for (int row = blockIdx.x * wpb + warp; row < M; row += gridDim.x * wpb) {
     Row<VPL> x = ld_row<VPL>(a + (size_t)row * lda, lane);
     if (b) {
-      const Row<VPL> r2 = ld_row<VPL>(b + (size_t)row * ldb, lane);
+      Row<VPL> r2 = ld_row<VPL>(b + (size_t)row * ldb, lane);
+      if (dp.thr16) drop_row<VPL>(r2, seed, dp.site, row, lane, dp.thr16, ds);
 #pragma unroll
       for (int i = 0; i < VPL; ++i) x.v[i] += r2.v[i];
     }
@@ -148,17 +171,20 @@ add_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __r
     }
     s1 = warp_sum(s1) * invD;
     s2 = warp_sum(s2) * invD;
-    Row<VPL> o;
+    Row<VPL> o;  // gradient w.r.t. the LayerNorm input (a + dropout(b)): what flows into the residual stream `a`
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      o.v[i] = rstd * (d.v[i] * g.v[i] - s1 - x.v[i] * s2);
-      accx.v[i] += o.v[i];
-    }
-    st_row<VPL>(dx + (size_t)row * lddx, lane, o);
-    if (res_out) {  // res_out = res_in + dx  (gradient of the residual stream)
-      const Row<VPL> r = ld_row<VPL>(res_in + (size_t)row * ldri, lane);
+    for (int i = 0; i < VPL; ++i) o.v[i] = rstd * (d.v[i] * g.v[i] - s1 - x.v[i] * s2);
+    Row<VPL> ob = o;  // gradient w.r.t. b: the same, through the dropout mask
+    if (dp.thr16) drop_row<VPL>(ob, seed, dp.site, row, lane, dp.thr16, ds);
 #pragma unroll
-      for (int i = 0; i < VPL; ++i) o.v[i] += r.v[i];
+    for (int i = 0; i < VPL; ++i) accx.v[i] += ob.v[i];
+    st_row<VPL>(dx + (size_t)row * lddx, lane, ob);
+    if (res_out) {  // res_out = [res_in +] d(a)  (gradient of the residual stream)
+      if (res_in) {
+        const Row<VPL> r = ld_row<VPL>(res_in + (size_t)row * ldri, lane);
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) o.v[i] += r.v[i];
+      }
       st_row<VPL>(res_out + (size_t)row * ldro, lane, o);
     }
   }
@@ -197,12 +223,14 @@ dual_ln_mix_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
                        const __nv_bfloat16* __restrict__ o2, const int32_t* __restrict__ pairs,
                        const float* __restrict__ g1, const float* __restrict__ b1, const float* __restrict__ g2,
                        const float* __restrict__ b2, float lam, __nv_bfloat16* __restrict__ out,
-                       float* __restrict__ stats, int M, int Q) {
+                       float* __restrict__ stats, int M, int Q, Drop dp, uint32_t site2) {
   constexpr int VPL = 16, D = 512;
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const Row<VPL> G1 = ld_vec<VPL>(g1, lane), B1 = ld_vec<VPL>(b1, lane);
   const Row<VPL> G2 = ld_vec<VPL>(g2, lane), B2 = ld_vec<VPL>(b2, lane);
+  const uint32_t seed = (dp.thr16 && dp.seed) ? *dp.seed : 0u;
+  const float ds = drop_scale(dp.thr16);
   for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += gridDim.x * wpb) {
     const int i = row % Q;
     const float k0 = pairs[2 * row] == i ? 1.f : 0.f, k1 = pairs[2 * row + 1] == i ? 1.f : 0.f;
@@ -212,9 +240,15 @@ dual_ln_mix_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
     const Row<VPL> c = ld_row<VPL>(o2 + (size_t)row * 2 * D + D, lane);
     Row<VPL> w;
 #pragma unroll
+    for (int e = 0; e < VPL; ++e) w.v[e] = k0 * a.v[e] + k1 * c.v[e];
+    if (dp.thr16) {  // dropout1(o1), dropout1(o2): two independent masks (decoder_block.py:182-184)
+      drop_row<VPL>(u, seed, dp.site, row, lane, dp.thr16, ds);
+      drop_row<VPL>(w, seed, site2, row, lane, dp.thr16, ds);
+    }
+#pragma unroll
     for (int e = 0; e < VPL; ++e) {
       u.v[e] += xr.v[e];
-      w.v[e] = xr.v[e] + (k0 * a.v[e] + k1 * c.v[e]);
+      w.v[e] += xr.v[e];
     }
     float m1, r1, m2, r2;
     row_stats<VPL>(u, m1, r1);
@@ -239,13 +273,15 @@ dual_ln_mix_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat
                        __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ do1,
                        __nv_bfloat16* __restrict__ do2, float* __restrict__ dg1, float* __restrict__ db1,
                        float* __restrict__ dg2, float* __restrict__ db2, int M, int Q, int head_major,
-                       float* __restrict__ delta1, float* __restrict__ delta2) {
+                       float* __restrict__ delta1, float* __restrict__ delta2, Drop dp, uint32_t site2) {
   constexpr int VPL = 16, D = 512;
   constexpr float invD = 1.0f / D;
   extern __shared__ float red[];  // [4][warps][D]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
   const Row<VPL> G1 = ld_vec<VPL>(g1, lane), G2 = ld_vec<VPL>(g2, lane);
+  const uint32_t seed = (dp.thr16 && dp.seed) ? *dp.seed : 0u;
+  const float ds = drop_scale(dp.thr16);
   Row<VPL> ag1, ab1, ag2, ab2;
 #pragma unroll
   for (int e = 0; e < VPL; ++e) ag1.v[e] = ab1.v[e] = ag2.v[e] = ab2.v[e] = 0.f;
@@ -260,11 +296,17 @@ dual_ln_mix_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat
     const Row<VPL> d = ld_row<VPL>(dout + (size_t)row * D, lane);
     const float4 st = reinterpret_cast<const float4*>(stats)[row];
     Row<VPL> w;
+#pragma unroll
+    for (int e = 0; e < VPL; ++e) w.v[e] = k0 * a.v[e] + k1 * c.v[e];
+    if (dp.thr16) {
+      drop_row<VPL>(u, seed, dp.site, row, lane, dp.thr16, ds);
+      drop_row<VPL>(w, seed, site2, row, lane, dp.thr16, ds);
+    }
     float s11 = 0.f, s12 = 0.f, s21 = 0.f, s22 = 0.f;
 #pragma unroll
     for (int e = 0; e < VPL; ++e) {
       u.v[e] = (u.v[e] + xr.v[e] - st.x) * st.y;                                   // xhat1
-      w.v[e] = (xr.v[e] + (k0 * a.v[e] + k1 * c.v[e]) - st.z) * st.w;              // xhat2
+      w.v[e] = (xr.v[e] + w.v[e] - st.z) * st.w;                                   // xhat2
       const float d1 = lam * d.v[e], d2 = (1.f - lam) * d.v[e];
       const float gy1 = d1 * G1.v[e], gy2 = d2 * G2.v[e];
       s11 += gy1; s12 = fmaf(gy1, u.v[e], s12);
@@ -280,6 +322,13 @@ dual_ln_mix_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat
       r1.v[e] = st.y * (lam * d.v[e] * G1.v[e] - s11 - u.v[e] * s12);
       r2.v[e] = st.w * ((1.f - lam) * d.v[e] * G2.v[e] - s21 - w.v[e] * s22);
       rx.v[e] = r1.v[e] + r2.v[e];
+    }
+    if (dp.thr16) {  // gradients w.r.t. o1 / o2 pass through their dropout masks; dx (residual) does not
+      drop_row<VPL>(r1, seed, dp.site, row, lane, dp.thr16, ds);
+      drop_row<VPL>(r2, seed, site2, row, lane, dp.thr16, ds);
+    }
+#pragma unroll
+    for (int e = 0; e < VPL; ++e) {
       ra.v[e] = k0 * r2.v[e];
       rc.v[e] = k1 * r2.v[e];
     }
@@ -363,8 +412,11 @@ inline int ln_grid(int M) {
 
 using namespace destr;
 
+#define DESTR_DROP(seed, thr, site) destr::Drop{(seed), (thr), (site)}
+
 extern "C" int destr_add_layernorm_fwd(const void* a, int lda, const void* b, int ldb, const float* gamma,
                                        const float* beta, void* y, int ldy, float* mean, float* rstd, int M, int D,
+                                       const uint32_t* drop_seed, uint32_t drop_thr16, uint32_t drop_site,
                                        void* stream) {
   DESTR_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && ldy % 8 == 0 && lda >= D && ldy >= D, "row pitch");
   DESTR_CHECK_ARG(a && gamma && beta && y && M > 0, "null pointer / shape");
@@ -373,10 +425,12 @@ extern "C" int destr_add_layernorm_fwd(const void* a, int lda, const void* b, in
   cudaStream_t st = (cudaStream_t)stream;
   if (D == 256)
     add_ln_fwd_kernel<8><<<ln_grid(M), 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, gamma, beta,
-                                                     (__nv_bfloat16*)y, mean, rstd, M, lda, ldb, ldy);
+                                                     (__nv_bfloat16*)y, mean, rstd, M, lda, ldb, ldy,
+                                                     DESTR_DROP(drop_seed, drop_thr16, drop_site));
   else
     add_ln_fwd_kernel<16><<<ln_grid(M), 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, gamma, beta,
-                                                      (__nv_bfloat16*)y, mean, rstd, M, lda, ldb, ldy);
+                                                      (__nv_bfloat16*)y, mean, rstd, M, lda, ldb, ldy,
+                                                      DESTR_DROP(drop_seed, drop_thr16, drop_site));
   DESTR_LAUNCH_CHECK();
   return 0;
 }
@@ -384,10 +438,11 @@ extern "C" int destr_add_layernorm_fwd(const void* a, int lda, const void* b, in
 extern "C" int destr_add_layernorm_bwd(const void* dy, int lddy, const void* a, int lda, const void* b, int ldb,
                                        const float* gamma, const float* mean, const float* rstd, void* dx, int lddx,
                                        float* dgamma, float* dbeta, float* dbias, const void* res_in, int ldri,
-                                       void* res_out, int ldro, int M, int D, void* stream) {
+                                       void* res_out, int ldro, int M, int D, const uint32_t* drop_seed,
+                                       uint32_t drop_thr16, uint32_t drop_site, void* stream) {
   DESTR_CHECK_ARG(lddy % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && lddx % 8 == 0 && ldri % 8 == 0 && ldro % 8 == 0,
                   "row pitch");
-  DESTR_CHECK_ARG((res_in == nullptr) == (res_out == nullptr), "res_in and res_out go together");
+  DESTR_CHECK_ARG(res_in == nullptr || res_out != nullptr, "res_in needs res_out");
   DESTR_CHECK_ARG(dy && a && gamma && mean && rstd && dx && dgamma && dbeta && M > 0, "null pointer / shape");
   DESTR_CHECK_ARG(D == 256 || D == 512, "D must be 256 or 512");
   cudaStream_t st = (cudaStream_t)stream;
@@ -397,22 +452,25 @@ extern "C" int destr_add_layernorm_bwd(const void* dy, int lddy, const void* a, 
   if (D == 256)
     add_ln_bwd_kernel<8><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)a,
                                                (const __nv_bfloat16*)b, gamma, mean, rstd, (__nv_bfloat16*)dx, dgamma,
-                                               dbeta, M, lddy, lda, ldb, lddx, dbias, ri, ro, ldri, ldro);
+                                               dbeta, M, lddy, lda, ldb, lddx, dbias, ri, ro, ldri, ldro,
+                                               DESTR_DROP(drop_seed, drop_thr16, drop_site));
   else
     add_ln_bwd_kernel<16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)a,
                                                 (const __nv_bfloat16*)b, gamma, mean, rstd, (__nv_bfloat16*)dx, dgamma,
-                                                dbeta, M, lddy, lda, ldb, lddx, dbias, ri, ro, ldri, ldro);
+                                                dbeta, M, lddy, lda, ldb, lddx, dbias, ri, ro, ldri, ldro,
+                                                DESTR_DROP(drop_seed, drop_thr16, drop_site));
   DESTR_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int destr_dual_ln_mix_fwd(const void* x, const void* o1, const void* o2, const int32_t* pairs,
                                      const float* g1, const float* b1, const float* g2, const float* b2, float lam,
-                                     void* out, float* stats, int M, int Q, void* stream) {
+                                     void* out, float* stats, int M, int Q, const uint32_t* drop_seed,
+                                     uint32_t drop_thr16, uint32_t drop_site1, uint32_t drop_site2, void* stream) {
   DESTR_CHECK_ARG(x && o1 && o2 && pairs && g1 && b1 && g2 && b2 && out && M > 0 && Q > 0, "null pointer / shape");
   dual_ln_mix_fwd_kernel<<<ln_grid(M), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)x, (const __nv_bfloat16*)o1, (const __nv_bfloat16*)o2, pairs, g1, b1, g2, b2, lam,
-      (__nv_bfloat16*)out, stats, M, Q);
+      (__nv_bfloat16*)out, stats, M, Q, DESTR_DROP(drop_seed, drop_thr16, drop_site1), drop_site2);
   DESTR_LAUNCH_CHECK();
   return 0;
 }
@@ -421,7 +479,8 @@ extern "C" int destr_dual_ln_mix_bwd(const void* dout, const void* x, const void
                                      const int32_t* pairs, const float* g1, const float* g2, const float* stats,
                                      float lam, void* dx, void* do1, void* do2, float* dg1, float* db1, float* dg2,
                                      float* db2, int M, int Q, int head_major, float* delta1, float* delta2,
-                                     void* stream) {
+                                     const uint32_t* drop_seed, uint32_t drop_thr16, uint32_t drop_site1,
+                                     uint32_t drop_site2, void* stream) {
   DESTR_CHECK_ARG(dout && x && o1 && o2 && pairs && g1 && g2 && stats && dx && do1 && do2 && dg1 && db1 && dg2 && db2,
                   "null pointer");
   DESTR_CHECK_ARG((delta1 == nullptr) == (delta2 == nullptr) && (!delta1 || head_major), "delta needs head_major");
@@ -431,7 +490,7 @@ extern "C" int destr_dual_ln_mix_bwd(const void* dout, const void* x, const void
   dual_ln_mix_bwd_kernel<<<grid, threads, 4 * 4 * 512 * sizeof(float), (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)dout, (const __nv_bfloat16*)x, (const __nv_bfloat16*)o1, (const __nv_bfloat16*)o2, pairs,
       g1, g2, stats, lam, (__nv_bfloat16*)dx, (__nv_bfloat16*)do1, (__nv_bfloat16*)do2, dg1, db1, dg2, db2, M, Q,
-      head_major, delta1, delta2);
+      head_major, delta1, delta2, DESTR_DROP(drop_seed, drop_thr16, drop_site1), drop_site2);
   DESTR_LAUNCH_CHECK();
   return 0;
 }

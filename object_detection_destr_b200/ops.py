@@ -29,6 +29,18 @@ def _chk(t: Tensor, dtype, name: str) -> Tensor:
     return t
 
 
+def _dargs(drop):
+    """drop = None | (seed int32/uint32 device tensor [1], thr16, site[, site2]) -> C arguments (seed ptr, thr16, site...)."""
+    if drop is None or drop[1] == 0:
+        return None, 0, 0
+    return drop[0].data_ptr(), int(drop[1]), int(drop[2])
+
+
+def drop_thr16(p: float) -> int:
+    """probability -> 16-bit threshold of the kernels' keep test (kept values are scaled by 65536/(65536-thr16))."""
+    return int(round(float(p) * 65536.0))
+
+
 def _ptr(t: Optional[Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -108,8 +120,8 @@ def _rows(t: Tensor, dtype, name: str, D: int) -> Tensor:
 
 
 def add_layernorm(a: Tensor, b: Optional[Tensor], gamma: Tensor, beta: Tensor, save_stats: bool = False,
-                  out: Optional[Tensor] = None):
-    """y = LN(a + b).  a, b (and `out`, if given) may be strided [M, D] views."""
+                  out: Optional[Tensor] = None, drop=None):
+    """y = LN(a + dropout(b)).  a, b (and `out`, if given) may be strided [M, D] views; drop: see _dargs."""
     D = a.shape[-1]
     a = _rows(a, BF16, "a", D)
     M = a.shape[0]
@@ -120,16 +132,17 @@ def add_layernorm(a: Tensor, b: Optional[Tensor], gamma: Tensor, beta: Tensor, s
     mean = torch.empty(M, dtype=torch.float32, device=a.device) if save_stats else None
     rstd = torch.empty(M, dtype=torch.float32, device=a.device) if save_stats else None
     _lib.call("destr_add_layernorm_fwd", a.data_ptr(), a.stride(0), _ptr(b), 0 if b is None else b.stride(0),
-              g.data_ptr(), be.data_ptr(), y.data_ptr(), y.stride(0), _ptr(mean), _ptr(rstd), M, D, _stream())
+              g.data_ptr(), be.data_ptr(), y.data_ptr(), y.stride(0), _ptr(mean), _ptr(rstd), M, D, *_dargs(drop), _stream())
     return (y, mean, rstd) if save_stats else y
 
 
 def add_layernorm_bwd(dy: Tensor, a: Tensor, b: Optional[Tensor], gamma: Tensor, mean: Tensor, rstd: Tensor,
                       dgamma: Optional[Tensor] = None, dbeta: Optional[Tensor] = None, dbias: Optional[Tensor] = None,
                       res_in: Optional[Tensor] = None, dx_out: Optional[Tensor] = None,
-                      res_out: Optional[Tensor] = None):
-    """dx = d(a+b).  dgamma/dbeta/dbias (fp32 [D]) are accumulated into when given (else fresh zeros for
-    dgamma/dbeta).  res_in: returns additionally res_out = res_in + dx."""
+                      res_out: Optional[Tensor] = None, drop=None, want_sum: bool = False):
+    """dx = gradient w.r.t. b (through b's dropout mask, if any).  dgamma/dbeta/dbias (fp32 [D]) are accumulated into
+    when given (else fresh zeros for dgamma/dbeta).  res_in (or want_sum): returns additionally
+    res_out = [res_in +] d(a+b), the un-masked gradient of the residual stream."""
     D = a.shape[-1]
     dy = _rows(dy, BF16, "dy", D)
     a = _rows(a, BF16, "a", D)
@@ -142,12 +155,14 @@ def add_layernorm_bwd(dy: Tensor, a: Tensor, b: Optional[Tensor], gamma: Tensor,
     ro = None
     if res_in is not None:
         res_in = _rows(res_in, BF16, "res_in", D)
+    if res_in is not None or want_sum:
         ro = torch.empty(M, D, dtype=BF16, device=a.device) if res_out is None else res_out
     _lib.call("destr_add_layernorm_bwd", dy.data_ptr(), dy.stride(0), a.data_ptr(), a.stride(0), _ptr(b),
               0 if b is None else b.stride(0), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(),
               dx.stride(0), dg.data_ptr(), db.data_ptr(), _ptr(dbias), _ptr(res_in),
-              0 if res_in is None else res_in.stride(0), _ptr(ro), 0 if ro is None else ro.stride(0), M, D, _stream())
-    if res_in is not None:
+              0 if res_in is None else res_in.stride(0), _ptr(ro), 0 if ro is None else ro.stride(0), M, D,
+              *_dargs(drop), _stream())
+    if ro is not None:
         return dx, dg, db, ro
     return dx, dg, db
 
@@ -160,14 +175,24 @@ def pos_mul_add_bwd_acc(dy: Tensor, pos: Tensor, dx_in: Tensor):
     return ds, dx_out
 
 
-def relu_bwd_colsum(dy: Tensor, h: Optional[Tensor], dbias: Tensor) -> Optional[Tensor]:
-    """dpre = dy*(h>0) (returned), dbias += colsum(dpre).  h=None: dbias += colsum(dy), returns None.
+def relu_bwd_colsum(dy: Tensor, h: Optional[Tensor], dbias: Tensor, scale: float = 1.0) -> Optional[Tensor]:
+    """dpre = scale*dy*(h>0) (returned), dbias += colsum(dpre).  h=None: dbias += colsum(dy), returns None.
+    scale = 1/(1-p) when h is a dropped post-ReLU activation (its zeros carry the dropout mask).
     dy, h: bf16 [M,C] views with unit column stride."""
     M, C = dy.shape
     dpre = torch.empty(M, C, dtype=BF16, device=dy.device) if h is not None else None
     _lib.call("destr_relu_bwd_colsum", dy.data_ptr(), dy.stride(0), _ptr(h), 0 if h is None else h.stride(0),
-              _ptr(dpre), C, dbias.data_ptr(), M, C, _stream())
+              _ptr(dpre), C, dbias.data_ptr(), M, C, float(scale), _stream())
     return dpre
+
+
+def dropout_inplace(x: Tensor, drop) -> Tensor:
+    """x <- dropout(x) in place (bf16 [M,C], unit column stride); drop: see _dargs."""
+    ptr, thr, site = _dargs(drop)
+    if thr:
+        _chk(x, BF16, "x")
+        _lib.call("destr_dropout_inplace", x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], ptr, thr, site, _stream())
+    return x
 
 
 # ----------------------------------------------------------------------------------------------
@@ -251,18 +276,19 @@ def dec_self_pair_attn_fwd(qkv: Tensor, cat: Tensor, B: int, Q: int, need_lse: b
 
 
 def dual_ln_mix(x: Tensor, o1: Tensor, o2: Tensor, pairs: Tensor, g1, b1, g2, b2, lam: float, Q: int,
-                save_stats: bool = True):
+                save_stats: bool = True, drop=None):
     x, o1, o2 = (_chk(t.contiguous(), BF16, n) for t, n in ((x, "x"), (o1, "o1"), (o2, "o2")))
     M = x.shape[0]
     out = torch.empty_like(x)
     stats = torch.empty(M, 4, dtype=torch.float32, device=x.device) if save_stats else None
     _lib.call("destr_dual_ln_mix_fwd", x.data_ptr(), o1.data_ptr(), o2.data_ptr(), pairs.data_ptr(), g1.data_ptr(),
-              b1.data_ptr(), g2.data_ptr(), b2.data_ptr(), float(lam), out.data_ptr(), _ptr(stats), M, Q, _stream())
+              b1.data_ptr(), g2.data_ptr(), b2.data_ptr(), float(lam), out.data_ptr(), _ptr(stats), M, Q,
+              *_dargs(drop), 0 if drop is None else int(drop[3]), _stream())
     return out, stats
 
 
 def dual_ln_mix_bwd(dout: Tensor, x: Tensor, o1: Tensor, o2: Tensor, pairs: Tensor, g1, g2, stats, lam: float, Q: int,
-                    pg: Optional[Sequence[Tensor]] = None, head_major: bool = False):
+                    pg: Optional[Sequence[Tensor]] = None, head_major: bool = False, drop=None):
     """pg: optional (dg1, db1, dg2, db2) fp32 [512] buffers to ACCUMULATE the parameter gradients into.
     head_major: do1 -> [B,8,Q,64], do2 -> [B,8,Q,128] and additionally returns (delta1, delta2) fp32 [B,8,Q]."""
     dout = _chk(dout.contiguous(), BF16, "dout")
@@ -281,7 +307,8 @@ def dual_ln_mix_bwd(dout: Tensor, x: Tensor, o1: Tensor, o2: Tensor, pairs: Tens
               g1.data_ptr(), g2.data_ptr(), stats.data_ptr(), float(lam), dx.data_ptr(), do1.data_ptr(),
               do2.data_ptr(), pg[0].data_ptr(), pg[1].data_ptr(), pg[2].data_ptr(), pg[3].data_ptr(), M, Q,
               int(head_major), None if delta is None else delta[0].data_ptr(),
-              None if delta is None else delta[1].data_ptr(), _stream())
+              None if delta is None else delta[1].data_ptr(), *_dargs(drop), 0 if drop is None else int(drop[3]),
+              _stream())
     if head_major:
         return dx, do1, do2, delta[0], delta[1]
     return dx, do1, do2, pg[0], pg[1], pg[2], pg[3]
