@@ -129,7 +129,10 @@ int destr_dual_ln_mix_bwd(const void* dout, const void* x, const void* o1, const
  * d_head is fixed at 32, heads*32 <= 256.  Needs sm_100a (tcgen05/TMEM/TMA). */
 int destr_enc_attn_fwd(const void* q, const void* k, const void* v, int ld_q, int ld_k, int ld_v,
                        const uint32_t* mask_bits, int words_per_row, void* out, float* lse, int B, int N,
-                       int heads, float scale, void* stream);
+                       int heads, float scale, const uint32_t* drop_seed, uint32_t drop_thr16, uint32_t drop_site,
+                       void* stream);
+/*   dropout (see destr_add_layernorm_fwd) acts on the attention probabilities, as nn.MultiheadAttention(dropout=p)
+ *   does in training: mask row = (b*heads + h)*N + query, column = key; the softmax denominator is not dropped. */
 /* backward: dq, dk, dv bf16 with the same row pitches as q, k, v (ld_dq, ld_dk, ld_dv).
  * Caller-provided workspaces: stats (fp32, destr_enc_attn_bwd_stats_floats(B,N,heads) elements: -lse and
  * -delta = -rowsum(dO o O), padded to 128-query tiles) and dq_acc (fp32 [B*N, heads*32]). */
@@ -137,7 +140,8 @@ int destr_enc_attn_bwd_stats_floats(int B, int N, int heads);
 int destr_enc_attn_bwd(const void* q, const void* k, const void* v, int ld_q, int ld_k, int ld_v,
                        const uint32_t* mask_bits, int words_per_row, const void* out, const void* dout,
                        const float* lse, float* stats, float* dq_acc, void* dq, void* dk, void* dv, int ld_dq,
-                       int ld_dk, int ld_dv, int B, int N, int heads, float scale, void* stream);
+                       int ld_dk, int ld_dv, int B, int N, int heads, float scale, const uint32_t* drop_seed,
+                       uint32_t drop_thr16, uint32_t drop_site, void* stream);
 
 /* ---------------- decoder: pairing, self + pair attention, split cross-attention ---------------- */
 

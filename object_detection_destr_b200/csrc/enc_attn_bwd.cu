@@ -80,13 +80,14 @@ __device__ __forceinline__ Item decode_item(int w, int nkt, int heads) {
   return it;
 }
 
-template <int POLYQ>
+template <int POLYQ, bool DROP>
 __global__ void __launch_bounds__(NTHREADS, 1)
 enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
                     const uint32_t* __restrict__ mask_bits, int words_per_row, const float* __restrict__ stats,
                     float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv,
-                    int ld_dk, int ld_dv, int N, int heads, int n_items, float scale, float scale_log2, Knobs kn) {
+                    int ld_dk, int ld_dv, int N, int heads, int n_items, float scale, float scale_log2, Knobs kn,
+                    Drop dp) {
   extern __shared__ uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -288,6 +289,8 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const uint32_t t_st = tmem + lane_addr + g * C_SBUF + C_ST + cg * 32;
     const uint32_t t_pt = tmem + lane_addr + C_PT + g * 32 + cg * 16;
     const uint32_t swz = krow & 7;
+    const uint32_t drop_seed = (DROP && dp.seed) ? *dp.seed : 0u;
+    const float drop_s = drop_scale(dp.thr16);
 
     Item prev{0, 0, 0};
     uint32_t Pf = 0;
@@ -295,8 +298,10 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       const Item im = decode_item(blockIdx.x + it * gridDim.x, nkt, heads);
       const int key = im.j * BT + krow;
       const bool key_masked = (mask_bits[static_cast<size_t>(im.b) * words_per_row + (key >> 5)] >> (key & 31)) & 1u;
+      const uint32_t drop_row0 = static_cast<uint32_t>(im.b * heads + im.h) * N;
       for (int p = 0; p < npairs; ++p, ++Pf) {
         const uint32_t U = 2 * Pf + g, s = U % QSTAGES, pb = Pf & 1;
+        const uint32_t qcol0 = (2 * p + g) * BQ + cg * 32;  // first query column of this thread in the sub-tile
         mbar_wait_a(b_sdp, Pf & 1, 10);
         mbar_wait_a(b_qfull + s * 8, (U / QSTAGES) & 1, 11);  // long complete: makes the TMA-written stats visible
         tc_fence_after();
@@ -304,9 +309,9 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const uint32_t ds_row = a_ds + pb * (2 * DS_BLOCK_BYTES);
 #pragma unroll
         for (int hc = 0; hc < 2; ++hc) {  // two chunks of 16 query columns (keeps the live set small)
-          uint32_t st[16], dp[16];
+          uint32_t st[16], dpv[16];
           tmem_ld_x16(t_st + hc * 16, st);
-          tmem_ld_x16(t_st + (C_DPT - C_ST) + hc * 16, dp);
+          tmem_ld_x16(t_st + (C_DPT - C_ST) + hc * 16, dpv);
           tc_wait_ld();
           if (hc == 0) mbar_wait_a(b_dqdone + pb * 8, ((Pf >> 1) & 1) ^ 1, 12);  // dS^T block free: dQ(Pf-2) has read it
           uint32_t pk[8], dsk[8];
@@ -327,12 +332,21 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                 p0 = ex2_approx(x0);
                 p1 = ex2_approx(x1);
               }
-              const uint64_t dd = add_f32x2(pack_f32x2(__uint_as_float(dp[c]), __uint_as_float(dp[c + 1])),
-                                            pack_f32x2(nd[e], nd[e + 1]));
+              float g0 = __uint_as_float(dpv[c]), g1 = __uint_as_float(dpv[c + 1]), pd0 = p0, pd1 = p1;
+              if (DROP) {  // the forward dropped P (and rescaled): dP and the P that multiplies dO go through the mask
+                const uint32_t q = qcol0 + hc * 16 + c;  // query of column c; mask row = (b, h, query), column = key
+                const bool k0 = drop_keep(drop_seed, dp.site, drop_row0 + q, key, dp.thr16);
+                const bool k1 = drop_keep(drop_seed, dp.site, drop_row0 + q + 1, key, dp.thr16);
+                g0 = k0 ? g0 * drop_s : 0.f;
+                g1 = k1 ? g1 * drop_s : 0.f;
+                pd0 = k0 ? p0 * drop_s : 0.f;
+                pd1 = k1 ? p1 * drop_s : 0.f;
+              }
+              const uint64_t dd = add_f32x2(pack_f32x2(g0, g1), pack_f32x2(nd[e], nd[e + 1]));
               const uint64_t ds2 = mul_f32x2(pack_f32x2(p0, p1), dd);
               float d0, d1;
               unpack_f32x2(ds2, d0, d1);
-              pk[c >> 1] = pack_bf16x2(p0, p1);
+              pk[c >> 1] = pack_bf16x2(pd0, pd1);
               dsk[c >> 1] = pack_bf16x2(d0, d1);
             }
           }
@@ -431,7 +445,7 @@ extern "C" int destr_enc_attn_bwd(const void* q, const void* k, const void* v, i
                                   const uint32_t* mask_bits, int words_per_row, const void* out, const void* dout,
                                   const float* lse, float* stats, float* dq_acc, void* dq, void* dk, void* dv,
                                   int ld_dq, int ld_dk, int ld_dv, int B, int N, int heads, float scale,
-                                  void* stream) {
+                                  const uint32_t* drop_seed, uint32_t drop_thr16, uint32_t drop_site, void* stream) {
   using namespace destr;
   DESTR_CHECK_ARG(q && k && v && mask_bits && out && dout && lse && stats && dq_acc && dq && dk && dv, "null pointer");
   DESTR_CHECK_ARG(B > 0 && N > 0 && heads > 0 && heads * DH <= 256, "shape");
@@ -448,12 +462,14 @@ extern "C" int destr_enc_attn_bwd(const void* q, const void* k, const void* v, i
   if ((rc = make_tmap_bf16_2d(&tv, v, rows, cols, ld_v, BT, DH, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   if ((rc = make_tmap_bf16_2d(&tdo, dout, rows, cols, cols, BQ, DH, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   const size_t smem = sizeof(Smem) + 1024;
-  using KernelT = decltype(&enc_attn_bwd_kernel<0>);
-  static const KernelT kernels[4] = {enc_attn_bwd_kernel<0>, enc_attn_bwd_kernel<1>, enc_attn_bwd_kernel<2>,
-                                     enc_attn_bwd_kernel<3>};
+  using KernelT = decltype(&enc_attn_bwd_kernel<0, false>);
+  static const KernelT kernels[8] = {enc_attn_bwd_kernel<0, false>, enc_attn_bwd_kernel<1, false>,
+                                     enc_attn_bwd_kernel<2, false>, enc_attn_bwd_kernel<3, false>,
+                                     enc_attn_bwd_kernel<0, true>,  enc_attn_bwd_kernel<1, true>,
+                                     enc_attn_bwd_kernel<2, true>,  enc_attn_bwd_kernel<3, true>};
   static bool attr_done = false;
   if (!attr_done) {
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
       DESTR_CUDA(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
@@ -468,10 +484,10 @@ extern "C" int destr_enc_attn_bwd(const void* q, const void* k, const void* v, i
   const int n_items = B * heads * ceil_div(N, BT);
   int grid = n_items < 148 ? n_items : 148;  // persistent: one CTA per SM
   if (g_knobs[13] > 0 && g_knobs[13] < grid) grid = g_knobs[13];
-  kernels[g_knobs[10] & 3]<<<grid, NTHREADS, smem, st>>>(tq, tk, tv, tdo, mask_bits, words_per_row, stats, dq_acc,
-                                                         static_cast<__nv_bfloat16*>(dk),
-                                                         static_cast<__nv_bfloat16*>(dv), ld_dk, ld_dv, N, heads,
-                                                         n_items, scale, scale * 1.4426950408889634f, kn);
+  kernels[(g_knobs[10] & 3) + (drop_thr16 ? 4 : 0)]<<<grid, NTHREADS, smem, st>>>(
+      tq, tk, tv, tdo, mask_bits, words_per_row, stats, dq_acc, static_cast<__nv_bfloat16*>(dk),
+      static_cast<__nv_bfloat16*>(dv), ld_dk, ld_dv, N, heads, n_items, scale, scale * 1.4426950408889634f, kn,
+      Drop{drop_seed, drop_thr16, drop_site});
   DESTR_LAUNCH_CHECK();
   const int64_t n4 = static_cast<int64_t>(rows) * cols / 4;
   int blocks = (int)((n4 + 255) / 256);

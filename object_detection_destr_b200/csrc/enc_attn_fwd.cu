@@ -71,12 +71,12 @@ struct Knobs {
 };
 
 // POLYQ of every 4 key pairs take the FMA-pipe polynomial exp instead of MUFU.EX2
-template <int POLYQ>
+template <int POLYQ, bool DROP>
 __global__ void __launch_bounds__(NTHREADS, 2)
 enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const uint32_t* __restrict__ mask_bits,
                     int words_per_row, __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int N, int heads,
-                    int n_items, float scale_log2, float lazy_tau, Knobs kn) {
+                    int n_items, float scale_log2, float lazy_tau, Knobs kn, Drop dp) {
   extern __shared__ uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -194,6 +194,7 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const int row = wq * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(wq * 32) << 16;
     const uint64_t sc2 = pack_f32x2(scale_log2, scale_log2);
+    const uint32_t drop_seed = (DROP && dp.seed) ? *dp.seed : 0u;
     int f = 0;
     for (int it = 0; it < my_items; ++it) {
       const int w = blockIdx.x + it * gridDim.x;
@@ -201,6 +202,7 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       const int h = bh % heads, b = bh / heads;
       const uint32_t* mrow = mask_bits + static_cast<size_t>(b) * words_per_row;
       float m_ref = -INFINITY, l = 0.f;
+      const uint32_t drop_row = static_cast<uint32_t>(bh) * N + qt * BM + row;  // mask row = (b, h, query)
       // mask bits of this half's 48 keys of tile j (bit i <-> key 96 j + 48 hf + i) live in two words; the raw
       // words are prefetched one tile ahead and only combined when consumed (no stall on the load)
       const uint32_t* mw = mrow + hf;
@@ -270,7 +272,12 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             p0 = ex2_approx(x0);
             p1 = ex2_approx(x1);
           }
-          rs2[i & 1] = add_f32x2(rs2[i & 1], pack_f32x2(p0, p1));
+          rs2[i & 1] = add_f32x2(rs2[i & 1], pack_f32x2(p0, p1));  // the softmax denominator is NOT dropped
+          if (DROP) {  // attention-probability dropout (nn.MultiheadAttention(dropout=p)): zero P, rescale O at the end
+            const uint32_t bits = drop_bits(drop_seed, dp.site, drop_row, j * (BN / 2) + hf * (HN / 2) + i);
+            if ((bits & 0xFFFFu) < dp.thr16) p0 = 0.f;
+            if ((bits >> 16) < dp.thr16) p1 = 0.f;
+          }
           pk[i] = pack_bf16x2(p0, p1);
         }
         {
@@ -313,7 +320,7 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       const float m_fin = (m_all == -INFINITY) ? 0.f : m_all;
       const float a_s = ex2_approx(m_ref - m_fin), a_o = ex2_approx(m_o - m_fin);
       const float l_all = l * a_s + l_o * a_o;
-      const float inv = 1.f / l_all;
+      const float inv = (DROP ? drop_scale(dp.thr16) : 1.f) / l_all;
       const float cs = a_s * inv, co = a_o * inv;
       const int qrow = qt * BM + row;
       uint32_t ob[8];
@@ -351,7 +358,8 @@ extern "C" int destr_debug_knob(int idx, int value) {
 
 extern "C" int destr_enc_attn_fwd(const void* q, const void* k, const void* v, int ld_q, int ld_k, int ld_v,
                                   const uint32_t* mask_bits, int words_per_row, void* out, float* lse, int B, int N,
-                                  int heads, float scale, void* stream) {
+                                  int heads, float scale, const uint32_t* drop_seed, uint32_t drop_thr16,
+                                  uint32_t drop_site, void* stream) {
   using namespace destr;
   DESTR_CHECK_ARG(q && k && v && mask_bits && out, "null pointer");
   DESTR_CHECK_ARG(B > 0 && N > 0 && heads > 0 && heads * DH <= 256, "shape");
@@ -363,16 +371,18 @@ extern "C" int destr_enc_attn_fwd(const void* q, const void* k, const void* v, i
   if ((rc = make_tmap_bf16_2d(&tk, k, rows, heads * DH, ld_k, BN, DH, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   if ((rc = make_tmap_bf16_2d(&tv, v, rows, heads * DH, ld_v, BN, DH, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   const size_t smem = sizeof(Smem) + 1024;
-  using KernelT = decltype(&enc_attn_fwd_kernel<0>);
-  static const KernelT kernels[4] = {enc_attn_fwd_kernel<0>, enc_attn_fwd_kernel<1>, enc_attn_fwd_kernel<2>,
-                                     enc_attn_fwd_kernel<3>};
+  using KernelT = decltype(&enc_attn_fwd_kernel<0, false>);
+  static const KernelT kernels[8] = {enc_attn_fwd_kernel<0, false>, enc_attn_fwd_kernel<1, false>,
+                                     enc_attn_fwd_kernel<2, false>, enc_attn_fwd_kernel<3, false>,
+                                     enc_attn_fwd_kernel<0, true>,  enc_attn_fwd_kernel<1, true>,
+                                     enc_attn_fwd_kernel<2, true>,  enc_attn_fwd_kernel<3, true>};
   static bool attr_done = false;
   if (!attr_done) {
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
       DESTR_CUDA(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  const KernelT kernel = kernels[g_knobs[9] & 3];
+  const KernelT kernel = kernels[(g_knobs[9] & 3) + (drop_thr16 ? 4 : 0)];
   const int n_items = B * heads * ceil_div(N, BM);
   int grid = n_items < 2 * 148 ? n_items : 2 * 148;  // persistent: 2 CTAs per SM
   if (g_knobs[12] > 0 && g_knobs[12] < grid) grid = g_knobs[12];
@@ -380,7 +390,8 @@ extern "C" int destr_enc_attn_fwd(const void* q, const void* k, const void* v, i
            (uint32_t)g_knobs[3], (uint32_t)g_knobs[4], (uint32_t)g_knobs[5]};
   kernel<<<grid, NTHREADS, smem, static_cast<cudaStream_t>(stream)>>>(
       tq, tk, tv, mask_bits, words_per_row, static_cast<__nv_bfloat16*>(out), lse, N, heads, n_items,
-      scale * 1.4426950408889634f, g_knobs[11] ? (float)(g_knobs[11] - 1) : kLazyTau, kn);
+      scale * 1.4426950408889634f, g_knobs[11] ? (float)(g_knobs[11] - 1) : kLazyTau, kn,
+      Drop{drop_seed, drop_thr16, drop_site});
   DESTR_LAUNCH_CHECK();
   return 0;
 }

@@ -199,7 +199,7 @@ def dropout_inplace(x: Tensor, drop) -> Tensor:
 # encoder attention
 # ----------------------------------------------------------------------------------------------
 def enc_attn_fwd(q: Tensor, k: Tensor, v: Tensor, mask_bits: Tensor, B: int, N: int, heads: int,
-                 scale: float, need_lse: bool = True):
+                 scale: float, need_lse: bool = True, drop=None):
     """q,k,v: bf16 2-D views [B*N, heads*32] (any row pitch, unit column stride).
     Returns (out bf16 [B*N, heads*32], lse fp32 [B,heads,N])."""
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
@@ -211,12 +211,12 @@ def enc_attn_fwd(q: Tensor, k: Tensor, v: Tensor, mask_bits: Tensor, B: int, N: 
     lse = torch.empty(B, heads, N, dtype=torch.float32, device=q.device) if need_lse else None
     _lib.call("destr_enc_attn_fwd", q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), k.stride(0), v.stride(0),
               mask_bits.data_ptr(), mask_bits.shape[1], out.data_ptr(), _ptr(lse), B, N, heads, float(scale),
-              _stream())
+              *_dargs(drop), _stream())
     return out, lse
 
 
 def enc_attn_bwd(q: Tensor, k: Tensor, v: Tensor, mask_bits: Tensor, out: Tensor, dout: Tensor, lse: Tensor,
-                 B: int, N: int, heads: int, scale: float):
+                 B: int, N: int, heads: int, scale: float, drop=None):
     """Returns (dqk bf16 [B*N, 2*heads*32] = [dq | dk], dv bf16 [B*N, heads*32])."""
     C = heads * 32
     dout = _chk(dout.contiguous(), BF16, "dout")
@@ -228,7 +228,7 @@ def enc_attn_bwd(q: Tensor, k: Tensor, v: Tensor, mask_bits: Tensor, out: Tensor
     _lib.call("destr_enc_attn_bwd", q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), k.stride(0), v.stride(0),
               mask_bits.data_ptr(), mask_bits.shape[1], out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
               delta.data_ptr(), dq_acc.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), 2 * C, 2 * C, C,
-              B, N, heads, float(scale), _stream())
+              B, N, heads, float(scale), *_dargs(drop), _stream())
     return dqk, dv
 
 

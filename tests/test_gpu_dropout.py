@@ -75,3 +75,39 @@ def test_relu_bwd_scale():
     ref = (dy.float() * (h.float() > 0) * s)
     assert float((dpre - ref.bfloat16().float()).abs().max()) == 0.0
     assert torch.allclose(dbias.cpu(), ref.sum(0), rtol=1e-3, atol=0.05)
+
+
+@pytest.mark.parametrize("B,N,heads", [(2, 300, 8), (8, 600, 8), (1, 130, 2)])
+def test_encoder_attention_dropout_fwd_bwd(B, N, heads):
+    """Attention-probability dropout inside the flash kernels == softmax -> mask -> scale -> PV with the twin mask
+    (nn.MultiheadAttention(dropout=p) arithmetic, torch functional.py:6645), forward and all three gradients."""
+    import math
+    from object_detection_destr_b200 import ops
+    g = torch.Generator().manual_seed(B * N)
+    C = heads * 32
+    qk = torch.randn(B * N, 2 * C, generator=g).bfloat16()
+    v = torch.randn(B * N, C, generator=g).bfloat16()
+    dout = torch.randn(B * N, C, generator=g).bfloat16()
+    kpm = torch.zeros(B, N, dtype=torch.bool)
+    kpm[B - 1, N - 37:] = True
+    site, seed = 21, 77
+    mk = _mask(seed, site, B * heads * N, N).view(B, heads, N, N)
+    scale = 1 / math.sqrt(32)
+    split = lambda t: t.reshape(B, N, heads, 32).transpose(1, 2)
+    qf, kf, vf = (t.float().requires_grad_() for t in (qk[:, :C], qk[:, C:], v))
+    s = torch.einsum("bhqd,bhkd->bhqk", split(qf), split(kf)) * scale
+    s = s.masked_fill(kpm[:, None, None, :], float("-inf"))
+    ref = torch.einsum("bhqk,bhkd->bhqd", torch.softmax(s, -1) * mk, split(vf)).transpose(1, 2).reshape(B * N, C)
+    ref.backward(dout.float())
+    drop = _drop(seed, site)
+    bits = ops.pack_key_mask(kpm.cuda(), B, N)
+    qk_d, v_d = qk.cuda(), v.cuda()
+    out, lse = ops.enc_attn_fwd(qk_d[:, :C], qk_d[:, C:], v_d, bits, B, N, heads, scale, drop=drop)
+    assert float((out.cpu().float() - ref).abs().max()) < 3e-2, float((out.cpu().float() - ref).abs().max())
+    dqk, dv = ops.enc_attn_bwd(qk_d[:, :C], qk_d[:, C:], v_d, bits, out, dout.cuda(), lse, B, N, heads, scale, drop=drop)
+    for got, exp, name in ((dv, vf.grad, "dV"), (dqk[:, C:], kf.grad, "dK"), (dqk[:, :C], qf.grad, "dQ")):
+        err = float((got.cpu().float() - exp).abs().max())
+        assert err < 3e-2 * float(exp.abs().max()) + 2e-2, (name, err, float(exp.abs().max()))
+    # and it really dropped something: the no-dropout output differs
+    out0, _ = ops.enc_attn_fwd(qk_d[:, :C], qk_d[:, C:], v_d, bits, B, N, heads, scale)
+    assert float((out0.float() - out.float()).abs().max()) > 0.05
