@@ -168,7 +168,8 @@ int destr_dec_qkv_prep(const void* qkv_obj, const void* qk_pos, int ld_pos, cons
  * (head-major, before the slot masking that destr_dual_ln_mix_fwd applies).  lse1/lse2 fp32 [B,8,Q]
  * (log2 domain, for the backward; may be NULL).  Q <= 384. */
 int destr_dec_self_pair_attn_fwd(const void* qkv, const void* cat, void* o1, void* o2, float* lse1, float* lse2,
-                                 int B, int Q, void* stream);
+                                 int B, int Q, const uint32_t* drop_seed, uint32_t drop_thr16,
+    uint32_t drop_site, void* stream);
 
 /* Backward of destr_dec_self_pair_attn_fwd, stage 1 (one launch, tcgen05): recomputes S and dP = dO.v^T and
  * applies the softmax backward.  qkv / cat / do1 [B,8,Q,64] / do2 [B,8,Q,128] head-major; lse*, delta*
@@ -177,7 +178,8 @@ int destr_dec_self_pair_attn_fwd(const void* qkv, const void* cat, void* o1, voi
  * batched GEMMs: dV = P^T dO, dQ = dS K, dK = dS^T Q (see ops.dec_self_pair_attn_bwd). */
 int destr_dec_self_pair_attn_bwd_ds(const void* qkv, const void* cat, const void* do1, const void* do2,
                                     const float* lse1, const float* lse2, const float* delta1, const float* delta2,
-                                    void* P1, void* dS1, void* P2, void* dS2, int B, int Q, void* stream);
+                                    void* P1, void* dS1, void* P2, void* dS2, int B, int Q, const uint32_t* drop_seed, uint32_t drop_thr16,
+    uint32_t drop_site, void* stream);
 /* Backward of destr_dec_qkv_prep (gather formulation of the scatter-add, deterministic): head-major
  * d_qkv [3][B,8,Q,64], d_cat [3][B,8,Q,128] -> d_qkv_obj bf16 [B*Q,1536], d_qk_pos bf16 [B*Q,512] (pitch ld_pos). */
 int destr_dec_qkv_prep_bwd(const void* d_qkv, const void* d_cat, const int32_t* pairs, void* d_qkv_obj,
@@ -197,7 +199,8 @@ int64_t destr_split_cross_attn_ws_floats(int B, int Q, int N);
 int destr_split_cross_attn_fwd(const void* q_obj, const void* q_pos, const void* k_enc, const void* k_pos,
                                const void* v, int ld_kenc, int ld_kpos, int ld_v, const uint32_t* mask_bits,
                                int words_per_row, void* out, float* lse, float* ws_partial, int B, int Q, int N,
-                               float scale, void* stream);
+                               float scale, const uint32_t* drop_seed, uint32_t drop_thr16,
+    uint32_t drop_site, void* stream);
 
 /* Backward of destr_split_cross_attn_fwd, stage 1: recomputes S and dP = dO.V^T on tcgen05 and applies
  * the softmax backward.  Rows are ordered (2q + br):
@@ -210,7 +213,8 @@ int destr_split_cross_attn_bwd_ds(const void* q_obj, const void* q_pos, const vo
                                   const void* v, int ld_kenc, int ld_kpos, int ld_v, const uint32_t* mask_bits,
                                   int words_per_row, const void* out, const void* dout, const float* lse,
                                   float* delta, void* P_all, void* dS_all, void* dS_sum, int B, int Q, int N,
-                                  float scale, void* stream);
+                                  float scale, const uint32_t* drop_seed, uint32_t drop_thr16,
+    uint32_t drop_site, void* stream);
 
 /* ---------------- set-prediction cost matrix ---------------- */
 

@@ -43,11 +43,11 @@ SIGNATURES = {
     "destr_dual_ln_mix_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _u, _u,
                               _u, _p],
     "destr_dec_qkv_prep": [_p, _p, _i, _p, _p, _p, _i, _i, _p],
-    "destr_dec_self_pair_attn_fwd": [_p, _p, _p, _p, _p, _p, _i, _i, _p],
-    "destr_split_cross_attn_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _p, _i, _p, _p, _p, _i, _i, _i, _f, _p],
+    "destr_dec_self_pair_attn_fwd": [_p, _p, _p, _p, _p, _p, _i, _i, _p, _u, _u, _p],
+    "destr_split_cross_attn_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _p, _i, _p, _p, _p, _i, _i, _i, _f, _p, _u, _u, _p],
     "destr_split_cross_attn_bwd_ds": [_p, _p, _p, _p, _p, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i,
-                                      _f, _p],
-    "destr_dec_self_pair_attn_bwd_ds": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
+                                      _f, _p, _u, _u, _p],
+    "destr_dec_self_pair_attn_bwd_ds": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _u, _u, _p],
     "destr_dec_qkv_prep_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _p],
     "destr_pair_indices": [_p, _p, _i, _i, _p],
     "destr_box_refine": [_p, _p, _p, _i, _p],

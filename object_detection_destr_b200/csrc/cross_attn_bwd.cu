@@ -44,7 +44,7 @@ cross_attn_bwd_ds_kernel(const __grid_constant__ CUtensorMap tm_qobj, const __gr
                          const uint32_t* __restrict__ mask_bits, int words_per_row, const float* __restrict__ lse,
                          const float* __restrict__ delta, __nv_bfloat16* __restrict__ P_all,
                          __nv_bfloat16* __restrict__ dS_all, __nv_bfloat16* __restrict__ dS_sum, int Q, int N, int Np,
-                         float scale, float scale_log2) {
+                         float scale, float scale_log2, Drop dp) {
   extern __shared__ uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -112,6 +112,8 @@ cross_attn_bwd_ds_kernel(const __grid_constant__ CUtensorMap tm_qobj, const __gr
     const uint32_t lane_addr = static_cast<uint32_t>(wq * 32) << 16;
     const int q = qt * BT + wq * 32 + lane;
     const bool qvalid = q < Q;
+    const uint32_t drop_seed = (dp.thr16 && dp.seed) ? *dp.seed : 0u;
+    const float drop_s = drop_scale(dp.thr16);
     const uint4 mw = *reinterpret_cast<const uint4*>(mask_bits + static_cast<size_t>(b) * words_per_row + j * 4);
     const uint32_t mwa[4] = {mw.x, mw.y, mw.z, mw.w};
     uint32_t stash[4][16];  // packed dS of branch 0
@@ -135,13 +137,18 @@ cross_attn_bwd_ds_kernel(const __grid_constant__ CUtensorMap tm_qobj, const __gr
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           float pv[2], dv[2];
+          uint32_t bits = 0xFFFFFFFFu;
+          if (dp.thr16)
+            bits = drop_bits(drop_seed, dp.site, static_cast<uint32_t>((b * 2 + br) * Q + q), j * (BT / 2) + c * 16 + i);
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int k = 2 * i + e;
             float p = ex2_approx(fmaf(__uint_as_float(s[k]), scale_log2, -l2));
             p = ((mwa[c] >> k) & 1u) ? 0.f : p;
-            pv[e] = p;
-            dv[e] = p * (__uint_as_float(d[k]) - dl) * scale;
+            // forward: O = dropout(P) V  ->  dV takes the dropped P, dP passes through the same mask
+            const float keep = (((bits >> (16 * e)) & 0xFFFFu) >= dp.thr16) ? drop_s : 0.f;
+            pv[e] = p * keep;
+            dv[e] = p * (__uint_as_float(d[k]) * keep - dl) * scale;
           }
           pp[i] = pack_bf16x2(pv[0], pv[1]);
           dd[i] = pack_bf16x2(dv[0], dv[1]);
@@ -204,6 +211,7 @@ extern "C" int destr_split_cross_attn_bwd_ds(const void* q_obj, const void* q_po
                                              const uint32_t* mask_bits, int words_per_row, const void* out,
                                              const void* dout, const float* lse, float* delta, void* P_all,
                                              void* dS_all, void* dS_sum, int B, int Q, int N, float scale,
+                                             const uint32_t* drop_seed, uint32_t drop_thr16, uint32_t drop_site,
                                              void* stream) {
   using namespace destr;
   DESTR_CHECK_ARG(q_obj && q_pos && k_enc && k_pos && v && mask_bits && out && dout && lse && delta && P_all &&
@@ -235,7 +243,7 @@ extern "C" int destr_split_cross_attn_bwd_ds(const void* q_obj, const void* q_po
   cross_attn_bwd_ds_kernel<<<grid, NTHREADS, smem, st>>>(
       tqo, tqp, tke, tkp, tv, tdo, mask_bits, words_per_row, lse, delta, static_cast<__nv_bfloat16*>(P_all),
       static_cast<__nv_bfloat16*>(dS_all), static_cast<__nv_bfloat16*>(dS_sum), Q, N, nkv * BT, scale,
-      scale * 1.4426950408889634f);
+      scale * 1.4426950408889634f, Drop{drop_seed, drop_thr16, drop_site});
   DESTR_LAUNCH_CHECK();
   return 0;
 }

@@ -47,7 +47,7 @@ cross_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qobj, const __grid_
                       const __grid_constant__ CUtensorMap tm_kenc, const __grid_constant__ CUtensorMap tm_kpos,
                       const __grid_constant__ CUtensorMap tm_v, const uint32_t* __restrict__ mask_bits,
                       int words_per_row, float* __restrict__ ws_o, float* __restrict__ ws_ml, int Q, int N, int nqt,
-                      float scale_log2) {
+                      float scale_log2, Drop dp) {
   extern __shared__ uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -128,6 +128,8 @@ cross_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qobj, const __grid_
     const uint32_t lane_addr = static_cast<uint32_t>(wq * 32) << 16;
     const int r_in_tile = wq * 32 + lane;
     const int q = qt * BT + r_in_tile;
+    const uint32_t drop_seed = (dp.thr16 && dp.seed) ? *dp.seed : 0u;
+    const uint32_t drop_row = static_cast<uint32_t>((b * 2 + br) * Q + q);
     mbar_wait(&sm.s_full, 0, 35);
     tc_fence_after();
     uint32_t sr[4][32];
@@ -161,6 +163,10 @@ cross_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qobj, const __grid_
         const float p1 = ex2_approx(fmaf(__uint_as_float(sr[2 * c + ((e + 1) >> 5)][(e + 1) & 31]), scale_log2, -m_use));
         l += p0 + p1;
         pk[i] = pack_bf16x2(p0, p1);
+        if (dp.thr16) {  // ClsRegBranch's SelfAttention drops P (always, self_attention.py:40): row = (b, branch, query)
+          const uint32_t bits = drop_bits(drop_seed, dp.site, drop_row, j * (BT / 2) + c * 32 + i);
+          pk[i] = pack_bf16x2(((bits & 0xFFFFu) >= dp.thr16) ? p0 : 0.f, ((bits >> 16) >= dp.thr16) ? p1 : 0.f);
+        }
       }
       tmem_st_x32(tmem + lane_addr + c * 32, pk);
     }
@@ -192,7 +198,7 @@ cross_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qobj, const __grid_
 // one warp per (b, branch, query): merge the nkv partials
 __global__ void cross_attn_combine_kernel(const float* __restrict__ ws_o, const float* __restrict__ ws_ml,
                                           __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int B, int Q,
-                                          int nqt, int nkv) {
+                                          int nqt, int nkv, float out_scale) {
   const int lane = threadIdx.x & 31;
   const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (idx >= B * 2 * Q) return;
@@ -215,7 +221,7 @@ __global__ void cross_attn_combine_kernel(const float* __restrict__ ws_o, const 
     acc[3] = fmaf(w, x0.w, acc[3]); acc[4] = fmaf(w, x1.x, acc[4]); acc[5] = fmaf(w, x1.y, acc[5]);
     acc[6] = fmaf(w, x1.z, acc[6]); acc[7] = fmaf(w, x1.w, acc[7]);
   }
-  const float inv = 1.f / L;
+  const float inv = out_scale / L;  // out_scale = 1/(1-p) of the attention-probability dropout
   const uint4 o = make_uint4(pack_bf16x2(acc[0] * inv, acc[1] * inv), pack_bf16x2(acc[2] * inv, acc[3] * inv),
                              pack_bf16x2(acc[4] * inv, acc[5] * inv), pack_bf16x2(acc[6] * inv, acc[7] * inv));
   *reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * Q + q) * 512 + br * 256 + lane * 8) = o;
@@ -233,7 +239,9 @@ extern "C" int64_t destr_split_cross_attn_ws_floats(int B, int Q, int N) {
 extern "C" int destr_split_cross_attn_fwd(const void* q_obj, const void* q_pos, const void* k_enc, const void* k_pos,
                                           const void* v, int ld_kenc, int ld_kpos, int ld_v,
                                           const uint32_t* mask_bits, int words_per_row, void* out, float* lse,
-                                          float* ws_partial, int B, int Q, int N, float scale, void* stream) {
+                                          float* ws_partial, int B, int Q, int N, float scale,
+                                          const uint32_t* drop_seed, uint32_t drop_thr16, uint32_t drop_site,
+                                          void* stream) {
   using namespace destr;
   DESTR_CHECK_ARG(q_obj && q_pos && k_enc && k_pos && v && mask_bits && out && ws_partial, "null pointer");
   DESTR_CHECK_ARG(B > 0 && Q > 0 && N > 0, "shape");
@@ -258,11 +266,12 @@ extern "C" int destr_split_cross_attn_fwd(const void* q_obj, const void* q_pos, 
   float* ws_ml = ws_partial + static_cast<size_t>(B) * 2 * nqt * nkv * BT * DV;
   dim3 grid(nkv, 2 * nqt, B);
   cross_attn_fwd_kernel<<<grid, NTHREADS, smem, st>>>(tqo, tqp, tke, tkp, tv, mask_bits, words_per_row, ws_o, ws_ml,
-                                                      Q, N, nqt, scale * 1.4426950408889634f);
+                                                      Q, N, nqt, scale * 1.4426950408889634f,
+                                                      Drop{drop_seed, drop_thr16, drop_site});
   DESTR_LAUNCH_CHECK();
   const int total = B * 2 * Q;
   cross_attn_combine_kernel<<<ceil_div(total, 8), 256, 0, st>>>(ws_o, ws_ml, static_cast<__nv_bfloat16*>(out), lse, B,
-                                                               Q, nqt, nkv);
+                                                               Q, nqt, nkv, drop_scale(drop_thr16));
   DESTR_LAUNCH_CHECK();
   return 0;
 }

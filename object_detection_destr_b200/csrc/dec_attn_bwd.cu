@@ -33,6 +33,7 @@ struct Params {
   const float* lse1; const float* lse2; const float* delta1; const float* delta2;
   __nv_bfloat16* P1; __nv_bfloat16* dS1; __nv_bfloat16* P2; __nv_bfloat16* dS2;
   int Q, Qp;
+  Drop dp;  // self-attention heads only (self_attention.py:40)
 };
 
 template <int D>
@@ -40,7 +41,7 @@ __device__ __forceinline__ void body(Smem& sm, const CUtensorMap* tm_q, const CU
                                      const CUtensorMap* tm_v, const CUtensorMap* tm_do, const float* __restrict__ lse,
                                      const float* __restrict__ delta, __nv_bfloat16* __restrict__ P_out,
                                      __nv_bfloat16* __restrict__ dS_out, int Q, int Qp, int h, int b, int mt,
-                                     float scale_log2, float p_scale, float dp_scale, float ds_scale, uint32_t tmem) {
+                                     float scale_log2, float p_scale, float dp_scale, float ds_scale, uint32_t tmem, Drop dp) {
   constexpr int NCH = D / 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkv = (Q + BT - 1) / BT;
@@ -99,6 +100,8 @@ __device__ __forceinline__ void body(Smem& sm, const CUtensorMap* tm_q, const CU
     const uint32_t lane_addr = static_cast<uint32_t>(wq * 32) << 16;
     const int qrow = mt * BT + wq * 32 + lane;
     const bool valid = qrow < Q;
+    const uint32_t drop_seed = (dp.thr16 && dp.seed) ? *dp.seed : 0u;
+    const float drop_s = drop_scale(dp.thr16);  // 1 when dropout is off (thr16 = 0 keeps everything)
     const float l2 = valid ? lse[static_cast<size_t>(hrow) + qrow] : INFINITY;
     const float dl = valid ? delta[static_cast<size_t>(hrow) + qrow] : 0.f;
     __nv_bfloat16* prow = P_out + (static_cast<size_t>(hrow) + (valid ? qrow : 0)) * Qp;
@@ -118,13 +121,17 @@ __device__ __forceinline__ void body(Smem& sm, const CUtensorMap* tm_q, const CU
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           float pv[2], dv[2];
+          uint32_t bits = 0xFFFFFFFFu;
+          if (dp.thr16) bits = drop_bits(drop_seed, dp.site, static_cast<uint32_t>(hrow + qrow), (key0 >> 1) + i);
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int k = 2 * i + e;
             float p = ex2_approx(fmaf(__uint_as_float(s[k]), scale_log2, -l2));
             p = (key0 + k < Q) ? p : 0.f;
-            pv[e] = p * p_scale;
-            dv[e] = p * (__uint_as_float(d[k]) * dp_scale - dl) * ds_scale;
+            // forward: O = dropout(P) V  ->  dV takes the dropped P, dP passes through the same mask
+            const float keep = (((bits >> (16 * e)) & 0xFFFFu) >= dp.thr16) ? drop_s : 0.f;
+            pv[e] = p * p_scale * keep;
+            dv[e] = p * (__uint_as_float(d[k]) * keep * dp_scale - dl) * ds_scale;
           }
           pp[i] = pack_bf16x2(pv[0], pv[1]);
           dd[i] = pack_bf16x2(dv[0], dv[1]);
@@ -173,10 +180,10 @@ dec_attn_bwd_ds_kernel(const __grid_constant__ CUtensorMap tq1, const __grid_con
   const float log2e = 1.4426950408889634f, r = 0.08838834764831845f;
   if (hy < 8)
     body<64>(sm, &tq1, &tk1, &tv1, &td1, p.lse1, p.delta1, p.P1, p.dS1, p.Q, p.Qp, hy, b, mt, log2e * 0.125f, 1.f, 1.f,
-             0.125f, tmem);
+             0.125f, tmem, p.dp);
   else
     body<128>(sm, &tq2, &tk2, &tv2, &td2, p.lse2, p.delta2, p.P2, p.dS2, p.Q, p.Qp, hy - 8, b, mt, log2e, r, r, 1.f,
-              tmem);
+              tmem, Drop{nullptr, 0u, 0u});
   tc_fence_before();
   __syncthreads();
   if (warp == 5) tmem_dealloc<512>(tmem);
@@ -269,7 +276,8 @@ extern "C" int destr_dec_qkv_prep_bwd(const void* d_qkv, const void* d_cat, cons
 extern "C" int destr_dec_self_pair_attn_bwd_ds(const void* qkv, const void* cat, const void* do1, const void* do2,
                                                const float* lse1, const float* lse2, const float* delta1,
                                                const float* delta2, void* P1, void* dS1, void* P2, void* dS2, int B,
-                                               int Q, void* stream) {
+                                               int Q, const uint32_t* drop_seed, uint32_t drop_thr16,
+                                               uint32_t drop_site, void* stream) {
   using namespace destr;
   DESTR_CHECK_ARG(qkv && cat && do1 && do2 && lse1 && lse2 && delta1 && delta2 && P1 && dS1 && P2 && dS2,
                   "null pointer");
@@ -296,7 +304,8 @@ extern "C" int destr_dec_self_pair_attn_bwd_ds(const void* qkv, const void* cat,
   }
   const int Qp = ceil_div(Q, BT) * BT;
   Params p{lse1, lse2, delta1, delta2, static_cast<__nv_bfloat16*>(P1), static_cast<__nv_bfloat16*>(dS1),
-           static_cast<__nv_bfloat16*>(P2), static_cast<__nv_bfloat16*>(dS2), Q, Qp};
+           static_cast<__nv_bfloat16*>(P2), static_cast<__nv_bfloat16*>(dS2), Q, Qp,
+           Drop{drop_seed, drop_thr16, drop_site}};
   dim3 grid(ceil_div(Q, BT), 16, B);
   dec_attn_bwd_ds_kernel<<<grid, NTHREADS, smem, static_cast<cudaStream_t>(stream)>>>(t[0], t[1], t[2], t[3], t[4],
                                                                                       t[5], t[6], t[7], p);

@@ -43,13 +43,14 @@ struct Params {
   float* lse1;
   float* lse2;
   int Q;
+  Drop dp;  // attention-probability dropout of the SELF-attention heads (self_attention.py:40); the pair heads have none
 };
 
 template <int D>
 __device__ __forceinline__ void body(Smem& sm, const CUtensorMap* tm_q, const CUtensorMap* tm_k,
                                      const CUtensorMap* tm_v, __nv_bfloat16* __restrict__ out,
                                      float* __restrict__ lse, int Q, int h, int b, int mt, float scale_log2,
-                                     float out_scale, uint32_t tmem) {
+                                     float out_scale, uint32_t tmem, Drop dp) {
   constexpr int NCH = D / 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkv = (Q + BT - 1) / BT;
@@ -109,6 +110,7 @@ __device__ __forceinline__ void body(Smem& sm, const CUtensorMap* tm_q, const CU
     const int wq = warp;
     const uint32_t lane_addr = static_cast<uint32_t>(wq * 32) << 16;
     const int qrow = mt * BT + wq * 32 + lane;
+    const uint32_t drop_seed = (dp.thr16 && dp.seed) ? *dp.seed : 0u;
     mbar_wait(&sm.s_full, 0, 26);
     tc_fence_after();
     // pass 1: row max over all keys < Q
@@ -143,6 +145,11 @@ __device__ __forceinline__ void body(Smem& sm, const CUtensorMap* tm_q, const CU
           p0 = (key0 + 2 * i < Q) ? p0 : 0.f;
           p1 = (key0 + 2 * i + 1 < Q) ? p1 : 0.f;
           l += p0 + p1;
+          if (dp.thr16) {  // mask row = (b, h, query), column = key; the denominator l is not dropped
+            const uint32_t bits = drop_bits(drop_seed, dp.site, static_cast<uint32_t>(hrow + qrow), (key0 >> 1) + i);
+            if ((bits & 0xFFFFu) < dp.thr16) p0 = 0.f;
+            if ((bits >> 16) < dp.thr16) p1 = 0.f;
+          }
           pk[i] = pack_bf16x2(p0, p1);
         }
         tmem_st_x16(tmem + lane_addr + j * BT + c * 16, pk);
@@ -153,7 +160,7 @@ __device__ __forceinline__ void body(Smem& sm, const CUtensorMap* tm_q, const CU
     mbar_arrive(&sm.p_full);
     mbar_wait(&sm.o_full, 0, 27);
     tc_fence_after();
-    const float inv = out_scale / l;
+    const float inv = out_scale * drop_scale(dp.thr16) / l;
     const bool valid = qrow < Q;
     __nv_bfloat16* dst = out + (static_cast<size_t>(row_base + qrow) * 8 + h) * D;
 #pragma unroll
@@ -203,9 +210,10 @@ dec_attn_fwd_kernel(const __grid_constant__ CUtensorMap tq1, const __grid_consta
   const int mt = blockIdx.x, hy = blockIdx.y, b = blockIdx.z;
   const float log2e = 1.4426950408889634f;
   if (hy < 8)
-    body<64>(sm, &tq1, &tk1, &tv1, p.o1, p.lse1, p.Q, hy, b, mt, log2e * 0.125f, 1.0f, tmem);
+    body<64>(sm, &tq1, &tk1, &tv1, p.o1, p.lse1, p.Q, hy, b, mt, log2e * 0.125f, 1.0f, tmem, p.dp);
   else
-    body<128>(sm, &tq2, &tk2, &tv2, p.o2, p.lse2, p.Q, hy - 8, b, mt, log2e, 0.08838834764831845f, tmem);
+    body<128>(sm, &tq2, &tk2, &tv2, p.o2, p.lse2, p.Q, hy - 8, b, mt, log2e, 0.08838834764831845f, tmem,
+              Drop{nullptr, 0u, 0u});
   tc_fence_before();
   __syncthreads();
   if (warp == 5) tmem_dealloc<512>(tmem);
@@ -279,7 +287,8 @@ extern "C" int destr_dec_qkv_prep(const void* qkv_obj, const void* qk_pos, int l
 }
 
 extern "C" int destr_dec_self_pair_attn_fwd(const void* qkv, const void* cat, void* o1, void* o2, float* lse1,
-                                            float* lse2, int B, int Q, void* stream) {
+                                            float* lse2, int B, int Q, const uint32_t* drop_seed, uint32_t drop_thr16,
+                                            uint32_t drop_site, void* stream) {
   using namespace destr;
   DESTR_CHECK_ARG(qkv && cat && o1 && o2, "null pointer");
   DESTR_CHECK_ARG(B > 0 && Q > 0 && Q <= BT * MAX_TILES, "Q must be <= 384");
@@ -301,7 +310,8 @@ extern "C" int destr_dec_self_pair_attn_fwd(const void* qkv, const void* cat, vo
     DESTR_CUDA(cudaFuncSetAttribute(dec_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  Params p{static_cast<__nv_bfloat16*>(o1), static_cast<__nv_bfloat16*>(o2), lse1, lse2, Q};
+  Params p{static_cast<__nv_bfloat16*>(o1), static_cast<__nv_bfloat16*>(o2), lse1, lse2, Q,
+           Drop{drop_seed, drop_thr16, drop_site}};
   dim3 grid(ceil_div(Q, BT), 16, B);
   dec_attn_fwd_kernel<<<grid, NTHREADS, smem, static_cast<cudaStream_t>(stream)>>>(t[0], t[1], t[2], t[3], t[4],
                                                                                    t[5], p);

@@ -264,14 +264,14 @@ def dec_qkv_prep(qkv_obj: Tensor, qk_pos: Tensor, pairs: Tensor, B: int, Q: int)
     return qkv, cat
 
 
-def dec_self_pair_attn_fwd(qkv: Tensor, cat: Tensor, B: int, Q: int, need_lse: bool = True):
+def dec_self_pair_attn_fwd(qkv: Tensor, cat: Tensor, B: int, Q: int, need_lse: bool = True, drop=None):
     """-> (o1 bf16 [B*Q,512], o2 bf16 [B*Q,1024], lse1, lse2 fp32 [B,8,Q])."""
     o1 = torch.empty(B * Q, 512, dtype=BF16, device=qkv.device)
     o2 = torch.empty(B * Q, 1024, dtype=BF16, device=qkv.device)
     lse1 = torch.empty(B, 8, Q, dtype=torch.float32, device=qkv.device) if need_lse else None
     lse2 = torch.empty(B, 8, Q, dtype=torch.float32, device=qkv.device) if need_lse else None
     _lib.call("destr_dec_self_pair_attn_fwd", _chk(qkv, BF16, "qkv").data_ptr(), _chk(cat, BF16, "cat").data_ptr(),
-              o1.data_ptr(), o2.data_ptr(), _ptr(lse1), _ptr(lse2), B, Q, _stream())
+              o1.data_ptr(), o2.data_ptr(), _ptr(lse1), _ptr(lse2), B, Q, *_dargs(drop), _stream())
     return o1, o2, lse1, lse2
 
 
@@ -315,7 +315,7 @@ def dual_ln_mix_bwd(dout: Tensor, x: Tensor, o1: Tensor, o2: Tensor, pairs: Tens
 
 
 def split_cross_attn_fwd(q_obj: Tensor, q_pos: Tensor, k_enc: Tensor, k_pos: Tensor, v: Tensor, mask_bits: Tensor,
-                         B: int, Q: int, N: int, need_lse: bool = True):
+                         B: int, Q: int, N: int, need_lse: bool = True, drop=None):
     """q_obj bf16 [B*Q,512], q_pos bf16 [B*Q,256], k_enc/k_pos/v bf16 [B*N,256] views (unit column stride).
     -> (out bf16 [B*Q,512] = [cls|reg], lse fp32 [B,2,Q])."""
     q_obj, q_pos = _chk(q_obj.contiguous(), BF16, "q_obj"), _chk(q_pos.contiguous(), BF16, "q_pos")
@@ -328,14 +328,14 @@ def split_cross_attn_fwd(q_obj: Tensor, q_pos: Tensor, k_enc: Tensor, k_pos: Ten
     ws = torch.empty(_lib.lib.destr_split_cross_attn_ws_floats(B, Q, N), dtype=torch.float32, device=q_obj.device)
     _lib.call("destr_split_cross_attn_fwd", q_obj.data_ptr(), q_pos.data_ptr(), k_enc.data_ptr(), k_pos.data_ptr(),
               v.data_ptr(), k_enc.stride(0), k_pos.stride(0), v.stride(0), mask_bits.data_ptr(), mask_bits.shape[1],
-              out.data_ptr(), _ptr(lse), ws.data_ptr(), B, Q, N, 1.0 / math.sqrt(512.0), _stream())
+              out.data_ptr(), _ptr(lse), ws.data_ptr(), B, Q, N, 1.0 / math.sqrt(512.0), *_dargs(drop), _stream())
     return out, lse
 
 
 # Backward of the decoder attention ops: cuBLAS batched GEMMs + elementwise torch on the GPU
 # (see _composed_bwd.py for status; the fused tcgen05 backward exists for the encoder only so far).
 def dec_self_pair_attn_bwd(qkv: Tensor, cat: Tensor, do1: Tensor, do2: Tensor, lse1: Tensor, lse2: Tensor,
-                           delta1: Tensor, delta2: Tensor, B: int, Q: int):
+                           delta1: Tensor, delta2: Tensor, B: int, Q: int, drop=None):
     """Backward of dec_self_pair_attn_fwd.  All operands head-major: qkv [3,B,8,Q,64], cat [3,B,8,Q,128],
     do1 [B,8,Q,64], do2 [B,8,Q,128]; lse/delta fp32 [B,8,Q].  The tcgen05 kernel recomputes S, dP and does the
     softmax backward; six cuBLAS batched GEMMs finish.  -> head-major (d_qkv [3,B,8,Q,64], d_cat [3,B,8,Q,128])."""
@@ -345,7 +345,7 @@ def dec_self_pair_attn_bwd(qkv: Tensor, cat: Tensor, do1: Tensor, do2: Tensor, l
     PD = torch.empty(4, BH, Q, Qp, dtype=BF16, device=dev)  # P1, dS1, P2, dS2
     _lib.call("destr_dec_self_pair_attn_bwd_ds", qkv.data_ptr(), cat.data_ptr(), do1.data_ptr(), do2.data_ptr(),
               lse1.data_ptr(), lse2.data_ptr(), delta1.data_ptr(), delta2.data_ptr(), PD[0].data_ptr(),
-              PD[1].data_ptr(), PD[2].data_ptr(), PD[3].data_ptr(), B, Q, _stream())
+              PD[1].data_ptr(), PD[2].data_ptr(), PD[3].data_ptr(), B, Q, *_dargs(drop), _stream())
     d_qkv = torch.empty(3, BH, Q, 64, dtype=BF16, device=dev)
     d_cat = torch.empty(3, BH, Q, 128, dtype=BF16, device=dev)
     for x, dx, P, dS, dO in ((qkv.view(3, BH, Q, 64), d_qkv, PD[0][:, :, :Q], PD[1][:, :, :Q], do1.view(BH, Q, 64)),
@@ -380,7 +380,7 @@ def _bmm_aligned_k(a: Tensor, b: Tensor) -> Tensor:
 def split_cross_attn_bwd(q_obj: Tensor, q_pos: Tensor, k_enc: Tensor, k_pos: Tensor, v: Tensor, mask_bits: Tensor,
                          out: Tensor, dout: Tensor, lse: Tensor, B: int, Q: int, N: int,
                          dke_out: Optional[Tensor] = None, dkp_out: Optional[Tensor] = None,
-                         dv_out: Optional[Tensor] = None):
+                         dv_out: Optional[Tensor] = None, drop=None):
     """Backward of split_cross_attn_fwd: the tcgen05 kernel recomputes S, dP and does the softmax backward
     (P, dS, dS_cls+dS_reg in bf16); five cuBLAS batched GEMMs on plain views finish the contractions.
     -> (dq_obj [B*Q,512], dq_pos [B*Q,256], dk_enc, dk_pos, dv [B*N,256]) bf16."""
@@ -394,7 +394,7 @@ def split_cross_attn_bwd(q_obj: Tensor, q_pos: Tensor, k_enc: Tensor, k_pos: Ten
     _lib.call("destr_split_cross_attn_bwd_ds", q_obj.data_ptr(), q_pos.data_ptr(), k_enc.data_ptr(), k_pos.data_ptr(),
               v.data_ptr(), k_enc.stride(0), k_pos.stride(0), v.stride(0), mask_bits.data_ptr(), mask_bits.shape[1],
               out.data_ptr(), dout.data_ptr(), lse.data_ptr(), delta.data_ptr(), P_all.data_ptr(), dS_all.data_ptr(),
-              dS_sum.data_ptr(), B, Q, N, 1.0 / math.sqrt(512.0), _stream())
+              dS_sum.data_ptr(), B, Q, N, 1.0 / math.sqrt(512.0), *_dargs(drop), _stream())
     Pv, dSv, dSs = P_all[:, :, :N], dS_all[:, :, :N], dS_sum[:, :, :N]
     v3 = lambda t: t.as_strided((B, N, 256), (N * t.stride(0), t.stride(0), 1))  # [B*N,256] view -> [B,N,256]
     do_v, qo_v, qp_v = dout.view(B, 2 * Q, 256), q_obj.view(B, 2 * Q, 256), q_pos.view(B, Q, 256)

@@ -48,7 +48,7 @@ def test_bad_arguments_fail_loudly_without_gpu():
     from object_detection_destr_b200 import _lib
     rc = _lib.lib.destr_add_layernorm_fwd(None, 256, None, 0, None, None, None, 256, None, None, 4, 256, None, 0, 0, None)
     assert rc != 0 and b"null pointer" in _lib.lib.destr_last_error()
-    rc = _lib.lib.destr_enc_attn_fwd(1, 1, 1, 256, 256, 256, 1, 4, 1, None, 1, 128, 9, 0.1, None)
+    rc = _lib.lib.destr_enc_attn_fwd(1, 1, 1, 256, 256, 256, 1, 4, 1, None, 1, 128, 9, 0.1, None, 0, 0, None)
     assert rc != 0 and b"shape" in _lib.lib.destr_last_error()
 
 
