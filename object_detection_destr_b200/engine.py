@@ -103,6 +103,9 @@ class GraphedTrainStep:
 
     # ---- pieces (also run eagerly during warm-up) ----
     def _forward(self):
+        rt = getattr(self.model, "_rt", None)
+        if rt is not None and any(rt._drop_config().values()):
+            rt.seed.add_(1)  # fresh dropout masks every step (device-side counter: also under graph replay)
         out, _ = self.model(self.s_feats, self.s_mask, self.s_sel, self.s_centers)
         with torch.no_grad():
             ops.match_cost_blockdiag(out["pred_class"].detach(), out["pred_boxes"].detach(), self.s_ids, self.s_tboxes,

@@ -87,8 +87,7 @@ class TransformerHalf(nn.Module):
         sel = selected_objects.reshape(B * Q, 512).to(BF16)
         if self.use_runtime:
             from .runtime import _RuntimeFn
-            _check_dropout(self)
-            rt = self.runtime()
+            rt = self.runtime()  # dropout (incl. the decoder's always-on attention dropout) is applied in the kernels
             dec, enc = _RuntimeFn.apply(rt, rt.anchor, x, pos, bits, kpm, sel, pos_embed, pos_embed, centers, B, N, Q,
                                         pairs_override, aux)
         else:

@@ -40,6 +40,10 @@ def _mm_bias(x: Tensor, w: Tensor, b: Tensor) -> Tensor:
     return torch.addmm(b, x, w.t())
 
 
+def _drop_scale(thr16: int) -> float:
+    return 65536.0 / (65536.0 - thr16)
+
+
 def _mm_bias_relu(x: Tensor, w: Tensor, b: Tensor) -> Tensor:
     # cuBLASLt GEMM with the bias + ReLU epilogue fused
     return torch._addmm_activation(b, x, w.t(), use_gelu=False)
@@ -277,16 +281,58 @@ class FlatAdamW:
             self.extra.step()
 
 
+# ids of the dropout calls ("sites") of the reference, one per call and layer; the mask of a site is a pure function
+# of (seed, site, row, column), so forward and backward agree without storing it (csrc/common.cuh)
+ENC_SITES = {"attn": 0, "d1": 1, "d2": 2, "d3": 3}                      # encoder_block.py:57-69, 97-109
+DEC_SITES = {"sa": 0, "d1a": 1, "d1b": 2, "ca": 3,                       # decoder_block.py:86,132,182-184,230
+             "b0.d_ca": 4, "b0.d_relu": 5, "b0.d_fc2": 6, "b1.d_ca": 7, "b1.d_relu": 8, "b1.d_fc2": 9}  # :234,253-256
+
+
+def enc_site(layer: int, name: str) -> int:
+    return 16 * layer + ENC_SITES[name]
+
+
+def dec_site(layer: int, name: str) -> int:
+    return 4096 + 32 * layer + DEC_SITES[name]
+
+
 class HotPathRuntime:
     """forward()/backward() of encoder -> fine_pos -> decoder on token-major bf16 activations."""
 
     def __init__(self, encoder: nn.Module, decoder: nn.Module, bbox_embed: nn.Module, device):
         self.P = FlatParams(encoder, decoder, device)
         self.bbox = bbox_embed
+        self.enc_mod, self.dec_mod = encoder, decoder
+        self.seed = torch.zeros(1, dtype=torch.int32, device=device)  # dropout seed (device: graph replays see updates)
         self.Le, self.Ld = self.P.Le, self.P.Ld
         self.saved = None
         self._bbox_cache = None
         self.anchor = torch.zeros(1, device=device, requires_grad=True)
+
+    # ------------------------------------------------------------------ dropout
+    def _drop_config(self):
+        """Dropout probabilities in force for this forward, as 16-bit thresholds.  nn.Dropout and
+        nn.MultiheadAttention(dropout=) act in training mode only; the reference's SelfAttention builds its
+        nn.Dropout inline (self_attention.py:40), so the decoder's attention-probability dropout is ALWAYS on."""
+        t = ops.drop_thr16
+        eb, db = self.enc_mod._encoder[0], self.dec_mod._decoder[0]
+        etr, dtr = self.enc_mod.training, self.dec_mod.training
+        cfg = {
+            "e.attn": t(eb.self_attn.dropout) if etr else 0,
+            "e.d1": t(eb.dropout1.p) if etr else 0, "e.d2": t(eb.dropout2.p) if etr else 0,
+            "e.d3": t(eb.dropout3.p) if etr else 0,
+            "d.sa": t(db._self_attn._dropout_prob),
+            "d.d1": t(db.dropout1.p) if dtr else 0,
+            "d.ca": t(db._cls_branch.cross_attn._dropout_prob),
+            "d.br": t(db._cls_branch.dropout.p) if dtr else 0,
+        }
+        return cfg
+
+    def _d(self, thr16: int, site: int, site2: Optional[int] = None):
+        """`drop` argument of an op: None when the site is inactive."""
+        if not thr16:
+            return None
+        return (self.seed, thr16, site) if site2 is None else (self.seed, thr16, site, site2)
 
     def _bbox_bf16(self):
         """bf16 copy of the box head's first layer, refreshed once per forward()."""
@@ -305,12 +351,17 @@ class HotPathRuntime:
         xq = ops.pos_mul_add(x, pos, s)
         qk = _mm_bias(xq, Win[:512], b_in[:512])
         P.join(0)
-        a, lse = ops.enc_attn_fwd(qk[:, :256], qk[:, 256:], v, bits, B, N, 8, 1.0 / math.sqrt(32))
+        dc = self.dc
+        a, lse = ops.enc_attn_fwd(qk[:, :256], qk[:, 256:], v, bits, B, N, 8, 1.0 / math.sqrt(32),
+                                  drop=self._d(dc["e.attn"], enc_site(l, "attn")))
         o = _mm_bias(a, P.w(f"e{l}.out_w"), P.w(f"e{l}.out_b"))
-        x1, m1, r1 = ops.add_layernorm(x, o, P.f(f"e{l}.n1_w"), P.f(f"e{l}.n1_b"), save_stats=True)
+        x1, m1, r1 = ops.add_layernorm(x, o, P.f(f"e{l}.n1_w"), P.f(f"e{l}.n1_b"), save_stats=True,
+                                       drop=self._d(dc["e.d1"], enc_site(l, "d1")))
         f1 = _mm_bias_relu(x1, P.w(f"e{l}.fc1_w"), P.w(f"e{l}.fc1_b"))
+        ops.dropout_inplace(f1, self._d(dc["e.d2"], enc_site(l, "d2")))
         g = _mm_bias(f1, P.w(f"e{l}.fc2_w"), P.w(f"e{l}.fc2_b"))
-        x2, m2, r2 = ops.add_layernorm(x1, g, P.f(f"e{l}.n2_w"), P.f(f"e{l}.n2_b"), save_stats=True)
+        x2, m2, r2 = ops.add_layernorm(x1, g, P.f(f"e{l}.n2_w"), P.f(f"e{l}.n2_b"), save_stats=True,
+                                       drop=self._d(dc["e.d3"], enc_site(l, "d3")))
         xo, m3, r3 = ops.add_layernorm(x, x2, P.f("e.n_w"), P.f("e.n_b"), save_stats=True)
         return xo, (x, h1, xq, qk, v, a, lse, o, x1, m1, r1, f1, g, x2, m2, r2, m3, r3)
 
@@ -320,19 +371,25 @@ class HotPathRuntime:
         # xo = LN(x + x2)
         d3, _, _ = ops.add_layernorm_bwd(dxo, x, x2, P.f("e.n_w"), m3, r3, dgamma=P.g("e.n_w"), dbeta=P.g("e.n_b"))
         # x2 = LN(x1 + fc2(relu(fc1 x1)))
-        d2, _, _ = ops.add_layernorm_bwd(d3, x1, g, P.f(f"e{l}.n2_w"), m2, r2, dgamma=P.g(f"e{l}.n2_w"),
-                                         dbeta=P.g(f"e{l}.n2_b"), dbias=P.g(f"e{l}.fc2_b"))
+        # (with dropout3 active the gradient splits: d2 goes through the mask into fc2, d2s is the un-masked residual)
+        dc = self.dc
+        r_ = ops.add_layernorm_bwd(d3, x1, g, P.f(f"e{l}.n2_w"), m2, r2, dgamma=P.g(f"e{l}.n2_w"),
+                                   dbeta=P.g(f"e{l}.n2_b"), dbias=P.g(f"e{l}.fc2_b"),
+                                   drop=self._d(dc["e.d3"], enc_site(l, "d3")), want_sum=bool(dc["e.d3"]))
+        d2, d2s = r_[0], (r_[3] if dc["e.d3"] else r_[0])
         P.acc_gw(f"e{l}.fc2_w", d2, f1)
         df1 = torch.mm(d2, P.w(f"e{l}.fc2_w"))
-        dpre = ops.relu_bwd_colsum(df1, f1, P.g(f"e{l}.fc1_b"))
+        dpre = ops.relu_bwd_colsum(df1, f1, P.g(f"e{l}.fc1_b"), scale=_drop_scale(dc["e.d2"]))
         P.acc_gw(f"e{l}.fc1_w", dpre, x1)
-        dx1 = torch.addmm(d2, dpre, P.w(f"e{l}.fc1_w"))
-        # x1 = LN(x + out_proj(attn));  dx = d3 + d1
+        dx1 = torch.addmm(d2s, dpre, P.w(f"e{l}.fc1_w"))
+        # x1 = LN(x + dropout1(out_proj(attn)));  dx = d3 + d(x1 input)
         d1, _, _, dx = ops.add_layernorm_bwd(dx1, x, o, P.f(f"e{l}.n1_w"), m1, r1, dgamma=P.g(f"e{l}.n1_w"),
-                                             dbeta=P.g(f"e{l}.n1_b"), dbias=P.g(f"e{l}.out_b"), res_in=d3)
+                                             dbeta=P.g(f"e{l}.n1_b"), dbias=P.g(f"e{l}.out_b"), res_in=d3,
+                                             drop=self._d(dc["e.d1"], enc_site(l, "d1")))
         P.acc_gw(f"e{l}.out_w", d1, a)
         da = torch.mm(d1, P.w(f"e{l}.out_w"))
-        dqk, dv = ops.enc_attn_bwd(qk[:, :256], qk[:, 256:], v, bits, a, da, lse, B, N, 8, 1.0 / math.sqrt(32))
+        dqk, dv = ops.enc_attn_bwd(qk[:, :256], qk[:, 256:], v, bits, a, da, lse, B, N, 8, 1.0 / math.sqrt(32),
+                                   drop=self._d(dc["e.attn"], enc_site(l, "attn")))
         gb = P.g(f"e{l}.in_b")
         P.off_path(lambda: (ops.relu_bwd_colsum(dqk, None, gb[:512]), ops.relu_bwd_colsum(dv, None, gb[512:])), dqk, dv)
         Win = P.w(f"e{l}.in_w")
@@ -377,25 +434,28 @@ class HotPathRuntime:
         pairs = ops.pair_indices(coords.view(B, Q, 4)) if pairs_ov is None else pairs_ov
         P.join(1)
         qkv, cat = ops.dec_qkv_prep(qkv_obj, qkpos_all[:, l * 512:(l + 1) * 512], pairs, B, Q)
-        o1, o2, lse1, lse2 = ops.dec_self_pair_attn_fwd(qkv, cat, B, Q)
+        dc = self.dc
+        o1, o2, lse1, lse2 = ops.dec_self_pair_attn_fwd(qkv, cat, B, Q, drop=self._d(dc["d.sa"], dec_site(l, "sa")))
         o, st = ops.dual_ln_mix(x, o1, o2, pairs, P.f(f"d{l}.n1_w"), P.f(f"d{l}.n1_b"), P.f(f"d{l}.n2_w"),
-                                P.f(f"d{l}.n2_b"), lam, Q)
+                                P.f(f"d{l}.n2_b"), lam, Q,
+                                drop=self._d(dc["d.d1"], dec_site(l, "d1a"), dec_site(l, "d1b")))
         qo = torch.mm(o, P.w(f"d{l}.cq_w").t())
         P.join(0)
         ke, vv = kv_all[:, l * 512:l * 512 + 256], kv_all[:, l * 512 + 256:(l + 1) * 512]
         kp = kpos_all[:, l * 256:(l + 1) * 256]
-        ca, lse_c = ops.split_cross_attn_fwd(qo, qp, ke, kp, vv, bits, B, Q, N)
+        ca, lse_c = ops.split_cross_attn_fwd(qo, qp, ke, kp, vv, bits, B, Q, N, drop=self._d(dc["d.ca"], dec_site(l, "ca")))
         y = torch.empty_like(x)
         br_saved = []
         for i in (1, 0):  # the class / box branches are independent: branch 1 is forked to the second stream
             sl = slice(i * 256, (i + 1) * 256)
             with P.fork(i == 1):
                 xb, mb1, rb1 = ops.add_layernorm(o[:, sl], ca[:, sl], P.f(f"d{l}.b{i}.n1_w"), P.f(f"d{l}.b{i}.n1_b"),
-                                                 save_stats=True)
+                                                 save_stats=True, drop=self._d(dc["d.br"], dec_site(l, f"b{i}.d_ca")))
                 f = _mm_bias_relu(xb, P.w(f"d{l}.b{i}.fc1_w"), P.w(f"d{l}.b{i}.fc1_b"))
+                ops.dropout_inplace(f, self._d(dc["d.br"], dec_site(l, f"b{i}.d_relu")))
                 g = _mm_bias(f, P.w(f"d{l}.b{i}.fc2_w"), P.w(f"d{l}.b{i}.fc2_b"))
                 _, mb2, rb2 = ops.add_layernorm(xb, g, P.f(f"d{l}.b{i}.n2_w"), P.f(f"d{l}.b{i}.n2_b"), save_stats=True,
-                                                out=y[:, sl])
+                                                out=y[:, sl], drop=self._d(dc["d.br"], dec_site(l, f"b{i}.d_fc2")))
             br_saved.append((xb, mb1, rb1, f, g, mb2, rb2))
         br_saved.reverse()
         P.join()
@@ -408,30 +468,37 @@ class HotPathRuntime:
         kv_all, kpos_all, sine, bits, kpm, B, Q, N, lam = ctx
         x, t1, sin, pairs, qkv, cat, o1, o2, lse1, lse2, o, st, qo, qp, ca, lse_c, y, br_saved, mn, rn = sv
         d, _, _ = ops.add_layernorm_bwd(dxo, x, y, P.f("d.n_w"), mn, rn, dgamma=P.g("d.n_w"), dbeta=P.g("d.n_b"))
-        dca = torch.empty_like(x)
+        dc = self.dc
+        dca = torch.empty_like(x)                               # d(cross-attention output): through the branch dropout
+        dres = torch.empty_like(x) if dc["d.br"] else dca       # d(o) along the residual: not masked
         for i in (1, 0):  # independent branches: branch 1 on the second stream
             sl = slice(i * 256, (i + 1) * 256)
             xb, mb1, rb1, f, g, mb2, rb2 = br_saved[i]
             pf = f"d{l}.b{i}."
             with P.fork(i == 1):
-                d2, _, _ = ops.add_layernorm_bwd(d[:, sl], xb, g, P.f(pf + "n2_w"), mb2, rb2, dgamma=P.g(pf + "n2_w"),
-                                                 dbeta=P.g(pf + "n2_b"), dbias=P.g(pf + "fc2_b"))
+                r_ = ops.add_layernorm_bwd(d[:, sl], xb, g, P.f(pf + "n2_w"), mb2, rb2, dgamma=P.g(pf + "n2_w"),
+                                           dbeta=P.g(pf + "n2_b"), dbias=P.g(pf + "fc2_b"),
+                                           drop=self._d(dc["d.br"], dec_site(l, f"b{i}.d_fc2")), want_sum=bool(dc["d.br"]))
+                d2, d2s = r_[0], (r_[3] if dc["d.br"] else r_[0])
                 P.acc_gw(pf + "fc2_w", d2, f)
                 df = torch.mm(d2, P.w(pf + "fc2_w"))
-                dpre = ops.relu_bwd_colsum(df, f, P.g(pf + "fc1_b"))
+                dpre = ops.relu_bwd_colsum(df, f, P.g(pf + "fc1_b"), scale=_drop_scale(dc["d.br"]))
                 P.acc_gw(pf + "fc1_w", dpre, xb)
-                dxb = torch.addmm(d2, dpre, P.w(pf + "fc1_w"))
+                dxb = torch.addmm(d2s, dpre, P.w(pf + "fc1_w"))
                 ops.add_layernorm_bwd(dxb, o[:, sl], ca[:, sl], P.f(pf + "n1_w"), mb1, rb1, dgamma=P.g(pf + "n1_w"),
-                                      dbeta=P.g(pf + "n1_b"), dx_out=dca[:, sl])
-                P._keep += [d2, df, dpre, dxb]
+                                      dbeta=P.g(pf + "n1_b"), dx_out=dca[:, sl],
+                                      drop=self._d(dc["d.br"], dec_site(l, f"b{i}.d_ca")), want_sum=bool(dc["d.br"]),
+                                      res_out=dres[:, sl] if dc["d.br"] else None)
+                P._keep += [d2, d2s, df, dpre, dxb]
         P.join()
         ke, vv = kv_all[:, l * 512:l * 512 + 256], kv_all[:, l * 512 + 256:(l + 1) * 512]
         kp = kpos_all[:, l * 256:(l + 1) * 256]
         dqo, dqp, _, _, _ = ops.split_cross_attn_bwd(
             qo, qp, ke, kp, vv, bits, ca, dca, lse_c, B, Q, N, dke_out=d_kv_all[:, l * 512:l * 512 + 256],
-            dkp_out=d_kpos_all[:, l * 256:(l + 1) * 256], dv_out=d_kv_all[:, l * 512 + 256:(l + 1) * 512])
+            dkp_out=d_kpos_all[:, l * 256:(l + 1) * 256], dv_out=d_kv_all[:, l * 512 + 256:(l + 1) * 512],
+            drop=self._d(dc["d.ca"], dec_site(l, "ca")))
         P.acc_gw(f"d{l}.cq_w", dqo, o)
-        do = torch.addmm(dca, dqo, P.w(f"d{l}.cq_w"))   # d(o) = d(o_cls|o_reg residual) + dq_obj W
+        do = torch.addmm(dres, dqo, P.w(f"d{l}.cq_w"))   # d(o) = d(o_cls|o_reg residual) + dq_obj W
         P.acc_gw(f"d{l}.cqp_w", dqp, sin)
         with P.fork(_FORK["DSIN"], k=0):  # sin = sine * pos_scale(x_reg): independent of the self/pair-attention chain below
             dsin = torch.mm(dqp, P.w(f"d{l}.cqp_w"))
@@ -441,9 +508,11 @@ class HotPathRuntime:
             self._pos_scale_bwd("d", dt2, t1, xr, dxr)
         dx2, do1, do2, delta1, delta2 = ops.dual_ln_mix_bwd(
             do, x, o1, o2, pairs, P.f(f"d{l}.n1_w"), P.f(f"d{l}.n2_w"), st, lam, Q,
-            pg=(P.g(f"d{l}.n1_w"), P.g(f"d{l}.n1_b"), P.g(f"d{l}.n2_w"), P.g(f"d{l}.n2_b")), head_major=True)
+            pg=(P.g(f"d{l}.n1_w"), P.g(f"d{l}.n1_b"), P.g(f"d{l}.n2_w"), P.g(f"d{l}.n2_b")), head_major=True,
+            drop=self._d(dc["d.d1"], dec_site(l, "d1a"), dec_site(l, "d1b")))
         dx = d + dx2
-        d_qkv, d_cat = ops.dec_self_pair_attn_bwd(qkv, cat, do1, do2, lse1, lse2, delta1, delta2, B, Q)
+        d_qkv, d_cat = ops.dec_self_pair_attn_bwd(qkv, cat, do1, do2, lse1, lse2, delta1, delta2, B, Q,
+                                                  drop=self._d(dc["d.sa"], dec_site(l, "sa")))
         d_qkv_obj, _ = ops.dec_qkv_prep_bwd(d_qkv, d_cat, pairs, B, Q,
                                             d_pos_out=d_qkpos_all[:, l * 512:(l + 1) * 512])
         P.acc_gw(f"d{l}.q_w", d_qkv_obj, x, rows=1536)
@@ -460,6 +529,7 @@ class HotPathRuntime:
         Returns (dec_out bf16 [B*Q,512], enc_out bf16 [B*N,256])."""
         P, Ld = self.P, self.Ld
         self._bbox_cache = None  # the box head is trained: re-cast it every step
+        self.dc = self._drop_config()  # dropout in force for this forward AND its backward
         enc_saved = []
         for l in range(self.Le):
             x, sv = self._enc_fwd(l, x, pos, bits, B, N)

@@ -34,6 +34,41 @@ SD = Dict[str, Tensor]
 # --------------------------------------------------------------------------------------
 # small math: a11 / a12
 # --------------------------------------------------------------------------------------
+# --------------------------------------------------------------------------------------
+# dropout hooks.  The reference's dropout sites are identity by default (the configuration
+# parity is defined on).  Tests that exercise the kernels' in-kernel dropout
+# install a `dropper` with the kernels' own counter-based masks (oracle/dropout_mask.py):
+#     with dropout(dropper): encoder_forward(...)
+# dropper.rows(prefix, name, x)      x (B,S,C): nn.Dropout on a token-major activation
+# dropper.attn(prefix, name, p)      p (B,H,Q,K): dropout on attention probabilities
+# `prefix` is the state-dict prefix of the module ("_encoder.3.", "_decoder.0._cls_branch."),
+# `name` the site inside it.
+# --------------------------------------------------------------------------------------
+_DROPPER = None
+
+
+class dropout:
+    def __init__(self, dropper):
+        self.dropper = dropper
+
+    def __enter__(self):
+        global _DROPPER
+        self._prev, _DROPPER = _DROPPER, self.dropper
+        return self
+
+    def __exit__(self, *exc):
+        global _DROPPER
+        _DROPPER = self._prev
+
+
+def _drop_rows(prefix: str, name: str, x: Tensor) -> Tensor:
+    return x if _DROPPER is None else _DROPPER.rows(prefix, name, x)
+
+
+def _drop_attn(site, p: Tensor) -> Tensor:
+    return p if (_DROPPER is None or site is None) else _DROPPER.attn(site[0], site[1], p)
+
+
 def inverse_sigmoid(x: Tensor, eps: float = 1e-6) -> Tensor:
     """logit with a lower clip only (src/utils/misc.py:59-62): -log(1/max(x,eps) - 1)."""
     return -torch.log(1.0 / x.clamp(min=eps) - 1.0)
@@ -162,8 +197,9 @@ def get_pairs(coords_cxcyhw: Tensor, eps: float = 1e-6) -> Tensor:
 
 
 def sdp_attention(q: Tensor, k: Tensor, v: Tensor, attn_mask: Optional[Tensor] = None,
-                  key_padding_mask: Optional[Tensor] = None) -> Tensor:
-    """SelfAttention.forward (src/model/attention/self_attention.py:18-47), dropout = identity.
+                  key_padding_mask: Optional[Tensor] = None, drop_site=None) -> Tensor:
+    """SelfAttention.forward (src/model/attention/self_attention.py:18-47); the dropout on the
+    probabilities (:40) is the hook `drop_site` (identity unless a dropper is installed).
 
     q (B,h,Sq,dq), k (B,h,Sk,dq), v (B,h,Sk,dv) -> (B,Sq,h*dv).  The scale is 1/sqrt of the
     LAST DIM OF q AS PASSED (:26)."""
@@ -172,7 +208,7 @@ def sdp_attention(q: Tensor, k: Tensor, v: Tensor, attn_mask: Optional[Tensor] =
         s = s.masked_fill(attn_mask, float("-inf")) if attn_mask.dtype == torch.bool else s + attn_mask
     if key_padding_mask is not None:
         s = s.masked_fill(key_padding_mask.bool()[:, None, None, :], float("-inf"))
-    p = s.softmax(-1)
+    p = _drop_attn(drop_site, s.softmax(-1))
     o = torch.einsum("bhqk,bhkd->bqhd", p, v)
     return o.reshape(o.shape[0], o.shape[1], -1)
 
@@ -229,16 +265,17 @@ def encoder_mha(x_qk: Tensor, x_v: Tensor, kpm: Optional[Tensor], sd: SD, prefix
     B, N, _ = q.shape
     dh = d // heads
     split = lambda t: t.reshape(B, N, heads, dh).transpose(1, 2)
-    o = sdp_attention(split(q), split(k), split(v), key_padding_mask=kpm)  # scale 1/sqrt(dh)
+    o = sdp_attention(split(q), split(k), split(v), key_padding_mask=kpm,  # scale 1/sqrt(dh)
+                      drop_site=(prefix[:-len("self_attn.")], "attn"))
     return F.linear(o, sd[prefix + "out_proj.weight"], sd[prefix + "out_proj.bias"])
 
 
 def encoder_block(x: Tensor, pos: Tensor, kpm: Optional[Tensor], sd: SD, prefix: str) -> Tensor:
     """EncoderBlock.forward (src/model/blocks/encoder_block.py:88-112), batch-first."""
     a = encoder_mha(x + pos, x, kpm, sd, prefix + "self_attn.")
-    x1 = _ln(x + a, sd, prefix + "norm1.")
-    f = F.linear(F.relu(F.linear(x1, sd[prefix + "fc1.weight"], sd[prefix + "fc1.bias"])),
-                 sd[prefix + "fc2.weight"], sd[prefix + "fc2.bias"])
+    x1 = _ln(x + _drop_rows(prefix, "d1", a), sd, prefix + "norm1.")
+    h = _drop_rows(prefix, "d2", F.relu(F.linear(x1, sd[prefix + "fc1.weight"], sd[prefix + "fc1.bias"])))
+    f = _drop_rows(prefix, "d3", F.linear(h, sd[prefix + "fc2.weight"], sd[prefix + "fc2.bias"]))
     return _ln(x1 + f, sd, prefix + "norm2.")
 
 
@@ -271,10 +308,10 @@ def cls_reg_branch(inp: Tensor, q512: Tensor, k512: Tensor, v256: Tensor, kpm: T
                    sd: SD, prefix: str) -> Tensor:
     """ClsRegBranch.forward (src/model/blocks/decoder_block.py:238-260): single-head
     cross-attention with scale 1/sqrt(512), post-LN residual, FFN 256->1024->256, post-LN."""
-    ca = sdp_attention(q512[:, None], k512[:, None], v256[:, None], key_padding_mask=kpm)
-    x = _ln(inp + ca, sd, prefix + "norm1.")
-    f = F.linear(F.relu(F.linear(x, sd[prefix + "fc1.weight"], sd[prefix + "fc1.bias"])),
-                 sd[prefix + "fc2.weight"], sd[prefix + "fc2.bias"])
+    ca = sdp_attention(q512[:, None], k512[:, None], v256[:, None], key_padding_mask=kpm, drop_site=(prefix, "ca"))
+    x = _ln(inp + _drop_rows(prefix, "d_ca", ca), sd, prefix + "norm1.")
+    h = _drop_rows(prefix, "d_relu", F.relu(F.linear(x, sd[prefix + "fc1.weight"], sd[prefix + "fc1.bias"])))
+    f = _drop_rows(prefix, "d_fc2", F.linear(h, sd[prefix + "fc2.weight"], sd[prefix + "fc2.bias"]))
     return _ln(x + f, sd, prefix + "norm2.")
 
 
@@ -301,9 +338,10 @@ def decoder_block(x: Tensor, enc_out: Tensor, coords: Tensor, pos_embed: Tensor,
     v = F.linear(x, w("_sa_proj_to_v_obj"))
     split = lambda t: t.reshape(B, Q, heads, D // heads).transpose(1, 2)
     q, k, v = split(q), split(k), split(v)
-    o1 = sdp_attention(q, k, v)
+    o1 = sdp_attention(q, k, v, drop_site=(prefix, "sa"))
     o2 = pair_self_attention(q, k, v, coords, pairs=pairs)
-    o = lam * _ln(x + o1, sd, prefix + "norm1.") + (1 - lam) * _ln(x + o2, sd, prefix + "norm2.")
+    o = lam * _ln(x + _drop_rows(prefix, "d1a", o1), sd, prefix + "norm1.") + \
+        (1 - lam) * _ln(x + _drop_rows(prefix, "d1b", o2), sd, prefix + "norm2.")
     o_cls, o_reg = o[..., :D // 2], o[..., D // 2:]
 
     q_obj = F.linear(o, w("_ca_proj_to_q_obj"))

@@ -111,3 +111,103 @@ def test_encoder_attention_dropout_fwd_bwd(B, N, heads):
     # and it really dropped something: the no-dropout output differs
     out0, _ = ops.enc_attn_fwd(qk_d[:, :C], qk_d[:, C:], v_d, bits, B, N, heads, scale)
     assert float((out0.float() - out.float()).abs().max()) > 0.05
+
+
+class TwinDropper:
+    """Feeds the oracle the masks the kernels generate (site numbering of runtime.py, rows/cols as in the kernels)."""
+
+    def __init__(self, seed, p=P):
+        from oracle.dropout_mask import thr16_of, scale_of
+        self.seed, self.thr = seed, thr16_of(p)
+        self.scale = scale_of(self.thr)
+
+    @staticmethod
+    def _site(prefix, name):
+        import re
+        from object_detection_destr_b200.runtime import dec_site, enc_site
+        l = int(re.search(r"\.(\d+)\.", prefix).group(1))
+        if prefix.startswith("_encoder."):
+            return enc_site(l, name)
+        if "_branch." in prefix:
+            if name == "ca":
+                return dec_site(l, "ca")
+            return dec_site(l, ("b0." if "_cls_branch" in prefix else "b1.") + name)
+        return dec_site(l, name)
+
+    def _m(self, site, rows, ncols, shape):
+        from oracle.dropout_mask import keep_mask
+        return (torch.from_numpy(keep_mask(self.seed, site, rows, np.arange(ncols), self.thr)).float() * self.scale).view(shape)
+
+    def rows(self, prefix, name, x):
+        B, S, C = x.shape
+        return x * self._m(self._site(prefix, name), np.arange(B * S), C, (B, S, C)).to(x.device)
+
+    def attn(self, prefix, name, p):
+        B, H, Q, K = p.shape
+        if name == "ca":  # (B,1,Q,N): mask row = (b, branch, query)
+            br = 0 if "_cls_branch" in prefix else 1
+            rows = ((np.arange(B)[:, None] * 2 + br) * Q + np.arange(Q)[None, :]).reshape(-1)
+        else:             # mask row = (b, head, query)
+            rows = np.arange(B * H * Q)
+        return p * self._m(self._site(prefix, name), rows, K, (B, H, Q, K)).to(p.device)
+
+
+def test_transformer_half_with_dropout_fwd_bwd():
+    """The whole hot path in TRAINING mode with the reference's default dropout (p = 0.3 at all 16 sites per layer
+    pair): outputs and every parameter gradient vs the fp32 oracle run with the SAME masks."""
+    from argparse import Namespace
+    from oracle import destr_oracle as O
+    from object_detection_destr_b200.hotpath import TransformerHalf
+    L, B, H, W, Q, C = 2, 2, 25, 42, 100, 91
+    g = torch.Generator().manual_seed(19)
+    enc_sd, dec_sd = O.make_encoder_weights(L, seed=41), O.make_decoder_weights(L, seed=42)
+    cls_sd, bbox_sd = O.make_head_weights(C, seed=43)
+    feats = torch.randn(B, 256, H, W, generator=g)
+    mask = torch.zeros(B, H, W, dtype=torch.bool)
+    mask[1, :, 35:] = True
+    sel = torch.randn(B, Q, 512, generator=g)
+    centers = 0.05 + 0.9 * torch.rand(B, Q, 2, generator=g)
+    seed = 4242
+    req = lambda sd: {k: v.clone().requires_grad_() for k, v in sd.items()}
+    r_e, r_d, r_c, r_b = req(enc_sd), req(dec_sd), req(cls_sd), req(bbox_sd)
+    with O.dropout(TwinDropper(seed)):
+        pos = O.sine_pos2d(mask)
+        enc = O.encoder_forward(feats, mask, pos, r_e, L)
+        fine = O.fine_pos_tokens(enc, pos, r_e)
+        dec, coords = O.decoder_forward(sel, enc.flatten(2).transpose(1, 2), mask.flatten(1), fine,
+                                        O.query_sine_embed(centers, 256), centers, r_d, r_b, L, return_coords=True)
+        ref = O.heads_forward(dec, centers, r_c, r_b)
+    ref_pairs = [O.get_pairs(c.detach()).int().cuda() for c in coords]
+    gcls, gbox = torch.randn(B, Q, C, generator=g), torch.randn(B, Q, 4, generator=g)
+    (ref["pred_class"] * gcls).sum().add((ref["pred_boxes"] * gbox).sum()).backward()
+
+    model = TransformerHalf(Namespace(hidden_dim=256, num_encoder_blocks=L, num_decoder_blocks=L, num_cls=C))
+    model._encoder.load_state_dict(enc_sd)
+    model._decoder.load_state_dict(dec_sd)
+    model._cls_embed.load_state_dict(cls_sd)
+    model._bbox_embed.load_state_dict(bbox_sd)
+    model.cuda().train()  # dropout stays at the reference defaults
+    model.runtime().seed.fill_(seed)
+    out, _ = model(feats.cuda(), mask.cuda(), sel.cuda(), centers.cuda(), pairs_override=ref_pairs)
+    (out["pred_class"] * gcls.cuda()).sum().add((out["pred_boxes"] * gbox.cuda()).sum()).backward()
+    rel = lambda a, b: float((a.float().cpu() - b).norm() / b.norm())
+    assert rel(out["pred_class"], ref["pred_class"].detach()) < 3e-2
+    assert float((out["pred_boxes"].cpu() - ref["pred_boxes"].detach()).abs().max()) < 3e-2
+    named = dict(model.named_parameters())
+    worst = 0.0
+    n = 0
+    for prefix, r_sd in (("_encoder.", r_e), ("_decoder.", r_d), ("_cls_embed.", r_c), ("_bbox_embed.", r_b)):
+        for k, v in r_sd.items():
+            if v.grad is None or named[prefix + k].grad is None:
+                continue
+            e = rel(named[prefix + k].grad, v.grad)
+            worst = max(worst, e)
+            n += 1
+            assert e < 8e-2, (prefix + k, e)
+    print(f"{n} parameter gradients with dropout, worst rel-fro error {worst:.3e}")
+    assert n > 100
+    # a different seed gives a different forward (the masks really depend on it)
+    model.runtime().seed.fill_(seed + 1)
+    with torch.no_grad():
+        out2, _ = model(feats.cuda(), mask.cuda(), sel.cuda(), centers.cuda(), pairs_override=ref_pairs)
+    assert float((out2["pred_class"] - out["pred_class"]).abs().max()) > 1e-2
