@@ -100,16 +100,34 @@ class ClockSampler(threading.Thread):
 # ----------------------------------------------------------------------------------------------------
 # reference arm: the reference algorithm (oracle port, fp32 eager torch) on the host CPU cores
 # ----------------------------------------------------------------------------------------------------
+class _TorchDropper:
+    """The reference's own dropout (nn.Dropout / F.dropout, p = 0.3 at every site) for the CPU arm's oracle hooks."""
+
+    def __init__(self, p: float):
+        self.p = p
+
+    def rows(self, prefix, name, x):
+        return torch.nn.functional.dropout(x, self.p, training=True)
+
+    def attn(self, prefix, name, p):
+        return torch.nn.functional.dropout(p, self.p, training=True)
+
+
 class CpuReference:
-    def __init__(self, cfg=CFG):
+    def __init__(self, cfg=CFG, dropout: float = 0.0):
         from oracle import destr_oracle as O
         self.O, self.cfg = O, cfg
+        self.dropper = _TorchDropper(dropout) if dropout > 0 else None
         req = lambda sd: {k: v.requires_grad_() for k, v in sd.items()}
         self.enc, self.dec = req(O.make_encoder_weights(cfg["L"], 0)), req(O.make_decoder_weights(cfg["L"], 1))
         c, b = O.make_head_weights(cfg["C"], 2)
         self.cls, self.bbox = req(c), req(b)
 
     def step(self, batch):
+        with self.O.dropout(self.dropper):
+            return self._step(batch)
+
+    def _step(self, batch):
         O, L = self.O, self.cfg["L"]
         feats, mask, sel, centers, labels, boxes = batch
         pos = O.sine_pos2d(mask)
@@ -130,9 +148,9 @@ class CpuReference:
         return float(loss.sum())
 
 
-def time_cpu_reference(sample_b: int, steps: int, warmup: int):
+def time_cpu_reference(sample_b: int, steps: int, warmup: int, dropout: float = 0.0):
     torch.set_num_threads(os.cpu_count() or 1)
-    ref = CpuReference()
+    ref = CpuReference(dropout=dropout)
     for s in range(warmup):
         ref.step(make_batch(0, s, sample_b))
     t0 = time.perf_counter()
@@ -148,11 +166,12 @@ def run_reference(args):
         return
     sample_b = CFG["B"]
     steps = max(1, min(args.steps, 10))
-    ips, spstep, cores = time_cpu_reference(sample_b, steps, min(args.warmup, 1))
+    ips, spstep, cores = time_cpu_reference(sample_b, steps, min(args.warmup, 1), 0.3 if args.dropout else 0.0)
     sample = f"{steps} steps of batch {sample_b} (the full config-2 batch; reference algorithm via oracle/destr_oracle.py, fp32 eager torch, all host threads)"
     line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": min(args.warmup, 1), "ms_per_step": spstep * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": CFG["workload"]},
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": CFG["workload"], "dropout": 0.3 if args.dropout else 0.0},
             "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -220,7 +239,10 @@ def run_ours(args):
     torch.manual_seed(0)
     model = TransformerHalf(Namespace(hidden_dim=256, num_encoder_blocks=cfg["L"], num_decoder_blocks=cfg["L"],
                                       num_cls=cfg["C"]))
-    disable_dropout(model).to(dev).train()
+    if args.dropout:
+        model.to(dev).train()      # the reference's defaults: p = 0.3 at every dropout site, applied inside the kernels
+    else:
+        disable_dropout(model).to(dev).train()
     opt = model.make_optimizer(lr=1e-5)  # AdamW: flat kernel over the runtime's parameter buffer + heads
     weights = {"class": 0.5, "bbox": 0.0, "ciou": 0.5}  # arg_parser.py:41-61 defaults
 
@@ -323,7 +345,7 @@ def run_ours(args):
                                                 "op_ms_with_prep_and_convert_launches": kernel_ms["destr_enc_attn_bwd_op"]}}}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            ips, spstep, cores = time_cpu_reference(1, 2, 1)
+            ips, spstep, cores = time_cpu_reference(1, 2, 1, 0.3 if args.dropout else 0.0)
             cpu = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
                    "sample": "2 steps of batch 1 through oracle/destr_oracle.py (fp32 eager torch, all host threads)"}
         imgs = B * world * args.steps
@@ -332,7 +354,7 @@ def run_ours(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": cfg["workload"], "global_batch": B * world, "parallelism": f"dp{world}",
                            "step": "fwd + matcher (cost kernel + device LSAP, bit-identical to scipy) + fused set loss + bwd + grad all-reduce + flat AdamW, one CUDA graph",
-                           "dropout": 0.0, "cuda_graphs": not args.eager, "l2": "4 rotating input batches; activations (~0.6 GB/step) exceed the 126 MB L2"},
+                           "dropout": 0.3 if args.dropout else 0.0, "cuda_graphs": not args.eager, "l2": "4 rotating input batches; activations (~0.6 GB/step) exceed the 126 MB L2"},
                 "e2e": {"value": imgs / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": int(h2d_bytes),
                         "d2h_bytes_per_step": 4 + 4 * B, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
@@ -357,6 +379,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="no CUDA graphs (debug / comparison)")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the end-to-end leg")
+    ap.add_argument("--no-dropout", dest="dropout", action="store_false",
+                    help="p = 0 at every dropout site (the parity configuration) instead of the reference's training "
+                         "default p = 0.3; applies to both arms")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
