@@ -244,6 +244,7 @@ def run_ours(args):
     else:
         disable_dropout(model).to(dev).train()
     opt = model.make_optimizer(lr=1e-5)  # AdamW: flat kernel over the runtime's parameter buffer + heads
+    model.runtime().seed.fill_(7919 * rank + 1)  # dropout streams differ across ranks, like independent workers' RNGs
     weights = {"class": 0.5, "bbox": 0.0, "ciou": 0.5}  # arg_parser.py:41-61 defaults
 
     n_batches = 4
