@@ -14,7 +14,7 @@ from torch import nn
 
 from . import functional as Fn
 from . import ops
-from .encoder import _check_dropout, _params
+from .encoder import _params, drop_scope
 
 BF16 = torch.bfloat16
 
@@ -32,9 +32,6 @@ class SelfAttention(nn.Module):
 
     def forward(self, query, key, value, attn_mask: Optional[torch.Tensor] = None,
                 key_padding_mask: Optional[torch.Tensor] = None):
-        if self._dropout_prob > 0:
-            raise NotImplementedError("attention-probability dropout is not implemented in the B200 kernels yet; "
-                                      "set _dropout_prob = 0 (disable_dropout(model)); see DESIGN.md")
         if attn_mask is not None:
             raise NotImplementedError("attn_mask is never passed by the reference decoder (decoder_block.py:179,246)")
         B, H, Sq, dq = query.shape
@@ -44,7 +41,8 @@ class SelfAttention(nn.Module):
             qkv = torch.cat([tok(query), tok(key), tok(value)], dim=-1)
             ident = torch.arange(Sq, device=query.device, dtype=torch.int32)[None, :, None].expand(B, Sq, 2).contiguous()
             qkv2, cat = Fn._DecQkvPrep.apply(qkv, torch.zeros(B * Sq, 512, dtype=BF16, device=query.device), ident, B, Sq)
-            o1, _ = Fn._DecSelfPairAttn.apply(qkv2, cat, B, Sq)
+            with drop_scope(self, query.device):  # the inline nn.Dropout of the reference: always on (self_attention.py:40)
+                o1, _ = Fn._DecSelfPairAttn.apply(qkv2, cat, B, Sq, Fn._dr("d.sa", Fn._dec_site(0, "sa")))
             return o1.view(B, Sq, 512).to(query.dtype)
         if H == 1 and dq == 512 and dv == 256:
             q = tok(query)
@@ -52,7 +50,9 @@ class SelfAttention(nn.Module):
             bits = ops.pack_key_mask(key_padding_mask, B, Sk, device=query.device)
             kpm = None if key_padding_mask is None else key_padding_mask.contiguous()
             q_obj = torch.cat([q[:, :256], q[:, :256]], dim=-1)
-            out = Fn._SplitCrossAttn.apply(q_obj, q[:, 256:].contiguous(), k[:, :256], k[:, 256:], v, bits, kpm, B, Sq, Sk)
+            with drop_scope(self, query.device):
+                out = Fn._SplitCrossAttn.apply(q_obj, q[:, 256:].contiguous(), k[:, :256], k[:, 256:], v, bits, kpm, B, Sq,
+                                               Sk, Fn._dr("d.ca", Fn._dec_site(0, "ca")))
             return out[:, :256].reshape(B, Sq, 256).to(query.dtype)
         raise NotImplementedError(f"SelfAttention shape (H={H}, d_qk={dq}, d_v={dv}) is not on the DESTR hot path")
 
@@ -96,15 +96,18 @@ class ClsRegBranch(nn.Module):
         self.norm2 = nn.LayerNorm(hidden_dim)
 
     def forward(self, inputs, query, key, value, key_mask):
-        _check_dropout(self)
         B, Q, d = inputs.shape
         ca = self.cross_attn(query=query.unsqueeze(1), key=key.unsqueeze(1), value=value.unsqueeze(1),
                              key_padding_mask=key_mask)
         p = _params(self)
-        xb = Fn.add_layernorm(inputs.reshape(B * Q, d).to(BF16), ca.reshape(B * Q, d).to(BF16), p["norm1.weight"],
-                              p["norm1.bias"])
-        f = Fn.linear(torch.relu(Fn.linear(xb, p["fc1.weight"], p["fc1.bias"])), p["fc2.weight"], p["fc2.bias"])
-        return Fn.add_layernorm(xb, f, p["norm2.weight"], p["norm2.bias"]).view(B, Q, d).to(inputs.dtype)
+        S = Fn._dec_site
+        with drop_scope(self, inputs.device):
+            xb = Fn.add_layernorm(inputs.reshape(B * Q, d).to(BF16), ca.reshape(B * Q, d).to(BF16), p["norm1.weight"],
+                                  p["norm1.bias"], Fn._dr("d.br", S(0, "b0.d_ca")))
+            h = Fn.dropout(torch.relu(Fn.linear(xb, p["fc1.weight"], p["fc1.bias"])), Fn._dr("d.br", S(0, "b0.d_relu")))
+            f = Fn.linear(h, p["fc2.weight"], p["fc2.bias"])
+            y = Fn.add_layernorm(xb, f, p["norm2.weight"], p["norm2.bias"], Fn._dr("d.br", S(0, "b0.d_fc2")))
+        return y.view(B, Q, d).to(inputs.dtype)
 
 
 class DecoderBlock(nn.Module):
@@ -140,7 +143,6 @@ class DecoderBlock(nn.Module):
                 enc_key_mask):
         """Reference signature (decoder_block.py:157-166): obj_selected (B,Q,512); enc_output, enc_pos_embed
         (B,N,256); obj_coords (B,Q,4) cxcyhw; obj_pos_embed, obj_sin_embed (B,Q,256); enc_key_mask (B,N) bool."""
-        _check_dropout(self)
         B, Q, _ = obj_selected.shape
         N = enc_output.shape[1]
         t = lambda a: a.reshape(-1, a.shape[-1]).to(BF16)
@@ -151,8 +153,9 @@ class DecoderBlock(nn.Module):
         qk_pos = Fn.linear(t(obj_pos_embed), torch.cat([p["blk._sa_proj_to_q_pos.weight"], p["blk._sa_proj_to_k_pos.weight"]]))
         kv = Fn.linear(t(enc_output), torch.cat([p["blk._ca_proj_to_k_enc.weight"], p["blk._ca_proj_to_v_enc.weight"]]))
         k_pos = Fn.linear(t(enc_pos_embed), p["blk._ca_proj_to_k_pos.weight"])
-        y = Fn.decoder_block_core(t(obj_selected), t(obj_sin_embed), pairs, qk_pos, kv[:, :256], k_pos, kv[:, 256:],
-                                  bits, kpm, p, "blk.", B, Q, N, self._lambda)
+        with drop_scope(self, obj_selected.device):
+            y = Fn.decoder_block_core(t(obj_selected), t(obj_sin_embed), pairs, qk_pos, kv[:, :256], k_pos, kv[:, 256:],
+                                      bits, kpm, p, "blk.", B, Q, N, self._lambda)
         return y.view(B, Q, 512).to(obj_selected.dtype)
 
 
@@ -168,9 +171,9 @@ class Decoder(nn.Module):
 
     def forward_tokens(self, x, enc_out, bits, kpm, fine_pos, pos_embed, centers, bbox_embed: nn.Module, B, Q, N):
         """Token-major fast path (bf16 [rows, C] activations, fp32 centers [B*Q,2])."""
-        _check_dropout(self)
-        return Fn.decoder_tokens(x, enc_out, bits, kpm, fine_pos, pos_embed, centers, _params(self),
-                                 _params(bbox_embed), self._num_dec, B, Q, N)
+        with drop_scope(self, x.device):
+            return Fn.decoder_tokens(x, enc_out, bits, kpm, fine_pos, pos_embed, centers, _params(self),
+                                     _params(bbox_embed), self._num_dec, B, Q, N)
 
     def forward(self, selected_objects, encoder_output, mask, fine_pos, selected_objects_pos_embed,
                 selected_centers, bbox_embed: nn.Module):

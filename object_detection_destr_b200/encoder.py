@@ -56,13 +56,13 @@ class EncoderBlock(nn.Module):
         """inputs, pos_embed: (N, B, 256) seq-first as in the reference; key_mask (B, N) bool."""
         if mask is not None:
             raise NotImplementedError("attn_mask is never used by the reference encoder (encoder_block.py:35-39)")
-        _check_dropout(self)
         N, B, d = inputs.shape
         x = inputs.transpose(0, 1).reshape(B * N, d).to(BF16)
         pos = pos_embed.transpose(0, 1).reshape(B * N, d).to(BF16)
         bits = ops.pack_key_mask(key_mask, B, N, device=inputs.device)
         p = {"blk." + k: v for k, v in self.named_parameters()}
-        y = _block_only(x, pos, bits, p, "blk.", B, N)
+        with drop_scope(self, inputs.device):
+            y = _block_only(x, pos, bits, p, "blk.", B, N)
         return y.view(B, N, d).transpose(0, 1).to(inputs.dtype)
 
 
@@ -73,23 +73,60 @@ def _block_only(x, pos, bits, p, lp, B, N):
     d = x.shape[-1]
     qk = Fn.linear(xq, W[: 2 * d], bias[: 2 * d])
     v = Fn.linear(x, W[2 * d:], bias[2 * d:])
-    a = Fn.enc_attn(qk, v, bits, B, N, 8)
+    S = Fn._enc_site
+    a = Fn.enc_attn(qk, v, bits, B, N, 8, drop=Fn._dr("e.attn", S(0, "attn")))
     o = Fn.linear(a, p[lp + "self_attn.out_proj.weight"], p[lp + "self_attn.out_proj.bias"])
-    x1 = Fn.add_layernorm(x, o, p[lp + "norm1.weight"], p[lp + "norm1.bias"])
-    f = Fn.linear(torch.relu(Fn.linear(x1, p[lp + "fc1.weight"], p[lp + "fc1.bias"])), p[lp + "fc2.weight"],
-                  p[lp + "fc2.bias"])
-    return Fn.add_layernorm(x1, f, p[lp + "norm2.weight"], p[lp + "norm2.bias"])
+    x1 = Fn.add_layernorm(x, o, p[lp + "norm1.weight"], p[lp + "norm1.bias"], Fn._dr("e.d1", S(0, "d1")))
+    h = Fn.dropout(torch.relu(Fn.linear(x1, p[lp + "fc1.weight"], p[lp + "fc1.bias"])), Fn._dr("e.d2", S(0, "d2")))
+    f = Fn.linear(h, p[lp + "fc2.weight"], p[lp + "fc2.bias"])
+    return Fn.add_layernorm(x1, f, p[lp + "norm2.weight"], p[lp + "norm2.bias"], Fn._dr("e.d3", S(0, "d3")))
 
 
 def _check_dropout(module: nn.Module):
-    if module.training:
-        for m in module.modules():
-            p_drop = m.p if isinstance(m, nn.Dropout) else (m.dropout if isinstance(m, nn.MultiheadAttention) else
-                                                            getattr(m, "_dropout_prob", 0.0))
-            if p_drop > 0:
-                raise NotImplementedError(
-                    "train-mode dropout is not implemented in the B200 kernels yet: set every nn.Dropout.p = 0 "
-                    "(object_detection_destr_b200.disable_dropout(model)) or call .eval(); see DESIGN.md")
+    """(kept for callers that predate in-kernel dropout: nothing to refuse any more)"""
+    return None
+
+
+def drop_scope(module: nn.Module, device, seed: Optional[torch.Tensor] = None):
+    """Context that installs the dropout in force for `module`'s forward (functional.dropout_ctx): the probabilities
+    are read from the module tree the way the reference applies them -- nn.Dropout and nn.MultiheadAttention(dropout=)
+    only in training mode, the SelfAttention attention-probability dropout ALWAYS (it builds its nn.Dropout inline,
+    self_attention.py:40).  The seed is a per-module device counter (not a registered buffer: state_dict keys stay the
+    reference's), bumped on every forward; `set_dropout_seed(module, v)` pins it."""
+    t = ops.drop_thr16
+    thr = {}
+    tr = module.training
+    for m in module.modules():
+        cls = type(m).__name__
+        if isinstance(m, nn.MultiheadAttention):
+            thr["e.attn"] = t(m.dropout) if tr else 0
+        elif cls == "EncoderBlock":
+            thr.update({"e.d1": t(m.dropout1.p) if tr else 0, "e.d2": t(m.dropout2.p) if tr else 0,
+                        "e.d3": t(m.dropout3.p) if tr else 0})
+        elif cls == "DecoderBlock":
+            thr.update({"d.sa": t(m._self_attn._dropout_prob), "d.d1": t(m.dropout1.p) if tr else 0})
+        elif cls == "ClsRegBranch":
+            thr.update({"d.ca": t(m.cross_attn._dropout_prob), "d.br": t(m.dropout.p) if tr else 0})
+        elif cls == "SelfAttention" and m is module:  # stand-alone use
+            thr.update({"d.sa": t(m._dropout_prob), "d.ca": t(m._dropout_prob)})
+    if seed is None:
+        seed = getattr(module, "_drop_seed_t", None)
+        if seed is None or seed.device != torch.device(device):
+            seed = torch.zeros(1, dtype=torch.int32, device=device)
+            object.__setattr__(module, "_drop_seed_t", seed)
+        if any(thr.values()) and not getattr(module, "_drop_seed_pinned", False):
+            seed.add_(1)
+    return Fn.dropout_ctx(seed, thr)
+
+
+def set_dropout_seed(module: nn.Module, value: int, device=None):
+    """Pin the dropout seed of a drop-in module (tests, reproducibility): no automatic bump until reset with None."""
+    dev = device or next(module.parameters()).device
+    if value is None:
+        object.__setattr__(module, "_drop_seed_pinned", False)
+        return
+    object.__setattr__(module, "_drop_seed_t", torch.full((1,), int(value), dtype=torch.int32, device=dev))
+    object.__setattr__(module, "_drop_seed_pinned", True)
 
 
 class Encoder(nn.Module):
@@ -104,8 +141,8 @@ class Encoder(nn.Module):
 
     def forward_tokens(self, x: torch.Tensor, pos: torch.Tensor, bits: torch.Tensor, B: int, N: int):
         """Token-major fast path: x, pos bf16 [B*N, 256] -> bf16 [B*N, 256]."""
-        _check_dropout(self)
-        return Fn.encoder_tokens(x, pos, bits, _params(self), self._num_enc, B, N)
+        with drop_scope(self, x.device):
+            return Fn.encoder_tokens(x, pos, bits, _params(self), self._num_enc, B, N)
 
     def forward(self, inputs, mask, pos_embed):
         """inputs, pos_embed (B,256,H,W); mask (B,H,W) bool -> (B,256,H,W)  (reference signature)."""

@@ -18,6 +18,45 @@ Tensor = torch.Tensor
 BF16 = torch.bfloat16
 
 
+# ----------------------------------------------------------------------------------------------
+# dropout context: the modules install the probabilities in force (as 16-bit thresholds, keys as in
+# runtime.HotPathRuntime._drop_config) and a device seed; the functions below turn a (kind, site) into the `drop`
+# argument of the kernels.  No context / threshold 0 -> no dropout.
+# ----------------------------------------------------------------------------------------------
+_CTX = None
+
+
+class dropout_ctx:
+    def __init__(self, seed: Optional[Tensor], thr: Optional[Dict[str, int]]):
+        self.seed, self.thr = seed, thr or {}
+
+    def __enter__(self):
+        global _CTX
+        self._prev, _CTX = _CTX, (self if any(self.thr.values()) else None)
+        return self
+
+    def __exit__(self, *exc):
+        global _CTX
+        _CTX = self._prev
+
+
+def _dr(kind: str, site: int, site2: Optional[int] = None):
+    if _CTX is None or not _CTX.thr.get(kind, 0):
+        return None
+    t = _CTX.thr[kind]
+    return (_CTX.seed, t, site) if site2 is None else (_CTX.seed, t, site, site2)
+
+
+def _enc_site(layer: int, name: str) -> int:
+    from .runtime import enc_site
+    return enc_site(layer, name)
+
+
+def _dec_site(layer: int, name: str) -> int:
+    from .runtime import dec_site
+    return dec_site(layer, name)
+
+
 class _PosMulAdd(torch.autograd.Function):
     """y = x + pos * s   (encoder_block.py:38,95)."""
 
@@ -37,27 +76,47 @@ class _AddLayerNorm(torch.autograd.Function):
     """y = LayerNorm(a + b)."""
 
     @staticmethod
-    def forward(ctx, a, b, gamma, beta):
-        y, mean, rstd = ops.add_layernorm(a, b, gamma, beta, save_stats=True)
+    def forward(ctx, a, b, gamma, beta, drop=None):
+        y, mean, rstd = ops.add_layernorm(a, b, gamma, beta, save_stats=True, drop=drop)
         ctx.save_for_backward(a, b, gamma, mean, rstd)
+        ctx.drop = drop
         return y
 
     @staticmethod
     def backward(ctx, dy):
         a, b, gamma, mean, rstd = ctx.saved_tensors
-        dx, dg, db = ops.add_layernorm_bwd(dy, a, b, gamma, mean, rstd)
-        return dx, dx, dg, db
+        if ctx.drop is None:
+            dx, dg, db = ops.add_layernorm_bwd(dy, a, b, gamma, mean, rstd)
+            return dx, dx, dg, db, None
+        # y = LN(a + dropout(b)): d(b) goes through the mask, d(a) does not
+        dxb, dg, db, dsum = ops.add_layernorm_bwd(dy, a, b, gamma, mean, rstd, drop=ctx.drop, want_sum=True)
+        return dsum, dxb, dg, db, None
+
+
+class _Dropout(torch.autograd.Function):
+    """nn.Dropout on a bf16 [M,C] activation with the kernels' counter-based mask (the mask is linear: the backward
+    applies the same mask to the gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, drop):
+        ctx.drop = drop
+        return ops.dropout_inplace(x.contiguous().clone(), drop)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.dropout_inplace(dy.contiguous().clone(), ctx.drop), None
 
 
 class _EncAttn(torch.autograd.Function):
     """Fused encoder attention; qk = [q | k] projection output, v projection output."""
 
     @staticmethod
-    def forward(ctx, qk, v, bits, B, N, heads, scale):
+    def forward(ctx, qk, v, bits, B, N, heads, scale, drop=None):
         C = heads * 32
-        out, lse = ops.enc_attn_fwd(qk[:, :C], qk[:, C:], v, bits, B, N, heads, scale)
+        out, lse = ops.enc_attn_fwd(qk[:, :C], qk[:, C:], v, bits, B, N, heads, scale, drop=drop)
         ctx.save_for_backward(qk, v, bits, out, lse)
         ctx.dims = (B, N, heads, scale)
+        ctx.drop = drop
         return out
 
     @staticmethod
@@ -65,20 +124,24 @@ class _EncAttn(torch.autograd.Function):
         qk, v, bits, out, lse = ctx.saved_tensors
         B, N, heads, scale = ctx.dims
         C = heads * 32
-        dqk, dv = ops.enc_attn_bwd(qk[:, :C], qk[:, C:], v, bits, out, dout, lse, B, N, heads, scale)
-        return dqk, dv, None, None, None, None, None
+        dqk, dv = ops.enc_attn_bwd(qk[:, :C], qk[:, C:], v, bits, out, dout, lse, B, N, heads, scale, drop=ctx.drop)
+        return dqk, dv, None, None, None, None, None, None
 
 
 def pos_mul_add(x, pos, s):
     return _PosMulAdd.apply(x, pos, s)
 
 
-def add_layernorm(a, b, gamma, beta):
-    return _AddLayerNorm.apply(a, b, gamma, beta)
+def add_layernorm(a, b, gamma, beta, drop=None):
+    return _AddLayerNorm.apply(a, b, gamma, beta, drop)
 
 
-def enc_attn(qk, v, bits, B, N, heads=8):
-    return _EncAttn.apply(qk, v, bits, B, N, heads, 1.0 / math.sqrt(32))
+def dropout(x, drop):
+    return x if drop is None else _Dropout.apply(x, drop)
+
+
+def enc_attn(qk, v, bits, B, N, heads=8, drop=None):
+    return _EncAttn.apply(qk, v, bits, B, N, heads, 1.0 / math.sqrt(32), drop)
 
 
 def linear(x: Tensor, w: Tensor, b: Optional[Tensor] = None) -> Tensor:
@@ -95,7 +158,7 @@ def mlp2(x: Tensor, p: Dict[str, Tensor], prefix: str) -> Tensor:
 # encoder  (reference: src/model/blocks/encoder_block.py)
 # ----------------------------------------------------------------------------------------------
 def encoder_layer(x: Tensor, pos: Tensor, bits: Tensor, p: Dict[str, Tensor], lp: str, B: int, N: int,
-                  heads: int = 8) -> Tensor:
+                  heads: int = 8, layer: int = 0) -> Tensor:
     """One `x = norm(x + EncoderBlock(x, pos*pos_scale(x)))` step (encoder_block.py:33-40, 88-112).
     x, pos: bf16 [B*N, 256]."""
     s = mlp2(x, p, "_pos_scale.")
@@ -104,19 +167,19 @@ def encoder_layer(x: Tensor, pos: Tensor, bits: Tensor, p: Dict[str, Tensor], lp
     d = x.shape[-1]
     qk = linear(xq, W[: 2 * d], bias[: 2 * d])
     v = linear(x, W[2 * d:], bias[2 * d:])
-    a = enc_attn(qk, v, bits, B, N, heads)
+    a = enc_attn(qk, v, bits, B, N, heads, drop=_dr("e.attn", _enc_site(layer, "attn")))
     o = linear(a, p[lp + "self_attn.out_proj.weight"], p[lp + "self_attn.out_proj.bias"])
-    x1 = add_layernorm(x, o, p[lp + "norm1.weight"], p[lp + "norm1.bias"])
-    f = linear(torch.relu(linear(x1, p[lp + "fc1.weight"], p[lp + "fc1.bias"])), p[lp + "fc2.weight"],
-               p[lp + "fc2.bias"])
-    x2 = add_layernorm(x1, f, p[lp + "norm2.weight"], p[lp + "norm2.bias"])
+    x1 = add_layernorm(x, o, p[lp + "norm1.weight"], p[lp + "norm1.bias"], _dr("e.d1", _enc_site(layer, "d1")))
+    h = dropout(torch.relu(linear(x1, p[lp + "fc1.weight"], p[lp + "fc1.bias"])), _dr("e.d2", _enc_site(layer, "d2")))
+    f = linear(h, p[lp + "fc2.weight"], p[lp + "fc2.bias"])
+    x2 = add_layernorm(x1, f, p[lp + "norm2.weight"], p[lp + "norm2.bias"], _dr("e.d3", _enc_site(layer, "d3")))
     return add_layernorm(x, x2, p["norm.weight"], p["norm.bias"])
 
 
 def encoder_tokens(x: Tensor, pos: Tensor, bits: Tensor, p: Dict[str, Tensor], num_layers: int, B: int, N: int):
     """Encoder.forward on token-major bf16 activations."""
     for l in range(num_layers):
-        x = encoder_layer(x, pos, bits, p, f"_encoder.{l}.", B, N)
+        x = encoder_layer(x, pos, bits, p, f"_encoder.{l}.", B, N, layer=l)
     return x
 
 
@@ -141,17 +204,18 @@ class _DualLnMix(torch.autograd.Function):
     """lam*LN1(x+o1) + (1-lam)*LN2(x+o2eff) with the pair-attention slot masking fused."""
 
     @staticmethod
-    def forward(ctx, x, o1, o2, pairs, g1, b1, g2, b2, lam, Q):
-        out, stats = ops.dual_ln_mix(x, o1, o2, pairs, g1, b1, g2, b2, lam, Q)
+    def forward(ctx, x, o1, o2, pairs, g1, b1, g2, b2, lam, Q, drop=None):
+        out, stats = ops.dual_ln_mix(x, o1, o2, pairs, g1, b1, g2, b2, lam, Q, drop=drop)
         ctx.save_for_backward(x, o1, o2, pairs, g1, g2, stats)
-        ctx.lam, ctx.Q = lam, Q
+        ctx.lam, ctx.Q, ctx.drop = lam, Q, drop
         return out
 
     @staticmethod
     def backward(ctx, dout):
         x, o1, o2, pairs, g1, g2, stats = ctx.saved_tensors
-        dx, do1, do2, dg1, db1, dg2, db2 = ops.dual_ln_mix_bwd(dout, x, o1, o2, pairs, g1, g2, stats, ctx.lam, ctx.Q)
-        return dx, do1, do2, None, dg1, db1, dg2, db2, None, None
+        dx, do1, do2, dg1, db1, dg2, db2 = ops.dual_ln_mix_bwd(dout, x, o1, o2, pairs, g1, g2, stats, ctx.lam, ctx.Q,
+                                                               drop=ctx.drop)
+        return dx, do1, do2, None, dg1, db1, dg2, db2, None, None, None
 
 
 class _DecQkvPrep(torch.autograd.Function):
@@ -173,10 +237,11 @@ class _DecQkvPrep(torch.autograd.Function):
 
 class _DecSelfPairAttn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, qkv, cat, B, Q):
-        o1, o2, lse1, lse2 = ops.dec_self_pair_attn_fwd(qkv, cat, B, Q)
+    def forward(ctx, qkv, cat, B, Q, drop=None):
+        o1, o2, lse1, lse2 = ops.dec_self_pair_attn_fwd(qkv, cat, B, Q, drop=drop)
         ctx.save_for_backward(qkv, cat, o1, o2, lse1, lse2)
         ctx.dims = (B, Q)
+        ctx.drop = drop
         return o1, o2
 
     @staticmethod
@@ -187,24 +252,26 @@ class _DecSelfPairAttn(torch.autograd.Function):
         d1, d2 = hm(do1, 64), hm(do2, 128)
         delta1 = (d1.float() * hm(o1, 64).float()).sum(-1)
         delta2 = (d2.float() * hm(o2, 128).float()).sum(-1)
-        d_qkv, d_cat = ops.dec_self_pair_attn_bwd(qkv, cat, d1, d2, lse1, lse2, delta1, delta2, B, Q)
-        return d_qkv, d_cat, None, None
+        d_qkv, d_cat = ops.dec_self_pair_attn_bwd(qkv, cat, d1, d2, lse1, lse2, delta1, delta2, B, Q, drop=ctx.drop)
+        return d_qkv, d_cat, None, None, None
 
 
 class _SplitCrossAttn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q_obj, q_pos, k_enc, k_pos, v, bits, kpm, B, Q, N):
-        out, lse = ops.split_cross_attn_fwd(q_obj, q_pos, k_enc, k_pos, v, bits, B, Q, N)
+    def forward(ctx, q_obj, q_pos, k_enc, k_pos, v, bits, kpm, B, Q, N, drop=None):
+        out, lse = ops.split_cross_attn_fwd(q_obj, q_pos, k_enc, k_pos, v, bits, B, Q, N, drop=drop)
         ctx.save_for_backward(q_obj, q_pos, k_enc, k_pos, v, bits, out, lse)
         ctx.dims = (B, Q, N)
+        ctx.drop = drop
         return out
 
     @staticmethod
     def backward(ctx, dout):
         q_obj, q_pos, k_enc, k_pos, v, bits, out, lse = ctx.saved_tensors
         B, Q, N = ctx.dims
-        g = ops.split_cross_attn_bwd(q_obj, q_pos, k_enc, k_pos, v, bits, out, dout.contiguous(), lse, B, Q, N)
-        return g + (None, None, None, None, None)
+        g = ops.split_cross_attn_bwd(q_obj, q_pos, k_enc, k_pos, v, bits, out, dout.contiguous(), lse, B, Q, N,
+                                     drop=ctx.drop)
+        return g + (None, None, None, None, None, None)
 
 
 def decoder_hoisted_projections(enc_out: Tensor, fine_pos: Tensor, pos_embed: Tensor, p: Dict[str, Tensor],
@@ -224,7 +291,7 @@ def decoder_hoisted_projections(enc_out: Tensor, fine_pos: Tensor, pos_embed: Te
 
 def decoder_block_core(x: Tensor, sin_embed: Tensor, pairs: Tensor, qk_pos: Tensor, k_enc: Tensor, k_pos: Tensor,
                        v: Tensor, bits: Tensor, kpm: Optional[Tensor], p: Dict[str, Tensor], lp: str, B: int, Q: int,
-                       N: int, lam: float = 0.5) -> Tensor:
+                       N: int, lam: float = 0.5, layer: int = 0) -> Tensor:
     """DecoderBlock.forward (decoder_block.py:157-220) given the projected keys/values.
     x bf16 [B*Q,512]; sin_embed bf16 [B*Q,256]; pairs int32 [B,Q,2]; qk_pos bf16 [B*Q,512] = [W_q_pos p | W_k_pos p];
     k_enc, k_pos, v bf16 [B*N,256] views.  Returns cat(cls, reg) bf16 [B*Q,512]."""
@@ -232,20 +299,22 @@ def decoder_block_core(x: Tensor, sin_embed: Tensor, pairs: Tensor, qk_pos: Tens
                       p[lp + "_sa_proj_to_v_obj.weight"]])
     qkv_obj = linear(x, wqkv)
     qkv, cat = _DecQkvPrep.apply(qkv_obj, qk_pos, pairs, B, Q)
-    o1, o2 = _DecSelfPairAttn.apply(qkv, cat, B, Q)
+    o1, o2 = _DecSelfPairAttn.apply(qkv, cat, B, Q, _dr("d.sa", _dec_site(layer, "sa")))
     o = _DualLnMix.apply(x, o1, o2, pairs, p[lp + "norm1.weight"], p[lp + "norm1.bias"], p[lp + "norm2.weight"],
-                         p[lp + "norm2.bias"], lam, Q)
+                         p[lp + "norm2.bias"], lam, Q, _dr("d.d1", _dec_site(layer, "d1a"), _dec_site(layer, "d1b")))
     q_obj = linear(o, p[lp + "_ca_proj_to_q_obj.weight"])
     q_pos = linear(sin_embed, p[lp + "_ca_proj_to_q_pos.weight"])
-    ca = _SplitCrossAttn.apply(q_obj, q_pos, k_enc, k_pos, v, bits, kpm, B, Q, N)
+    ca = _SplitCrossAttn.apply(q_obj, q_pos, k_enc, k_pos, v, bits, kpm, B, Q, N, _dr("d.ca", _dec_site(layer, "ca")))
     outs = []
     for i, br in enumerate(("_cls_branch.", "_reg_branch.")):
         bp = lp + br
         xb = add_layernorm(o[:, i * 256:(i + 1) * 256], ca[:, i * 256:(i + 1) * 256], p[bp + "norm1.weight"],
-                           p[bp + "norm1.bias"])
-        f = linear(torch.relu(linear(xb, p[bp + "fc1.weight"], p[bp + "fc1.bias"])), p[bp + "fc2.weight"],
-                   p[bp + "fc2.bias"])
-        outs.append(add_layernorm(xb, f, p[bp + "norm2.weight"], p[bp + "norm2.bias"]))
+                           p[bp + "norm1.bias"], _dr("d.br", _dec_site(layer, f"b{i}.d_ca")))
+        h = dropout(torch.relu(linear(xb, p[bp + "fc1.weight"], p[bp + "fc1.bias"])),
+                    _dr("d.br", _dec_site(layer, f"b{i}.d_relu")))
+        f = linear(h, p[bp + "fc2.weight"], p[bp + "fc2.bias"])
+        outs.append(add_layernorm(xb, f, p[bp + "norm2.weight"], p[bp + "norm2.bias"],
+                                  _dr("d.br", _dec_site(layer, f"b{i}.d_fc2"))))
     return torch.cat(outs, dim=-1)
 
 
@@ -265,7 +334,7 @@ def decoder_layer(x: Tensor, l: int, kv_all: Tensor, kpos_all: Tensor, qkpos_all
         pairs = ops.pair_indices(coords.view(B, Q, 4)) if pairs_override is None else pairs_override
     y = decoder_block_core(x, sin_embed, pairs, qkpos_all[:, l * 512:(l + 1) * 512],
                            kv_all[:, l * 512:l * 512 + 256], kpos_all[:, l * 256:(l + 1) * 256],
-                           kv_all[:, l * 512 + 256:(l + 1) * 512], bits, kpm, p, f"_decoder.{l}.", B, Q, N, lam)
+                           kv_all[:, l * 512 + 256:(l + 1) * 512], bits, kpm, p, f"_decoder.{l}.", B, Q, N, lam, layer=l)
     return add_layernorm(x, y, p["norm.weight"], p["norm.bias"]), (coords, pairs)
 
 

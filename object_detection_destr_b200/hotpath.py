@@ -17,7 +17,7 @@ from torch import nn
 from . import functional as Fn
 from . import ops
 from .decoder import build_decoder
-from .encoder import _check_dropout, _params, build_encoder
+from .encoder import _params, build_encoder
 
 BF16 = torch.bfloat16
 
@@ -64,6 +64,15 @@ class TransformerHalf(nn.Module):
         extra = [p for p in self.parameters() if not (lo <= p.data_ptr() < hi)]
         return FlatAdamW(P, extra, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
 
+    def set_dropout_seed(self, value: int):
+        """Seed of the in-kernel dropout masks.  Runtime path: the device counter of the runtime (the engine bumps it
+        every step); module-level path: pins the per-module seed (None releases it)."""
+        if self.use_runtime:
+            self.runtime().seed.fill_(int(value))
+        else:
+            from .encoder import set_dropout_seed
+            set_dropout_seed(self, value)
+
     def after_optimizer_step(self):
         """Refresh the bf16 weight shadows (call after every optimizer step when runtime=True)."""
         if self._rt is not None:
@@ -91,12 +100,14 @@ class TransformerHalf(nn.Module):
             dec, enc = _RuntimeFn.apply(rt, rt.anchor, x, pos, bits, kpm, sel, pos_embed, pos_embed, centers, B, N, Q,
                                         pairs_override, aux)
         else:
-            enc = self._encoder.forward_tokens(x, pos, bits, B, N)
-            # fine_pos = pos * encoder._pos_scale(enc_out)  (model.py:89-92)
-            fine_pos = Fn._MulConst.apply(Fn.mlp2(enc, _params(self._encoder), "_pos_scale."), pos)
-            dec = Fn.decoder_tokens(sel, enc, bits, kpm, fine_pos, pos_embed, centers, _params(self._decoder),
-                                    _params(self._bbox_embed), len(self._decoder._decoder), B, Q, N,
-                                    pairs_override=pairs_override, aux=aux)
+            from .encoder import drop_scope
+            with drop_scope(self, features.device):  # one seed for the whole path (sites differ per layer / call)
+                enc = Fn.encoder_tokens(x, pos, bits, _params(self._encoder), len(self._encoder._encoder), B, N)
+                # fine_pos = pos * encoder._pos_scale(enc_out)  (model.py:89-92)
+                fine_pos = Fn._MulConst.apply(Fn.mlp2(enc, _params(self._encoder), "_pos_scale."), pos)
+                dec = Fn.decoder_tokens(sel, enc, bits, kpm, fine_pos, pos_embed, centers, _params(self._decoder),
+                                        _params(self._bbox_embed), len(self._decoder._decoder), B, Q, N,
+                                        pairs_override=pairs_override, aux=aux)
         cls = Fn.linear(dec[:, :256], self._cls_embed.weight, self._cls_embed.bias).float()
         delta = self._bbox_embed(dec[:, 256:].float())  # fp32 box head (box coords need 1e-3 abs)
         boxes = torch.cat([delta[:, :2] + inverse_sigmoid(centers), delta[:, 2:]], dim=-1).sigmoid()

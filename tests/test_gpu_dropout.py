@@ -152,7 +152,8 @@ class TwinDropper:
         return p * self._m(self._site(prefix, name), rows, K, (B, H, Q, K)).to(p.device)
 
 
-def test_transformer_half_with_dropout_fwd_bwd():
+@pytest.mark.parametrize("runtime", [True, False])
+def test_transformer_half_with_dropout_fwd_bwd(runtime):
     """The whole hot path in TRAINING mode with the reference's default dropout (p = 0.3 at all 16 sites per layer
     pair): outputs and every parameter gradient vs the fp32 oracle run with the SAME masks."""
     from argparse import Namespace
@@ -181,13 +182,14 @@ def test_transformer_half_with_dropout_fwd_bwd():
     gcls, gbox = torch.randn(B, Q, C, generator=g), torch.randn(B, Q, 4, generator=g)
     (ref["pred_class"] * gcls).sum().add((ref["pred_boxes"] * gbox).sum()).backward()
 
-    model = TransformerHalf(Namespace(hidden_dim=256, num_encoder_blocks=L, num_decoder_blocks=L, num_cls=C))
+    model = TransformerHalf(Namespace(hidden_dim=256, num_encoder_blocks=L, num_decoder_blocks=L, num_cls=C),
+                            runtime=runtime)  # hand-scheduled runtime AND the module-level autograd path
     model._encoder.load_state_dict(enc_sd)
     model._decoder.load_state_dict(dec_sd)
     model._cls_embed.load_state_dict(cls_sd)
     model._bbox_embed.load_state_dict(bbox_sd)
     model.cuda().train()  # dropout stays at the reference defaults
-    model.runtime().seed.fill_(seed)
+    model.set_dropout_seed(seed)
     out, _ = model(feats.cuda(), mask.cuda(), sel.cuda(), centers.cuda(), pairs_override=ref_pairs)
     (out["pred_class"] * gcls.cuda()).sum().add((out["pred_boxes"] * gbox.cuda()).sum()).backward()
     rel = lambda a, b: float((a.float().cpu() - b).norm() / b.norm())
@@ -207,7 +209,32 @@ def test_transformer_half_with_dropout_fwd_bwd():
     print(f"{n} parameter gradients with dropout, worst rel-fro error {worst:.3e}")
     assert n > 100
     # a different seed gives a different forward (the masks really depend on it)
-    model.runtime().seed.fill_(seed + 1)
+    model.set_dropout_seed(seed + 1)
     with torch.no_grad():
         out2, _ = model(feats.cuda(), mask.cuda(), sel.cuda(), centers.cuda(), pairs_override=ref_pairs)
     assert float((out2["pred_class"] - out["pred_class"]).abs().max()) > 1e-2
+
+
+def test_standalone_modules_apply_the_reference_dropout():
+    """Drop-in modules used on their own: EncoderBlock in train mode drops (and is reproducible under a pinned seed),
+    in eval mode it does not; SelfAttention drops ALWAYS, like the reference's inline nn.Dropout (self_attention.py:40)."""
+    from object_detection_destr_b200.decoder import SelfAttention
+    from object_detection_destr_b200.encoder import EncoderBlock, set_dropout_seed
+    g = torch.Generator().manual_seed(5)
+    blk = EncoderBlock().cuda()
+    x, pos = torch.randn(300, 2, 256, generator=g).cuda(), torch.randn(300, 2, 256, generator=g).cuda()
+    blk.eval()
+    with torch.no_grad():
+        y_eval = blk(x, pos_embed=pos)
+        assert torch.equal(y_eval, blk(x, pos_embed=pos))
+        blk.train()
+        set_dropout_seed(blk, 9)
+        y1, y2 = blk(x, pos_embed=pos), blk(x, pos_embed=pos)
+        assert torch.equal(y1, y2) and float((y1 - y_eval).abs().max()) > 0.05
+        set_dropout_seed(blk, None)          # released: the seed advances on every forward
+        assert not torch.equal(blk(x, pos_embed=pos), blk(x, pos_embed=pos))
+        sa = SelfAttention(heads_num=8).cuda().eval()
+        q, k, v = (torch.randn(2, 8, 100, 64, generator=g).cuda() for _ in range(3))
+        assert not torch.equal(sa(q, k, v), sa(q, k, v))          # stochastic even in eval
+        sa._dropout_prob = 0.0
+        assert torch.equal(sa(q, k, v), sa(q, k, v))
