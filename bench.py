@@ -181,7 +181,7 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------
-def time_dominant_kernels(cfg, B, dev, iters: int = 20):
+def time_dominant_kernels(cfg, B, dev, iters: int = 20, dropout: float = 0.0):
     """CUDA-event duration of the encoder attention kernels at the workload shape, each launch alone with the
     L2 flushed (a 256 MB write) in between.  (Inside the CUDA-graph replay individual kernels cannot be
     bracketed by events; the ncu launch list in profiles/ gives their share of the step.)"""
@@ -197,9 +197,11 @@ def time_dominant_kernels(cfg, B, dev, iters: int = 20):
     scale = 1.0 / math.sqrt(32)
     out, lse = ops.enc_attn_fwd(qk[:, :256], qk[:, 256:], v, bits, B, N, 8, scale)
     res = {}
-    bwd = lambda: ops.enc_attn_bwd(qk[:, :256], qk[:, 256:], v, bits, out, do, lse, B, N, 8, scale)
+    # same dropout setting as the timed step: the kernels then hash a keep-mask per probability
+    drop = (torch.ones(1, dtype=torch.int32, device=dev), ops.drop_thr16(dropout), 0) if dropout > 0 else None
+    bwd = lambda: ops.enc_attn_bwd(qk[:, :256], qk[:, 256:], v, bits, out, do, lse, B, N, 8, scale, drop=drop)
     from object_detection_destr_b200 import _lib
-    for name, fn in (("destr_enc_attn_fwd", lambda: ops.enc_attn_fwd(qk[:, :256], qk[:, 256:], v, bits, B, N, 8, scale)),
+    for name, fn in (("destr_enc_attn_fwd", lambda: ops.enc_attn_fwd(qk[:, :256], qk[:, 256:], v, bits, B, N, 8, scale, drop=drop)),
                      ("destr_enc_attn_bwd_op", bwd),     # all three launches of the op: prep + tcgen05 kernel + dQ convert
                      ("destr_enc_attn_bwd", bwd)):       # the tcgen05 kernel alone (debug knob 14 skips the two helpers)
         _lib.lib.destr_debug_knob(14, 1 if name == "destr_enc_attn_bwd" else 0)
@@ -320,7 +322,8 @@ def run_ours(args):
             e2e_step(s)
         ms_e2e = timed(e2e_step, args.steps)
     clocks = sampler.stop() if sampler else None
-    kernel_ms = time_dominant_kernels(cfg, B, dev) if rank == 0 else None
+    kernel_ms = time_dominant_kernels(cfg, B, dev, dropout=0.3 if args.dropout else 0.0) if rank == 0 else None
+    kernel_ms0 = time_dominant_kernels(cfg, B, dev) if (rank == 0 and args.dropout) else kernel_ms
 
     if rank == 0:
         pk = peaks()
@@ -343,7 +346,9 @@ def run_ours(args):
                                                 "frac": fwd_flops / t_f / 1e9 / pk["tf_burst"]},
                          "destr_enc_attn_bwd": {"launch_ms": t_b, "achieved": bwd_flops / t_b / 1e9,
                                                 "frac": bwd_flops / t_b / 1e9 / pk["tf_burst"],
-                                                "op_ms_with_prep_and_convert_launches": kernel_ms["destr_enc_attn_bwd_op"]}}}
+                                                "op_ms_with_prep_and_convert_launches": kernel_ms["destr_enc_attn_bwd_op"]},
+                         "without_dropout": {k: {"launch_ms": kernel_ms0[k], "frac": f / kernel_ms0[k] / 1e9 / pk["tf_burst"]}
+                                             for k, f in (("destr_enc_attn_fwd", fwd_flops), ("destr_enc_attn_bwd", bwd_flops))}}}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             ips, spstep, cores = time_cpu_reference(1, 2, 1, 0.3 if args.dropout else 0.0)
@@ -374,7 +379,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
