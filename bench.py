@@ -199,9 +199,11 @@ def time_dominant_kernels(cfg, B, dev, iters: int = 20, dropout: float = 0.0):
     res = {}
     # same dropout setting as the timed step: the kernels then hash a keep-mask per probability
     drop = (torch.ones(1, dtype=torch.int32, device=dev), ops.drop_thr16(dropout), 0) if dropout > 0 else None
-    bwd = lambda: ops.enc_attn_bwd(qk[:, :256], qk[:, 256:], v, bits, out, do, lse, B, N, 8, scale, drop=drop)
+    rb, cb = ops.attn_dropout_bits(drop, B * 8, N, dev) if drop else (None, None)
+    bwd = lambda: ops.enc_attn_bwd(qk[:, :256], qk[:, 256:], v, bits, out, do, lse, B, N, 8, scale, drop=drop, colbits=cb)
     from object_detection_destr_b200 import _lib
-    for name, fn in (("destr_enc_attn_fwd", lambda: ops.enc_attn_fwd(qk[:, :256], qk[:, 256:], v, bits, B, N, 8, scale, drop=drop)),
+    for name, fn in (("destr_attn_dropout_bits", (lambda: ops.attn_dropout_bits(drop, B * 8, N, dev)) if drop else (lambda: None)),
+                     ("destr_enc_attn_fwd", lambda: ops.enc_attn_fwd(qk[:, :256], qk[:, 256:], v, bits, B, N, 8, scale, drop=drop, rowbits=rb)),
                      ("destr_enc_attn_bwd_op", bwd),     # all three launches of the op: prep + tcgen05 kernel + dQ convert
                      ("destr_enc_attn_bwd", bwd)):       # the tcgen05 kernel alone (debug knob 14 skips the two helpers)
         _lib.lib.destr_debug_knob(14, 1 if name == "destr_enc_attn_bwd" else 0)
@@ -347,6 +349,8 @@ def run_ours(args):
                          "destr_enc_attn_bwd": {"launch_ms": t_b, "achieved": bwd_flops / t_b / 1e9,
                                                 "frac": bwd_flops / t_b / 1e9 / pk["tf_burst"],
                                                 "op_ms_with_prep_and_convert_launches": kernel_ms["destr_enc_attn_bwd_op"]},
+                         "destr_attn_dropout_bits": {"launch_ms": kernel_ms.get("destr_attn_dropout_bits", 0.0),
+                                                     "note": "mask bit matrices, once per layer (0 when dropout is off)"},
                          "without_dropout": {k: {"launch_ms": kernel_ms0[k], "frac": f / kernel_ms0[k] / 1e9 / pk["tf_burst"]}
                                              for k, f in (("destr_enc_attn_fwd", fwd_flops), ("destr_enc_attn_bwd", bwd_flops))}}}
         cpu = None

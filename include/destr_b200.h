@@ -129,10 +129,22 @@ int destr_dual_ln_mix_bwd(const void* dout, const void* x, const void* o1, const
  * d_head is fixed at 32, heads*32 <= 256.  Needs sm_100a (tcgen05/TMEM/TMA). */
 int destr_enc_attn_fwd(const void* q, const void* k, const void* v, int ld_q, int ld_k, int ld_v,
                        const uint32_t* mask_bits, int words_per_row, void* out, float* lse, int B, int N,
-                       int heads, float scale, const uint32_t* drop_seed, uint32_t drop_thr16, uint32_t drop_site,
+                       int heads, float scale, const uint32_t* drop_rowbits, int drop_words, uint32_t drop_thr16,
                        void* stream);
-/*   dropout (see destr_add_layernorm_fwd) acts on the attention probabilities, as nn.MultiheadAttention(dropout=p)
- *   does in training: mask row = (b*heads + h)*N + query, column = key; the softmax denominator is not dropped. */
+/*   dropout acts on the attention probabilities, as nn.MultiheadAttention(dropout=p) does in training
+ *   (encoder_block.py:58-60): mask row = (b*heads + h)*N + query, column = key, the same counter-based mask as
+ *   destr_add_layernorm_fwd's; the softmax denominator is not dropped.  The two flash kernels read the mask as bit
+ *   matrices (1 = dropped) written once per layer by destr_attn_dropout_bits -- evaluating the hash per score inside
+ *   their issue-bound loops cost 40-80% of the kernel time:
+ *     rowbits [n_sites][B*heads][words][Np]  bit i of word (w, q) <-> key   32w+i  (forward;  Np = 128*ceil(N/128))
+ *     colbits [n_sites][B*heads][words][Np]  bit i of word (w, k) <-> query 32w+i  (backward)
+ *   words >= max(Np/32, 3*ceil(N/96)); either output may be NULL; only the ceil(N/32)^2 blocks of real (query, key)
+ *   pairs are written.  One call can fill the matrices of n_sites dropout sites (site = site0 + i*site_stride, e.g.
+ *   all encoder layers of a step); the attention calls take one [B*heads][words][Np] slice.  drop_thr16 = 0 in the
+ *   attention calls disables dropout. */
+int destr_attn_dropout_bits(const uint32_t* drop_seed, uint32_t drop_thr16, uint32_t drop_site0,
+                            uint32_t drop_site_stride, int n_sites, int BH, int N, int words, uint32_t* rowbits,
+                            uint32_t* colbits, void* stream);
 /* backward: dq, dk, dv bf16 with the same row pitches as q, k, v (ld_dq, ld_dk, ld_dv).
  * Caller-provided workspaces: stats (fp32, destr_enc_attn_bwd_stats_floats(B,N,heads) elements: -lse and
  * -delta = -rowsum(dO o O), padded to 128-query tiles) and dq_acc (fp32 [B*N, heads*32]). */
@@ -140,8 +152,8 @@ int destr_enc_attn_bwd_stats_floats(int B, int N, int heads);
 int destr_enc_attn_bwd(const void* q, const void* k, const void* v, int ld_q, int ld_k, int ld_v,
                        const uint32_t* mask_bits, int words_per_row, const void* out, const void* dout,
                        const float* lse, float* stats, float* dq_acc, void* dq, void* dk, void* dv, int ld_dq,
-                       int ld_dk, int ld_dv, int B, int N, int heads, float scale, const uint32_t* drop_seed,
-                       uint32_t drop_thr16, uint32_t drop_site, void* stream);
+                       int ld_dk, int ld_dv, int B, int N, int heads, float scale, const uint32_t* drop_colbits,
+                       int drop_words, uint32_t drop_thr16, void* stream);
 
 /* ---------------- decoder: pairing, self + pair attention, split cross-attention ---------------- */
 

@@ -36,9 +36,10 @@ SIGNATURES = {
     "destr_dropout_inplace": [_p, _i, _i, _i, _p, _u, _u, _p],
     "destr_pos_mul_add_bwd_acc": [_p, _p, _p, _p, _p, _i64, _p],
     "destr_relu_bwd_colsum": [_p, _i, _p, _i, _p, _i, _p, _i, _i, _f, _p],
-    "destr_enc_attn_fwd": [_p, _p, _p, _i, _i, _i, _p, _i, _p, _p, _i, _i, _i, _f, _p, _u, _u, _p],
+    "destr_enc_attn_fwd": [_p, _p, _p, _i, _i, _i, _p, _i, _p, _p, _i, _i, _i, _f, _p, _i, _u, _p],
+    "destr_attn_dropout_bits": [_p, _u, _u, _u, _i, _i, _i, _i, _p, _p, _p],
     "destr_enc_attn_bwd": [_p, _p, _p, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i,
-                           _f, _p, _u, _u, _p],
+                           _f, _p, _i, _u, _p],
     "destr_dual_ln_mix_fwd": [_p, _p, _p, _p, _p, _p, _p, _p, _f, _p, _p, _i, _i, _p, _u, _u, _u, _p],
     "destr_dual_ln_mix_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _u, _u,
                               _u, _p],

@@ -72,5 +72,11 @@ struct Drop {
   const uint32_t* seed;
   uint32_t thr16, site;
 };
+// the encoder attention kernels take the mask as a precomputed bit matrix instead (attn_dropout_bits.cu)
+struct DropBits {
+  const uint32_t* bits;  // [B*heads][words][Np], 1 = dropped
+  uint32_t thr16;
+  int words;
+};
 }  // namespace destr
 #endif

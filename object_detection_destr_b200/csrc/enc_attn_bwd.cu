@@ -87,7 +87,7 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                     const uint32_t* __restrict__ mask_bits, int words_per_row, const float* __restrict__ stats,
                     float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv,
                     int ld_dk, int ld_dv, int N, int heads, int n_items, float scale, float scale_log2, Knobs kn,
-                    Drop dp) {
+                    DropBits dp) {
   extern __shared__ uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -269,7 +269,8 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       mbar_arrive(&sm.dkv_free[kb]);
       const int key = im.j * BT + krow;
       if (key < N) {
-        const float f = (g == 0) ? 1.f : scale;
+        // dV = (dropped P)^T dO: the 1/(1-p) of the forward's dropout is applied here, once per output
+        const float f = (g == 0) ? (DROP ? drop_scale(dp.thr16) : 1.f) : scale;
         uint32_t o[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) o[c] = pack_bf16x2(__uint_as_float(r[2 * c]) * f, __uint_as_float(r[2 * c + 1]) * f);
@@ -289,8 +290,8 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const uint32_t t_st = tmem + lane_addr + g * C_SBUF + C_ST + cg * 32;
     const uint32_t t_pt = tmem + lane_addr + C_PT + g * 32 + cg * 16;
     const uint32_t swz = krow & 7;
-    const uint32_t drop_seed = (DROP && dp.seed) ? *dp.seed : 0u;
     const float drop_s = drop_scale(dp.thr16);
+    const uint64_t ds2s = pack_f32x2(drop_s, drop_s);
 
     Item prev{0, 0, 0};
     uint32_t Pf = 0;
@@ -298,10 +299,14 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       const Item im = decode_item(blockIdx.x + it * gridDim.x, nkt, heads);
       const int key = im.j * BT + krow;
       const bool key_masked = (mask_bits[static_cast<size_t>(im.b) * words_per_row + (key >> 5)] >> (key & 31)) & 1u;
-      const uint32_t drop_row0 = static_cast<uint32_t>(im.b * heads + im.h) * N;
+      // dropout bits of my key row: word w <-> queries [32 w, 32 w + 32) = sub-tile w / 2, half cg
+      const uint32_t* dw = DROP ? dp.bits + (static_cast<size_t>(im.b * heads + im.h) * dp.words + g * 2 + cg) * (nkt * BT) + key
+                                : mask_bits;
+      uint32_t dnext = DROP ? dw[0] : 0u;
       for (int p = 0; p < npairs; ++p, ++Pf) {
+        const uint32_t dbits = dnext;
+        if (DROP && p + 1 < npairs) dnext = dw[static_cast<size_t>(4 * (p + 1)) * (nkt * BT)];
         const uint32_t U = 2 * Pf + g, s = U % QSTAGES, pb = Pf & 1;
-        const uint32_t qcol0 = (2 * p + g) * BQ + cg * 32;  // first query column of this thread in the sub-tile
         mbar_wait_a(b_sdp, Pf & 1, 10);
         mbar_wait_a(b_qfull + s * 8, (U / QSTAGES) & 1, 11);  // long complete: makes the TMA-written stats visible
         tc_fence_after();
@@ -334,15 +339,11 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
               }
               float g0 = __uint_as_float(dpv[c]), g1 = __uint_as_float(dpv[c + 1]), pd0 = p0, pd1 = p1;
               if (DROP) {  // the forward dropped P (and rescaled): dP and the P that multiplies dO go through the mask
-                const uint32_t q = qcol0 + hc * 16 + c;  // query of column c; mask row = (b, h, query), column = key
-                const bool k0 = drop_keep(drop_seed, dp.site, drop_row0 + q, key, dp.thr16);
-                const bool k1 = drop_keep(drop_seed, dp.site, drop_row0 + q + 1, key, dp.thr16);
-                g0 = k0 ? g0 * drop_s : 0.f;
-                g1 = k1 ? g1 * drop_s : 0.f;
-                pd0 = k0 ? p0 * drop_s : 0.f;
-                pd1 = k1 ? p1 * drop_s : 0.f;
+                if ((dbits >> (hc * 16 + c)) & 1u) g0 = pd0 = 0.f;      // bit = query column of this thread
+                if ((dbits >> (hc * 16 + c + 1)) & 1u) g1 = pd1 = 0.f;  // (the 1/(1-p) of P^T is applied to dV at the drain)
               }
-              const uint64_t dd = add_f32x2(pack_f32x2(g0, g1), pack_f32x2(nd[e], nd[e + 1]));
+              const uint64_t dd = DROP ? fma_f32x2(pack_f32x2(g0, g1), ds2s, pack_f32x2(nd[e], nd[e + 1]))
+                                       : add_f32x2(pack_f32x2(g0, g1), pack_f32x2(nd[e], nd[e + 1]));
               const uint64_t ds2 = mul_f32x2(pack_f32x2(p0, p1), dd);
               float d0, d1;
               unpack_f32x2(ds2, d0, d1);
@@ -445,11 +446,13 @@ extern "C" int destr_enc_attn_bwd(const void* q, const void* k, const void* v, i
                                   const uint32_t* mask_bits, int words_per_row, const void* out, const void* dout,
                                   const float* lse, float* stats, float* dq_acc, void* dq, void* dk, void* dv,
                                   int ld_dq, int ld_dk, int ld_dv, int B, int N, int heads, float scale,
-                                  const uint32_t* drop_seed, uint32_t drop_thr16, uint32_t drop_site, void* stream) {
+                                  const uint32_t* drop_colbits, int drop_words, uint32_t drop_thr16, void* stream) {
   using namespace destr;
   DESTR_CHECK_ARG(q && k && v && mask_bits && out && dout && lse && stats && dq_acc && dq && dk && dv, "null pointer");
   DESTR_CHECK_ARG(B > 0 && N > 0 && heads > 0 && heads * DH <= 256, "shape");
   DESTR_CHECK_ARG(words_per_row >= ceil_div(N, BT) * 4, "words_per_row");
+  DESTR_CHECK_ARG(!drop_thr16 || (drop_colbits && drop_words >= ceil_div(N, BT) * 4),
+                  "dropout needs the column bit matrix of destr_attn_dropout_bits");
   DESTR_CHECK_ARG(ld_dq % 8 == 0 && ld_dk % 8 == 0 && ld_dv % 8 == 0, "gradient row pitch must be a multiple of 8");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const uint64_t rows = static_cast<uint64_t>(B) * N;
@@ -487,7 +490,7 @@ extern "C" int destr_enc_attn_bwd(const void* q, const void* k, const void* v, i
   kernels[(g_knobs[10] & 3) + (drop_thr16 ? 4 : 0)]<<<grid, NTHREADS, smem, st>>>(
       tq, tk, tv, tdo, mask_bits, words_per_row, stats, dq_acc, static_cast<__nv_bfloat16*>(dk),
       static_cast<__nv_bfloat16*>(dv), ld_dk, ld_dv, N, heads, n_items, scale, scale * 1.4426950408889634f, kn,
-      Drop{drop_seed, drop_thr16, drop_site});
+      DropBits{drop_colbits, drop_thr16, drop_words});
   DESTR_LAUNCH_CHECK();
   const int64_t n4 = static_cast<int64_t>(rows) * cols / 4;
   int blocks = (int)((n4 + 255) / 256);

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
 enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const uint32_t* __restrict__ mask_bits,
                     int words_per_row, __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int N, int heads,
-                    int n_items, float scale_log2, float lazy_tau, Knobs kn, Drop dp) {
+                    int n_items, float scale_log2, float lazy_tau, Knobs kn, DropBits dp) {
   extern __shared__ uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -194,7 +194,7 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const int row = wq * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(wq * 32) << 16;
     const uint64_t sc2 = pack_f32x2(scale_log2, scale_log2);
-    const uint32_t drop_seed = (DROP && dp.seed) ? *dp.seed : 0u;
+    const int Np_drop = (N + 127) / 128 * 128;
     int f = 0;
     for (int it = 0; it < my_items; ++it) {
       const int w = blockIdx.x + it * gridDim.x;
@@ -202,7 +202,13 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       const int h = bh % heads, b = bh / heads;
       const uint32_t* mrow = mask_bits + static_cast<size_t>(b) * words_per_row;
       float m_ref = -INFINITY, l = 0.f;
-      const uint32_t drop_row = static_cast<uint32_t>(bh) * N + qt * BM + row;  // mask row = (b, h, query)
+      // dropout bits of my query row: same word / half split as the key mask (bit i <-> key 96 j + 48 hf + i)
+      const uint32_t* dw = DROP ? dp.bits + (static_cast<size_t>(bh) * dp.words + hf) * Np_drop + qt * BM + row : mrow;
+      uint32_t dw0 = 0, dw1 = 0;
+      if (DROP) {
+        dw0 = dw[0];
+        dw1 = dw[Np_drop];
+      }
       // mask bits of this half's 48 keys of tile j (bit i <-> key 96 j + 48 hf + i) live in two words; the raw
       // words are prefetched one tile ahead and only combined when consumed (no stall on the load)
       const uint32_t* mw = mrow + hf;
@@ -211,9 +217,14 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       for (int j = 0; j < nkv; ++j, ++f) {
         const uint32_t s_addr = tmem + lane_addr + C_S + (f & 1) * BN + hf * HN;
         const uint32_t c0 = mw0, c1 = mw1;
+        const uint32_t e0 = dw0, e1 = dw1;
         if (j + 1 < nkv) {
           mw0 = mw[3 * (j + 1)];
           mw1 = mw[3 * (j + 1) + 1];
+          if (DROP) {
+            dw0 = dw[static_cast<size_t>(3 * (j + 1)) * Np_drop];
+            dw1 = dw[static_cast<size_t>(3 * (j + 1) + 1) * Np_drop];
+          }
         }
         mbar_wait(&sm.s_full[f & 1], (f >> 1) & 1, 7);
         tc_fence_after();
@@ -260,6 +271,8 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const uint64_t nm2 = pack_f32x2(-m_use, -m_use);
         uint64_t rs2[2] = {0ull, 0ull};
         uint32_t pk[HN / 2];
+        const uint64_t db = hf == 0 ? (static_cast<uint64_t>(e0) | (static_cast<uint64_t>(e1 & 0xffffu) << 32))
+                                    : (static_cast<uint64_t>(e0 >> 16) | (static_cast<uint64_t>(e1) << 16));
 #pragma unroll
         for (int i = 0; i < HN / 2; ++i) {  // P column i holds keys 2i, 2i+1 of the half
           const uint64_t x2 =
@@ -274,9 +287,8 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           }
           rs2[i & 1] = add_f32x2(rs2[i & 1], pack_f32x2(p0, p1));  // the softmax denominator is NOT dropped
           if (DROP) {  // attention-probability dropout (nn.MultiheadAttention(dropout=p)): zero P, rescale O at the end
-            const uint32_t bits = drop_bits(drop_seed, dp.site, drop_row, j * (BN / 2) + hf * (HN / 2) + i);
-            if ((bits & 0xFFFFu) < dp.thr16) p0 = 0.f;
-            if ((bits >> 16) < dp.thr16) p1 = 0.f;
+            if ((db >> (2 * i)) & 1ull) p0 = 0.f;
+            if ((db >> (2 * i + 1)) & 1ull) p1 = 0.f;
           }
           pk[i] = pack_bf16x2(p0, p1);
         }
@@ -358,12 +370,14 @@ extern "C" int destr_debug_knob(int idx, int value) {
 
 extern "C" int destr_enc_attn_fwd(const void* q, const void* k, const void* v, int ld_q, int ld_k, int ld_v,
                                   const uint32_t* mask_bits, int words_per_row, void* out, float* lse, int B, int N,
-                                  int heads, float scale, const uint32_t* drop_seed, uint32_t drop_thr16,
-                                  uint32_t drop_site, void* stream) {
+                                  int heads, float scale, const uint32_t* drop_rowbits, int drop_words,
+                                  uint32_t drop_thr16, void* stream) {
   using namespace destr;
   DESTR_CHECK_ARG(q && k && v && mask_bits && out, "null pointer");
   DESTR_CHECK_ARG(B > 0 && N > 0 && heads > 0 && heads * DH <= 256, "shape");
   DESTR_CHECK_ARG(words_per_row >= ceil_div(N, BN) * 3, "words_per_row (need >= 3 words per 96-key tile)");
+  DESTR_CHECK_ARG(!drop_thr16 || (drop_rowbits && drop_words >= ceil_div(N, BN) * 3),
+                  "dropout needs the row bit matrix of destr_attn_dropout_bits");
   const uint64_t rows = static_cast<uint64_t>(B) * N;
   CUtensorMap tq, tk, tv;
   int rc;
@@ -391,7 +405,7 @@ extern "C" int destr_enc_attn_fwd(const void* q, const void* k, const void* v, i
   kernel<<<grid, NTHREADS, smem, static_cast<cudaStream_t>(stream)>>>(
       tq, tk, tv, mask_bits, words_per_row, static_cast<__nv_bfloat16*>(out), lse, N, heads, n_items,
       scale * 1.4426950408889634f, g_knobs[11] ? (float)(g_knobs[11] - 1) : kLazyTau, kn,
-      Drop{drop_seed, drop_thr16, drop_site});
+      DropBits{drop_rowbits, drop_thr16, drop_words});
   DESTR_LAUNCH_CHECK();
   return 0;
 }

@@ -113,7 +113,11 @@ class _EncAttn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qk, v, bits, B, N, heads, scale, drop=None):
         C = heads * 32
-        out, lse = ops.enc_attn_fwd(qk[:, :C], qk[:, C:], v, bits, B, N, heads, scale, drop=drop)
+        rb = cb = None
+        if drop is not None and drop[1]:  # both orientations of the mask now: the seed may move before backward runs
+            rb, cb = ops.attn_dropout_bits(drop, B * heads, N, qk.device)
+        out, lse = ops.enc_attn_fwd(qk[:, :C], qk[:, C:], v, bits, B, N, heads, scale, drop=drop, rowbits=rb)
+        ctx.colbits = cb
         ctx.save_for_backward(qk, v, bits, out, lse)
         ctx.dims = (B, N, heads, scale)
         ctx.drop = drop
@@ -124,7 +128,8 @@ class _EncAttn(torch.autograd.Function):
         qk, v, bits, out, lse = ctx.saved_tensors
         B, N, heads, scale = ctx.dims
         C = heads * 32
-        dqk, dv = ops.enc_attn_bwd(qk[:, :C], qk[:, C:], v, bits, out, dout, lse, B, N, heads, scale, drop=ctx.drop)
+        dqk, dv = ops.enc_attn_bwd(qk[:, :C], qk[:, C:], v, bits, out, dout, lse, B, N, heads, scale, drop=ctx.drop,
+                                   colbits=ctx.colbits)
         return dqk, dv, None, None, None, None, None, None
 
 

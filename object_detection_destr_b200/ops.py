@@ -198,10 +198,38 @@ def dropout_inplace(x: Tensor, drop) -> Tensor:
 # ----------------------------------------------------------------------------------------------
 # encoder attention
 # ----------------------------------------------------------------------------------------------
+def attn_dropout_bits(drop, BH: int, N: int, device, want_row: bool = True, want_col: bool = True,
+                      n_sites: int = 1, site_stride: int = 0, out=None):
+    """Bit matrices (1 = dropped) of the encoder attention-probability dropout mask for `drop` = (seed, thr16, site):
+    (rowbits, colbits), int32 [n_sites, BH, mask_words(N), 128*ceil(N/128)] each (the leading axis is dropped when
+    n_sites == 1) -- the forward kernel reads rowbits, the backward colbits (keep colbits with the saved activations
+    to skip regenerating it).  Site i of the batch is drop's site + i*site_stride."""
+    seed, thr, site = drop
+    words, Np = mask_words(N), (N + 127) // 128 * 128
+    shape = (BH, words, Np) if n_sites == 1 else (n_sites, BH, words, Np)
+    if out is not None:  # caller-provided (rowbits, colbits) of that shape
+        rb, cb = out
+    else:
+        rb = torch.empty(shape, dtype=torch.int32, device=device) if want_row else None
+        cb = torch.empty(shape, dtype=torch.int32, device=device) if want_col else None
+    _lib.call("destr_attn_dropout_bits", seed.data_ptr(), int(thr), int(site), int(site_stride), n_sites, BH, N, words,
+              _ptr(rb), _ptr(cb), _stream())
+    return rb, cb
+
+
+def _bits_args(drop, bits, BH, N, device, row: bool):
+    if drop is None or not drop[1]:
+        return None, 0, 0
+    if bits is None:
+        bits = attn_dropout_bits(drop, BH, N, device, want_row=row, want_col=not row)[0 if row else 1]
+    return bits.data_ptr(), bits.shape[1], int(drop[1])
+
+
 def enc_attn_fwd(q: Tensor, k: Tensor, v: Tensor, mask_bits: Tensor, B: int, N: int, heads: int,
-                 scale: float, need_lse: bool = True, drop=None):
+                 scale: float, need_lse: bool = True, drop=None, rowbits: Optional[Tensor] = None):
     """q,k,v: bf16 2-D views [B*N, heads*32] (any row pitch, unit column stride).
-    Returns (out bf16 [B*N, heads*32], lse fp32 [B,heads,N])."""
+    Returns (out bf16 [B*N, heads*32], lse fp32 [B,heads,N]).  drop = (seed, thr16, site) applies the attention
+    dropout; `rowbits` from attn_dropout_bits (generated here when omitted)."""
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
         _chk(t, BF16, n)
         if t.dim() != 2 or t.stride(1) != 1 or t.shape != (B * N, heads * 32):
@@ -211,12 +239,12 @@ def enc_attn_fwd(q: Tensor, k: Tensor, v: Tensor, mask_bits: Tensor, B: int, N: 
     lse = torch.empty(B, heads, N, dtype=torch.float32, device=q.device) if need_lse else None
     _lib.call("destr_enc_attn_fwd", q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), k.stride(0), v.stride(0),
               mask_bits.data_ptr(), mask_bits.shape[1], out.data_ptr(), _ptr(lse), B, N, heads, float(scale),
-              *_dargs(drop), _stream())
+              *_bits_args(drop, rowbits, B * heads, N, q.device, True), _stream())
     return out, lse
 
 
 def enc_attn_bwd(q: Tensor, k: Tensor, v: Tensor, mask_bits: Tensor, out: Tensor, dout: Tensor, lse: Tensor,
-                 B: int, N: int, heads: int, scale: float, drop=None):
+                 B: int, N: int, heads: int, scale: float, drop=None, colbits: Optional[Tensor] = None):
     """Returns (dqk bf16 [B*N, 2*heads*32] = [dq | dk], dv bf16 [B*N, heads*32])."""
     C = heads * 32
     dout = _chk(dout.contiguous(), BF16, "dout")
@@ -228,7 +256,7 @@ def enc_attn_bwd(q: Tensor, k: Tensor, v: Tensor, mask_bits: Tensor, out: Tensor
     _lib.call("destr_enc_attn_bwd", q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(0), k.stride(0), v.stride(0),
               mask_bits.data_ptr(), mask_bits.shape[1], out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
               delta.data_ptr(), dq_acc.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), 2 * C, 2 * C, C,
-              B, N, heads, float(scale), *_dargs(drop), _stream())
+              B, N, heads, float(scale), *_bits_args(drop, colbits, B * heads, N, q.device, False), _stream())
     return dqk, dv
 
 

@@ -334,6 +334,30 @@ class HotPathRuntime:
             return None
         return (self.seed, thr16, site) if site2 is None else (self.seed, thr16, site, site2)
 
+    def _gen_attn_bits(self, B: int, N: int, device):
+        """Bit matrices of the encoder attention dropout mask of every layer (ops.attn_dropout_bits), written by a
+        background stream while the first layers' GEMMs run: [(rowbits_l, colbits_l, ready event)]."""
+        thr = self.dc["e.attn"]
+        if not thr:
+            return None
+        P, L = self.P, self.Le
+        words, Np = ops.mask_words(N), (N + 127) // 128 * 128
+        rb = torch.empty(L, B * 8, words, Np, dtype=torch.int32, device=device)  # allocated on the caller's stream
+        cb = torch.empty_like(rb)
+        bg = P.forks[1] if P.forks else None
+        out = []
+        if bg is not None:
+            bg.wait_stream(torch.cuda.current_stream())
+        with (torch.cuda.stream(bg) if bg is not None else contextlib.nullcontext()):
+            for l in range(L):
+                ops.attn_dropout_bits((self.seed, thr, enc_site(l, "attn")), B * 8, N, device, out=(rb[l], cb[l]))
+                ev = None
+                if bg is not None:
+                    ev = torch.cuda.Event()
+                    ev.record(bg)
+                out.append((rb[l], cb[l], ev))
+        return out
+
     def _bbox_bf16(self):
         """bf16 copy of the box head's first layer, refreshed once per forward()."""
         if self._bbox_cache is None:
@@ -352,8 +376,14 @@ class HotPathRuntime:
         qk = _mm_bias(xq, Win[:512], b_in[:512])
         P.join(0)
         dc = self.dc
-        a, lse = ops.enc_attn_fwd(qk[:, :256], qk[:, 256:], v, bits, B, N, 8, 1.0 / math.sqrt(32),
-                                  drop=self._d(dc["e.attn"], enc_site(l, "attn")))
+        da_ = self._d(dc["e.attn"], enc_site(l, "attn"))
+        # attention dropout mask as bit matrices: rows for the forward kernel, columns kept for the backward
+        rb = cb = None
+        if da_ is not None:
+            rb, cb, ev = self._attn_bits[l]
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)
+        a, lse = ops.enc_attn_fwd(qk[:, :256], qk[:, 256:], v, bits, B, N, 8, 1.0 / math.sqrt(32), drop=da_, rowbits=rb)
         o = _mm_bias(a, P.w(f"e{l}.out_w"), P.w(f"e{l}.out_b"))
         x1, m1, r1 = ops.add_layernorm(x, o, P.f(f"e{l}.n1_w"), P.f(f"e{l}.n1_b"), save_stats=True,
                                        drop=self._d(dc["e.d1"], enc_site(l, "d1")))
@@ -363,11 +393,11 @@ class HotPathRuntime:
         x2, m2, r2 = ops.add_layernorm(x1, g, P.f(f"e{l}.n2_w"), P.f(f"e{l}.n2_b"), save_stats=True,
                                        drop=self._d(dc["e.d3"], enc_site(l, "d3")))
         xo, m3, r3 = ops.add_layernorm(x, x2, P.f("e.n_w"), P.f("e.n_b"), save_stats=True)
-        return xo, (x, h1, xq, qk, v, a, lse, o, x1, m1, r1, f1, g, x2, m2, r2, m3, r3)
+        return xo, (x, h1, xq, qk, v, a, lse, o, x1, m1, r1, f1, g, x2, m2, r2, m3, r3, cb)
 
     def _enc_bwd(self, l: int, dxo: Tensor, sv, pos: Tensor, bits: Tensor, B: int, N: int) -> Tensor:
         P = self.P
-        x, h1, xq, qk, v, a, lse, o, x1, m1, r1, f1, g, x2, m2, r2, m3, r3 = sv
+        x, h1, xq, qk, v, a, lse, o, x1, m1, r1, f1, g, x2, m2, r2, m3, r3, cb = sv
         # xo = LN(x + x2)
         d3, _, _ = ops.add_layernorm_bwd(dxo, x, x2, P.f("e.n_w"), m3, r3, dgamma=P.g("e.n_w"), dbeta=P.g("e.n_b"))
         # x2 = LN(x1 + fc2(relu(fc1 x1)))
@@ -389,7 +419,7 @@ class HotPathRuntime:
         P.acc_gw(f"e{l}.out_w", d1, a)
         da = torch.mm(d1, P.w(f"e{l}.out_w"))
         dqk, dv = ops.enc_attn_bwd(qk[:, :256], qk[:, 256:], v, bits, a, da, lse, B, N, 8, 1.0 / math.sqrt(32),
-                                   drop=self._d(dc["e.attn"], enc_site(l, "attn")))
+                                   drop=self._d(dc["e.attn"], enc_site(l, "attn")), colbits=cb)
         gb = P.g(f"e{l}.in_b")
         P.off_path(lambda: (ops.relu_bwd_colsum(dqk, None, gb[:512]), ops.relu_bwd_colsum(dv, None, gb[512:])), dqk, dv)
         Win = P.w(f"e{l}.in_w")
@@ -531,6 +561,7 @@ class HotPathRuntime:
         self._bbox_cache = None  # the box head is trained: re-cast it every step
         self.dc = self._drop_config()  # dropout in force for this forward AND its backward
         enc_saved = []
+        self._attn_bits = self._gen_attn_bits(B, N, x.device)
         for l in range(self.Le):
             x, sv = self._enc_fwd(l, x, pos, bits, B, N)
             enc_saved.append(sv)
