@@ -270,10 +270,14 @@ int destr_set_loss_fwd_bwd(const float* logits, const float* boxes, const int64_
 
 /* torch.optim.AdamW arithmetic (decoupled weight decay, bias correction; amsgrad off) on flat fp32 buffers of
  * n elements (n % 4 == 0, 16-byte aligned), plus the refresh of the bf16 weight shadow the GEMMs read.
- * `step` points to a device float holding the 1-based step count of THIS update. */
-int destr_flat_adamw(float* master, const float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16,
-                     int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, const float* step,
-                     void* stream);
+ * `step` points to a device float holding the 1-based step count of THIS update.
+ * The first n_bf16 gradients (n_bf16 % 4 == 0; 0 = none) are read from `grad_bf16` instead of `grad` -- the weight-
+ * matrix gradients as the dW GEMMs leave them -- and every gradient is multiplied by grad_scale (1/world for the
+ * data-parallel mean, else 1); the fp32 value actually used is written back to `grad`, so that buffer (the
+ * parameters' .grad) is complete after the call. */
+int destr_flat_adamw(float* master, float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, int64_t n,
+                     float lr, float beta1, float beta2, float eps, float weight_decay, const float* step,
+                     const void* grad_bf16, int64_t n_bf16, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -134,6 +134,9 @@ class FlatParams:
         self.forks = [torch.cuda.Stream(device=device) for _ in range(2)] if self.side is not None else []  # parallel chains
         self._keep: List[Tensor] = []
         self._forked = set()
+        self.defer_grad_cast = False  # set by FlatAdamW: its kernel reads the bf16 weight gradients itself
+        self.g16_pending = False
+        self.grad_scale = 1.0
 
     def _v(self, buf: Tensor, name: str, rows: Optional[int] = None) -> Tensor:
         off, shape = self.off[name]
@@ -191,14 +194,28 @@ class FlatParams:
                 dist.all_reduce(self.g16[:self.dec_off], group=self.group)
                 dist.all_reduce(self.g32[self.nW:], group=self.group)
             torch.cuda.current_stream().wait_stream(self.comm)
-            inv = 1.0 / self.world
-            torch.mul(self.g16, inv, out=self.g32[:self.nW])   # bf16 -> fp32 with the 1/world of the mean
-            self.g32[self.nW:].mul_(inv)
-        else:
-            self.g32[:self.nW].copy_(self.g16)
+        # the weight gradients are still bf16 (g16) and, data-parallel, everything is a SUM over ranks: a FlatAdamW
+        # bound to this buffer folds the widening and the 1/world into its own pass (and leaves the fp32 values in
+        # .grad); otherwise do it here
+        self.grad_scale = 1.0 / getattr(self, "world", 1)
+        self.g16_pending = True
+        if not self.defer_grad_cast:
+            self.materialize_grads()
         for t, gv in zip(self.params, self._gviews):  # zero_grad(set_to_none=True) may have detached them
             if t.grad is not gv:
                 t.grad = gv
+
+    def materialize_grads(self):
+        """Finish .grad after backward(): widen the bf16 weight gradients into the fp32 buffer and apply the
+        data-parallel 1/world.  (No-op when already done; FlatAdamW.step() does the same inside its kernel.)"""
+        if not getattr(self, "g16_pending", False):
+            return
+        if self.grad_scale != 1.0:
+            torch.mul(self.g16, self.grad_scale, out=self.g32[:self.nW])
+            self.g32[self.nW:].mul_(self.grad_scale)
+        else:
+            self.g32[:self.nW].copy_(self.g16)
+        self.g16_pending = False
 
     @contextlib.contextmanager
     def fork(self, enable: bool = True, k: int = 0):
@@ -261,6 +278,7 @@ class FlatAdamW:
         self.exp_avg = torch.zeros_like(P.m32)
         self.exp_avg_sq = torch.zeros_like(P.m32)
         self.t = torch.zeros(1, dtype=torch.float32, device=P.m32.device)
+        P.defer_grad_cast = True  # step() consumes the bf16 weight gradients directly (P.materialize_grads() to peek)
         extra = [p for p in extra if p.requires_grad]
         self.extra = torch.optim.AdamW(extra, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, fused=True,
                                        capturable=True) if extra else None
@@ -274,9 +292,13 @@ class FlatAdamW:
         self.t.add_(1.0)
         n = (P.n + 3) // 4 * 4
         from . import _lib
+        pend = P.g16_pending  # backward left bf16 weight gradients (else .grad was filled by the caller)
         _lib.call("destr_flat_adamw", P.m32.data_ptr(), P.g32.data_ptr(), self.exp_avg.data_ptr(),
                   self.exp_avg_sq.data_ptr(), P.s16.data_ptr(), n, float(self.lr), float(self.betas[0]),
-                  float(self.betas[1]), float(self.eps), float(self.wd), self.t.data_ptr(), ops._stream())
+                  float(self.betas[1]), float(self.eps), float(self.wd), self.t.data_ptr(),
+                  P.g16.data_ptr() if pend else None, P.nW if pend else 0, float(P.grad_scale) if pend else 1.0,
+                  ops._stream())
+        P.g16_pending = False
         if self.extra is not None:
             self.extra.step()
 

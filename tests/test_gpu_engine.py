@@ -51,6 +51,18 @@ def test_flat_adamw_matches_torch_adamw():
             rp.grad = p.grad.detach().clone()
         opt.step()
         ref.step()
+    # a step straight after backward(): the weight gradients are still bf16 (P.g16) and everything is a sum over
+    # `world` ranks -- the kernel widens, scales by 1/world and leaves the fp32 values in .grad
+    P.g16.copy_((torch.randn(P.g16.shape, generator=g, device="cuda") * 0.1).bfloat16())
+    P.g32.copy_(torch.randn(P.g32.shape, generator=g, device="cuda") * 0.1)
+    expect = torch.cat([P.g16.float(), P.g32[P.nW:]]) * 0.5
+    P.g16_pending, P.grad_scale = True, 0.5
+    for rp, p in zip(ref_p, P.params):
+        off = p.grad.storage_offset()  # .grad is a view of the flat fp32 gradient buffer
+        rp.grad = expect[off:off + p.numel()].view(p.shape).clone()
+    opt.step()
+    ref.step()
+    assert not P.g16_pending and torch.equal(P.g32, expect)
     for rp, p in zip(ref_p, P.params):
         assert torch.allclose(p, rp, rtol=2e-6, atol=2e-7), float((p - rp).abs().max())
     for name in ("e0.fc1_w", "d0.q_w"):  # bf16 shadows follow the masters

@@ -15,8 +15,11 @@ v = torch.randn(B * N, 256, generator=g).bfloat16().cuda()
 do = torch.randn(B * N, 256, generator=g).bfloat16().cuda()
 bits = ops.pack_key_mask(None, B, N, device=qk.device)
 sc = 1 / math.sqrt(32)
+pdrop = float(os.environ.get("PDROP", 0.0))  # PDROP=0.3: the dropout variants + the mask bit-matrix generator
+drop = (torch.ones(1, dtype=torch.int32, device="cuda"), ops.drop_thr16(pdrop), 0) if pdrop > 0 else None
 for _ in range(3):
-    out, lse = ops.enc_attn_fwd(qk[:, :256], qk[:, 256:], v, bits, B, N, 8, sc)
-    ops.enc_attn_bwd(qk[:, :256], qk[:, 256:], v, bits, out, do, lse, B, N, 8, sc)
+    rb, cb = ops.attn_dropout_bits(drop, B * 8, N, qk.device) if drop else (None, None)
+    out, lse = ops.enc_attn_fwd(qk[:, :256], qk[:, 256:], v, bits, B, N, 8, sc, drop=drop, rowbits=rb)
+    ops.enc_attn_bwd(qk[:, :256], qk[:, 256:], v, bits, out, do, lse, B, N, 8, sc, drop=drop, colbits=cb)
 torch.cuda.synchronize()
 print("ok")
