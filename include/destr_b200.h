@@ -266,6 +266,22 @@ int destr_set_loss_fwd_bwd(const float* logits, const float* boxes, const int64_
                            float w_bbox, float w_ciou, float* losses, float* dlogits, float* dboxes,
                            float* workspace, void* stream);
 
+/* ---------------- prediction heads ---------------- */
+
+/* Class and box heads of the detector (model.py:120-131) on the decoder output, fp32 weights and arithmetic:
+ *   logits = dec[:, :256] Wc^T + bc;   boxes = sigmoid(W2 relu(W1 dec[:, 256:] + b1) + b2 + [inverse_sigmoid(centers), 0, 0])
+ *   dec bf16 [M,512]; centers fp32 [M,2]; Wc [C,256], W1 [256,256], W2 [4,256] row-major as nn.Linear stores them
+ *   (C <= 128); logits fp32 [M,C], boxes fp32 [M,4] (cx,cy,h,w in (0,1)); hidden fp32 [M,256] is kept for backward.
+ * Backward: d_dec bf16 [M,512] and the six parameter gradients (overwritten, not accumulated) from dlogits, dboxes;
+ * dh_ws (M*256 floats) and dz_ws (M*4 floats) are scratch. */
+int destr_heads_fwd(const void* dec, const float* centers, const float* Wc, const float* bc, int C, const float* W1,
+                    const float* b1, const float* W2, const float* b2, float* logits, float* boxes, float* hidden,
+                    int M, void* stream);
+int destr_heads_bwd(const void* dec, const float* hidden, const float* boxes, const float* dlogits,
+                    const float* dboxes, const float* Wc, const float* W1, const float* W2, int C, void* d_dec,
+                    float* dh_ws, float* dz_ws, float* dWc, float* dbc, float* dW1, float* db1, float* dW2,
+                    float* db2, int M, void* stream);
+
 /* ---------------- optimizer step on the flat parameter buffer ---------------- */
 
 /* torch.optim.AdamW arithmetic (decoupled weight decay, bias correction; amsgrad off) on flat fp32 buffers of

@@ -108,7 +108,8 @@ class TransformerHalf(nn.Module):
                 dec = Fn.decoder_tokens(sel, enc, bits, kpm, fine_pos, pos_embed, centers, _params(self._decoder),
                                         _params(self._bbox_embed), len(self._decoder._decoder), B, Q, N,
                                         pairs_override=pairs_override, aux=aux)
-        cls = Fn.linear(dec[:, :256], self._cls_embed.weight, self._cls_embed.bias).float()
-        delta = self._bbox_embed(dec[:, 256:].float())  # fp32 box head (box coords need 1e-3 abs)
-        boxes = torch.cat([delta[:, :2] + inverse_sigmoid(centers), delta[:, 2:]], dim=-1).sigmoid()
+        # class + box heads, fp32 as in the reference (model.py:120-131): one kernel (csrc/heads.cu)
+        cls, boxes = ops.heads(dec, centers, self._cls_embed.weight, self._cls_embed.bias,
+                               self._bbox_embed[0].weight, self._bbox_embed[0].bias,
+                               self._bbox_embed[2].weight, self._bbox_embed[2].bias)
         return {"pred_class": cls.view(B, Q, -1), "pred_boxes": boxes.view(B, Q, 4)}, enc.view(B, N, C)

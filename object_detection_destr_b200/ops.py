@@ -481,6 +481,53 @@ def lsap_blockdiag(cost: Tensor, tgt_offsets: Tensor, B: int, Q: int, max_target
 # ----------------------------------------------------------------------------------------------
 # fused set-prediction loss (forward + backward in one launch)
 # ----------------------------------------------------------------------------------------------
+class _HeadsFn(torch.autograd.Function):
+    """Class + box heads (csrc/heads.cu): one forward launch, two backward launches."""
+
+    @staticmethod
+    def forward(ctx, dec, centers, Wc, bc, W1, b1, W2, b2):
+        dec = _chk(dec.contiguous(), BF16, "dec")
+        M, C = dec.shape[0], Wc.shape[0]
+        if dec.shape[1] != 512 or tuple(W1.shape) != (256, 256) or tuple(W2.shape) != (4, 256) or Wc.shape[1] != 256:
+            raise ValueError("heads: dec [M,512], Wc [C,256], W1 [256,256], W2 [4,256] expected")
+        ws = [_chk(t.detach().contiguous(), torch.float32, n) for t, n in
+              ((Wc, "Wc"), (bc, "bc"), (W1, "W1"), (b1, "b1"), (W2, "W2"), (b2, "b2"))]
+        cen = _chk(centers.contiguous(), torch.float32, "centers")
+        logits = torch.empty(M, C, dtype=torch.float32, device=dec.device)
+        boxes = torch.empty(M, 4, dtype=torch.float32, device=dec.device)
+        hidden = torch.empty(M, 256, dtype=torch.float32, device=dec.device)
+        _lib.call("destr_heads_fwd", dec.data_ptr(), cen.data_ptr(), ws[0].data_ptr(), ws[1].data_ptr(), C,
+                  ws[2].data_ptr(), ws[3].data_ptr(), ws[4].data_ptr(), ws[5].data_ptr(), logits.data_ptr(),
+                  boxes.data_ptr(), hidden.data_ptr(), M, _stream())
+        ctx.save_for_backward(dec, hidden, boxes, ws[0], ws[2], ws[4])
+        return logits, boxes
+
+    @staticmethod
+    def backward(ctx, dlogits, dboxes):
+        dec, hidden, boxes, Wc, W1, W2 = ctx.saved_tensors
+        M, C, dev = dec.shape[0], Wc.shape[0], dec.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        dlogits = torch.zeros(M, C, **f32) if dlogits is None else _chk(dlogits.contiguous(), torch.float32, "dlogits")
+        dboxes = torch.zeros(M, 4, **f32) if dboxes is None else _chk(dboxes.contiguous(), torch.float32, "dboxes")
+        d_dec = torch.empty(M, 512, dtype=BF16, device=dev)
+        dh, dz = torch.empty(M, 256, **f32), torch.empty(M, 4, **f32)
+        dWc, dbc = torch.empty(C, 256, **f32), torch.empty(C, **f32)
+        dW1, db1 = torch.empty(256, 256, **f32), torch.empty(256, **f32)
+        dW2, db2 = torch.empty(4, 256, **f32), torch.empty(4, **f32)
+        _lib.call("destr_heads_bwd", dec.data_ptr(), hidden.data_ptr(), boxes.data_ptr(), dlogits.data_ptr(),
+                  dboxes.data_ptr(), Wc.data_ptr(), W1.data_ptr(), W2.data_ptr(), C, d_dec.data_ptr(), dh.data_ptr(),
+                  dz.data_ptr(), dWc.data_ptr(), dbc.data_ptr(), dW1.data_ptr(), db1.data_ptr(), dW2.data_ptr(),
+                  db2.data_ptr(), M, _stream())
+        return d_dec, None, dWc, dbc, dW1, db1, dW2, db2
+
+
+def heads(dec: Tensor, centers: Tensor, Wc: Tensor, bc: Tensor, W1: Tensor, b1: Tensor, W2: Tensor, b2: Tensor):
+    """dec bf16 [M,512] (class stream | box stream), centers fp32 [M,2] -> (logits fp32 [M,C], boxes fp32 [M,4]):
+    logits = Linear(Wc, bc)(dec[:, :256]); boxes = sigmoid(Linear(W2,b2)(relu(Linear(W1,b1)(dec[:, 256:]))) +
+    [inverse_sigmoid(centers), 0, 0])  (model.py:120-131).  Differentiable w.r.t. dec and the six parameters."""
+    return _HeadsFn.apply(dec, centers, Wc, bc, W1, b1, W2, b2)
+
+
 class _SetLossFn(torch.autograd.Function):
     """total = w_class*class + w_bbox*bbox + w_ciou*ciou with hand-written gradients (csrc/set_loss.cu)."""
 

@@ -58,3 +58,40 @@ def test_sine_pos2d_wide_and_padded():
     pf, _ = ops.sine_pos2d(mask.cuda(), want_f32=True, want_bf16=False)
     ref = O.sine_pos2d(mask).flatten(2).transpose(1, 2)
     assert float((pf.cpu() - ref).abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize("M,C", [(800, 91), (37, 7), (8, 128)])
+def test_heads_fwd_bwd(M, C):
+    """csrc/heads.cu against the plain torch fp32 statement of model.py:120-131 (same bf16 decoder output)."""
+    import torch
+    from object_detection_destr_b200 import ops
+    g = torch.Generator().manual_seed(M + C)
+    dec = (torch.randn(M, 512, generator=g) * 0.7).bfloat16()
+    centers = torch.rand(M, 2, generator=g) * 0.98 + 0.01
+    centers[0, 0] = 0.0  # clamped by inverse_sigmoid (misc.py:59-62)
+    P = [torch.randn(C, 256, generator=g) * 0.06, torch.randn(C, generator=g) * 0.1,
+         torch.randn(256, 256, generator=g) * 0.06, torch.randn(256, generator=g) * 0.1,
+         torch.randn(4, 256, generator=g) * 0.06, torch.randn(4, generator=g) * 0.1]
+    dl, db = torch.randn(M, C, generator=g), torch.randn(M, 4, generator=g)
+
+    def ref(dec_f, Wc, bc, W1, b1, W2, b2):
+        logits = dec_f[:, :256] @ Wc.t() + bc
+        delta = torch.relu(dec_f[:, 256:] @ W1.t() + b1) @ W2.t() + b2
+        inv = -torch.log(1.0 / centers.double().clamp(min=1e-6) - 1.0)
+        return logits, torch.cat([delta[:, :2] + inv, delta[:, 2:]], -1).sigmoid()
+
+    dec_r = dec.double().requires_grad_()
+    Pr = [p.double().requires_grad_() for p in P]
+    lr, br = ref(dec_r, *Pr)
+    ((lr * dl.double()).sum() + (br * db.double()).sum()).backward()
+
+    dec_d = dec.cuda().requires_grad_()
+    Pd = [p.cuda().requires_grad_() for p in P]
+    lo, bo = ops.heads(dec_d, centers.cuda(), *Pd)
+    ((lo * dl.cuda()).sum() + (bo * db.cuda()).sum()).backward()
+    assert torch.allclose(lo.cpu().double(), lr, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(bo.cpu().double(), br, rtol=1e-5, atol=1e-6)
+    # d_dec leaves in bf16 (the decoder's gradient dtype): 2^-8 relative
+    assert torch.allclose(dec_d.grad.cpu().double(), dec_r.grad, rtol=1e-2, atol=2e-3)
+    for got, exp in zip(Pd, Pr):
+        assert torch.allclose(got.grad.cpu().double(), exp.grad, rtol=1e-4, atol=1e-4 * float(exp.grad.abs().max()))
