@@ -21,21 +21,26 @@ struct Best {
   double lowest;
   int first, last_unassigned;
 };
-__device__ __forceinline__ Best combine(const Best& a, const Best& b) {
-  if (a.lowest < b.lowest) return a;
-  if (b.lowest < a.lowest) return b;
-  return Best{a.lowest, min(a.first, b.first), max(a.last_unassigned, b.last_unassigned)};
-}
+// combining rule of two partial scans (equivalent to the sequential scan): the lower value wins; on equal values
+// first = min(first), last_unassigned = max(last_unassigned)
+// warp-wide combine with four redux.sync instead of a 5-round shuffle butterfly of (double, int, int): the double is
+// mapped to an order-preserving 64-bit key, whose high and low words are minimised one after the other; among the
+// lanes that hold the minimum, first = min and last_unassigned = max
 __device__ __forceinline__ Best warp_best(Best v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    Best w;
-    w.lowest = __shfl_xor_sync(0xffffffffu, v.lowest, o);
-    w.first = __shfl_xor_sync(0xffffffffu, v.first, o);
-    w.last_unassigned = __shfl_xor_sync(0xffffffffu, v.last_unassigned, o);
-    v = combine(v, w);
-  }
-  return v;
+  const unsigned full = 0xffffffffu;
+  const long long bits = __double_as_longlong(v.lowest + 0.0);  // (+0.0: -0 and +0 must map to one key)
+  const unsigned long long key = static_cast<unsigned long long>(bits) ^
+                                 (bits < 0 ? 0xffffffffffffffffull : 0x8000000000000000ull);
+  const unsigned hi = static_cast<unsigned>(key >> 32), lo = static_cast<unsigned>(key);
+  const unsigned mhi = __reduce_min_sync(full, hi);
+  const unsigned mlo = __reduce_min_sync(full, hi == mhi ? lo : 0xffffffffu);
+  const bool mine = hi == mhi && lo == mlo;
+  Best r;
+  r.first = static_cast<int>(__reduce_min_sync(full, mine ? static_cast<unsigned>(v.first) : 0x7fffffffu));
+  r.last_unassigned = __reduce_max_sync(full, mine ? v.last_unassigned : -1);
+  const unsigned src = __ffs(__ballot_sync(full, mine)) - 1;
+  r.lowest = __shfl_sync(full, v.lowest, src);
+  return r;
 }
 
 // one warp per image; dynamic shared memory: 3 double[M] + 4 int[M] + 2 uint8[M], M = max(Q, max targets)
