@@ -268,7 +268,7 @@ int destr_set_loss_fwd_bwd(const float* logits, const float* boxes, const int64_
 
 /* ---------------- mini-detector query selection ---------------- */
 
-/* MiniDetector.get_topk_index + the gathers of MiniDetector.forward (mini_detector.py:70-104, 142-170), one launch:
+/* MiniDetector.get_topk_index + the gathers of MiniDetector.forward (mini_detector.py:70-104, 142-170), two small launches:
  *   scores fp32 [B,N,C]   class scores as passed at :156 (sigmoid'ed, padded rows zeroed); key = max over classes
  *   mask   u8 [B,N] (1 = padded) or NULL;   cls_feat, reg_feat fp32 [B,N,D] (D % 4 == 0);   coords fp32 [B,N,4]
  *   k      = min(top_k, N, valid positions of image 0), computed by the caller as the reference does (:153-154)
@@ -276,10 +276,11 @@ int destr_set_loss_fwd_bwd(const float* logits, const float* boxes, const int64_
  *            inside a tie is torch.topk's unspecified one); an image with valid < k un-padded positions keeps its
  *            top `valid` and fills slot s >= valid with idx[valid-1-(s % valid)] (:86-98)
  *   sel_f32 [B,k,2D] and/or sel_bf16 (either may be NULL) = [cls_feat | reg_feat] rows; centers fp32 [B,k,2]
- *   status int32 [B]: 1 = image without valid positions (the reference raises ZeroDivisionError). */
+ *   status int32 [B]: 1 = image without valid positions (the reference raises ZeroDivisionError).
+ *   key_ws: scratch of B*N + B 32-bit words. */
 int destr_select_queries(const float* scores, const uint8_t* mask, const float* cls_feat, const float* reg_feat,
                          const float* coords, int B, int N, int C, int D, int k, int64_t* topk_idx, float* sel_f32,
-                         void* sel_bf16, float* centers, int32_t* status, void* stream);
+                         void* sel_bf16, float* centers, int32_t* status, uint32_t* key_ws, void* stream);
 
 /* ---------------- prediction heads ---------------- */
 

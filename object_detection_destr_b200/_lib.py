@@ -54,7 +54,7 @@ SIGNATURES = {
     "destr_box_refine": [_p, _p, _p, _i, _p],
     "destr_match_cost_blockdiag": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _f, _i, _p],
     "destr_lsap_blockdiag": [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p],
-    "destr_select_queries": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p],
+    "destr_select_queries": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p],
     "destr_heads_fwd": [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _p],
     "destr_heads_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p],
     "destr_flat_adamw": [_p, _p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _p, _p, _i64, _f, _p],
@@ -73,7 +73,7 @@ lib.destr_last_error.argtypes = []
 lib.destr_last_error.restype = C.c_char_p
 
 # kernels launched per C-ABI call (bench.py reports the sum over a step as gpu_launches)
-KERNELS_PER_CALL = {"destr_enc_attn_bwd": 3, "destr_heads_bwd": 2, "destr_split_cross_attn_fwd": 2, "destr_split_cross_attn_bwd_ds": 2}
+KERNELS_PER_CALL = {"destr_enc_attn_bwd": 3, "destr_select_queries": 2, "destr_heads_bwd": 2, "destr_split_cross_attn_fwd": 2, "destr_split_cross_attn_bwd_ds": 2}
 launch_count = 0
 # bench.py: {name: []} -> (start, end) CUDA-event pairs are appended around every call of `name`
 KERNEL_TIMERS = None

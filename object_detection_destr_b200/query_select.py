@@ -1,7 +1,7 @@
 """Query selection of the mini-detector on the B200 kernels (reference src/model/blocks/mini_detector.py).
 
 `get_topk_index` keeps the reference method's signature and return value; `select_queries` is the tail of
-MiniDetector.forward (:142-170) -- top-k + padding fix-up + gathers -- as one kernel launch.  The only host-side
+MiniDetector.forward (:142-170) -- top-k + padding fix-up + gathers -- as two small kernel launches (keys, rank + gather).  The only host-side
 quantity is k = min(top_k, H*W, valid positions of image 0) (:153-154): it fixes the output SHAPE, so the reference
 reads it back from the device; pass `valid0` when the padding mask was built on the host (as data loaders do) and no
 synchronisation happens at all.
@@ -44,9 +44,10 @@ def select_queries(scores: Tensor, mask: Optional[Tensor], cls_features: Tensor,
     sel = torch.empty(B, k, 2 * D, dtype=torch.bfloat16 if want_bf16 else torch.float32, device=dev)
     cen = torch.empty(B, k, 2, dtype=torch.float32, device=dev)
     status = torch.empty(B, dtype=torch.int32, device=dev)
+    ws = torch.empty(B * N + B, dtype=torch.int32, device=dev)
     _lib.call("destr_select_queries", sc.data_ptr(), ops._ptr(mk), cf.data_ptr(), rf.data_ptr(), co.data_ptr(), B, N, C,
               D, k, idx.data_ptr(), None if want_bf16 else sel.data_ptr(), sel.data_ptr() if want_bf16 else None,
-              cen.data_ptr(), status.data_ptr(), ops._stream())
+              cen.data_ptr(), status.data_ptr(), ws.data_ptr(), ops._stream())
     select_queries.last_status = status  # device tensor; check_status() reads it back
     return sel, cen, idx
 
