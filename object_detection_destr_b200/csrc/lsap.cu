@@ -125,21 +125,42 @@ lsap_kernel(const float* __restrict__ cost, const int32_t* __restrict__ offs, in
       if (lane == 0) SR[i] = 1;
       const double ui = u[i];
       Best best{CUDART_INF, 0x7fffffff, -1};
-      for (int it = lane; it < num_remaining; it += 32) {
-        const int j = remaining[it];
-        const double r = min_val + cst(i, j) - ui - v[j];
-        if (r < spc[j]) {
-          path[j] = i;
-          spc[j] = r;
+      // this lane's columns, four at a time: the (independent) loads and fp64 updates of the four are issued
+      // together, then folded into `best` in scan order -- the serial chain per step is one column, not four
+      for (int it0 = lane; it0 < num_remaining; it0 += 128) {
+        int jj[4];
+        double rr[4], sp[4];
+        bool un[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int it = it0 + 32 * q;
+          jj[q] = it < num_remaining ? remaining[it] : -1;
         }
-        const double s = spc[j];
-        const bool unassigned = row4col[j] == -1;
-        if (s < best.lowest) {
-          best = Best{s, it, unassigned ? it : -1};
-        } else if (s == best.lowest) {
-          if (best.first == 0x7fffffff) best.first = it;  // (only when everything so far was +inf)
-          if (unassigned) best.last_unassigned = it;
-        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (jj[q] >= 0) {
+            const int j = jj[q];
+            rr[q] = min_val + cst(i, j) - ui - v[j];
+            sp[q] = spc[j];
+            un[q] = row4col[j] == -1;
+          }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (jj[q] >= 0) {
+            const int j = jj[q], it = it0 + 32 * q;
+            double s = sp[q];
+            if (rr[q] < s) {
+              path[j] = i;
+              spc[j] = rr[q];
+              s = rr[q];
+            }
+            if (s < best.lowest) {
+              best = Best{s, it, un[q] ? it : -1};
+            } else if (s == best.lowest) {
+              if (best.first == 0x7fffffff) best.first = it;  // (only when everything so far was +inf)
+              if (un[q]) best.last_unassigned = it;
+            }
+          }
       }
       best = warp_best(best);
       min_val = best.lowest;
