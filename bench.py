@@ -339,7 +339,8 @@ def run_ours(args):
         tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
         if os.path.exists(tp):
             with open(tp) as f:
-                traffic = json.load(f).get(dom)
+                tj = json.load(f)
+                traffic = tj.get(dom + "@dropout", tj.get(dom)) if args.dropout else tj.get(dom)
         roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": pk["tf_burst"], "unit": "TFLOP/s",
                 "frac": ach / pk["tf_burst"], "traffic": traffic,
                 "peak_source": pk["src"] + " (burst bf16 GEMM; kernel timed alone with CUDA events, L2 flushed between launches)",
