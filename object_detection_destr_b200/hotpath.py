@@ -48,7 +48,8 @@ class TransformerHalf(nn.Module):
         re-points the encoder/decoder parameters at views of its flat master buffer)."""
         if self._rt is None:
             from .runtime import HotPathRuntime
-            self._rt = HotPathRuntime(self._encoder, self._decoder, self._bbox_embed, self._cls_embed.weight.device)
+            self._rt = HotPathRuntime(self._encoder, self._decoder, self._bbox_embed, self._cls_embed.weight.device,
+                                      cls_embed=self._cls_embed)
         return self._rt
 
     def make_optimizer(self, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2):
@@ -109,7 +110,12 @@ class TransformerHalf(nn.Module):
                                         _params(self._bbox_embed), len(self._decoder._decoder), B, Q, N,
                                         pairs_override=pairs_override, aux=aux)
         # class + box heads, fp32 as in the reference (model.py:120-131): one kernel (csrc/heads.cu)
-        cls, boxes = ops.heads(dec, centers, self._cls_embed.weight, self._cls_embed.bias,
-                               self._bbox_embed[0].weight, self._bbox_embed[0].bias,
-                               self._bbox_embed[2].weight, self._bbox_embed[2].bias)
+        hp = (self._cls_embed.weight, self._cls_embed.bias, self._bbox_embed[0].weight, self._bbox_embed[0].bias,
+              self._bbox_embed[2].weight, self._bbox_embed[2].bias)
+        # with the runtime the head parameters live in its flat buffer: the backward kernel writes their gradients
+        # straight into the flat gradient buffer (.grad are views of it)
+        grad_out = None
+        if self.use_runtime and self._rt.heads_in_flat and torch.is_grad_enabled():
+            grad_out = tuple(self._rt.P.g("h." + n) for n in ("cls_w", "cls_b", "box0_w", "box0_b", "box2_w", "box2_b"))
+        cls, boxes = ops.heads(dec, centers, *hp, grad_out=grad_out)
         return {"pred_class": cls.view(B, Q, -1), "pred_boxes": boxes.view(B, Q, 4)}, enc.view(B, N, C)

@@ -485,7 +485,8 @@ class _HeadsFn(torch.autograd.Function):
     """Class + box heads (csrc/heads.cu): one forward launch, two backward launches."""
 
     @staticmethod
-    def forward(ctx, dec, centers, Wc, bc, W1, b1, W2, b2):
+    def forward(ctx, dec, centers, Wc, bc, W1, b1, W2, b2, grad_out=None):
+        ctx.grad_out = grad_out
         dec = _chk(dec.contiguous(), BF16, "dec")
         M, C = dec.shape[0], Wc.shape[0]
         if dec.shape[1] != 512 or tuple(W1.shape) != (256, 256) or tuple(W2.shape) != (4, 256) or Wc.shape[1] != 256:
@@ -511,21 +512,31 @@ class _HeadsFn(torch.autograd.Function):
         dboxes = torch.zeros(M, 4, **f32) if dboxes is None else _chk(dboxes.contiguous(), torch.float32, "dboxes")
         d_dec = torch.empty(M, 512, dtype=BF16, device=dev)
         dh, dz = torch.empty(M, 256, **f32), torch.empty(M, 4, **f32)
-        dWc, dbc = torch.empty(C, 256, **f32), torch.empty(C, **f32)
-        dW1, db1 = torch.empty(256, 256, **f32), torch.empty(256, **f32)
-        dW2, db2 = torch.empty(4, 256, **f32), torch.empty(4, **f32)
+        if ctx.grad_out is not None:  # caller-owned gradient tensors (overwritten), e.g. views of a flat buffer
+            dWc, dbc, dW1, db1, dW2, db2 = (_chk(t, torch.float32, "grad_out") for t in ctx.grad_out)
+            if not all(t.is_contiguous() for t in ctx.grad_out):
+                raise ValueError("heads: grad_out tensors must be contiguous")
+        else:
+            dWc, dbc = torch.empty(C, 256, **f32), torch.empty(C, **f32)
+            dW1, db1 = torch.empty(256, 256, **f32), torch.empty(256, **f32)
+            dW2, db2 = torch.empty(4, 256, **f32), torch.empty(4, **f32)
         _lib.call("destr_heads_bwd", dec.data_ptr(), hidden.data_ptr(), boxes.data_ptr(), dlogits.data_ptr(),
                   dboxes.data_ptr(), Wc.data_ptr(), W1.data_ptr(), W2.data_ptr(), C, d_dec.data_ptr(), dh.data_ptr(),
                   dz.data_ptr(), dWc.data_ptr(), dbc.data_ptr(), dW1.data_ptr(), db1.data_ptr(), dW2.data_ptr(),
                   db2.data_ptr(), M, _stream())
-        return d_dec, None, dWc, dbc, dW1, db1, dW2, db2
+        if ctx.grad_out is not None:
+            return (d_dec,) + (None,) * 8
+        return d_dec, None, dWc, dbc, dW1, db1, dW2, db2, None
 
 
-def heads(dec: Tensor, centers: Tensor, Wc: Tensor, bc: Tensor, W1: Tensor, b1: Tensor, W2: Tensor, b2: Tensor):
+def heads(dec: Tensor, centers: Tensor, Wc: Tensor, bc: Tensor, W1: Tensor, b1: Tensor, W2: Tensor, b2: Tensor,
+          grad_out=None):
     """dec bf16 [M,512] (class stream | box stream), centers fp32 [M,2] -> (logits fp32 [M,C], boxes fp32 [M,4]):
     logits = Linear(Wc, bc)(dec[:, :256]); boxes = sigmoid(Linear(W2,b2)(relu(Linear(W1,b1)(dec[:, 256:]))) +
-    [inverse_sigmoid(centers), 0, 0])  (model.py:120-131).  Differentiable w.r.t. dec and the six parameters."""
-    return _HeadsFn.apply(dec, centers, Wc, bc, W1, b1, W2, b2)
+    [inverse_sigmoid(centers), 0, 0])  (model.py:120-131).  Differentiable w.r.t. dec and the six parameters.
+    grad_out = six caller-owned tensors (dWc, dbc, dW1, db1, dW2, db2): backward overwrites them instead of returning
+    parameter gradients to autograd."""
+    return _HeadsFn.apply(dec, centers, Wc, bc, W1, b1, W2, b2, grad_out)
 
 
 class _SetLossFn(torch.autograd.Function):

@@ -57,7 +57,10 @@ class FlatParams:
     reference parameter names and any optimizer keep working; the dead `_proj_to_q/k/v` parameters of
     the reference encoder block are left alone (they never receive gradients)."""
 
-    def __init__(self, encoder: nn.Module, decoder: nn.Module, device):
+    def __init__(self, encoder: nn.Module, decoder: nn.Module, device, heads=()):
+        """heads: [(name, parameter)] of the prediction heads -- they join the fp32 part of the buffer (one optimizer
+        launch, one gradient exchange for everything); their gradients are WRITTEN by the heads kernel before
+        backward() of the runtime starts, so begin_backward() leaves that region alone."""
         e, d = dict(encoder.named_parameters()), dict(decoder.named_parameters())
         Le, Ld = len(encoder._encoder), len(decoder._decoder)
         self.Le, self.Ld = Le, Ld
@@ -109,6 +112,11 @@ class FlatParams:
         for name, t in S:
             self.off[name] = (o, t.shape)
             o += (t.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.heads_off = o
+        H = [(f"h.{name}", t) for name, t in heads]
+        for name, t in H:
+            self.off[name] = (o, t.shape)
+            o += (t.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
         self.n = o
         self.m32 = torch.zeros(o, dtype=torch.float32, device=device)
         self.s16 = torch.zeros(o, dtype=BF16, device=device)
@@ -117,7 +125,7 @@ class FlatParams:
         self.params: List[nn.Parameter] = []
         self._gviews: List[Tensor] = []
         with torch.no_grad():
-            for name, t in W + S:
+            for name, t in W + S + H:
                 off, shape = self.off[name]
                 view = self.m32[off:off + t.numel()].view(shape)
                 view.copy_(t.detach().to(device))
@@ -161,7 +169,7 @@ class FlatParams:
         self.s16.copy_(self.m32)
 
     def begin_backward(self):
-        self.g32[self.nW:].zero_()
+        self.g32[self.nW:self.heads_off].zero_()
         self._written.clear()
 
     # ---- data parallel: the one exchange of a training step, overlapped with backward ----
@@ -321,8 +329,13 @@ def dec_site(layer: int, name: str) -> int:
 class HotPathRuntime:
     """forward()/backward() of encoder -> fine_pos -> decoder on token-major bf16 activations."""
 
-    def __init__(self, encoder: nn.Module, decoder: nn.Module, bbox_embed: nn.Module, device):
-        self.P = FlatParams(encoder, decoder, device)
+    def __init__(self, encoder: nn.Module, decoder: nn.Module, bbox_embed: nn.Module, device, cls_embed=None):
+        heads = []
+        if cls_embed is not None:  # the prediction heads share the flat buffer (fp32 region)
+            heads = [("cls_w", cls_embed.weight), ("cls_b", cls_embed.bias), ("box0_w", bbox_embed[0].weight),
+                     ("box0_b", bbox_embed[0].bias), ("box2_w", bbox_embed[2].weight), ("box2_b", bbox_embed[2].bias)]
+        self.P = FlatParams(encoder, decoder, device, heads=heads)
+        self.heads_in_flat = bool(heads)
         self.bbox = bbox_embed
         self.enc_mod, self.dec_mod = encoder, decoder
         self.seed = torch.zeros(1, dtype=torch.int32, device=device)  # dropout seed (device: graph replays see updates)
