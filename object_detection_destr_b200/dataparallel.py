@@ -4,8 +4,8 @@ gradients (the reference trains single-process, src/train/train.py:164-178; this
 equivalent of running it under DDP).
 
 The gradients of the encoder/decoder already live in ONE flat fp32 buffer (`runtime.FlatParams.g32`), so
-they go to NCCL as a single in-place all-reduce with no flatten/unflatten copies; the few tensors outside
-that buffer (the class / box heads) are coalesced into one more call.  Nothing here touches the device
+they go to NCCL as in-place all-reduces with no flatten/unflatten copies (with the hand-scheduled runtime the
+class / box heads live in that buffer too); tensors outside it, if any, are coalesced into one more call.  Nothing here touches the device
 directly, which is why the same code runs under `gloo` on CPU tensors in tests/test_dataparallel_gloo.py.
 """
 from __future__ import annotations
