@@ -8,12 +8,21 @@ synchronisation happens at all.
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import NamedTuple, Optional, Tuple
 
 import torch
 from torch import Tensor
 
 from . import _lib, ops
+
+
+class QuerySelection(NamedTuple):
+    """(selected_objects (B,k,2D), selected_centers (B,k,2), topk_idx (B,k) int64, status (B,) int32 device tensor:
+    non-zero = that image has no valid position -- the reference raises there; see check_status)."""
+    selected_objects: Tensor
+    selected_centers: Tensor
+    topk_idx: Tensor
+    status: Tensor
 
 
 def _avail_k(top_k: int, N: int, mask: Optional[Tensor], valid0: Optional[int]) -> int:
@@ -23,11 +32,12 @@ def _avail_k(top_k: int, N: int, mask: Optional[Tensor], valid0: Optional[int]) 
 
 
 def select_queries(scores: Tensor, mask: Optional[Tensor], cls_features: Tensor, reg_features: Tensor,
-                   coords: Tensor, top_k: int, valid0: Optional[int] = None, want_bf16: bool = False):
+                   coords: Tensor, top_k: int, valid0: Optional[int] = None, want_bf16: bool = False) -> QuerySelection:
     """scores (B,N,C) fp32 = det_output_class as passed to get_topk_index (:156); mask (B,N) bool (True = padded);
     cls_features / reg_features (B,N,D) fp32; coords (B,N,4) fp32 (masked det_output_coord).
-    -> (selected_objects (B,k,2D), selected_centers (B,k,2), topk_idx (B,k) int64); selected_objects is bf16 when
-    want_bf16 (the dtype the decoder kernels consume) else fp32.  Outputs are detached, as in the reference."""
+    -> QuerySelection(selected_objects (B,k,2D), selected_centers (B,k,2), topk_idx (B,k) int64, status (B,));
+    selected_objects is bf16 when want_bf16 (the dtype the decoder kernels consume) else fp32.  Outputs are detached,
+    as in the reference.  Nothing is read back from the device: `check_status(result.status)` does that on demand."""
     if not scores.is_cuda:
         raise RuntimeError("select_queries needs CUDA tensors (there is no CPU fallback)")
     B, N, C = scores.shape
@@ -48,14 +58,13 @@ def select_queries(scores: Tensor, mask: Optional[Tensor], cls_features: Tensor,
     _lib.call("destr_select_queries", sc.data_ptr(), ops._ptr(mk), cf.data_ptr(), rf.data_ptr(), co.data_ptr(), B, N, C,
               D, k, idx.data_ptr(), None if want_bf16 else sel.data_ptr(), sel.data_ptr() if want_bf16 else None,
               cen.data_ptr(), status.data_ptr(), ws.data_ptr(), ops._stream())
-    select_queries.last_status = status  # device tensor; check_status() reads it back
-    return sel, cen, idx
+    return QuerySelection(sel, cen, idx, status)
 
 
-def check_status(status: Optional[Tensor] = None) -> None:
-    """Raise what the reference raises for an image without valid positions (ZeroDivisionError at :93)."""
-    st = status if status is not None else getattr(select_queries, "last_status", None)
-    if st is not None and bool((st != 0).any()):
+def check_status(status: Tensor) -> None:
+    """Raise what the reference raises for an image without valid positions (ZeroDivisionError at :93).
+    Reads `status` back from the device (a synchronisation)."""
+    if bool((status != 0).any()):
         raise ZeroDivisionError("select_queries: an image has no valid (un-padded) position")
 
 
@@ -63,6 +72,8 @@ def get_topk_index(scores: Tensor, k: int, padding_mask: Optional[Tensor]) -> Tu
     """MiniDetector.get_topk_index (:70-104): -> (batch_idx int32 [B*k], idx int64 [B*k])."""
     B, N, _ = scores.shape
     z = torch.zeros(B, N, 4, dtype=torch.float32, device=scores.device)
-    _, _, idx = select_queries(scores, padding_mask, z, z, z, k, valid0=N)
+    r = select_queries(scores, padding_mask, z, z, z, k, valid0=N)
+    check_status(r.status)  # the reference method raises here (:93), and it synchronises anyway
+    idx = r.topk_idx
     batch_idx = torch.arange(B, device=scores.device, dtype=torch.int32).repeat_interleave(k)
     return batch_idx, idx.flatten()

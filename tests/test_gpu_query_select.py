@@ -17,14 +17,14 @@ def test_kernel_matches_reference_golden(i):
     B, N, _ = c["scores"].shape
     t = lambda a: torch.from_numpy(a).cuda()
     if "sel" in c:
-        sel, cen, idx = QS.select_queries(t(c["scores"]), t(c["mask"]), t(c["cls_feat"]), t(c["reg_feat"]), t(c["coords"]),
-                                          top_k=10 ** 6, valid0=k)
+        sel, cen, idx, status = QS.select_queries(t(c["scores"]), t(c["mask"]), t(c["cls_feat"]), t(c["reg_feat"]),
+                                                  t(c["coords"]), top_k=10 ** 6, valid0=k)
+        QS.check_status(status)
         assert np.array_equal(sel.cpu().numpy(), c["sel"]) and np.array_equal(cen.cpu().numpy(), c["cen"])
     else:
         bi, flat = QS.get_topk_index(t(c["scores"]), k, t(c["mask"]))
         idx = flat.view(B, k)
         assert bi.tolist() == [b for b in range(B) for _ in range(k)]
-    QS.check_status()
     idx = idx.cpu().numpy()
     check_against_reference(c, idx)
     assert np.array_equal(idx, QO.topk_index(c["scores"], k, c["mask"]))  # and bit-exact against the oracle, ties included
@@ -43,10 +43,10 @@ def test_kernel_matches_oracle(B, N, C, k, pad):
     cf, rf = torch.randn(B, N, 256, generator=g), torch.randn(B, N, 256, generator=g)
     co = torch.rand(B, N, 4, generator=g)
     ei, es, ec = QO.select_queries(scores.numpy(), mask.numpy(), cf.numpy(), rf.numpy(), co.numpy(), k)
-    sel, cen, idx = QS.select_queries(scores.cuda(), mask.cuda(), cf.cuda(), rf.cuda(), co.cuda(), top_k=k)
+    sel, cen, idx, _ = QS.select_queries(scores.cuda(), mask.cuda(), cf.cuda(), rf.cuda(), co.cuda(), top_k=k)
     assert np.array_equal(idx.cpu().numpy(), ei)
     assert np.array_equal(sel.cpu().numpy(), es) and np.array_equal(cen.cpu().numpy(), ec)
-    sel16, _, _ = QS.select_queries(scores.cuda(), mask.cuda(), cf.cuda(), rf.cuda(), co.cuda(), top_k=k, want_bf16=True)
+    sel16 = QS.select_queries(scores.cuda(), mask.cuda(), cf.cuda(), rf.cuda(), co.cuda(), top_k=k, want_bf16=True).selected_objects
     assert torch.equal(sel16.cpu(), torch.from_numpy(es).bfloat16())
 
 
@@ -56,6 +56,9 @@ def test_no_valid_position_is_reported():
     mask = torch.zeros(2, 32, dtype=torch.bool)
     mask[1] = True
     z = torch.zeros(2, 32, 8).cuda()
-    QS.select_queries(scores, mask.cuda(), z, z, torch.zeros(2, 32, 4).cuda(), top_k=5)
+    r = QS.select_queries(scores, mask.cuda(), z, z, torch.zeros(2, 32, 4).cuda(), top_k=5)
+    assert r.status.tolist() == [0, 1]
     with pytest.raises(ZeroDivisionError):
-        QS.check_status()
+        QS.check_status(r.status)
+    with pytest.raises(ZeroDivisionError):
+        QS.get_topk_index(scores, 5, mask.cuda())
