@@ -266,6 +266,18 @@ int destr_set_loss_fwd_bwd(const float* logits, const float* boxes, const int64_
                            float w_bbox, float w_ciou, float* losses, float* dlogits, float* dboxes,
                            float* workspace, void* stream);
 
+/* ---------------- FFN first layer: GEMM + bias + ReLU + dropout (tcgen05) ---------------- */
+
+/* out = dropout(relu(a w^T + bias)) in bf16: `dropout2(relu(fc1(x)))` of encoder_block.py:107-108 and the branch FFNs
+ * of decoder_block.py:255 as one tcgen05 GEMM whose epilogue does the whole tail (first member).
+ *   a bf16 [M,K], row pitch lda;  w bf16 [N,K] (nn.Linear layout);  bias fp32 [N] or NULL;  out bf16 [M,N], pitch ldo
+ *   K == 256 (the weight block of a CTA stays resident in shared memory), N % 256 == 0, pitches multiples of 8
+ *   elements;  relu = 0 skips the ReLU
+ *   dropout: the mask of destr_dropout_inplace on the [M,N] output (row = output row, column = output column). */
+int destr_linear_bias_relu_dropout(const void* a, int lda, const void* w, const float* bias, void* out, int ldo,
+                                   int M, int N, int K, int relu, const uint32_t* drop_seed, uint32_t drop_thr16,
+                                   uint32_t drop_site, void* stream);
+
 /* ---------------- mini-detector query selection ---------------- */
 
 /* MiniDetector.get_topk_index + the gathers of MiniDetector.forward (mini_detector.py:70-104, 142-170), two small launches:

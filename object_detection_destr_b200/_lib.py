@@ -54,6 +54,7 @@ SIGNATURES = {
     "destr_box_refine": [_p, _p, _p, _i, _p],
     "destr_match_cost_blockdiag": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _f, _i, _p],
     "destr_lsap_blockdiag": [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p],
+    "destr_linear_bias_relu_dropout": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _p, _u, _u, _p],
     "destr_select_queries": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p],
     "destr_heads_fwd": [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _p],
     "destr_heads_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p],

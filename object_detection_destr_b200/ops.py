@@ -195,6 +195,22 @@ def dropout_inplace(x: Tensor, drop) -> Tensor:
     return x
 
 
+def linear_bias_relu_dropout(x: Tensor, w: Tensor, bias: Optional[Tensor], drop=None, relu: bool = True) -> Tensor:
+    """dropout(relu(x w^T + bias)) as one tcgen05 GEMM (csrc/gemm_bias_relu.cu): x bf16 [M,K] (unit column stride),
+    w bf16 [N,K] contiguous, bias fp32 [N]; K == 256, N % 256 == 0.  drop: see _dargs (None = no dropout)."""
+    _chk(x, BF16, "x"), _chk(w, BF16, "w")
+    M, K = x.shape
+    N = w.shape[0]
+    if x.stride(1) != 1 or not w.is_contiguous() or w.shape[1] != K or K != 256 or N % 256:
+        raise ValueError(f"linear_bias_relu_dropout: unsupported operands x {tuple(x.shape)} w {tuple(w.shape)}")
+    out = torch.empty(M, N, dtype=BF16, device=x.device)
+    ptr, thr, site = _dargs(drop)
+    _lib.call("destr_linear_bias_relu_dropout", x.data_ptr(), x.stride(0), w.data_ptr(),
+              _ptr(None if bias is None else _chk(bias, torch.float32, "bias")), out.data_ptr(), N, M, N, K, int(relu),
+              ptr, thr, site, _stream())
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
 # encoder attention
 # ----------------------------------------------------------------------------------------------

@@ -33,6 +33,7 @@ Tensor = torch.Tensor
 BF16 = torch.bfloat16
 _ALIGN = 64
 import os as _os
+_FUSED_FFN1 = _os.environ.get("DESTR_FUSED_FFN1", "1") == "1"
 _FORK = {k: _os.environ.get("DESTR_FORK_" + k, d) == "1" for k, d in (("ENC_V", "0"), ("DEC_HEAD", "1"), ("DSIN", "1"))}
 
 
@@ -422,8 +423,12 @@ class HotPathRuntime:
         o = _mm_bias(a, P.w(f"e{l}.out_w"), P.w(f"e{l}.out_b"))
         x1, m1, r1 = ops.add_layernorm(x, o, P.f(f"e{l}.n1_w"), P.f(f"e{l}.n1_b"), save_stats=True,
                                        drop=self._d(dc["e.d1"], enc_site(l, "d1")))
-        f1 = _mm_bias_relu(x1, P.w(f"e{l}.fc1_w"), P.w(f"e{l}.fc1_b"))
-        ops.dropout_inplace(f1, self._d(dc["e.d2"], enc_site(l, "d2")))
+        if _FUSED_FFN1:  # tcgen05 GEMM with bias + ReLU + dropout2 in its epilogue (csrc/gemm_bias_relu.cu)
+            f1 = ops.linear_bias_relu_dropout(x1, P.w(f"e{l}.fc1_w"), P.f(f"e{l}.fc1_b"),
+                                              self._d(dc["e.d2"], enc_site(l, "d2")))
+        else:    # library path: cuBLASLt bias+ReLU epilogue, then the dropout pass
+            f1 = _mm_bias_relu(x1, P.w(f"e{l}.fc1_w"), P.w(f"e{l}.fc1_b"))
+            ops.dropout_inplace(f1, self._d(dc["e.d2"], enc_site(l, "d2")))
         g = _mm_bias(f1, P.w(f"e{l}.fc2_w"), P.w(f"e{l}.fc2_b"))
         x2, m2, r2 = ops.add_layernorm(x1, g, P.f(f"e{l}.n2_w"), P.f(f"e{l}.n2_b"), save_stats=True,
                                        drop=self._d(dc["e.d3"], enc_site(l, "d3")))

@@ -95,3 +95,33 @@ def test_heads_fwd_bwd(M, C):
     assert torch.allclose(dec_d.grad.cpu().double(), dec_r.grad, rtol=1e-2, atol=2e-3)
     for got, exp in zip(Pd, Pr):
         assert torch.allclose(got.grad.cpu().double(), exp.grad, rtol=1e-4, atol=1e-4 * float(exp.grad.abs().max()))
+
+
+@pytest.mark.parametrize("M,N,K,p", [(8400, 2048, 256, 0.3), (800, 1024, 256, 0.3), (37, 256, 256, 0.0), (33600, 2048, 256, 0.3)])
+def test_linear_bias_relu_dropout(M, N, K, p):
+    """tcgen05 GEMM + bias + ReLU + dropout epilogue (csrc/gemm_bias_relu.cu) vs fp32 torch with the numpy twin's mask."""
+    import numpy as np
+    import torch
+    from object_detection_destr_b200 import ops
+    from oracle.dropout_mask import keep_mask, scale_of, thr16_of
+    g = torch.Generator().manual_seed(M + N)
+    x = torch.randn(M, K, generator=g).bfloat16()
+    w = (torch.randn(N, K, generator=g) * K ** -0.5).bfloat16()
+    b = torch.randn(N, generator=g) * 0.5
+    ref = torch.relu(x.float() @ w.float().t() + b)
+    drop = None
+    if p > 0:
+        t = thr16_of(p)
+        ref = ref * torch.from_numpy(keep_mask(5, 77, np.arange(M), np.arange(N), t)).float() * scale_of(t)
+        drop = (torch.tensor([5], dtype=torch.int32, device="cuda"), ops.drop_thr16(p), 77)
+    out = ops.linear_bias_relu_dropout(x.cuda(), w.cuda(), b.cuda(), drop).cpu().float()
+    assert torch.isfinite(out).all()
+    # bf16 output of an fp32-accumulated product: 2^-8 relative
+    assert torch.allclose(out, ref, rtol=1e-2, atol=1e-2), float((out - ref).abs().max())
+    if p > 0:  # exactly the twin's zero pattern (ReLU zeros aside)
+        assert torch.equal((out == 0) | (ref == 0), ref == 0) or float(((out == 0) != (ref == 0)).float().mean()) < 1e-3
+    # a strided input view (row pitch > K) gives the same result
+    xs = torch.zeros(M, K + 64, dtype=torch.bfloat16)
+    xs[:, :K] = x
+    out2 = ops.linear_bias_relu_dropout(xs.cuda()[:, :K], w.cuda(), b.cuda(), drop).cpu().float()
+    assert torch.equal(out2, out)
