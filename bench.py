@@ -368,7 +368,7 @@ def run_ours(args):
                            "dropout": 0.3 if args.dropout else 0.0, "cuda_graphs": not args.eager, "l2": "4 rotating input batches; activations (~0.6 GB/step) exceed the 126 MB L2"},
                 "e2e": {"value": imgs / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": int(h2d_bytes),
                         "d2h_bytes_per_step": 4 + 4 * B, "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+                "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         # NCCL kernels are captured inside the CUDA graphs: release the graphs first, and leave without the
