@@ -54,7 +54,8 @@ class TransformerHalf(nn.Module):
 
     def make_optimizer(self, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2):
         """AdamW for this module (call after .to(device)).  With the hand-scheduled runtime: one flat kernel for
-        every encoder/decoder parameter (+ bf16 shadow refresh) and a fused torch AdamW for the heads; otherwise a
+        every parameter -- encoder, decoder and the prediction heads, which share the runtime's flat buffer --
+        (+ bf16 shadow refresh); otherwise a
         plain fused torch.optim.AdamW.  Same arithmetic either way (tests/test_gpu_engine.py)."""
         if not self.use_runtime:
             return torch.optim.AdamW(self.parameters(), lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,

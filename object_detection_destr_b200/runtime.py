@@ -275,9 +275,10 @@ class FlatParams:
 
 class FlatAdamW:
     """torch.optim.AdamW semantics on the runtime's flat parameter buffer: one kernel per step updates every
-    encoder/decoder parameter and refreshes the bf16 shadows (csrc/optim.cu).  `extra` parameters (the class /
-    box heads, which live outside the flat buffer) go through a regular fused torch AdamW with the same
-    hyper-parameters.  CUDA-graph capturable (the step count lives on the device)."""
+    parameter in it (encoder, decoder and -- with TransformerHalf -- the prediction heads) and refreshes the bf16
+    shadows (csrc/optim.cu); the kernel reads the bf16 weight gradients backward() left and folds the 1/world of the
+    data-parallel mean.  `extra` parameters living outside the flat buffer, if any, go through a regular fused torch
+    AdamW with the same hyper-parameters.  CUDA-graph capturable (the step count lives on the device)."""
 
     refreshes_shadows = True  # engine: no separate master -> bf16 shadow cast after step()
 
