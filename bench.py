@@ -148,34 +148,83 @@ class CpuReference:
         return float(loss.sum())
 
 
-def time_cpu_reference(sample_b: int, steps: int, warmup: int, dropout: float = 0.0):
+def _ref_harness():
+    """oracle/ref_harness.py when the staged reference (oracle/_ref, see oracle/stage_ref.py) travelled with the repo."""
+    from oracle import ref_harness as RH
+    return RH if RH.available() else None
+
+
+def time_cpu_reference(sample_b: int, steps: int, warmup: int, dropout: float = 0.0, budget_s: float = 200.0):
+    """The reference's transformer-half training step on the host cores.  kind "reference": the UNMODIFIED reference
+    modules (oracle/_ref: build_encoder / build_decoder / HungarianMatcherWoL1 / SetCriterion + AdamW) through
+    oracle/ref_harness.py; kind "port" (only if the staged copy is missing): the oracle restatement.
+    Each step is a bounded sample of the workload: batch `sample_b` of the config-2 images, halved until
+    (steps + warmup) steps fit `budget_s` (estimated from the first warm-up step).
+    -> (images/s, s/step, threads, kind, batch used, warm-up steps run)"""
     torch.set_num_threads(os.cpu_count() or 1)
-    ref = CpuReference(dropout=dropout)
-    for s in range(warmup):
-        ref.step(make_batch(0, s, sample_b))
+    RH = _ref_harness()
+    if RH is not None:
+        tr = RH.RefTrainer(CFG, "cpu", dropout=dropout > 0)
+        step, kind = (lambda b: float(tr.step(b).sum())), "reference"
+    else:
+        ref = CpuReference(dropout=dropout)
+        step, kind = ref.step, "port"
+    warmup = max(warmup, 1)
+    t0 = time.perf_counter()
+    step(make_batch(0, 0, sample_b))                      # warm-up step 1, also the cost estimate
+    t1 = time.perf_counter() - t0
+    b = sample_b
+    while b > 1 and (steps + warmup - 1) * t1 * b / sample_b > budget_s:
+        b //= 2
+    for s in range(1, warmup):
+        step(make_batch(0, s, b))
     t0 = time.perf_counter()
     for s in range(steps):
-        ref.step(make_batch(0, 100 + s, sample_b))
+        step(make_batch(0, 100 + s, b))
     dt = time.perf_counter() - t0
-    return sample_b * steps / dt, dt / steps, torch.get_num_threads()
+    return b * steps / dt, dt / steps, torch.get_num_threads(), kind, b, warmup
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_b = CFG["B"]
-    steps = max(1, min(args.steps, 10))
-    ips, spstep, cores = time_cpu_reference(sample_b, steps, min(args.warmup, 1), 0.3 if args.dropout else 0.0)
-    sample = f"{steps} steps of batch {sample_b} (the full config-2 batch; reference algorithm via oracle/destr_oracle.py, fp32 eager torch, all host threads)"
-    line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": steps,
-            "warmup": min(args.warmup, 1), "ms_per_step": spstep * 1e3, "higher_is_better": True, "scaling": "weak",
+    ips, spstep, cores, kind, b, warm = time_cpu_reference(CFG["B"], args.steps, args.warmup, 0.3 if args.dropout else 0.0)
+    what = ("the reference's own modules (oracle/_ref: build_encoder, build_decoder, HungarianMatcherWoL1, SetCriterion, AdamW)"
+            if kind == "reference" else "reference algorithm via oracle/destr_oracle.py")
+    sample = (f"{args.steps} steps of batch {b} of the config-2 images per step ({'the full batch' if b == CFG['B'] else 'bounded sample of the batch of ' + str(CFG['B'])}); "
+              f"{what}, fp32 eager torch, all host threads")
+    line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": warm, "ms_per_step": spstep * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": CFG["workload"], "dropout": 0.3 if args.dropout else 0.0},
-            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": CFG["workload"], "dropout": 0.3 if args.dropout else 0.0, "sample_batch": b},
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def time_reference_on_gpu(dev, dropout: bool, steps: int = 10, warmup: int = 3):
+    """SURVEY 8(d) "practical bar": the reference's own modules run by stock eager torch ON THIS GPU, same batch and
+    step (fwd + matcher + loss + bwd + AdamW), inputs resident on the device, in fp32 and under autocast(bf16).
+    None when the staged reference is absent."""
+    RH = _ref_harness()
+    if RH is None:
+        return None
+    out = {"what": "unmodified reference modules (oracle/_ref) through oracle/ref_harness.py, stock eager torch on this GPU, "
+                   "batch 8, device-resident inputs, fwd + matcher (C.cpu() + scipy) + loss + bwd + AdamW",
+           "steps": steps, "warmup": warmup, "dropout": 0.3 if dropout else 0.0}
+    batches = [make_batch(0, s, CFG["B"]) for s in range(4)]
+    for key, autocast in (("fp32", False), ("bf16", True)):
+        tr = RH.RefTrainer(CFG, dev, dropout=dropout, autocast=autocast)
+        ips, sps = RH.time_trainer(tr, batches, steps, warmup, on_device=True)
+        out[key] = {"images_per_s": ips, "ms_per_step": sps * 1e3}
+        tr2 = RH.RefTrainer(CFG, dev, dropout=dropout, autocast=autocast, optimizer=False)
+        ips2, sps2 = RH.time_trainer(tr2, batches, steps, warmup, on_device=True)
+        out[key]["fwd_bwd_no_optimizer"] = {"images_per_s": ips2, "ms_per_step": sps2 * 1e3}
+        del tr, tr2
+        torch.cuda.empty_cache()
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -324,6 +373,21 @@ def run_ours(args):
             e2e_step(s)
         ms_e2e = timed(e2e_step, args.steps)
     clocks = sampler.stop() if sampler else None
+    # ---- fwd + bwd without the optimizer step (SURVEY 8d reports both): a second graph over the same model ----
+    ms_nopt = None
+    if not args.eager and not args.no_e2e:
+        eng2 = GraphedTrainStep(model, None, B=B, H=cfg["H"], W=cfg["W"], Q=cfg["Q"], num_classes=cfg["C"], t_max=40,
+                                cost_class=0.5, cost_ciou=0.5, loss_weights=weights, world=world, device=dev)
+        eng2.load_batch(*resident[0])
+        eng2.capture(warmup=2)
+
+        def nopt_step(s):
+            eng2.load_batch(*resident[s % n_batches])
+            return eng2.step()
+        for s in range(3):
+            nopt_step(s)
+        ms_nopt = timed(nopt_step, args.steps)
+        eng2.gA = eng2.gB = None
     kernel_ms = time_dominant_kernels(cfg, B, dev, dropout=0.3 if args.dropout else 0.0) if rank == 0 else None
     kernel_ms0 = time_dominant_kernels(cfg, B, dev) if (rank == 0 and args.dropout) else kernel_ms
 
@@ -356,10 +420,19 @@ def run_ours(args):
                                              for k, f in (("destr_enc_attn_fwd", fwd_flops), ("destr_enc_attn_bwd", bwd_flops))}}}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            ips, spstep, cores = time_cpu_reference(1, 2, 1, 0.3 if args.dropout else 0.0)
-            cpu = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
-                   "sample": "2 steps of batch 1 through oracle/destr_oracle.py (fp32 eager torch, all host threads)"}
+            ips, spstep, cores, kind, b, _ = time_cpu_reference(2, 3, 1, 0.3 if args.dropout else 0.0, budget_s=30.0)
+            cpu = {"value": ips, "unit": "images/s", "cores": cores, "kind": kind,
+                   "sample": f"3 steps of batch {b} of the config-2 images ("
+                             + ("the reference's own modules from oracle/_ref" if kind == "reference" else "oracle/destr_oracle.py")
+                             + ", fp32 eager torch, all host threads)"}
+        ref_gpu = None
+        if world == 1 and not args.no_ref_gpu:
+            ref_gpu = time_reference_on_gpu(dev, args.dropout)
+            if ref_gpu is not None:
+                for key in ("fp32", "bf16"):
+                    ref_gpu[key]["our_speedup"] = (B * args.steps / (ms / 1e3)) / ref_gpu[key]["images_per_s"]
         imgs = B * world * args.steps
+        nodes = getattr(eng, "graph_kernel_nodes", None) if not args.eager else None
         line = {"metric": METRIC, "value": imgs / (ms / 1e3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -368,7 +441,14 @@ def run_ours(args):
                            "dropout": 0.3 if args.dropout else 0.0, "cuda_graphs": not args.eager, "l2": "4 rotating input batches; activations (~0.6 GB/step) exceed the 126 MB L2"},
                 "e2e": {"value": imgs / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": int(h2d_bytes),
                         "d2h_bytes_per_step": 4 + 4 * B, "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+                "gpu_launches": int(nodes if nodes else launches) * args.steps,
+                "gpu_launches_per_step": int(nodes if nodes else launches),
+                "gpu_launches_detail": {"graph_kernel_nodes_per_step": nodes, "own_kernels_per_step": int(launches),
+                                        "note": "graph_kernel_nodes = every kernel node of the captured step graph (ours + cuBLAS/NCCL/torch); own_kernels = launched through libdestr_b200.so"},
+                "fwd_bwd_no_optimizer": None if ms_nopt is None else {"value": imgs / (ms_nopt / 1e3), "unit": "images/s",
+                                                                      "ms_per_step": ms_nopt / args.steps},
+                "reference_gpu_eager": ref_gpu,
+                "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         # NCCL kernels are captured inside the CUDA graphs: release the graphs first, and leave without the
@@ -390,6 +470,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="no CUDA graphs (debug / comparison)")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the end-to-end leg")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-on-this-GPU eager comparator")
     ap.add_argument("--no-dropout", dest="dropout", action="store_false",
                     help="p = 0 at every dropout site (the parity configuration) instead of the reference's training "
                          "default p = 0.3; applies to both arms")

@@ -2,6 +2,10 @@
 #include "../../include/destr_b200.h"
 #include "common.cuh"
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 namespace destr {
 
 static thread_local std::string g_last_error;
@@ -47,6 +51,28 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_
     set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
     return 1;
   }
+  return 0;
+}
+
+// Opt-in to more than 48 KB of dynamic shared memory.  The attribute belongs to (kernel, device): a process-wide
+// "done" flag would leave a second GPU of the same process without it, so the cache is keyed by both.
+int ensure_dyn_smem(const void* kernel, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> granted;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    set_error("cudaGetDevice failed");
+    return 1;
+  }
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& have = granted[{kernel, dev}];
+  if (bytes <= 48 * 1024 || bytes <= have) return 0;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaFuncSetAttribute(MaxDynamicSharedMemorySize): ") + cudaGetErrorString(e));
+    return 1;
+  }
+  have = bytes;
   return 0;
 }
 

@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(128) attn_dropout_bits_kernel(const uint32_t* 
   const uint32_t seed = seed_ptr ? *seed_ptr : 0u;
   const int q = qb * 32 + lane;
   // the part of the hash that does not depend on the key pair
-  const uint32_t h0 = (seed ^ (site * 0x9E3779B1u)) ^ ((static_cast<uint32_t>(bh) * N + q) * 0x85EBCA77u);
+  const uint32_t h0 = drop_base(seed, site) ^ ((static_cast<uint32_t>(bh) * N + q) * 0x85EBCA77u);
   const size_t plane = static_cast<size_t>(blockIdx.z) * words * Np;
   const int kb_end = min(nW, (static_cast<int>(blockIdx.y) + 1) * kWordsPerWarp);
   for (int kb = blockIdx.y * kWordsPerWarp; kb < kb_end; ++kb) {

@@ -127,7 +127,11 @@ match_cost_kernel(const float* __restrict__ logits, const float* __restrict__ bo
   for (int t = lane; t < T; t += 32) {
     const float4 g = reinterpret_cast<const float4*>(tgt_boxes)[t0 + t];  // x0,y0,x1,y1
     // ---- focal class cost (matcher.py:87-93) ----
-    const float prob = 1.f / (1.f + expf(-lrow[tgt_ids[t0 + t]]));
+    // a label outside [0, C) is an IndexError in the reference (matcher.py:91 `[:, tgt_ids]`); here its cost is NaN, which
+    // the assignment kernel reports through its status flag (the matcher then raises, like scipy on NaN costs)
+    const int cls_id = tgt_ids[t0 + t];
+    const float lg = (cls_id >= 0 && cls_id < C) ? lrow[cls_id] : __int_as_float(0x7fc00000);
+    const float prob = 1.f / (1.f + expf(-lg));
     const float om = __fsub_rn(1.f, prob);
     const float neg = __fmul_rn(__fmul_rn(0.75f, __fmul_rn(prob, prob)), -logf(__fadd_rn(om, 1e-8f)));
     const float pos = __fmul_rn(__fmul_rn(0.25f, __fmul_rn(om, om)), -logf(__fadd_rn(prob, 1e-8f)));
@@ -178,6 +182,7 @@ using namespace destr;
 extern "C" int destr_pair_indices(const float* coords, int32_t* pairs, int B, int Q, void* stream) {
   DESTR_CHECK_ARG(coords && pairs && B > 0 && Q > 0 && Q <= 4096, "shape");
   dim3 grid(ceil_div(Q, 8), B);
+  DESTR_SMEM_OPTIN(pair_indices_kernel, (size_t)Q * 6 * sizeof(float));  // Q > 2048 needs more than the default 48 KB
   pair_indices_kernel<<<grid, 256, (size_t)Q * 6 * sizeof(float), (cudaStream_t)stream>>>(coords, pairs, Q);
   DESTR_LAUNCH_CHECK();
   return 0;

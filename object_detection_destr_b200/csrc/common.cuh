@@ -36,12 +36,20 @@ void set_error(const std::string& msg);  // api.cu
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swizzle);
 
+// opt-in to `bytes` of dynamic shared memory for `kernel` on the current device (cached per kernel AND device)
+int ensure_dyn_smem(const void* kernel, size_t bytes);
+#define DESTR_SMEM_OPTIN(kernel, bytes)                                             \
+  do {                                                                              \
+    int _rc = ::destr::ensure_dyn_smem(reinterpret_cast<const void*>(kernel), (bytes)); \
+    if (_rc) return _rc;                                                            \
+  } while (0)
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace destr
 
 // ------------------------------------------------------------------------------------------------------
-// Dropout masks: counter-based, no state.  keep(seed, site, row, col) comes from one 32-bit mix hash per PAIR of
+// Dropout masks: counter-based, no state.  keep(seed, site, row, col) comes from one 32-bit mix hash (of a pre-mixed (seed, site) base, the row and the column pair) per PAIR of
 // adjacent columns (even col -> low 16 bits, odd col -> high 16 bits); an element is KEPT when its 16 bits are
 // >= thr16 = round(p * 65536), and kept values are scaled by 65536 / (65536 - thr16).  `site` identifies the
 // dropout call (layer, position in the layer), `row`/`col` the element; forward and backward kernels recompute the
@@ -49,8 +57,19 @@ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 // ------------------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
 namespace destr {
+// (seed, site) -> avalanche-mixed base: consecutive seeds (the per-step counter) and neighbouring sites give unrelated
+// tables, not XOR re-indexings of one another.  Loop-invariant in every kernel (hoisted by the compiler).
+__device__ __forceinline__ uint32_t drop_base(uint32_t seed, uint32_t site) {
+  uint32_t h = seed * 0x9E3779B1u + site * 0x7F4A7C15u + 0x165667B1u;
+  h ^= h >> 16;
+  h *= 0x7FEB352Du;
+  h ^= h >> 15;
+  h *= 0x846CA68Bu;
+  h ^= h >> 16;
+  return h;
+}
 __device__ __forceinline__ uint32_t drop_bits(uint32_t seed, uint32_t site, uint32_t row, uint32_t col_pair) {
-  uint32_t h = seed ^ (site * 0x9E3779B1u);
+  uint32_t h = drop_base(seed, site);
   h ^= row * 0x85EBCA77u;
   h ^= col_pair * 0xC2B2AE3Du;
   h ^= h >> 16;

@@ -231,11 +231,7 @@ extern "C" int destr_split_cross_attn_bwd_ds(const void* q_obj, const void* q_po
   if ((rc = make_tmap_bf16_2d(&tv, v, krows, 256, ld_v, BT, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_tmap_bf16_2d(&tdo, dout, qrows, 512, 512, BT, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   const size_t smem = sizeof(Smem) + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
-    DESTR_CUDA(cudaFuncSetAttribute(cross_attn_bwd_ds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  DESTR_SMEM_OPTIN(cross_attn_bwd_ds_kernel, smem);
   cross_delta_kernel<<<ceil_div((int)qrows, 8), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(out),
                                                               static_cast<const __nv_bfloat16*>(dout), delta, B, Q);
   DESTR_LAUNCH_CHECK();

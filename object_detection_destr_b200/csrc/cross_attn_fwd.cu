@@ -257,11 +257,7 @@ extern "C" int destr_split_cross_attn_fwd(const void* q_obj, const void* q_pos, 
   if ((rc = make_tmap_bf16_2d(&tkp, k_pos, krows, 256, ld_kpos, BT, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_tmap_bf16_2d(&tv, v, krows, 256, ld_v, BT, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   const size_t smem = sizeof(Smem) + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
-    DESTR_CUDA(cudaFuncSetAttribute(cross_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  DESTR_SMEM_OPTIN(cross_attn_fwd_kernel, smem);
   float* ws_o = ws_partial;
   float* ws_ml = ws_partial + static_cast<size_t>(B) * 2 * nqt * nkv * BT * DV;
   dim3 grid(nkv, 2 * nqt, B);

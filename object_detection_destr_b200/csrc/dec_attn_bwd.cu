@@ -297,11 +297,7 @@ extern "C" int destr_dec_self_pair_attn_bwd_ds(const void* qkv, const void* cat,
   if ((rc = make_tmap_bf16_2d(&t[3], do1, rows * 8, 64, 64, BT, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_tmap_bf16_2d(&t[7], do2, rows * 8, 128, 128, BT, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   const size_t smem = sizeof(Smem) + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
-    DESTR_CUDA(cudaFuncSetAttribute(dec_attn_bwd_ds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  DESTR_SMEM_OPTIN(dec_attn_bwd_ds_kernel, smem);
   const int Qp = ceil_div(Q, BT) * BT;
   Params p{lse1, lse2, delta1, delta2, static_cast<__nv_bfloat16*>(P1), static_cast<__nv_bfloat16*>(dS1),
            static_cast<__nv_bfloat16*>(P2), static_cast<__nv_bfloat16*>(dS2), Q, Qp,

@@ -305,11 +305,7 @@ extern "C" int destr_dec_self_pair_attn_fwd(const void* qkv, const void* cat, vo
       return rc;
   }
   const size_t smem = sizeof(Smem) + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
-    DESTR_CUDA(cudaFuncSetAttribute(dec_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  DESTR_SMEM_OPTIN(dec_attn_fwd_kernel, smem);
   Params p{static_cast<__nv_bfloat16*>(o1), static_cast<__nv_bfloat16*>(o2), lse1, lse2, Q,
            Drop{drop_seed, drop_thr16, drop_site}};
   dim3 grid(ceil_div(Q, BT), 16, B);

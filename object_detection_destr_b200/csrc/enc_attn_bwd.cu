@@ -470,12 +470,7 @@ extern "C" int destr_enc_attn_bwd(const void* q, const void* k, const void* v, i
                                      enc_attn_bwd_kernel<2, false>, enc_attn_bwd_kernel<3, false>,
                                      enc_attn_bwd_kernel<0, true>,  enc_attn_bwd_kernel<1, true>,
                                      enc_attn_bwd_kernel<2, true>,  enc_attn_bwd_kernel<3, true>};
-  static bool attr_done = false;
-  if (!attr_done) {
-    for (int i = 0; i < 8; ++i)
-      DESTR_CUDA(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  for (int i = 0; i < 8; ++i) DESTR_SMEM_OPTIN(kernels[i], smem);
   const bool main_only = g_knobs[14] != 0;  // bench: time the tcgen05 kernel alone (outputs are then meaningless)
   if (!main_only)
     attn_bwd_prep_kernel<<<ceil_div(B * Np, 8), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(out),

@@ -390,12 +390,7 @@ extern "C" int destr_enc_attn_fwd(const void* q, const void* k, const void* v, i
                                      enc_attn_fwd_kernel<2, false>, enc_attn_fwd_kernel<3, false>,
                                      enc_attn_fwd_kernel<0, true>,  enc_attn_fwd_kernel<1, true>,
                                      enc_attn_fwd_kernel<2, true>,  enc_attn_fwd_kernel<3, true>};
-  static bool attr_done = false;
-  if (!attr_done) {
-    for (int i = 0; i < 8; ++i)
-      DESTR_CUDA(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  for (int i = 0; i < 8; ++i) DESTR_SMEM_OPTIN(kernels[i], smem);
   const KernelT kernel = kernels[(g_knobs[9] & 3) + (drop_thr16 ? 4 : 0)];
   const int n_items = B * heads * ceil_div(N, BM);
   int grid = n_items < 2 * 148 ? n_items : 2 * 148;  // persistent: 2 CTAs per SM

@@ -210,11 +210,7 @@ extern "C" int destr_linear_bias_relu_dropout(const void* a, int lda, const void
   if ((rc = make_tmap_bf16_2d(&ta, a, M, K, lda, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_tmap_bf16_2d(&tw, w, N, K, K, BN, BK, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   const size_t smem = sizeof(Smem) + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
-    DESTR_CUDA(cudaFuncSetAttribute(gemm_bias_relu_drop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  DESTR_SMEM_OPTIN(gemm_bias_relu_drop_kernel, smem);
   const int mt = ceil_div(M, BM), nb = N / BN;
   int gs = 148 / nb;  // CTAs per n-block (each keeps that block's weights resident)
   if (gs < 1) gs = 1;

@@ -237,11 +237,7 @@ extern "C" int destr_lsap_blockdiag(const float* cost, const int32_t* tgt_offset
   const size_t block = static_cast<size_t>(Q) * max_targets * sizeof(float);
   const int cost_in_smem = smem + block <= 200 * 1024 ? 1 : 0;
   if (cost_in_smem) smem += block;
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    DESTR_CUDA(cudaFuncSetAttribute(lsap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  DESTR_SMEM_OPTIN(lsap_kernel, smem);
   lsap_kernel<<<B, 32, smem, static_cast<cudaStream_t>(stream)>>>(cost, tgt_offsets, Q, n_slots, M, cost_in_smem, pred_idx,
                                                                   tgt_idx, valid, status);
   DESTR_LAUNCH_CHECK();

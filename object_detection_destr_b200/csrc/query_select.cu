@@ -118,11 +118,7 @@ extern "C" int destr_select_queries(const float* scores, const uint8_t* mask, co
   DESTR_CHECK_ARG(B > 0 && N > 0 && C > 0 && D > 0 && D % 4 == 0 && k > 0 && k <= N, "shape (D % 4 == 0, 1 <= k <= N)");
   const size_t smem = (static_cast<size_t>(N) + 1) * 4 + static_cast<size_t>(k) * 8;
   DESTR_CHECK_ARG(smem <= 200 * 1024, "N too large for the shared-memory ranking");
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    DESTR_CUDA(cudaFuncSetAttribute(select_queries_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
+  DESTR_SMEM_OPTIN(select_queries_kernel, smem);
   cudaStream_t st = (cudaStream_t)stream;
   // key_ws: B*N keys followed by B counters of valid positions
   int32_t* valid_cnt = reinterpret_cast<int32_t*>(key_ws + static_cast<size_t>(B) * N);

@@ -23,6 +23,37 @@ def _params(module: nn.Module):
     return dict(module.named_parameters())
 
 
+class EncoderMHA(nn.MultiheadAttention):
+    """`EncoderBlock.self_attn` (encoder_block.py:57-63, called at :97-103) as a swap point of its own: the same
+    parameters and call signature as nn.MultiheadAttention, but forward runs the fused tcgen05 attention instead of
+    torch's math path.  Supports what the reference calls it with: seq-first (N, B, 256) inputs, query is key,
+    a boolean key_padding_mask, no attn_mask; the attention weights are not materialised (the reference discards
+    them) -> returns (out, None)."""
+
+    def forward(self, query, key, value, key_padding_mask=None, need_weights=True, attn_mask=None,
+                average_attn_weights=True, is_causal=False):
+        if attn_mask is not None or is_causal:
+            raise NotImplementedError("attn_mask is never used by the reference encoder (encoder_block.py:35-39)")
+        if self.embed_dim != 256 or self.num_heads != 8 or query.dim() != 3 or self.batch_first:
+            raise NotImplementedError("fused encoder attention: (N, B, 256) seq-first inputs, 8 heads x 32")
+        if not query.is_cuda:
+            raise RuntimeError("destr_b200 has no CPU path")
+        N, B, d = query.shape
+        tok = lambda t: t.transpose(0, 1).reshape(B * N, d).to(BF16)
+        W, bias = self.in_proj_weight, self.in_proj_bias
+        xq, xk, xv = tok(query), (tok(key) if key is not query else None), tok(value)
+        if xk is None:
+            qk = Fn.linear(xq, W[:2 * d], bias[:2 * d])
+        else:
+            qk = torch.cat([Fn.linear(xq, W[:d], bias[:d]), Fn.linear(xk, W[d:2 * d], bias[d:2 * d])], dim=-1)
+        v = Fn.linear(xv, W[2 * d:], bias[2 * d:])
+        bits = ops.pack_key_mask(key_padding_mask, B, N, device=query.device)
+        with drop_scope(self, query.device):
+            a = Fn.enc_attn(qk, v, bits, B, N, 8, drop=Fn._dr("e.attn", Fn._enc_site(0, "attn")))
+        o = Fn.linear(a, self.out_proj.weight, self.out_proj.bias)
+        return o.view(B, N, d).transpose(0, 1).to(query.dtype), None
+
+
 class EncoderBlock(nn.Module):
     """reference: encoder_block.py:47-112."""
 
@@ -31,8 +62,8 @@ class EncoderBlock(nn.Module):
         if hidden_dim != 256 or heads_num != 8:
             raise ValueError("the B200 encoder kernels are built for hidden_dim=256, 8 heads (d_head=32), "
                              "the only configuration the reference can run (encoder_block.py:17-22)")
-        self.self_attn = nn.MultiheadAttention(embed_dim=hidden_dim, num_heads=heads_num, dropout=0.3,
-                                               kdim=hidden_dim, vdim=hidden_dim)
+        self.self_attn = EncoderMHA(embed_dim=hidden_dim, num_heads=heads_num, dropout=0.3, kdim=hidden_dim,
+                                    vdim=hidden_dim)
         self.fc1 = nn.Linear(hidden_dim, 2048)
         self.fc2 = nn.Linear(2048, hidden_dim)
         self.dropout1 = nn.Dropout(0.3)
@@ -82,9 +113,21 @@ def _block_only(x, pos, bits, p, lp, B, N):
     return Fn.add_layernorm(x1, f, p[lp + "norm2.weight"], p[lp + "norm2.bias"], Fn._dr("e.d3", S(0, "d3")))
 
 
-def _check_dropout(module: nn.Module):
-    """(kept for callers that predate in-kernel dropout: nothing to refuse any more)"""
-    return None
+_SEED_STREAMS = 0
+
+
+def initial_dropout_seed() -> int:
+    """Start value of a dropout seed counter: derived from torch's generator seed (so `torch.manual_seed` controls
+    it, as it controls the reference's nn.Dropout), the data-parallel rank (independent masks per worker) and a
+    per-process stream number (separately constructed modules do not replay each other's masks)."""
+    global _SEED_STREAMS
+    _SEED_STREAMS += 1
+    import os
+    rank = int(os.environ.get("RANK", "0"))
+    x = (torch.initial_seed() * 0x9E3779B97F4A7C15 + rank * 0xD1B54A32D192ED03 + _SEED_STREAMS * 0x94D049BB133111EB)
+    x &= (1 << 64) - 1
+    x ^= x >> 31
+    return int(x & 0x3FFFFFFF)
 
 
 def drop_scope(module: nn.Module, device, seed: Optional[torch.Tensor] = None):
@@ -112,7 +155,7 @@ def drop_scope(module: nn.Module, device, seed: Optional[torch.Tensor] = None):
     if seed is None:
         seed = getattr(module, "_drop_seed_t", None)
         if seed is None or seed.device != torch.device(device):
-            seed = torch.zeros(1, dtype=torch.int32, device=device)
+            seed = torch.full((1,), initial_dropout_seed(), dtype=torch.int32, device=device)
             object.__setattr__(module, "_drop_seed_t", seed)
         if any(thr.values()) and not getattr(module, "_drop_seed_pinned", False):
             seed.add_(1)

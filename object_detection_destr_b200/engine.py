@@ -56,12 +56,36 @@ def set_loss_static(logits, boxes, tl, tb, pi, ti, valid, num_classes: int):
     return {"class": loss_cls, "bbox": (l1 * has).sum() / denom, "ciou": (ciou * has).sum() / denom}
 
 
+def _count_kernel_nodes(graphs) -> Optional[int]:
+    """Kernel nodes of captured CUDA graphs (cudaGraphGetNodes on the raw cudaGraph_t): the number of GPU kernels one
+    replay launches, library kernels included.  None when the raw graph is not reachable."""
+    try:
+        from cuda.bindings import runtime as rt
+        total = 0
+        for g in graphs:
+            raw = rt.cudaGraph_t(int(g.raw_cuda_graph()))
+            err, _, n = rt.cudaGraphGetNodes(raw, 0)
+            if int(err) != 0:
+                return None
+            err, nodes, n = rt.cudaGraphGetNodes(raw, n)
+            if int(err) != 0:
+                return None
+            for nd in nodes[:n]:
+                err, ty = rt.cudaGraphNodeGetType(nd)
+                if int(err) == 0 and ty == rt.cudaGraphNodeType.cudaGraphNodeTypeKernel:
+                    total += 1
+        return total
+    except Exception:
+        return None
+
+
 class GraphedTrainStep:
     """One training step of the hot path as two CUDA graphs (see module docstring)."""
 
     def __init__(self, model, optimizer, *, B: int, H: int, W: int, Q: int, num_classes: int, t_max: int = 40,
                  cost_class: float = 0.5, cost_ciou: float = 0.5, loss_weights: Optional[Dict[str, float]] = None,
                  world: int = 1, device=None, fused_loss: bool = True, gpu_lsa: bool = True):
+        """optimizer=None: the step ends after backward (+ gradient exchange) -- the "fwd+bwd" figure of SURVEY 8(d)."""
         self.model, self.opt = model, optimizer
         self.B, self.Q, self.C, self.t_max, self.world = B, Q, num_classes, t_max, world
         self.wc, self.wi = cost_class, cost_ciou
@@ -99,7 +123,9 @@ class GraphedTrainStep:
         self.out = None
         self.sizes: List[int] = []
         self.launches_per_step = 0
+        self.graph_kernel_nodes = None  # kernel nodes of the captured graph(s): every GPU kernel of a step, ours and libraries'
         self._slots = None
+        self._loaded = None  # event: the H2D copies of the last load_batch() have left the pinned staging arrays
 
     # ---- pieces (also run eagerly during warm-up) ----
     def _forward(self):
@@ -131,6 +157,8 @@ class GraphedTrainStep:
             from .dataparallel import allreduce_mean_, grads_of
             flat, loose = grads_of(self.model)
             allreduce_mean_(flat, loose, world=self.world)
+        if self.opt is None:
+            return loss
         self.opt.step()
         if hasattr(self.model, "after_optimizer_step") and not getattr(self.opt, "refreshes_shadows", False):
             self.model.after_optimizer_step()
@@ -160,6 +188,9 @@ class GraphedTrainStep:
         B, tm = self.B, self.t_max
         sizes = [int(l.numel()) for l in labels]
         assert max(sizes) <= tm, "raise t_max"
+        for l in labels:  # the reference raises (IndexError / one_hot) on a label outside [0, C): so do we, on the host
+            if l.numel() and (int(l.min()) < 0 or int(l.max()) >= self.C):
+                raise IndexError(f"target label out of range [0, {self.C}): min {int(l.min())}, max {int(l.max())}")
         hi, hf = h_tgt_i.numpy(), h_tgt_f.numpy().reshape(-1, 4)
         tl, tb = h_tl.numpy(), h_tb.numpy()
         tl.fill(1)
@@ -185,11 +216,18 @@ class GraphedTrainStep:
         """Copy one batch into the static buffers.  feats/mask/sel/centers may be host (pinned) or device
         tensors; labels/boxes are per-image HOST tensors (int64 [T_i], fp32 [T_i,4] xyxy), T_i <= t_max."""
         B, tm = self.B, self.t_max
+        if self._loaded is not None:
+            # the previous call's non-blocking copies read the SAME pinned arrays: they must have executed before the
+            # host rewrites them (a caller looping load_batch()+step() without reading the loss runs ahead of the GPU)
+            self._loaded.synchronize()
         self.sizes = self._pack_targets(labels, boxes, self.h_tgt_i, self.h_tgt_f, self.h_tl, self.h_tb)
         srcs = [feats, mask, sel, centers, self.h_tgt_i[:B * tm], self.h_tgt_i[B * tm:], self.h_tgt_f.view(-1, 4),
                 self.h_tl, self.h_tb]
         for dst, src in zip(self._statics(), srcs):
             dst.copy_(src, non_blocking=True)
+        if self._loaded is None:
+            self._loaded = torch.cuda.Event()
+        self._loaded.record()
 
     # ---- input pipelining: stage batch s+1 (host packing + H2D on a copy stream) while step s runs ----
     def prefetch(self, feats, mask, sel, centers, labels: Sequence[torch.Tensor], boxes: Sequence[torch.Tensor]):
@@ -235,7 +273,8 @@ class GraphedTrainStep:
         if not self.gpu_lsa:
             torch.cuda.current_stream().synchronize()
             self._assign()
-        self.opt.zero_grad(set_to_none=False)  # keep the (possibly graph-static) .grad tensors in place
+        if self.opt is not None:
+            self.opt.zero_grad(set_to_none=False)  # keep the (possibly graph-static) .grad tensors in place
         return self._backward(out)
 
     def capture(self, warmup: int = 3):
@@ -247,10 +286,11 @@ class GraphedTrainStep:
                 self.eager_step()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        self.opt.zero_grad(set_to_none=True)  # backward inside the capture allocates .grad from the graph pool
+        if self.opt is not None:
+            self.opt.zero_grad(set_to_none=True)  # backward inside the capture allocates .grad from the graph pool
         from . import _lib
         n0 = _lib.launch_count
-        self.gA = torch.cuda.CUDAGraph()
+        self.gA = torch.cuda.CUDAGraph(keep_graph=True)
         if self.gpu_lsa:  # one graph: forward, cost, assignment, loss, backward, optimizer
             with torch.cuda.graph(self.gA):
                 self.out = self._forward()
@@ -261,11 +301,15 @@ class GraphedTrainStep:
                 self.out = self._forward()
             torch.cuda.synchronize()
             self._assign()
-            self.gB = torch.cuda.CUDAGraph()
+            self.gB = torch.cuda.CUDAGraph(keep_graph=True)
             with torch.cuda.graph(self.gB, pool=self.gA.pool()):
                 self.loss = self._backward(self.out)
         torch.cuda.synchronize()
-        self.launches_per_step = _lib.launch_count - n0  # our kernels captured in the graph(s)
+        self.launches_per_step = _lib.launch_count - n0  # kernels launched by our C-ABI calls during the capture
+        self.graph_kernel_nodes = _count_kernel_nodes([g for g in (self.gA, self.gB) if g is not None])
+        for g in (self.gA, self.gB):
+            if g is not None:
+                g.instantiate()
 
     def step(self):
         """Replay one training step.  Returns the (device) loss tensor."""

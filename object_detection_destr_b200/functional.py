@@ -28,7 +28,11 @@ _CTX = None
 
 class dropout_ctx:
     def __init__(self, seed: Optional[Tensor], thr: Optional[Dict[str, int]]):
-        self.seed, self.thr = seed, thr or {}
+        self.thr = thr or {}
+        # every autograd Function of this forward keeps (seed tensor, thr, site) for its backward, and the kernels read
+        # the seed from DEVICE memory: it must be this forward's own copy -- the module's live counter advances on the
+        # next forward (gradient accumulation, a second view, an eval pass before backward ...)
+        self.seed = seed.clone() if (seed is not None and any(self.thr.values())) else seed
 
     def __enter__(self):
         global _CTX

@@ -340,7 +340,9 @@ class HotPathRuntime:
         self.heads_in_flat = bool(heads)
         self.bbox = bbox_embed
         self.enc_mod, self.dec_mod = encoder, decoder
-        self.seed = torch.zeros(1, dtype=torch.int32, device=device)  # dropout seed (device: graph replays see updates)
+        from .encoder import initial_dropout_seed
+        # dropout seed counter (on the device: graph replays see the updates); starts from torch's seed and the rank
+        self.seed = torch.full((1,), initial_dropout_seed(), dtype=torch.int32, device=device)
         self.Le, self.Ld = self.P.Le, self.P.Ld
         self.saved = None
         self._bbox_cache = None

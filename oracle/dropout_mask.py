@@ -19,11 +19,22 @@ def _mul(a, c):
     return (a.astype(np.uint64) * np.uint64(c)) & M32
 
 
+def _base(seed: int, site: int) -> np.uint64:
+    """drop_base(seed, site) of common.cuh: the avalanche-mixed per-(step, call) base of the hash."""
+    h = (int(seed & 0xFFFFFFFF) * 0x9E3779B1 + int(site) * 0x7F4A7C15 + 0x165667B1) & 0xFFFFFFFF
+    h ^= h >> 16
+    h = (h * 0x7FEB352D) & 0xFFFFFFFF
+    h ^= h >> 15
+    h = (h * 0x846CA68B) & 0xFFFFFFFF
+    h ^= h >> 16
+    return np.uint64(h)
+
+
 def keep_mask(seed: int, site: int, rows, cols, thr16: int) -> np.ndarray:
     """rows: int array [R] (global row ids), cols: int array [C] -> bool [R, C] (True = kept)."""
     rows = np.asarray(rows, dtype=np.uint64)[:, None]
     cols = np.asarray(cols, dtype=np.uint64)[None, :]
-    h = np.uint64(seed & 0xFFFFFFFF) ^ ((np.uint64(site) * np.uint64(0x9E3779B1)) & M32)
+    h = _base(seed, site)
     h = h ^ _mul(rows, 0x85EBCA77)
     h = h ^ _mul(cols >> np.uint64(1), 0xC2B2AE3D)
     h = h ^ (h >> np.uint64(16))

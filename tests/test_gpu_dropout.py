@@ -238,3 +238,35 @@ def test_standalone_modules_apply_the_reference_dropout():
         assert not torch.equal(sa(q, k, v), sa(q, k, v))          # stochastic even in eval
         sa._dropout_prob = 0.0
         assert torch.equal(sa(q, k, v), sa(q, k, v))
+
+
+def test_two_forwards_then_backward_uses_each_forwards_own_masks():
+    """the module-level autograd path used to keep a reference to the module's LIVE seed counter, so a
+    second forward before backward (gradient accumulation, two views per step) made the first forward's backward
+    recompute different masks.  Each forward now snapshots its seed: backward of forward #1 after forward #2 equals
+    backward of forward #1 alone."""
+    from object_detection_destr_b200.encoder import EncoderBlock, set_dropout_seed
+    g = torch.Generator().manual_seed(6)
+    blk = EncoderBlock().cuda().train()
+    x = torch.randn(200, 2, 256, generator=g).cuda()
+    pos = torch.randn(200, 2, 256, generator=g).cuda()
+    dy = torch.randn(200, 2, 256, generator=g).cuda()
+
+    def grads(second_forward: bool):
+        set_dropout_seed(blk, 100)
+        set_dropout_seed(blk, None)       # released at a known value: every forward advances the counter
+        blk._drop_seed_t.fill_(100)
+        blk.zero_grad()
+        y1 = blk(x, pos_embed=pos)
+        if second_forward:
+            with torch.no_grad():
+                blk(x * 0.5, pos_embed=pos)    # moves the module's seed before y1's backward runs
+        y1.backward(dy)
+        return y1.detach().clone(), {k: v.grad.clone() for k, v in blk.named_parameters() if v.grad is not None}
+
+    ya, ga = grads(False)
+    yb, gb = grads(True)
+    assert torch.equal(ya, yb)
+    assert len(ga) >= 12
+    for k in ga:
+        assert torch.equal(ga[k], gb[k]), k

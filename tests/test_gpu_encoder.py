@@ -93,3 +93,29 @@ def test_encoder_c2_shape_fwd_bwd():
         worst = max(worst, ours)
     # dead parameters get no gradient, as in the reference
     assert dict(enc.named_parameters())["_encoder.0._proj_to_q.weight"].grad is None
+
+
+def test_encoder_mha_swap_point_matches_torch_mha():
+    """`EncoderBlock.self_attn` used directly (SURVEY 8b lists it as a swap point): same parameters and call
+    signature as nn.MultiheadAttention, result within bf16 tolerance of torch's own fp32 math path."""
+    from object_detection_destr_b200.encoder import EncoderMHA
+    from parity_log import record
+    g = torch.Generator().manual_seed(8)
+    N, B = 333, 3
+    ours = EncoderMHA(embed_dim=256, num_heads=8, dropout=0.3, kdim=256, vdim=256).cuda().eval()
+    stock = torch.nn.MultiheadAttention(embed_dim=256, num_heads=8, dropout=0.3, kdim=256, vdim=256).cuda().eval()
+    stock.load_state_dict(ours.state_dict(), strict=True)
+    x = torch.randn(N, B, 256, generator=g).cuda()
+    pos = torch.randn(N, B, 256, generator=g).cuda()
+    kpm = torch.zeros(B, N, dtype=torch.bool)
+    kpm[1, 300:] = True
+    kpm[2, 17:40] = True
+    with torch.no_grad():
+        xq = x + pos
+        got, w = ours(query=xq, key=xq, value=x, attn_mask=None, key_padding_mask=kpm.cuda())      # query is key
+        got2, _ = ours(query=xq, key=xq.clone(), value=x, attn_mask=None, key_padding_mask=kpm.cuda())
+        ref, _ = stock(query=xq, key=xq, value=x, attn_mask=None, key_padding_mask=kpm.cuda())
+    assert w is None and got.shape == ref.shape and torch.equal(got, got2)
+    err = float((got - ref).abs().max() / ref.abs().max())
+    record("EncoderMHA_vs_torch_MultiheadAttention_N333_B3", "out.max_err_over_absmax", err, 2e-2)
+    assert err <= 2e-2

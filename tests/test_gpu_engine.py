@@ -121,3 +121,49 @@ def test_prefetched_steps_equal_plain_steps():
         eng.prefetch(*pinned[(s + 1) % 4])
         piped.append(float(loss_t))
     assert piped == plain, (piped, plain)
+
+
+def test_load_batch_step_back_to_back_without_host_sync():
+    """load_batch() re-packs targets into ONE set of pinned arrays and enqueues non-blocking copies; a
+    caller looping load_batch()+step() without reading anything back must not overwrite them before the previous
+    step's copies ran.  Losses of an un-synchronised loop == losses of the same loop with a sync after every step."""
+    import bench
+    from object_detection_destr_b200.encoder import disable_dropout
+    from object_detection_destr_b200.engine import GraphedTrainStep
+    from object_detection_destr_b200.hotpath import TransformerHalf
+    cfg = dict(bench.CFG, B=2, L=1, H=10, W=14, Q=60)
+    torch.manual_seed(0)
+    model = TransformerHalf(Namespace(hidden_dim=256, num_encoder_blocks=1, num_decoder_blocks=1, num_cls=cfg["C"]))
+    disable_dropout(model).cuda().train()
+    opt = model.make_optimizer(lr=0.0)   # lr 0: every pass sees the same weights
+    eng = GraphedTrainStep(model, opt, B=2, H=10, W=14, Q=60, num_classes=cfg["C"], t_max=40)
+    batches = [bench.make_batch(0, s, 2, cfg, padded=True) for s in range(12)]
+    dev_batches = [tuple(t.cuda() for t in bt[:4]) + (bt[4], bt[5]) for bt in batches]
+    eng.load_batch(*dev_batches[0])
+    eng.capture(warmup=2)
+    assert eng.graph_kernel_nodes is None or eng.graph_kernel_nodes >= eng.launches_per_step
+
+    def run(sync: bool):
+        out = []
+        for bt in dev_batches:
+            eng.load_batch(*bt)
+            out.append(eng.step().clone())   # device-side copy of the loss, no host read
+            if sync:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        return [float(t) for t in out]
+
+    assert run(False) == run(True)
+
+
+def test_out_of_range_label_raises_like_the_reference():
+    import bench
+    from object_detection_destr_b200.engine import GraphedTrainStep
+    from object_detection_destr_b200.hotpath import TransformerHalf
+    cfg = dict(bench.CFG, B=2, L=1, H=10, W=14, Q=60)
+    model = TransformerHalf(Namespace(hidden_dim=256, num_encoder_blocks=1, num_decoder_blocks=1, num_cls=cfg["C"])).cuda()
+    eng = GraphedTrainStep(model, None, B=2, H=10, W=14, Q=60, num_classes=cfg["C"], t_max=40)
+    f, m, s, c, labels, boxes = bench.make_batch(0, 0, 2, cfg)
+    labels[1][0] = cfg["C"]   # one past the last class
+    with pytest.raises(IndexError):
+        eng.load_batch(f, m, s, c, labels, boxes)

@@ -1,5 +1,6 @@
 """-m gpu: the fused set-loss kernel (csrc/set_loss.cu) vs (a) the CPU oracle's SetCriterion restatement
-(loss values) and (b) torch autograd of the batched restatement on the same device (gradients).
+(loss values AND, through the oracle's own autograd, gradients) and (b) torch autograd of the batched restatement on the
+same device (gradients).
 fp32 throughout; tolerance 2e-5 relative to the largest entry (different summation order only)."""
 import pytest
 import torch
@@ -59,6 +60,16 @@ def test_fused_set_loss_matches_oracle_and_autograd(B, Q, C, seed, empty, clampy
     for got, exp, name in ((lg.grad, lg2.grad, "dlogits"), (bx.grad, bx2.grad, "dboxes")):
         tol = 2e-5 * float(exp.abs().max()) + 1e-9
         assert float((got - exp).abs().max()) <= tol, (name, float((got - exp).abs().max()), float(exp.abs().max()))
+    # gradients vs the ORACLE's autograd (CPU fp32, per-image loop exactly as criterion.py:57-79)
+    lo, bo = logits.clone().requires_grad_(), boxes.clone().requires_grad_()
+    ro = O.set_criterion(lo, bo, labels, tboxes, idx, C)
+    (w[0] * ro["class"] + w[1] * ro["bbox"] + w[2] * ro["ciou"]).sum().backward()
+    from parity_log import record
+    for got, exp, name in ((lg.grad, lo.grad, "dlogits"), (bx.grad, bo.grad, "dboxes")):
+        err = float((got.cpu() - exp).abs().max())
+        tol = 2e-5 * float(exp.abs().max()) + 1e-9
+        record(f"set_loss_B{B}_Q{Q}_C{C}", name + ".max_abs_vs_oracle_autograd", err, tol)
+        assert err <= tol, (name, err, float(exp.abs().max()))
     # upstream gradient scaling
     lg3, bx3 = logits.cuda().requires_grad_(), boxes.cuda().requires_grad_()
     t3, _ = ops.set_loss(lg3, bx3, tl, tb, pi, ti, valid, w)

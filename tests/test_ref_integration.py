@@ -1,0 +1,154 @@
+"""The reference's OWN model class with this repo's builders swapped in, against the
+unswapped reference.
+
+`oracle/_ref/` is the unmodified reference staged by oracle/stage_ref.py (git-ignored, travels to the GPU box).
+  * CPU (-m "not gpu"): the staged copy is intact, the harness's transformer half equals the oracle restatement on
+    the same weights (so the `--impl reference` arm of bench.py and the oracle are the same function), the 91-class
+    criterion shim equals the oracle's `set_criterion`.
+  * GPU (-m gpu): `ObjDetSplitTransformer` (src/model/model.py:14-133) built twice by the reference's `build_model`
+    -- once stock, once with `build_encoder` / `build_decoder` replaced by ours -- same state_dict, same image batch;
+    backbone and mini-detector are the reference's in both.  Discrete decisions are injected from the stock run
+    (top-k query indices, pair indices: SURVEY 7.3-3) so the comparison measures arithmetic, not arg-max flips.
+"""
+import os
+import sys
+from argparse import Namespace
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+from oracle import destr_oracle as O  # noqa: E402
+from oracle import ref_harness as RH  # noqa: E402
+from oracle import stage_ref  # noqa: E402
+
+if not RH.available() and os.path.isdir("/root/reference/src"):
+    stage_ref.stage()
+needs_ref = pytest.mark.skipif(not RH.available(), reason="oracle/_ref not staged (python oracle/stage_ref.py)")
+
+
+@needs_ref
+def test_staged_reference_is_intact():
+    assert stage_ref.verify()
+
+
+@needs_ref
+def test_harness_equals_oracle_on_cpu():
+    """RefTransformerHalf (the reference's modules) == oracle restatement, fp32 CPU, dropout neutralised."""
+    Lh, B, H, W, Q, C = 2, 2, 6, 9, 12, 7
+    g = torch.Generator().manual_seed(3)
+    m = RH.RefTransformerHalf(Namespace(hidden_dim=256, num_encoder_blocks=Lh, num_decoder_blocks=Lh, num_cls=C))
+    enc_sd, dec_sd = O.make_encoder_weights(Lh, seed=5), O.make_decoder_weights(Lh, seed=6)
+    cls_sd, bbox_sd = O.make_head_weights(C, seed=7)
+    m._encoder.load_state_dict(enc_sd)
+    m._decoder.load_state_dict(dec_sd)
+    m._cls_embed.load_state_dict(cls_sd)
+    m._bbox_embed.load_state_dict(bbox_sd)
+    RH.neutralise_dropout(m)
+    feats = torch.randn(B, 256, H, W, generator=g)
+    mask = torch.zeros(B, H, W, dtype=torch.bool)
+    mask[1, :, 6:] = True
+    sel = torch.randn(B, Q, 512, generator=g)
+    centers = 0.05 + 0.9 * torch.rand(B, Q, 2, generator=g)
+    with torch.no_grad():
+        out, enc = m(feats, mask, sel, centers)
+        pos = O.sine_pos2d(mask)
+        e = O.encoder_forward(feats, mask, pos, enc_sd, Lh)
+        fine = O.fine_pos_tokens(e, pos, enc_sd)
+        d = O.decoder_forward(sel, e.flatten(2).transpose(1, 2), mask.flatten(1), fine, O.query_sine_embed(centers, 256),
+                              centers, dec_sd, bbox_sd, Lh)
+        ref = O.heads_forward(d, centers, cls_sd, bbox_sd)
+    assert torch.allclose(enc, e, atol=1e-5)
+    assert torch.allclose(out["pred_class"], ref["pred_class"], atol=2e-5)
+    assert torch.allclose(out["pred_boxes"], ref["pred_boxes"], atol=1e-5)
+
+
+@needs_ref
+def test_criterion_shim_equals_oracle():
+    B, Q, C = 3, 20, 91
+    g = torch.Generator().manual_seed(1)
+    logits = torch.randn(B, Q, C, generator=g)
+    boxes = torch.cat([0.1 + 0.8 * torch.rand(B, Q, 2, generator=g), 0.03 + 0.4 * torch.rand(B, Q, 2, generator=g)], -1)
+    labels, tboxes = O.make_targets(B, seed=4, max_t=15, num_cls=C)
+    crit = RH.make_criterion(C)
+    got = crit({"pred_class": logits, "pred_boxes": boxes}, [{"labels": l, "boxes": b} for l, b in zip(labels, tboxes)])
+    idx = O.hungarian_match(O.match_cost_blocks(logits, boxes, labels, tboxes, 0.5, 0.0, 0.5, with_l1=False))
+    ref = O.set_criterion(logits, boxes, labels, tboxes, idx, C)
+    for k in ("class", "bbox", "ciou"):
+        assert abs(float(got[k]) - float(ref[k])) < 1e-6, k
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_reference_model_with_swapped_builders(monkeypatch):
+    import torchvision
+    from parity_log import record
+    RH.ref()
+    from src.model import model as ref_model
+    from src.model.attention import pair_self_attention as ref_pair
+    from object_detection_destr_b200 import ops
+    from object_detection_destr_b200.decoder import build_decoder
+    from object_detection_destr_b200.encoder import build_encoder, disable_dropout
+
+    # offline: random-init ResNet-50 instead of the pretrained download (backbone.py:139-143; SURVEY 8c gotcha 1)
+    orig_resnet = torchvision.models.resnet50
+    monkeypatch.setattr(torchvision.models, "resnet50", lambda **kw: orig_resnet(**{**kw, "weights": None}))
+    args = Namespace(hidden_dim=256, num_encoder_blocks=2, num_decoder_blocks=2, top_k=40, num_cls=91, lr_backbone=1e-4,
+                     resume=False)
+    torch.manual_seed(0)
+    stock = ref_model.build_model(args)                       # the reference, untouched
+    monkeypatch.setattr(ref_model, "build_encoder", build_encoder)   # the two swapped imports
+    monkeypatch.setattr(ref_model, "build_decoder", build_decoder)
+    swapped = ref_model.build_model(args)
+    assert type(swapped._encoder).__module__.startswith("object_detection_destr_b200")
+    sd = stock.state_dict()
+    imgs = torch.rand(2, 3, 256, 352, generator=torch.Generator().manual_seed(1))
+    # a random-init ResNet without real batch statistics produces features of arbitrary scale: normalise the 1x1
+    # reduce_dim conv (model.py:59-64) so the transformer sees unit-scale inputs, as a trained backbone gives it
+    with torch.no_grad():
+        stock.eval()
+        f, _ = stock._backbone(ref_model.nested_tensor_from_tensor_list(imgs))
+        x = stock._reduce_dim(f[-1].tensors)
+        sd["_reduce_dim.weight"] = sd["_reduce_dim.weight"] / x.std()
+        sd["_reduce_dim.bias"] = sd["_reduce_dim.bias"] * 0
+    stock.load_state_dict(sd)
+    swapped.load_state_dict(sd, strict=True)                  # identical parameter names, dead parameters included
+    RH.neutralise_dropout(stock).cuda()
+    disable_dropout(swapped).eval().cuda()
+
+    rec = {"topk": None, "pairs": []}
+    orig_topk = stock._mini_detector.get_topk_index
+    orig_pairs = ref_pair._get_pairs
+
+    def rec_topk(*a, **kw):
+        rec["topk"] = orig_topk(*a, **kw)
+        return rec["topk"]
+
+    def rec_pairs(*a, **kw):
+        p = orig_pairs(*a, **kw)
+        rec["pairs"].append(p)
+        return p
+
+    stock._mini_detector.get_topk_index = rec_topk
+    monkeypatch.setattr(ref_pair, "_get_pairs", rec_pairs)
+    with torch.no_grad():
+        ref_out, ref_det = stock(imgs.cuda())
+    monkeypatch.setattr(ref_pair, "_get_pairs", orig_pairs)
+    assert rec["topk"] is not None and len(rec["pairs"]) == 2
+
+    replay = iter(rec["pairs"])
+    swapped._mini_detector.get_topk_index = lambda *a, **kw: rec["topk"]
+    monkeypatch.setattr(ops, "pair_indices", lambda coords: next(replay).to(torch.int32).contiguous())
+    with torch.no_grad():
+        out, det = swapped(imgs.cuda())
+
+    tag = "reference_ObjDetSplitTransformer_swapped_builders_2+2_N88_Q40"
+    for name, a, b, tol, relative in (("pred_class", out["pred_class"], ref_out["pred_class"], 3e-2, True),
+                                      ("pred_boxes", out["pred_boxes"], ref_out["pred_boxes"], 5e-3, False),
+                                      ("det.pred_class", det["pred_class"], ref_det["pred_class"], 3e-2, True),
+                                      ("det.pred_boxes", det["pred_boxes"], ref_det["pred_boxes"], 5e-3, False)):
+        scale = float(b.abs().max()) if relative else 1.0
+        err = float((a.float() - b.float()).abs().max()) / scale
+        record(tag, name + (".max_rel" if relative else ".max_abs"), err, tol, ref_absmax=float(b.abs().max()))
+        assert a.shape == b.shape and torch.isfinite(a).all()
+        assert err <= tol, (name, err)
