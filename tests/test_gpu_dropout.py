@@ -268,5 +268,6 @@ def test_two_forwards_then_backward_uses_each_forwards_own_masks():
     yb, gb = grads(True)
     assert torch.equal(ya, yb)
     assert len(ga) >= 12
-    for k in ga:
-        assert torch.equal(ga[k], gb[k]), k
+    for k in ga:   # (LayerNorm-affine / bias gradients are accumulated with atomics: equal up to summation order;
+        #            a different mask would change them by O(1))
+        assert float((ga[k] - gb[k]).abs().max()) <= 1e-3 * float(ga[k].abs().max()) + 1e-6, k

@@ -6,11 +6,14 @@ all sites, the oracle fed the very masks the kernels generate).
 Stated tolerances (asserted below, measured values are appended to profiles/r02_parity_errors.json):
   * the comparison injects the oracle's pair indices (arg-max decisions flip under ANY bf16 rounding,
     the reference's own autocast(bf16) run included), and separately asserts >= 95 % agreement of our own pairing;
-  * outputs are bf16 activations through 12 layers.  The yardstick is what stock torch makes of the SAME graph under
-    `torch.autocast(bfloat16)` on the same GPU: our error must stay within TOL_X of the tensor's absmax AND within
-    1.5x the yardstick's own error.  north_star's example figures (1e-2 rel, 1e-3 abs on boxes) are asserted as
-    MEAN absolute errors (BOX_MEAN, REL_MEAN); the max over 800 boxes x 4 / 72 800 logits is asserted against the
-    yardstick.
+  * logits: max |err| <= 1e-2 x absmax (north_star's "max rel err 1e-2"), measured 5.8e-3;
+  * boxes: MEAN abs error <= 1e-3 (north_star's figure; measured 2.2e-4) and MAX over the 3200 coordinates <= 2e-3
+    (measured 1.05e-3).  The yardstick for the max is what stock torch makes of the SAME graph under
+    `torch.autocast(bfloat16)` on the same GPU: 8.4e-4 -- twelve layers of bf16 activations cannot hold a 1e-3 max
+    whoever computes them, so the asserted max is 2e-3, about 2x the yardstick;
+  * every parameter gradient (270 tensors): rel-Frobenius error <= 6e-2, or 2.5x the autocast yardstick's own error
+    for the few deep-decoder tensors where bf16 rounding noise alone exceeds that (worst measured 7.7e-2);
+  * with dropout (p = 0.3 everywhere) rounding noise is amplified by 1/(1-p): the same tolerances / 0.7.
 """
 from argparse import Namespace
 
@@ -24,9 +27,9 @@ from parity_log import record
 pytestmark = pytest.mark.gpu
 
 L, B, H, W, Q, C = 6, 8, 25, 42, 100, 91
-REL_MAX = 3e-2     # max |err| / absmax(ref) of logits (12 bf16 layers; yardstick-bounded, see docstring)
-REL_MEAN = 1e-2    # mean |err| / absmax(ref): north_star's "max rel err 1e-2" as a mean
-BOX_MAX = 5e-3     # max abs error of box coordinates
+REL_MAX = 1e-2     # max |err| / absmax(ref) of logits: north_star's "max rel err 1e-2"
+REL_MEAN = 2e-3    # mean |err| / absmax(ref)
+BOX_MAX = 2e-3     # max abs error of box coordinates (autocast-bf16 yardstick on the same graph: 8.4e-4)
 BOX_MEAN = 1e-3    # north_star's 1e-3 abs, as the mean over all coordinates
 GRAD_REL = 6e-2    # rel-Frobenius error of a parameter gradient (or 2.5x the autocast yardstick)
 
@@ -88,7 +91,7 @@ def _check_outputs(tag, out, ref, yard=None):
         res[key] = (mx, mean, y_mx)
         assert torch.isfinite(out[key]).all()
         assert mean <= mean_tol, (key, mean)
-        assert mx <= mx_tol or (y_mx is not None and mx <= 1.5 * y_mx), (key, mx, y_mx)
+        assert mx <= mx_tol, (key, mx, y_mx)
     return res
 
 
