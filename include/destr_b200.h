@@ -278,6 +278,43 @@ int destr_linear_bias_relu_dropout(const void* a, int lda, const void* w, const 
                                    int M, int N, int K, int relu, const uint32_t* drop_seed, uint32_t drop_thr16,
                                    uint32_t drop_site, void* stream);
 
+/* ---------------- tcgen05 GEMM family with fused epilogues (csrc/gemm_tc.cu) ---------------- */
+
+/* C[M,N] = A[M,K] . op(B) with the tail of the surrounding layer in the epilogue -- replaces nn.Linear / its dX product
+ * plus the elementwise kernels around it (encoder_block.py:24-44, 88-112 and their autograd).
+ *   a bf16 [M,K] row-major, pitch lda.  b_kn = 0: b bf16 [N,K] row-major (nn.Linear weight; forward y = x W^T)
+ *                                       b_kn = 1: b bf16 [K,N] row-major (the same weight used for dX = dY W)
+ *   x    = act(acc + bias) [relu = 1], then the dropout mask of destr_dropout_inplace on the [M,N] output
+ *   out  = add + mul * x     (mul, add: bf16 [M,N] or NULL)       e.g. x + pos * pos_scale(x), dX + residual gradient
+ *   out2 = add2 + x          (out2 NULL: not written)             e.g. ds = dxq * pos (out) together with dx += dxq (out2)
+ *   N % 32 == 0, K % 8 == 0, every pitch a multiple of 8 elements; out may alias add (in-place accumulation). */
+int destr_gemm_bf16(const void* a, int lda, const void* b, int ldb, int b_kn, int M, int N, int K, const float* bias,
+                    int relu, const uint32_t* drop_seed, uint32_t drop_thr16, uint32_t drop_site, const void* mul,
+                    int ldmul, const void* add, int ldadd, void* out, int ldo, const void* add2, int ldadd2, void* out2,
+                    int ldo2, void* stream);
+
+/* Backward of `dropout(relu(fc1 x))` seen from fc2 (encoder_block.py:107-109): dpre = scale * (dy w) * (h > 0) with
+ * w bf16 [K,N] row-major (fc2.weight: [256, 2048]), h the saved (dropped) activation bf16 [M,N] whose zeros carry both
+ * the ReLU and the dropout mask, scale = 1/(1-p); dbias[n] += column sums of dpre (fc1.bias gradient; NULL to skip). */
+int destr_gemm_relu_bwd(const void* dy, int lddy, const void* w, int ldw, int M, int N, int K, const void* h, int ldh,
+                        float scale, void* dpre, int ldo, float* dbias, void* stream);
+
+/* Linear + dropout + residual + LayerNorm in one kernel, N = 256 (encoder_block.py:104-106 `norm1(x + dropout1(attn))`,
+ * :108-110 `norm2(x + dropout3(fc2 ..))` and, through res2, the encoder's shared `norm(x + blk(x))` of :40):
+ *   z = res + dropout(a w^T + bias);  y = LN(z; gamma, beta);  mean/rstd fp32 [M]
+ *   res2 != NULL:  y2 = LN(res2 + y; gamma2, beta2), mean2/rstd2
+ *   w bf16 [256,K]; z (bf16, may be NULL) is what destr_add_layernorm_bwd(a = z, b = NULL, drop) needs. */
+int destr_gemm_res_ln(const void* a, int lda, const void* w, int ldw, int M, int K, const float* bias,
+                      const uint32_t* drop_seed, uint32_t drop_thr16, uint32_t drop_site, const void* res, int ldres,
+                      const float* gamma, const float* beta, void* z, int ldz, void* y, int ldy, float* mean,
+                      float* rstd, const void* res2, int ldres2, const float* gamma2, const float* beta2, void* y2,
+                      int ldy2, float* mean2, float* rstd2, void* stream);
+
+/* Weight gradient dw[Nout,Kin] += dy[M,Nout]^T x[M,Kin] (fp32 accumulation INTO dw with red.global.add: zero it first),
+ * split over the M rows so small weight matrices still fill the GPU.  dy, x bf16 row-major; dw fp32, pitch lddw. */
+int destr_gemm_dw(const void* dy, int lddy, const void* x, int ldx, int M, int Nout, int Kin, float* dw, int lddw,
+                  void* stream);
+
 /* ---------------- mini-detector query selection ---------------- */
 
 /* MiniDetector.get_topk_index + the gathers of MiniDetector.forward (mini_detector.py:70-104, 142-170), two small launches:
@@ -315,13 +352,14 @@ int destr_heads_bwd(const void* dec, const float* hidden, const float* boxes, co
 /* torch.optim.AdamW arithmetic (decoupled weight decay, bias correction; amsgrad off) on flat fp32 buffers of
  * n elements (n % 4 == 0, 16-byte aligned), plus the refresh of the bf16 weight shadow the GEMMs read.
  * `step` points to a device float holding the 1-based step count of THIS update.
- * The first n_bf16 gradients (n_bf16 % 4 == 0; 0 = none) are read from `grad_bf16` instead of `grad` -- the weight-
- * matrix gradients as the dW GEMMs leave them -- and every gradient is multiplied by grad_scale (1/world for the
+ * The gradients of parameters [bf16_begin, n_bf16) (both % 4 == 0; n_bf16 = 0: none) are read from `grad_bf16` instead of
+ * `grad` -- weight-matrix gradients left in bf16 by library dW GEMMs or by a bf16 gradient exchange; destr_gemm_dw
+ * accumulates in fp32 straight into `grad` -- and every gradient is multiplied by grad_scale (1/world for the
  * data-parallel mean, else 1); the fp32 value actually used is written back to `grad`, so that buffer (the
  * parameters' .grad) is complete after the call. */
 int destr_flat_adamw(float* master, float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, int64_t n,
                      float lr, float beta1, float beta2, float eps, float weight_decay, const float* step,
-                     const void* grad_bf16, int64_t n_bf16, float grad_scale, void* stream);
+                     const void* grad_bf16, int64_t bf16_begin, int64_t n_bf16, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -55,10 +55,15 @@ SIGNATURES = {
     "destr_match_cost_blockdiag": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _f, _i, _p],
     "destr_lsap_blockdiag": [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p],
     "destr_linear_bias_relu_dropout": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _p, _u, _u, _p],
+    "destr_gemm_bf16": [_p, _i, _p, _i, _i, _i, _i, _i, _p, _i, _p, _u, _u, _p, _i, _p, _i, _p, _i, _p, _i, _p, _i, _p],
+    "destr_gemm_relu_bwd": [_p, _i, _p, _i, _i, _i, _i, _p, _i, _f, _p, _i, _p, _p],
+    "destr_gemm_res_ln": [_p, _i, _p, _i, _i, _i, _p, _p, _u, _u, _p, _i, _p, _p, _p, _i, _p, _i, _p, _p, _p, _i, _p, _p,
+                          _p, _i, _p, _p, _p],
+    "destr_gemm_dw": [_p, _i, _p, _i, _i, _i, _i, _p, _i, _p],
     "destr_select_queries": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p],
     "destr_heads_fwd": [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _p],
     "destr_heads_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p],
-    "destr_flat_adamw": [_p, _p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _p, _p, _i64, _f, _p],
+    "destr_flat_adamw": [_p, _p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _p, _p, _i64, _i64, _f, _p],
     "destr_set_loss_fwd_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _f, _p, _p, _p, _p, _p],
 }
 

@@ -5,7 +5,8 @@
 // torch.optim.AdamW, src/train/train.py:236-244):
 //   p *= 1 - lr*wd;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
 //   p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
-// The weight-matrix gradients are produced in bf16 by the dW GEMMs (first n_bf16 parameters): the kernel reads them
+// The weight-matrix gradients of parameters [bf16_begin, n_bf16) are bf16 (library dW GEMMs, or a bf16 gradient exchange;
+// the tcgen05 split-K dW kernel accumulates fp32 straight into `grad`): the kernel reads them
 // directly (times grad_scale = 1/world for the data-parallel mean) and writes the fp32 value back to `grad`, which
 // replaces a separate bf16 -> fp32 cast pass over the whole buffer (61 us of a 5 ms step).
 // HBM-bound: 14-16 B read + 14-18 B written per parameter; 128-bit accesses, grid = multiple of the SM count.
@@ -18,7 +19,8 @@ namespace {
 __global__ void __launch_bounds__(256)
 flat_adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                   __nv_bfloat16* __restrict__ shadow, int64_t n4, float lr, float b1, float b2, float eps, float wd,
-                  const float* __restrict__ step, const __nv_bfloat16* __restrict__ g16, int64_t n16_4, float gscale) {
+                  const float* __restrict__ step, const __nv_bfloat16* __restrict__ g16, int64_t lo16_4, int64_t n16_4,
+                  float gscale) {
   const float t = *step;
   const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
   const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2), decay = 1.f - lr * wd;
@@ -26,7 +28,7 @@ flat_adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restric
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     float4 pp = reinterpret_cast<float4*>(p)[i];
     float4 gg;
-    if (i < n16_4) {  // bf16 gradient of a weight matrix: widen, scale, and leave the fp32 value in .grad
+    if (i >= lo16_4 && i < n16_4) {  // bf16 gradient of a weight matrix: widen, scale, and leave the fp32 value in .grad
       const uint2 w = reinterpret_cast<const uint2*>(g16)[i];
       gg = make_float4(__uint_as_float(w.x << 16) * gscale, __uint_as_float(w.x & 0xffff0000u) * gscale,
                        __uint_as_float(w.y << 16) * gscale, __uint_as_float(w.y & 0xffff0000u) * gscale);
@@ -67,18 +69,19 @@ flat_adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restric
 
 extern "C" int destr_flat_adamw(float* master, float* grad, float* exp_avg, float* exp_avg_sq, void* shadow_bf16,
                                 int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
-                                const float* step, const void* grad_bf16, int64_t n_bf16, float grad_scale,
-                                void* stream) {
+                                const float* step, const void* grad_bf16, int64_t bf16_begin, int64_t n_bf16,
+                                float grad_scale, void* stream) {
   using namespace destr;
   DESTR_CHECK_ARG(master && grad && exp_avg && exp_avg_sq && shadow_bf16 && step, "null pointer");
   DESTR_CHECK_ARG(n > 0 && n % 4 == 0, "n must be a positive multiple of 4");
   DESTR_CHECK_ARG(n_bf16 >= 0 && n_bf16 <= n && n_bf16 % 4 == 0 && (n_bf16 == 0 || grad_bf16), "n_bf16 / grad_bf16");
+  DESTR_CHECK_ARG(bf16_begin >= 0 && bf16_begin % 4 == 0 && bf16_begin <= n_bf16, "bf16_begin");
   const int64_t n4 = n / 4;
   int64_t blocks = (n4 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   flat_adamw_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       master, grad, exp_avg, exp_avg_sq, static_cast<__nv_bfloat16*>(shadow_bf16), n4, lr, beta1, beta2, eps,
-      weight_decay, step, static_cast<const __nv_bfloat16*>(grad_bf16), n_bf16 / 4, grad_scale);
+      weight_decay, step, static_cast<const __nv_bfloat16*>(grad_bf16), bf16_begin / 4, n_bf16 / 4, grad_scale);
   DESTR_LAUNCH_CHECK();
   return 0;
 }

@@ -212,6 +212,95 @@ def linear_bias_relu_dropout(x: Tensor, w: Tensor, bias: Optional[Tensor], drop=
 
 
 # ----------------------------------------------------------------------------------------------
+# tcgen05 GEMM family with fused epilogues (csrc/gemm_tc.cu)
+# ----------------------------------------------------------------------------------------------
+def _mat(t: Optional[Tensor], name: str, rows: int, cols: int) -> Optional[Tensor]:
+    """bf16 [rows, cols] view with unit column stride and a row pitch that is a multiple of 8 elements."""
+    if t is None:
+        return None
+    _chk(t, BF16, name)
+    if t.dim() != 2 or t.shape[0] != rows or t.shape[1] != cols:
+        raise ValueError(f"{name}: expected [{rows}, {cols}], got {tuple(t.shape)}")
+    if t.stride(1) != 1 or t.stride(0) % 8 != 0 or t.data_ptr() % 16 != 0:
+        raise ValueError(f"{name}: needs unit column stride, a row pitch multiple of 8 and 16-byte alignment")
+    return t
+
+
+def gemm(a: Tensor, b: Tensor, *, b_kn: bool = False, bias: Optional[Tensor] = None, relu: bool = False, drop=None,
+         mul: Optional[Tensor] = None, add: Optional[Tensor] = None, out: Optional[Tensor] = None,
+         add2: Optional[Tensor] = None, out2=None):
+    """out = add + mul * dropout(act(a . op(b) + bias)) on tcgen05 tensor cores (destr_gemm_bf16).
+    a bf16 [M,K]; b bf16 [N,K] (b_kn=False: nn.Linear weight, forward) or [K,N] (b_kn=True: dX = dY W);
+    bias fp32 [N]; mul/add/add2 bf16 [M,N] views; out2=True (or a tensor) additionally returns add2 + x.
+    Returns out, or (out, out2)."""
+    M, K = a.shape
+    N = b.shape[1] if b_kn else b.shape[0]
+    a = _mat(a, "a", M, K)
+    b = _mat(b, "b", K if b_kn else N, N if b_kn else K)
+    if out is None:
+        out = torch.empty(M, N, dtype=BF16, device=a.device)
+    if out2 is True:
+        out2 = torch.empty(M, N, dtype=BF16, device=a.device)
+    for t, n in ((mul, "mul"), (add, "add"), (add2, "add2"), (out, "out"), (out2, "out2")):
+        _mat(t, n, M, N)
+    ld = lambda t: 0 if t is None else t.stride(0)
+    _lib.call("destr_gemm_bf16", a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), int(b_kn), M, N, K,
+              _ptr(None if bias is None else _chk(bias, torch.float32, "bias")), int(relu), *_dargs(drop), _ptr(mul), ld(mul),
+              _ptr(add), ld(add), out.data_ptr(), out.stride(0), _ptr(add2), ld(add2), _ptr(out2), ld(out2), _stream())
+    return out if out2 is None else (out, out2)
+
+
+def gemm_relu_bwd(dy: Tensor, w: Tensor, h: Tensor, scale: float, dbias: Optional[Tensor]) -> Tensor:
+    """dpre = scale * (dy @ w) * (h > 0), dbias += colsum(dpre): dy bf16 [M,K], w bf16 [K,N] (fc2.weight), h bf16 [M,N]."""
+    M, K = dy.shape
+    N = w.shape[1]
+    dy, w, h = _mat(dy, "dy", M, K), _mat(w, "w", K, N), _mat(h, "h", M, N)
+    dpre = torch.empty(M, N, dtype=BF16, device=dy.device)
+    _lib.call("destr_gemm_relu_bwd", dy.data_ptr(), dy.stride(0), w.data_ptr(), w.stride(0), M, N, K, h.data_ptr(),
+              h.stride(0), float(scale), dpre.data_ptr(), N, _ptr(dbias), _stream())
+    return dpre
+
+
+def gemm_res_ln(a: Tensor, w: Tensor, bias: Optional[Tensor], res: Tensor, gamma: Tensor, beta: Tensor, drop=None,
+                want_z: bool = True, res2: Optional[Tensor] = None, gamma2: Optional[Tensor] = None,
+                beta2: Optional[Tensor] = None, y2_out: Optional[Tensor] = None):
+    """z = res + dropout(a w^T + bias); y = LN(z); with res2: y2 = LN(res2 + y).  w bf16 [256,K].
+    Returns (y, z, mean, rstd) or (y, z, mean, rstd, y2, mean2, rstd2); z is None when want_z is False."""
+    M, K = a.shape
+    a, w, res = _mat(a, "a", M, K), _mat(w, "w", 256, K), _mat(res, "res", M, 256)
+    dev = a.device
+    y = torch.empty(M, 256, dtype=BF16, device=dev)
+    z = torch.empty(M, 256, dtype=BF16, device=dev) if want_z else None
+    mean, rstd = torch.empty(M, dtype=torch.float32, device=dev), torch.empty(M, dtype=torch.float32, device=dev)
+    y2 = mean2 = rstd2 = None
+    if res2 is not None:
+        res2 = _mat(res2, "res2", M, 256)
+        y2 = torch.empty(M, 256, dtype=BF16, device=dev) if y2_out is None else _mat(y2_out, "y2", M, 256)
+        mean2, rstd2 = torch.empty(M, dtype=torch.float32, device=dev), torch.empty(M, dtype=torch.float32, device=dev)
+    _lib.call("destr_gemm_res_ln", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, K,
+              _ptr(None if bias is None else _chk(bias, torch.float32, "bias")), *_dargs(drop), res.data_ptr(), res.stride(0),
+              _chk(gamma, torch.float32, "gamma").data_ptr(), _chk(beta, torch.float32, "beta").data_ptr(), _ptr(z), 256,
+              y.data_ptr(), 256, mean.data_ptr(), rstd.data_ptr(), _ptr(res2), 0 if res2 is None else res2.stride(0),
+              _ptr(gamma2), _ptr(beta2), _ptr(y2), 0 if y2 is None else y2.stride(0), _ptr(mean2), _ptr(rstd2), _stream())
+    if res2 is None:
+        return y, z, mean, rstd
+    return y, z, mean, rstd, y2, mean2, rstd2
+
+
+def gemm_dw(dy: Tensor, x: Tensor, dw: Tensor) -> Tensor:
+    """dw (fp32 [Nout,Kin] view, ACCUMULATED into) += dy^T x;  dy bf16 [M,Nout], x bf16 [M,Kin]."""
+    M, Nout = dy.shape
+    Kin = x.shape[1]
+    dy, x = _mat(dy, "dy", M, Nout), _mat(x, "x", M, Kin)
+    _chk(dw, torch.float32, "dw")
+    if tuple(dw.shape) != (Nout, Kin) or dw.stride(1) != 1:
+        raise ValueError(f"dw: expected fp32 [{Nout}, {Kin}] with unit column stride, got {tuple(dw.shape)}")
+    _lib.call("destr_gemm_dw", dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), M, Nout, Kin, dw.data_ptr(),
+              dw.stride(0), _stream())
+    return dw
+
+
+# ----------------------------------------------------------------------------------------------
 # encoder attention
 # ----------------------------------------------------------------------------------------------
 def attn_dropout_bits(drop, BH: int, N: int, device, want_row: bool = True, want_col: bool = True,
@@ -376,8 +465,6 @@ def split_cross_attn_fwd(q_obj: Tensor, q_pos: Tensor, k_enc: Tensor, k_pos: Ten
     return out, lse
 
 
-# Backward of the decoder attention ops: cuBLAS batched GEMMs + elementwise torch on the GPU
-# (see _composed_bwd.py for status; the fused tcgen05 backward exists for the encoder only so far).
 def dec_self_pair_attn_bwd(qkv: Tensor, cat: Tensor, do1: Tensor, do2: Tensor, lse1: Tensor, lse2: Tensor,
                            delta1: Tensor, delta2: Tensor, B: int, Q: int, drop=None):
     """Backward of dec_self_pair_attn_fwd.  All operands head-major: qkv [3,B,8,Q,64], cat [3,B,8,Q,128],

@@ -34,6 +34,12 @@ BF16 = torch.bfloat16
 _ALIGN = 64
 import os as _os
 _FUSED_FFN1 = _os.environ.get("DESTR_FUSED_FFN1", "1") == "1"
+# encoder projections / FFN / dX / dW on the tcgen05 GEMM family (csrc/gemm_tc.cu) instead of cuBLAS; "0" = library path
+_TC = _os.environ.get("DESTR_TC_GEMM", "1") == "1"
+# out-proj / fc2 with dropout + residual + LayerNorm(s) in the GEMM epilogue (needs _TC).  Parity-green, but OFF by
+# default: a CTA must own whole 256-wide rows, so at M = 8400 only 66 CTAs run and the 5-pass epilogue costs more than
+# the two row-wise kernels it replaces (measured in situ: 4.97 ms/step with it, 4.77 without)
+_TC_LN = _TC and _os.environ.get("DESTR_TC_LN", "0") == "1"
 _FORK = {k: _os.environ.get("DESTR_FORK_" + k, d) == "1" for k, d in (("ENC_V", "0"), ("DEC_HEAD", "1"), ("DSIN", "1"))}
 
 
@@ -144,6 +150,9 @@ class FlatParams:
         self._keep: List[Tensor] = []
         self._forked = set()
         self.defer_grad_cast = False  # set by FlatAdamW: its kernel reads the bf16 weight gradients itself
+        self.enc_w_end = self.off["d0.q_w"][0]  # W region = [encoder weights | decoder weights]
+        # first parameter whose gradient backward() leaves in bf16 (g16); below it the fp32 buffer is already final
+        self.bf16_begin = self.enc_w_end if _TC else 0
         self.g16_pending = False
         self.grad_scale = 1.0
 
@@ -172,6 +181,14 @@ class FlatParams:
     def begin_backward(self):
         self.g32[self.nW:self.heads_off].zero_()
         self._written.clear()
+        self._enc_reduced = self.enc_w_end
+        if _TC:
+            # the split-K dW kernel accumulates the encoder's weight gradients in fp32 (red.global.add) straight into
+            # the flat gradient buffer: zero that region, on the stream the dW kernels run on
+            if self.side is not None:
+                self.side.wait_stream(torch.cuda.current_stream())
+            with (torch.cuda.stream(self.side) if self.side is not None else contextlib.nullcontext()):
+                self.g32[:self.enc_w_end].zero_()
 
     # ---- data parallel: the one exchange of a training step, overlapped with backward ----
     def enable_data_parallel(self, world: int, group=None):
@@ -192,6 +209,23 @@ class FlatParams:
         with torch.cuda.stream(self.comm):
             dist.all_reduce(self.g16[self.dec_off:], group=self.group)
 
+    def reduce_encoder_layer(self, l: int):
+        """Data parallel: layer l's weight gradients are final once its backward (and its dW kernels on the side
+        stream) is done -> exchange them now, under the backward of layer l-1.  Only layer 0's bucket, the shared
+        position-scale MLP and the small fp32 block stay for end_backward()."""
+        if getattr(self, "world", 1) <= 1:
+            return
+        import torch.distributed as dist
+        a = self.off[f"e{l}.in_w"][0]
+        b = self.off[f"e{l + 1}.in_w"][0] if l + 1 < self.Le else self.off["e.ps0_w"][0]
+        self.comm.wait_stream(self.side)
+        self.comm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.comm):
+            if _TC:
+                self.g16[a:b].copy_(self.g32[a:b])  # fp32 accumulators -> the bf16 the exchange carries
+            dist.all_reduce(self.g16[a:b], group=self.group)
+        self._enc_reduced = min(getattr(self, "_enc_reduced", self.enc_w_end), a)
+
     def end_backward(self):
         if self.side is not None:
             torch.cuda.current_stream().wait_stream(self.side)
@@ -200,7 +234,16 @@ class FlatParams:
             import torch.distributed as dist
             self.comm.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.comm):
-                dist.all_reduce(self.g16[:self.dec_off], group=self.group)
+                # whatever the per-layer buckets did not cover: the shared position-scale MLP (and, without per-layer
+                # calls, the whole encoder) + the fp32 bias / LayerNorm / head block
+                done = getattr(self, "_enc_reduced", self.enc_w_end)
+                rest = [(0, self.enc_w_end)] if done >= self.enc_w_end else [(0, done), (self.off["e.ps0_w"][0], self.enc_w_end)]
+                for a, b in rest:
+                    if b > a:
+                        if _TC:
+                            self.g16[a:b].copy_(self.g32[a:b])
+                        dist.all_reduce(self.g16[a:b], group=self.group)
+                self._enc_reduced = self.enc_w_end
                 dist.all_reduce(self.g32[self.nW:], group=self.group)
             torch.cuda.current_stream().wait_stream(self.comm)
         # the weight gradients are still bf16 (g16) and, data-parallel, everything is a SUM over ranks: a FlatAdamW
@@ -219,12 +262,19 @@ class FlatParams:
         data-parallel 1/world.  (No-op when already done; FlatAdamW.step() does the same inside its kernel.)"""
         if not getattr(self, "g16_pending", False):
             return
+        b0 = self.g16_begin()
         if self.grad_scale != 1.0:
-            torch.mul(self.g16, self.grad_scale, out=self.g32[:self.nW])
+            torch.mul(self.g16[b0:], self.grad_scale, out=self.g32[b0:self.nW])
+            self.g32[:b0].mul_(self.grad_scale)
             self.g32[self.nW:].mul_(self.grad_scale)
         else:
-            self.g32[:self.nW].copy_(self.g16)
+            self.g32[b0:self.nW].copy_(self.g16[b0:])
         self.g16_pending = False
+
+    def g16_begin(self) -> int:
+        """First parameter whose final gradient is in the bf16 buffer after backward(): the decoder's (library dW GEMMs);
+        data-parallel, the encoder's too (they travel as bf16)."""
+        return 0 if getattr(self, "world", 1) > 1 else self.bf16_begin
 
     @contextlib.contextmanager
     def fork(self, enable: bool = True, k: int = 0):
@@ -254,6 +304,11 @@ class FlatParams:
 
     def acc_gw(self, name: str, dy: Tensor, x: Tensor, rows: Optional[int] = None, sl: Optional[slice] = None):
         """weight gradient dW (+)= dy^T x into the bf16 gradient buffer (first write overwrites)."""
+        if _TC and self.off[name][0] < self.enc_w_end:  # encoder weight: tcgen05 split-K kernel, fp32 accumulation
+            gv = self._v(self.g32, name, rows)
+            if sl is not None:
+                gv = gv[sl]
+            return self.off_path(lambda: ops.gemm_dw(dy, x, gv), dy, x)
         gv = self.gw(name, rows)
         key = name
         if sl is not None:
@@ -306,8 +361,8 @@ class FlatAdamW:
         _lib.call("destr_flat_adamw", P.m32.data_ptr(), P.g32.data_ptr(), self.exp_avg.data_ptr(),
                   self.exp_avg_sq.data_ptr(), P.s16.data_ptr(), n, float(self.lr), float(self.betas[0]),
                   float(self.betas[1]), float(self.eps), float(self.wd), self.t.data_ptr(),
-                  P.g16.data_ptr() if pend else None, P.nW if pend else 0, float(P.grad_scale) if pend else 1.0,
-                  ops._stream())
+                  P.g16.data_ptr() if pend else None, P.g16_begin() if pend else 0, P.nW if pend else 0,
+                  float(P.grad_scale) if pend else 1.0, ops._stream())
         P.g16_pending = False
         if self.extra is not None:
             self.extra.step()
@@ -407,14 +462,22 @@ class HotPathRuntime:
     def _enc_fwd(self, l: int, x: Tensor, pos: Tensor, bits: Tensor, B: int, N: int):
         P = self.P
         Win, b_in = P.w(f"e{l}.in_w"), P.w(f"e{l}.in_b")
-        with P.fork(_FORK["ENC_V"], k=0):  # the value projection does not depend on the position-scale chain
-            v = _mm_bias(x, Win[512:], b_in[512:])
-        h1 = _mm_bias_relu(x, P.w("e.ps0_w"), P.w("e.ps0_b"))
-        s = _mm_bias(h1, P.w("e.ps2_w"), P.w("e.ps2_b"))
-        xq = ops.pos_mul_add(x, pos, s)
-        qk = _mm_bias(xq, Win[:512], b_in[:512])
-        P.join(0)
         dc = self.dc
+        if _TC:  # tcgen05 GEMM family: biases are read in fp32, the position-scale add lives in a GEMM epilogue
+            bf = P.f(f"e{l}.in_b")
+            with P.fork(_FORK["ENC_V"], k=0):
+                v = ops.gemm(x, Win[512:], bias=bf[512:])
+            h1 = ops.gemm(x, P.w("e.ps0_w"), bias=P.f("e.ps0_b"), relu=True)
+            xq = ops.gemm(h1, P.w("e.ps2_w"), bias=P.f("e.ps2_b"), mul=pos, add=x)     # x + pos * pos_scale(x)
+            qk = ops.gemm(xq, Win[:512], bias=bf[:512])
+        else:
+            with P.fork(_FORK["ENC_V"], k=0):  # the value projection does not depend on the position-scale chain
+                v = _mm_bias(x, Win[512:], b_in[512:])
+            h1 = _mm_bias_relu(x, P.w("e.ps0_w"), P.w("e.ps0_b"))
+            s = _mm_bias(h1, P.w("e.ps2_w"), P.w("e.ps2_b"))
+            xq = ops.pos_mul_add(x, pos, s)
+            qk = _mm_bias(xq, Win[:512], b_in[:512])
+        P.join(0)
         da_ = self._d(dc["e.attn"], enc_site(l, "attn"))
         # attention dropout mask as bit matrices: rows for the forward kernel, columns kept for the backward
         rb = cb = None
@@ -423,19 +486,31 @@ class HotPathRuntime:
             if ev is not None:
                 torch.cuda.current_stream().wait_event(ev)
         a, lse = ops.enc_attn_fwd(qk[:, :256], qk[:, 256:], v, bits, B, N, 8, 1.0 / math.sqrt(32), drop=da_, rowbits=rb)
-        o = _mm_bias(a, P.w(f"e{l}.out_w"), P.w(f"e{l}.out_b"))
-        x1, m1, r1 = ops.add_layernorm(x, o, P.f(f"e{l}.n1_w"), P.f(f"e{l}.n1_b"), save_stats=True,
-                                       drop=self._d(dc["e.d1"], enc_site(l, "d1")))
+        d1_, d2_, d3_ = (self._d(dc["e.d" + k], enc_site(l, "d" + k)) for k in "123")
+        if _TC_LN:
+            # out-proj + dropout1 + residual + norm1 in one kernel; z1 = x + dropout1(out_proj(a)) is what norm1's
+            # backward needs (it replaces the saved out-proj output)
+            x1, o, m1, r1 = ops.gemm_res_ln(a, P.w(f"e{l}.out_w"), P.f(f"e{l}.out_b"), x, P.f(f"e{l}.n1_w"),
+                                            P.f(f"e{l}.n1_b"), drop=d1_)
+        else:
+            o = ops.gemm(a, P.w(f"e{l}.out_w"), bias=P.f(f"e{l}.out_b")) if _TC else \
+                _mm_bias(a, P.w(f"e{l}.out_w"), P.w(f"e{l}.out_b"))
+            x1, m1, r1 = ops.add_layernorm(x, o, P.f(f"e{l}.n1_w"), P.f(f"e{l}.n1_b"), save_stats=True, drop=d1_)
         if _FUSED_FFN1:  # tcgen05 GEMM with bias + ReLU + dropout2 in its epilogue (csrc/gemm_bias_relu.cu)
-            f1 = ops.linear_bias_relu_dropout(x1, P.w(f"e{l}.fc1_w"), P.f(f"e{l}.fc1_b"),
-                                              self._d(dc["e.d2"], enc_site(l, "d2")))
+            f1 = ops.linear_bias_relu_dropout(x1, P.w(f"e{l}.fc1_w"), P.f(f"e{l}.fc1_b"), d2_)
         else:    # library path: cuBLASLt bias+ReLU epilogue, then the dropout pass
             f1 = _mm_bias_relu(x1, P.w(f"e{l}.fc1_w"), P.w(f"e{l}.fc1_b"))
-            ops.dropout_inplace(f1, self._d(dc["e.d2"], enc_site(l, "d2")))
-        g = _mm_bias(f1, P.w(f"e{l}.fc2_w"), P.w(f"e{l}.fc2_b"))
-        x2, m2, r2 = ops.add_layernorm(x1, g, P.f(f"e{l}.n2_w"), P.f(f"e{l}.n2_b"), save_stats=True,
-                                       drop=self._d(dc["e.d3"], enc_site(l, "d3")))
-        xo, m3, r3 = ops.add_layernorm(x, x2, P.f("e.n_w"), P.f("e.n_b"), save_stats=True)
+            ops.dropout_inplace(f1, d2_)
+        if _TC_LN:
+            # fc2 + dropout3 + residual + norm2, then the encoder's shared norm on x + block(x), all in the epilogue
+            x2, g, m2, r2, xo, m3, r3 = ops.gemm_res_ln(f1, P.w(f"e{l}.fc2_w"), P.f(f"e{l}.fc2_b"), x1, P.f(f"e{l}.n2_w"),
+                                                        P.f(f"e{l}.n2_b"), drop=d3_, res2=x, gamma2=P.f("e.n_w"),
+                                                        beta2=P.f("e.n_b"))
+        else:
+            g = ops.gemm(f1, P.w(f"e{l}.fc2_w"), bias=P.f(f"e{l}.fc2_b")) if _TC else \
+                _mm_bias(f1, P.w(f"e{l}.fc2_w"), P.w(f"e{l}.fc2_b"))
+            x2, m2, r2 = ops.add_layernorm(x1, g, P.f(f"e{l}.n2_w"), P.f(f"e{l}.n2_b"), save_stats=True, drop=d3_)
+            xo, m3, r3 = ops.add_layernorm(x, x2, P.f("e.n_w"), P.f("e.n_b"), save_stats=True)
         return xo, (x, h1, xq, qk, v, a, lse, o, x1, m1, r1, f1, g, x2, m2, r2, m3, r3, cb)
 
     def _enc_bwd(self, l: int, dxo: Tensor, sv, pos: Tensor, bits: Tensor, B: int, N: int) -> Tensor:
@@ -445,22 +520,30 @@ class HotPathRuntime:
         d3, _, _ = ops.add_layernorm_bwd(dxo, x, x2, P.f("e.n_w"), m3, r3, dgamma=P.g("e.n_w"), dbeta=P.g("e.n_b"))
         # x2 = LN(x1 + fc2(relu(fc1 x1)))
         # (with dropout3 active the gradient splits: d2 goes through the mask into fc2, d2s is the un-masked residual)
+        # fused-LayerNorm forward: `g` / `o` hold the pre-LayerNorm sums z = residual + dropout(linear), so the
+        # backward reads one operand (a = z, b = None); the dropout mask is still applied to the branch gradient
         dc = self.dc
-        r_ = ops.add_layernorm_bwd(d3, x1, g, P.f(f"e{l}.n2_w"), m2, r2, dgamma=P.g(f"e{l}.n2_w"),
-                                   dbeta=P.g(f"e{l}.n2_b"), dbias=P.g(f"e{l}.fc2_b"),
+        r_ = ops.add_layernorm_bwd(d3, g if _TC_LN else x1, None if _TC_LN else g, P.f(f"e{l}.n2_w"), m2, r2,
+                                   dgamma=P.g(f"e{l}.n2_w"), dbeta=P.g(f"e{l}.n2_b"), dbias=P.g(f"e{l}.fc2_b"),
                                    drop=self._d(dc["e.d3"], enc_site(l, "d3")), want_sum=bool(dc["e.d3"]))
         d2, d2s = r_[0], (r_[3] if dc["e.d3"] else r_[0])
         P.acc_gw(f"e{l}.fc2_w", d2, f1)
-        df1 = torch.mm(d2, P.w(f"e{l}.fc2_w"))
-        dpre = ops.relu_bwd_colsum(df1, f1, P.g(f"e{l}.fc1_b"), scale=_drop_scale(dc["e.d2"]))
-        P.acc_gw(f"e{l}.fc1_w", dpre, x1)
-        dx1 = torch.addmm(d2s, dpre, P.w(f"e{l}.fc1_w"))
+        if _TC:
+            # dX of fc2 + the ReLU/dropout2 mask + fc1's bias gradient in one kernel, then dX of fc1 + residual gradient
+            dpre = ops.gemm_relu_bwd(d2, P.w(f"e{l}.fc2_w"), f1, _drop_scale(dc["e.d2"]), P.g(f"e{l}.fc1_b"))
+            P.acc_gw(f"e{l}.fc1_w", dpre, x1)
+            dx1 = ops.gemm(dpre, P.w(f"e{l}.fc1_w"), b_kn=True, add=d2s)
+        else:
+            df1 = torch.mm(d2, P.w(f"e{l}.fc2_w"))
+            dpre = ops.relu_bwd_colsum(df1, f1, P.g(f"e{l}.fc1_b"), scale=_drop_scale(dc["e.d2"]))
+            P.acc_gw(f"e{l}.fc1_w", dpre, x1)
+            dx1 = torch.addmm(d2s, dpre, P.w(f"e{l}.fc1_w"))
         # x1 = LN(x + dropout1(out_proj(attn)));  dx = d3 + d(x1 input)
-        d1, _, _, dx = ops.add_layernorm_bwd(dx1, x, o, P.f(f"e{l}.n1_w"), m1, r1, dgamma=P.g(f"e{l}.n1_w"),
-                                             dbeta=P.g(f"e{l}.n1_b"), dbias=P.g(f"e{l}.out_b"), res_in=d3,
-                                             drop=self._d(dc["e.d1"], enc_site(l, "d1")))
+        d1, _, _, dx = ops.add_layernorm_bwd(dx1, o if _TC_LN else x, None if _TC_LN else o, P.f(f"e{l}.n1_w"), m1, r1,
+                                             dgamma=P.g(f"e{l}.n1_w"), dbeta=P.g(f"e{l}.n1_b"), dbias=P.g(f"e{l}.out_b"),
+                                             res_in=d3, drop=self._d(dc["e.d1"], enc_site(l, "d1")))
         P.acc_gw(f"e{l}.out_w", d1, a)
-        da = torch.mm(d1, P.w(f"e{l}.out_w"))
+        da = ops.gemm(d1, P.w(f"e{l}.out_w"), b_kn=True) if _TC else torch.mm(d1, P.w(f"e{l}.out_w"))
         dqk, dv = ops.enc_attn_bwd(qk[:, :256], qk[:, 256:], v, bits, a, da, lse, B, N, 8, 1.0 / math.sqrt(32),
                                    drop=self._d(dc["e.attn"], enc_site(l, "attn")), colbits=cb)
         gb = P.g(f"e{l}.in_b")
@@ -468,16 +551,27 @@ class HotPathRuntime:
         Win = P.w(f"e{l}.in_w")
         P.acc_gw(f"e{l}.in_w", dqk, xq, sl=slice(0, 512))
         P.acc_gw(f"e{l}.in_w", dv, x, sl=slice(512, 768))
-        dxq = torch.mm(dqk, Win[:512])
-        dx.addmm_(dv, Win[512:])
-        ds, dx = ops.pos_mul_add_bwd_acc(dxq, pos, dx)
-        return self._pos_scale_bwd("e", ds, h1, x, dx)
+        if _TC:
+            ops.gemm(dv, Win[512:], b_kn=True, add=dx, out=dx)                         # dx += dv Wv
+            ds, dx = ops.gemm(dqk, Win[:512], b_kn=True, mul=pos, add2=dx, out2=True)  # ds = dxq * pos, dx += dxq
+        else:
+            dxq = torch.mm(dqk, Win[:512])
+            dx.addmm_(dv, Win[512:])
+            ds, dx = ops.pos_mul_add_bwd_acc(dxq, pos, dx)
+        dx = self._pos_scale_bwd("e", ds, h1, x, dx)
+        P.reduce_encoder_layer(l)  # data parallel: this layer's weight gradients are final
+        return dx
 
     def _pos_scale_bwd(self, pfx: str, ds: Tensor, h1: Tensor, xin: Tensor, dx_acc: Tensor) -> Tensor:
         """backward of s = W2 relu(W0 xin + b0) + b2 (shared MLP): accumulates weight grads, dx_acc += ..."""
         P = self.P
         P.off_path(lambda: ops.relu_bwd_colsum(ds, None, P.g(pfx + ".ps2_b")), ds)
         P.acc_gw(pfx + ".ps2_w", ds, h1)
+        if _TC and pfx == "e":
+            dpre = ops.gemm_relu_bwd(ds, P.w(pfx + ".ps2_w"), h1, 1.0, P.g(pfx + ".ps0_b"))
+            P.acc_gw(pfx + ".ps0_w", dpre, xin)
+            ops.gemm(dpre, P.w(pfx + ".ps0_w"), b_kn=True, add=dx_acc, out=dx_acc)
+            return dx_acc
         dh = torch.mm(ds, P.w(pfx + ".ps2_w"))
         dpre = ops.relu_bwd_colsum(dh, h1, P.g(pfx + ".ps0_b"))
         P.acc_gw(pfx + ".ps0_w", dpre, xin)
@@ -610,8 +704,12 @@ class HotPathRuntime:
             enc_saved.append(sv)
         enc = x
         # fine_pos = pos * encoder._pos_scale(enc_out)   (model.py:89-92)
-        hfp = _mm_bias_relu(enc, P.w("e.ps0_w"), P.w("e.ps0_b"))
-        fine = ops.mul(_mm_bias(hfp, P.w("e.ps2_w"), P.w("e.ps2_b")), pos)
+        if _TC:
+            hfp = ops.gemm(enc, P.w("e.ps0_w"), bias=P.f("e.ps0_b"), relu=True)
+            fine = ops.gemm(hfp, P.w("e.ps2_w"), bias=P.f("e.ps2_b"), mul=pos)
+        else:
+            hfp = _mm_bias_relu(enc, P.w("e.ps0_w"), P.w("e.ps0_b"))
+            fine = ops.mul(_mm_bias(hfp, P.w("e.ps2_w"), P.w("e.ps2_b")), pos)
         # projections of layer-invariant inputs for ALL decoder layers: three packed GEMMs
         kv_all = torch.mm(enc, P.w("d0.ke_w", rows=Ld * 512).t())
         kpos_all = torch.mm(fine, P.w("d0.kp_w", rows=Ld * 256).t())
