@@ -192,6 +192,17 @@ int destr_dec_self_pair_attn_bwd_ds(const void* qkv, const void* cat, const void
                                     const float* lse1, const float* lse2, const float* delta1, const float* delta2,
                                     void* P1, void* dS1, void* P2, void* dS2, int B, int Q, const uint32_t* drop_seed, uint32_t drop_thr16,
     uint32_t drop_site, void* stream);
+/* FUSED backward of destr_dec_self_pair_attn_fwd for Q <= 128 (the training shape, 100 queries): S and dP are
+ * recomputed on the tensor cores, the softmax backward runs in registers, P and dS stay in shared memory as bf16 tiles
+ * and dQ = dS K, dK = dS^T Q, dV = P^T dO are tcgen05 products in the same kernel -- nothing but the gradients is
+ * written (autograd of self_attention.py:26-45 with 8 x 64 heads and of pair_self_attention.py:91-99).
+ *   qkv [3][B,8,Q,64], cat [3][B,8,Q,128], do1 [B,8,Q,64], do2 [B,8,Q,128] head-major bf16; lse / delta fp32 [B,8,Q]
+ *   d_qkv [3][B,8,Q,64], d_cat [3][B,8,Q,128] bf16 out.  Q > 128: destr_dec_self_pair_attn_bwd_ds + batched GEMMs. */
+int destr_dec_self_pair_attn_bwd(const void* qkv, const void* cat, const void* do1, const void* do2, const float* lse1,
+                                 const float* lse2, const float* delta1, const float* delta2, void* d_qkv, void* d_cat,
+                                 int B, int Q, const uint32_t* drop_seed, uint32_t drop_thr16, uint32_t drop_site,
+                                 void* stream);
+
 /* Backward of destr_dec_qkv_prep (gather formulation of the scatter-add, deterministic): head-major
  * d_qkv [3][B,8,Q,64], d_cat [3][B,8,Q,128] -> d_qkv_obj bf16 [B*Q,1536], d_qk_pos bf16 [B*Q,512] (pitch ld_pos). */
 int destr_dec_qkv_prep_bwd(const void* d_qkv, const void* d_cat, const int32_t* pairs, void* d_qkv_obj,
@@ -227,6 +238,19 @@ int destr_split_cross_attn_bwd_ds(const void* q_obj, const void* q_pos, const vo
                                   float* delta, void* P_all, void* dS_all, void* dS_sum, int B, int Q, int N,
                                   float scale, const uint32_t* drop_seed, uint32_t drop_thr16,
     uint32_t drop_site, void* stream);
+
+/* FUSED backward of destr_split_cross_attn_fwd for Q <= 128: as the _ds entry point, but P never leaves the chip and
+ * the key-side gradients are finished inside the kernel -- dv = sum_br P_br^T dO_br, dk_enc = sum_br dS_br^T q_obj_br,
+ * dk_pos = sum_br dS_br^T q_pos, complete per key tile, stored bf16 into dk_enc / dk_pos / dv ([B*N,256] views with
+ * row pitches ld_*: e.g. column slices of the packed d_kv_all / d_kpos_all buffers).  dS_all [B,2Q,Np] (rows 2q+br) and
+ * dS_sum [B,Q,Np] (bf16, Np = 128*ceil(N/128), pad columns zero) are written for the query-side products
+ * dq_obj = dS k_enc, dq_pos = dS_sum k_pos (destr_gemm_bf16_batched). */
+int destr_split_cross_attn_bwd_fused(const void* q_obj, const void* q_pos, const void* k_enc, const void* k_pos,
+                                     const void* v, int ld_kenc, int ld_kpos, int ld_v, const uint32_t* mask_bits,
+                                     int words_per_row, const void* out, const void* dout, const float* lse,
+                                     float* delta, void* dS_all, void* dS_sum, void* dk_enc, int ld_dke, void* dk_pos,
+                                     int ld_dkp, void* dv, int ld_dv, int B, int Q, int N, float scale,
+                                     const uint32_t* drop_seed, uint32_t drop_thr16, uint32_t drop_site, void* stream);
 
 /* ---------------- set-prediction cost matrix ---------------- */
 
@@ -309,6 +333,13 @@ int destr_gemm_res_ln(const void* a, int lda, const void* w, int ldw, int M, int
                       const float* gamma, const float* beta, void* z, int ldz, void* y, int ldy, float* mean,
                       float* rstd, const void* res2, int ldres2, const float* gamma2, const float* beta2, void* y2,
                       int ldy2, float* mean2, float* rstd2, void* stream);
+
+/* `batch` independent products out_i[M,N] = a_i[M,K] . op(b_i) in one launch (plain store epilogue).  a is ONE
+ * row-major matrix holding the a_i stacked every a_batch_rows rows, b likewise every b_batch_rows rows (b_kn as above),
+ * out the stack of the [M,N] results.  Used for the query side of the split cross-attention backward:
+ * dq_obj_b = dS_b k_enc_b, dq_pos_b = (dS_cls + dS_reg)_b k_pos_b per image b (decoder_block.py:189-217 autograd). */
+int destr_gemm_bf16_batched(const void* a, int lda, int a_batch_rows, const void* b, int ldb, int b_batch_rows,
+                            int b_kn, int batch, int M, int N, int K, void* out, int ldo, void* stream);
 
 /* Weight gradient dw[Nout,Kin] += dy[M,Nout]^T x[M,Kin] (fp32 accumulation INTO dw with red.global.add: zero it first),
  * split over the M rows so small weight matrices still fill the GPU.  dy, x bf16 row-major; dw fp32, pitch lddw. */

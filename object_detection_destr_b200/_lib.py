@@ -48,7 +48,11 @@ SIGNATURES = {
     "destr_split_cross_attn_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _p, _i, _p, _p, _p, _i, _i, _i, _f, _p, _u, _u, _p],
     "destr_split_cross_attn_bwd_ds": [_p, _p, _p, _p, _p, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i,
                                       _f, _p, _u, _u, _p],
+    "destr_split_cross_attn_bwd_fused": [_p, _p, _p, _p, _p, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _p, _i,
+                                         _p, _i, _i, _i, _i, _f, _p, _u, _u, _p],
+    "destr_gemm_bf16_batched": [_p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p],
     "destr_dec_self_pair_attn_bwd_ds": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _u, _u, _p],
+    "destr_dec_self_pair_attn_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _u, _u, _p],
     "destr_dec_qkv_prep_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _p],
     "destr_pair_indices": [_p, _p, _i, _i, _p],
     "destr_box_refine": [_p, _p, _p, _i, _p],
@@ -79,7 +83,8 @@ lib.destr_last_error.argtypes = []
 lib.destr_last_error.restype = C.c_char_p
 
 # kernels launched per C-ABI call (bench.py reports the sum over a step as gpu_launches)
-KERNELS_PER_CALL = {"destr_enc_attn_bwd": 3, "destr_select_queries": 2, "destr_heads_bwd": 2, "destr_split_cross_attn_fwd": 2, "destr_split_cross_attn_bwd_ds": 2}
+KERNELS_PER_CALL = {"destr_enc_attn_bwd": 3, "destr_select_queries": 2, "destr_heads_bwd": 2, "destr_split_cross_attn_fwd": 2, "destr_split_cross_attn_bwd_ds": 2,
+                    "destr_split_cross_attn_bwd_fused": 2}
 launch_count = 0
 # bench.py: {name: []} -> (start, end) CUDA-event pairs are appended around every call of `name`
 KERNEL_TIMERS = None

@@ -177,6 +177,271 @@ cross_attn_bwd_ds_kernel(const __grid_constant__ CUtensorMap tm_qobj, const __gr
   if (warp == 5) tmem_dealloc<512>(tmem);
 }
 
+// ------------------------------------------------------------------------------------------------
+// FUSED backward for Q <= 128 (one query tile, the training shape): CTA = (key tile j, image b), both branches.
+//   phase 1 (as above)   S_br, dP_br on the tensor cores -> softmax backward -> P_br, dS_br as bf16 TILES IN SHARED
+//                        MEMORY ([128 queries][128 keys], two SW128 chunks of 64 keys each); P never goes to HBM
+//   phase 2              dV_j  = sum_br P_br^T  dO_br        TMEM [0,256)      A = tile read MN-major (contraction
+//                        dKe_j = sum_br dS_br^T q_obj_br     TMEM [256,512)        over the 128 query rows),
+//   phase 3              dKp_j = sum_br dS_br^T q_pos        TMEM [0,256)      B = [128 queries][64] chunks, MN-major
+//   The key-side gradients of a key tile are complete inside its CTA: they are stored (bf16) straight into the packed
+//   d_kv_all / d_kpos_all slices -- no atomics, no partials.  The query side (dq_obj = dS k_enc, dq_pos =
+//   (dS_cls + dS_reg) k_pos) contracts over ALL keys of the image: the kernel also writes dS and dS_cls + dS_reg
+//   (bf16, 2 x 3.4 MB + 1.7 MB at config 2) and two batched tcgen05 GEMMs (destr_gemm_bf16_batched) finish.
+// TMA ring: 3 stages of (A 16 KB, B 16 KB); phases 2-3 stream single B chunks through the same ring.
+// ------------------------------------------------------------------------------------------------
+constexpr int NSTAGE_F = 3;
+struct __align__(1024) SmemF {
+  uint8_t a[NSTAGE_F][CHUNK_BYTES];
+  uint8_t b[NSTAGE_F][CHUNK_BYTES];
+  uint8_t p[2][2][CHUNK_BYTES];   // [branch][64-key chunk]
+  uint8_t ds[2][2][CHUNK_BYTES];
+  uint64_t full[NSTAGE_F];
+  uint64_t empty[NSTAGE_F];
+  uint64_t sdp_full[2];
+  uint64_t tiles_full;   // P / dS tiles written, S / dP read out of TMEM (128 arrivals)
+  uint64_t g_full[2];    // phase 2 / phase 3 accumulators complete
+  uint64_t g_drained;    // phase 2 accumulators read out (128 arrivals)
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+cross_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qobj, const __grid_constant__ CUtensorMap tm_qpos,
+                            const __grid_constant__ CUtensorMap tm_kenc, const __grid_constant__ CUtensorMap tm_kpos,
+                            const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
+                            const uint32_t* __restrict__ mask_bits, int words_per_row, const float* __restrict__ lse,
+                            const float* __restrict__ delta, __nv_bfloat16* __restrict__ dS_all,
+                            __nv_bfloat16* __restrict__ dS_sum, __nv_bfloat16* __restrict__ dke, int ld_dke,
+                            __nv_bfloat16* __restrict__ dkp, int ld_dkp, __nv_bfloat16* __restrict__ dv, int ld_dv,
+                            int Q, int N, int Np, float scale, float scale_log2, Drop dp) {
+  extern __shared__ uint8_t smem_raw[];
+  SmemF& sm = *reinterpret_cast<SmemF*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x, b = blockIdx.y;
+  const int qrow0 = b * Q;
+  const int krow0 = b * N + j * BT;
+  constexpr int NS = NSTAGE_F;
+  constexpr int T1 = 24, T2 = 16, T3 = 4;  // ring entries of the three phases
+
+  if (warp == 4 && lane == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.empty[s], 1);
+    }
+    mbar_init(&sm.sdp_full[0], 1);
+    mbar_init(&sm.sdp_full[1], 1);
+    mbar_init(&sm.tiles_full, 128);
+    mbar_init(&sm.g_full[0], 1);
+    mbar_init(&sm.g_full[1], 1);
+    mbar_init(&sm.g_drained, 128);
+    fence_mbar_init();
+  }
+  if (warp == 5) tmem_alloc<512>(&sm.tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == 4) {
+    if (elect_one()) {
+      for (int t = 0; t < T1 + T2 + T3; ++t) {
+        const int s = t % NS;
+        mbar_wait(&sm.empty[s], ((t / NS) & 1) ^ 1, 41);
+        if (t < T1) {
+          const int br = t / 12, c = t % 12;
+          mbar_arrive_expect_tx(&sm.full[s], 2 * CHUNK_BYTES);
+          if (c < 4) {
+            tma_load_2d(sm.a[s], &tm_qobj, &sm.full[s], br * 256 + c * 64, qrow0);
+            tma_load_2d(sm.b[s], &tm_kenc, &sm.full[s], c * 64, krow0);
+          } else if (c < 8) {
+            tma_load_2d(sm.a[s], &tm_qpos, &sm.full[s], (c - 4) * 64, qrow0);
+            tma_load_2d(sm.b[s], &tm_kpos, &sm.full[s], (c - 4) * 64, krow0);
+          } else {
+            tma_load_2d(sm.a[s], &tm_do, &sm.full[s], br * 256 + (c - 8) * 64, qrow0);
+            tma_load_2d(sm.b[s], &tm_v, &sm.full[s], (c - 8) * 64, krow0);
+          }
+        } else {
+          // phases 2 / 3: one [128 queries][64 columns] chunk, the MN-major B operand of a key-side product
+          const int u = t - T1;
+          mbar_arrive_expect_tx(&sm.full[s], CHUNK_BYTES);
+          if (u < 8) {            // dO_br chunk c        (dV)
+            tma_load_2d(sm.a[s], &tm_do, &sm.full[s], (u >> 2) * 256 + (u & 3) * 64, qrow0);
+          } else if (u < 16) {    // q_obj_br chunk c     (dK_enc)
+            tma_load_2d(sm.a[s], &tm_qobj, &sm.full[s], ((u - 8) >> 2) * 256 + (u & 3) * 64, qrow0);
+          } else {                // q_pos chunk c        (dK_pos)
+            tma_load_2d(sm.a[s], &tm_qpos, &sm.full[s], (u - 16) * 64, qrow0);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BT, BT, false, false);
+      constexpr uint32_t id_nn = umma_idesc_bf16(BT, 64, true, true);     // A MN-major (tile), B MN-major, N = 64
+      constexpr uint64_t D_BMN = umma_desc_const(16, 1024, SWZ_128B);       // one 64-wide atom, k-step 2048 B
+      constexpr uint64_t D_AMN = umma_desc_const(16384, 1024, SWZ_128B);    // two 64-wide atoms 16 KB apart
+      int t = 0;
+      for (; t < T1; ++t) {
+        const int br = t / 12, c = t % 12;
+        const int s = t % NS;
+        mbar_wait(&sm.full[s], (t / NS) & 1, 42);
+        tc_fence_after();
+        const uint32_t dst = tmem + br * 256 + (c < 8 ? 0 : 128);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          umma_ss(dst, umma_smem_desc(smem_u32(sm.a[s]) + ks * 32, 16, 1024, SWZ_128B),
+                  umma_smem_desc(smem_u32(sm.b[s]) + ks * 32, 16, 1024, SWZ_128B), idesc,
+                  ((c != 0 && c != 8) || ks > 0) ? 1u : 0u);
+        }
+        tc_commit(&sm.empty[s]);
+        if (c == 11) tc_commit(&sm.sdp_full[br]);
+      }
+      mbar_wait(&sm.tiles_full, 0, 44);  // tiles in shared memory, S / dP consumed: TMEM is free for the accumulators
+      tc_fence_after();
+      for (; t < T1 + T2 + T3; ++t) {
+        const int u = t - T1;
+        const int s = t % NS;
+        mbar_wait(&sm.full[s], (t / NS) & 1, 45);
+        if (u == T2) {  // phase 3 reuses dV's columns
+          mbar_wait(&sm.g_drained, 0, 46);
+        }
+        tc_fence_after();
+        const uint64_t db = D_BMN + (smem_u32(sm.a[s]) >> 4);
+        if (u < T2) {
+          const int br = (u >> 2) & 1, c = u & 3;
+          const uint32_t a_tile = (u < 8) ? smem_u32(sm.p[br][0]) : smem_u32(sm.ds[br][0]);
+          const uint32_t dst = tmem + (u < 8 ? 0 : 256) + c * 64;
+#pragma unroll
+          for (int ks = 0; ks < BT / 16; ++ks)  // contraction over the 128 query rows
+            umma_ss(dst, D_AMN + ((a_tile + ks * 2048) >> 4), db + ks * 128, id_nn, (br > 0 || ks > 0) ? 1u : 0u);
+        } else {
+          const int c = u - T2;
+#pragma unroll
+          for (int br = 0; br < 2; ++br)
+#pragma unroll
+            for (int ks = 0; ks < BT / 16; ++ks)
+              umma_ss(tmem + c * 64, D_AMN + ((smem_u32(sm.ds[br][0]) + ks * 2048) >> 4), db + ks * 128, id_nn,
+                      (br > 0 || ks > 0) ? 1u : 0u);
+        }
+        tc_commit(&sm.empty[s]);
+        if (u == T2 - 1) tc_commit(&sm.g_full[0]);
+      }
+      tc_commit(&sm.g_full[1]);
+    }
+    __syncwarp();
+  } else {
+    const int wq = warp;
+    const uint32_t lane_addr = static_cast<uint32_t>(wq * 32) << 16;
+    const int r = wq * 32 + lane;  // query row (phase 1) / key row of the tile (drains)
+    const int q = r;
+    const bool qvalid = q < Q;
+    const uint32_t drop_seed = (dp.thr16 && dp.seed) ? *dp.seed : 0u;
+    const float drop_s = drop_scale(dp.thr16);
+    const uint4 mw = *reinterpret_cast<const uint4*>(mask_bits + static_cast<size_t>(b) * words_per_row + j * 4);
+    const uint32_t mwa[4] = {mw.x, mw.y, mw.z, mw.w};
+    uint32_t stash[4][16];  // packed dS of branch 0
+#pragma unroll
+    for (int br = 0; br < 2; ++br) {
+      const float l2 = qvalid ? lse[(static_cast<size_t>(b) * 2 + br) * Q + q] : INFINITY;
+      const float dl = qvalid ? delta[(static_cast<size_t>(b) * 2 + br) * Q + q] : 0.f;
+      mbar_wait(&sm.sdp_full[br], 0, 43);
+      tc_fence_after();
+      const size_t row = (static_cast<size_t>(b) * Q + (qvalid ? q : 0)) * 2 + br;
+      __nv_bfloat16* drow = dS_all + row * Np + j * BT;
+      __nv_bfloat16* srow = dS_sum + (static_cast<size_t>(b) * Q + (qvalid ? q : 0)) * Np + j * BT;
+      const uint32_t a_p = smem_u32(sm.p[br][0]), a_ds = smem_u32(sm.ds[br][0]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t s[32], d[32];
+        tmem_ld_x32(tmem + lane_addr + br * 256 + c * 32, s);
+        tmem_ld_x32(tmem + lane_addr + br * 256 + 128 + c * 32, d);
+        tc_wait_ld();
+        uint32_t pp[16], dd[16], ss[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float pv[2], dv_[2];
+          uint32_t bits = 0xFFFFFFFFu;
+          if (dp.thr16)
+            bits = drop_bits(drop_seed, dp.site, static_cast<uint32_t>((b * 2 + br) * Q + q), j * (BT / 2) + c * 16 + i);
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int k = 2 * i + e;
+            float pr = ex2_approx(fmaf(__uint_as_float(s[k]), scale_log2, -l2));
+            pr = ((mwa[c] >> k) & 1u) ? 0.f : pr;
+            const float keep = (((bits >> (16 * e)) & 0xFFFFu) >= dp.thr16) ? drop_s : 0.f;
+            pv[e] = pr * keep;
+            dv_[e] = pr * (__uint_as_float(d[k]) * keep - dl) * scale;
+          }
+          pp[i] = pack_bf16x2(pv[0], pv[1]);
+          dd[i] = pack_bf16x2(dv_[0], dv_[1]);
+          if (br == 0) {
+            stash[c][i] = dd[i];
+          } else {
+            const uint32_t o = stash[c][i];
+            ss[i] = pack_bf16x2(dv_[0] + __uint_as_float(o << 16), dv_[1] + __uint_as_float(o & 0xffff0000u));
+          }
+        }
+        // tiles for the key-side products: row r, columns [32c, 32c+32) of chunk c/2 (rows >= Q are zero: lse = inf)
+        const uint32_t chunk = (c >> 1) * CHUNK_BYTES;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t off = chunk + swz_offset<128>(r, (c & 1) * 4 + u);
+          sts_u4(a_p + off, pp[4 * u], pp[4 * u + 1], pp[4 * u + 2], pp[4 * u + 3]);
+          sts_u4(a_ds + off, dd[4 * u], dd[4 * u + 1], dd[4 * u + 2], dd[4 * u + 3]);
+        }
+        if (qvalid) {  // dS for the query-side GEMMs
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            reinterpret_cast<uint4*>(drow + c * 32)[i] = make_uint4(dd[4 * i], dd[4 * i + 1], dd[4 * i + 2], dd[4 * i + 3]);
+            if (br == 1)
+              reinterpret_cast<uint4*>(srow + c * 32)[i] =
+                  make_uint4(ss[4 * i], ss[4 * i + 1], ss[4 * i + 2], ss[4 * i + 3]);
+          }
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    mbar_arrive(&sm.tiles_full);
+    // ---- drains: thread = key row of the tile ----
+    const int key = j * BT + r;
+    const bool kvalid = key < N;
+    const size_t grow = static_cast<size_t>(b) * N + (kvalid ? key : 0);
+    auto drain = [&](uint32_t col, __nv_bfloat16* dst) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint32_t v[32];
+        tmem_ld_x32(tmem + lane_addr + col + c * 32, v);
+        tc_wait_ld();
+        if (kvalid) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(v[8 * u]), __uint_as_float(v[8 * u + 1]));
+            o.y = pack_bf16x2(__uint_as_float(v[8 * u + 2]), __uint_as_float(v[8 * u + 3]));
+            o.z = pack_bf16x2(__uint_as_float(v[8 * u + 4]), __uint_as_float(v[8 * u + 5]));
+            o.w = pack_bf16x2(__uint_as_float(v[8 * u + 6]), __uint_as_float(v[8 * u + 7]));
+            reinterpret_cast<uint4*>(dst + c * 32)[u] = o;
+          }
+        }
+      }
+    };
+    mbar_wait(&sm.g_full[0], 0, 47);
+    tc_fence_after();
+    drain(0, dv + grow * ld_dv);
+    tc_fence_before();
+    mbar_arrive(&sm.g_drained);  // dV's columns may be overwritten by phase 3
+    drain(256, dke + grow * ld_dke);
+    mbar_wait(&sm.g_full[1], 0, 48);
+    tc_fence_after();
+    drain(0, dkp + grow * ld_dkp);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<512>(tmem);
+}
+
 // delta[b, br, q] = sum_c dO[b*Q+q, br*256+c] * O[b*Q+q, br*256+c]   (one warp per query row)
 __global__ void cross_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
                                    float* __restrict__ delta, int B, int Q) {
@@ -239,6 +504,47 @@ extern "C" int destr_split_cross_attn_bwd_ds(const void* q_obj, const void* q_po
   cross_attn_bwd_ds_kernel<<<grid, NTHREADS, smem, st>>>(
       tqo, tqp, tke, tkp, tv, tdo, mask_bits, words_per_row, lse, delta, static_cast<__nv_bfloat16*>(P_all),
       static_cast<__nv_bfloat16*>(dS_all), static_cast<__nv_bfloat16*>(dS_sum), Q, N, nkv * BT, scale,
+      scale * 1.4426950408889634f, Drop{drop_seed, drop_thr16, drop_site});
+  DESTR_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int destr_split_cross_attn_bwd_fused(const void* q_obj, const void* q_pos, const void* k_enc,
+                                                const void* k_pos, const void* v, int ld_kenc, int ld_kpos, int ld_v,
+                                                const uint32_t* mask_bits, int words_per_row, const void* out,
+                                                const void* dout, const float* lse, float* delta, void* dS_all,
+                                                void* dS_sum, void* dk_enc, int ld_dke, void* dk_pos, int ld_dkp,
+                                                void* dv, int ld_dv, int B, int Q, int N, float scale,
+                                                const uint32_t* drop_seed, uint32_t drop_thr16, uint32_t drop_site,
+                                                void* stream) {
+  using namespace destr;
+  DESTR_CHECK_ARG(q_obj && q_pos && k_enc && k_pos && v && mask_bits && out && dout && lse && delta && dS_all &&
+                      dS_sum && dk_enc && dk_pos && dv,
+                  "null pointer");
+  DESTR_CHECK_ARG(B > 0 && Q > 0 && Q <= BT && N > 0, "fused backward: Q must be <= 128 (use the _ds entry point)");
+  DESTR_CHECK_ARG(ld_dke % 8 == 0 && ld_dkp % 8 == 0 && ld_dv % 8 == 0 && ld_dke >= 256 && ld_dkp >= 256 && ld_dv >= 256,
+                  "gradient pitches");
+  const int nkv = ceil_div(N, BT);
+  DESTR_CHECK_ARG(words_per_row >= nkv * 4, "words_per_row");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint64_t qrows = static_cast<uint64_t>(B) * Q, krows = static_cast<uint64_t>(B) * N;
+  CUtensorMap tqo, tqp, tke, tkp, tv, tdo;
+  int rc;
+  if ((rc = make_tmap_bf16_2d(&tqo, q_obj, qrows, 512, 512, BT, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tqp, q_pos, qrows, 256, 256, BT, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tke, k_enc, krows, 256, ld_kenc, BT, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tkp, k_pos, krows, 256, ld_kpos, BT, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tv, v, krows, 256, ld_v, BT, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tdo, dout, qrows, 512, 512, BT, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  const size_t smem = sizeof(SmemF) + 1024;
+  DESTR_SMEM_OPTIN(cross_attn_bwd_fused_kernel, smem);
+  cross_delta_kernel<<<ceil_div((int)qrows, 8), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(out),
+                                                              static_cast<const __nv_bfloat16*>(dout), delta, B, Q);
+  DESTR_LAUNCH_CHECK();
+  cross_attn_bwd_fused_kernel<<<dim3(nkv, B), NTHREADS, smem, st>>>(
+      tqo, tqp, tke, tkp, tv, tdo, mask_bits, words_per_row, lse, delta, static_cast<__nv_bfloat16*>(dS_all),
+      static_cast<__nv_bfloat16*>(dS_sum), static_cast<__nv_bfloat16*>(dk_enc), ld_dke,
+      static_cast<__nv_bfloat16*>(dk_pos), ld_dkp, static_cast<__nv_bfloat16*>(dv), ld_dv, Q, N, nkv * BT, scale,
       scale * 1.4426950408889634f, Drop{drop_seed, drop_thr16, drop_site});
   DESTR_LAUNCH_CHECK();
   return 0;

@@ -43,6 +43,9 @@ enum { EPI_STORE = 0, EPI_RELU_BWD = 1, EPI_RES_LN = 2 };
 
 struct GemmArgs {
   int M, N, K;
+  // batched products (blockIdx.y = batch index): A and B are stacks of per-batch row blocks inside ONE 2-D tensor map
+  // (a_brows / b_brows rows per batch); `out` is the stack of the [M, N] results.  0 = not batched.
+  int a_brows, b_brows;
   const float* bias;
   int relu;
   Drop dp;
@@ -161,17 +164,17 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;" ::: 
 // __grid_constant__ parameters: TMA must read the descriptor from param/const/global space, never from a local copy)
 template <int BN, bool B_MN>
 __device__ __forceinline__ void issue_chunk(Smem<BN>& sm, const CUtensorMap* ta, const CUtensorMap* tb, int c, int m0,
-                                            int kc, int n0) {
+                                            int kc, int n0, int a_row0, int b_row0) {
   constexpr int NSTAGE = Smem<BN>::NSTAGE;
   const int s = c % NSTAGE;
   mbar_arrive_expect_tx(&sm.full[s], A_BYTES + BN * BK * 2);
-  tma_load_2d(sm.a[s], ta, &sm.full[s], kc * BK, m0);
+  tma_load_2d(sm.a[s], ta, &sm.full[s], kc * BK, a_row0 + m0);
   if (!B_MN) {
-    tma_load_2d(sm.b[s], tb, &sm.full[s], kc * BK, n0);  // [BN rows (n)] x [64 k]: K-major
+    tma_load_2d(sm.b[s], tb, &sm.full[s], kc * BK, b_row0 + n0);  // [BN rows (n)] x [64 k]: K-major
   } else {
 #pragma unroll
     for (int a64 = 0; a64 < BN / 64; ++a64)  // [64 k rows] x [64 n]: one MN-major SW128 atom column per box
-      tma_load_2d(sm.b[s] + a64 * 8192, tb, &sm.full[s], n0 + a64 * 64, kc * BK);
+      tma_load_2d(sm.b[s] + a64 * 8192, tb, &sm.full[s], n0 + a64 * 64, b_row0 + kc * BK);
   }
 }
 
@@ -192,6 +195,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   const int n0 = (static_cast<int>(blockIdx.x) % nb) * BN;
   const int j0 = static_cast<int>(blockIdx.x) / nb, gs = static_cast<int>(gridDim.x) / nb;
   const int my_tiles = (mt - j0 + gs - 1) / gs;
+  const int bz = blockIdx.y;  // batch index (0 when not batched)
 
   if (warp == NEPI && lane == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
@@ -220,7 +224,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         const int m0 = (j0 + i * gs) * BM;
         for (int kc = 0; kc < nkc; ++kc, ++c) {
           mbar_wait(&sm.empty[c % NSTAGE], ((c / NSTAGE) & 1) ^ 1, 51);
-          issue_chunk<BN, B_MN>(sm, &tm_a, &tm_b, c, m0, kc, n0);
+          issue_chunk<BN, B_MN>(sm, &tm_a, &tm_b, c, m0, kc, n0, bz * ga.a_brows, bz * ga.b_brows);
         }
       }
     }
@@ -274,6 +278,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     epi_bar();
     const uint32_t stg = smem_u32(sm.stage[warp]);
     const int cw0 = cg * CW;  // first column of this warp inside the tile
+    __nv_bfloat16* const out_b = ga.out + static_cast<size_t>(bz) * M * ga.ldo;  // batched: stack of [M, N] results
     for (int i = 0; i < my_tiles; ++i) {
       const int m0 = (j0 + i * gs) * BM;
       const int acc = i & 1;
@@ -498,7 +503,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             }
 #pragma unroll
             for (int p = 0; p < 16; ++p) pk[p] = pack_bf16x2(__uint_as_float(v[2 * p]), __uint_as_float(v[2 * p + 1]));
-            warp_store_tile(stg, ga.out, ga.ldo, row0, col0, M, lane, pk);
+            warp_store_tile(stg, out_b, ga.ldo, row0, col0, M, lane, pk);
           }
         }
       }
@@ -618,14 +623,16 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant_
 }
 
 template <int BN, bool B_MN, int EPI>
-int launch_gemm(const void* a, int lda, const void* b, int ldb, const GemmArgs& ga, cudaStream_t st) {
+int launch_gemm(const void* a, int lda, const void* b, int ldb, const GemmArgs& ga, cudaStream_t st, int batch = 1) {
   CUtensorMap ta, tb;
   int rc;
-  if ((rc = make_tmap_bf16_2d(&ta, a, ga.M, ga.K, lda, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  const uint64_t a_rows = batch > 1 ? static_cast<uint64_t>(batch) * ga.a_brows : ga.M;
+  const uint64_t b_rows = batch > 1 ? static_cast<uint64_t>(batch) * ga.b_brows : (B_MN ? ga.K : ga.N);
+  if ((rc = make_tmap_bf16_2d(&ta, a, a_rows, ga.K, lda, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if (!B_MN) {
-    if ((rc = make_tmap_bf16_2d(&tb, b, ga.N, ga.K, ldb, BN, BK, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tb, b, b_rows, ga.K, ldb, BN, BK, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   } else {
-    if ((rc = make_tmap_bf16_2d(&tb, b, ga.K, ga.N, ldb, BK, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tb, b, b_rows, ga.N, ldb, BK, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   }
   const size_t smem = sizeof(Smem<BN>) + 1024;
   DESTR_SMEM_OPTIN((gemm_tc_kernel<BN, B_MN, EPI>), smem);
@@ -634,7 +641,7 @@ int launch_gemm(const void* a, int lda, const void* b, int ldb, const GemmArgs& 
   if (gs < 1) gs = 1;
   if (gs > mt) gs = mt;
   gs = ceil_div(mt, ceil_div(mt, gs));
-  gemm_tc_kernel<BN, B_MN, EPI><<<gs * nb, NTHREADS, smem, st>>>(ta, tb, ga);
+  gemm_tc_kernel<BN, B_MN, EPI><<<dim3(gs * nb, batch), NTHREADS, smem, st>>>(ta, tb, ga);
   DESTR_LAUNCH_CHECK();
   return 0;
 }
@@ -743,4 +750,19 @@ extern "C" int destr_gemm_dw(const void* dy, int lddy, const void* x, int ldx, i
                                                                                          nchunk, per);
   DESTR_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int destr_gemm_bf16_batched(const void* a, int lda, int a_batch_rows, const void* b, int ldb,
+                                       int b_batch_rows, int b_kn, int batch, int M, int N, int K, void* out, int ldo,
+                                       void* stream) {
+  int rc = check_common(a, lda, b, ldb, M, N, K, b_kn);
+  if (rc) return rc;
+  DESTR_CHECK_ARG(out && ldo % 8 == 0 && ldo >= N && batch > 0 && a_batch_rows >= M && b_batch_rows > 0, "out / batch");
+  GemmArgs ga{};
+  ga.M = M, ga.N = N, ga.K = K;
+  ga.a_brows = a_batch_rows, ga.b_brows = b_batch_rows;
+  ga.out = static_cast<bf16*>(out), ga.ldo = ldo;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return b_kn ? launch_gemm<128, true, EPI_STORE>(a, lda, b, ldb, ga, st, batch)
+              : launch_gemm<128, false, EPI_STORE>(a, lda, b, ldb, ga, st, batch);
 }

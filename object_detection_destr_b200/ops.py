@@ -465,14 +465,26 @@ def split_cross_attn_fwd(q_obj: Tensor, q_pos: Tensor, k_enc: Tensor, k_pos: Ten
     return out, lse
 
 
+import os as _os
+_FUSED_DEC_BWD = _os.environ.get("DESTR_FUSED_DEC_BWD", "1") == "1"  # "0": two-stage path (ds kernel + batched GEMMs)
+
+
 def dec_self_pair_attn_bwd(qkv: Tensor, cat: Tensor, do1: Tensor, do2: Tensor, lse1: Tensor, lse2: Tensor,
                            delta1: Tensor, delta2: Tensor, B: int, Q: int, drop=None):
     """Backward of dec_self_pair_attn_fwd.  All operands head-major: qkv [3,B,8,Q,64], cat [3,B,8,Q,128],
-    do1 [B,8,Q,64], do2 [B,8,Q,128]; lse/delta fp32 [B,8,Q].  The tcgen05 kernel recomputes S, dP and does the
-    softmax backward; six cuBLAS batched GEMMs finish.  -> head-major (d_qkv [3,B,8,Q,64], d_cat [3,B,8,Q,128])."""
+    do1 [B,8,Q,64], do2 [B,8,Q,128]; lse/delta fp32 [B,8,Q].  Q <= 128: ONE fused tcgen05 kernel (S, dP, softmax
+    backward, dQ / dK / dV).  Q > 128: the tcgen05 kernel recomputes S, dP and does the softmax backward, six batched
+    library GEMMs finish.  -> head-major (d_qkv [3,B,8,Q,64], d_cat [3,B,8,Q,128])."""
     dev = qkv.device
     Qp = ((Q + 127) // 128) * 128
     BH = B * 8
+    if Q <= 128 and _FUSED_DEC_BWD:  # one kernel: P / dS never leave the chip (csrc/dec_attn_bwd.cu, fused kernel)
+        d_qkv = torch.empty(3, B, 8, Q, 64, dtype=BF16, device=dev)
+        d_cat = torch.empty(3, B, 8, Q, 128, dtype=BF16, device=dev)
+        _lib.call("destr_dec_self_pair_attn_bwd", qkv.data_ptr(), cat.data_ptr(), do1.data_ptr(), do2.data_ptr(),
+                  lse1.data_ptr(), lse2.data_ptr(), delta1.data_ptr(), delta2.data_ptr(), d_qkv.data_ptr(),
+                  d_cat.data_ptr(), B, Q, *_dargs(drop), _stream())
+        return d_qkv, d_cat
     PD = torch.empty(4, BH, Q, Qp, dtype=BF16, device=dev)  # P1, dS1, P2, dS2
     _lib.call("destr_dec_self_pair_attn_bwd_ds", qkv.data_ptr(), cat.data_ptr(), do1.data_ptr(), do2.data_ptr(),
               lse1.data_ptr(), lse2.data_ptr(), delta1.data_ptr(), delta2.data_ptr(), PD[0].data_ptr(),
@@ -512,12 +524,34 @@ def split_cross_attn_bwd(q_obj: Tensor, q_pos: Tensor, k_enc: Tensor, k_pos: Ten
                          out: Tensor, dout: Tensor, lse: Tensor, B: int, Q: int, N: int,
                          dke_out: Optional[Tensor] = None, dkp_out: Optional[Tensor] = None,
                          dv_out: Optional[Tensor] = None, drop=None):
-    """Backward of split_cross_attn_fwd: the tcgen05 kernel recomputes S, dP and does the softmax backward
-    (P, dS, dS_cls+dS_reg in bf16); five cuBLAS batched GEMMs on plain views finish the contractions.
+    """Backward of split_cross_attn_fwd.  Q <= 128: one fused tcgen05 kernel (S, dP, softmax backward, dV / dK_enc /
+    dK_pos; P never leaves the chip) + two batched tcgen05 GEMMs for dq_obj / dq_pos.  Q > 128: the tcgen05 kernel
+    recomputes S, dP and does the softmax backward (P, dS, dS_cls+dS_reg in bf16), five batched library GEMMs finish.
     -> (dq_obj [B*Q,512], dq_pos [B*Q,256], dk_enc, dk_pos, dv [B*N,256]) bf16."""
     Np = ((N + 127) // 128) * 128
     dev = q_obj.device
     dout = _chk(dout.contiguous(), BF16, "dout")
+    if Q <= 128 and _FUSED_DEC_BWD:
+        # one fused kernel (P stays on chip, key-side gradients finished in it) + two batched tcgen05 GEMMs for the
+        # query side, which contracts over all keys of an image
+        dS_all = torch.empty(B, 2 * Q, Np, dtype=BF16, device=dev)
+        dS_sum = torch.empty(B, Q, Np, dtype=BF16, device=dev)
+        delta = torch.empty(B, 2, Q, dtype=torch.float32, device=dev)
+        dke = torch.empty(B * N, 256, dtype=BF16, device=dev) if dke_out is None else dke_out
+        dkp = torch.empty(B * N, 256, dtype=BF16, device=dev) if dkp_out is None else dkp_out
+        dv = torch.empty(B * N, 256, dtype=BF16, device=dev) if dv_out is None else dv_out
+        _lib.call("destr_split_cross_attn_bwd_fused", q_obj.data_ptr(), q_pos.data_ptr(), k_enc.data_ptr(),
+                  k_pos.data_ptr(), v.data_ptr(), k_enc.stride(0), k_pos.stride(0), v.stride(0), mask_bits.data_ptr(),
+                  mask_bits.shape[1], out.data_ptr(), dout.data_ptr(), lse.data_ptr(), delta.data_ptr(),
+                  dS_all.data_ptr(), dS_sum.data_ptr(), dke.data_ptr(), dke.stride(0), dkp.data_ptr(), dkp.stride(0),
+                  dv.data_ptr(), dv.stride(0), B, Q, N, 1.0 / math.sqrt(512.0), *_dargs(drop), _stream())
+        dqo = torch.empty(B * 2 * Q, 256, dtype=BF16, device=dev)
+        dqp = torch.empty(B * Q, 256, dtype=BF16, device=dev)
+        _lib.call("destr_gemm_bf16_batched", dS_all.data_ptr(), Np, 2 * Q, k_enc.data_ptr(), k_enc.stride(0), N, 1, B,
+                  2 * Q, 256, Np, dqo.data_ptr(), 256, _stream())
+        _lib.call("destr_gemm_bf16_batched", dS_sum.data_ptr(), Np, Q, k_pos.data_ptr(), k_pos.stride(0), N, 1, B, Q, 256,
+                  Np, dqp.data_ptr(), 256, _stream())
+        return dqo.view(B * Q, 512), dqp, dke, dkp, dv
     P_all = torch.empty(B, 2 * Q, Np, dtype=BF16, device=dev)
     dS_all = torch.empty(B, 2 * Q, Np, dtype=BF16, device=dev)
     dS_sum = torch.empty(B, Q, Np, dtype=BF16, device=dev)
