@@ -165,6 +165,12 @@ int destr_pair_indices(const float* coords, int32_t* pairs, int B, int Q, void* 
  * inverse_sigmoid misc.py:59-62).  delta fp32 [M,4], centers fp32 [M,2] -> boxes fp32 [M,4]. */
 int destr_box_refine(const float* delta, const float* centers, float* boxes, int M, void* stream);
 
+/* The box head's output layer fused with the refinement: boxes = sigmoid(hidden W2^T + b2 + [logit(cx), logit(cy), 0, 0])
+ * (decoder_block.py:51-54 with bbox_embed[2] = Linear(256, 4), fp32 weights): hidden bf16 [M,256] (pitch ldh) is the
+ * post-ReLU output of bbox_embed[0]; W2 fp32 [4,256], b2 fp32 [4]; boxes fp32 [M,4]. */
+int destr_box_head_refine(const void* hidden, int ldh, const float* W2, const float* b2, const float* centers,
+                          float* boxes, int M, void* stream);
+
 /* SA operand preparation (decoder_block.py:167-177) + the left/right gathers of pair attention
  * (pair_self_attention.py:47-89) in one pass.
  *   qkv_obj bf16 [B*Q,1536] = [W_q x | W_k x | W_v x];  qk_pos bf16 [B*Q,512] (row pitch ld_pos) = [W_qp p | W_kp p]
@@ -373,10 +379,12 @@ int destr_select_queries(const float* scores, const uint8_t* mask, const float* 
 int destr_heads_fwd(const void* dec, const float* centers, const float* Wc, const float* bc, int C, const float* W1,
                     const float* b1, const float* W2, const float* b2, float* logits, float* boxes, float* hidden,
                     int M, void* stream);
+/* which: 1 = row gradients only (d_dec + the dh / dz workspaces), 2 = parameter gradients only (reads the workspaces a
+ * which = 1 call filled: lets the caller run them off the critical path, on another stream), 3 = both. */
 int destr_heads_bwd(const void* dec, const float* hidden, const float* boxes, const float* dlogits,
                     const float* dboxes, const float* Wc, const float* W1, const float* W2, int C, void* d_dec,
                     float* dh_ws, float* dz_ws, float* dWc, float* dbc, float* dW1, float* db1, float* dW2,
-                    float* db2, int M, void* stream);
+                    float* db2, int M, int which, void* stream);
 
 /* ---------------- optimizer step on the flat parameter buffer ---------------- */
 

@@ -56,6 +56,7 @@ SIGNATURES = {
     "destr_dec_qkv_prep_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _p],
     "destr_pair_indices": [_p, _p, _i, _i, _p],
     "destr_box_refine": [_p, _p, _p, _i, _p],
+    "destr_box_head_refine": [_p, _i, _p, _p, _p, _p, _i, _p],
     "destr_match_cost_blockdiag": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _f, _i, _p],
     "destr_lsap_blockdiag": [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p],
     "destr_linear_bias_relu_dropout": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _p, _u, _u, _p],
@@ -66,7 +67,7 @@ SIGNATURES = {
     "destr_gemm_dw": [_p, _i, _p, _i, _i, _i, _i, _p, _i, _p],
     "destr_select_queries": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p],
     "destr_heads_fwd": [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _p],
-    "destr_heads_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _p],
+    "destr_heads_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
     "destr_flat_adamw": [_p, _p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _p, _p, _i64, _i64, _f, _p],
     "destr_set_loss_fwd_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _f, _p, _p, _p, _p, _p],
 }
@@ -83,7 +84,7 @@ lib.destr_last_error.argtypes = []
 lib.destr_last_error.restype = C.c_char_p
 
 # kernels launched per C-ABI call (bench.py reports the sum over a step as gpu_launches)
-KERNELS_PER_CALL = {"destr_enc_attn_bwd": 3, "destr_select_queries": 2, "destr_heads_bwd": 2, "destr_split_cross_attn_fwd": 2, "destr_split_cross_attn_bwd_ds": 2,
+KERNELS_PER_CALL = {"destr_enc_attn_bwd": 3, "destr_select_queries": 2, "destr_split_cross_attn_fwd": 2, "destr_split_cross_attn_bwd_ds": 2,
                     "destr_split_cross_attn_bwd_fused": 2}
 launch_count = 0
 # bench.py: {name: []} -> (start, end) CUDA-event pairs are appended around every call of `name`

@@ -283,18 +283,23 @@ extern "C" int destr_heads_fwd(const void* dec, const float* centers, const floa
 extern "C" int destr_heads_bwd(const void* dec, const float* hidden, const float* boxes, const float* dlogits,
                                const float* dboxes, const float* Wc, const float* W1, const float* W2, int C,
                                void* d_dec, float* dh_ws, float* dz_ws, float* dWc, float* dbc, float* dW1,
-                               float* db1, float* dW2, float* db2, int M, void* stream) {
+                               float* db1, float* dW2, float* db2, int M, int which, void* stream) {
   DESTR_CHECK_ARG(dec && hidden && boxes && dlogits && dboxes && Wc && W1 && W2 && d_dec && dh_ws && dz_ws,
                   "null pointer");
+  DESTR_CHECK_ARG(which >= 1 && which <= 3, "which: 1 = row gradients (d_dec, workspaces), 2 = parameter gradients, 3 = both");
   DESTR_CHECK_ARG(dWc && dbc && dW1 && db1 && dW2 && db2, "null gradient pointer");
   DESTR_CHECK_ARG(M > 0 && C > 0 && C <= HMAXC, "shape (1 <= C <= 128)");
   cudaStream_t st = (cudaStream_t)stream;
-  heads_bwd_rows_kernel<<<ceil_div(M, HROWS), 512, 0, st>>>(hidden, boxes, dlogits, dboxes, Wc, W1, W2, C,
-                                                          static_cast<__nv_bfloat16*>(d_dec), dh_ws, dz_ws, M);
-  DESTR_LAUNCH_CHECK();
-  const int blocks = HD / WB + ceil_div(C, WB) + 1;
-  heads_bwd_weights_kernel<<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dec), hidden, dlogits, dh_ws,
-                                                   dz_ws, C, dWc, dbc, dW1, db1, dW2, db2, M);
-  DESTR_LAUNCH_CHECK();
+  if (which & 1) {
+    heads_bwd_rows_kernel<<<ceil_div(M, HROWS), 512, 0, st>>>(hidden, boxes, dlogits, dboxes, Wc, W1, W2, C,
+                                                            static_cast<__nv_bfloat16*>(d_dec), dh_ws, dz_ws, M);
+    DESTR_LAUNCH_CHECK();
+  }
+  if (which & 2) {  // reads the dh / dz workspaces of the row kernel; nothing downstream of d_dec waits for it
+    const int blocks = HD / WB + ceil_div(C, WB) + 1;
+    heads_bwd_weights_kernel<<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dec), hidden, dlogits, dh_ws,
+                                                     dz_ws, C, dWc, dbc, dW1, db1, dW2, db2, M);
+    DESTR_LAUNCH_CHECK();
+  }
   return 0;
 }

@@ -118,5 +118,6 @@ class TransformerHalf(nn.Module):
         grad_out = None
         if self.use_runtime and self._rt.heads_in_flat and torch.is_grad_enabled():
             grad_out = tuple(self._rt.P.g("h." + n) for n in ("cls_w", "cls_b", "box0_w", "box0_b", "box2_w", "box2_b"))
-        cls, boxes = ops.heads(dec, centers, *hp, grad_out=grad_out)
+        cls, boxes = ops.heads(dec, centers, *hp, grad_out=grad_out,
+                               off_path=self._rt.P.off_path if grad_out is not None else None)
         return {"pred_class": cls.view(B, Q, -1), "pred_boxes": boxes.view(B, Q, 4)}, enc.view(B, N, C)

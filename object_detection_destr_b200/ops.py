@@ -385,6 +385,22 @@ def box_refine(delta: Tensor, centers: Tensor) -> Tensor:
     return out
 
 
+def box_head_refine(hidden: Tensor, W2: Tensor, b2: Tensor, centers: Tensor) -> Tensor:
+    """boxes = sigmoid(hidden W2^T + b2 + [logit(centers), 0, 0]): hidden bf16 [M,256] view (post-ReLU output of
+    bbox_embed[0]), W2 fp32 [4,256], b2 fp32 [4], centers fp32 [M,2] -> fp32 [M,4]  (decoder_block.py:51-54)."""
+    _chk(hidden, BF16, "hidden")
+    if hidden.dim() != 2 or hidden.shape[1] != 256 or hidden.stride(1) != 1:
+        raise ValueError("hidden: expected a bf16 [M,256] view with unit column stride")
+    W2 = _chk(W2.contiguous(), torch.float32, "W2")
+    b2 = _chk(b2.contiguous(), torch.float32, "b2")
+    c = _chk(centers.contiguous(), torch.float32, "centers")
+    M = hidden.shape[0]
+    out = torch.empty(M, 4, dtype=torch.float32, device=hidden.device)
+    _lib.call("destr_box_head_refine", hidden.data_ptr(), hidden.stride(0), W2.data_ptr(), b2.data_ptr(), c.data_ptr(),
+              out.data_ptr(), M, _stream())
+    return out
+
+
 def dec_qkv_prep(qkv_obj: Tensor, qk_pos: Tensor, pairs: Tensor, B: int, Q: int):
     """-> head-major (qkv bf16 [3, B, 8, Q, 64], cat bf16 [3, B, 8, Q, 128])."""
     qkv_obj = _chk(qkv_obj.contiguous(), BF16, "qkv_obj")
@@ -622,8 +638,9 @@ class _HeadsFn(torch.autograd.Function):
     """Class + box heads (csrc/heads.cu): one forward launch, two backward launches."""
 
     @staticmethod
-    def forward(ctx, dec, centers, Wc, bc, W1, b1, W2, b2, grad_out=None):
+    def forward(ctx, dec, centers, Wc, bc, W1, b1, W2, b2, grad_out=None, off_path=None):
         ctx.grad_out = grad_out
+        ctx.off_path = off_path
         dec = _chk(dec.contiguous(), BF16, "dec")
         M, C = dec.shape[0], Wc.shape[0]
         if dec.shape[1] != 512 or tuple(W1.shape) != (256, 256) or tuple(W2.shape) != (4, 256) or Wc.shape[1] != 256:
@@ -657,23 +674,33 @@ class _HeadsFn(torch.autograd.Function):
             dWc, dbc = torch.empty(C, 256, **f32), torch.empty(C, **f32)
             dW1, db1 = torch.empty(256, 256, **f32), torch.empty(256, **f32)
             dW2, db2 = torch.empty(4, 256, **f32), torch.empty(4, **f32)
-        _lib.call("destr_heads_bwd", dec.data_ptr(), hidden.data_ptr(), boxes.data_ptr(), dlogits.data_ptr(),
-                  dboxes.data_ptr(), Wc.data_ptr(), W1.data_ptr(), W2.data_ptr(), C, d_dec.data_ptr(), dh.data_ptr(),
-                  dz.data_ptr(), dWc.data_ptr(), dbc.data_ptr(), dW1.data_ptr(), db1.data_ptr(), dW2.data_ptr(),
-                  db2.data_ptr(), M, _stream())
+        def launch(which):
+            _lib.call("destr_heads_bwd", dec.data_ptr(), hidden.data_ptr(), boxes.data_ptr(), dlogits.data_ptr(),
+                      dboxes.data_ptr(), Wc.data_ptr(), W1.data_ptr(), W2.data_ptr(), C, d_dec.data_ptr(), dh.data_ptr(),
+                      dz.data_ptr(), dWc.data_ptr(), dbc.data_ptr(), dW1.data_ptr(), db1.data_ptr(), dW2.data_ptr(),
+                      db2.data_ptr(), M, which, _stream())
+        if ctx.grad_out is not None and ctx.off_path is not None:
+            # the parameter-gradient kernel (57 us running alone) feeds nothing downstream of d_dec: it goes to the
+            # caller's side stream (a parallel branch of the step graph), joined where the caller joins that stream
+            launch(1)
+            ctx.off_path(lambda: launch(2), dec, hidden, dlogits, dh, dz)
+        else:
+            launch(3)
         if ctx.grad_out is not None:
-            return (d_dec,) + (None,) * 8
-        return d_dec, None, dWc, dbc, dW1, db1, dW2, db2, None
+            return (d_dec,) + (None,) * 9
+        return d_dec, None, dWc, dbc, dW1, db1, dW2, db2, None, None
 
 
 def heads(dec: Tensor, centers: Tensor, Wc: Tensor, bc: Tensor, W1: Tensor, b1: Tensor, W2: Tensor, b2: Tensor,
-          grad_out=None):
+          grad_out=None, off_path=None):
     """dec bf16 [M,512] (class stream | box stream), centers fp32 [M,2] -> (logits fp32 [M,C], boxes fp32 [M,4]):
     logits = Linear(Wc, bc)(dec[:, :256]); boxes = sigmoid(Linear(W2,b2)(relu(Linear(W1,b1)(dec[:, 256:]))) +
     [inverse_sigmoid(centers), 0, 0])  (model.py:120-131).  Differentiable w.r.t. dec and the six parameters.
     grad_out = six caller-owned tensors (dWc, dbc, dW1, db1, dW2, db2): backward overwrites them instead of returning
-    parameter gradients to autograd."""
-    return _HeadsFn.apply(dec, centers, Wc, bc, W1, b1, W2, b2, grad_out)
+    parameter gradients to autograd.  off_path (with grad_out): callable (fn, *tensors_to_keep_alive) that runs fn on a side
+    stream the caller joins later (runtime.FlatParams.off_path) -- the parameter-gradient kernel then leaves the
+    critical path."""
+    return _HeadsFn.apply(dec, centers, Wc, bc, W1, b1, W2, b2, grad_out, off_path)
 
 
 class _SetLossFn(torch.autograd.Function):

@@ -596,8 +596,7 @@ class HotPathRuntime:
         # 256 -> 4 output layer stays fp32
         w0, b0 = self._bbox_bf16()
         hbox = _mm_bias_relu(xr, w0, b0)
-        delta = F.linear(hbox.float(), bp[2].weight, bp[2].bias)
-        coords = ops.box_refine(delta, centers)
+        coords = ops.box_head_refine(hbox, bp[2].weight.detach(), bp[2].bias.detach(), centers)  # 256 -> 4 tail + refinement
         pairs = ops.pair_indices(coords.view(B, Q, 4)) if pairs_ov is None else pairs_ov
         P.join(1)
         qkv, cat = ops.dec_qkv_prep(qkv_obj, qkpos_all[:, l * 512:(l + 1) * 512], pairs, B, Q)
