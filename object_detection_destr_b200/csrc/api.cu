@@ -2,6 +2,8 @@
 #include "../../include/destr_b200.h"
 #include "common.cuh"
 
+#include <stdlib.h>
+
 #include <map>
 #include <mutex>
 #include <utility>
@@ -74,6 +76,18 @@ int ensure_dyn_smem(const void* kernel, size_t bytes) {
   }
   have = bytes;
   return 0;
+}
+
+extern int g_knobs[24];  // enc_attn_fwd.cu; knob 16: -1 = read DESTR_PDL from the environment, 0 = off, 1 = on
+bool pdl_enabled() {
+  static int env = -1;
+  if (g_knobs[16] == 0 || g_knobs[16] == 1) return g_knobs[16] == 1;
+  if (env < 0) {
+    const char* e = getenv("DESTR_PDL");
+    env = (e && e[0] == '1') ? 1 : 0;  // default OFF: measured 4.548 ms/step with it vs 4.543 without (the graph's
+                                      // kernel-to-kernel hand-over is already cheaper than the overlapped prologues)
+  }
+  return env == 1;
 }
 
 }  // namespace destr

@@ -7,6 +7,7 @@
 #include <stdio.h>
 
 #include <string>
+#include <utility>
 
 namespace destr {
 
@@ -46,6 +47,32 @@ int ensure_dyn_smem(const void* kernel, size_t bytes);
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Programmatic dependent launch (PDL).  A training step is a chain of several hundred SMALL dependent kernels whose
+// lifetimes are dominated by fixed costs (grid launch, barrier init, TMEM allocation, descriptor prefetch, pipeline
+// fill).  Kernels launched through launch_k() carry cudaLaunchAttributeProgrammaticStreamSerialization: their CTAs may
+// be scheduled while the previous kernel of the stream is still draining, run their prologue, and block in
+// pdl_wait() (griddepcontrol.wait) until that kernel has completed and its memory is visible; every such kernel calls
+// pdl_launch() (griddepcontrol.launch_dependents) once its own prologue is done so that its successor can do the same.
+// Rule for kernels: NO global memory access before pdl_wait().  Under stream capture the dependency becomes a
+// programmatic edge of the CUDA graph.  DESTR_PDL=0 in the environment (or destr_debug_knob(16, 0)) disables the
+// attribute; the device-side instructions are then no-ops.
+bool pdl_enabled();  // api.cu
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 }  // namespace destr
 
 // ------------------------------------------------------------------------------------------------------
@@ -57,6 +84,9 @@ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 // ------------------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
 namespace destr {
+// see launch_k(): wait for the previous kernel of the stream (no-op for a normal launch) / let the next one start launching
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // (seed, site) -> avalanche-mixed base: consecutive seeds (the per-step counter) and neighbouring sites give unrelated
 // tables, not XOR re-indexings of one another.  Loop-invariant in every kernel (hoisted by the compiler).
 __device__ __forceinline__ uint32_t drop_base(uint32_t seed, uint32_t site) {

@@ -10,6 +10,8 @@ constexpr int kSMs = 148;
 
 __global__ void pack_key_mask_kernel(const uint8_t* __restrict__ kpm, uint32_t* __restrict__ bits, int n_keys,
                                      int words_per_row) {
+  pdl_wait();  // (common.cuh: programmatic dependent launch) nothing global is touched before this
+  pdl_launch();
   const int b = blockIdx.y;
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= words_per_row) return;
@@ -34,6 +36,8 @@ constexpr int kMaxW = 512;
 __global__ void __launch_bounds__(128)
 sine_pos2d_kernel(const uint8_t* __restrict__ mask, float* __restrict__ pos_f32, __nv_bfloat16* __restrict__ pos_bf16,
                   int H, int W) {
+  pdl_wait();  // (common.cuh: programmatic dependent launch) nothing global is touched before this
+  pdl_launch();
   __shared__ float s_ye[kMaxW], s_xe[kMaxW];
   const int b = blockIdx.x / H, y = blockIdx.x - b * H;
   const uint8_t* mb = mask + static_cast<size_t>(b) * H * W;
@@ -74,6 +78,8 @@ sine_pos2d_kernel(const uint8_t* __restrict__ mask, float* __restrict__ pos_f32,
 
 __global__ void query_sine_embed_kernel(const float* __restrict__ centers, float* __restrict__ out_f32,
                                         __nv_bfloat16* __restrict__ out_bf16, int M) {
+  pdl_wait();  // (common.cuh: programmatic dependent launch) nothing global is touched before this
+  pdl_launch();
   const int r = blockIdx.x;
   const int c = threadIdx.x;  // 0..127
   const float two_pi = 6.283185307179586f;
@@ -123,6 +129,8 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const F8& f) {
 template <int MODE>
 __global__ void ew3_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ p,
                            const __nv_bfloat16* __restrict__ s, __nv_bfloat16* __restrict__ y, int64_t n8) {
+  pdl_wait();  // (common.cuh: programmatic dependent launch) nothing global is touched before this
+  pdl_launch();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
     F8 r;
     if (MODE == 0) {
@@ -142,6 +150,8 @@ __global__ void ew3_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloa
 __global__ void pos_mul_add_bwd_acc_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ pos,
                                            const __nv_bfloat16* __restrict__ dx_in, __nv_bfloat16* __restrict__ ds,
                                            __nv_bfloat16* __restrict__ dx_out, int64_t n8) {
+  pdl_wait();  // (common.cuh: programmatic dependent launch) nothing global is touched before this
+  pdl_launch();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
     const F8 g = ld8(dy + i * 8), p = ld8(pos + i * 8), r = ld8(dx_in + i * 8);
     F8 a, b;
@@ -166,6 +176,8 @@ __global__ void __launch_bounds__(256)
 relu_bwd_colsum_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ h,
                        __nv_bfloat16* __restrict__ dpre, float* __restrict__ dbias, int M, int C, int lddy, int ldh,
                        int ldo, float scale) {
+  pdl_wait();  // (common.cuh: programmatic dependent launch) nothing global is touched before this
+  pdl_launch();
   __shared__ float red[8][256];
   const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + cg * 8;
@@ -216,6 +228,8 @@ relu_bwd_colsum_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16
 // thread = 8 consecutive channels of one row, one hash per channel pair
 __global__ void __launch_bounds__(256)
 dropout_inplace_kernel(__nv_bfloat16* __restrict__ x, int M, int C, int ld, Drop dp) {
+  pdl_wait();  // (common.cuh: programmatic dependent launch) nothing global is touched before this
+  pdl_launch();
   const uint32_t seed = dp.seed ? *dp.seed : 0u;
   const float s = drop_scale(dp.thr16);
   const int c8 = C / 8;
@@ -250,7 +264,7 @@ extern "C" int destr_pack_key_mask(const uint8_t* kpm, uint32_t* bits, int B, in
                                    void* stream) {
   DESTR_CHECK_ARG(bits && B > 0 && n_keys > 0 && words_per_row * 32 >= n_keys, "shape");
   dim3 grid(ceil_div(words_per_row, 64), B);
-  pack_key_mask_kernel<<<grid, 64, 0, (cudaStream_t)stream>>>(kpm, bits, n_keys, words_per_row);
+  DESTR_CUDA(launch_k(pack_key_mask_kernel, dim3(grid), dim3(64), 0, (cudaStream_t)stream, kpm, bits, n_keys, words_per_row));
   DESTR_LAUNCH_CHECK();
   return 0;
 }
@@ -258,14 +272,14 @@ extern "C" int destr_pack_key_mask(const uint8_t* kpm, uint32_t* bits, int B, in
 extern "C" int destr_sine_pos2d(const uint8_t* mask, float* pos_f32, void* pos_bf16, int B, int H, int W,
                                 void* stream) {
   DESTR_CHECK_ARG(mask && (pos_f32 || pos_bf16) && B > 0 && H > 0 && W > 0 && W <= kMaxW, "shape (W <= 512)");
-  sine_pos2d_kernel<<<B * H, 128, 0, (cudaStream_t)stream>>>(mask, pos_f32, (__nv_bfloat16*)pos_bf16, H, W);
+  DESTR_CUDA(launch_k(sine_pos2d_kernel, dim3(B * H), dim3(128), 0, (cudaStream_t)stream, mask, pos_f32, (__nv_bfloat16*)pos_bf16, H, W));
   DESTR_LAUNCH_CHECK();
   return 0;
 }
 
 extern "C" int destr_query_sine_embed(const float* centers, float* out_f32, void* out_bf16, int M, void* stream) {
   DESTR_CHECK_ARG(centers && (out_f32 || out_bf16) && M > 0, "shape");
-  query_sine_embed_kernel<<<M, 128, 0, (cudaStream_t)stream>>>(centers, out_f32, (__nv_bfloat16*)out_bf16, M);
+  DESTR_CUDA(launch_k(query_sine_embed_kernel, dim3(M), dim3(128), 0, (cudaStream_t)stream, centers, out_f32, (__nv_bfloat16*)out_bf16, M));
   DESTR_LAUNCH_CHECK();
   return 0;
 }
@@ -274,8 +288,8 @@ extern "C" int destr_pos_mul_add_fwd(const void* x, const void* pos, const void*
                                      void* stream) {
   DESTR_CHECK_ARG(x && pos && s && y && n_elem > 0 && n_elem % 8 == 0, "n_elem must be a multiple of 8");
   const int64_t n8 = n_elem / 8;
-  ew3_kernel<0><<<ew_grid(n8, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, (const __nv_bfloat16*)pos, (const __nv_bfloat16*)s, (__nv_bfloat16*)y, n8);
+  DESTR_CUDA(launch_k(ew3_kernel<0>, dim3(ew_grid(n8, 256)), dim3(256), 0, (cudaStream_t)stream, 
+      (const __nv_bfloat16*)x, (const __nv_bfloat16*)pos, (const __nv_bfloat16*)s, (__nv_bfloat16*)y, n8));
   DESTR_LAUNCH_CHECK();
   return 0;
 }
@@ -283,8 +297,8 @@ extern "C" int destr_pos_mul_add_fwd(const void* x, const void* pos, const void*
 extern "C" int destr_pos_mul_add_bwd(const void* dy, const void* pos, void* ds, int64_t n_elem, void* stream) {
   DESTR_CHECK_ARG(dy && pos && ds && n_elem > 0 && n_elem % 8 == 0, "n_elem must be a multiple of 8");
   const int64_t n8 = n_elem / 8;
-  ew3_kernel<1><<<ew_grid(n8, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)dy, (const __nv_bfloat16*)pos, nullptr, (__nv_bfloat16*)ds, n8);
+  DESTR_CUDA(launch_k(ew3_kernel<1>, dim3(ew_grid(n8, 256)), dim3(256), 0, (cudaStream_t)stream, 
+      (const __nv_bfloat16*)dy, (const __nv_bfloat16*)pos, nullptr, (__nv_bfloat16*)ds, n8));
   DESTR_LAUNCH_CHECK();
   return 0;
 }
@@ -292,8 +306,8 @@ extern "C" int destr_pos_mul_add_bwd(const void* dy, const void* pos, void* ds, 
 extern "C" int destr_mul_fwd(const void* a, const void* b, void* y, int64_t n_elem, void* stream) {
   DESTR_CHECK_ARG(a && b && y && n_elem > 0 && n_elem % 8 == 0, "n_elem must be a multiple of 8");
   const int64_t n8 = n_elem / 8;
-  ew3_kernel<2><<<ew_grid(n8, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, nullptr, (__nv_bfloat16*)y, n8);
+  DESTR_CUDA(launch_k(ew3_kernel<2>, dim3(ew_grid(n8, 256)), dim3(256), 0, (cudaStream_t)stream, 
+      (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, nullptr, (__nv_bfloat16*)y, n8));
   DESTR_LAUNCH_CHECK();
   return 0;
 }
@@ -302,9 +316,9 @@ extern "C" int destr_pos_mul_add_bwd_acc(const void* dy, const void* pos, const 
                                          int64_t n_elem, void* stream) {
   DESTR_CHECK_ARG(dy && pos && dx_in && ds && dx_out && n_elem > 0 && n_elem % 8 == 0, "n_elem must be a multiple of 8");
   const int64_t n8 = n_elem / 8;
-  pos_mul_add_bwd_acc_kernel<<<ew_grid(n8, 256), 256, 0, (cudaStream_t)stream>>>(
+  DESTR_CUDA(launch_k(pos_mul_add_bwd_acc_kernel, dim3(ew_grid(n8, 256)), dim3(256), 0, (cudaStream_t)stream, 
       (const __nv_bfloat16*)dy, (const __nv_bfloat16*)pos, (const __nv_bfloat16*)dx_in, (__nv_bfloat16*)ds,
-      (__nv_bfloat16*)dx_out, n8);
+      (__nv_bfloat16*)dx_out, n8));
   DESTR_LAUNCH_CHECK();
   return 0;
 }
@@ -315,12 +329,12 @@ extern "C" int destr_relu_bwd_colsum(const void* dy, int lddy, const void* h, in
   DESTR_CHECK_ARG((h == nullptr) == (dpre == nullptr), "h and dpre go together (both NULL = plain column sum)");
   if (static_cast<int64_t>(M) * C >= (1 << 22)) {  // FFN-sized: fewer, longer blocks (atomics on dbias bound the short ones)
     dim3 grid(ceil_div(C, 256), ceil_div(M, kRowsPerChunk * 4));
-    relu_bwd_colsum_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)dy, (const __nv_bfloat16*)h, (__nv_bfloat16*)dpre, dbias, M, C, lddy, ldh, ldo, scale);
+    DESTR_CUDA(launch_k(relu_bwd_colsum_kernel<4>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, 
+        (const __nv_bfloat16*)dy, (const __nv_bfloat16*)h, (__nv_bfloat16*)dpre, dbias, M, C, lddy, ldh, ldo, scale));
   } else {
     dim3 grid(ceil_div(C, 256), ceil_div(M, kRowsPerChunk));
-    relu_bwd_colsum_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)dy, (const __nv_bfloat16*)h, (__nv_bfloat16*)dpre, dbias, M, C, lddy, ldh, ldo, scale);
+    DESTR_CUDA(launch_k(relu_bwd_colsum_kernel<1>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, 
+        (const __nv_bfloat16*)dy, (const __nv_bfloat16*)h, (__nv_bfloat16*)dpre, dbias, M, C, lddy, ldh, ldo, scale));
   }
   DESTR_LAUNCH_CHECK();
   return 0;
@@ -331,8 +345,8 @@ extern "C" int destr_dropout_inplace(void* x, int ld, int M, int C, const uint32
   DESTR_CHECK_ARG(x && M > 0 && C > 0 && C % 8 == 0 && ld % 8 == 0 && ld >= C, "shape");
   if (drop_thr16 == 0) return 0;
   const int64_t n = static_cast<int64_t>(M) * (C / 8);
-  dropout_inplace_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(
-      (__nv_bfloat16*)x, M, C, ld, destr::Drop{drop_seed, drop_thr16, drop_site});
+  DESTR_CUDA(launch_k(dropout_inplace_kernel, dim3(ew_grid(n, 256)), dim3(256), 0, (cudaStream_t)stream, 
+      (__nv_bfloat16*)x, M, C, ld, destr::Drop{drop_seed, drop_thr16, drop_site}));
   DESTR_LAUNCH_CHECK();
   return 0;
 }

@@ -30,7 +30,7 @@
 #include "sm100_ptx.cuh"
 
 namespace destr {
-extern int g_knobs[16];
+extern int g_knobs[24];
 namespace {
 
 constexpr int DH = 32;

@@ -33,7 +33,8 @@ namespace destr {
 // debug / tuning knobs (destr_debug_knob): 0 v_lbo 1 v_sbo 2 qk_lbo 3 qk_sbo 4 p_kstep_cols 5 v_kstep_bytes
 // 6-8 enc_attn_bwd descriptors, 9 enc fwd polynomial-exp quarter count (0..3), 10 enc bwd ditto,
 // 11 lazy-rescale tau+1, 12/13 grid overrides, 14 enc bwd: launch the main kernel only (bench timing)
-int g_knobs[16] = {512, 512, 16, 512, 8, 1024, 16384, 1024, 2048, 1, 0, 0, 0, 0, 0, 0};
+// 15 gemm_dw split override, 16 programmatic dependent launch: -1 = DESTR_PDL from the environment, 0 off, 1 on
+int g_knobs[24] = {512, 512, 16, 512, 8, 1024, 16384, 1024, 2048, 1, 0, 0, 0, 0, 0, 0, -1, 0, 0, 0, 0, 0, 0, 0};
 
 namespace {
 
@@ -363,7 +364,7 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 }  // namespace destr
 
 extern "C" int destr_debug_knob(int idx, int value) {
-  if (idx < 0 || idx >= 16) return 2;
+  if (idx < 0 || idx >= 24) return 2;
   destr::g_knobs[idx] = value;
   return 0;
 }

@@ -73,6 +73,8 @@ gemm_bias_relu_drop_kernel(const __grid_constant__ CUtensorMap tm_a, const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
+  pdl_wait();    // (common.cuh: programmatic dependent launch) prologue done, global memory is touched from here on
+  pdl_launch();
 
   if (warp == NEPI) {
     // ------------------------------ TMA producer ------------------------------
@@ -218,8 +220,7 @@ extern "C" int destr_linear_bias_relu_dropout(const void* a, int lda, const void
   // balance: no more CTAs per n-block than needed for ceil(mt / gs) tiles each
   gs = ceil_div(mt, ceil_div(mt, gs));
   const int grid = gs * nb;
-  gemm_bias_relu_drop_kernel<<<grid, NTHREADS, smem, static_cast<cudaStream_t>(stream)>>>(
-      ta, tw, bias, static_cast<__nv_bfloat16*>(out), M, N, ldo, relu, Drop{drop_seed, drop_thr16, drop_site});
-  DESTR_LAUNCH_CHECK();
+  DESTR_CUDA(launch_k(gemm_bias_relu_drop_kernel, dim3(grid), dim3(NTHREADS), smem, static_cast<cudaStream_t>(stream), ta, tw,
+                      bias, static_cast<__nv_bfloat16*>(out), M, N, ldo, relu, Drop{drop_seed, drop_thr16, drop_site}));
   return 0;
 }

@@ -29,7 +29,7 @@
 #include "sm100_ptx.cuh"
 
 namespace destr {
-extern int g_knobs[16];
+extern int g_knobs[24];
 namespace {
 #define g_dw_split (::destr::g_knobs[15])
 
@@ -215,6 +215,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
+  pdl_wait();    // prologue done; from here on global memory is touched: the previous kernel must have completed
+  pdl_launch();  // and the next kernel may start its own prologue
 
   if (warp == NEPI) {
     // ------------------------------ TMA producer ------------------------------
@@ -566,6 +568,8 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
+  pdl_wait();
+  pdl_launch();
 
   if (warp == 4) {
     if (elect_one()) {
@@ -641,8 +645,7 @@ int launch_gemm(const void* a, int lda, const void* b, int ldb, const GemmArgs& 
   if (gs < 1) gs = 1;
   if (gs > mt) gs = mt;
   gs = ceil_div(mt, ceil_div(mt, gs));
-  gemm_tc_kernel<BN, B_MN, EPI><<<dim3(gs * nb, batch), NTHREADS, smem, st>>>(ta, tb, ga);
-  DESTR_LAUNCH_CHECK();
+  DESTR_CUDA(launch_k(gemm_tc_kernel<BN, B_MN, EPI>, dim3(gs * nb, batch), dim3(NTHREADS), smem, st, ta, tb, ga));
   return 0;
 }
 
@@ -746,9 +749,8 @@ extern "C" int destr_gemm_dw(const void* dy, int lddy, const void* x, int ldx, i
   if (S > nchunk) S = nchunk;
   const int per = ceil_div(nchunk, S);
   S = ceil_div(nchunk, per);
-  gemm_dw_kernel<<<dim3(tiles, S), DW_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(tdy, tx, dw, lddw, Nout, Kin,
-                                                                                         nchunk, per);
-  DESTR_LAUNCH_CHECK();
+  DESTR_CUDA(launch_k(gemm_dw_kernel, dim3(tiles, S), dim3(DW_THREADS), smem, static_cast<cudaStream_t>(stream), tdy, tx,
+                      dw, lddw, Nout, Kin, nchunk, per));
   return 0;
 }
 

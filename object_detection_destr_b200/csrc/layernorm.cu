@@ -102,6 +102,8 @@ add_ln_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __re
                   const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
                   float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int lda, int ldb, int ldy,
                   Drop dp) {
+  pdl_wait();  // (common.cuh: programmatic dependent launch) nothing global is touched before this
+  pdl_launch();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const Row<VPL> g = ld_vec<VPL>(gamma, lane), be = ld_vec<VPL>(beta, lane);
@@ -137,6 +139,8 @@ add_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __r
                   int lddy, int lda, int ldb, int lddx, float* __restrict__ dbias,
                   const __nv_bfloat16* __restrict__ res_in, __nv_bfloat16* __restrict__ res_out, int ldri, int ldro,
                   Drop dp) {
+  pdl_wait();  // (common.cuh: programmatic dependent launch) nothing global is touched before this
+  pdl_launch();
   constexpr int D = VPL * 32;
   constexpr float invD = 1.0f / D;
   __shared__ float red[3][8][D];  // [dgamma|dbeta|dbias][warp][channel]  (<= 48 KB at D=512)
@@ -149,43 +153,67 @@ add_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __r
   Row<VPL> accg, accb, accx;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) accg.v[i] = accb.v[i] = accx.v[i] = 0.f;
-  for (int row = blockIdx.x * wpb + warp; row < M; row += gridDim.x * wpb) {
-    Row<VPL> x = ld_row<VPL>(a + (size_t)row * lda, lane);
-    if (b) {
-      Row<VPL> r2 = ld_row<VPL>(b + (size_t)row * ldb, lane);
-      if (dp.thr16) drop_row<VPL>(r2, seed, dp.site, row, lane, dp.thr16, ds);
+  // Two rows per warp iteration: every load of both rows is issued before any arithmetic (a warp has only 3-4 rows in
+  // all, so without this the kernel is a chain of exposed memory latencies: 13 us against a 3.5 us bandwidth floor).
+  const int stride = gridDim.x * wpb;
+  for (int row0 = blockIdx.x * wpb + warp; row0 < M; row0 += 2 * stride) {
+    constexpr int NR = 2;
+    int rows[NR];
+    bool ok[NR];
+    Row<VPL> xs[NR], bs[NR], dys[NR], rins[NR];
+    float means[NR], rstds[NR];
 #pragma unroll
-      for (int i = 0; i < VPL; ++i) x.v[i] += r2.v[i];
+    for (int k = 0; k < NR; ++k) {
+      rows[k] = row0 + k * stride;
+      ok[k] = rows[k] < M;
+      const int row = ok[k] ? rows[k] : row0;  // (a valid address; the result is discarded)
+      xs[k] = ld_row<VPL>(a + (size_t)row * lda, lane);
+      if (b) bs[k] = ld_row<VPL>(b + (size_t)row * ldb, lane);
+      dys[k] = ld_row<VPL>(dy + (size_t)row * lddy, lane);
+      if (res_out && res_in) rins[k] = ld_row<VPL>(res_in + (size_t)row * ldri, lane);
+      means[k] = mean_in[row];
+      rstds[k] = rstd_in[row];
     }
-    const Row<VPL> d = ld_row<VPL>(dy + (size_t)row * lddy, lane);
-    const float mean = mean_in[row], rstd = rstd_in[row];
-    float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      x.v[i] = (x.v[i] - mean) * rstd;  // xhat
-      const float gy = d.v[i] * g.v[i];
-      s1 += gy;
-      s2 = fmaf(gy, x.v[i], s2);
-      accg.v[i] = fmaf(d.v[i], x.v[i], accg.v[i]);
-      accb.v[i] += d.v[i];
-    }
-    s1 = warp_sum(s1) * invD;
-    s2 = warp_sum(s2) * invD;
-    Row<VPL> o;  // gradient w.r.t. the LayerNorm input (a + dropout(b)): what flows into the residual stream `a`
+    for (int k = 0; k < NR; ++k) {
+      if (!ok[k]) continue;  // warp-uniform
+      const int row = rows[k];
+      Row<VPL>& x = xs[k];
+      if (b) {
+        Row<VPL>& r2 = bs[k];
+        if (dp.thr16) drop_row<VPL>(r2, seed, dp.site, row, lane, dp.thr16, ds);
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) o.v[i] = rstd * (d.v[i] * g.v[i] - s1 - x.v[i] * s2);
-    Row<VPL> ob = o;  // gradient w.r.t. b: the same, through the dropout mask
-    if (dp.thr16) drop_row<VPL>(ob, seed, dp.site, row, lane, dp.thr16, ds);
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) accx.v[i] += ob.v[i];
-    st_row<VPL>(dx + (size_t)row * lddx, lane, ob);
-    if (res_out) {  // res_out = [res_in +] d(a)  (gradient of the residual stream)
-      if (res_in) {
-        const Row<VPL> r = ld_row<VPL>(res_in + (size_t)row * ldri, lane);
-#pragma unroll
-        for (int i = 0; i < VPL; ++i) o.v[i] += r.v[i];
+        for (int i = 0; i < VPL; ++i) x.v[i] += r2.v[i];
       }
-      st_row<VPL>(res_out + (size_t)row * ldro, lane, o);
+      const Row<VPL>& d = dys[k];
+      const float mean = means[k], rstd = rstds[k];
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        x.v[i] = (x.v[i] - mean) * rstd;  // xhat
+        const float gy = d.v[i] * g.v[i];
+        s1 += gy;
+        s2 = fmaf(gy, x.v[i], s2);
+        accg.v[i] = fmaf(d.v[i], x.v[i], accg.v[i]);
+        accb.v[i] += d.v[i];
+      }
+      s1 = warp_sum(s1) * invD;
+      s2 = warp_sum(s2) * invD;
+      Row<VPL> o;  // gradient w.r.t. the LayerNorm input (a + dropout(b)): what flows into the residual stream `a`
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) o.v[i] = rstd * (d.v[i] * g.v[i] - s1 - x.v[i] * s2);
+      Row<VPL> ob = o;  // gradient w.r.t. b: the same, through the dropout mask
+      if (dp.thr16) drop_row<VPL>(ob, seed, dp.site, row, lane, dp.thr16, ds);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) accx.v[i] += ob.v[i];
+      st_row<VPL>(dx + (size_t)row * lddx, lane, ob);
+      if (res_out) {  // res_out = [res_in +] d(a)  (gradient of the residual stream)
+        if (res_in) {
+#pragma unroll
+          for (int i = 0; i < VPL; ++i) o.v[i] += rins[k].v[i];
+        }
+        st_row<VPL>(res_out + (size_t)row * ldro, lane, o);
+      }
     }
   }
   // block reduction of the parameter gradients, then one atomic per channel per block
@@ -224,6 +252,8 @@ dual_ln_mix_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
                        const float* __restrict__ g1, const float* __restrict__ b1, const float* __restrict__ g2,
                        const float* __restrict__ b2, float lam, __nv_bfloat16* __restrict__ out,
                        float* __restrict__ stats, int M, int Q, Drop dp, uint32_t site2) {
+  pdl_wait();  // (common.cuh: programmatic dependent launch) nothing global is touched before this
+  pdl_launch();
   constexpr int VPL = 16, D = 512;
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
@@ -274,6 +304,8 @@ dual_ln_mix_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat
                        __nv_bfloat16* __restrict__ do2, float* __restrict__ dg1, float* __restrict__ db1,
                        float* __restrict__ dg2, float* __restrict__ db2, int M, int Q, int head_major,
                        float* __restrict__ delta1, float* __restrict__ delta2, Drop dp, uint32_t site2) {
+  pdl_wait();  // (common.cuh: programmatic dependent launch) nothing global is touched before this
+  pdl_launch();
   constexpr int VPL = 16, D = 512;
   constexpr float invD = 1.0f / D;
   extern __shared__ float red[];  // [4][warps][D]
@@ -424,13 +456,13 @@ extern "C" int destr_add_layernorm_fwd(const void* a, int lda, const void* b, in
   DESTR_CHECK_ARG((mean == nullptr) == (rstd == nullptr), "mean and rstd go together");
   cudaStream_t st = (cudaStream_t)stream;
   if (D == 256)
-    add_ln_fwd_kernel<8><<<ln_grid(M), 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, gamma, beta,
+    DESTR_CUDA(launch_k(add_ln_fwd_kernel<8>, dim3(ln_grid(M)), dim3(256), 0, st, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, gamma, beta,
                                                      (__nv_bfloat16*)y, mean, rstd, M, lda, ldb, ldy,
-                                                     DESTR_DROP(drop_seed, drop_thr16, drop_site));
+                                                     DESTR_DROP(drop_seed, drop_thr16, drop_site)));
   else
-    add_ln_fwd_kernel<16><<<ln_grid(M), 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, gamma, beta,
+    DESTR_CUDA(launch_k(add_ln_fwd_kernel<16>, dim3(ln_grid(M)), dim3(256), 0, st, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, gamma, beta,
                                                       (__nv_bfloat16*)y, mean, rstd, M, lda, ldb, ldy,
-                                                      DESTR_DROP(drop_seed, drop_thr16, drop_site));
+                                                      DESTR_DROP(drop_seed, drop_thr16, drop_site)));
   DESTR_LAUNCH_CHECK();
   return 0;
 }
@@ -450,15 +482,15 @@ extern "C" int destr_add_layernorm_bwd(const void* dy, int lddy, const void* a, 
   const __nv_bfloat16* ri = (const __nv_bfloat16*)res_in;
   __nv_bfloat16* ro = (__nv_bfloat16*)res_out;
   if (D == 256)
-    add_ln_bwd_kernel<8><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)a,
+    DESTR_CUDA(launch_k(add_ln_bwd_kernel<8>, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)a,
                                                (const __nv_bfloat16*)b, gamma, mean, rstd, (__nv_bfloat16*)dx, dgamma,
                                                dbeta, M, lddy, lda, ldb, lddx, dbias, ri, ro, ldri, ldro,
-                                               DESTR_DROP(drop_seed, drop_thr16, drop_site));
+                                               DESTR_DROP(drop_seed, drop_thr16, drop_site)));
   else
-    add_ln_bwd_kernel<16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)a,
+    DESTR_CUDA(launch_k(add_ln_bwd_kernel<16>, dim3(grid), dim3(256), 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)a,
                                                 (const __nv_bfloat16*)b, gamma, mean, rstd, (__nv_bfloat16*)dx, dgamma,
                                                 dbeta, M, lddy, lda, ldb, lddx, dbias, ri, ro, ldri, ldro,
-                                                DESTR_DROP(drop_seed, drop_thr16, drop_site));
+                                                DESTR_DROP(drop_seed, drop_thr16, drop_site)));
   DESTR_LAUNCH_CHECK();
   return 0;
 }
@@ -468,9 +500,9 @@ extern "C" int destr_dual_ln_mix_fwd(const void* x, const void* o1, const void* 
                                      void* out, float* stats, int M, int Q, const uint32_t* drop_seed,
                                      uint32_t drop_thr16, uint32_t drop_site1, uint32_t drop_site2, void* stream) {
   DESTR_CHECK_ARG(x && o1 && o2 && pairs && g1 && b1 && g2 && b2 && out && M > 0 && Q > 0, "null pointer / shape");
-  dual_ln_mix_fwd_kernel<<<ln_grid(M), 256, 0, (cudaStream_t)stream>>>(
+  DESTR_CUDA(launch_k(dual_ln_mix_fwd_kernel, dim3(ln_grid(M)), dim3(256), 0, (cudaStream_t)stream, 
       (const __nv_bfloat16*)x, (const __nv_bfloat16*)o1, (const __nv_bfloat16*)o2, pairs, g1, b1, g2, b2, lam,
-      (__nv_bfloat16*)out, stats, M, Q, DESTR_DROP(drop_seed, drop_thr16, drop_site1), drop_site2);
+      (__nv_bfloat16*)out, stats, M, Q, DESTR_DROP(drop_seed, drop_thr16, drop_site1), drop_site2));
   DESTR_LAUNCH_CHECK();
   return 0;
 }
@@ -487,10 +519,10 @@ extern "C" int destr_dual_ln_mix_bwd(const void* dout, const void* x, const void
   const int threads = 128;  // 4 warps -> 4*4*512*4 B = 32 KB of reduction scratch
   int grid = ceil_div(M, 4);
   if (grid > kSMs * 2) grid = kSMs * 2;
-  dual_ln_mix_bwd_kernel<<<grid, threads, 4 * 4 * 512 * sizeof(float), (cudaStream_t)stream>>>(
+  DESTR_CUDA(launch_k(dual_ln_mix_bwd_kernel, dim3(grid), dim3(threads), 4 * 4 * 512 * sizeof(float), (cudaStream_t)stream, 
       (const __nv_bfloat16*)dout, (const __nv_bfloat16*)x, (const __nv_bfloat16*)o1, (const __nv_bfloat16*)o2, pairs,
       g1, g2, stats, lam, (__nv_bfloat16*)dx, (__nv_bfloat16*)do1, (__nv_bfloat16*)do2, dg1, db1, dg2, db2, M, Q,
-      head_major, delta1, delta2, DESTR_DROP(drop_seed, drop_thr16, drop_site1), drop_site2);
+      head_major, delta1, delta2, DESTR_DROP(drop_seed, drop_thr16, drop_site1), drop_site2));
   DESTR_LAUNCH_CHECK();
   return 0;
 }
