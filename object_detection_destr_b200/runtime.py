@@ -36,6 +36,12 @@ import os as _os
 _FUSED_FFN1 = _os.environ.get("DESTR_FUSED_FFN1", "1") == "1"
 # encoder projections / FFN / dX / dW on the tcgen05 GEMM family (csrc/gemm_tc.cu) instead of cuBLAS; "0" = library path
 _TC = _os.environ.get("DESTR_TC_GEMM", "1") == "1"
+# the decoder's projections / FFNs / dX products on the same family (M = B*Q = 800 rows)
+# "1": only where an epilogue fusion removes a kernel (ps2 * sine, fc1 + dropout, ReLU-backward + bias gradient);
+# "2": every decoder GEMM (measured slower than the library for the plain 800-row products: 4.69 vs 4.61 ms/step)
+_TC_DEC_LEVEL = int(_os.environ.get("DESTR_TC_DEC", "1")) if _TC else 0
+_TC_DEC = _TC_DEC_LEVEL >= 1     # fused members
+_TC_DEC_ALL = _TC_DEC_LEVEL >= 2  # plain members too
 # out-proj / fc2 with dropout + residual + LayerNorm(s) in the GEMM epilogue (needs _TC).  Parity-green, but OFF by
 # default: a CTA must own whole 256-wide rows, so at M = 8400 only 66 CTAs run and the 5-pass epilogue costs more than
 # the two row-wise kernels it replaces (measured in situ: 4.97 ms/step with it, 4.77 without)
@@ -567,10 +573,13 @@ class HotPathRuntime:
         P = self.P
         P.off_path(lambda: ops.relu_bwd_colsum(ds, None, P.g(pfx + ".ps2_b")), ds)
         P.acc_gw(pfx + ".ps2_w", ds, h1)
-        if _TC and pfx == "e":
+        if (_TC and pfx == "e") or (_TC_DEC and pfx == "d"):
             dpre = ops.gemm_relu_bwd(ds, P.w(pfx + ".ps2_w"), h1, 1.0, P.g(pfx + ".ps0_b"))
             P.acc_gw(pfx + ".ps0_w", dpre, xin)
-            ops.gemm(dpre, P.w(pfx + ".ps0_w"), b_kn=True, add=dx_acc, out=dx_acc)
+            if pfx == "e" or _TC_DEC_ALL:
+                ops.gemm(dpre, P.w(pfx + ".ps0_w"), b_kn=True, add=dx_acc, out=dx_acc)
+            else:
+                dx_acc.addmm_(dpre, P.w(pfx + ".ps0_w"))
             return dx_acc
         dh = torch.mm(ds, P.w(pfx + ".ps2_w"))
         dpre = ops.relu_bwd_colsum(dh, h1, P.g(pfx + ".ps0_b"))
@@ -584,18 +593,24 @@ class HotPathRuntime:
         xr = x[:, 256:]
         # three independent chains start from the layer input; only the box -> pairing chain is on the critical path
         with P.fork(_FORK["DEC_HEAD"], k=0):  # query-position chain: pos_scale MLP -> sin -> its cross-attention projection
-            t1 = _mm_bias_relu(xr, P.w("d.ps0_w"), P.w("d.ps0_b"))
-            t2 = _mm_bias(t1, P.w("d.ps2_w"), P.w("d.ps2_b"))
-            sin = ops.mul(t2, sine)
-            qp = torch.mm(sin, P.w(f"d{l}.cqp_w").t())
+            if _TC_DEC:
+                t1 = ops.gemm(xr, P.w("d.ps0_w"), bias=P.f("d.ps0_b"), relu=True) if _TC_DEC_ALL else \
+                    _mm_bias_relu(xr, P.w("d.ps0_w"), P.w("d.ps0_b"))
+                sin = ops.gemm(t1, P.w("d.ps2_w"), bias=P.f("d.ps2_b"), mul=sine)   # pos_scale(x_reg) * sine embedding
+                qp = ops.gemm(sin, P.w(f"d{l}.cqp_w")) if _TC_DEC_ALL else torch.mm(sin, P.w(f"d{l}.cqp_w").t())
+            else:
+                t1 = _mm_bias_relu(xr, P.w("d.ps0_w"), P.w("d.ps0_b"))
+                t2 = _mm_bias(t1, P.w("d.ps2_w"), P.w("d.ps2_b"))
+                sin = ops.mul(t2, sine)
+                qp = torch.mm(sin, P.w(f"d{l}.cqp_w").t())
         with P.fork(_FORK["DEC_HEAD"], k=1):  # packed q|k|v object projection
-            qkv_obj = torch.mm(x, P.w(f"d{l}.q_w", rows=1536).t())
+            qkv_obj = ops.gemm(x, P.w(f"d{l}.q_w", rows=1536)) if _TC_DEC_ALL else torch.mm(x, P.w(f"d{l}.q_w", rows=1536).t())
         bp = self.bbox
         # box refinement of the layer's queries: feeds ONLY the pairing (arg-max indices) and its input is already bf16,
         # so the 256x256 layer runs as a bf16 tensor-core GEMM (bias + ReLU fused) instead of an fp32 SIMT one; the
         # 256 -> 4 output layer stays fp32
         w0, b0 = self._bbox_bf16()
-        hbox = _mm_bias_relu(xr, w0, b0)
+        hbox = ops.gemm(xr, w0, bias=bp[0].bias.detach(), relu=True) if _TC_DEC_ALL else _mm_bias_relu(xr, w0, b0)
         coords = ops.box_head_refine(hbox, bp[2].weight.detach(), bp[2].bias.detach(), centers)  # 256 -> 4 tail + refinement
         pairs = ops.pair_indices(coords.view(B, Q, 4)) if pairs_ov is None else pairs_ov
         P.join(1)
@@ -605,7 +620,7 @@ class HotPathRuntime:
         o, st = ops.dual_ln_mix(x, o1, o2, pairs, P.f(f"d{l}.n1_w"), P.f(f"d{l}.n1_b"), P.f(f"d{l}.n2_w"),
                                 P.f(f"d{l}.n2_b"), lam, Q,
                                 drop=self._d(dc["d.d1"], dec_site(l, "d1a"), dec_site(l, "d1b")))
-        qo = torch.mm(o, P.w(f"d{l}.cq_w").t())
+        qo = ops.gemm(o, P.w(f"d{l}.cq_w")) if _TC_DEC_ALL else torch.mm(o, P.w(f"d{l}.cq_w").t())
         P.join(0)
         ke, vv = kv_all[:, l * 512:l * 512 + 256], kv_all[:, l * 512 + 256:(l + 1) * 512]
         kp = kpos_all[:, l * 256:(l + 1) * 256]
@@ -617,9 +632,15 @@ class HotPathRuntime:
             with P.fork(i == 1):
                 xb, mb1, rb1 = ops.add_layernorm(o[:, sl], ca[:, sl], P.f(f"d{l}.b{i}.n1_w"), P.f(f"d{l}.b{i}.n1_b"),
                                                  save_stats=True, drop=self._d(dc["d.br"], dec_site(l, f"b{i}.d_ca")))
-                f = _mm_bias_relu(xb, P.w(f"d{l}.b{i}.fc1_w"), P.w(f"d{l}.b{i}.fc1_b"))
-                ops.dropout_inplace(f, self._d(dc["d.br"], dec_site(l, f"b{i}.d_relu")))
-                g = _mm_bias(f, P.w(f"d{l}.b{i}.fc2_w"), P.w(f"d{l}.b{i}.fc2_b"))
+                if _TC_DEC:  # fc1 + bias + ReLU + dropout in one tcgen05 GEMM, fc2 on the family too
+                    f = ops.linear_bias_relu_dropout(xb, P.w(f"d{l}.b{i}.fc1_w"), P.f(f"d{l}.b{i}.fc1_b"),
+                                                     self._d(dc["d.br"], dec_site(l, f"b{i}.d_relu")))
+                    g = ops.gemm(f, P.w(f"d{l}.b{i}.fc2_w"), bias=P.f(f"d{l}.b{i}.fc2_b")) if _TC_DEC_ALL else \
+                        _mm_bias(f, P.w(f"d{l}.b{i}.fc2_w"), P.w(f"d{l}.b{i}.fc2_b"))
+                else:
+                    f = _mm_bias_relu(xb, P.w(f"d{l}.b{i}.fc1_w"), P.w(f"d{l}.b{i}.fc1_b"))
+                    ops.dropout_inplace(f, self._d(dc["d.br"], dec_site(l, f"b{i}.d_relu")))
+                    g = _mm_bias(f, P.w(f"d{l}.b{i}.fc2_w"), P.w(f"d{l}.b{i}.fc2_b"))
                 _, mb2, rb2 = ops.add_layernorm(xb, g, P.f(f"d{l}.b{i}.n2_w"), P.f(f"d{l}.b{i}.n2_b"), save_stats=True,
                                                 out=y[:, sl], drop=self._d(dc["d.br"], dec_site(l, f"b{i}.d_fc2")))
             br_saved.append((xb, mb1, rb1, f, g, mb2, rb2))
@@ -647,10 +668,17 @@ class HotPathRuntime:
                                            drop=self._d(dc["d.br"], dec_site(l, f"b{i}.d_fc2")), want_sum=bool(dc["d.br"]))
                 d2, d2s = r_[0], (r_[3] if dc["d.br"] else r_[0])
                 P.acc_gw(pf + "fc2_w", d2, f)
-                df = torch.mm(d2, P.w(pf + "fc2_w"))
-                dpre = ops.relu_bwd_colsum(df, f, P.g(pf + "fc1_b"), scale=_drop_scale(dc["d.br"]))
-                P.acc_gw(pf + "fc1_w", dpre, xb)
-                dxb = torch.addmm(d2s, dpre, P.w(pf + "fc1_w"))
+                if _TC_DEC:
+                    df = None
+                    dpre = ops.gemm_relu_bwd(d2, P.w(pf + "fc2_w"), f, _drop_scale(dc["d.br"]), P.g(pf + "fc1_b"))
+                    P.acc_gw(pf + "fc1_w", dpre, xb)
+                    dxb = ops.gemm(dpre, P.w(pf + "fc1_w"), b_kn=True, add=d2s) if _TC_DEC_ALL else \
+                        torch.addmm(d2s, dpre, P.w(pf + "fc1_w"))
+                else:
+                    df = torch.mm(d2, P.w(pf + "fc2_w"))
+                    dpre = ops.relu_bwd_colsum(df, f, P.g(pf + "fc1_b"), scale=_drop_scale(dc["d.br"]))
+                    P.acc_gw(pf + "fc1_w", dpre, xb)
+                    dxb = torch.addmm(d2s, dpre, P.w(pf + "fc1_w"))
                 ops.add_layernorm_bwd(dxb, o[:, sl], ca[:, sl], P.f(pf + "n1_w"), mb1, rb1, dgamma=P.g(pf + "n1_w"),
                                       dbeta=P.g(pf + "n1_b"), dx_out=dca[:, sl],
                                       drop=self._d(dc["d.br"], dec_site(l, f"b{i}.d_ca")), want_sum=bool(dc["d.br"]),
@@ -664,11 +692,16 @@ class HotPathRuntime:
             dkp_out=d_kpos_all[:, l * 256:(l + 1) * 256], dv_out=d_kv_all[:, l * 512 + 256:(l + 1) * 512],
             drop=self._d(dc["d.ca"], dec_site(l, "ca")))
         P.acc_gw(f"d{l}.cq_w", dqo, o)
-        do = torch.addmm(dres, dqo, P.w(f"d{l}.cq_w"))   # d(o) = d(o_cls|o_reg residual) + dq_obj W
+        # d(o) = d(o_cls|o_reg residual) + dq_obj W
+        do = ops.gemm(dqo, P.w(f"d{l}.cq_w"), b_kn=True, add=dres) if _TC_DEC_ALL else torch.addmm(dres, dqo, P.w(f"d{l}.cq_w"))
         P.acc_gw(f"d{l}.cqp_w", dqp, sin)
         with P.fork(_FORK["DSIN"], k=0):  # sin = sine * pos_scale(x_reg): independent of the self/pair-attention chain below
-            dsin = torch.mm(dqp, P.w(f"d{l}.cqp_w"))
-            dt2 = ops.mul(dsin, sine)
+            if _TC_DEC:
+                dsin = None
+                dt2 = ops.gemm(dqp, P.w(f"d{l}.cqp_w"), b_kn=True, mul=sine)
+            else:
+                dsin = torch.mm(dqp, P.w(f"d{l}.cqp_w"))
+                dt2 = ops.mul(dsin, sine)
             xr = x[:, 256:]
             dxr = torch.zeros(x.shape[0], 256, dtype=BF16, device=x.device)
             self._pos_scale_bwd("d", dt2, t1, xr, dxr)
@@ -682,7 +715,10 @@ class HotPathRuntime:
         d_qkv_obj, _ = ops.dec_qkv_prep_bwd(d_qkv, d_cat, pairs, B, Q,
                                             d_pos_out=d_qkpos_all[:, l * 512:(l + 1) * 512])
         P.acc_gw(f"d{l}.q_w", d_qkv_obj, x, rows=1536)
-        dx.addmm_(d_qkv_obj, P.w(f"d{l}.q_w", rows=1536))
+        if _TC_DEC_ALL:
+            ops.gemm(d_qkv_obj, P.w(f"d{l}.q_w", rows=1536), b_kn=True, add=dx, out=dx)
+        else:
+            dx.addmm_(d_qkv_obj, P.w(f"d{l}.q_w", rows=1536))
         P.join(0)
         dx[:, 256:] += dxr
         P._keep += [dsin, dt2, dxr]
@@ -710,9 +746,14 @@ class HotPathRuntime:
             hfp = _mm_bias_relu(enc, P.w("e.ps0_w"), P.w("e.ps0_b"))
             fine = ops.mul(_mm_bias(hfp, P.w("e.ps2_w"), P.w("e.ps2_b")), pos)
         # projections of layer-invariant inputs for ALL decoder layers: three packed GEMMs
-        kv_all = torch.mm(enc, P.w("d0.ke_w", rows=Ld * 512).t())
-        kpos_all = torch.mm(fine, P.w("d0.kp_w", rows=Ld * 256).t())
-        qkpos_all = torch.mm(pos_embed, P.w("d0.sqp_w", rows=Ld * 512).t())
+        if _TC_DEC_ALL:
+            kv_all = ops.gemm(enc, P.w("d0.ke_w", rows=Ld * 512))
+            kpos_all = ops.gemm(fine, P.w("d0.kp_w", rows=Ld * 256))
+            qkpos_all = ops.gemm(pos_embed, P.w("d0.sqp_w", rows=Ld * 512))
+        else:
+            kv_all = torch.mm(enc, P.w("d0.ke_w", rows=Ld * 512).t())
+            kpos_all = torch.mm(fine, P.w("d0.kp_w", rows=Ld * 256).t())
+            qkpos_all = torch.mm(pos_embed, P.w("d0.sqp_w", rows=Ld * 512).t())
         dec_saved = []
         y = sel
         for l in range(Ld):
@@ -739,9 +780,11 @@ class HotPathRuntime:
         for l in reversed(range(Ld)):
             dy = self._dec_bwd(l, dy, dec_saved[l], ctx, d_kv_all, d_kpos_all, d_qkpos_all)
         P.acc_gw("d0.ke_w", d_kv_all, enc, rows=Ld * 512)
-        d_enc = torch.mm(d_kv_all, P.w("d0.ke_w", rows=Ld * 512))
+        d_enc = ops.gemm(d_kv_all, P.w("d0.ke_w", rows=Ld * 512), b_kn=True) if _TC_DEC_ALL else \
+            torch.mm(d_kv_all, P.w("d0.ke_w", rows=Ld * 512))
         P.acc_gw("d0.kp_w", d_kpos_all, fine, rows=Ld * 256)
-        d_fine = torch.mm(d_kpos_all, P.w("d0.kp_w", rows=Ld * 256))
+        d_fine = ops.gemm(d_kpos_all, P.w("d0.kp_w", rows=Ld * 256), b_kn=True) if _TC_DEC_ALL else \
+            torch.mm(d_kpos_all, P.w("d0.kp_w", rows=Ld * 256))
         P.acc_gw("d0.sqp_w", d_qkpos_all, pos_embed, rows=Ld * 512)
         P.reduce_decoder_grads()  # data parallel: the decoder's gradients are final -> exchange them under the encoder backward
         du = ops.mul(d_fine, pos)
