@@ -191,6 +191,7 @@ cross_attn_bwd_ds_kernel(const __grid_constant__ CUtensorMap tm_qobj, const __gr
 // TMA ring: 3 stages of (A 16 KB, B 16 KB); phases 2-3 stream single B chunks through the same ring.
 // ------------------------------------------------------------------------------------------------
 constexpr int NSTAGE_F = 3;
+constexpr int NTHREADS_F = 320;  // 8 math warps + TMA warp + MMA warp
 struct __align__(1024) SmemF {
   uint8_t a[NSTAGE_F][CHUNK_BYTES];
   uint8_t b[NSTAGE_F][CHUNK_BYTES];
@@ -205,7 +206,7 @@ struct __align__(1024) SmemF {
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS_F, 1)
 cross_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qobj, const __grid_constant__ CUtensorMap tm_qpos,
                             const __grid_constant__ CUtensorMap tm_kenc, const __grid_constant__ CUtensorMap tm_kpos,
                             const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
@@ -223,26 +224,26 @@ cross_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qobj, const _
   constexpr int NS = NSTAGE_F;
   constexpr int T1 = 24, T2 = 16, T3 = 4;  // ring entries of the three phases
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     for (int s = 0; s < NS; ++s) {
       mbar_init(&sm.full[s], 1);
       mbar_init(&sm.empty[s], 1);
     }
     mbar_init(&sm.sdp_full[0], 1);
     mbar_init(&sm.sdp_full[1], 1);
-    mbar_init(&sm.tiles_full, 128);
+    mbar_init(&sm.tiles_full, 256);
     mbar_init(&sm.g_full[0], 1);
     mbar_init(&sm.g_full[1], 1);
-    mbar_init(&sm.g_drained, 128);
+    mbar_init(&sm.g_drained, 256);
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc<512>(&sm.tmem_base);
+  if (warp == 9) tmem_alloc<512>(&sm.tmem_base);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (elect_one()) {
       for (int t = 0; t < T1 + T2 + T3; ++t) {
         const int s = t % NS;
@@ -275,7 +276,7 @@ cross_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qobj, const _
       }
     }
     __syncwarp();
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(BT, BT, false, false);
       constexpr uint32_t id_nn = umma_idesc_bf16(BT, 64, true, true);     // A MN-major (tile), B MN-major, N = 64
@@ -331,7 +332,9 @@ cross_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qobj, const _
     }
     __syncwarp();
   } else {
-    const int wq = warp;
+    // 8 math warps: warps w and w + 4 own the same 32 TMEM lanes (rows) and split the columns, so the per-thread
+    // instruction stream of the softmax backward and of the drains is half as long (the kernel is a latency chain)
+    const int wq = warp & 3, ch = warp >> 2;
     const uint32_t lane_addr = static_cast<uint32_t>(wq * 32) << 16;
     const int r = wq * 32 + lane;  // query row (phase 1) / key row of the tile (drains)
     const int q = r;
@@ -339,8 +342,7 @@ cross_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qobj, const _
     const uint32_t drop_seed = (dp.thr16 && dp.seed) ? *dp.seed : 0u;
     const float drop_s = drop_scale(dp.thr16);
     const uint4 mw = *reinterpret_cast<const uint4*>(mask_bits + static_cast<size_t>(b) * words_per_row + j * 4);
-    const uint32_t mwa[4] = {mw.x, mw.y, mw.z, mw.w};
-    uint32_t stash[4][16];  // packed dS of branch 0
+    uint32_t stash[2][16];  // packed dS of branch 0 (this thread's two 32-key chunks)
 #pragma unroll
     for (int br = 0; br < 2; ++br) {
       const float l2 = qvalid ? lse[(static_cast<size_t>(b) * 2 + br) * Q + q] : INFINITY;
@@ -352,7 +354,9 @@ cross_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qobj, const _
       __nv_bfloat16* srow = dS_sum + (static_cast<size_t>(b) * Q + (qvalid ? q : 0)) * Np + j * BT;
       const uint32_t a_p = smem_u32(sm.p[br][0]), a_ds = smem_u32(sm.ds[br][0]);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = ch * 2 + cc;  // 32-key chunk of the tile
+        const uint32_t mword = ch == 0 ? (cc == 0 ? mw.x : mw.y) : (cc == 0 ? mw.z : mw.w);
         uint32_t s[32], d[32];
         tmem_ld_x32(tmem + lane_addr + br * 256 + c * 32, s);
         tmem_ld_x32(tmem + lane_addr + br * 256 + 128 + c * 32, d);
@@ -368,7 +372,7 @@ cross_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qobj, const _
           for (int e = 0; e < 2; ++e) {
             const int k = 2 * i + e;
             float pr = ex2_approx(fmaf(__uint_as_float(s[k]), scale_log2, -l2));
-            pr = ((mwa[c] >> k) & 1u) ? 0.f : pr;
+            pr = ((mword >> k) & 1u) ? 0.f : pr;
             const float keep = (((bits >> (16 * e)) & 0xFFFFu) >= dp.thr16) ? drop_s : 0.f;
             pv[e] = pr * keep;
             dv_[e] = pr * (__uint_as_float(d[k]) * keep - dl) * scale;
@@ -376,9 +380,9 @@ cross_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qobj, const _
           pp[i] = pack_bf16x2(pv[0], pv[1]);
           dd[i] = pack_bf16x2(dv_[0], dv_[1]);
           if (br == 0) {
-            stash[c][i] = dd[i];
+            stash[cc][i] = dd[i];
           } else {
-            const uint32_t o = stash[c][i];
+            const uint32_t o = stash[cc][i];
             ss[i] = pack_bf16x2(dv_[0] + __uint_as_float(o << 16), dv_[1] + __uint_as_float(o & 0xffff0000u));
           }
         }
@@ -408,9 +412,9 @@ cross_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qobj, const _
     const int key = j * BT + r;
     const bool kvalid = key < N;
     const size_t grow = static_cast<size_t>(b) * N + (kvalid ? key : 0);
-    auto drain = [&](uint32_t col, __nv_bfloat16* dst) {
+    auto drain = [&](uint32_t col, __nv_bfloat16* dst) {  // this thread: 128 of the row's 256 columns
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = ch * 4; c < ch * 4 + 4; ++c) {
         uint32_t v[32];
         tmem_ld_x32(tmem + lane_addr + col + c * 32, v);
         tc_wait_ld();
@@ -439,7 +443,7 @@ cross_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qobj, const _
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc<512>(tmem);
+  if (warp == 9) tmem_dealloc<512>(tmem);
 }
 
 // delta[b, br, q] = sum_c dO[b*Q+q, br*256+c] * O[b*Q+q, br*256+c]   (one warp per query row)
@@ -541,7 +545,7 @@ extern "C" int destr_split_cross_attn_bwd_fused(const void* q_obj, const void* q
   cross_delta_kernel<<<ceil_div((int)qrows, 8), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(out),
                                                               static_cast<const __nv_bfloat16*>(dout), delta, B, Q);
   DESTR_LAUNCH_CHECK();
-  cross_attn_bwd_fused_kernel<<<dim3(nkv, B), NTHREADS, smem, st>>>(
+  cross_attn_bwd_fused_kernel<<<dim3(nkv, B), NTHREADS_F, smem, st>>>(
       tqo, tqp, tke, tkp, tv, tdo, mask_bits, words_per_row, lse, delta, static_cast<__nv_bfloat16*>(dS_all),
       static_cast<__nv_bfloat16*>(dS_sum), static_cast<__nv_bfloat16*>(dk_enc), ld_dke,
       static_cast<__nv_bfloat16*>(dk_pos), ld_dkp, static_cast<__nv_bfloat16*>(dv), ld_dv, Q, N, nkv * BT, scale,

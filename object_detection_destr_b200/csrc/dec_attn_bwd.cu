@@ -217,6 +217,8 @@ struct ParamsF {
   Drop dp;
 };
 
+constexpr int NTHREADS_F = 320;  // fused kernel: 8 math warps + TMA warp + MMA warp
+
 template <int D>
 __device__ __forceinline__ void body_fused(SmemF& sm, const CUtensorMap* tm_q, const CUtensorMap* tm_k,
                                            const CUtensorMap* tm_v, const CUtensorMap* tm_do,
@@ -229,7 +231,7 @@ __device__ __forceinline__ void body_fused(SmemF& sm, const CUtensorMap* tm_q, c
   const int hrow = (b * 8 + h) * Q;
   constexpr uint32_t C_DP = 128, C_DQ = 256, C_DK = 0, C_DV = 128;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (elect_one()) {
       mbar_arrive_expect_tx(&sm.qk_full, 2 * NCH * CHUNK_BYTES);
       for (int c = 0; c < NCH; ++c) tma_load_2d(sm.q[c], tm_q, &sm.qk_full, c * 64, hrow);
@@ -239,7 +241,7 @@ __device__ __forceinline__ void body_fused(SmemF& sm, const CUtensorMap* tm_q, c
       for (int c = 0; c < NCH; ++c) tma_load_2d(sm.v[c], tm_v, &sm.dov_full, c * 64, hrow);
     }
     __syncwarp();
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (elect_one()) {
       constexpr uint32_t id_kk = umma_idesc_bf16(BT, BT, false, false);  // K-major x K-major, N = 128
       constexpr uint32_t id_kn = umma_idesc_bf16(BT, 64, false, true);   // A K-major, B MN-major, N = 64
@@ -282,7 +284,9 @@ __device__ __forceinline__ void body_fused(SmemF& sm, const CUtensorMap* tm_q, c
     }
     __syncwarp();
   } else {
-    const int wq = warp;
+    // 8 math warps: warps w and w + 4 own the same TMEM lanes (rows) and split the columns (half the instruction
+    // stream per thread: the kernel is one latency chain per CTA)
+    const int wq = warp & 3, ch = warp >> 2;
     const uint32_t lane_addr = static_cast<uint32_t>(wq * 32) << 16;
     const int r = wq * 32 + lane;  // query row in the softmax phase, output row (query / key) in the epilogue
     const bool valid = r < Q;
@@ -294,7 +298,8 @@ __device__ __forceinline__ void body_fused(SmemF& sm, const CUtensorMap* tm_q, c
     mbar_wait(&sm.s_full, 0, 74);
     tc_fence_after();
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int cc = 0; cc < 2; ++cc) {
+      const int c = ch * 2 + cc;
       uint32_t s[32], d[32];
       tmem_ld_x32(tmem + lane_addr + c * 32, s);
       tmem_ld_x32(tmem + lane_addr + C_DP + c * 32, d);
@@ -339,7 +344,8 @@ __device__ __forceinline__ void body_fused(SmemF& sm, const CUtensorMap* tm_q, c
       const uint32_t col = (w == 0 ? C_DQ : (w == 1 ? C_DK : C_DV));
       __nv_bfloat16* dst = (w == 0 ? dq_out : (w == 1 ? dk_out : dv_out)) + orow;
 #pragma unroll
-      for (int c = 0; c < D / 32; ++c) {
+      for (int cc = 0; cc < D / 64; ++cc) {
+        const int c = ch * (D / 64) + cc;  // this thread's half of the row
         uint32_t v[32];
         tmem_ld_x32(tmem + lane_addr + col + c * 32, v);
         tc_wait_ld();
@@ -359,7 +365,7 @@ __device__ __forceinline__ void body_fused(SmemF& sm, const CUtensorMap* tm_q, c
   }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS_F, 1)
 dec_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tq1, const __grid_constant__ CUtensorMap tk1,
                           const __grid_constant__ CUtensorMap tv1, const __grid_constant__ CUtensorMap td1,
                           const __grid_constant__ CUtensorMap tq2, const __grid_constant__ CUtensorMap tk2,
@@ -367,15 +373,15 @@ dec_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tq1, const __grid_
   extern __shared__ uint8_t smem_raw[];
   SmemF& sm = *reinterpret_cast<SmemF*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     mbar_init(&sm.qk_full, 1);
     mbar_init(&sm.dov_full, 1);
     mbar_init(&sm.s_full, 1);
-    mbar_init(&sm.p_full, 128);
+    mbar_init(&sm.p_full, 256);
     mbar_init(&sm.g_full, 1);
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc<512>(&sm.tmem_base);
+  if (warp == 9) tmem_alloc<512>(&sm.tmem_base);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -390,7 +396,7 @@ dec_attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tq1, const __grid_
                     p.dcat + 2 * p.rows * 1024, p.Q, hy - 8, b, log2e, r, r, 1.f, tmem, Drop{nullptr, 0u, 0u});
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc<512>(tmem);
+  if (warp == 9) tmem_dealloc<512>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -539,7 +545,7 @@ extern "C" int destr_dec_self_pair_attn_bwd(const void* qkv, const void* cat, co
   DESTR_SMEM_OPTIN(dec_attn_bwd_fused_kernel, smem);
   ParamsF p{lse1, lse2, delta1, delta2, static_cast<__nv_bfloat16*>(d_qkv), static_cast<__nv_bfloat16*>(d_cat), Q,
             static_cast<size_t>(rows), Drop{drop_seed, drop_thr16, drop_site}};
-  dec_attn_bwd_fused_kernel<<<dim3(16, B), NTHREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+  dec_attn_bwd_fused_kernel<<<dim3(16, B), NTHREADS_F, smem, static_cast<cudaStream_t>(stream)>>>(
       t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], p);
   DESTR_LAUNCH_CHECK();
   return 0;
