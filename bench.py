@@ -400,7 +400,7 @@ def run_ours(args):
         dom = "destr_enc_attn_bwd" if t_b >= t_f else "destr_enc_attn_fwd"
         ach = (bwd_flops / t_b if dom.endswith("bwd") else fwd_flops / t_f) / 1e9
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
         if os.path.exists(tp):
             with open(tp) as f:
                 tj = json.load(f)

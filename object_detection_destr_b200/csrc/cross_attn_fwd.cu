@@ -14,7 +14,8 @@
 // and stores the un-normalised partial (O fp32, m, l).  cross_attn_combine_kernel merges the key
 // tiles:  out = sum_j 2^(m_j-M) O_j / sum_j 2^(m_j-M) l_j.   (split-KV: the decoder has only
 // 2*ceil(Q/128)*B query tiles, far fewer than 148 SMs.)
-// warps 0-3 softmax/epilogue (thread <-> query row <-> TMEM lane), warp 4 TMA, warp 5 MMA.
+// warps 0-7 softmax/epilogue (thread <-> query row x half of the key columns: warps w and w+4 own the same TMEM lanes and
+// exchange the row maximum / row sum through shared memory), warp 8 TMA, warp 9 MMA.
 #include "../../include/destr_b200.h"
 #include "common.cuh"
 #include "sm100_ptx.cuh"
@@ -26,7 +27,7 @@ constexpr int BT = 128;
 constexpr int NSTAGE = 4;
 constexpr int NCHUNK = 8;   // 512 / 64
 constexpr int DV = 256;
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;  // 8 math warps (warp pairs share TMEM lanes, split the key columns) + TMA + MMA
 constexpr uint32_t CHUNK_BYTES = BT * 128;  // 16 KB
 
 struct __align__(1024) Smem {
@@ -39,6 +40,8 @@ struct __align__(1024) Smem {
   uint64_t s_full;
   uint64_t p_full;
   uint64_t o_full;
+  float xmax[2][BT];  // row maximum / row sum of each column half
+  float xsum[2][BT];
   uint32_t tmem_base;
 };
 
@@ -58,24 +61,24 @@ cross_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qobj, const __grid_
   const int krow0 = b * N + j * BT;
   constexpr uint32_t C_O = 128;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(&sm.full[s], 1);
       mbar_init(&sm.empty[s], 1);
     }
     mbar_init(&sm.v_full, 1);
     mbar_init(&sm.s_full, 1);
-    mbar_init(&sm.p_full, 128);
+    mbar_init(&sm.p_full, 256);
     mbar_init(&sm.o_full, 1);
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc<512>(&sm.tmem_base);
+  if (warp == 9) tmem_alloc<512>(&sm.tmem_base);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (elect_one()) {
       for (int c = 0; c < NCHUNK; ++c) {
         const int s = c % NSTAGE;
@@ -93,7 +96,7 @@ cross_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qobj, const __grid_
       for (int c = 0; c < DV / 64; ++c) tma_load_2d(sm.v[c], &tm_v, &sm.v_full, c * 64, krow0);
     }
     __syncwarp();
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (elect_one()) {
       constexpr uint32_t id_qk = umma_idesc_bf16(BT, BT, false, false);
       constexpr uint32_t id_pv = umma_idesc_bf16(BT, 64, false, true);
@@ -124,7 +127,7 @@ cross_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qobj, const __grid_
     }
     __syncwarp();
   } else {
-    const int wq = warp;
+    const int wq = warp & 3, ch = warp >> 2;  // TMEM lane quadrant, half of the 128 key columns
     const uint32_t lane_addr = static_cast<uint32_t>(wq * 32) << 16;
     const int r_in_tile = wq * 32 + lane;
     const int q = qt * BT + r_in_tile;
@@ -132,44 +135,46 @@ cross_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qobj, const __grid_
     const uint32_t drop_row = static_cast<uint32_t>((b * 2 + br) * Q + q);
     mbar_wait(&sm.s_full, 0, 35);
     tc_fence_after();
-    uint32_t sr[4][32];
+    uint32_t sr[2][32];  // keys [64 ch, 64 ch + 64) of the tile
 #pragma unroll
-    for (int c = 0; c < 4; ++c) tmem_ld_x32(tmem + lane_addr + c * 32, sr[c]);
+    for (int c = 0; c < 2; ++c) tmem_ld_x32(tmem + lane_addr + (2 * ch + c) * 32, sr[c]);
     tc_wait_ld();
-    const uint4 mw = *reinterpret_cast<const uint4*>(mask_bits + static_cast<size_t>(b) * words_per_row + j * 4);
-    const uint32_t mwa[4] = {mw.x, mw.y, mw.z, mw.w};
-    if ((mw.x | mw.y | mw.z | mw.w) != 0u) {
+    const uint2 mw = *reinterpret_cast<const uint2*>(mask_bits + static_cast<size_t>(b) * words_per_row + j * 4 + 2 * ch);
+    const uint32_t mwa[2] = {mw.x, mw.y};
+    if ((mw.x | mw.y) != 0u) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+      for (int c = 0; c < 2; ++c)
 #pragma unroll
         for (int i = 0; i < 32; ++i)
           if ((mwa[c] >> i) & 1u) sr[c][i] = 0xff800000u;
     }
     float mx = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
+    for (int c = 0; c < 2; ++c)
 #pragma unroll
       for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sr[c][i]));
-    const float m = mx * scale_log2;
+    sm.xmax[ch][r_in_tile] = mx;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float m = fmaxf(mx, sm.xmax[1 - ch][r_in_tile]) * scale_log2;
     const float m_use = (m == -INFINITY) ? 0.f : m;
     float l = 0.f;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t pk[32];
+    {
+      uint32_t pk[32];  // packed P columns [32 ch, 32 ch + 32) = keys [64 ch, 64 ch + 64)
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const int e = 2 * i;
-        const float p0 = ex2_approx(fmaf(__uint_as_float(sr[2 * c + (e >> 5)][e & 31]), scale_log2, -m_use));
-        const float p1 = ex2_approx(fmaf(__uint_as_float(sr[2 * c + ((e + 1) >> 5)][(e + 1) & 31]), scale_log2, -m_use));
+        const float p0 = ex2_approx(fmaf(__uint_as_float(sr[e >> 5][e & 31]), scale_log2, -m_use));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(sr[(e + 1) >> 5][(e + 1) & 31]), scale_log2, -m_use));
         l += p0 + p1;
         pk[i] = pack_bf16x2(p0, p1);
         if (dp.thr16) {  // ClsRegBranch's SelfAttention drops P (always, self_attention.py:40): row = (b, branch, query)
-          const uint32_t bits = drop_bits(drop_seed, dp.site, drop_row, j * (BT / 2) + c * 32 + i);
+          const uint32_t bits = drop_bits(drop_seed, dp.site, drop_row, j * (BT / 2) + ch * 32 + i);
           pk[i] = pack_bf16x2(((bits & 0xFFFFu) >= dp.thr16) ? p0 : 0.f, ((bits >> 16) >= dp.thr16) ? p1 : 0.f);
         }
       }
-      tmem_st_x32(tmem + lane_addr + c * 32, pk);
+      tmem_st_x32(tmem + lane_addr + ch * 32, pk);
     }
+    sm.xsum[ch][r_in_tile] = l;
     tc_wait_st();
     tc_fence_before();
     mbar_arrive(&sm.p_full);
@@ -178,7 +183,7 @@ cross_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qobj, const __grid_
     const size_t slot = ((static_cast<size_t>(b) * 2 + br) * nqt + qt) * nkv + j;
     float* od = ws_o + (slot * BT + r_in_tile) * DV;
 #pragma unroll
-    for (int c = 0; c < DV / 32; ++c) {
+    for (int c = ch * (DV / 64); c < (ch + 1) * (DV / 64); ++c) {  // this thread's half of the row's 256 output columns
       uint32_t r[32];
       tmem_ld_x32(tmem + lane_addr + C_O + c * 32, r);
       tc_wait_ld();
@@ -188,11 +193,14 @@ cross_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qobj, const __grid_
           reinterpret_cast<uint4*>(od + c * 32)[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
       }
     }
-    if (q < Q) reinterpret_cast<float2*>(ws_ml)[slot * BT + r_in_tile] = make_float2(m, l);
+    // (every thread passed the mbarrier wait on o_full after all 256 had arrived on p_full, i.e. after both halves of
+    // xsum were written)
+    if (ch == 0 && q < Q)
+      reinterpret_cast<float2*>(ws_ml)[slot * BT + r_in_tile] = make_float2(m, l + sm.xsum[1][r_in_tile]);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc<512>(tmem);
+  if (warp == 9) tmem_dealloc<512>(tmem);
 }
 
 // one warp per (b, branch, query): merge the nkv partials

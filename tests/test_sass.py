@@ -20,6 +20,11 @@ EXPECT = {
     "cross_attn_fwd_kernel": ("UTCHMMA", "LDTM", "STTM", "UTMALDG"),
     "cross_attn_bwd_ds_kernel": ("UTCHMMA", "LDTM", "UTMALDG"),
     "gemm_bias_relu_drop_kernel": ("UTCHMMA", "LDTM", "UTMALDG"),
+    # round 2: the GEMM family (all template instances) and the fused decoder attention backward kernels
+    "gemm_tc_kernel": ("UTCHMMA", "LDTM", "UTMALDG"),
+    "gemm_dw_kernel": ("UTCHMMA", "LDTM", "UTMALDG", "RED"),
+    "dec_attn_bwd_fused_kernel": ("UTCHMMA", "LDTM", "UTMALDG"),
+    "cross_attn_bwd_fused_kernel": ("UTCHMMA", "LDTM", "UTMALDG"),
 }
 
 
