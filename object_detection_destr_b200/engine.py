@@ -114,6 +114,7 @@ class GraphedTrainStep:
             model.runtime().P.enable_data_parallel(world)  # gradient exchange overlapped with the encoder backward
         self.fused_loss = fused_loss
         self.gpu_lsa = gpu_lsa
+        self.overlap_opt = True  # FlatAdamW: decoder share of the step under the encoder backward
         self.s_status = z(B, dt=torch.int32)
         self.loss_ws = ops.set_loss_workspace(B, dev)
         self.losses = None
@@ -152,6 +153,11 @@ class GraphedTrainStep:
             losses = set_loss_static(out["pred_class"], out["pred_boxes"], self.s_tl, self.s_tb, self.s_pi, self.s_ti,
                                      self.s_valid, self.C)
             loss = sum(self.lw[k] * losses[k] for k in self.lw)
+        # the decoder's share of the optimizer step overlaps the encoder backward (runtime.FlatAdamW.enable_overlap);
+        # set per call: another engine over the same model (e.g. the fwd+bwd-only graph) must not step
+        rt = getattr(self.model, "_rt", None)
+        if rt is not None:
+            rt.P.early_opt = self.opt._early if (self.overlap_opt and hasattr(self.opt, "_early")) else None
         loss.backward()
         if self.world > 1:  # the one exchange of the step: mean all-reduce of the gradients (NCCL over NVLink)
             from .dataparallel import allreduce_mean_, grads_of

@@ -168,3 +168,32 @@ def test_out_of_range_label_raises_like_the_reference():
     labels[1][0] = cfg["C"]   # one past the last class
     with pytest.raises(IndexError):
         eng.load_batch(f, m, s, c, labels, boxes)
+
+
+def test_overlapped_optimizer_step_equals_plain_step():
+    """FlatAdamW with the decoder's share of the step launched under the encoder backward (engine default) produces
+    the same parameters as the single flat launch after the backward: 3 training steps from identical states."""
+    import bench
+    from object_detection_destr_b200.encoder import disable_dropout
+    from object_detection_destr_b200.engine import GraphedTrainStep
+    from object_detection_destr_b200.hotpath import TransformerHalf
+    cfg = dict(bench.CFG, B=2, L=2, H=10, W=14, Q=60)
+    batches = [bench.make_batch(0, s, 2, cfg, padded=True) for s in range(3)]
+    finals = []
+    for overlap in (True, False):
+        torch.manual_seed(0)
+        model = TransformerHalf(Namespace(hidden_dim=256, num_encoder_blocks=2, num_decoder_blocks=2, num_cls=cfg["C"]))
+        disable_dropout(model).cuda().train()
+        opt = model.make_optimizer(lr=1e-3)
+        eng = GraphedTrainStep(model, opt, B=2, H=10, W=14, Q=60, num_classes=cfg["C"], t_max=40)
+        eng.overlap_opt = overlap
+        for bt in batches:
+            eng.load_batch(*bt)
+            eng.eager_step()
+        torch.cuda.synchronize()
+        finals.append((model.runtime().P.m32.clone(), float(opt.t)))
+    (pa, ta), (pb, tb) = finals
+    assert ta == tb == 3.0
+    # (bias / LayerNorm gradients are accumulated with atomics: equal up to summation order)
+    assert float((pa - pb).abs().max()) <= 2e-5, float((pa - pb).abs().max())
+    assert float((pa - pb).abs().mean()) <= 1e-7
