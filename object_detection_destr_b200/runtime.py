@@ -79,6 +79,9 @@ class FlatParams:
         self.Le, self.Ld = Le, Ld
         W: List[Tuple[str, Tensor]] = []
         S: List[Tuple[str, Tensor]] = []
+        # encoder weights: the shared position-scale MLP first, then the layers in order -- [ps | e0] (whose gradients are
+        # final last) is then ONE contiguous tail bucket of the data-parallel exchange
+        W += [("e.ps0_w", e["_pos_scale.0.weight"]), ("e.ps2_w", e["_pos_scale.2.weight"])]
         for l in range(Le):
             p = f"_encoder.{l}."
             W += [(f"e{l}.in_w", e[p + "self_attn.in_proj_weight"]), (f"e{l}.out_w", e[p + "self_attn.out_proj.weight"]),
@@ -87,7 +90,6 @@ class FlatParams:
                   (f"e{l}.fc1_b", e[p + "fc1.bias"]), (f"e{l}.fc2_b", e[p + "fc2.bias"]),
                   (f"e{l}.n1_w", e[p + "norm1.weight"]), (f"e{l}.n1_b", e[p + "norm1.bias"]),
                   (f"e{l}.n2_w", e[p + "norm2.weight"]), (f"e{l}.n2_b", e[p + "norm2.bias"])]
-        W += [("e.ps0_w", e["_pos_scale.0.weight"]), ("e.ps2_w", e["_pos_scale.2.weight"])]
         S += [("e.ps0_b", e["_pos_scale.0.bias"]), ("e.ps2_b", e["_pos_scale.2.bias"]),
               ("e.n_w", e["norm.weight"]), ("e.n_b", e["norm.bias"])]
         for l in range(Ld):
@@ -191,6 +193,7 @@ class FlatParams:
     def begin_backward(self):
         self.g32[self.nW:self.heads_off].zero_()
         self._written.clear()
+        self._dec_reduced = False
         self.early_stream = None
         self._enc_reduced = self.enc_w_end
         if _TC:
@@ -231,29 +234,53 @@ class FlatParams:
         with torch.cuda.stream(stream):
             if dp:
                 import torch.distributed as dist
-                dist.all_reduce(self.g16[self.dec_off:], group=self.group)
+                # the per-layer blocks went during the decoder backward: what is left are the hoisted key / value /
+                # position projections and the shared position-scale MLP
+                a = self.off["d0.ke_w"][0] if getattr(self, "_dec_reduced", False) else self.dec_off
+                dist.all_reduce(self.g16[a:], group=self.group)
                 if early is not None:  # the decoder's + heads' fp32 block travels now too
                     dist.all_reduce(self.g32[self.dec_s_off:], group=self.group)
             if early is not None:
                 early()
         self.early_stream = stream if early is not None else None
 
-    def reduce_encoder_layer(self, l: int):
-        """Data parallel: layer l's weight gradients are final once its backward (and its dW kernels on the side
-        stream) is done -> exchange them now, under the backward of layer l-1.  Only layer 0's bucket, the shared
-        position-scale MLP and the small fp32 block stay for end_backward()."""
+    def reduce_decoder_layer(self, l: int):
+        """Data parallel: decoder layer l's own weight gradients (q|k|v, cross-attention query projections, both branch
+        FFNs: contiguous in the flat layout) are final when its backward is done -> exchange them under the backward of
+        layer l-1.  The decoder's kernels are small (<= 128 CTAs), so a co-running collective costs them little; issuing
+        the whole 30 MB at the start of the ENCODER backward instead displaced its single-wave 132-148-CTA kernels."""
         if getattr(self, "world", 1) <= 1:
             return
         import torch.distributed as dist
+        a = self.off[f"d{l}.q_w"][0]
+        b = self.off[f"d{l + 1}.q_w"][0] if l + 1 < self.Ld else self.off["d0.ke_w"][0]
+        self.comm.wait_stream(self.side)
+        self.comm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.comm):
+            dist.all_reduce(self.g16[a:b], group=self.group)
+        self._dec_reduced = True
+
+    def reduce_encoder_layer(self, l: int):
+        """Data parallel: called when layer l's backward (and its dW kernels on the side stream) is done.  The encoder's
+        weight gradients travel in a few LARGE buckets issued under the remaining backward -- layers [L/2, L) after
+        layer L/2, layers [1, L/2) after layer 1 -- because every collective costs launch latency and SMs that the
+        single-wave compute kernels then miss; [position-scale MLP | layer 0], final only at the very end, is one
+        contiguous tail bucket in end_backward()."""
+        if getattr(self, "world", 1) <= 1:
+            return
+        starts = sorted({max(1, self.Le // 2), 1} & set(range(1, self.Le)), reverse=True)
+        if l not in starts:
+            return
+        import torch.distributed as dist
         a = self.off[f"e{l}.in_w"][0]
-        b = self.off[f"e{l + 1}.in_w"][0] if l + 1 < self.Le else self.off["e.ps0_w"][0]
+        b = getattr(self, "_enc_reduced", self.enc_w_end)
         self.comm.wait_stream(self.side)
         self.comm.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.comm):
             if _TC:
                 self.g16[a:b].copy_(self.g32[a:b])  # fp32 accumulators -> the bf16 the exchange carries
             dist.all_reduce(self.g16[a:b], group=self.group)
-        self._enc_reduced = min(getattr(self, "_enc_reduced", self.enc_w_end), a)
+        self._enc_reduced = a
 
     def end_backward(self):
         if self.side is not None:
@@ -265,13 +292,12 @@ class FlatParams:
             with torch.cuda.stream(self.comm):
                 # whatever the per-layer buckets did not cover: the shared position-scale MLP (and, without per-layer
                 # calls, the whole encoder) + the fp32 bias / LayerNorm / head block
-                done = getattr(self, "_enc_reduced", self.enc_w_end)
-                rest = [(0, self.enc_w_end)] if done >= self.enc_w_end else [(0, done), (self.off["e.ps0_w"][0], self.enc_w_end)]
-                for a, b in rest:
-                    if b > a:
-                        if _TC:
-                            self.g16[a:b].copy_(self.g32[a:b])
-                        dist.all_reduce(self.g16[a:b], group=self.group)
+                # the tail bucket: whatever the in-backward buckets did not cover = [position-scale MLP | layer 0 ...]
+                a, b = 0, getattr(self, "_enc_reduced", self.enc_w_end)
+                if b > a:
+                    if _TC:
+                        self.g16[a:b].copy_(self.g32[a:b])
+                    dist.all_reduce(self.g16[a:b], group=self.group)
                 self._enc_reduced = self.enc_w_end
                 # (the decoder's / heads' part went with the decoder exchange when the optimizer overlaps its step)
                 s_end = self.dec_s_off if getattr(self, "early_stream", None) is not None else self.n
@@ -780,6 +806,7 @@ class HotPathRuntime:
         P.join(0)
         dx[:, 256:] += dxr
         P._keep += [dsin, dt2, dxr]
+        P.reduce_decoder_layer(l)  # data parallel: this layer's own weight gradients are final
         return dx
 
     # ------------------------------------------------------------------ whole path
