@@ -84,6 +84,25 @@ int destr_add_layernorm_fwd(const void* a, int lda, const void* b, int ldb, cons
  * CUDA-graph replays), drop_thr16 = round(p * 65536) (0 = no dropout), drop_site = id of the dropout call (the
  * forward and the backward of one site must pass the same).  Kept values are scaled by 65536 / (65536 - thr16).
  * Here: y = LN(a + dropout(b)). */
+/* Two chained LayerNorms in one pass (D = 256): y1 = LN1(a + dropout(b)), y2 = LN2(c + y1) with both sets of row
+ * statistics -- `norm2(x + dropout3(fc2 ..))` followed by the Encoder's shared `norm(x + block(x))`
+ * (encoder_block.py:108-110, :40).  y1 enters the second LayerNorm as stored (bf16). */
+int destr_add_layernorm2_fwd(const void* a, int lda, const void* b, int ldb, const float* gamma1, const float* beta1,
+                             void* y1, int ldy1, float* mean1, float* rstd1, const void* c, int ldc,
+                             const float* gamma2, const float* beta2, void* y2, int ldy2, float* mean2, float* rstd2,
+                             int M, int D, const uint32_t* drop_seed, uint32_t drop_thr16, uint32_t drop_site,
+                             void* stream);
+
+/* Backward of destr_add_layernorm2_fwd in one pass (dense [M,256] bf16 operands): d3 = gradient w.r.t. (c + y1) (also
+ * the residual-stream gradient of c), dxb = gradient w.r.t. b through its dropout mask, dsum (may be NULL) = the
+ * un-masked gradient w.r.t. (a + dropout(b)); dgamma2/dbeta2 (outer LayerNorm), dgamma1/dbeta1 (inner) and dbias
+ * (column sums of dxb, may be NULL) are ACCUMULATED into. */
+int destr_add_layernorm2_bwd(const void* dy, const void* c, const void* y1, const float* gamma2, const float* mean2,
+                             const float* rstd2, const void* a, const void* b, const float* gamma1, const float* mean1,
+                             const float* rstd1, void* d3, void* dxb, void* dsum, float* dgamma2, float* dbeta2,
+                             float* dgamma1, float* dbeta1, float* dbias, int M, int D, const uint32_t* drop_seed,
+                             uint32_t drop_thr16, uint32_t drop_site, void* stream);
+
 /* backward of y = LN(a+b): dx (bf16, pitch lddx) = d(a+b); dgamma/dbeta fp32 [D] are ACCUMULATED into
  * (caller zeroes).  a+b is recomputed from a and b. */
 int destr_add_layernorm_bwd(const void* dy, int lddy, const void* a, int lda, const void* b, int ldb,

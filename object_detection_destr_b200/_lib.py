@@ -31,6 +31,9 @@ SIGNATURES = {
     "destr_pos_mul_add_bwd": [_p, _p, _p, _i64, _p],
     "destr_mul_fwd": [_p, _p, _p, _i64, _p],
     "destr_add_layernorm_fwd": [_p, _i, _p, _i, _p, _p, _p, _i, _p, _p, _i, _i, _p, _u, _u, _p],
+    "destr_add_layernorm2_fwd": [_p, _i, _p, _i, _p, _p, _p, _i, _p, _p, _p, _i, _p, _p, _p, _i, _p, _p, _i, _i, _p, _u, _u, _p],
+    "destr_add_layernorm2_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _u, _u,
+                                 _p],
     "destr_add_layernorm_bwd": [_p, _i, _p, _i, _p, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _i, _p, _i, _i, _i, _p, _u, _u,
                                 _p],
     "destr_dropout_inplace": [_p, _i, _i, _i, _p, _u, _u, _p],

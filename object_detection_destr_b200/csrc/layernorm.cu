@@ -129,6 +129,55 @@ add_ln_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __re
   }
 }
 
+// Two chained LayerNorms in one row pass: y1 = LN1(a + dropout(b)), y2 = LN2(c + y1) -- the tail of an encoder layer,
+// norm2(x1 + dropout3(fc2 ..)) followed by the Encoder's shared norm(x + block(x)) (encoder_block.py:108-110, :40).
+// y1 enters the second LayerNorm as stored (bf16), so the backward kernels, which recompute xhat from the stored
+// tensors, see exactly the forward's values.
+template <int VPL>
+__global__ void __launch_bounds__(256)
+add_ln2_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                   const float* __restrict__ gamma1, const float* __restrict__ beta1, __nv_bfloat16* __restrict__ y1,
+                   float* __restrict__ mean1, float* __restrict__ rstd1, const __nv_bfloat16* __restrict__ c,
+                   const float* __restrict__ gamma2, const float* __restrict__ beta2, __nv_bfloat16* __restrict__ y2,
+                   float* __restrict__ mean2, float* __restrict__ rstd2, int M, int lda, int ldb, int ldy1, int ldc,
+                   int ldy2, Drop dp) {
+  pdl_wait();
+  pdl_launch();
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const Row<VPL> g1 = ld_vec<VPL>(gamma1, lane), b1 = ld_vec<VPL>(beta1, lane);
+  const Row<VPL> g2 = ld_vec<VPL>(gamma2, lane), b2 = ld_vec<VPL>(beta2, lane);
+  const uint32_t seed = (dp.thr16 && dp.seed) ? *dp.seed : 0u;
+  const float ds = drop_scale(dp.thr16);
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += gridDim.x * wpb) {
+    Row<VPL> x = ld_row<VPL>(a + (size_t)row * lda, lane);
+    Row<VPL> r2 = ld_row<VPL>(b + (size_t)row * ldb, lane);
+    Row<VPL> rc = ld_row<VPL>(c + (size_t)row * ldc, lane);
+    if (dp.thr16) drop_row<VPL>(r2, seed, dp.site, row, lane, dp.thr16, ds);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) x.v[i] += r2.v[i];
+    float mean, rstd;
+    row_stats<VPL>(x, mean, rstd);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) x.v[i] = fmaf((x.v[i] - mean) * rstd, g1.v[i], b1.v[i]);
+    st_row<VPL>(y1 + (size_t)row * ldy1, lane, x);
+    if (lane == 0) {
+      mean1[row] = mean;
+      rstd1[row] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) x.v[i] = __bfloat162float(__float2bfloat16(x.v[i])) + rc.v[i];  // y1 as stored
+    row_stats<VPL>(x, mean, rstd);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) x.v[i] = fmaf((x.v[i] - mean) * rstd, g2.v[i], b2.v[i]);
+    st_row<VPL>(y2 + (size_t)row * ldy2, lane, x);
+    if (lane == 0) {
+      mean2[row] = mean;
+      rstd2[row] = rstd;
+    }
+  }
+}
+
 // dx = rstd * (gy - mean(gy) - xhat * mean(gy*xhat)),  gy = dy*gamma;  dgamma += dy*xhat; dbeta += dy
 template <int VPL>
 __global__ void __launch_bounds__(256)
@@ -239,6 +288,102 @@ add_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __r
   }
 }
 
+
+// Backward of add_ln2_fwd in one row pass:  y2 = LN2(c + y1),  y1 = LN1(a + dropout(b))
+//   d3  = gradient w.r.t. (c + y1)                     (stored: it is also the gradient of the residual stream c)
+//   dxb = gradient w.r.t. b (through b's dropout mask), dsum = the un-masked gradient w.r.t. (a + dropout(b))
+//   dgamma2/dbeta2 (outer), dgamma1/dbeta1 (inner), dbias (= column sums of dxb: the bias of the Linear that made b)
+// d3 enters the inner LayerNorm as stored (bf16), like the two-kernel path it replaces.
+template <int VPL>
+__global__ void __launch_bounds__(256)
+add_ln2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ c,
+                   const __nv_bfloat16* __restrict__ y1, const float* __restrict__ gamma2,
+                   const float* __restrict__ mean2, const float* __restrict__ rstd2,
+                   const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                   const float* __restrict__ gamma1, const float* __restrict__ mean1, const float* __restrict__ rstd1,
+                   __nv_bfloat16* __restrict__ d3_out, __nv_bfloat16* __restrict__ dxb_out,
+                   __nv_bfloat16* __restrict__ dsum_out, float* __restrict__ dgamma2, float* __restrict__ dbeta2,
+                   float* __restrict__ dgamma1, float* __restrict__ dbeta1, float* __restrict__ dbias, int M, Drop dp) {
+  constexpr int D = VPL * 32;
+  constexpr float invD = 1.0f / D;
+  __shared__ float red[5][8][D];  // [dgamma2|dbeta2|dgamma1|dbeta1|dbias][warp][channel]  (40 KB at D = 256)
+  pdl_wait();
+  pdl_launch();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const Row<VPL> g2 = ld_vec<VPL>(gamma2, lane), g1 = ld_vec<VPL>(gamma1, lane);
+  const uint32_t seed = (dp.thr16 && dp.seed) ? *dp.seed : 0u;
+  const float ds = drop_scale(dp.thr16);
+  Row<VPL> acc[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k)
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) acc[k].v[i] = 0.f;
+  for (int row = blockIdx.x * wpb + warp; row < M; row += gridDim.x * wpb) {
+    const size_t ro = (size_t)row * D;
+    Row<VPL> xo = ld_row<VPL>(c + ro, lane);
+    const Row<VPL> ry1 = ld_row<VPL>(y1 + ro, lane);
+    const Row<VPL> d = ld_row<VPL>(dy + ro, lane);
+    Row<VPL> xi = ld_row<VPL>(a + ro, lane);
+    Row<VPL> rb = ld_row<VPL>(b + ro, lane);
+    const float m2 = mean2[row], r2 = rstd2[row], m1 = mean1[row], r1 = rstd1[row];
+    // ---- outer LayerNorm ----
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      xo.v[i] = (xo.v[i] + ry1.v[i] - m2) * r2;  // xhat
+      const float gy = d.v[i] * g2.v[i];
+      s1 += gy;
+      s2 = fmaf(gy, xo.v[i], s2);
+      acc[0].v[i] = fmaf(d.v[i], xo.v[i], acc[0].v[i]);
+      acc[1].v[i] += d.v[i];
+    }
+    s1 = warp_sum(s1) * invD;
+    s2 = warp_sum(s2) * invD;
+    Row<VPL> d3;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) d3.v[i] = r2 * (d.v[i] * g2.v[i] - s1 - xo.v[i] * s2);
+    st_row<VPL>(d3_out + ro, lane, d3);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) d3.v[i] = __bfloat162float(__float2bfloat16(d3.v[i]));  // as stored
+    // ---- inner LayerNorm ----
+    if (dp.thr16) drop_row<VPL>(rb, seed, dp.site, row, lane, dp.thr16, ds);
+    s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      xi.v[i] = (xi.v[i] + rb.v[i] - m1) * r1;  // xhat
+      const float gy = d3.v[i] * g1.v[i];
+      s1 += gy;
+      s2 = fmaf(gy, xi.v[i], s2);
+      acc[2].v[i] = fmaf(d3.v[i], xi.v[i], acc[2].v[i]);
+      acc[3].v[i] += d3.v[i];
+    }
+    s1 = warp_sum(s1) * invD;
+    s2 = warp_sum(s2) * invD;
+    Row<VPL> o;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) o.v[i] = r1 * (d3.v[i] * g1.v[i] - s1 - xi.v[i] * s2);
+    if (dsum_out) st_row<VPL>(dsum_out + ro, lane, o);
+    if (dp.thr16) drop_row<VPL>(o, seed, dp.site, row, lane, dp.thr16, ds);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) acc[4].v[i] += o.v[i];
+    st_row<VPL>(dxb_out + ro, lane, o);
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k)
+#pragma unroll
+    for (int cch = 0; cch < VPL / 8; ++cch)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) red[k][warp][(cch * 32 + lane) * 8 + i] = acc[k].v[cch * 8 + i];
+  __syncthreads();
+  float* outp[5] = {dgamma2, dbeta2, dgamma1, dbeta1, dbias};
+  for (int idx = threadIdx.x; idx < 5 * D; idx += blockDim.x) {
+    const int which = idx / D, ch = idx - which * D;
+    if (outp[which] == nullptr) continue;
+    float sacc = 0.f;
+    for (int w2 = 0; w2 < wpb; ++w2) sacc += red[which][w2][ch];
+    atomicAdd(outp[which] + ch, sacc);
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // out = lam*LN1(x+o1) + (1-lam)*LN2(x+o2eff), D = 512  (decoder_block.py:182-184), where o2eff folds
@@ -464,6 +609,42 @@ extern "C" int destr_add_layernorm_fwd(const void* a, int lda, const void* b, in
                                                       (__nv_bfloat16*)y, mean, rstd, M, lda, ldb, ldy,
                                                       DESTR_DROP(drop_seed, drop_thr16, drop_site)));
   DESTR_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int destr_add_layernorm2_fwd(const void* a, int lda, const void* b, int ldb, const float* gamma1,
+                                        const float* beta1, void* y1, int ldy1, float* mean1, float* rstd1,
+                                        const void* c, int ldc, const float* gamma2, const float* beta2, void* y2,
+                                        int ldy2, float* mean2, float* rstd2, int M, int D, const uint32_t* drop_seed,
+                                        uint32_t drop_thr16, uint32_t drop_site, void* stream) {
+  DESTR_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0 && ldy1 % 8 == 0 && ldy2 % 8 == 0, "row pitch");
+  DESTR_CHECK_ARG(a && b && c && gamma1 && beta1 && gamma2 && beta2 && y1 && y2 && mean1 && rstd1 && mean2 && rstd2 && M > 0,
+                  "null pointer / shape");
+  DESTR_CHECK_ARG(D == 256, "D must be 256");
+  DESTR_CUDA(launch_k(add_ln2_fwd_kernel<8>, dim3(ln_grid(M)), dim3(256), 0, (cudaStream_t)stream,
+                      (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, gamma1, beta1, (__nv_bfloat16*)y1, mean1, rstd1,
+                      (const __nv_bfloat16*)c, gamma2, beta2, (__nv_bfloat16*)y2, mean2, rstd2, M, lda, ldb, ldy1, ldc, ldy2,
+                      DESTR_DROP(drop_seed, drop_thr16, drop_site)));
+  return 0;
+}
+
+extern "C" int destr_add_layernorm2_bwd(const void* dy, const void* c, const void* y1, const float* gamma2,
+                                        const float* mean2, const float* rstd2, const void* a, const void* b,
+                                        const float* gamma1, const float* mean1, const float* rstd1, void* d3,
+                                        void* dxb, void* dsum, float* dgamma2, float* dbeta2, float* dgamma1,
+                                        float* dbeta1, float* dbias, int M, int D, const uint32_t* drop_seed,
+                                        uint32_t drop_thr16, uint32_t drop_site, void* stream) {
+  DESTR_CHECK_ARG(dy && c && y1 && gamma2 && mean2 && rstd2 && a && b && gamma1 && mean1 && rstd1 && d3 && dxb && M > 0,
+                  "null pointer / shape");
+  DESTR_CHECK_ARG(dgamma2 && dbeta2 && dgamma1 && dbeta1, "null parameter-gradient pointer");
+  DESTR_CHECK_ARG(D == 256, "D must be 256 (dense [M,256] operands)");
+  int grid = ln_grid(M);
+  if (grid > kSMs * 2) grid = kSMs * 2;
+  DESTR_CUDA(launch_k(add_ln2_bwd_kernel<8>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)dy,
+                      (const __nv_bfloat16*)c, (const __nv_bfloat16*)y1, gamma2, mean2, rstd2, (const __nv_bfloat16*)a,
+                      (const __nv_bfloat16*)b, gamma1, mean1, rstd1, (__nv_bfloat16*)d3, (__nv_bfloat16*)dxb,
+                      (__nv_bfloat16*)dsum, dgamma2, dbeta2, dgamma1, dbeta1, dbias, M,
+                      DESTR_DROP(drop_seed, drop_thr16, drop_site)));
   return 0;
 }
 

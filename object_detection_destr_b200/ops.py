@@ -136,6 +136,40 @@ def add_layernorm(a: Tensor, b: Optional[Tensor], gamma: Tensor, beta: Tensor, s
     return (y, mean, rstd) if save_stats else y
 
 
+def add_layernorm2(a: Tensor, b: Tensor, gamma1: Tensor, beta1: Tensor, c: Tensor, gamma2: Tensor, beta2: Tensor,
+                   drop=None):
+    """y1 = LN1(a + dropout(b)), y2 = LN2(c + y1) in one row pass (D = 256).  -> (y1, mean1, rstd1, y2, mean2, rstd2)."""
+    a, b, c = _rows(a, BF16, "a", 256), _rows(b, BF16, "b", 256), _rows(c, BF16, "c", 256)
+    M = a.shape[0]
+    dev = a.device
+    y1, y2 = torch.empty(M, 256, dtype=BF16, device=dev), torch.empty(M, 256, dtype=BF16, device=dev)
+    st = torch.empty(4, M, dtype=torch.float32, device=dev)
+    _lib.call("destr_add_layernorm2_fwd", a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0),
+              _chk(gamma1, torch.float32, "gamma1").data_ptr(), _chk(beta1, torch.float32, "beta1").data_ptr(), y1.data_ptr(),
+              256, st[0].data_ptr(), st[1].data_ptr(), c.data_ptr(), c.stride(0),
+              _chk(gamma2, torch.float32, "gamma2").data_ptr(), _chk(beta2, torch.float32, "beta2").data_ptr(), y2.data_ptr(),
+              256, st[2].data_ptr(), st[3].data_ptr(), M, 256, *_dargs(drop), _stream())
+    return y1, st[0], st[1], y2, st[2], st[3]
+
+
+def add_layernorm2_bwd(dy: Tensor, c: Tensor, y1: Tensor, gamma2: Tensor, mean2: Tensor, rstd2: Tensor, a: Tensor,
+                       b: Tensor, gamma1: Tensor, mean1: Tensor, rstd1: Tensor, dgamma2: Tensor, dbeta2: Tensor,
+                       dgamma1: Tensor, dbeta1: Tensor, dbias: Optional[Tensor] = None, drop=None, want_sum: bool = False):
+    """Backward of add_layernorm2 (dense [M,256] bf16 operands).  -> (d3, dxb, dsum or None); the five parameter
+    gradients (fp32 [256]) are accumulated into."""
+    ts = [_chk(t.contiguous(), BF16, n) for t, n in ((dy, "dy"), (c, "c"), (y1, "y1"), (a, "a"), (b, "b"))]
+    dy, c, y1, a, b = ts
+    M = a.shape[0]
+    dev = a.device
+    d3, dxb = torch.empty(M, 256, dtype=BF16, device=dev), torch.empty(M, 256, dtype=BF16, device=dev)
+    dsum = torch.empty(M, 256, dtype=BF16, device=dev) if want_sum else None
+    _lib.call("destr_add_layernorm2_bwd", dy.data_ptr(), c.data_ptr(), y1.data_ptr(), gamma2.data_ptr(), mean2.data_ptr(),
+              rstd2.data_ptr(), a.data_ptr(), b.data_ptr(), gamma1.data_ptr(), mean1.data_ptr(), rstd1.data_ptr(),
+              d3.data_ptr(), dxb.data_ptr(), _ptr(dsum), dgamma2.data_ptr(), dbeta2.data_ptr(), dgamma1.data_ptr(),
+              dbeta1.data_ptr(), _ptr(dbias), M, 256, *_dargs(drop), _stream())
+    return d3, dxb, dsum
+
+
 def add_layernorm_bwd(dy: Tensor, a: Tensor, b: Optional[Tensor], gamma: Tensor, mean: Tensor, rstd: Tensor,
                       dgamma: Optional[Tensor] = None, dbeta: Optional[Tensor] = None, dbias: Optional[Tensor] = None,
                       res_in: Optional[Tensor] = None, dx_out: Optional[Tensor] = None,

@@ -599,24 +599,33 @@ class HotPathRuntime:
         else:
             g = ops.gemm(f1, P.w(f"e{l}.fc2_w"), bias=P.f(f"e{l}.fc2_b")) if _TC else \
                 _mm_bias(f1, P.w(f"e{l}.fc2_w"), P.w(f"e{l}.fc2_b"))
-            x2, m2, r2 = ops.add_layernorm(x1, g, P.f(f"e{l}.n2_w"), P.f(f"e{l}.n2_b"), save_stats=True, drop=d3_)
-            xo, m3, r3 = ops.add_layernorm(x, x2, P.f("e.n_w"), P.f("e.n_b"), save_stats=True)
+            # norm2(x1 + dropout3(fc2 ..)) and the encoder's shared norm(x + block(x)) in one row pass
+            x2, m2, r2, xo, m3, r3 = ops.add_layernorm2(x1, g, P.f(f"e{l}.n2_w"), P.f(f"e{l}.n2_b"), x, P.f("e.n_w"),
+                                                        P.f("e.n_b"), drop=d3_)
         return xo, (x, h1, xq, qk, v, a, lse, o, x1, m1, r1, f1, g, x2, m2, r2, m3, r3, cb)
 
     def _enc_bwd(self, l: int, dxo: Tensor, sv, pos: Tensor, bits: Tensor, B: int, N: int) -> Tensor:
         P = self.P
         x, h1, xq, qk, v, a, lse, o, x1, m1, r1, f1, g, x2, m2, r2, m3, r3, cb = sv
-        # xo = LN(x + x2)
-        d3, _, _ = ops.add_layernorm_bwd(dxo, x, x2, P.f("e.n_w"), m3, r3, dgamma=P.g("e.n_w"), dbeta=P.g("e.n_b"))
-        # x2 = LN(x1 + fc2(relu(fc1 x1)))
-        # (with dropout3 active the gradient splits: d2 goes through the mask into fc2, d2s is the un-masked residual)
-        # fused-LayerNorm forward: `g` / `o` hold the pre-LayerNorm sums z = residual + dropout(linear), so the
-        # backward reads one operand (a = z, b = None); the dropout mask is still applied to the branch gradient
         dc = self.dc
-        r_ = ops.add_layernorm_bwd(d3, g if _TC_LN else x1, None if _TC_LN else g, P.f(f"e{l}.n2_w"), m2, r2,
-                                   dgamma=P.g(f"e{l}.n2_w"), dbeta=P.g(f"e{l}.n2_b"), dbias=P.g(f"e{l}.fc2_b"),
-                                   drop=self._d(dc["e.d3"], enc_site(l, "d3")), want_sum=bool(dc["e.d3"]))
-        d2, d2s = r_[0], (r_[3] if dc["e.d3"] else r_[0])
+        if _TC_LN:
+            # xo = LN(x + x2)
+            d3, _, _ = ops.add_layernorm_bwd(dxo, x, x2, P.f("e.n_w"), m3, r3, dgamma=P.g("e.n_w"), dbeta=P.g("e.n_b"))
+            # x2 = LN(x1 + fc2(relu(fc1 x1))): `g` holds the pre-LayerNorm sum z (fused-LayerNorm forward), so the backward
+            # reads one operand (a = z, b = None); the dropout mask is still applied to the branch gradient
+            r_ = ops.add_layernorm_bwd(d3, g, None, P.f(f"e{l}.n2_w"), m2, r2, dgamma=P.g(f"e{l}.n2_w"),
+                                       dbeta=P.g(f"e{l}.n2_b"), dbias=P.g(f"e{l}.fc2_b"),
+                                       drop=self._d(dc["e.d3"], enc_site(l, "d3")), want_sum=bool(dc["e.d3"]))
+            d2, d2s = r_[0], (r_[3] if dc["e.d3"] else r_[0])
+        else:
+            # xo = LN(x + x2), x2 = LN(x1 + dropout3(fc2 ..)): both LayerNorm backwards in one row pass.  With dropout3
+            # active the gradient splits: d2 goes through the mask into fc2, d2s is the un-masked residual gradient
+            d3, d2, d2s = ops.add_layernorm2_bwd(dxo, x, x2, P.f("e.n_w"), m3, r3, x1, g, P.f(f"e{l}.n2_w"), m2, r2,
+                                                 P.g("e.n_w"), P.g("e.n_b"), P.g(f"e{l}.n2_w"), P.g(f"e{l}.n2_b"),
+                                                 dbias=P.g(f"e{l}.fc2_b"), drop=self._d(dc["e.d3"], enc_site(l, "d3")),
+                                                 want_sum=bool(dc["e.d3"]))
+            if d2s is None:
+                d2s = d2
         P.acc_gw(f"e{l}.fc2_w", d2, f1)
         if _TC:
             # dX of fc2 + the ReLU/dropout2 mask + fc1's bias gradient in one kernel, then dX of fc1 + residual gradient

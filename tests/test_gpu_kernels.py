@@ -125,3 +125,43 @@ def test_linear_bias_relu_dropout(M, N, K, p):
     xs[:, :K] = x
     out2 = ops.linear_bias_relu_dropout(xs.cuda()[:, :K], w.cuda(), b.cuda(), drop).cpu().float()
     assert torch.equal(out2, out)
+
+
+@pytest.mark.parametrize("M,p", [(8400, 0.0), (8400, 0.3), (803, 0.3)])
+def test_add_layernorm2_fwd_bwd(M, p):
+    """Two chained LayerNorms in one pass, y1 = LN1(a + dropout(b)), y2 = LN2(c + y1), and its one-pass backward,
+    vs torch autograd on the same bf16 inputs (the dropout mask from the numpy twin of the kernels' hash)."""
+    import numpy as np
+    from object_detection_destr_b200 import ops
+    from oracle.dropout_mask import keep_mask, scale_of, thr16_of
+    from parity_log import record
+    g = torch.Generator().manual_seed(M)
+    a, b, c, dy = (torch.randn(M, 256, generator=g).bfloat16() for _ in range(4))
+    g1, b1, g2, b2 = (1 + 0.1 * torch.randn(256, generator=g), 0.1 * torch.randn(256, generator=g),
+                      1 + 0.1 * torch.randn(256, generator=g), 0.1 * torch.randn(256, generator=g))
+    mk = torch.ones(M, 256)
+    drop = None
+    if p:
+        t = thr16_of(p)
+        mk = torch.from_numpy(keep_mask(9, 4, np.arange(M), np.arange(256), t)).float() * scale_of(t)
+        drop = (torch.tensor([9], dtype=torch.int32, device="cuda"), ops.drop_thr16(p), 4)
+    af, bf, cf = (t.float().requires_grad_() for t in (a, b, c))
+    p1 = [t.clone().requires_grad_() for t in (g1, b1, g2, b2)]
+    LN = torch.nn.functional.layer_norm
+    y1r = LN(af + bf * mk, (256,), p1[0], p1[1], 1e-5)
+    y2r = LN(cf + y1r, (256,), p1[2], p1[3], 1e-5)
+    y2r.backward(dy.float())
+    dev = [t.cuda() for t in (g1, b1, g2, b2)]
+    y1, m1, r1, y2, m2, r2 = ops.add_layernorm2(a.cuda(), b.cuda(), dev[0], dev[1], c.cuda(), dev[2], dev[3], drop=drop)
+    assert float((y1.cpu().float() - y1r).abs().max()) < 3e-2 and float((y2.cpu().float() - y2r).abs().max()) < 4e-2
+    grads = [torch.zeros(256, device="cuda") for _ in range(5)]  # dgamma2, dbeta2, dgamma1, dbeta1, dbias
+    d3, dxb, dsum = ops.add_layernorm2_bwd(dy.cuda(), c.cuda(), y1, dev[2], m2, r2, a.cuda(), b.cuda(), dev[0], m1, r1,
+                                           grads[0], grads[1], grads[2], grads[3], dbias=grads[4], drop=drop, want_sum=True)
+    e3 = float((d3.cpu().float() - cf.grad).abs().max())      # gradient of the residual stream c (= d(c + y1))
+    eb = float((dxb.cpu().float() - bf.grad).abs().max())     # through b's dropout mask
+    es = float((dsum.cpu().float() - af.grad).abs().max())    # un-masked
+    record(f"add_layernorm2_M{M}_p{p}", "d3/dxb/dsum.max_abs", max(e3, eb, es), 5e-2)
+    assert max(e3, eb, es) < 5e-2, (e3, eb, es)
+    for got, ref in ((grads[0], p1[2].grad), (grads[1], p1[3].grad), (grads[2], p1[0].grad), (grads[3], p1[1].grad),
+                     (grads[4], bf.grad.sum(0))):
+        assert torch.allclose(got.cpu(), ref, rtol=3e-2, atol=0.5), float((got.cpu() - ref).abs().max())
