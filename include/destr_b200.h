@@ -366,6 +366,13 @@ int destr_gemm_res_ln(const void* a, int lda, const void* w, int ldw, int M, int
 int destr_gemm_bf16_batched(const void* a, int lda, int a_batch_rows, const void* b, int ldb, int b_batch_rows,
                             int b_kn, int batch, int M, int N, int K, void* out, int ldo, void* stream);
 
+/* Two batched products with the same (N, K, batch, b_kn) -- e.g. dq_obj and dq_pos of the split cross-attention
+ * backward -- in ONE launch (the second problem rides on gridDim.z): they are independent, latency-bound and small. */
+int destr_gemm_bf16_batched2(const void* a1, int lda1, int a1_batch_rows, const void* b1, int ldb1, int b1_batch_rows,
+                             int M1, void* out1, int ldo1, const void* a2, int lda2, int a2_batch_rows, const void* b2,
+                             int ldb2, int b2_batch_rows, int M2, void* out2, int ldo2, int b_kn, int batch, int N,
+                             int K, void* stream);
+
 /* Weight gradient dw[Nout,Kin] += dy[M,Nout]^T x[M,Kin] (fp32 accumulation INTO dw with red.global.add: zero it first),
  * split over the M rows so small weight matrices still fill the GPU.  dy, x bf16 row-major; dw fp32, pitch lddw. */
 int destr_gemm_dw(const void* dy, int lddy, const void* x, int ldx, int M, int Nout, int Kin, float* dw, int lddw,

@@ -53,6 +53,7 @@ SIGNATURES = {
                                       _f, _p, _u, _u, _p],
     "destr_split_cross_attn_bwd_fused": [_p, _p, _p, _p, _p, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _p, _i,
                                          _p, _i, _i, _i, _i, _f, _p, _u, _u, _p],
+    "destr_gemm_bf16_batched2": [_p, _i, _i, _p, _i, _i, _i, _p, _i, _p, _i, _i, _p, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p],
     "destr_gemm_bf16_batched": [_p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p],
     "destr_dec_self_pair_attn_bwd_ds": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _u, _u, _p],
     "destr_dec_self_pair_attn_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _u, _u, _p],

@@ -180,8 +180,16 @@ __device__ __forceinline__ void issue_chunk(Smem<BN>& sm, const CUtensorMap* ta,
 
 template <int BN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(NTHREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-               const __grid_constant__ GemmArgs ga) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a1, const __grid_constant__ CUtensorMap tm_b1,
+               const __grid_constant__ GemmArgs ga1, const __grid_constant__ CUtensorMap tm_a2,
+               const __grid_constant__ CUtensorMap tm_b2, const __grid_constant__ GemmArgs ga2) {
+  // blockIdx.z selects one of two independent problems of the same (N, K) family sharing the launch (e.g. dq_obj and
+  // dq_pos of the split cross-attention backward); ordinary launches have gridDim.z = 1 and the second set unused
+  // (the tensor maps are only ever addressed directly as kernel parameters -- TMA must read a descriptor from param /
+  // const / global space, and a run-time selected pointer makes the compiler copy them to the local stack; the plain
+  // argument struct is simply copied)
+  const bool second = blockIdx.z != 0;
+  const GemmArgs ga = second ? ga2 : ga1;
   using SM = Smem<BN>;
   constexpr int NSTAGE = SM::NSTAGE;
   constexpr int CW = BN / 4;   // output columns per epilogue warp
@@ -207,8 +215,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       mbar_init(&sm.acc_empty[s], NEPI * 32);
     }
     fence_mbar_init();
-    tma_prefetch_desc(&tm_a);
-    tma_prefetch_desc(&tm_b);
+    if (second) {
+      tma_prefetch_desc(&tm_a2);
+      tma_prefetch_desc(&tm_b2);
+    } else {
+      tma_prefetch_desc(&tm_a1);
+      tma_prefetch_desc(&tm_b1);
+    }
   }
   if (warp == NEPI + 1) tmem_alloc<2 * BN>(&sm.tmem_base);
   tc_fence_before();
@@ -226,7 +239,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         const int m0 = (j0 + i * gs) * BM;
         for (int kc = 0; kc < nkc; ++kc, ++c) {
           mbar_wait(&sm.empty[c % NSTAGE], ((c / NSTAGE) & 1) ^ 1, 51);
-          issue_chunk<BN, B_MN>(sm, &tm_a, &tm_b, c, m0, kc, n0, bz * ga.a_brows, bz * ga.b_brows);
+          if (second)
+            issue_chunk<BN, B_MN>(sm, &tm_a2, &tm_b2, c, m0, kc, n0, bz * ga.a_brows, bz * ga.b_brows);
+          else
+            issue_chunk<BN, B_MN>(sm, &tm_a1, &tm_b1, c, m0, kc, n0, bz * ga.a_brows, bz * ga.b_brows);
         }
       }
     }
@@ -626,26 +642,47 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant_
   if (warp == 5) tmem_dealloc<DW_BN>(tmem);
 }
 
-template <int BN, bool B_MN, int EPI>
-int launch_gemm(const void* a, int lda, const void* b, int ldb, const GemmArgs& ga, cudaStream_t st, int batch = 1) {
-  CUtensorMap ta, tb;
+template <int BN, bool B_MN>
+int make_maps(const void* a, int lda, const void* b, int ldb, const GemmArgs& ga, int batch, CUtensorMap* ta,
+              CUtensorMap* tb) {
   int rc;
   const uint64_t a_rows = batch > 1 ? static_cast<uint64_t>(batch) * ga.a_brows : ga.M;
   const uint64_t b_rows = batch > 1 ? static_cast<uint64_t>(batch) * ga.b_brows : (B_MN ? ga.K : ga.N);
-  if ((rc = make_tmap_bf16_2d(&ta, a, a_rows, ga.K, lda, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_tmap_bf16_2d(ta, a, a_rows, ga.K, lda, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if (!B_MN) {
-    if ((rc = make_tmap_bf16_2d(&tb, b, b_rows, ga.K, ldb, BN, BK, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    if ((rc = make_tmap_bf16_2d(tb, b, b_rows, ga.K, ldb, BN, BK, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   } else {
-    if ((rc = make_tmap_bf16_2d(&tb, b, b_rows, ga.N, ldb, BK, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    if ((rc = make_tmap_bf16_2d(tb, b, b_rows, ga.N, ldb, BK, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  }
+  return 0;
+}
+
+// `second` (optional): another problem with the same N, K, batch in the same launch (gridDim.z = 2)
+template <int BN, bool B_MN, int EPI>
+int launch_gemm(const void* a, int lda, const void* b, int ldb, const GemmArgs& ga, cudaStream_t st, int batch = 1,
+                const void* a2 = nullptr, int lda2 = 0, const void* b2 = nullptr, int ldb2 = 0,
+                const GemmArgs* second = nullptr) {
+  CUtensorMap ta, tb, ta2, tb2;
+  int rc;
+  if ((rc = make_maps<BN, B_MN>(a, lda, b, ldb, ga, batch, &ta, &tb))) return rc;
+  GemmArgs g2 = ga;
+  if (second) {
+    g2 = *second;
+    if ((rc = make_maps<BN, B_MN>(a2, lda2, b2, ldb2, g2, batch, &ta2, &tb2))) return rc;
+  } else {
+    ta2 = ta;
+    tb2 = tb;
   }
   const size_t smem = sizeof(Smem<BN>) + 1024;
   DESTR_SMEM_OPTIN((gemm_tc_kernel<BN, B_MN, EPI>), smem);
-  const int mt = ceil_div(ga.M, BM), nb = ceil_div(ga.N, BN);
+  const int mmax = second && second->M > ga.M ? second->M : ga.M;
+  const int mt = ceil_div(mmax, BM), nb = ceil_div(ga.N, BN);
   int gs = 148 / nb;
   if (gs < 1) gs = 1;
   if (gs > mt) gs = mt;
   gs = ceil_div(mt, ceil_div(mt, gs));
-  DESTR_CUDA(launch_k(gemm_tc_kernel<BN, B_MN, EPI>, dim3(gs * nb, batch), dim3(NTHREADS), smem, st, ta, tb, ga));
+  DESTR_CUDA(launch_k(gemm_tc_kernel<BN, B_MN, EPI>, dim3(gs * nb, batch, second ? 2 : 1), dim3(NTHREADS), smem, st, ta, tb,
+                      ga, ta2, tb2, g2));
   return 0;
 }
 
@@ -767,4 +804,24 @@ extern "C" int destr_gemm_bf16_batched(const void* a, int lda, int a_batch_rows,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return b_kn ? launch_gemm<128, true, EPI_STORE>(a, lda, b, ldb, ga, st, batch)
               : launch_gemm<128, false, EPI_STORE>(a, lda, b, ldb, ga, st, batch);
+}
+
+// two batched products with the same (N, K, batch, b_kn) in ONE launch (gridDim.z = 2)
+extern "C" int destr_gemm_bf16_batched2(const void* a1, int lda1, int a1_batch_rows, const void* b1, int ldb1,
+                                        int b1_batch_rows, int M1, void* out1, int ldo1, const void* a2, int lda2,
+                                        int a2_batch_rows, const void* b2, int ldb2, int b2_batch_rows, int M2,
+                                        void* out2, int ldo2, int b_kn, int batch, int N, int K, void* stream) {
+  int rc = check_common(a1, lda1, b1, ldb1, M1, N, K, b_kn);
+  if (rc) return rc;
+  if ((rc = check_common(a2, lda2, b2, ldb2, M2, N, K, b_kn))) return rc;
+  DESTR_CHECK_ARG(out1 && out2 && ldo1 % 8 == 0 && ldo2 % 8 == 0 && ldo1 >= N && ldo2 >= N && batch > 0, "out / batch");
+  DESTR_CHECK_ARG(a1_batch_rows >= M1 && a2_batch_rows >= M2 && b1_batch_rows > 0 && b2_batch_rows > 0, "batch rows");
+  GemmArgs g1{}, g2{};
+  g1.M = M1, g1.N = N, g1.K = K, g1.a_brows = a1_batch_rows, g1.b_brows = b1_batch_rows;
+  g1.out = static_cast<bf16*>(out1), g1.ldo = ldo1;
+  g2.M = M2, g2.N = N, g2.K = K, g2.a_brows = a2_batch_rows, g2.b_brows = b2_batch_rows;
+  g2.out = static_cast<bf16*>(out2), g2.ldo = ldo2;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return b_kn ? launch_gemm<128, true, EPI_STORE>(a1, lda1, b1, ldb1, g1, st, batch, a2, lda2, b2, ldb2, &g2)
+              : launch_gemm<128, false, EPI_STORE>(a1, lda1, b1, ldb1, g1, st, batch, a2, lda2, b2, ldb2, &g2);
 }

@@ -597,10 +597,10 @@ def split_cross_attn_bwd(q_obj: Tensor, q_pos: Tensor, k_enc: Tensor, k_pos: Ten
                   dv.data_ptr(), dv.stride(0), B, Q, N, 1.0 / math.sqrt(512.0), *_dargs(drop), _stream())
         dqo = torch.empty(B * 2 * Q, 256, dtype=BF16, device=dev)
         dqp = torch.empty(B * Q, 256, dtype=BF16, device=dev)
-        _lib.call("destr_gemm_bf16_batched", dS_all.data_ptr(), Np, 2 * Q, k_enc.data_ptr(), k_enc.stride(0), N, 1, B,
-                  2 * Q, 256, Np, dqo.data_ptr(), 256, _stream())
-        _lib.call("destr_gemm_bf16_batched", dS_sum.data_ptr(), Np, Q, k_pos.data_ptr(), k_pos.stride(0), N, 1, B, Q, 256,
-                  Np, dqp.data_ptr(), 256, _stream())
+        # dq_obj = dS k_enc and dq_pos = (dS_cls + dS_reg) k_pos per image: two batched products, one launch
+        _lib.call("destr_gemm_bf16_batched2", dS_all.data_ptr(), Np, 2 * Q, k_enc.data_ptr(), k_enc.stride(0), N, 2 * Q,
+                  dqo.data_ptr(), 256, dS_sum.data_ptr(), Np, Q, k_pos.data_ptr(), k_pos.stride(0), N, Q, dqp.data_ptr(),
+                  256, 1, B, 256, Np, _stream())
         return dqo.view(B * Q, 512), dqp, dke, dkp, dv
     P_all = torch.empty(B, 2 * Q, Np, dtype=BF16, device=dev)
     dS_all = torch.empty(B, 2 * Q, Np, dtype=BF16, device=dev)
