@@ -12,11 +12,16 @@ from object_detection_destr_b200.engine import GraphedTrainStep
 from object_detection_destr_b200.hotpath import TransformerHalf
 
 cfg, B = bench.CFG, bench.CFG["B"]
+world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+if world > 1:  # under torchrun: the data-parallel step (NCCL kernels show up in the timeline of rank 0)
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 torch.manual_seed(0)
 model = TransformerHalf(Namespace(hidden_dim=256, num_encoder_blocks=cfg["L"], num_decoder_blocks=cfg["L"], num_cls=cfg["C"]))
 (model if "--dropout" in sys.argv else disable_dropout(model)).cuda().train()  # --dropout: the bench default (p = 0.3)
 opt = model.make_optimizer(lr=1e-5)
-eng = GraphedTrainStep(model, opt, B=B, H=cfg["H"], W=cfg["W"], Q=cfg["Q"], num_classes=cfg["C"], t_max=40)
+eng = GraphedTrainStep(model, opt, B=B, H=cfg["H"], W=cfg["W"], Q=cfg["Q"], num_classes=cfg["C"], t_max=40, world=world)
 bt = bench.make_batch(0, 0, B)
 res = tuple(t.cuda() for t in bt[:4]) + (bt[4], bt[5])
 eng.load_batch(*res)
@@ -57,3 +62,17 @@ for i, k in enumerate(ks):
 print("time running alone, by kernel:")
 for n, v in sorted(solo.items(), key=lambda kv: -kv[1])[:40]:
     print(f"  {v:8.1f} us x{cnt[n]:3d}  {n}")
+
+if world > 1:
+    if rank == 0:
+        nc = [k for k in ks if "nccl" in k[2].lower()]
+        print(f"NCCL kernels: {len(nc)}, total {sum(k[1] - k[0] for k in nc):.1f} us")
+        for k in nc:
+            print(f"  start {k[0] - t0:8.1f} us  dur {k[1] - k[0]:7.1f} us  {k[2][:70]}")
+        last_compute = max(k[1] for k in ks if "nccl" not in k[2].lower() and "adamw" not in k[2].lower())
+        print(f"last non-NCCL, non-AdamW kernel ends at {last_compute - t0:.1f} us; step ends at {t1 - t0:.1f} us")
+        tail = [k for k in ks if k[0] >= last_compute - 1.0]
+        for k in tail:
+            print(f"  tail: start {k[0] - t0:8.1f} dur {k[1] - k[0]:7.1f}  {k[2][:70]}")
+    sys.stdout.flush()
+    os._exit(0)
