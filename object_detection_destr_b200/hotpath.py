@@ -88,7 +88,7 @@ class TransformerHalf(nn.Module):
         B, C, H, W = features.shape
         N = H * W
         Q = selected_objects.shape[1]
-        x = features.flatten(2).transpose(1, 2).reshape(B * N, C).to(BF16)
+        x = features.flatten(2).transpose(1, 2).reshape(B * N, C).to(BF16).contiguous()  # (B = 1: the reshape is a column-major view)
         _, pos = ops.sine_pos2d(mask, want_f32=False, want_bf16=True)  # K1 (position_encoding_cdetr.py:39-63)
         pos = pos.view(B * N, C)
         kpm = mask.flatten(1).contiguous()

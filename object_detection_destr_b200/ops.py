@@ -269,6 +269,8 @@ def gemm(a: Tensor, b: Tensor, *, b_kn: bool = False, bias: Optional[Tensor] = N
     Returns out, or (out, out2)."""
     M, K = a.shape
     N = b.shape[1] if b_kn else b.shape[0]
+    if a.stride(1) != 1 or a.stride(0) % 8 != 0:  # e.g. a transposed view: TMA needs rows of contiguous elements
+        a = a.contiguous()
     a = _mat(a, "a", M, K)
     b = _mat(b, "b", K if b_kn else N, N if b_kn else K)
     if out is None:

@@ -50,6 +50,8 @@ def config4():
     model = TransformerHalf(Namespace(hidden_dim=256, num_encoder_blocks=6, num_decoder_blocks=1, num_cls=91))
     disable_dropout(model).to(dev).train()
     rt = model.runtime()
+    rt.dc = rt._drop_config()  # (what HotPathRuntime.forward() sets up: dropout is disabled here, p = 0 everywhere)
+    rt._attn_bits = None
     x = torch.randn(B * N, 256, generator=g).bfloat16().to(dev)
     mask = torch.zeros(B, H, W, dtype=torch.bool, device=dev)
     _, pos = ops.sine_pos2d(mask, want_f32=False, want_bf16=True)
