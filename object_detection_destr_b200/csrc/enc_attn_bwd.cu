@@ -4,7 +4,7 @@
 // F.multi_head_attention_forward as called at src/model/blocks/encoder_block.py:97-103).
 // Scores are recomputed from Q,K and the saved log-sum-exp; nothing N x N is ever stored.
 //
-// Work item = one 128-key tile j of one (batch, head); a persistent CTA (one per SM, 576 threads) walks
+// Work item = one 128-key tile j of one (batch, head); a persistent CTA (one per SM, 640 threads) walks
 // its items and, inside an item, the queries in 64-row sub-tiles u.  Everything is computed TRANSPOSED
 // (rows = keys) so that thread <-> key row <-> TMEM lane:
 //   S^T_u  = K_j . Q_u^T            (SS MMA, N = 64)      -> TMEM ST[g]
@@ -14,17 +14,20 @@
 //   dK_j += dS^T_u . Q_u            (SS MMA, A = dS^T in smem K-major SW128, B = Q_u MN-major)
 //   dQ_p  = dS_p . K_j              once per PAIR p of sub-tiles (M = 128 queries): A = the two dS^T blocks
 //                                   of the pair read MN-major, B = K_j MN-major
-// Two compute groups of 8 warps ping-pong on the sub-tiles (group g owns ST[g]/DPT[g]/PT[g]), so the
-// tensor pipe works on sub-tile u+1 while the exp/FMA pipes work on u -- at d_head = 32 both are busy
-// (16 k exps = 1024 MUFU cycles against ~800 tensor cycles per 128x128 tile).  Warp w of a group:
-// TMEM lanes 32*(w%4).., query columns 32*((w/4)%2).. of the sub-tile.
-// Nothing in the loop waits for a drain: dQ_p is pulled out of TMEM one pair later (group p&1,
-// red.global.add.v4.f32 into an fp32 accumulator that a small kernel converts to bf16), dV_j / dK_j are
-// double buffered in TMEM by item parity and stored while the next item is already running, and the
-// TMA / MMA warps run ahead across item boundaries.
+// Two compute groups of 8 warps alternate on the sub-tiles (group g = u & 1).  S^T / dP^T live in THREE TMEM
+// buffers (u % 3): S^T/dP^T of sub-tile u+3 are issued as soon as the gradients of u are, i.e. a whole group
+// iteration before the group that owns u+3 asks for them -- no compute warp ever waits for the
+// arrive -> MMA warp -> tensor pipe -> commit round trip (with two buffers that wait was ~25 % of the warps'
+// time).  P^T (bf16) overwrites the columns of S^T its own warp has already read (in-place, like the
+// forward), which is what pays for the third buffer.  Warp w of a group: TMEM lanes 32*(w%4).., query
+// columns 32*((w/4)%2).. of the sub-tile.
+// dQ_p is pulled out of TMEM one pair later (group p&1, red.global.add.v4.f32 into an fp32 accumulator that a
+// small kernel converts to bf16); dV_j / dK_j are stored right after the first sub-tile of the next item (the
+// next item's first gradient MMA waits for that drain: one bubble per 2*ceil(N/128) sub-tiles); the TMA / MMA
+// warps run ahead across item boundaries.
 //
-// TMEM (512 columns): ST0 [0,64) DPT0 [64,128) ST1 [128,192) DPT1 [192,256) DV0/DK0 [256,320)
-//                     DV1/DK1 [320,384) DQ0 [384,416) DQ1 [416,448) PT0 [448,480) PT1 [480,512)
+// TMEM (512 columns): buffer b = u % 3 at 128 b: ST [0,64) DPT [64,128), P^T of the warp owning query columns
+//                     32 cg.. in ST columns [32 cg, 32 cg + 16);  DV [384,416) DK [416,448) DQ0 [448,480) DQ1 [480,512)
 #include "../../include/destr_b200.h"
 #include "common.cuh"
 #include "sm100_ptx.cuh"
@@ -36,13 +39,13 @@ namespace {
 constexpr int DH = 32;
 constexpr int BT = 128;  // keys per item, queries per pair
 constexpr int BQ = 64;   // queries per sub-tile
-constexpr int QSTAGES = 4;
-constexpr int NTHREADS = 576;  // 16 compute warps + TMA warp + MMA warp
+constexpr int QSTAGES = 8;
+constexpr int NTHREADS = 640;  // 16 compute warps + TMA warp + 3 MMA-issuing warps
 constexpr uint32_t KV_BYTES = BT * DH * 2;       // 8192
 constexpr uint32_t Q_BYTES = BQ * DH * 2;        // 4096
 constexpr uint32_t STAT_BYTES = 2 * BQ * 4;      // 512: -lse[64] | -delta[64]
 constexpr uint32_t DS_BLOCK_BYTES = BT * 128;    // 16384: [128 key rows][64 queries] bf16, SW128
-constexpr uint32_t C_ST = 0, C_DPT = 64, C_SBUF = 128, C_DV = 256, C_DK = 288, C_ACC = 64, C_DQ = 384, C_PT = 448;
+constexpr uint32_t C_ST = 0, C_DPT = 64, C_SBUF = 128, C_DV = 384, C_DK = 416, C_DQ = 448;
 
 struct __align__(1024) Smem {
   uint8_t k[2][KV_BYTES];
@@ -53,14 +56,17 @@ struct __align__(1024) Smem {
   float stat[QSTAGES][2 * BQ];
   uint64_t kv_full[2], kv_free[2];
   uint64_t q_full[QSTAGES], q_empty[QSTAGES];
-  uint64_t sdp_full[2], pds_full[2];
+  uint64_t sdp_full[3], pds_full[3];  // S^T/dP^T ready, P^T/dS^T written: both by TMEM buffer (u % 3) -- a group can
+                                      // never be two phases ahead of the MMA warp on a buffer (it can on its own parity)
+  uint64_t g_done[3];                 // dV / dK of the sub-tile in TMEM buffer b have completed (P^T consumed)
   uint64_t dq_done[2], dq_free[2];
-  uint64_t dkv_full[2], dkv_free[2];
+  uint64_t dkv_full, dkv_free;
   uint32_t tmem_base;
 };
 
 struct Knobs {
   uint32_t mn64_lbo, mn64_sbo, kmaj_lbo, a_mn_lbo, a_mn_sbo, a_mn_kstep;
+  uint32_t dbg;  // timing experiments only (knob 18): 1 no dV, 2 no dK, 4 no dQ, 8 no softmax-backward math, 16 no S/dP, 32 no dQ atomics, 64 no dK/dV stores
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -105,14 +111,17 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     tma_prefetch_desc(&tm_do);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&sm.kv_full[s], 1);
-      mbar_init(&sm.kv_free[s], 1);
-      mbar_init(&sm.sdp_full[s], 1);
-      mbar_init(&sm.pds_full[s], 256);
-      mbar_init(&sm.dq_done[s], 1);
-      mbar_init(&sm.dq_free[s], 256);
-      mbar_init(&sm.dkv_full[s], 1);
-      mbar_init(&sm.dkv_free[s], 512);
+      mbar_init(&sm.kv_free[s], 2);
+      mbar_init(&sm.dq_done[s], 2);
+      mbar_init(&sm.dq_free[s], 8);
     }
+    for (int s = 0; s < 3; ++s) {
+      mbar_init(&sm.sdp_full[s], 1);
+      mbar_init(&sm.g_done[s], 1);
+      mbar_init(&sm.pds_full[s], 8);
+    }
+    mbar_init(&sm.dkv_full, 1);
+    mbar_init(&sm.dkv_free, 16);
     for (int s = 0; s < QSTAGES; ++s) {
       mbar_init(&sm.q_full[s], 1);
       mbar_init(&sm.q_empty[s], 1);
@@ -140,20 +149,28 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const float* st_bh = stats + (static_cast<size_t>(im.b) * heads + im.h) * (2 * npairs) * (2 * BQ);
         for (int u = 0; u < 2 * npairs; ++u, ++U) {
           const int s = U % QSTAGES;
-          mbar_wait_backoff(&sm.q_empty[s], ((U / QSTAGES) & 1) ^ 1, 2);
-          mbar_arrive_expect_tx(&sm.q_full[s], 2 * Q_BYTES + STAT_BYTES);
-          tma_load_2d(sm.q[s], &tm_q, &sm.q_full[s], im.h * DH, row_base + u * BQ);
-          tma_load_2d(sm.d_o[s], &tm_do, &sm.q_full[s], im.h * DH, row_base + u * BQ);
+          mbar_wait(&sm.q_empty[s], ((U / QSTAGES) & 1) ^ 1, 2);
+          if (kn.dbg & 128) {
+            mbar_arrive_expect_tx(&sm.q_full[s], STAT_BYTES);
+          } else {
+            mbar_arrive_expect_tx(&sm.q_full[s], 2 * Q_BYTES + STAT_BYTES);
+            tma_load_2d(sm.q[s], &tm_q, &sm.q_full[s], im.h * DH, row_base + u * BQ);
+            tma_load_2d(sm.d_o[s], &tm_do, &sm.q_full[s], im.h * DH, row_base + u * BQ);
+          }
           bulk_load(sm.stat[s], st_bh + static_cast<size_t>(u) * (2 * BQ), STAT_BYTES, &sm.q_full[s]);
         }
       }
     }
     __syncwarp();
-  } else if (warp == 17) {
-    // ------------------------------ MMA issuer ------------------------------
-    // One thread issues every MMA, so its instruction stream is the critical path between "group g has
-    // consumed S/dP" and "group g's next S/dP is ready": descriptors are compile-time constants plus a
-    // shifted address, and everything the next S/dP needs is prepared BEFORE waiting for the group.
+  } else if (warp >= 17) {
+    // ------------------------------ MMA issuers ------------------------------
+    // At d_head = 32 the MMAs are small (16-64 tensor cycles each) and ~20 of them, 3 commits and 3-4 barrier waits
+    // are needed per sub-tile: ONE issuing thread took ~1100 cycles per sub-tile for that (measured with clock64),
+    // co-critical with the compute groups.  So three single-thread issuers, one per SM sub-partition:
+    //   warp 17  S^T / dP^T of sub-tile U+3 into TMEM buffer U % 3 once the gradients of U have read P^T from it
+    //   warp 18  dV, dK of sub-tile U (releases the Q/dO stage and the TMEM buffer)
+    //   warp 19  dQ of pair Pf
+    // MMAs of different issuers are only ordered through mbarriers (tcgen05.commit), never through program order.
     if (elect_one()) {
       constexpr uint32_t id_sT = umma_idesc_bf16(BT, BQ, false, false);   // K-major x K-major, N = 64
       constexpr uint32_t id_kn = umma_idesc_bf16(BT, DH, false, true);    // A K-major (TMEM/smem), B MN-major
@@ -164,70 +181,88 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       constexpr uint64_t D_AMN128 = umma_desc_const(16384, 1024, SWZ_128B); // dS^T pair as MN-major A (k-step 2048 B)
       const uint32_t a_k = smem_u32(sm.k[0]) >> 4, a_v = smem_u32(sm.v[0]) >> 4, a_q = smem_u32(sm.q[0]) >> 4,
                      a_do = smem_u32(sm.d_o[0]) >> 4, a_ds = smem_u32(sm.ds[0][0]) >> 4;
-      const int Utot = 2 * Ptot;
-      // S^T / dP^T of flat sub-tile U (item parity kb) into the buffers of group U & 1
-      auto issue_sdp = [&](int U, int kb) {
-        const uint32_t g = U & 1, s = U % QSTAGES;
-        const uint64_t dk_ = D_KMAJ64 + (a_k + kb * (KV_BYTES >> 4)), dv_ = D_KMAJ64 + (a_v + kb * (KV_BYTES >> 4));
-        const uint64_t dq_ = D_KMAJ64 + (a_q + s * (Q_BYTES >> 4)), ddo_ = D_KMAJ64 + (a_do + s * (Q_BYTES >> 4));
-        umma_ss(tmem + g * C_SBUF + C_ST, dk_, dq_, id_sT, 0u);
-        umma_ss(tmem + g * C_SBUF + C_ST, dk_ + 2, dq_ + 2, id_sT, 1u);
-        umma_ss(tmem + g * C_SBUF + C_DPT, dv_, ddo_, id_sT, 0u);
-        umma_ss(tmem + g * C_SBUF + C_DPT, dv_ + 2, ddo_ + 2, id_sT, 1u);
-        tc_commit(&sm.sdp_full[g]);
-      };
-      if (Utot > 0) {
-        mbar_wait_backoff(&sm.kv_full[0], 0, 3);
-        for (int U = 0; U < 2 && U < Utot; ++U) {
-          mbar_wait_backoff(&sm.q_full[U], 0, 4);
+      const int Utot = 2 * Ptot, SUB = 2 * npairs;
+      if (warp == 17) {
+        // ---- S^T = K_j Q_u^T, dP^T = V_j dO_u^T ----
+        int it = 0, u = 0, b3 = 0, ph3 = 0;
+        for (int U = 0; U < Utot; ++U) {
+          const uint32_t s = U % QSTAGES, kb = it & 1;
+          if (U >= 3) mbar_wait(&sm.g_done[b3], ph3 ^ 1, 3);  // dV(U-3) has read P^T out of this buffer
+          if (u == 0) mbar_wait_backoff(&sm.kv_full[kb], (it >> 1) & 1, 3);
+          mbar_wait_backoff(&sm.q_full[s], (U / QSTAGES) & 1, 4);
           tc_fence_after();
-          issue_sdp(U, 0);
+          const uint64_t dk_ = D_KMAJ64 + (a_k + kb * (KV_BYTES >> 4)), dv_ = D_KMAJ64 + (a_v + kb * (KV_BYTES >> 4));
+          const uint64_t dq_ = D_KMAJ64 + (a_q + s * (Q_BYTES >> 4)), ddo_ = D_KMAJ64 + (a_do + s * (Q_BYTES >> 4));
+          const uint32_t t = tmem + b3 * C_SBUF;
+          if (!(kn.dbg & 16)) {
+            umma_ss(t + C_ST, dk_, dq_, id_sT, 0u);
+            umma_ss(t + C_ST, dk_ + 2, dq_ + 2, id_sT, 1u);
+            umma_ss(t + C_DPT, dv_, ddo_, id_sT, 0u);
+            umma_ss(t + C_DPT, dv_ + 2, ddo_ + 2, id_sT, 1u);
+          }
+          tc_commit(&sm.sdp_full[b3]);
+          if (++u == SUB) {
+            tc_commit(&sm.kv_free[kb]);  // (1 of 2 arrivals) every S^T / dP^T of the item has been issued
+            u = 0;
+            ++it;
+          }
+          if (++b3 == 3) { b3 = 0; ph3 ^= 1; }
         }
-      }
-      int it = 0, p = 0;  // item / pair within the item of sub-tile U
-      for (int U = 0; U < Utot; ++U) {
-        const int Pf = U >> 1, g = U & 1, s = U % QSTAGES, kb = it & 1, pb = Pf & 1;
-        // ---- stage the group's NEXT sub-tile (U+2 = pair Pf+1): operands landed? ----
-        const bool has_next = U + 2 < Utot;
-        const int it_n = (p + 1 == npairs) ? it + 1 : it;
-        if (has_next) {
-          if (g == 0 && p + 1 == npairs) mbar_wait_backoff(&sm.kv_full[it_n & 1], (it_n >> 1) & 1, 3);
-          mbar_wait_backoff(&sm.q_full[(U + 2) % QSTAGES], ((U + 2) / QSTAGES) & 1, 4);
-        }
-        mbar_wait(&sm.pds_full[g], Pf & 1, 5);
-        tc_fence_after();
-        if (has_next) issue_sdp(U + 2, it_n & 1);  // the group waits for this: first into the tensor pipe
-        // ---- gradients of sub-tile U: off the critical path, queue up behind ----
-        if (p == 0 && g == 0) {
-          mbar_wait_backoff(&sm.dkv_free[kb], ((it >> 1) & 1) ^ 1, 6);  // accumulators of item it-2 drained
+      } else if (warp == 18) {
+        // ---- dV_j += P^T_u dO_u, dK_j += dS^T_u Q_u ----
+        int it = 0, u = 0, b3 = 0, ph3 = 0;
+        for (int U = 0; U < Utot; ++U) {
+          const uint32_t g = U & 1, s = U % QSTAGES, pb = (U >> 1) & 1;
+          mbar_wait(&sm.pds_full[b3], ph3, 5);  // group g has written P^T (TMEM, in place of S^T) and dS^T (smem)
+          if (u == 0 && it > 0) mbar_wait_backoff(&sm.dkv_free, (it - 1) & 1, 6);  // dV / dK of item it-1 drained
           tc_fence_after();
+          const uint32_t first = (u == 0) ? 0u : 1u;
+          const uint64_t ddo_mn = D_MN64 + (a_do + s * (Q_BYTES >> 4)), dq_mn = D_MN64 + (a_q + s * (Q_BYTES >> 4));
+          const uint64_t dds_k = D_KMAJ128 + (a_ds + (pb * 2 + g) * (DS_BLOCK_BYTES >> 4));
+          const uint32_t t_pt = tmem + b3 * C_SBUF + C_ST;
+          if (!(kn.dbg & 1))
+#pragma unroll
+            for (int ks = 0; ks < BQ / 16; ++ks)  // k-step ks = 16 queries: warp column cg = ks / 2, chunk ks % 2
+              umma_ts(tmem + C_DV, t_pt + (ks >> 1) * 32 + (ks & 1) * 8, ddo_mn + ks * 64, id_kn, (ks > 0) ? 1u : first);
+          if (!(kn.dbg & 2))
+#pragma unroll
+            for (int ks = 0; ks < BQ / 16; ++ks)
+              umma_ss(tmem + C_DK, dds_k + ks * 2, dq_mn + ks * 64, id_kn, (ks > 0) ? 1u : first);
+          tc_commit(&sm.q_empty[s]);
+          tc_commit(&sm.g_done[b3]);
+          if (g == 1) tc_commit(&sm.dq_done[pb]);  // (1 of 2) dK has read both dS^T blocks of the pair
+          if (++u == SUB) {
+            tc_commit(&sm.dkv_full);
+            u = 0;
+            ++it;
+          }
+          if (++b3 == 3) { b3 = 0; ph3 ^= 1; }
         }
-        const uint32_t first = (p == 0 && g == 0) ? 0u : 1u;
-        const uint64_t ddo_mn = D_MN64 + (a_do + s * (Q_BYTES >> 4)), dq_mn = D_MN64 + (a_q + s * (Q_BYTES >> 4));
-        const uint64_t dds_k = D_KMAJ128 + (a_ds + (pb * 2 + g) * (DS_BLOCK_BYTES >> 4));
-#pragma unroll
-        for (int ks = 0; ks < BQ / 16; ++ks)  // dV += P^T_u . dO_u
-          umma_ts(tmem + C_DV + kb * C_ACC, tmem + C_PT + g * 32 + ks * 8, ddo_mn + ks * 64, id_kn,
-                  (ks > 0) ? 1u : first);
-#pragma unroll
-        for (int ks = 0; ks < BQ / 16; ++ks)  // dK += dS^T_u . Q_u
-          umma_ss(tmem + C_DK + kb * C_ACC, dds_k + ks * 2, dq_mn + ks * 64, id_kn, (ks > 0) ? 1u : first);
-        tc_commit(&sm.q_empty[s]);
-        if (g == 1) {
-          // dQ_pair = dS_pair . K_j   (M = 128 queries spanning the pair's two dS^T blocks)
+      } else if (warp == 19) {
+        // ---- dQ_pair = dS_pair K_j   (M = 128 queries spanning the pair's two dS^T blocks) ----
+        int it = 0, p = 0, b3 = 0, ph3 = 0;  // buffer / parity of the pair's first sub-tile
+        for (int Pf = 0; Pf < Ptot; ++Pf) {
+          const uint32_t kb = it & 1, pb = Pf & 1;
+          int b1 = b3 + 1, ph1 = ph3;
+          if (b1 == 3) { b1 = 0; ph1 ^= 1; }
+          mbar_wait(&sm.pds_full[b3], ph3, 5);
+          mbar_wait(&sm.pds_full[b1], ph1, 5);
           mbar_wait_backoff(&sm.dq_free[pb], ((Pf >> 1) & 1) ^ 1, 7);
           tc_fence_after();
           const uint64_t dds_mn = D_AMN128 + (a_ds + pb * 2 * (DS_BLOCK_BYTES >> 4));
           const uint64_t dk_mn = D_MN64 + (a_k + kb * (KV_BYTES >> 4));
+          if (!(kn.dbg & 4))
 #pragma unroll
-          for (int ks = 0; ks < BT / 16; ++ks)
-            umma_ss(tmem + C_DQ + pb * 32, dds_mn + ks * 128, dk_mn + ks * 64, id_nn, ks > 0);
-          tc_commit(&sm.dq_done[pb]);
-          if (p == npairs - 1) {
-            tc_commit(&sm.dkv_full[kb]);
-            tc_commit(&sm.kv_free[kb]);
+            for (int ks = 0; ks < BT / 16; ++ks)
+              umma_ss(tmem + C_DQ + pb * 32, dds_mn + ks * 128, dk_mn + ks * 64, id_nn, ks > 0);
+          tc_commit(&sm.dq_done[pb]);  // (2 of 2)
+          if (++p == npairs) {
+            tc_commit(&sm.kv_free[kb]);  // (2 of 2) K_j is no longer needed
+            p = 0;
+            ++it;
           }
-          if (++p == npairs) { p = 0; ++it; }
+          b3 += 2;
+          if (b3 >= 3) { b3 -= 3; ph3 ^= 1; }
         }
       }
     }
@@ -248,9 +283,10 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       tmem_ld_x16(tmem + lane_addr + C_DQ + pb * 32 + cg * 16, r);
       tc_wait_ld();
       tc_fence_before();
-      mbar_arrive(&sm.dq_free[pb]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.dq_free[pb]);
       const int qrow = pair * BT + krow;
-      if (qrow < N) {
+      if (qrow < N && !(kn.dbg & 32)) {
         float* dst = dq_acc + (static_cast<size_t>(im.b * N + qrow) * heads + im.h) * DH + cg * 16;
 #pragma unroll
         for (int c = 0; c < 4; ++c)
@@ -259,16 +295,16 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       }
     };
     auto drain_dkv = [&](int it, const Item& im) {  // group 0 stores dV_j, group 1 stores dK_j
-      const int kb = it & 1;
-      mbar_wait(&sm.dkv_full[kb], (it >> 1) & 1, 9);
+      mbar_wait(&sm.dkv_full, it & 1, 9);
       tc_fence_after();
       uint32_t r[16];
-      tmem_ld_x16(tmem + lane_addr + (g == 0 ? C_DV : C_DK) + kb * C_ACC + cg * 16, r);
+      tmem_ld_x16(tmem + lane_addr + (g == 0 ? C_DV : C_DK) + cg * 16, r);
       tc_wait_ld();
       tc_fence_before();
-      mbar_arrive(&sm.dkv_free[kb]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.dkv_free);
       const int key = im.j * BT + krow;
-      if (key < N) {
+      if (key < N && !(kn.dbg & 64)) {
         // dV = (dropped P)^T dO: the 1/(1-p) of the forward's dropout is applied here, once per output
         const float f = (g == 0) ? (DROP ? drop_scale(dp.thr16) : 1.f) : scale;
         uint32_t o[8];
@@ -283,18 +319,18 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     };
 
     const uint32_t sb = smem_u32(&sm);
-    const uint32_t b_sdp = sb + offsetof(Smem, sdp_full) + g * 8, b_pds = sb + offsetof(Smem, pds_full) + g * 8;
+    const uint32_t b_sdp = sb + offsetof(Smem, sdp_full), b_pds = sb + offsetof(Smem, pds_full);
     const uint32_t b_qfull = sb + offsetof(Smem, q_full), b_dqdone = sb + offsetof(Smem, dq_done);
     const uint32_t a_stat = sb + offsetof(Smem, stat) + cg * 128;                 // -lse of my 32 queries (+256: -delta)
     const uint32_t a_ds = sb + offsetof(Smem, ds) + g * DS_BLOCK_BYTES + krow * 128;  // my dS^T row (pair parity 0)
-    const uint32_t t_st = tmem + lane_addr + g * C_SBUF + C_ST + cg * 32;
-    const uint32_t t_pt = tmem + lane_addr + C_PT + g * 32 + cg * 16;
+    const uint32_t t_mine = tmem + lane_addr + C_ST + cg * 32;  // my 32 query columns of S^T (buffer 0)
     const uint32_t swz = krow & 7;
     const float drop_s = drop_scale(dp.thr16);
     const uint64_t ds2s = pack_f32x2(drop_s, drop_s);
 
     Item prev{0, 0, 0};
     uint32_t Pf = 0;
+    uint32_t b3 = g, ph3 = 0;  // TMEM buffer (U % 3) and barrier parity ((U / 3) & 1) of my sub-tile U = 2 Pf + g
     for (int it = 0; it < my_items; ++it) {
       const Item im = decode_item(blockIdx.x + it * gridDim.x, nkt, heads);
       const int key = im.j * BT + krow;
@@ -307,11 +343,16 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const uint32_t dbits = dnext;
         if (DROP && p + 1 < npairs) dnext = dw[static_cast<size_t>(4 * (p + 1)) * (nkt * BT)];
         const uint32_t U = 2 * Pf + g, s = U % QSTAGES, pb = Pf & 1;
-        mbar_wait_a(b_sdp, Pf & 1, 10);
+        mbar_wait_a(b_sdp + b3 * 8, ph3, 10);
         mbar_wait_a(b_qfull + s * 8, (U / QSTAGES) & 1, 11);  // long complete: makes the TMA-written stats visible
         tc_fence_after();
+        const uint32_t t_st = t_mine + b3 * C_SBUF, b_pds_u = b_pds + b3 * 8;
+        b3 += 2;
+        if (b3 >= 3) { b3 -= 3; ph3 ^= 1; }
         const uint32_t stat_s = a_stat + s * STAT_BYTES;
         const uint32_t ds_row = a_ds + pb * (2 * DS_BLOCK_BYTES);
+        if (kn.dbg & 8) mbar_wait_a(b_dqdone + pb * 8, ((Pf >> 1) & 1) ^ 1, 12);
+        if (!(kn.dbg & 8))
 #pragma unroll
         for (int hc = 0; hc < 2; ++hc) {  // two chunks of 16 query columns (keeps the live set small)
           uint32_t st[16], dpv[16];
@@ -355,16 +396,17 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 #pragma unroll
             for (int i = 0; i < 8; ++i) pk[i] = dsk[i] = 0u;
           }
-          tmem_st_x8(t_pt + hc * 8, pk);
+          tmem_st_x8(t_st + hc * 8, pk);  // P^T over S^T columns this warp has already read
 #pragma unroll
           for (int c = 0; c < 2; ++c)  // 8 queries per 16-byte chunk; chunk index = 4*cg + 2*hc + c
             sts_u4(ds_row + (((4 * cg + 2 * hc + c) ^ swz) << 4), dsk[4 * c], dsk[4 * c + 1], dsk[4 * c + 2],
                    dsk[4 * c + 3]);
         }
-        tc_wait_st();
-        fence_proxy_async_smem();
+        if (!(kn.dbg & 2048)) tc_wait_st();
+        if (!(kn.dbg & 1024)) fence_proxy_async_smem();
         tc_fence_before();
-        mbar_arrive_a(b_pds);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_a(b_pds_u);  // one arrival per warp (256 same-address arrivals serialise)
 
         // ---- deferred drains (their MMAs were issued one pair / one item ago) ----
         if (Pf > 0 && ((Pf - 1) & 1) == static_cast<uint32_t>(g)) {
@@ -478,7 +520,7 @@ extern "C" int destr_enc_attn_bwd(const void* q, const void* k, const void* v, i
                                                             dq_acc, B, N, Np, heads);
   DESTR_LAUNCH_CHECK();
   Knobs kn{(uint32_t)g_knobs[0], (uint32_t)g_knobs[1], (uint32_t)g_knobs[2],
-           (uint32_t)g_knobs[6], (uint32_t)g_knobs[7], (uint32_t)g_knobs[8]};
+           (uint32_t)g_knobs[6], (uint32_t)g_knobs[7], (uint32_t)g_knobs[8], (uint32_t)g_knobs[18]};
   const int n_items = B * heads * ceil_div(N, BT);
   int grid = n_items < 148 ? n_items : 148;  // persistent: one CTA per SM
   if (g_knobs[13] > 0 && g_knobs[13] < grid) grid = g_knobs[13];

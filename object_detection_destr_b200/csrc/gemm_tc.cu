@@ -717,8 +717,10 @@ extern "C" int destr_gemm_bf16(const void* a, int lda, const void* b, int ldb, i
   ga.add2 = static_cast<const bf16*>(add2), ga.ldadd2 = ldadd2;
   ga.out2 = static_cast<bf16*>(out2), ga.ldo2 = ldo2;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // 128-wide tiles when the 256-wide ones would leave most SMs without a tile
-  const bool narrow = ceil_div(M, BM) * ceil_div(N, 256) < 100 || N % 256 != 0;
+  // 128-wide tiles when the 256-wide ones would leave most SMs without a tile (knob 17: 1 / 2 force 128 / 256)
+  bool narrow = ceil_div(M, BM) * ceil_div(N, 256) < 100 || N % 256 != 0;
+  if (g_knobs[17] == 1) narrow = true;
+  if (g_knobs[17] == 2 && N % 256 == 0) narrow = false;
   if (b_kn) return narrow ? launch_gemm<128, true, EPI_STORE>(a, lda, b, ldb, ga, st)
                           : launch_gemm<256, true, EPI_STORE>(a, lda, b, ldb, ga, st);
   return narrow ? launch_gemm<128, false, EPI_STORE>(a, lda, b, ldb, ga, st)

@@ -167,29 +167,30 @@ __device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
 #ifndef DESTR_WAIT_TIMEOUT_NS
 #define DESTR_WAIT_TIMEOUT_NS 4000000000ull
 #endif
+// The global timer is only consulted every 4096 failed polls: reading it costs far more than a poll, and a wait that
+// misses its first try is the normal case in the producer / consumer pipelines.
+static __device__ __noinline__ void mbar_wait_timeout(int tag, uint32_t parity) {
+  printf("destr_b200: mbarrier wait timeout tag=%d block=(%d,%d,%d) thread=%d parity=%u\n", tag, blockIdx.x, blockIdx.y,
+         blockIdx.z, threadIdx.x, parity);
+  __trap();
+}
+#define DESTR_SPIN_CHECK(spins, t0, tag, parity)                                   \
+  if ((((++spins)) & 0xfff) == 0) {                                                \
+    const uint64_t now_ = globaltimer_ns();                                        \
+    if (t0 == 0) t0 = now_;                                                        \
+    else if (now_ - t0 > DESTR_WAIT_TIMEOUT_NS) mbar_wait_timeout(tag, parity);    \
+  }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = globaltimer_ns();
+  uint64_t t0 = 0;
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (((++spins) & 0x3ff) == 0 && globaltimer_ns() - t0 > DESTR_WAIT_TIMEOUT_NS) {
-      printf("destr_b200: mbarrier wait timeout tag=%d block=(%d,%d,%d) thread=%d parity=%u\n", tag,
-             blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, parity);
-      __trap();
-    }
-  }
+  while (!mbar_try_wait(bar, parity)) { DESTR_SPIN_CHECK(spins, t0, tag, parity) }
 }
 
 static __device__ __noinline__ void mbar_wait_slow_a(uint32_t bar, uint32_t parity, int tag) {
-  const uint64_t t0 = globaltimer_ns();
+  uint64_t t0 = 0;
   uint32_t spins = 0;
-  while (!mbar_try_wait_a(bar, parity)) {
-    if (((++spins) & 0x3ff) == 0 && globaltimer_ns() - t0 > DESTR_WAIT_TIMEOUT_NS) {
-      printf("destr_b200: mbarrier wait timeout tag=%d block=(%d,%d,%d) thread=%d parity=%u\n", tag,
-             blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, parity);
-      __trap();
-    }
-  }
+  while (!mbar_try_wait_a(bar, parity)) { DESTR_SPIN_CHECK(spins, t0, tag, parity) }
 }
 // wait on a 32-bit shared address; the (rare) spin path is an out-of-line call so hot loops stay compact
 __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity, int tag = 0) {
@@ -200,15 +201,11 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity, int t
 // take issue slots from the compute warps sharing the SM sub-partition.
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, int tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = globaltimer_ns();
+  uint64_t t0 = 0;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     __nanosleep(32);
-    if (((++spins) & 0x3ff) == 0 && globaltimer_ns() - t0 > DESTR_WAIT_TIMEOUT_NS) {
-      printf("destr_b200: mbarrier wait timeout tag=%d block=(%d,%d,%d) thread=%d parity=%u\n", tag,
-             blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, parity);
-      __trap();
-    }
+    DESTR_SPIN_CHECK(spins, t0, tag, parity)
   }
 }
 

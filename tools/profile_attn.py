@@ -6,7 +6,10 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
-from object_detection_destr_b200 import ops  # noqa: E402
+from object_detection_destr_b200 import ops, _lib  # noqa: E402
+
+for kv in filter(None, os.environ.get("KNOBS", "").split(",")):  # e.g. KNOBS=18=127,14=1 (debug knobs)
+    _lib.lib.destr_debug_knob(int(kv.split("=")[0]), int(kv.split("=")[1]))
 
 B, N = int(os.environ.get("PB", 8)), int(os.environ.get("PN", 1050))
 g = torch.Generator().manual_seed(0)
