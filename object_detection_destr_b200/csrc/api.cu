@@ -56,6 +56,32 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_
   return 0;
 }
 
+// 2-D fp32 tensor map (used as the destination of TMA reduce-adds)
+int make_tmap_f32_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                     uint32_t box_cols, CUtensorMapSwizzle swizzle) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled not available (driver too old or no GPU)");
+    return 1;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * 4) & 15)) {
+    set_error("TMA operand must be 16-byte aligned with a row pitch that is a multiple of 4 floats");
+    return 2;
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * 4};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (fp32) failed with CUresult " + std::to_string(static_cast<int>(r)));
+    return 1;
+  }
+  return 0;
+}
+
 // Opt-in to more than 48 KB of dynamic shared memory.  The attribute belongs to (kernel, device): a process-wide
 // "done" flag would leave a second GPU of the same process without it, so the cache is keyed by both.
 int ensure_dyn_smem(const void* kernel, size_t bytes) {

@@ -37,6 +37,9 @@ void set_error(const std::string& msg);  // api.cu
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swizzle);
 
+int make_tmap_f32_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                     uint32_t box_cols, CUtensorMapSwizzle swizzle);
+
 // opt-in to `bytes` of dynamic shared memory for `kernel` on the current device (cached per kernel AND device)
 int ensure_dyn_smem(const void* kernel, size_t bytes);
 #define DESTR_SMEM_OPTIN(kernel, bytes)                                             \

@@ -4,7 +4,7 @@
 // F.multi_head_attention_forward as called at src/model/blocks/encoder_block.py:97-103).
 // Scores are recomputed from Q,K and the saved log-sum-exp; nothing N x N is ever stored.
 //
-// Work item = one 128-key tile j of one (batch, head); a persistent CTA (one per SM, 640 threads) walks
+// Work item = one 128-key tile j of one (batch, head); a persistent CTA (one per SM, 608 threads) walks
 // its items and, inside an item, the queries in 64-row sub-tiles u.  Everything is computed TRANSPOSED
 // (rows = keys) so that thread <-> key row <-> TMEM lane:
 //   S^T_u  = K_j . Q_u^T            (SS MMA, N = 64)      -> TMEM ST[g]
@@ -40,7 +40,7 @@ constexpr int DH = 32;
 constexpr int BT = 128;  // keys per item, queries per pair
 constexpr int BQ = 64;   // queries per sub-tile
 constexpr int QSTAGES = 8;
-constexpr int NTHREADS = 640;  // 16 compute warps + TMA warp + 3 MMA-issuing warps
+constexpr int NTHREADS = 608;  // 16 compute warps + TMA warp + 2 MMA-issuing warps
 constexpr uint32_t KV_BYTES = BT * DH * 2;       // 8192
 constexpr uint32_t Q_BYTES = BQ * DH * 2;        // 4096
 constexpr uint32_t STAT_BYTES = 2 * BQ * 4;      // 512: -lse[64] | -delta[64]
@@ -53,12 +53,12 @@ struct __align__(1024) Smem {
   uint8_t q[QSTAGES][Q_BYTES];
   uint8_t d_o[QSTAGES][Q_BYTES];
   uint8_t ds[2][2][DS_BLOCK_BYTES];  // [pair parity][sub-tile within the pair]
+  float dq_stage[2][BT * DH];        // [group]: dQ pair tile (128 queries x 32, SW128) on its way to the TMA reduce-add
   float stat[QSTAGES][2 * BQ];
   uint64_t kv_full[2], kv_free[2];
   uint64_t q_full[QSTAGES], q_empty[QSTAGES];
   uint64_t sdp_full[3], pds_full[3];  // S^T/dP^T ready, P^T/dS^T written: both by TMEM buffer (u % 3) -- a group can
                                       // never be two phases ahead of the MMA warp on a buffer (it can on its own parity)
-  uint64_t g_done[3];                 // dV / dK of the sub-tile in TMEM buffer b have completed (P^T consumed)
   uint64_t dq_done[2], dq_free[2];
   uint64_t dkv_full, dkv_free;
   uint32_t tmem_base;
@@ -68,11 +68,6 @@ struct Knobs {
   uint32_t mn64_lbo, mn64_sbo, kmaj_lbo, a_mn_lbo, a_mn_sbo, a_mn_kstep;
   uint32_t dbg;  // timing experiments only (knob 18): 1 no dV, 2 no dK, 4 no dQ, 8 no softmax-backward math, 16 no S/dP, 32 no dQ atomics, 64 no dK/dV stores
 };
-
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
-               : "memory");
-}
 
 struct Item {
   int b, h, j;
@@ -90,8 +85,8 @@ template <int POLYQ, bool DROP>
 __global__ void __launch_bounds__(NTHREADS, 1)
 enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                     const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
-                    const uint32_t* __restrict__ mask_bits, int words_per_row, const float* __restrict__ stats,
-                    float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv,
+                    const __grid_constant__ CUtensorMap tm_dq, const uint32_t* __restrict__ mask_bits,
+                    int words_per_row, const float* __restrict__ stats, __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv,
                     int ld_dk, int ld_dv, int N, int heads, int n_items, float scale, float scale_log2, Knobs kn,
                     DropBits dp) {
   extern __shared__ uint8_t smem_raw[];
@@ -109,22 +104,22 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
     tma_prefetch_desc(&tm_do);
+    tma_prefetch_desc(&tm_dq);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&sm.kv_full[s], 1);
       mbar_init(&sm.kv_free[s], 2);
-      mbar_init(&sm.dq_done[s], 2);
+      mbar_init(&sm.dq_done[s], 1);
       mbar_init(&sm.dq_free[s], 8);
     }
     for (int s = 0; s < 3; ++s) {
       mbar_init(&sm.sdp_full[s], 1);
-      mbar_init(&sm.g_done[s], 1);
       mbar_init(&sm.pds_full[s], 8);
     }
-    mbar_init(&sm.dkv_full, 1);
+    mbar_init(&sm.dkv_full, 2);
     mbar_init(&sm.dkv_free, 16);
     for (int s = 0; s < QSTAGES; ++s) {
       mbar_init(&sm.q_full[s], 1);
-      mbar_init(&sm.q_empty[s], 1);
+      mbar_init(&sm.q_empty[s], 2);
     }
     fence_mbar_init();
   }
@@ -166,10 +161,10 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     // ------------------------------ MMA issuers ------------------------------
     // At d_head = 32 the MMAs are small (16-64 tensor cycles each) and ~20 of them, 3 commits and 3-4 barrier waits
     // are needed per sub-tile: ONE issuing thread took ~1100 cycles per sub-tile for that (measured with clock64),
-    // co-critical with the compute groups.  So three single-thread issuers, one per SM sub-partition:
-    //   warp 17  S^T / dP^T of sub-tile U+3 into TMEM buffer U % 3 once the gradients of U have read P^T from it
-    //   warp 18  dV, dK of sub-tile U (releases the Q/dO stage and the TMEM buffer)
-    //   warp 19  dQ of pair Pf
+    // co-critical with the compute groups.  So two single-thread issuers on different SM sub-partitions:
+    //   warp 17  dV(U) then S^T / dP^T of sub-tile U+3 into the TMEM buffer dV(U) has just read P^T from -- same
+    //            thread, so the tensor pipe orders them and the refill needs no barrier round trip
+    //   warp 18  dK(U) and, every second sub-tile, dQ of the pair
     // MMAs of different issuers are only ordered through mbarriers (tcgen05.commit), never through program order.
     if (elect_one()) {
       constexpr uint32_t id_sT = umma_idesc_bf16(BT, BQ, false, false);   // K-major x K-major, N = 64
@@ -183,86 +178,87 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                      a_do = smem_u32(sm.d_o[0]) >> 4, a_ds = smem_u32(sm.ds[0][0]) >> 4;
       const int Utot = 2 * Ptot, SUB = 2 * npairs;
       if (warp == 17) {
-        // ---- S^T = K_j Q_u^T, dP^T = V_j dO_u^T ----
-        int it = 0, u = 0, b3 = 0, ph3 = 0;
-        for (int U = 0; U < Utot; ++U) {
-          const uint32_t s = U % QSTAGES, kb = it & 1;
-          if (U >= 3) mbar_wait(&sm.g_done[b3], ph3 ^ 1, 3);  // dV(U-3) has read P^T out of this buffer
-          if (u == 0) mbar_wait_backoff(&sm.kv_full[kb], (it >> 1) & 1, 3);
-          mbar_wait_backoff(&sm.q_full[s], (U / QSTAGES) & 1, 4);
+        // look-ahead cursor of the S^T / dP^T issue: flat sub-tile Uq = sub-tile uq of item itq, TMEM buffer bq
+        int Uq = 0, itq = 0, uq = 0, bq = 0;
+        auto issue_sdp = [&]() {
+          const uint32_t s = Uq % QSTAGES, kb = itq & 1;
+          if (uq == 0) mbar_wait_backoff(&sm.kv_full[kb], (itq >> 1) & 1, 3);
+          mbar_wait_backoff(&sm.q_full[s], (Uq / QSTAGES) & 1, 4);
           tc_fence_after();
           const uint64_t dk_ = D_KMAJ64 + (a_k + kb * (KV_BYTES >> 4)), dv_ = D_KMAJ64 + (a_v + kb * (KV_BYTES >> 4));
           const uint64_t dq_ = D_KMAJ64 + (a_q + s * (Q_BYTES >> 4)), ddo_ = D_KMAJ64 + (a_do + s * (Q_BYTES >> 4));
-          const uint32_t t = tmem + b3 * C_SBUF;
+          const uint32_t t = tmem + bq * C_SBUF;
           if (!(kn.dbg & 16)) {
             umma_ss(t + C_ST, dk_, dq_, id_sT, 0u);
             umma_ss(t + C_ST, dk_ + 2, dq_ + 2, id_sT, 1u);
             umma_ss(t + C_DPT, dv_, ddo_, id_sT, 0u);
             umma_ss(t + C_DPT, dv_ + 2, ddo_ + 2, id_sT, 1u);
           }
-          tc_commit(&sm.sdp_full[b3]);
-          if (++u == SUB) {
+          tc_commit(&sm.sdp_full[bq]);
+          ++Uq;
+          if (++bq == 3) bq = 0;
+          if (++uq == SUB) {
             tc_commit(&sm.kv_free[kb]);  // (1 of 2 arrivals) every S^T / dP^T of the item has been issued
-            u = 0;
-            ++it;
+            uq = 0;
+            ++itq;
           }
-          if (++b3 == 3) { b3 = 0; ph3 ^= 1; }
-        }
-      } else if (warp == 18) {
-        // ---- dV_j += P^T_u dO_u, dK_j += dS^T_u Q_u ----
+        };
+        for (int i = 0; i < 3 && Uq < Utot; ++i) issue_sdp();
         int it = 0, u = 0, b3 = 0, ph3 = 0;
         for (int U = 0; U < Utot; ++U) {
-          const uint32_t g = U & 1, s = U % QSTAGES, pb = (U >> 1) & 1;
-          mbar_wait(&sm.pds_full[b3], ph3, 5);  // group g has written P^T (TMEM, in place of S^T) and dS^T (smem)
+          const uint32_t s = U % QSTAGES;
+          mbar_wait(&sm.pds_full[b3], ph3, 5);  // the group has written P^T (TMEM, in place of S^T) and dS^T (smem)
           if (u == 0 && it > 0) mbar_wait_backoff(&sm.dkv_free, (it - 1) & 1, 6);  // dV / dK of item it-1 drained
           tc_fence_after();
-          const uint32_t first = (u == 0) ? 0u : 1u;
-          const uint64_t ddo_mn = D_MN64 + (a_do + s * (Q_BYTES >> 4)), dq_mn = D_MN64 + (a_q + s * (Q_BYTES >> 4));
-          const uint64_t dds_k = D_KMAJ128 + (a_ds + (pb * 2 + g) * (DS_BLOCK_BYTES >> 4));
+          const uint64_t ddo_mn = D_MN64 + (a_do + s * (Q_BYTES >> 4));
           const uint32_t t_pt = tmem + b3 * C_SBUF + C_ST;
           if (!(kn.dbg & 1))
 #pragma unroll
-            for (int ks = 0; ks < BQ / 16; ++ks)  // k-step ks = 16 queries: warp column cg = ks / 2, chunk ks % 2
-              umma_ts(tmem + C_DV, t_pt + (ks >> 1) * 32 + (ks & 1) * 8, ddo_mn + ks * 64, id_kn, (ks > 0) ? 1u : first);
+            for (int ks = 0; ks < BQ / 16; ++ks)  // dV += P^T_u dO_u; k-step ks = 16 queries: warp column cg = ks / 2, chunk ks % 2
+              umma_ts(tmem + C_DV, t_pt + (ks >> 1) * 32 + (ks & 1) * 8, ddo_mn + ks * 64, id_kn,
+                      (ks > 0 || u > 0) ? 1u : 0u);
+          tc_commit(&sm.q_empty[s]);  // (1 of 2)
+          if (++u == SUB) {
+            tc_commit(&sm.dkv_full);  // (1 of 2)
+            u = 0;
+            ++it;
+          }
+          if (Uq < Utot) issue_sdp();  // refill the buffer dV(U) has just read: ordered behind it in the tensor pipe
+          if (++b3 == 3) { b3 = 0; ph3 ^= 1; }
+        }
+      } else if (warp == 18) {
+        int it = 0, u = 0, b3 = 0, ph3 = 0;
+        for (int U = 0; U < Utot; ++U) {
+          const uint32_t g = U & 1, s = U % QSTAGES, Pf = U >> 1, pb = Pf & 1, kb = it & 1;
+          mbar_wait(&sm.pds_full[b3], ph3, 5);
+          if (u == 0 && it > 0) mbar_wait_backoff(&sm.dkv_free, (it - 1) & 1, 6);
+          tc_fence_after();
+          const uint64_t dq_mn = D_MN64 + (a_q + s * (Q_BYTES >> 4));
+          const uint64_t dds_k = D_KMAJ128 + (a_ds + (pb * 2 + g) * (DS_BLOCK_BYTES >> 4));
           if (!(kn.dbg & 2))
 #pragma unroll
-            for (int ks = 0; ks < BQ / 16; ++ks)
-              umma_ss(tmem + C_DK, dds_k + ks * 2, dq_mn + ks * 64, id_kn, (ks > 0) ? 1u : first);
-          tc_commit(&sm.q_empty[s]);
-          tc_commit(&sm.g_done[b3]);
-          if (g == 1) tc_commit(&sm.dq_done[pb]);  // (1 of 2) dK has read both dS^T blocks of the pair
+            for (int ks = 0; ks < BQ / 16; ++ks)  // dK += dS^T_u Q_u
+              umma_ss(tmem + C_DK, dds_k + ks * 2, dq_mn + ks * 64, id_kn, (ks > 0 || u > 0) ? 1u : 0u);
+          tc_commit(&sm.q_empty[s]);  // (2 of 2)
+          if (g == 1) {
+            // dQ_pair = dS_pair K_j   (M = 128 queries spanning the pair's two dS^T blocks)
+            mbar_wait_backoff(&sm.dq_free[pb], ((Pf >> 1) & 1) ^ 1, 7);
+            tc_fence_after();
+            const uint64_t dds_mn = D_AMN128 + (a_ds + pb * 2 * (DS_BLOCK_BYTES >> 4));
+            const uint64_t dk_mn = D_MN64 + (a_k + kb * (KV_BYTES >> 4));
+            if (!(kn.dbg & 4))
+#pragma unroll
+              for (int ks = 0; ks < BT / 16; ++ks)
+                umma_ss(tmem + C_DQ + pb * 32, dds_mn + ks * 128, dk_mn + ks * 64, id_nn, ks > 0);
+            tc_commit(&sm.dq_done[pb]);  // dQ and both dK of the pair have completed: the pair's dS^T blocks are free
+          }
           if (++u == SUB) {
-            tc_commit(&sm.dkv_full);
+            tc_commit(&sm.dkv_full);     // (2 of 2)
+            tc_commit(&sm.kv_free[kb]);  // (2 of 2) K_j is no longer needed
             u = 0;
             ++it;
           }
           if (++b3 == 3) { b3 = 0; ph3 ^= 1; }
-        }
-      } else if (warp == 19) {
-        // ---- dQ_pair = dS_pair K_j   (M = 128 queries spanning the pair's two dS^T blocks) ----
-        int it = 0, p = 0, b3 = 0, ph3 = 0;  // buffer / parity of the pair's first sub-tile
-        for (int Pf = 0; Pf < Ptot; ++Pf) {
-          const uint32_t kb = it & 1, pb = Pf & 1;
-          int b1 = b3 + 1, ph1 = ph3;
-          if (b1 == 3) { b1 = 0; ph1 ^= 1; }
-          mbar_wait(&sm.pds_full[b3], ph3, 5);
-          mbar_wait(&sm.pds_full[b1], ph1, 5);
-          mbar_wait_backoff(&sm.dq_free[pb], ((Pf >> 1) & 1) ^ 1, 7);
-          tc_fence_after();
-          const uint64_t dds_mn = D_AMN128 + (a_ds + pb * 2 * (DS_BLOCK_BYTES >> 4));
-          const uint64_t dk_mn = D_MN64 + (a_k + kb * (KV_BYTES >> 4));
-          if (!(kn.dbg & 4))
-#pragma unroll
-            for (int ks = 0; ks < BT / 16; ++ks)
-              umma_ss(tmem + C_DQ + pb * 32, dds_mn + ks * 128, dk_mn + ks * 64, id_nn, ks > 0);
-          tc_commit(&sm.dq_done[pb]);  // (2 of 2)
-          if (++p == npairs) {
-            tc_commit(&sm.kv_free[kb]);  // (2 of 2) K_j is no longer needed
-            p = 0;
-            ++it;
-          }
-          b3 += 2;
-          if (b3 >= 3) { b3 -= 3; ph3 ^= 1; }
         }
       }
     }
@@ -275,7 +271,12 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const uint32_t lane_addr = static_cast<uint32_t>(wq * 32) << 16;
     const uint64_t sc2 = pack_f32x2(scale_log2, scale_log2);
 
-    auto drain_dq = [&](int Df, const Item& im, int pair) {  // flat pair Df (= pair `pair` of item im) -> dq_acc
+    // dQ of flat pair Df (= pair `pair` of item im; parity == g): TMEM -> registers -> this group's smem tile -> ONE TMA
+    // reduce-add (fp32) into dq_acc.  (Per-thread red.global.add: every lane hits a different 128-byte line, 4.8 M
+    // 16-byte atomics per launch, and the warp stalls on their operand registers at the top of its next iteration.)
+    // Padding query rows of the last pair (>= N) carry exact zeros (P = 0 there), so adding them into the next
+    // image's rows is harmless; rows past the end of the tensor are clipped by the tensor map.
+    auto drain_dq = [&](int Df, const Item& im, int pair) {
       const int pb = Df & 1;
       mbar_wait(&sm.dq_done[pb], (Df >> 1) & 1, 8);
       tc_fence_after();
@@ -285,13 +286,17 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.dq_free[pb]);
-      const int qrow = pair * BT + krow;
-      if (qrow < N && !(kn.dbg & 32)) {
-        float* dst = dq_acc + (static_cast<size_t>(im.b * N + qrow) * heads + im.h) * DH + cg * 16;
+      const uint32_t row_addr = smem_u32(sm.dq_stage[g]) + krow * 128;
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          red_add_v4(dst + 4 * c, __uint_as_float(r[4 * c]) * scale, __uint_as_float(r[4 * c + 1]) * scale,
-                     __uint_as_float(r[4 * c + 2]) * scale, __uint_as_float(r[4 * c + 3]) * scale);
+      for (int c = 0; c < 4; ++c)
+        sts_u4(row_addr + (((4 * cg + c) ^ (krow & 7)) << 4), __float_as_uint(__uint_as_float(r[4 * c]) * scale),
+               __float_as_uint(__uint_as_float(r[4 * c + 1]) * scale), __float_as_uint(__uint_as_float(r[4 * c + 2]) * scale),
+               __float_as_uint(__uint_as_float(r[4 * c + 3]) * scale));
+      fence_proxy_async_smem();
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
+      if ((warp & 7) == 0 && lane == 0 && !(kn.dbg & 32)) {
+        tma_reduce_add_2d(&tm_dq, sm.dq_stage[g], im.h * DH, im.b * N + pair * BT);
+        bulk_commit_group();
       }
     };
     auto drain_dkv = [&](int it, const Item& im) {  // group 0 stores dV_j, group 1 stores dK_j
@@ -406,7 +411,10 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         if (!(kn.dbg & 1024)) fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_a(b_pds_u);  // one arrival per warp (256 same-address arrivals serialise)
+        if (lane == 0) {
+          if ((warp & 7) == 0) bulk_wait_group_read0();  // the group's dQ staging tile has been read by its last reduce:
+          mbar_arrive_a(b_pds_u);                        // ordered before the next drain's writes through this arrival
+        }
 
         // ---- deferred drains (their MMAs were issued one pair / one item ago) ----
         if (Pf > 0 && ((Pf - 1) & 1) == static_cast<uint32_t>(g)) {
@@ -421,6 +429,7 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       if (((Ptot - 1) & 1) == g) drain_dq(Ptot - 1, prev, npairs - 1);
       drain_dkv(my_items - 1, prev);
     }
+    if ((warp & 7) == 0 && lane == 0) bulk_wait_group0();
   }
 
   tc_fence_before();
@@ -500,12 +509,13 @@ extern "C" int destr_enc_attn_bwd(const void* q, const void* k, const void* v, i
   const uint64_t rows = static_cast<uint64_t>(B) * N;
   const int cols = heads * DH;
   const int Np = ceil_div(N, BT) * BT;
-  CUtensorMap tq, tk, tv, tdo;
+  CUtensorMap tq, tk, tv, tdo, tdq;
   int rc;
   if ((rc = make_tmap_bf16_2d(&tq, q, rows, cols, ld_q, BQ, DH, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   if ((rc = make_tmap_bf16_2d(&tk, k, rows, cols, ld_k, BT, DH, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   if ((rc = make_tmap_bf16_2d(&tv, v, rows, cols, ld_v, BT, DH, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   if ((rc = make_tmap_bf16_2d(&tdo, dout, rows, cols, cols, BQ, DH, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  if ((rc = make_tmap_f32_2d(&tdq, dq_acc, rows, cols, cols, BT, DH, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   const size_t smem = sizeof(Smem) + 1024;
   using KernelT = decltype(&enc_attn_bwd_kernel<0, false>);
   static const KernelT kernels[8] = {enc_attn_bwd_kernel<0, false>, enc_attn_bwd_kernel<1, false>,
@@ -525,7 +535,7 @@ extern "C" int destr_enc_attn_bwd(const void* q, const void* k, const void* v, i
   int grid = n_items < 148 ? n_items : 148;  // persistent: one CTA per SM
   if (g_knobs[13] > 0 && g_knobs[13] < grid) grid = g_knobs[13];
   kernels[(g_knobs[10] & 3) + (drop_thr16 ? 4 : 0)]<<<grid, NTHREADS, smem, st>>>(
-      tq, tk, tv, tdo, mask_bits, words_per_row, stats, dq_acc, static_cast<__nv_bfloat16*>(dk),
+      tq, tk, tv, tdo, tdq, mask_bits, words_per_row, stats, static_cast<__nv_bfloat16*>(dk),
       static_cast<__nv_bfloat16*>(dv), ld_dk, ld_dv, N, heads, n_items, scale, scale * 1.4426950408889634f, kn,
       DropBits{drop_colbits, drop_thr16, drop_words});
   DESTR_LAUNCH_CHECK();
