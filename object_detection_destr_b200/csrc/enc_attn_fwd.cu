@@ -229,28 +229,30 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         }
         mbar_wait(&sm.s_full[f & 1], (f >> 1) & 1, 7);
         tc_fence_after();
-        uint32_t sr[HN];
-        {
-          uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sr[0]);
-          uint32_t(&hi)[16] = *reinterpret_cast<uint32_t(*)[16]>(&sr[32]);
-          tmem_ld_x32(s_addr, lo);
-          tmem_ld_x16(s_addr + 32, hi);
-        }
-        tc_wait_ld();
         // hf 0: keys [0,48) = word0 | low half of word1;  hf 1: keys [48,96) = high half of word1 | word2
         const uint64_t mb = hf == 0 ? (static_cast<uint64_t>(c0) | (static_cast<uint64_t>(c1 & 0xffffu) << 32))
                                     : (static_cast<uint64_t>(c0 >> 16) | (static_cast<uint64_t>(c1) << 16));
-        if (mb != 0ull) {
-#pragma unroll
-          for (int i = 0; i < HN; ++i)
-            if ((mb >> i) & 1ull) sr[i] = 0xff800000u;  // -inf
-        }
+        // Two passes over the half's 48 scores, 16 at a time (TMEM reads are cheap -- ~450 B/clk/SM measured -- and
+        // holding all 48 plus the packed P made the dropout variant spill around its prefetched mask words):
+        // pass 1 only takes the row maximum, pass 2 re-reads each chunk for the exponentials.
         float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four independent FMNMX3 chains
 #pragma unroll
-        for (int i = 0; i < HN; i += 8)
+        for (int ch = 0; ch < HN / 16; ++ch) {
+          uint32_t sr[16];
+          tmem_ld_x16(s_addr + ch * 16, sr);
+          tc_wait_ld();
+          if (mb != 0ull) {
+            const uint32_t m16 = static_cast<uint32_t>(mb >> (16 * ch)) & 0xffffu;
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-            mx4[u] = max3(mx4[u], __uint_as_float(sr[i + 2 * u]), __uint_as_float(sr[i + 2 * u + 1]));
+            for (int i = 0; i < 16; ++i)
+              if ((m16 >> i) & 1u) sr[i] = 0xff800000u;  // -inf
+          }
+#pragma unroll
+          for (int i = 0; i < 16; i += 8)
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              mx4[u] = max3(mx4[u], __uint_as_float(sr[i + 2 * u]), __uint_as_float(sr[i + 2 * u + 1]));
+        }
         const float m_new = fmaxf(m_ref, fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * scale_log2);
         // lazy rescale: O and l stay relative to m_ref unless the max grew by more than 2^tau
         const bool grow = m_new > m_ref + lazy_tau;  // also true for the first finite tile (m_ref = -inf)
@@ -271,33 +273,40 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
         const uint64_t nm2 = pack_f32x2(-m_use, -m_use);
         uint64_t rs2[2] = {0ull, 0ull};
-        uint32_t pk[HN / 2];
         const uint64_t db = hf == 0 ? (static_cast<uint64_t>(e0) | (static_cast<uint64_t>(e1 & 0xffffu) << 32))
                                     : (static_cast<uint64_t>(e0 >> 16) | (static_cast<uint64_t>(e1) << 16));
 #pragma unroll
-        for (int i = 0; i < HN / 2; ++i) {  // P column i holds keys 2i, 2i+1 of the half
-          const uint64_t x2 =
-              fma_f32x2(pack_f32x2(__uint_as_float(sr[2 * i]), __uint_as_float(sr[2 * i + 1])), sc2, nm2);
-          float x0, x1, p0, p1;
-          unpack_f32x2(x2, x0, x1);
-          if ((i & 3) < POLYQ) {
-            ex2_poly_f32x2(x0, x1, p0, p1);
-          } else {
-            p0 = ex2_approx(x0);
-            p1 = ex2_approx(x1);
+        for (int ch = 0; ch < HN / 16; ++ch) {
+          uint32_t sr[16], pk[8];
+          tmem_ld_x16(s_addr + ch * 16, sr);
+          tc_wait_ld();
+          if (mb != 0ull) {
+            const uint32_t m16 = static_cast<uint32_t>(mb >> (16 * ch)) & 0xffffu;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if ((m16 >> i) & 1u) sr[i] = 0xff800000u;
           }
-          rs2[i & 1] = add_f32x2(rs2[i & 1], pack_f32x2(p0, p1));  // the softmax denominator is NOT dropped
-          if (DROP) {  // attention-probability dropout (nn.MultiheadAttention(dropout=p)): zero P, rescale O at the end
-            if ((db >> (2 * i)) & 1ull) p0 = 0.f;
-            if ((db >> (2 * i + 1)) & 1ull) p1 = 0.f;
+          const uint32_t d16 = DROP ? static_cast<uint32_t>(db >> (16 * ch)) & 0xffffu : 0u;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {  // P column 8 ch + i holds keys 16 ch + 2i, 2i + 1 of the half
+            const uint64_t x2 =
+                fma_f32x2(pack_f32x2(__uint_as_float(sr[2 * i]), __uint_as_float(sr[2 * i + 1])), sc2, nm2);
+            float x0, x1, p0, p1;
+            unpack_f32x2(x2, x0, x1);
+            if ((i & 3) < POLYQ) {
+              ex2_poly_f32x2(x0, x1, p0, p1);
+            } else {
+              p0 = ex2_approx(x0);
+              p1 = ex2_approx(x1);
+            }
+            rs2[i & 1] = add_f32x2(rs2[i & 1], pack_f32x2(p0, p1));  // the softmax denominator is NOT dropped
+            if (DROP) {  // attention-probability dropout (nn.MultiheadAttention(dropout=p)): zero P, rescale O at the end
+              if ((d16 >> (2 * i)) & 1u) p0 = 0.f;
+              if ((d16 >> (2 * i + 1)) & 1u) p1 = 0.f;
+            }
+            pk[i] = pack_bf16x2(p0, p1);
           }
-          pk[i] = pack_bf16x2(p0, p1);
-        }
-        {
-          uint32_t(&lo)[16] = *reinterpret_cast<uint32_t(*)[16]>(&pk[0]);
-          uint32_t(&hi)[8] = *reinterpret_cast<uint32_t(*)[8]>(&pk[16]);
-          tmem_st_x16(s_addr, lo);
-          tmem_st_x8(s_addr + 16, hi);
+          tmem_st_x8(s_addr + ch * 8, pk);  // P over S columns this thread has already consumed
         }
         float r0, r1, r2, r3;
         unpack_f32x2(rs2[0], r0, r1);
