@@ -53,7 +53,7 @@ struct __align__(1024) Smem {
   uint8_t q[QSTAGES][Q_BYTES];
   uint8_t d_o[QSTAGES][Q_BYTES];
   uint8_t ds[2][2][DS_BLOCK_BYTES];  // [pair parity][sub-tile within the pair]
-  float dq_stage[2][BT * DH];        // [group]: dQ pair tile (128 queries x 32, SW128) on its way to the TMA reduce-add
+  float dq_stage[2][BT * DH];        // [group][warp]: 32 queries x 16 floats (SW64) on their way to the TMA reduce-add
   float stat[QSTAGES][2 * BQ];
   uint64_t kv_full[2], kv_free[2];
   uint64_t q_full[QSTAGES], q_empty[QSTAGES];
@@ -271,11 +271,13 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const uint32_t lane_addr = static_cast<uint32_t>(wq * 32) << 16;
     const uint64_t sc2 = pack_f32x2(scale_log2, scale_log2);
 
-    // dQ of flat pair Df (= pair `pair` of item im; parity == g): TMEM -> registers -> this group's smem tile -> ONE TMA
-    // reduce-add (fp32) into dq_acc.  (Per-thread red.global.add: every lane hits a different 128-byte line, 4.8 M
-    // 16-byte atomics per launch, and the warp stalls on their operand registers at the top of its next iteration.)
+    // dQ of flat pair Df (= pair `pair` of item im; parity == g): TMEM -> registers -> the warp's own smem tile (32
+    // queries x 16 floats, SW64) -> one TMA reduce-add (fp32) per warp into dq_acc; nothing but the warp itself is
+    // involved, so no block-level barrier.  (Per-thread red.global.add: every lane hits a different 128-byte line,
+    // 4.8 M 16-byte atomics per launch, and the warp stalls on their operand registers at its next iteration.)
     // Padding query rows of the last pair (>= N) carry exact zeros (P = 0 there), so adding them into the next
     // image's rows is harmless; rows past the end of the tensor are clipped by the tensor map.
+    const uint32_t stage_addr = smem_u32(sm.dq_stage[g]) + (wq * 2 + cg) * 2048;
     auto drain_dq = [&](int Df, const Item& im, int pair) {
       const int pb = Df & 1;
       mbar_wait(&sm.dq_done[pb], (Df >> 1) & 1, 8);
@@ -284,18 +286,19 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       tmem_ld_x16(tmem + lane_addr + C_DQ + pb * 32 + cg * 16, r);
       tc_wait_ld();
       tc_fence_before();
+      if (lane == 0) bulk_wait_group_read0();  // the warp's previous reduce has read the tile
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.dq_free[pb]);
-      const uint32_t row_addr = smem_u32(sm.dq_stage[g]) + krow * 128;
+      const uint32_t row_addr = stage_addr + lane * 64;
 #pragma unroll
       for (int c = 0; c < 4; ++c)
-        sts_u4(row_addr + (((4 * cg + c) ^ (krow & 7)) << 4), __float_as_uint(__uint_as_float(r[4 * c]) * scale),
+        sts_u4(row_addr + ((c ^ ((lane >> 1) & 3)) << 4), __float_as_uint(__uint_as_float(r[4 * c]) * scale),
                __float_as_uint(__uint_as_float(r[4 * c + 1]) * scale), __float_as_uint(__uint_as_float(r[4 * c + 2]) * scale),
                __float_as_uint(__uint_as_float(r[4 * c + 3]) * scale));
       fence_proxy_async_smem();
-      asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
-      if ((warp & 7) == 0 && lane == 0 && !(kn.dbg & 32)) {
-        tma_reduce_add_2d(&tm_dq, sm.dq_stage[g], im.h * DH, im.b * N + pair * BT);
+      __syncwarp();
+      if (lane == 0 && !(kn.dbg & 32)) {
+        tma_reduce_add_2d(&tm_dq, stage_addr, im.h * DH + cg * 16, im.b * N + pair * BT + wq * 32);
         bulk_commit_group();
       }
     };
@@ -411,10 +414,7 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         if (!(kn.dbg & 1024)) fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) {
-          if ((warp & 7) == 0) bulk_wait_group_read0();  // the group's dQ staging tile has been read by its last reduce:
-          mbar_arrive_a(b_pds_u);                        // ordered before the next drain's writes through this arrival
-        }
+        if (lane == 0) mbar_arrive_a(b_pds_u);  // one arrival per warp
 
         // ---- deferred drains (their MMAs were issued one pair / one item ago) ----
         if (Pf > 0 && ((Pf - 1) & 1) == static_cast<uint32_t>(g)) {
@@ -429,7 +429,7 @@ enc_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       if (((Ptot - 1) & 1) == g) drain_dq(Ptot - 1, prev, npairs - 1);
       drain_dkv(my_items - 1, prev);
     }
-    if ((warp & 7) == 0 && lane == 0) bulk_wait_group0();
+    if (lane == 0) bulk_wait_group0();
   }
 
   tc_fence_before();
@@ -515,7 +515,7 @@ extern "C" int destr_enc_attn_bwd(const void* q, const void* k, const void* v, i
   if ((rc = make_tmap_bf16_2d(&tk, k, rows, cols, ld_k, BT, DH, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   if ((rc = make_tmap_bf16_2d(&tv, v, rows, cols, ld_v, BT, DH, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   if ((rc = make_tmap_bf16_2d(&tdo, dout, rows, cols, cols, BQ, DH, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
-  if ((rc = make_tmap_f32_2d(&tdq, dq_acc, rows, cols, cols, BT, DH, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_tmap_f32_2d(&tdq, dq_acc, rows, cols, cols, 32, 16, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   const size_t smem = sizeof(Smem) + 1024;
   using KernelT = decltype(&enc_attn_bwd_kernel<0, false>);
   static const KernelT kernels[8] = {enc_attn_bwd_kernel<0, false>, enc_attn_bwd_kernel<1, false>,
