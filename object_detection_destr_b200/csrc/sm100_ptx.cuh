@@ -127,11 +127,16 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+#ifdef DESTR_MBAR_TEST_WAIT
+#define DESTR_MBAR_WAIT_OP "mbarrier.test_wait.parity.shared::cta.b64"
+#else
+#define DESTR_MBAR_WAIT_OP "mbarrier.try_wait.parity.shared::cta.b64"
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      DESTR_MBAR_WAIT_OP " P, [%1], %2;\n\t"
       "selp.b32 %0, 1, 0, P;\n\t}\n"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
@@ -155,7 +160,7 @@ __device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      DESTR_MBAR_WAIT_OP " P, [%1], %2;\n\t"
       "selp.b32 %0, 1, 0, P;\n\t}\n"
       : "=r"(ok)
       : "r"(bar), "r"(parity)

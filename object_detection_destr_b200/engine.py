@@ -297,18 +297,23 @@ class GraphedTrainStep:
         from . import _lib
         n0 = _lib.launch_count
         self.gA = torch.cuda.CUDAGraph(keep_graph=True)
+        # The step's critical chain is captured on a HIGH-priority stream; the side branches (weight-gradient GEMMs,
+        # dropout bit matrices, optimizer share) keep the default priority, so where both have CTAs to place the
+        # block scheduler serves the chain first.  (Stream priorities become kernel-node priorities in the graph.)
+        import os
+        cap = torch.cuda.Stream(priority=-1) if os.environ.get("DESTR_PRIO", "1") != "0" else None
         if self.gpu_lsa:  # one graph: forward, cost, assignment, loss, backward, optimizer
-            with torch.cuda.graph(self.gA):
+            with torch.cuda.graph(self.gA, stream=cap):
                 self.out = self._forward()
                 self.loss = self._backward(self.out)
             self.gB = None
         else:
-            with torch.cuda.graph(self.gA):
+            with torch.cuda.graph(self.gA, stream=cap):
                 self.out = self._forward()
             torch.cuda.synchronize()
             self._assign()
             self.gB = torch.cuda.CUDAGraph(keep_graph=True)
-            with torch.cuda.graph(self.gB, pool=self.gA.pool()):
+            with torch.cuda.graph(self.gB, pool=self.gA.pool(), stream=cap):
                 self.loss = self._backward(self.out)
         torch.cuda.synchronize()
         self.launches_per_step = _lib.launch_count - n0  # kernels launched by our C-ABI calls during the capture

@@ -154,7 +154,11 @@ class FlatParams:
         # optimizer): they go to a side stream and overlap the dX chain; inside a CUDA-graph capture this becomes a
         # parallel branch of the graph.  Their operands are kept alive until the streams join (end_backward).
         self.side = torch.cuda.Stream(device=device) if torch.device(device).type == "cuda" else None
-        self.forks = [torch.cuda.Stream(device=device) for _ in range(2)] if self.side is not None else []  # parallel chains
+        # forks[0]: short parallel chains the main chain joins right away (high priority, like the capture stream of
+        # engine.capture); forks[1]: background work (dropout bit matrices) at the default priority
+        hi = -1 if _os.environ.get("DESTR_PRIO", "1") != "0" else 0
+        self.forks = [torch.cuda.Stream(device=device, priority=hi), torch.cuda.Stream(device=device)] \
+            if self.side is not None else []
         self._keep: List[Tensor] = []
         self._forked = set()
         self.defer_grad_cast = False  # set by FlatAdamW: its kernel reads the bf16 weight gradients itself

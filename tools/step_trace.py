@@ -49,19 +49,41 @@ for t, d in events:
     last = t
 print(f"busy (>=1 kernel) {busy:.1f} us, idle {(t1 - t0) - busy:.1f} us; time at concurrency: " +
       ", ".join(f"{k}:{v:.0f}" for k, v in sorted(conc.items())))
-# per-name totals of time when the kernel was the ONLY one running (critical-path proxy)
+# per-name totals of the time during which the kernel was the ONLY one running (critical-path proxy; partial overlaps
+# count for their exclusive part)
 import collections
 solo = collections.defaultdict(float)
 cnt = collections.defaultdict(int)
-for i, k in enumerate(ks):
-    others = [o for o in ks if o is not k and o[0] < k[1] and o[1] > k[0]]
-    if not others:
-        n = k[2][:60]
-        solo[n] += k[1] - k[0]
-        cnt[n] += 1
-print("time running alone, by kernel:")
-for n, v in sorted(solo.items(), key=lambda kv: -kv[1])[:40]:
-    print(f"  {v:8.1f} us x{cnt[n]:3d}  {n}")
+tot = collections.defaultdict(float)
+bounds = sorted(set([k[0] for k in ks] + [k[1] for k in ks]))
+import bisect
+active = collections.defaultdict(list)
+for idx, k in enumerate(ks):
+    i0, i1 = bisect.bisect_left(bounds, k[0]), bisect.bisect_left(bounds, k[1])
+    for j in range(i0, i1):
+        active[j].append(idx)
+    cnt[k[2][:60]] += 1
+    tot[k[2][:60]] += k[1] - k[0]
+for j, lst in active.items():
+    if len(lst) == 1:
+        solo[ks[lst[0]][2][:60]] += bounds[j + 1] - bounds[j]
+print("exclusive time (only kernel running) / total time, by kernel:")
+for n, v in sorted(solo.items(), key=lambda kv: -kv[1])[:60]:
+    print(f"  {v:8.1f} / {tot[n]:8.1f} us x{cnt[n]:3d}  {n}")
+# phases of the step, by landmark kernels
+def first(sub):
+    return next((k[0] for k in ks if sub in k[2]), None)
+def last(sub):
+    return max((k[1] for k in ks if sub in k[2]), default=None)
+marks = [("start", t0), ("first enc_attn_fwd", first("enc_attn_fwd")), ("last enc_attn_fwd", last("enc_attn_fwd")),
+         ("match cost", first("match_cost")), ("lsap end", last("lsap")), ("set loss end", last("set_loss")),
+         ("first enc_attn_bwd", first("enc_attn_bwd")), ("last enc_attn_bwd", last("enc_attn_bwd")), ("end", t1)]
+prev = t0
+for n, t in marks:
+    if t is None:
+        continue
+    print(f"  {n:22s} at {t - t0:8.1f} us  (+{t - prev:7.1f})")
+    prev = t
 
 if world > 1:
     if rank == 0:
