@@ -16,6 +16,7 @@ read the true counts from device tensors), so one capture serves every batch.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -54,6 +55,21 @@ def set_loss_static(logits, boxes, tl, tb, pi, ti, valid, num_classes: int):
     ciou = (ci * (vf[:, :, None] * vf[:, None, :])).sum((1, 2)) / (cnt * cnt)
     denom = has.sum().clamp(min=1)
     return {"class": loss_cls, "bbox": (l1 * has).sum() / denom, "ciou": (ciou * has).sum() / denom}
+
+
+_CAPTURE_STREAMS = {}
+
+
+def _capture_stream(device):
+    """ONE high-priority capture stream per device, shared by every capture of the process (as torch.cuda.graph shares
+    its default capture stream): autograd's gradient accumulators stay bound to the stream they were first used on, and
+    a second engine capturing on a fresh stream would make the capture depend on that stream's uncaptured work."""
+    if os.environ.get("DESTR_PRIO", "1") == "0":
+        return None
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _CAPTURE_STREAMS:
+        _CAPTURE_STREAMS[key] = torch.cuda.Stream(device=key, priority=-1)
+    return _CAPTURE_STREAMS[key]
 
 
 def _count_kernel_nodes(graphs) -> Optional[int]:
@@ -300,8 +316,7 @@ class GraphedTrainStep:
         # The step's critical chain is captured on a HIGH-priority stream; the side branches (weight-gradient GEMMs,
         # dropout bit matrices, optimizer share) keep the default priority, so where both have CTAs to place the
         # block scheduler serves the chain first.  (Stream priorities become kernel-node priorities in the graph.)
-        import os
-        cap = torch.cuda.Stream(priority=-1) if os.environ.get("DESTR_PRIO", "1") != "0" else None
+        cap = _capture_stream(self.dev)
         if self.gpu_lsa:  # one graph: forward, cost, assignment, loss, backward, optimizer
             with torch.cuda.graph(self.gA, stream=cap):
                 self.out = self._forward()
