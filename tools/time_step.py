@@ -11,6 +11,9 @@ from object_detection_destr_b200.engine import GraphedTrainStep
 from object_detection_destr_b200.hotpath import TransformerHalf
 
 cfg, B = bench.CFG, bench.CFG["B"]
+from object_detection_destr_b200 import _lib
+for kv in filter(None, os.environ.get("KNOBS", "").split(",")):  # e.g. KNOBS=17=2 (debug knobs)
+    _lib.lib.destr_debug_knob(int(kv.split("=")[0]), int(kv.split("=")[1]))
 torch.manual_seed(0)
 model = TransformerHalf(Namespace(hidden_dim=256, num_encoder_blocks=cfg["L"], num_decoder_blocks=cfg["L"], num_cls=cfg["C"]))
 (disable_dropout(model) if "--no-dropout" in sys.argv else model).cuda().train()
