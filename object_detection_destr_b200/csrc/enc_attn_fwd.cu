@@ -327,17 +327,16 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       tc_wait_ld();
       tc_fence_before();
       mbar_arrive(&sm.o_free[hf]);
-      float* xw = sm.xch[hf][row];
-      xw[0] = m_ref;
-      xw[1] = l;
+      // (32-bit shared addresses: a generic pointer into dynamic smem makes these generic LD/ST on the long path)
+      const uint32_t xw = smem_u32(&sm.xch[hf][row][0]), xr = smem_u32(&sm.xch[1 - hf][row][0]);
+      sts_u4(xw, __float_as_uint(m_ref), __float_as_uint(l), 0u, 0u);
 #pragma unroll
       for (int i = 0; i < 16; i += 4)  // the 16 dims the other half finalises
-        *reinterpret_cast<float4*>(xw + 4 + i) =
-            make_float4(__uint_as_float(orr[(1 - hf) * 16 + i]), __uint_as_float(orr[(1 - hf) * 16 + i + 1]),
-                        __uint_as_float(orr[(1 - hf) * 16 + i + 2]), __uint_as_float(orr[(1 - hf) * 16 + i + 3]));
+        sts_u4(xw + 16 + i * 4, orr[(1 - hf) * 16 + i], orr[(1 - hf) * 16 + i + 1], orr[(1 - hf) * 16 + i + 2],
+               orr[(1 - hf) * 16 + i + 3]);
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float* xr = sm.xch[1 - hf][row];
-      const float m_o = xr[0], l_o = xr[1];
+      const float4 ml = lds_f4(xr);
+      const float m_o = ml.x, l_o = ml.y;
       const float m_all = fmaxf(m_ref, m_o);
       const float m_fin = (m_all == -INFINITY) ? 0.f : m_all;
       const float a_s = ex2_approx(m_ref - m_fin), a_o = ex2_approx(m_o - m_fin);
@@ -348,7 +347,7 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       uint32_t ob[8];
 #pragma unroll
       for (int i = 0; i < 16; i += 4) {
-        const float4 t = *reinterpret_cast<const float4*>(xr + 4 + i);
+        const float4 t = lds_f4(xr + 16 + i * 4);
         ob[i / 2] = pack_bf16x2(__uint_as_float(orr[hf * 16 + i]) * cs + t.x * co,
                                 __uint_as_float(orr[hf * 16 + i + 1]) * cs + t.y * co);
         ob[i / 2 + 1] = pack_bf16x2(__uint_as_float(orr[hf * 16 + i + 2]) * cs + t.z * co,
