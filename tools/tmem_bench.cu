@@ -1,9 +1,7 @@
 // Microbenchmark of TMEM read throughput / latency (tcgen05.ld 32x32b) as seen by the attention kernels:
-// W warps of ONE CTA per SM each loop over tcgen05.ld.x16 / .x32 (+ wait::ld) of their own 32-lane quarter.
+// W warps of ONE CTA per SM each loop over tcgen05.ld.x16 (+ wait::ld) of their own 32-lane quarter.
 //   MODE 0: one x16 load + wait per iteration (latency-exposed, what one compute warp sees)
 //   MODE 1: two x16 loads + one wait (the backward's S^T / dP^T pair)
-//   MODE 2: one x32 load + wait
-//   MODE 3: two x32 loads + one wait
 // Reports bytes per clock per SM and clocks per iteration per warp.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tmem_bench tools/tmem_bench.cu && ./tmem_bench
 #include <cstdio>
@@ -40,19 +38,6 @@ __global__ void __launch_bounds__(1024, 1) bench(uint32_t* out, long long* cycle
       tc_wait_ld();
 #pragma unroll
       for (int i = 0; i < 16; ++i) acc ^= r[i] + s[i];
-    } else if (MODE == 2) {
-      uint32_t r[32];
-      tmem_ld_x32(addr, r);
-      tc_wait_ld();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) acc ^= r[i];
-    } else {
-      uint32_t r[32], s[32];
-      tmem_ld_x32(addr, r);
-      tmem_ld_x32(addr + 32, s);
-      tc_wait_ld();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) acc ^= r[i] + s[i];
     }
   }
   const long long t1 = clock64();
@@ -73,7 +58,7 @@ void run(int warps, uint32_t* out, long long* cyc) {
   cudaError_t e = cudaDeviceSynchronize();
   long long c;
   cudaMemcpy(&c, cyc, sizeof(c), cudaMemcpyDeviceToHost);
-  const double words = (MODE == 0 ? 16 : MODE == 1 ? 32 : MODE == 2 ? 32 : 64);
+  const double words = (MODE == 0 ? 16 : 32);
   const double bytes = words * 4 * 32 * warps * iters;
   printf("mode %d  warps %2d: %8.1f clk/iter/warp   %7.1f B/clk/SM   (%s)\n", MODE, warps, double(c) / iters, bytes / c,
          cudaGetErrorString(e));
@@ -87,8 +72,6 @@ int main() {
   for (int w : {1, 4, 8, 16, 32}) {
     run<0>(w, out, cyc);
     run<1>(w, out, cyc);
-    run<2>(w, out, cyc);
-    run<3>(w, out, cyc);
   }
   return 0;
 }
