@@ -69,6 +69,7 @@ struct __align__(1024) Smem {
 
 struct Knobs {
   uint32_t v_lbo, v_sbo, qk_lbo, qk_sbo, p_kstep_cols, v_kstep_bytes;
+  uint32_t dbg;  // timing experiments only (knob 19): 1 no Q.K^T MMAs, 2 no P.V MMAs, 4 no softmax math
 };
 
 // POLYQ of every 4 key pairs take the FMA-pipe polynomial exp instead of MUFU.EX2
@@ -157,8 +158,10 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         mbar_wait_backoff(&sm.kv_full[stage], (fq / KSTAGES) & 1, 4);
         tc_fence_after();
         const uint64_t a = D_KMAJ + (a_q + qb * (Q_BYTES >> 4)), bd = D_KMAJ + (a_k + stage * (KV_BYTES >> 4));
-        umma_ss(tmem + C_S + (fq & 1) * BN, a, bd, idesc_qk, 0u);
-        umma_ss(tmem + C_S + (fq & 1) * BN, a + 2, bd + 2, idesc_qk, 1u);
+        if (!(kn.dbg & 1)) {
+          umma_ss(tmem + C_S + (fq & 1) * BN, a, bd, idesc_qk, 0u);
+          umma_ss(tmem + C_S + (fq & 1) * BN, a + 2, bd + 2, idesc_qk, 1u);
+        }
         tc_commit(&sm.s_full[fq & 1]);
         if (jq == nkv - 1) tc_commit(&sm.q_empty[qb]);  // every Q.K^T of the item has been issued
         ++fq;
@@ -176,6 +179,7 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           mbar_wait(&sm.p_full[hf][f & 1], (f >> 1) & 1, 5);
           if (j == 0 && it > 0) mbar_wait_backoff(&sm.o_free[hf], (it - 1) & 1, 6);  // epilogue has read O
           tc_fence_after();
+          if (!(kn.dbg & 2))
 #pragma unroll
           for (int ks = 0; ks < HN / 16; ++ks)
             umma_ts(tmem + C_O + hf * DH, t_p + hf * HN + ks * 8, dv + (hf * (HN / 16) + ks) * 64, idesc_pv,
@@ -229,6 +233,8 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         }
         mbar_wait(&sm.s_full[f & 1], (f >> 1) & 1, 7);
         tc_fence_after();
+        uint64_t rs2[2] = {0ull, 0ull};
+        if (!(kn.dbg & 4)) {
         // hf 0: keys [0,48) = word0 | low half of word1;  hf 1: keys [48,96) = high half of word1 | word2
         const uint64_t mb = hf == 0 ? (static_cast<uint64_t>(c0) | (static_cast<uint64_t>(c1 & 0xffffu) << 32))
                                     : (static_cast<uint64_t>(c0 >> 16) | (static_cast<uint64_t>(c1) << 16));
@@ -272,7 +278,6 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         if (grow) m_ref = m_new;
         const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
         const uint64_t nm2 = pack_f32x2(-m_use, -m_use);
-        uint64_t rs2[2] = {0ull, 0ull};
         const uint64_t db = hf == 0 ? (static_cast<uint64_t>(e0) | (static_cast<uint64_t>(e1 & 0xffffu) << 32))
                                     : (static_cast<uint64_t>(e0 >> 16) | (static_cast<uint64_t>(e1) << 16));
 #pragma unroll
@@ -307,6 +312,7 @@ enc_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             pk[i] = pack_bf16x2(p0, p1);
           }
           tmem_st_x8(s_addr + ch * 8, pk);  // P over S columns this thread has already consumed
+        }
         }
         float r0, r1, r2, r3;
         unpack_f32x2(rs2[0], r0, r1);
@@ -405,7 +411,7 @@ extern "C" int destr_enc_attn_fwd(const void* q, const void* k, const void* v, i
   int grid = n_items < 2 * 148 ? n_items : 2 * 148;  // persistent: 2 CTAs per SM
   if (g_knobs[12] > 0 && g_knobs[12] < grid) grid = g_knobs[12];
   Knobs kn{(uint32_t)g_knobs[0], (uint32_t)g_knobs[1], (uint32_t)g_knobs[2],
-           (uint32_t)g_knobs[3], (uint32_t)g_knobs[4], (uint32_t)g_knobs[5]};
+           (uint32_t)g_knobs[3], (uint32_t)g_knobs[4], (uint32_t)g_knobs[5], (uint32_t)g_knobs[19]};
   kernel<<<grid, NTHREADS, smem, static_cast<cudaStream_t>(stream)>>>(
       tq, tk, tv, mask_bits, words_per_row, static_cast<__nv_bfloat16*>(out), lse, N, heads, n_items,
       scale * 1.4426950408889634f, g_knobs[11] ? (float)(g_knobs[11] - 1) : kLazyTau, kn,
