@@ -355,15 +355,27 @@ def run_ours(args):
     # Every step's inputs come from pinned host memory (H2D inside the timed region) and its loss + assignment status
     # are read back.  The feed is pipelined like a data loader with prefetch: batch s+1 is packed and its H2D copies are
     # enqueued on a copy stream while step s runs on the GPU.
+    # Both feeds are pipelined by one step, like a training loop with a prefetching loader and asynchronous logging:
+    # batch s+1 is packed and copied H2D while step s runs, and the loss + assignment status of step s are read back
+    # (pinned, non-blocking D2H enqueued right behind the step) while step s+1 already runs.  EVERY step's inputs cross
+    # the bus and EVERY step's result is read inside the timed region; timed() waits for the last read.
+    rb_pending = []
+
+    def e2e_drain(keep=0):
+        loss = None
+        while len(rb_pending) > keep:
+            loss = eng.finish_readback(rb_pending.pop(0))      # loss (D2H) + status check (scipy would raise on NaN costs)
+        return loss
+
     def e2e_step(s):
         if args.eager:
             loss = train_step(host_pinned[s % n_batches]).item()
-        else:
-            loss_t = eng.step_prefetched()
-            eng.prefetch(*host_pinned[(s + 1) % n_batches])
-            loss = loss_t.item()                               # D2H read of the step's result
-        eng.raise_if_invalid()                                 # + the assignment status (scipy would raise on NaN costs)
-        return loss
+            eng.raise_if_invalid()
+            return loss
+        eng.step_prefetched()
+        rb_pending.append(eng.enqueue_readback())              # D2H read of THIS step's result, finished one step later
+        eng.prefetch(*host_pinned[(s + 1) % n_batches])
+        return e2e_drain(keep=1)
     if args.no_e2e:
         ms_e2e = float("nan")
     else:
@@ -371,7 +383,13 @@ def run_ours(args):
             eng.prefetch(*host_pinned[0])
         for s in range(2):
             e2e_step(s)
-        ms_e2e = timed(e2e_step, args.steps)
+        e2e_drain()
+
+        def e2e_run(s):
+            e2e_step(s)
+            if s == args.steps - 1:
+                e2e_drain()                                    # the last step's read belongs to the timed region
+        ms_e2e = timed(e2e_run, args.steps)
     clocks = sampler.stop() if sampler else None
     # ---- fwd + bwd without the optimizer step (SURVEY 8d reports both): a second graph over the same model ----
     ms_nopt = None
@@ -440,7 +458,8 @@ def run_ours(args):
                            "step": "fwd + matcher (cost kernel + device LSAP, bit-identical to scipy) + fused set loss + bwd + grad all-reduce + flat AdamW, one CUDA graph",
                            "dropout": 0.3 if args.dropout else 0.0, "cuda_graphs": not args.eager, "l2": "4 rotating input batches; activations (~0.6 GB/step) exceed the 126 MB L2"},
                 "e2e": {"value": imgs / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": int(h2d_bytes),
-                        "d2h_bytes_per_step": 4 + 4 * B, "ms_per_step": ms_e2e / args.steps},
+                        "d2h_bytes_per_step": 4 + 4 * B, "ms_per_step": ms_e2e / args.steps,
+                        "feed": "pinned host batch s+1 packed + copied H2D on a copy stream while step s runs; loss + assignment status of step s read back (pinned, non-blocking) while step s+1 runs; every step's copies and reads are inside the timed region"},
                 "gpu_launches": int(nodes if nodes else launches) * args.steps,
                 "gpu_launches_per_step": int(nodes if nodes else launches),
                 "gpu_launches_detail": {"graph_kernel_nodes_per_step": nodes, "own_kernels_per_step": int(launches),

@@ -426,6 +426,12 @@ int destr_flat_adamw(float* master, float* grad, float* exp_avg, float* exp_avg_
                      float lr, float beta1, float beta2, float eps, float weight_decay, const float* step,
                      const void* grad_bf16, int64_t bf16_begin, int64_t n_bf16, float grad_scale, void* stream);
 
+/* Batch hand-over into the static inputs of a captured training step (engine.py: load_batch / step_prefetched; the
+ * reference feeds a fresh batch per iteration through its DataLoader, src/train/train.py:164-170): n <= 16
+ * device-to-device copies in ONE launch.  `src`, `dst`, `bytes` are HOST arrays of n device pointers / byte counts;
+ * buffers may overlap in nothing; any alignment (16-byte aligned pairs take the vector path). */
+int destr_copy_many(const void* const* src, void* const* dst, const int64_t* bytes, int n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,6 +24,7 @@ _p, _i, _f, _i64, _u = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_uint32
 SIGNATURES = {
     "destr_version": [],
     "destr_debug_knob": [_i, _i],
+    "destr_copy_many": [_p, _p, _p, _i, _p],
     "destr_pack_key_mask": [_p, _p, _i, _i, _i, _p],
     "destr_sine_pos2d": [_p, _p, _p, _i, _i, _i, _p],
     "destr_query_sine_embed": [_p, _p, _p, _i, _p],

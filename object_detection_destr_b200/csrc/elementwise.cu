@@ -350,3 +350,56 @@ extern "C" int destr_dropout_inplace(void* x, int ld, int M, int C, const uint32
   DESTR_LAUNCH_CHECK();
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------------
+// Batch hand-over: up to 16 device-to-device copies in ONE launch.  The engine moves a staged batch (features, mask,
+// selected queries, centres, packed targets: 9 small buffers) into the static inputs of the step graph before every
+// replay; nine back-to-back memcpy nodes cost ~5 us each on the stream the graph replays on.
+// ------------------------------------------------------------------------------------------------------
+namespace destr {
+namespace {
+struct CopyMany {
+  const uint8_t* src[16];
+  uint8_t* dst[16];
+  long long bytes[16];
+  int n;
+};
+__global__ void copy_many_kernel(const CopyMany cm) {
+  for (int k = blockIdx.y; k < cm.n; k += gridDim.y) {
+    const uint8_t* __restrict__ s = cm.src[k];
+    uint8_t* __restrict__ d = cm.dst[k];
+    const long long nb = cm.bytes[k];
+    const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long nth = static_cast<long long>(gridDim.x) * blockDim.x;
+    if (((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d)) & 15) == 0) {
+      const long long n16 = nb >> 4;
+      for (long long i = tid; i < n16; i += nth) reinterpret_cast<uint4*>(d)[i] = reinterpret_cast<const uint4*>(s)[i];
+      for (long long i = (n16 << 4) + tid; i < nb; i += nth) d[i] = s[i];
+    } else {
+      for (long long i = tid; i < nb; i += nth) d[i] = s[i];
+    }
+  }
+}
+}  // namespace
+}  // namespace destr
+
+extern "C" int destr_copy_many(const void* const* src, void* const* dst, const int64_t* bytes, int n, void* stream) {
+  using namespace destr;
+  DESTR_CHECK_ARG(src && dst && bytes && n > 0 && n <= 16, "1..16 buffers (HOST arrays of device pointers / sizes)");
+  CopyMany cm{};
+  long long big = 0;
+  for (int k = 0; k < n; ++k) {
+    DESTR_CHECK_ARG(src[k] && dst[k] && bytes[k] >= 0, "null buffer / negative size");
+    cm.src[k] = static_cast<const uint8_t*>(src[k]);
+    cm.dst[k] = static_cast<uint8_t*>(dst[k]);
+    cm.bytes[k] = bytes[k];
+    big = bytes[k] > big ? bytes[k] : big;
+  }
+  cm.n = n;
+  int bx = static_cast<int>((big / 16 + 255) / 256);
+  bx = bx < 1 ? 1 : (bx > 64 ? 64 : bx);
+  copy_many_kernel<<<dim3(bx, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(cm);
+  DESTR_LAUNCH_CHECK();
+  return 0;
+}
+

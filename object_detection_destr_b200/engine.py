@@ -57,6 +57,33 @@ def set_loss_static(logits, boxes, tl, tb, pi, ti, valid, num_classes: int):
     return {"class": loss_cls, "bbox": (l1 * has).sum() / denom, "ciou": (ciou * has).sum() / denom}
 
 
+class _TargetBlock:
+    """The five target arrays of a batch in ONE byte buffer (pinned host or device), 16-byte aligned segments:
+    [ids int32 B*tm | offs int32 B+1 | pad | boxes fp32 B*tm*4 | padded labels int64 B*tm | padded boxes fp32 B*tm*4].
+    One H2D copy moves them all; the typed views are what the packer writes / the hand-over kernel reads."""
+
+    def __init__(self, B: int, tm: int, device=None):
+        al = lambda n: (n + 15) // 16 * 16
+        o_i, n_i = 0, 4 * (B * tm + B + 1)
+        o_f, n_f = al(n_i), 16 * B * tm
+        o_l, n_l = o_f + al(n_f), 8 * B * tm
+        o_b, n_b = o_l + al(n_l), 16 * B * tm
+        total = o_b + al(n_b)
+        self.buf = torch.empty(total, dtype=torch.uint8, pin_memory=True) if device is None else \
+            torch.empty(total, dtype=torch.uint8, device=device)
+        v = lambda o, n, dt: self.buf[o:o + n].view(dt)
+        self.ints = v(o_i, n_i, torch.int32)                       # ids followed by offsets (the packer's layout)
+        self.ids, self.offs = self.ints[:B * tm], self.ints[B * tm:]
+        self.flt = v(o_f, n_f, torch.float32)
+        self.tboxes = self.flt.view(-1, 4)
+        self.tl = v(o_l, n_l, torch.int64).view(B, tm)
+        self.tb = v(o_b, n_b, torch.float32).view(B, tm, 4)
+
+    def views(self):
+        """In the order of GraphedTrainStep._statics()[4:]."""
+        return [self.ids, self.offs, self.tboxes, self.tl, self.tb]
+
+
 _CAPTURE_STREAMS = {}
 
 
@@ -121,10 +148,9 @@ class GraphedTrainStep:
         self.s_tl, self.s_tb = z(B, t_max, dt=torch.int64) + 1, z(B, t_max, 4)
         self.s_pi, self.s_ti, self.s_valid = z(B, n, dt=torch.int64) + Q, z(B, n, dt=torch.int64), z(B, n, dt=torch.bool)
         self.h_idx = torch.empty(3, B, n, dtype=torch.int64, pin_memory=True)
-        self.h_tgt_i = torch.empty(B * t_max + B + 1, dtype=torch.int32, pin_memory=True)
-        self.h_tgt_f = torch.empty(B * t_max * 4, dtype=torch.float32, pin_memory=True)
-        self.h_tl = torch.empty(B, t_max, dtype=torch.int64, pin_memory=True)
-        self.h_tb = torch.empty(B, t_max, 4, dtype=torch.float32, pin_memory=True)
+        self.h_blk = _TargetBlock(B, t_max)               # pinned: packed by the host
+        self.d_blk = _TargetBlock(B, t_max, device=dev)   # its device copy (one H2D), scattered by the hand-over kernel
+        self.h_tgt_i, self.h_tgt_f, self.h_tl, self.h_tb = self.h_blk.ints, self.h_blk.flt, self.h_blk.tl, self.h_blk.tb
         self.params = [p for p in model.parameters()]
         if world > 1 and getattr(model, "use_runtime", False):
             model.runtime().P.enable_data_parallel(world)  # gradient exchange overlapped with the encoder backward
@@ -243,10 +269,15 @@ class GraphedTrainStep:
             # host rewrites them (a caller looping load_batch()+step() without reading the loss runs ahead of the GPU)
             self._loaded.synchronize()
         self.sizes = self._pack_targets(labels, boxes, self.h_tgt_i, self.h_tgt_f, self.h_tl, self.h_tb)
-        srcs = [feats, mask, sel, centers, self.h_tgt_i[:B * tm], self.h_tgt_i[B * tm:], self.h_tgt_f.view(-1, 4),
-                self.h_tl, self.h_tb]
-        for dst, src in zip(self._statics(), srcs):
-            dst.copy_(src, non_blocking=True)
+        self.d_blk.buf.copy_(self.h_blk.buf, non_blocking=True)  # all five target arrays in one H2D copy
+        dsts = self._statics()
+        srcs = [feats, mask, sel, centers] + self.d_blk.views()
+        on_dev = [k for k, src in enumerate(srcs) if src.is_cuda and src.is_contiguous() and src.dtype == dsts[k].dtype
+                  and src.numel() == dsts[k].numel()]
+        ops.copy_many([dsts[k] for k in on_dev], [srcs[k] for k in on_dev])  # one launch: targets (+ resident inputs)
+        for k, (dst, src) in enumerate(zip(dsts, srcs)):
+            if k not in on_dev:  # host (pinned) inputs, or inputs that need a cast / broadcast
+                dst.copy_(src, non_blocking=True)
         if self._loaded is None:
             self._loaded = torch.cuda.Event()
         self._loaded.record()
@@ -257,24 +288,24 @@ class GraphedTrainStep:
         device staging buffers on a copy stream.  Returns immediately; `step_prefetched()` consumes it."""
         if self._slots is None:
             B, tm = self.B, self.t_max
-            pin = lambda *s, dt: torch.empty(*s, dtype=dt, pin_memory=True)
             self._copy_stream = torch.cuda.Stream(device=self.dev)
-            self._slots = [dict(dev=[torch.empty_like(t) for t in self._statics()],
-                                h_i=pin(B * tm + B + 1, dt=torch.int32), h_f=pin(B * tm * 4, dt=torch.float32),
-                                h_tl=pin(B, tm, dt=torch.int64), h_tb=pin(B, tm, 4, dt=torch.float32),
-                                ready=torch.cuda.Event(), consumed=torch.cuda.Event()) for _ in range(2)]
+            self._slots = []
+            for _ in range(2):
+                hb, db = _TargetBlock(B, tm), _TargetBlock(B, tm, device=self.dev)
+                self._slots.append(dict(dev=[torch.empty_like(t) for t in self._statics()[:4]] + db.views(), hb=hb, db=db,
+                                        ready=torch.cuda.Event(), consumed=torch.cuda.Event()))
             self._slot = 0
         self._slot ^= 1
         st = self._slots[self._slot]
         st["ready"].synchronize()  # this slot's previous H2D copies are done: its pinned arrays may be rewritten
         B, tm = self.B, self.t_max
-        st["sizes"] = self._pack_targets(labels, boxes, st["h_i"], st["h_f"], st["h_tl"], st["h_tb"])
-        srcs = [feats, mask, sel, centers, st["h_i"][:B * tm], st["h_i"][B * tm:], st["h_f"].view(-1, 4), st["h_tl"],
-                st["h_tb"]]
+        hb = st["hb"]
+        st["sizes"] = self._pack_targets(labels, boxes, hb.ints, hb.flt, hb.tl, hb.tb)
         with torch.cuda.stream(self._copy_stream):
             self._copy_stream.wait_event(st["consumed"])  # the step that used this slot has copied it out
-            for dst, src in zip(st["dev"], srcs):
+            for dst, src in zip(st["dev"][:4], (feats, mask, sel, centers)):
                 dst.copy_(src, non_blocking=True)
+            st["db"].buf.copy_(hb.buf, non_blocking=True)  # all five target arrays in one H2D copy
             st["ready"].record(self._copy_stream)
         self._pending = self._slot
 
@@ -284,8 +315,7 @@ class GraphedTrainStep:
         st = self._slots[self._pending]
         main = torch.cuda.current_stream()
         main.wait_event(st["ready"])
-        for dst, src in zip(self._statics(), st["dev"]):
-            dst.copy_(src, non_blocking=True)
+        ops.copy_many(self._statics(), st["dev"])  # one launch instead of nine memcpy nodes in front of the replay
         st["consumed"].record(main)
         self.sizes = st["sizes"]
         return self.step()
@@ -345,6 +375,33 @@ class GraphedTrainStep:
             self._assign()
             self.gB.replay()
         return self.loss
+
+    # ---- result pipelining: read step s's loss / assignment status while step s+1 already runs ----
+    def enqueue_readback(self):
+        """Enqueue the device-to-host read of the LAST step's loss and assignment status (pinned slot, non-blocking)
+        behind it on the current stream and return a token for finish_readback().  A training loop that launches step
+        s+1 before finishing the read of step s keeps the GPU busy across the host's launch latency; the price is that
+        an invalid cost matrix (scipy would raise on NaN / -inf) surfaces one step late."""
+        if getattr(self, "_rb", None) is None:
+            self._rb = [dict(loss=torch.empty(1, dtype=torch.float32, pin_memory=True),
+                             status=torch.empty(self.B, dtype=torch.int32, pin_memory=True), ev=torch.cuda.Event())
+                        for _ in range(4)]
+            self._rb_next = 0
+        k = self._rb_next
+        self._rb_next = (k + 1) % len(self._rb)
+        slot = self._rb[k]
+        slot["loss"].copy_(self.loss.detach().reshape(1).float(), non_blocking=True)
+        slot["status"].copy_(self.s_status, non_blocking=True)
+        slot["ev"].record()
+        return k
+
+    def finish_readback(self, token: int) -> float:
+        """Wait for the read enqueued by enqueue_readback() and return the loss; raises like raise_if_invalid()."""
+        slot = self._rb[token]
+        slot["ev"].synchronize()
+        if self.gpu_lsa and int(slot["status"].max()) != 0:
+            raise ValueError("matrix contains invalid numeric entries")
+        return float(slot["loss"][0])
 
     def raise_if_invalid(self):
         """scipy raises on NaN / -inf costs (identical boxes make the CIoU cost NaN); the device

@@ -29,6 +29,27 @@ def _chk(t: Tensor, dtype, name: str) -> Tensor:
     return t
 
 
+def copy_many(dsts, srcs) -> None:
+    """dst[k].copy_(src[k]) for up to 16 contiguous CUDA tensor pairs of equal byte size in ONE launch (the batch
+    hand-over into a captured step's static inputs, engine.py)."""
+    import ctypes as C
+    n = len(dsts)
+    if n != len(srcs) or not 0 < n <= 16:
+        raise ValueError("copy_many: 1..16 (dst, src) pairs")
+    sizes = []
+    for d, s_ in zip(dsts, srcs):
+        if not (d.is_cuda and s_.is_cuda):
+            raise RuntimeError("copy_many: expected CUDA tensors (destr_b200 has no CPU path)")
+        nb = d.numel() * d.element_size()
+        if nb != s_.numel() * s_.element_size() or d.dtype != s_.dtype or not (d.is_contiguous() and s_.is_contiguous()):
+            raise ValueError("copy_many: pairs must be contiguous, of the same dtype and size")
+        sizes.append(nb)
+    src = (C.c_void_p * n)(*[t.data_ptr() for t in srcs])
+    dst = (C.c_void_p * n)(*[t.data_ptr() for t in dsts])
+    nbytes = (C.c_int64 * n)(*sizes)
+    _lib.call("destr_copy_many", C.cast(src, C.c_void_p), C.cast(dst, C.c_void_p), C.cast(nbytes, C.c_void_p), n, _stream())
+
+
 def _dargs(drop):
     """drop = None | (seed int32/uint32 device tensor [1], thr16, site[, site2]) -> C arguments (seed ptr, thr16, site...)."""
     if drop is None or drop[1] == 0:

@@ -165,3 +165,26 @@ def test_add_layernorm2_fwd_bwd(M, p):
     for got, ref in ((grads[0], p1[2].grad), (grads[1], p1[3].grad), (grads[2], p1[0].grad), (grads[3], p1[1].grad),
                      (grads[4], bf.grad.sum(0))):
         assert torch.allclose(got.cpu(), ref, rtol=3e-2, atol=0.5), float((got.cpu() - ref).abs().max())
+
+
+@pytest.mark.gpu
+def test_copy_many_matches_copy():
+    """destr_copy_many (the engine's batch hand-over): every pair copied bit-exactly, aligned and unaligned, 1 B .. 4 MB."""
+    from object_detection_destr_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    sizes = [1, 36, 6400, 8400, 4300800, 17, 1 << 20, 16, 15, 800 * 512 * 2]
+    base = [torch.randint(0, 256, (n + 64,), generator=g, dtype=torch.uint8).cuda() for n in sizes]
+    srcs = [b[(k % 3):(k % 3) + n] for k, (b, n) in enumerate(zip(base, sizes))]      # some views start off 16-byte alignment
+    dsts = [torch.zeros(n + 32, dtype=torch.uint8, device="cuda")[(k % 5):(k % 5) + n] for k, n in enumerate(sizes)]
+    ops.copy_many(dsts, srcs)
+    torch.cuda.synchronize()
+    for d, s in zip(dsts, srcs):
+        assert torch.equal(d, s)
+    f = torch.randn(8400, 256, generator=g).bfloat16().cuda()
+    out = torch.empty_like(f)
+    ops.copy_many([out], [f])
+    assert torch.equal(out, f)
+    with pytest.raises(ValueError):
+        ops.copy_many([out], [f[:100]])
+    with pytest.raises(RuntimeError):
+        ops.copy_many([out.cpu()], [f.cpu()])
