@@ -25,13 +25,25 @@ eng.capture(warmup=3)
 for _ in range(10):
     eng.step()
 torch.cuda.synchronize()
-best = 1e9
-for rep in range(3):
-    st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    st.record()
-    for _ in range(100):
-        eng.step()
-    en.record()
+from object_detection_destr_b200 import ops
+a8, b8 = torch.zeros(4096, device="cuda"), torch.zeros(4096, device="cuda")
+hp = torch.zeros(4096, pin_memory=True)
+res = tuple(t.cuda() for t in bt[:4]) + (bt[4], bt[5])
+variants = {"replay only": lambda: eng.step(),
+            "tiny kernel + replay": lambda: (ops.copy_many([a8], [b8]), eng.step()),
+            "tiny H2D + replay": lambda: (a8.copy_(hp, non_blocking=True), eng.step()),
+            "load_batch + replay": lambda: (eng.load_batch(*res), eng.step())}
+for name, fn in variants.items():
+    for _ in range(5):
+        fn()
     torch.cuda.synchronize()
-    best = min(best, st.elapsed_time(en) / 100)
-print(f"step {best:.4f} ms  ({B / best * 1e3:.0f} img/s)  kernel nodes {eng.graph_kernel_nodes}", flush=True)
+    best = 1e9
+    for rep in range(3):
+        st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        st.record()
+        for _ in range(100):
+            fn()
+        en.record()
+        torch.cuda.synchronize()
+        best = min(best, st.elapsed_time(en) / 100)
+    print(f"{name:24s} step {best:.4f} ms  ({B / best * 1e3:.0f} img/s)  kernel nodes {eng.graph_kernel_nodes}", flush=True)
