@@ -38,7 +38,8 @@ _FUSED_FFN1 = _os.environ.get("DESTR_FUSED_FFN1", "1") == "1"
 _TC = _os.environ.get("DESTR_TC_GEMM", "1") == "1"
 # the decoder's projections / FFNs / dX products on the same family (M = B*Q = 800 rows)
 # "1": only where an epilogue fusion removes a kernel (ps2 * sine, fc1 + dropout, ReLU-backward + bias gradient);
-# "2": every decoder GEMM (measured slower than the library for the plain 800-row products: 4.69 vs 4.61 ms/step)
+# "2": every decoder GEMM (parity-green, but measured slower than the library for the plain 800-row products:
+#      4.69 vs 4.61 ms/step mid-round, 4.09-4.15 vs 3.99 ms at the end of round 2)
 _TC_DEC_LEVEL = int(_os.environ.get("DESTR_TC_DEC", "1")) if _TC else 0
 _TC_DEC = _TC_DEC_LEVEL >= 1     # fused members
 _TC_DEC_ALL = _TC_DEC_LEVEL >= 2  # plain members too
