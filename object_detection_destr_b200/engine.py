@@ -62,14 +62,14 @@ class _TargetBlock:
     [ids int32 B*tm | offs int32 B+1 | pad | boxes fp32 B*tm*4 | padded labels int64 B*tm | padded boxes fp32 B*tm*4].
     One H2D copy moves them all; the typed views are what the packer writes / the hand-over kernel reads."""
 
-    def __init__(self, B: int, tm: int, device=None):
+    def __init__(self, B: int, tm: int, device=None, pin: bool = True):
         al = lambda n: (n + 15) // 16 * 16
         o_i, n_i = 0, 4 * (B * tm + B + 1)
         o_f, n_f = al(n_i), 16 * B * tm
         o_l, n_l = o_f + al(n_f), 8 * B * tm
         o_b, n_b = o_l + al(n_l), 16 * B * tm
         total = o_b + al(n_b)
-        self.buf = torch.empty(total, dtype=torch.uint8, pin_memory=True) if device is None else \
+        self.buf = torch.empty(total, dtype=torch.uint8, pin_memory=pin) if device is None else \
             torch.empty(total, dtype=torch.uint8, device=device)
         v = lambda o, n, dt: self.buf[o:o + n].view(dt)
         self.ints = v(o_i, n_i, torch.int32)                       # ids followed by offsets (the packer's layout)

@@ -14,7 +14,8 @@ LIB = os.path.join(ROOT, "object_detection_destr_b200", "libdestr_b200.so")
 # kernel name fragment -> SASS mnemonics it must contain
 EXPECT = {
     "enc_attn_fwd_kernel": ("UTCHMMA", "LDTM", "STTM", "UTMALDG"),
-    "enc_attn_bwd_kernel": ("UTCHMMA", "LDTM", "STTM", "UTMALDG", "UBLKCP"),
+    # (UTMAREDG.2D.ADD: the dQ tiles leave through TMA reduce-adds, not per-thread atomics)
+    "enc_attn_bwd_kernel": ("UTCHMMA", "LDTM", "STTM", "UTMALDG", "UBLKCP", "UTMAREDG"),
     "dec_attn_fwd_kernel": ("UTCHMMA", "LDTM", "UTMALDG"),
     "dec_attn_bwd_ds_kernel": ("UTCHMMA", "LDTM", "UTMALDG"),
     "cross_attn_fwd_kernel": ("UTCHMMA", "LDTM", "STTM", "UTMALDG"),
