@@ -7,24 +7,25 @@
 // Work item = one 128-key tile j of one (batch, head); a persistent CTA (one per SM, 608 threads) walks
 // its items and, inside an item, the queries in 64-row sub-tiles u.  Everything is computed TRANSPOSED
 // (rows = keys) so that thread <-> key row <-> TMEM lane:
-//   S^T_u  = K_j . Q_u^T            (SS MMA, N = 64)      -> TMEM ST[g]
-//   dP^T_u = V_j . dO_u^T           (SS MMA, N = 64)      -> TMEM DPT[g]
+//   S^T_u  = K_j . Q_u^T            (SS MMA, N = 64)      -> TMEM ST[u % 3]
+//   dP^T_u = V_j . dO_u^T           (SS MMA, N = 64)      -> TMEM DPT[u % 3]
 //   P^T = exp2(c*S^T - lse_q),  dS^T = P^T o (dP^T - delta_q)          (compute group g = u & 1)
-//   dV_j += P^T_u . dO_u            (TS MMA, A = P^T bf16 in TMEM PT[g], B = dO_u MN-major)
+//   dV_j += P^T_u . dO_u            (TS MMA, A = P^T bf16 in TMEM, in place of S^T; B = dO_u MN-major)
 //   dK_j += dS^T_u . Q_u            (SS MMA, A = dS^T in smem K-major SW128, B = Q_u MN-major)
 //   dQ_p  = dS_p . K_j              once per PAIR p of sub-tiles (M = 128 queries): A = the two dS^T blocks
 //                                   of the pair read MN-major, B = K_j MN-major
 // Two compute groups of 8 warps alternate on the sub-tiles (group g = u & 1).  S^T / dP^T live in THREE TMEM
-// buffers (u % 3): S^T/dP^T of sub-tile u+3 are issued as soon as the gradients of u are, i.e. a whole group
-// iteration before the group that owns u+3 asks for them -- no compute warp ever waits for the
+// buffers (u % 3): the refill with sub-tile u+3 is issued right behind dV(u) by the same thread, i.e. a whole group
+// iteration before the group that owns u+3 asks for it -- no compute warp waits for an
 // arrive -> MMA warp -> tensor pipe -> commit round trip (with two buffers that wait was ~25 % of the warps'
 // time).  P^T (bf16) overwrites the columns of S^T its own warp has already read (in-place, like the
 // forward), which is what pays for the third buffer.  Warp w of a group: TMEM lanes 32*(w%4).., query
-// columns 32*((w/4)%2).. of the sub-tile.
-// dQ_p is pulled out of TMEM one pair later (group p&1, red.global.add.v4.f32 into an fp32 accumulator that a
-// small kernel converts to bf16); dV_j / dK_j are stored right after the first sub-tile of the next item (the
-// next item's first gradient MMA waits for that drain: one bubble per 2*ceil(N/128) sub-tiles); the TMA / MMA
-// warps run ahead across item boundaries.
+// columns 32*((w/4)%2).. of the sub-tile.  Two MMA-issuing warps (see there) share the ~20 small MMAs per sub-tile.
+// dQ_p is pulled out of TMEM one pair later by group p&1: registers -> the warp's own smem tile -> one TMA reduce-add
+// (fp32) per warp into dq_acc, which a small kernel converts to bf16; dV_j / dK_j are stored right after the first
+// sub-tile of the next item (the next item's first gradient MMA waits for that drain: one bubble per
+// 2*ceil(N/128) sub-tiles); the TMA / MMA warps run ahead across item boundaries.
+// Measurements behind this shape: profiles/r02_enc_attn_bwd_knockout.txt (destr_debug_knob 18 = the knock-out bits).
 //
 // TMEM (512 columns): buffer b = u % 3 at 128 b: ST [0,64) DPT [64,128), P^T of the warp owning query columns
 //                     32 cg.. in ST columns [32 cg, 32 cg + 16);  DV [384,416) DK [416,448) DQ0 [448,480) DQ1 [480,512)
