@@ -18,6 +18,8 @@
 //     registers, which is what lets 640 threads/SM fit the register file.
 //   * S is double buffered (Q.K_{j+1}^T runs under softmax(S_j)); packed fp32x2 FMA/ADD, 3-input max;
 //     a knob moves a fraction of the exps from MUFU to an FMA-pipe polynomial (ex2_poly_f32x2).
+//   * the softmax reads its 48 scores twice, 16 at a time (max, then exp): TMEM reads are cheap and the live set stays
+//     small enough for 96 registers (holding all 48 made the dropout variant spill around its mask-word prefetch).
 //   warp 8 TMA producer (Q double buffered; K_j / V_j through a KSTAGES ring), warp 9 tcgen05.mma issuer.
 // TMEM (256 columns per CTA): S0 [0,96) S1 [96,192) O_a [192,224) O_b [224,256).  P (bf16) overwrites
 // the first 24 columns of each half's own S region and is the A operand of P.V straight from TMEM.
@@ -34,6 +36,8 @@ namespace destr {
 // 6-8 enc_attn_bwd descriptors, 9 enc fwd polynomial-exp quarter count (0..3), 10 enc bwd ditto,
 // 11 lazy-rescale tau+1, 12/13 grid overrides, 14 enc bwd: launch the main kernel only (bench timing)
 // 15 gemm_dw split override, 16 programmatic dependent launch: -1 = DESTR_PDL from the environment, 0 off, 1 on
+// 17 gemm tile width: 1 / 2 force 128 / 256, 18 enc bwd knock-out bits, 19 enc fwd knock-out bits (timing experiments:
+// tools/dbg_enc_attn_bwd.py, tools/dbg_enc_attn_fwd.py; results are meaningless with a bit set)
 int g_knobs[24] = {512, 512, 16, 512, 8, 1024, 16384, 1024, 2048, 1, 0, 0, 0, 0, 0, 0, -1, 0, 0, 0, 0, 0, 0, 0};
 
 namespace {
