@@ -430,25 +430,44 @@ __global__ void dec_qkv_prep_bwd_kernel(const __nv_bfloat16* __restrict__ d_qkv,
       acc[w][2 * e + 1] = __uint_as_float(uw[e] & 0xffff0000u);
     }
   }
-  for (int ip = 0; ip < Q; ++ip) {
-    const int L = sp[2 * ip], R = sp[2 * ip + 1];
-    if (L != i && R != i) continue;
+  // Which (i', side) gather from this row: key k = 2 i' + side matches iff sp[k] == i.  Warp 0 compacts the matching
+  // keys in ASCENDING order with ballots (7 rounds at Q = 100) instead of every thread scanning all Q pairs -- the
+  // scan was most of this kernel's time -- and everybody then adds the few (two on average) matches in that order,
+  // i.e. in the order of the sequential scan: same rounding, still no atomics.
+  __shared__ int32_t hits[256];  // (more than 256 gathers into one row: the tail is handled by the scan below)
+  __shared__ int32_t n_hits;
+  if (t < 32) {
+    int n = 0;
+    for (int base = 0; base < 2 * Q; base += 32) {
+      const int k = base + t;
+      const unsigned m = __ballot_sync(0xffffffffu, k < 2 * Q && sp[k] == i);
+      if (m & (1u << t)) {
+        const int pos = n + __popc(m & ((1u << t) - 1u));
+        if (pos < 256) hits[pos] = k;
+      }
+      n += __popc(m);
+    }
+    if (t == 0) n_hits = n;
+  }
+  __syncthreads();
+  const int nh = n_hits;
+  auto gather = [&](int k) {
+    const int ip = k >> 1, side = k & 1;
 #pragma unroll
-    for (int side = 0; side < 2; ++side) {
-      if ((side == 0 ? L : R) != i) continue;
+    for (int w = 0; w < 3; ++w) {
+      const uint4 u = *reinterpret_cast<const uint4*>(d_cat + w * cat_stride + (hm_base + ip) * 128 + side * 64 + within);
+      const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-      for (int w = 0; w < 3; ++w) {
-        const uint4 u =
-            *reinterpret_cast<const uint4*>(d_cat + w * cat_stride + (hm_base + ip) * 128 + side * 64 + within);
-        const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          acc[w][2 * e] += __uint_as_float(uw[e] << 16);
-          acc[w][2 * e + 1] += __uint_as_float(uw[e] & 0xffff0000u);
-        }
+      for (int e = 0; e < 4; ++e) {
+        acc[w][2 * e] += __uint_as_float(uw[e] << 16);
+        acc[w][2 * e + 1] += __uint_as_float(uw[e] & 0xffff0000u);
       }
     }
-  }
+  };
+  for (int h = 0; h < (nh < 256 ? nh : 256); ++h) gather(hits[h]);
+  if (nh > 256)  // (degenerate pairing: keep the order, scan for the rest)
+    for (int k = hits[255] + 1; k < 2 * Q; ++k)
+      if (sp[k] == i) gather(k);
 #pragma unroll
   for (int w = 0; w < 3; ++w) {
     uint32_t o[4];
