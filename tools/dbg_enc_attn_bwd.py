@@ -1,5 +1,8 @@
+"""Knock-out timings of the encoder attention backward main kernel (destr_debug_knob(18, bits), see enc_attn_bwd.cu:
+1 no dV, 2 no dK, 4 no dQ, 8 no softmax-backward math, 16 no S/dP, 32 no dQ reduction, 64 no dK/dV stores, 128 no Q/dO
+loads; results are meaningless with a bit set, only the time is read).  profiles/r02_enc_attn_bwd_knockout.txt."""
 import math, os, sys
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tools")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
 from object_detection_destr_b200 import ops, _lib
 B, N = 8, 1050

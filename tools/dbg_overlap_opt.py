@@ -1,6 +1,6 @@
 """Diagnostic for tests/test_gpu_engine.py::test_overlapped_optimizer_step_equals_plain_step: parameter differences
 between repeated runs of the overlapped (T) and plain (F) optimizer paths after 3 steps (EPS env: Adam eps)."""
-import sys; sys.path.insert(0, "/root/repo")
+import os, sys; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from argparse import Namespace
 import torch, bench
 from object_detection_destr_b200.encoder import disable_dropout

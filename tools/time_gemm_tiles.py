@@ -1,6 +1,7 @@
 import sys, torch
-sys.path.insert(0, "/root/repo")
-sys.path.insert(0, "/root/repo/tools")
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from object_detection_destr_b200 import ops, _lib
 import time_gemm as T
 BF = torch.bfloat16
